@@ -1,0 +1,112 @@
+/*
+ * lisflood_b200.h -- C ABI of liblisf_b200.so, the B200 (sm_100a) implementation of LISFLOOD's
+ * raster time-step hot path (kinematic-wave routing + per-cell soil / surface-runoff updates).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy types.  The Python host
+ * layer (lisflood_code_b200/) binds it with ctypes and mirrors the reference's operator API on top;
+ * INTEGRATION.md shows the stub a LISFLOOD maintainer would add.
+ *
+ * Conventions
+ *   - every function returns LF_OK (0) or a negative LF_ERR_* code; lf_last_error() returns a
+ *     thread-local description of the last failure.  No C++ exception crosses the ABI.
+ *   - opaque handles own device memory; host pointers are borrowed for the duration of a call.
+ *   - thread-compatible, not thread-safe (the reference drives everything from one Python thread).
+ *   - all floating point is IEEE float64; "compressed" arrays are the reference's 1-D arrays of
+ *     active pixels in row-major order of the mask (global_modules/add1.py:268-282).
+ *   - reference citations are relative to /root/reference/src/lisflood/.
+ */
+#ifndef LISFLOOD_B200_H
+#define LISFLOOD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LF_OK 0
+#define LF_ERR_INVALID (-1)   /* bad argument (null pointer, size, section ...) */
+#define LF_ERR_BAD_LDD (-2)   /* an LDD code outside 0..9 */
+#define LF_ERR_LDD_CYCLE (-3) /* the LDD contains a cycle (the reference would loop forever,
+                                 hydrological_modules/kinematic_wave_parallel.py:99) */
+#define LF_ERR_CUDA (-4)      /* CUDA runtime failure, text in lf_last_error() */
+#define LF_ERR_NO_DEVICE (-5) /* no sm_100 device: there is NO CPU fallback */
+#define LF_ERR_STATE (-6)     /* call order violated (e.g. floodplain section without alpha_fp) */
+
+#define LF_SECTION_MAIN 0       /* section="main_channel" */
+#define LF_SECTION_FLOODPLAIN 1 /* section="floodplains"  */
+
+typedef struct lf_graph lf_graph;   /* D8 drainage graph + routing order, device resident */
+typedef struct lf_router lf_router; /* one kinematicWave object */
+typedef struct lf_soil lf_soil;     /* fused per-cell soil / runoff state + parameters */
+typedef struct lf_model lf_model;   /* full hot-path step: soil -> overland -> channel sub-steps */
+
+const char *lf_last_error(void);
+int lf_version(void);
+
+/* Selects the CUDA device (default 0) and verifies it is compute capability 10.x.
+ * Every other entry point fails with LF_ERR_NO_DEVICE when there is no such device. */
+int lf_device_init(int device);
+/* name: >= 128 bytes.  Any out pointer may be NULL. */
+int lf_device_info(char *name, int *sm_count, int *cc_major, int *cc_minor, int64_t *hbm_bytes);
+/* Blocks until all work queued by this library on its stream has finished. */
+int lf_synchronize(void);
+/* Device-side stopwatch on the library's stream (CUDA events). */
+int lf_timer_start(void);
+int lf_timer_stop(double *elapsed_ms);
+/* Counts kernels launched by this library since the last reset (bench.py's gpu_launches). */
+int64_t lf_launch_count(int reset);
+/* Page-locks / unlocks a host buffer the caller will pass repeatedly (faster H2D/D2H). */
+int lf_host_register(void *ptr, int64_t bytes);
+int lf_host_unregister(void *ptr);
+
+/* ---------------------------------------------------------------------------------------------
+ * Drainage graph.  Replaces kinematicWave.__init__'s graph part:
+ *   rebuildFlowMatrix/decodeFlowMatrix  hydrological_modules/kinematic_wave_parallel.py:59-71
+ *   streamLookups + upDownLookups       :73-90, kinematic_wave_parallel_tools.py:111-130
+ *   topoDistFromSea + _setRoutingOrders :92-106, :140-158
+ * ldd_codes: f64[N] compressed keypad codes (1-9, 5 and 0 = pit); land_mask: u8[rows*cols], 1 =
+ * active pixel, N = number of ones.  The exported arrays are bit-identical to the reference's.
+ * ------------------------------------------------------------------------------------------- */
+int lf_ldd_build(const double *ldd_codes, const uint8_t *land_mask, int64_t rows, int64_t cols, lf_graph **out);
+int lf_graph_info(const lf_graph *g, int64_t *n_pixels, int64_t *n_orders, int64_t *max_upstream,
+                  int64_t *n_pits);
+/* Any pointer may be NULL.  pixels_ordered i64[N]; order_start_stop i64[n_orders*2];
+ * upstream_lookup i64[N*max_upstream] (-1 fill); num_upstream i64[N]; downstream f64[N] (-1 = none). */
+int lf_graph_export(const lf_graph *g, int64_t *pixels_ordered, int64_t *order_start_stop,
+                    int64_t *upstream_lookup, int64_t *num_upstream, double *downstream);
+/* Internal storage order ("position" = breadth-first layout from the outlets):
+ * pixel_of_position i32[N], level_start i32[n_orders+1].  For tests / diagnostics. */
+int lf_graph_layout(const lf_graph *g, int32_t *pixel_of_position, int32_t *level_start);
+void lf_graph_destroy(lf_graph *g);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kinematic-wave router.  Replaces class kinematicWave
+ * (hydrological_modules/kinematic_wave_parallel.py:114-184) and the Numba kernels
+ * kinematicRouting / solve1Pixel / closureError (kinematic_wave_parallel_tools.py:34-92).
+ * alpha f64[N]; dx f64[N] or NULL (then dx_scalar); alpha_floodplains f64[N] or NULL.
+ * The graph must outlive the router.
+ * ------------------------------------------------------------------------------------------- */
+int lf_router_create(lf_graph *g, const double *alpha, double beta, const double *dx, double dx_scalar,
+                     double dt, const double *alpha_floodplains, int flagnancheck, lf_router **out);
+/* kinematicWaveRouting(discharge, specific_lateral_inflow, section): host f64[N] in compressed
+ * order; discharge is updated IN PLACE (H2D, solve, D2H inside the call).
+ * nonfinite (may be NULL) receives 1 when flagnancheck is set and a NaN/Inf was produced
+ * (the reference warns once, it does not fail: kinematic_wave_parallel.py:180-184). */
+int lf_router_route(lf_router *r, double *discharge, const double *specific_lateral_inflow, int section,
+                    int *nonfinite);
+
+/* Device-resident variant: state stays in HBM between calls. */
+int lf_router_set_discharge(lf_router *r, int section, const double *discharge);
+int lf_router_get_discharge(lf_router *r, int section, double *discharge);
+int lf_router_set_inflow(lf_router *r, int section, const double *specific_lateral_inflow);
+/* Runs nsteps consecutive kinematicWaveRouting calls on the resident state as ONE space-time
+ * wavefront: step s uses lateral inflow q * q_scale[s] (q_scale NULL = all ones;
+ * host f64[nsteps]).  Same arithmetic per (pixel, step) as nsteps calls of lf_router_route. */
+int lf_router_run(lf_router *r, int section, int nsteps, const double *q_scale, int *nonfinite);
+void lf_router_destroy(lf_router *r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LISFLOOD_B200_H */

@@ -1,0 +1,122 @@
+"""ctypes binding of liblisf_b200.so (C ABI: include/lisflood_b200.h).
+
+The library is loaded on first use.  A missing library is a hard error -- the product path never
+falls back to a CPU implementation.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "liblisf_b200.so")
+
+LF_OK = 0
+LF_ERR_INVALID, LF_ERR_BAD_LDD, LF_ERR_LDD_CYCLE, LF_ERR_CUDA, LF_ERR_NO_DEVICE, LF_ERR_STATE = -1, -2, -3, -4, -5, -6
+SECTION = {"main_channel": 0, "floodplains": 1}
+
+
+class LisfloodB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("liblisf_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+_f64 = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i64 = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+_i64s = C.c_int64
+
+# name -> (restype, argtypes); must list every function declared in include/lisflood_b200.h
+SIGNATURES = {
+    "lf_last_error": (C.c_char_p, []),
+    "lf_version": (C.c_int, []),
+    "lf_device_init": (C.c_int, [C.c_int]),
+    "lf_device_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int64)]),
+    "lf_synchronize": (C.c_int, []),
+    "lf_timer_start": (C.c_int, []),
+    "lf_timer_stop": (C.c_int, [C.POINTER(C.c_double)]),
+    "lf_launch_count": (C.c_int64, [C.c_int]),
+    "lf_host_register": (C.c_int, [_vp, _i64s]),
+    "lf_host_unregister": (C.c_int, [_vp]),
+    "lf_ldd_build": (C.c_int, [_f64, _u8, _i64s, _i64s, C.POINTER(_vp)]),
+    "lf_graph_info": (C.c_int, [_vp, C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s)]),
+    "lf_graph_export": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "lf_graph_layout": (C.c_int, [_vp, _vp, _vp]),
+    "lf_graph_destroy": (None, [_vp]),
+    "lf_router_create": (C.c_int, [_vp, _f64, C.c_double, _vp, C.c_double, C.c_double, _vp, C.c_int,
+                                   C.POINTER(_vp)]),
+    "lf_router_route": (C.c_int, [_vp, _f64, _f64, C.c_int, C.POINTER(C.c_int)]),
+    "lf_router_set_discharge": (C.c_int, [_vp, C.c_int, _f64]),
+    "lf_router_get_discharge": (C.c_int, [_vp, C.c_int, _f64]),
+    "lf_router_set_inflow": (C.c_int, [_vp, C.c_int, _f64]),
+    "lf_router_run": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
+    "lf_router_destroy": (None, [_vp]),
+}
+
+_lib = None
+
+
+def build(force=False):
+    """Compiles liblisf_b200.so in-tree with nvcc for sm_100a (no GPU needed)."""
+    args = ["make", "-s", "-C", CSRC, "-j4"]
+    if force:
+        args.append("-B")
+    subprocess.check_call(args, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LisfloodB200Error(LF_ERR_NO_DEVICE,
+                                    "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                                    " (there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != LF_OK:
+        raise LisfloodB200Error(rc, lib().lf_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def device_info():
+    L = lib()
+    name = C.create_string_buffer(128)
+    sms, maj, mnr, mem = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    check(L.lf_device_info(name, C.byref(sms), C.byref(maj), C.byref(mnr), C.byref(mem)))
+    return {"name": name.value.decode(), "sm_count": sms.value, "cc": (maj.value, mnr.value), "hbm_bytes": mem.value}
+
+
+def synchronize():
+    check(lib().lf_synchronize())
+
+
+def timer_start():
+    check(lib().lf_timer_start())
+
+
+def timer_stop():
+    ms = C.c_double()
+    check(lib().lf_timer_stop(C.byref(ms)))
+    return ms.value
+
+
+def launch_count(reset=False):
+    return int(lib().lf_launch_count(1 if reset else 0))

@@ -1,0 +1,98 @@
+// lf_common.cuh -- shared plumbing for liblisf_b200.so (error reporting, stream, handles).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/lisflood_b200.h"
+
+namespace lf {
+
+void set_error(const char *fmt, ...);
+cudaStream_t stream();
+int ensure_device();  // LF_OK or LF_ERR_NO_DEVICE / LF_ERR_CUDA
+void count_launch(int64_t n = 1);
+int sm_count();
+
+#define LF_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            lf::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));   \
+            return LF_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define LF_CHECK(expr)                 \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != LF_OK) return _rc;  \
+    } while (0)
+
+#define LF_LAUNCH_CHECK()                                                                          \
+    do {                                                                                           \
+        lf::count_launch();                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess) {                                                                   \
+            lf::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return LF_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+// Owning device buffer (freed with the handle).
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu bytes) -> %s", count * sizeof(T), cudaGetErrorString(e));
+            return LF_ERR_CUDA;
+        }
+        n = count;
+        return LF_OK;
+    }
+};
+
+inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace lf
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct lf_graph {
+    int64_t rows = 0, cols = 0, n = 0;
+    int32_t n_orders = 0, max_ups = 1;
+    int64_t n_pits = 0;
+    // raster-order members (kept for export and for building routers)
+    lf::DevBuf<uint8_t> dir2d;        // [rows*cols] 0..7 direction, 8 pit, 9 off-mask
+    lf::DevBuf<int32_t> land_points;  // [rows*cols] compressed index or -1
+    lf::DevBuf<int32_t> cell_of_pix;  // [n] linear cell index
+    lf::DevBuf<int32_t> downstream;   // [n] pixel index or -1
+    lf::DevBuf<uint8_t> nups_pix;     // [n]
+    lf::DevBuf<int32_t> level_pix;    // [n] routing order of the pixel
+    lf::DevBuf<int32_t> pixels_ordered;  // [n] reference order: sorted by (order, pixel)
+    // internal breadth-first layout ("positions")
+    lf::DevBuf<int32_t> pix_of_pos;   // [n]
+    lf::DevBuf<int32_t> pos_of_pix;   // [n]
+    lf::DevBuf<int32_t> cfirst;       // [n+1] children of position i are positions cfirst[i]..cfirst[i+1]-1
+    lf::DevBuf<int32_t> lev_of_pos;   // [n]
+    lf::DevBuf<int32_t> level_start;  // [n_orders+1] (device copy)
+    std::vector<int32_t> h_level_start;  // host copy
+};

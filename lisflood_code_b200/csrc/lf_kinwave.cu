@@ -1,0 +1,322 @@
+// lf_kinwave.cu -- kinematic-wave router: class kinematicWave of the reference
+// (hydrological_modules/kinematic_wave_parallel.py:114-184) on device-resident state.
+//
+// Storage: every per-pixel array lives in the graph's breadth-first "position" order
+// (lf_graph.cu step 7).  In that order
+//   * routing level l is the contiguous span [level_start[l], level_start[l+1]),
+//   * the upstream pixels of position i are the contiguous positions cfirst[i]..cfirst[i+1]-1 of
+//     level l-1, already in the reference's slot order -- the gather is a short contiguous read,
+//   * every link goes from level l to level l+1, so the work item (level l, step s) depends only
+//     on (l-1, s) and (l, s-1).  All items with l + s = d are independent: a run of S routing steps
+//     is executed as L+S-1 "diagonal" launches instead of L*S level launches, each over ONE
+//     contiguous span of positions (the levels d-S+1..d), with discharge double-buffered by step
+//     parity.  S = 1 degenerates to the reference's level-by-level sweep.
+#include "lf_common.cuh"
+#include "lf_kw_solve.cuh"
+
+struct lf_router {
+    lf_graph *g = nullptr;
+    int64_t n = 0;
+    lfkw::Params P;
+    double dt = 0, dx_scalar = 0;
+    bool dx_is_array = false, has_fp = false;
+    int nancheck = 0;
+    lf::DevBuf<double> a[2];     // a_dx_div_dt per section            [position order]
+    lf::DevBuf<double> dx;       // space_delta if it is a map         [position order]
+    lf::DevBuf<double> Q[2][2];  // per section: ping-pong discharge   [position order]
+    lf::DevBuf<double> q[2];     // specific lateral inflow            [position order]
+    int64_t steps_done[2] = {0, 0};
+    lf::DevBuf<double> stage_a, stage_b;  // compressed (user) order staging
+    lf::DevBuf<double> scale;
+    lf::DevBuf<int> flag;
+};
+
+namespace {
+
+// to position order: dst[i] = src[pix_of_pos[i]]
+__global__ void k_to_pos(const double *__restrict__ src, double *__restrict__ dst,
+                         const int32_t *__restrict__ pix_of_pos, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[pix_of_pos[i]];
+}
+// alpha -> a_dx_div_dt = alpha * dx / dt   (kinematic_wave_parallel.py:126)
+__global__ void k_make_a(const double *__restrict__ alpha, const double *__restrict__ dx, double dx_scalar,
+                         double dt, double *__restrict__ a, double *__restrict__ dx_pos,
+                         const int32_t *__restrict__ pix_of_pos, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = pix_of_pos[i];
+    double d = dx ? dx[p] : dx_scalar;
+    a[i] = alpha[p] * d / dt;
+    if (dx_pos) dx_pos[i] = d;
+}
+// back to compressed order: dst[p] = src[pos_of_pix[p]]
+__global__ void k_to_pix(const double *__restrict__ src, double *__restrict__ dst,
+                         const int32_t *__restrict__ pos_of_pix, int64_t n)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) dst[p] = src[pos_of_pix[p]];
+}
+__global__ void k_nonfinite(const double *__restrict__ v, int64_t n, int *__restrict__ flag)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !isfinite(v[i])) *flag = 1;
+}
+
+// One diagonal of the space-time wavefront.  Positions [lo, hi) = levels d-S+1..d.
+constexpr int KW_THREADS = 128;
+__global__ void __launch_bounds__(KW_THREADS)
+    k_kw_diagonal(int lo, int hi, int d, int64_t g0, const int32_t *__restrict__ lev,
+                  const int32_t *__restrict__ cfirst, const double *__restrict__ a, const double *__restrict__ dx,
+                  double dx_scalar, const double *__restrict__ q, const double *__restrict__ scale, double *Q0,
+                  double *Q1, lfkw::Params P)
+{
+    int i = lo + blockIdx.x * KW_THREADS + threadIdx.x;
+    if (i >= hi) return;
+    int s = d - lev[i];
+    int64_t gs = g0 + s;  // global index of this routing step; parity selects the buffer
+    double *Qnew = (gs & 1) ? Q1 : Q0;
+    const double *Qold = (gs & 1) ? Q0 : Q1;
+    int c0 = cfirst[i], c1 = cfirst[i + 1];
+    double qo = Qold[i];
+    double qs = q[i];
+    if (scale) qs *= scale[s];
+    double lateral = qs * (dx ? dx[i] : dx_scalar);  // lateral_inflow = q * dx, kinematic_wave_parallel.py:163
+    double ai = a[i];
+    double U = 0.0;
+    for (int k = c0; k < c1; ++k) U += Qnew[k];  // upstream discharge of this step, slot order (tools:57-58)
+    Qnew[i] = lfkw::solve(U, qo, lateral, ai, P);
+}
+
+int run_steps(lf_router *r, int sec, int nsteps, const double *d_scale)
+{
+    lf_graph *g = r->g;
+    cudaStream_t st = lf::stream();
+    const std::vector<int32_t> &ls = g->h_level_start;
+    int L = g->n_orders;
+    int64_t g0 = r->steps_done[sec];
+    for (int d = 0; d < L + nsteps - 1; ++d) {
+        int lo_lev = d - nsteps + 1 > 0 ? d - nsteps + 1 : 0;
+        int hi_lev = d < L - 1 ? d : L - 1;
+        int lo = ls[lo_lev], hi = ls[hi_lev + 1];
+        k_kw_diagonal<<<lf::blocks_for(hi - lo, KW_THREADS), KW_THREADS, 0, st>>>(
+            lo, hi, d, g0, g->lev_of_pos.p, g->cfirst.p, r->a[sec].p, r->dx_is_array ? r->dx.p : nullptr, r->dx_scalar,
+            r->q[sec].p, d_scale, r->Q[sec][0].p, r->Q[sec][1].p, r->P);
+        LF_LAUNCH_CHECK();
+    }
+    r->steps_done[sec] = g0 + nsteps;
+    return LF_OK;
+}
+
+inline double *current_q(lf_router *r, int sec) { return r->Q[sec][(r->steps_done[sec] + 1) & 1].p; }
+
+int check_section(lf_router *r, int section, const char *fn)
+{
+    if (!r) {
+        lf::set_error("%s: null router", fn);
+        return LF_ERR_INVALID;
+    }
+    if (section != LF_SECTION_MAIN && section != LF_SECTION_FLOODPLAIN) {
+        // the reference raises Exception("The section parameter must be either 'main_channel' or 'floodplain'!")
+        lf::set_error("%s: the section parameter must be either 'main_channel' or 'floodplain'", fn);
+        return LF_ERR_INVALID;
+    }
+    if (section == LF_SECTION_FLOODPLAIN && !r->has_fp) {
+        lf::set_error("%s: router was created without alpha_floodplains", fn);
+        return LF_ERR_STATE;
+    }
+    return LF_OK;
+}
+
+int nan_check(lf_router *r, int sec, int *nonfinite)
+{
+    if (nonfinite) *nonfinite = 0;
+    if (!r->nancheck) return LF_OK;
+    cudaStream_t st = lf::stream();
+    LF_CUDA(cudaMemsetAsync(r->flag.p, 0, sizeof(int), st));
+    k_nonfinite<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(current_q(r, sec), r->n, r->flag.p);
+    LF_LAUNCH_CHECK();
+    int h = 0;
+    LF_CUDA(cudaMemcpyAsync(&h, r->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaStreamSynchronize(st));
+    if (nonfinite) *nonfinite = h;
+    return LF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lf_router_create(lf_graph *g, const double *alpha, double beta, const double *dx, double dx_scalar, double dt,
+                     const double *alpha_floodplains, int flagnancheck, lf_router **out)
+{
+    if (!g || !alpha || !out) {
+        lf::set_error("lf_router_create: null graph / alpha / out");
+        return LF_ERR_INVALID;
+    }
+    if (!(dt > 0) || !(beta > 0)) {
+        lf::set_error("lf_router_create: beta and time_delta must be positive");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    lf_router *r = new lf_router();
+    *out = nullptr;
+    r->g = g;
+    r->n = g->n;
+    r->P.beta = beta;
+    r->P.inv_beta = 1 / beta;   // kinematic_wave_parallel.py:124
+    r->P.b_minus_1 = beta - 1;  // :125
+    r->dt = dt;
+    r->dx_scalar = dx_scalar;
+    r->dx_is_array = dx != nullptr;
+    r->has_fp = alpha_floodplains != nullptr;
+    r->nancheck = flagnancheck;
+    int64_t n = r->n;
+    int rc = LF_OK;
+    auto fail = [&](int code) {
+        delete r;
+        return code;
+    };
+    if ((rc = r->stage_a.alloc(n)) || (rc = r->stage_b.alloc(n)) || (rc = r->flag.alloc(1))) return fail(rc);
+    if (r->dx_is_array && (rc = r->dx.alloc(n))) return fail(rc);
+    int nsec = r->has_fp ? 2 : 1;
+    for (int s = 0; s < nsec; ++s) {
+        if ((rc = r->a[s].alloc(n)) || (rc = r->Q[s][0].alloc(n)) || (rc = r->Q[s][1].alloc(n)) ||
+            (rc = r->q[s].alloc(n)))
+            return fail(rc);
+        cudaMemsetAsync(r->Q[s][0].p, 0, n * sizeof(double), st);
+        cudaMemsetAsync(r->Q[s][1].p, 0, n * sizeof(double), st);
+        cudaMemsetAsync(r->q[s].p, 0, n * sizeof(double), st);
+    }
+    if (r->dx_is_array) {
+        cudaError_t e = cudaMemcpyAsync(r->stage_b.p, dx, n * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) {
+            lf::set_error("lf_router_create: copy of space_delta failed: %s", cudaGetErrorString(e));
+            return fail(LF_ERR_CUDA);
+        }
+    }
+    for (int s = 0; s < nsec; ++s) {
+        const double *al = s == 0 ? alpha : alpha_floodplains;
+        cudaError_t e = cudaMemcpyAsync(r->stage_a.p, al, n * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) {
+            lf::set_error("lf_router_create: copy of alpha failed: %s", cudaGetErrorString(e));
+            return fail(LF_ERR_CUDA);
+        }
+        k_make_a<<<lf::blocks_for(n, 256), 256, 0, st>>>(r->stage_a.p, r->dx_is_array ? r->stage_b.p : nullptr,
+                                                         dx_scalar, dt, r->a[s].p,
+                                                         (s == 0 && r->dx_is_array) ? r->dx.p : nullptr,
+                                                         g->pix_of_pos.p, n);
+        lf::count_launch();
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        lf::set_error("lf_router_create: %s", cudaGetErrorString(e));
+        return fail(LF_ERR_CUDA);
+    }
+    *out = r;
+    return LF_OK;
+}
+
+int lf_router_set_discharge(lf_router *r, int section, const double *discharge)
+{
+    LF_CHECK(check_section(r, section, "lf_router_set_discharge"));
+    if (!discharge) {
+        lf::set_error("lf_router_set_discharge: null pointer");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    LF_CUDA(cudaMemcpyAsync(r->stage_a.p, discharge, r->n * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_to_pos<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(r->stage_a.p, current_q(r, section), r->g->pix_of_pos.p, r->n);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaStreamSynchronize(st));
+    return LF_OK;
+}
+
+int lf_router_get_discharge(lf_router *r, int section, double *discharge)
+{
+    LF_CHECK(check_section(r, section, "lf_router_get_discharge"));
+    if (!discharge) {
+        lf::set_error("lf_router_get_discharge: null pointer");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    k_to_pix<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(current_q(r, section), r->stage_a.p, r->g->pos_of_pix.p, r->n);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaMemcpyAsync(discharge, r->stage_a.p, r->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaStreamSynchronize(st));
+    return LF_OK;
+}
+
+int lf_router_set_inflow(lf_router *r, int section, const double *specific_lateral_inflow)
+{
+    LF_CHECK(check_section(r, section, "lf_router_set_inflow"));
+    if (!specific_lateral_inflow) {
+        lf::set_error("lf_router_set_inflow: null pointer");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    LF_CUDA(cudaMemcpyAsync(r->stage_b.p, specific_lateral_inflow, r->n * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_to_pos<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(r->stage_b.p, r->q[section].p, r->g->pix_of_pos.p, r->n);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaStreamSynchronize(st));
+    return LF_OK;
+}
+
+int lf_router_run(lf_router *r, int section, int nsteps, const double *q_scale, int *nonfinite)
+{
+    LF_CHECK(check_section(r, section, "lf_router_run"));
+    if (nsteps < 0) {
+        lf::set_error("lf_router_run: nsteps must be >= 0");
+        return LF_ERR_INVALID;
+    }
+    if (nonfinite) *nonfinite = 0;
+    if (nsteps == 0) return LF_OK;
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    const double *d_scale = nullptr;
+    if (q_scale) {
+        if (r->scale.n < (size_t)nsteps) LF_CHECK(r->scale.alloc(nsteps));
+        LF_CUDA(cudaMemcpyAsync(r->scale.p, q_scale, nsteps * sizeof(double), cudaMemcpyHostToDevice, st));
+        d_scale = r->scale.p;
+    }
+    LF_CHECK(run_steps(r, section, nsteps, d_scale));
+    LF_CHECK(nan_check(r, section, nonfinite));
+    if (q_scale) LF_CUDA(cudaStreamSynchronize(st));  // q_scale is borrowed only for the duration of the call
+    return LF_OK;
+}
+
+int lf_router_route(lf_router *r, double *discharge, const double *specific_lateral_inflow, int section,
+                    int *nonfinite)
+{
+    LF_CHECK(check_section(r, section, "lf_router_route"));
+    if (!discharge || !specific_lateral_inflow) {
+        lf::set_error("lf_router_route: null pointer");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    int64_t n = r->n;
+    LF_CUDA(cudaMemcpyAsync(r->stage_a.p, discharge, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    LF_CUDA(cudaMemcpyAsync(r->stage_b.p, specific_lateral_inflow, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_to_pos<<<lf::blocks_for(n, 256), 256, 0, st>>>(r->stage_a.p, current_q(r, section), r->g->pix_of_pos.p, n);
+    LF_LAUNCH_CHECK();
+    k_to_pos<<<lf::blocks_for(n, 256), 256, 0, st>>>(r->stage_b.p, r->q[section].p, r->g->pix_of_pos.p, n);
+    LF_LAUNCH_CHECK();
+    LF_CHECK(run_steps(r, section, 1, nullptr));
+    k_to_pix<<<lf::blocks_for(n, 256), 256, 0, st>>>(current_q(r, section), r->stage_a.p, r->g->pos_of_pix.p, n);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaMemcpyAsync(discharge, r->stage_a.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LF_CHECK(nan_check(r, section, nonfinite));
+    LF_CUDA(cudaStreamSynchronize(st));
+    return LF_OK;
+}
+
+void lf_router_destroy(lf_router *r) { delete r; }
+
+}  // extern "C"

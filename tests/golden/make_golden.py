@@ -1,0 +1,80 @@
+"""Generates the committed golden vectors by running the UNMODIFIED reference kernels
+(/root/reference, imported through oracle/ref_loader.py).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The .npz files next to this script are what the CPU tests (oracle pin) and the GPU parity tests
+compare against; /root/reference is never needed at test time.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
+
+from lisflood_code_b200 import synthetic  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+
+def routing_case(kwp, name, rows, cols, seed, noise, mask_fraction, dx_array, steps, split, beta=0.6, dt=3600.0,
+                 negative_q=False, ldd=None, mask=None, alpha=None, q0=None, q=None, dx=None):
+    if ldd is None:
+        ldd, mask = synthetic.random_ldd(rows, cols, seed=seed, noise=noise, mask_fraction=mask_fraction)
+    n = int(mask.sum())
+    a_, q0_, q_ = synthetic.routing_fields(n, seed)
+    alpha = a_ if alpha is None else alpha
+    q0 = q0_ if q0 is None else q0
+    q = q_ if q is None else q
+    rng = np.random.default_rng(seed + 1)
+    if dx is None:
+        dx = rng.uniform(3000.0, 7000.0, n) if dx_array else 5000.0
+    if negative_q:  # negative side-flow (water abstraction) exercises the C <= 1e-12 branch
+        q = q - 1.5e-4 * (rng.random(n) < 0.3)
+        q0 = q0 * (rng.random(n) < 0.7)
+    alpha2 = alpha * rng.uniform(1.5, 3.0, n) if split else None
+    kw = kwp.kinematicWave(ldd[mask].copy(), mask, alpha, beta, dx, dt, alpha_floodplains=alpha2)
+    out = dict(ldd=ldd[mask].astype(np.float64), mask=mask, alpha=alpha, beta=np.float64(beta), dx=np.asarray(dx),
+               dt=np.float64(dt), q0=q0, q=q,
+               downstream_lookup=kw.downstream_lookup, upstream_lookup=kw.upstream_lookup,
+               num_upstream_pixels=kw.num_upstream_pixels, pixels_ordered=kw.pixels_ordered,
+               order_start_stop=kw.order_start_stop)
+    Q = q0.copy()
+    snaps = []
+    for s in range(steps):
+        kw.kinematicWaveRouting(Q, q, "main_channel")
+        snaps.append(Q.copy())
+    out["Q_main"] = np.stack(snaps)
+    if split:
+        out["alpha2"] = alpha2
+        Q2 = q0.copy() * 0.5
+        snaps = []
+        for s in range(steps):
+            kw.kinematicWaveRouting(Q2, q * 0.3, "floodplains")
+            snaps.append(Q2.copy())
+        out["Q_fp"] = np.stack(snaps)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "n=%d levels=%d K=%d" % (n, kw.order_start_stop.shape[0], kw.upstream_lookup.shape[1]))
+
+
+def main():
+    kwpt, kwp, sl = ref_loader.load()
+    # known-answer vector of SURVEY.md §8c: 4x4, all south, bottom row pits
+    ldd = np.full((4, 4), 2.0)
+    ldd[3, :] = 5.0
+    mask = np.ones((4, 4), bool)
+    routing_case(kwp, "kw_4x4_south", 4, 4, 0, 0, 0, False, 3, False, ldd=ldd, mask=mask, alpha=np.full(16, 1.5),
+                 q0=np.ones(16), q=np.full(16, 1e-4), dx=1000.0)
+    routing_case(kwp, "kw_40x50_masked", 40, 50, 11, 1.0, 0.25, True, 6, True)
+    routing_case(kwp, "kw_64x48_deep", 64, 48, 12, 0.2, 0.0, False, 6, False)
+    routing_case(kwp, "kw_48x64_negq", 48, 64, 13, 2.0, 0.1, True, 6, True, negative_q=True)
+    routing_case(kwp, "kw_33x29_beta08", 33, 29, 14, 0.5, 0.05, True, 4, False, beta=0.8, dt=21600.0)
+    # degenerate shapes (a 1-pixel domain crashes the reference itself in _setRoutingOrders:
+    # Series.squeeze() returns a scalar, kinematic_wave_parallel.py:151-155 -- no golden possible)
+    routing_case(kwp, "kw_2x1_col", 2, 1, 15, 1.0, 0.0, False, 2, False)
+    routing_case(kwp, "kw_1x17_row", 1, 17, 16, 1.0, 0.0, True, 3, False)
+
+
+if __name__ == "__main__":
+    main()
