@@ -135,6 +135,14 @@ __global__ void k_pj_step(const int32_t *__restrict__ nxt, const int32_t *__rest
     nxt2[p] = b;
     if (b != a) *active = 1;  // benign race: everybody writes 1
 }
+// after convergence every pixel must have reached a true outlet; a pixel on (or draining into) a
+// cycle ends on a node that still has a downstream link
+__global__ void k_pj_check(const int32_t *__restrict__ nxt, const int32_t *__restrict__ ds, int64_t n,
+                           int *__restrict__ cyc)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n && ds[nxt[p]] >= 0) *cyc = 1;
+}
 __global__ void k_max(const int32_t *__restrict__ v, int64_t n, int *__restrict__ out)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -393,7 +401,17 @@ static int build_graph(const double *ldd_codes, const uint8_t *land_mask, int64_
         std::swap(rk, rk2);
         if (!h_flag[1]) break;
     }
-    // rk = hops to outlet for every pixel (a cycle never settles -> caught above)
+    // rk = hops to outlet for every pixel.  Odd cycles never settle (caught above); even cycles
+    // collapse onto self-loops that are not outlets:
+    LF_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(int), st));
+    k_pj_check<<<blocks_for(n, T), T, 0, st>>>(nx, g->downstream.p, n, d_flag.p);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaMemcpyAsync(h_flag, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaStreamSynchronize(st));
+    if (h_flag[0]) {
+        lf::set_error("the LDD contains a cycle (no outlet reachable)");
+        return LF_ERR_LDD_CYCLE;
+    }
     LF_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(int), st));
     k_max<<<blocks_for(n, T), T, 0, st>>>(rk, n, d_flag.p);
     LF_LAUNCH_CHECK();
