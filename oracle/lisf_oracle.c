@@ -181,9 +181,17 @@ int64_t lfo_kinematic_routing(double *discharge, const double *constant, const i
 {
     double inv_beta = 1.0 / beta, b_minus_1 = beta - 1.0;
     int64_t iters = 0;
+    int max_thr = 1;
+#ifdef _OPENMP
+    max_thr = omp_get_max_threads();
+#endif
     for (int64_t o = 0; o < n_orders; ++o) {
         int64_t first = start_stop[2 * o], last = start_stop[2 * o + 1];
-#pragma omp parallel for schedule(static) reduction(+ : iters) if (last - first > 256)
+        /* engage one thread per ~128 pixels of the level so that small levels do not pay a
+         * full-team fork/join (Numba's prange chunks similarly) */
+        int thr = (int)((last - first) / 128);
+        thr = thr < 1 ? 1 : (thr > max_thr ? max_thr : thr);
+#pragma omp parallel for schedule(static) reduction(+ : iters) num_threads(thr) if (thr > 1)
         for (int64_t i = first; i < last; ++i)
             iters += solve_1_pixel(ordered[i], discharge, constant, upstream, ups_stride, num_ups, a_dx_div_dt,
                                    b_a_dx_div_dt, beta, inv_beta, b_minus_1);
