@@ -62,3 +62,205 @@ def level_stats(order_start_stop):
     sizes = order_start_stop[:, 1] - order_start_stop[:, 0]
     return {"levels": int(sizes.size), "median_level": float(np.median(sizes)), "max_level": int(sizes.max()),
             "min_level": int(sizes.min())}
+
+
+# ------------------------------------------------------------------------------------------------
+# Full soil + overland + channel stack (config C3 of BASELINE.json)
+# ------------------------------------------------------------------------------------------------
+VEG = ["Rainfed_prescribed", "Forest_prescribed", "Irrigated_prescribed"]
+LANDUSE = ["Rainfed", "Forest", "Irrigated"]
+
+
+def mualem(w_res, w_sat, genu_alpha, genu_n, genu_m, head_cm):
+    """Soil moisture at pressure head [cm] (reference: hydrological_modules/soil.py:30-35)."""
+    return w_res + (w_sat - w_res) / ((1 + (genu_alpha * head_cm) ** genu_n) ** genu_m)
+
+
+def full_stack(rows, cols, seed=0, ldd_noise=0.5, mask_fraction=0.0, channel_threshold=60, split_routing=False,
+               dt_sec=86400.0, dt_sec_channel=3600.0, frozen_fraction=0.05):
+    """Static parameters + initial state of the hot path on a seeded synthetic catchment.
+
+    Keys follow the reference's `self.var.<name>` attributes.  (V, N) / (L, N) arrays are
+    C-contiguous float64; land use 2 (Irrigated) shares the parameter maps of land use 0 exactly like the
+    reference's `defsoil` without a third map (Lisflood_initial.py:371-391).
+    """
+    from .global_modules import ldd_ops
+    rng = np.random.default_rng(seed + 4242)
+    ldd, mask = random_ldd(rows, cols, seed=seed, noise=ldd_noise, mask_fraction=mask_fraction)
+    n = int(mask.sum())
+    S = {"rows": rows, "cols": cols, "mask": mask, "N": n, "Ldd": ldd[mask].astype(np.float64)}
+    S["Ldd"] = ldd_ops.lddrepair_codes(S["Ldd"], mask)
+
+    def U(lo, hi, shape=None):
+        return rng.uniform(lo, hi, (n,) if shape is None else shape)
+
+    def landuse3(a_other, a_forest):
+        return np.ascontiguousarray(np.stack([a_other, a_forest, a_other]))
+
+    # ---- time / geometry constants (miscInitial.py:44-181, routing.py:61-82)
+    S["DtSec"], S["DtSecChannel"] = float(dt_sec), float(dt_sec_channel)
+    S["DtDay"] = S["DtSec"] / 86400.0
+    S["InvDtSec"], S["InvDtDay"] = 1 / S["DtSec"], 1 / S["DtDay"]
+    S["NoRoutSteps"] = int(max(1, round(S["DtSec"] / S["DtSecChannel"], 0)))
+    S["DtRouting"] = S["DtSec"] / S["NoRoutSteps"]
+    S["InvDtRouting"] = 1 / S["DtRouting"]
+    S["InvNoRoutSteps"] = 1 / float(S["NoRoutSteps"])
+    S["PixelLength"] = 5000.0
+    S["InvPixelLength"] = 1.0 / S["PixelLength"]
+    S["PixelArea"] = np.full(n, S["PixelLength"] ** 2)
+    S["MMtoM"] = 0.001
+    S["MMtoM3"] = 0.001 * S["PixelArea"]
+    S["M3toMM"] = 1 / S["MMtoM3"]
+    S["Beta"] = 0.6
+    S["InvBeta"] = 1 / S["Beta"]
+    S["AlpPow"] = 2.0 / 3.0 * S["Beta"]
+
+    # ---- fractions (Dirichlet over other / forest / irrigated / sealed / water)
+    fr = rng.dirichlet([4.0, 3.0, 1.0, 0.6, 0.3], n).T
+    S["SoilFraction"] = np.ascontiguousarray(fr[:3])
+    S["DirectRunoffFraction"] = np.ascontiguousarray(fr[3])
+    S["WaterFraction"] = np.ascontiguousarray(fr[4])
+
+    # ---- soil hydraulic parameters per land use and layer (soil.py:109-228)
+    for lay, (d_lo, d_hi) in (("1a", (40, 60)), ("1b", (200, 300)), ("2", (500, 900))):
+        if lay == "2":
+            depth = U(d_lo, d_hi)
+            depth = landuse3(depth, depth)
+            ths, thr = U(.4, .5), U(.02, .08)
+            lam, gal = U(.15, .45), U(.005, .05)
+            ks = np.exp(U(np.log(1.0), np.log(500.0)))
+            ths, thr, lam, gal, ks = (landuse3(x, x) for x in (ths, thr, lam, gal, ks))
+        else:
+            depth = landuse3(U(d_lo, d_hi), U(d_lo, d_hi))
+            # (zero-depth soils are not generated: the reference's satFun divides by WFC-WWP = 0 and Numba
+            #  raises ZeroDivisionError, hydrological_modules/soilloop.py:393-396)
+            ths, thr = landuse3(U(.4, .5), U(.4, .5)), landuse3(U(.02, .08), U(.02, .08))
+            lam, gal = landuse3(U(.15, .45), U(.15, .45)), landuse3(U(.005, .05), U(.005, .05))
+            ks = landuse3(np.exp(U(np.log(1.0), np.log(500.0))), np.exp(U(np.log(1.0), np.log(500.0))))
+        gn = 1 + lam
+        gm = lam / gn
+        S["SoilDepth" + lay], S["KSat" + lay] = depth, ks
+        S["GenuM" + lay], S["GenuInvM" + lay] = gm, 1 / gm
+        ws, wres = ths * depth, thr * depth
+        S["WS" + lay], S["WRes" + lay] = ws, wres
+        S["WFC" + lay] = mualem(wres, ws, gal, gn, gm, 100)
+        S["WPF3" + {"1a": "a", "1b": "b", "2": "2"}[lay]] = mualem(wres, ws, gal, gn, gm, 1000)
+        S["WWP" + lay] = mualem(wres, ws, gal, gn, gm, 15000)
+        S["PoreSpaceNotZero" + lay] = np.logical_and(depth != 0, ws != 0)
+    for nm in ("WS", "WRes", "WFC", "WWP"):
+        S[nm + "1"] = S[nm + "1a"] + S[nm + "1b"]
+    S["WPF3"] = S["WPF3a"] + S["WPF3b"]
+    S["SoilDepthTotal"] = S["SoilDepth1a"] + S["SoilDepth1b"] + S["SoilDepth2"]
+    S["b_Xinanjiang"] = U(.1, .7)
+    S["PowerInfPot"] = (S["b_Xinanjiang"] + 1) / S["b_Xinanjiang"]
+    S["StoreMaxPervious"] = S["WS1"] / (S["b_Xinanjiang"] + 1)
+    S["PowerPrefFlow"] = U(1.0, 5.0)
+    S["CropCoef"] = np.ascontiguousarray(np.stack([U(.9, 1.1), U(.9, 1.3), U(.9, 1.2)]))
+    S["CropGroupNumber"] = np.ascontiguousarray(np.stack([U(1.0, 5.0), U(2.0, 5.0), U(1.0, 5.0)]))
+    S["CourantCrit"] = 0.4
+    S["LeafDrainageK"] = float(min(S["DtDay"] * (1 / 1.0), 1))
+    S["AvWaterThreshold"] = 5.0 * S["DtDay"]
+    S["DrainedFraction"] = 0.0
+    S["SMaxSealed"] = 1.0
+    S["kgb"] = 0.75 * 0.72
+
+    # ---- groundwater (groundwater.py:44-132, miscInitial.py:127-133)
+    S["UpperZoneK"] = np.minimum(S["DtDay"] * (1 / U(5.0, 20.0)), 1)
+    S["LowerZoneK"] = np.minimum(S["DtDay"] * (1 / U(50.0, 500.0)), 1)
+    gwloss = np.zeros(n)
+    S["GwPercStep"] = np.maximum(U(0.2, 1.5), gwloss) * S["DtDay"]
+    S["GwLossStep"] = gwloss * S["DtDay"]
+    S["LZThreshold"] = U(0.0, 20.0)
+
+    # ---- initial state (soil.py:268-277, 380-410; groundwater.py:97-118)
+    for lay in ("1a", "1b", "2"):
+        w = np.empty((3, n))
+        for v in range(3):
+            w[v] = np.where(S["PoreSpaceNotZero" + lay][v], S["WFC" + lay][v] * U(0.7, 1.1), 0)
+            w[v] = np.minimum(w[v], S["WS" + lay][v])
+        S["W" + lay] = w
+    S["W1"] = S["W1a"] + S["W1b"]
+    S["UZ"] = np.ascontiguousarray(U(0.0, 10.0, (3, n)))
+    S["LZ"] = U(20.0, 200.0)
+    S["DSLR"] = np.ascontiguousarray(np.floor(U(1.0, 6.0, (3, n))))
+    S["CumInterception"] = np.ascontiguousarray(U(0.0, 0.5, (3, n)))
+    S["CumInterSealed"] = U(0.0, 0.5)
+    S["LZInflowCUM"] = np.zeros(n)
+
+    # ---- drainage networks (routing.py:90-170)
+    ds = ldd_ops.downstream_index(S["Ldd"], mask)
+    uparea = ldd_ops.accuflux(ds, np.ones(n))
+    S["IsChannel"] = uparea >= channel_threshold
+    S["IsChannelKinematic"] = S["IsChannel"].copy()
+    S["LddKinematic"] = ldd_ops.lddrepair_codes(ldd_ops.lddmask_codes(S["Ldd"], S["IsChannel"]), mask)
+    # cells draining into a non-channel cell cannot exist (channels are downstream-closed by construction)
+    S["LddToChan"] = np.where(S["IsChannel"], 5.0, S["Ldd"])
+    S["AtLastPointC"] = ds < 0
+
+    # ---- channel geometry (routing.py:184-253)
+    S["ChanLength"] = S["PixelLength"] * U(1.0, 1.4)
+    S["InvChanLength"] = 1 / S["ChanLength"]
+    chan_grad = np.maximum(U(1e-4, 5e-3), 1e-5)
+    chan_man = U(0.02, 0.06)
+    width = 2.0 + 0.5 * np.sqrt(uparea)
+    depth_thr = 0.5 + 0.05 * np.sqrt(uparea)
+    sdxdy = 1.0
+    S["ChanBottomWidth"] = width
+    upper = width + 2 * sdxdy * depth_thr
+    bankfull = 0.5 * depth_thr * (upper + width)
+    S["TotalCrossSectionAreaBankFull"] = bankfull
+    S["TotalCrossSectionArea"] = 0.5 * bankfull
+    wd_alpha = np.where(S["IsChannel"], 0.5 * depth_thr, 0.0)
+    S["ChanWettedPerimeterAlpha"] = width + 2 * np.sqrt(np.square(wd_alpha) + np.square(wd_alpha * sdxdy))
+    alp_term = (chan_man / np.sqrt(chan_grad)) ** S["Beta"]
+    S["ChannelAlpha"] = (alp_term * (S["ChanWettedPerimeterAlpha"] ** S["AlpPow"])).astype(float)
+    S["InvChannelAlpha"] = 1 / S["ChannelAlpha"]
+    S["ChanM3"] = S["TotalCrossSectionArea"] * S["ChanLength"]
+    S["ChanM3Kin"] = S["ChanM3"].copy()
+    S["ChanQKin"] = np.where(S["ChannelAlpha"] > 0, (S["TotalCrossSectionArea"] / S["ChannelAlpha"]) ** S["InvBeta"], 0)
+    S["ChanQ"] = S["ChanQKin"].copy()
+    S["SplitRouting"] = bool(split_routing)
+    if split_routing:  # routing.py:353-397
+        man2 = chan_man * 3.0
+        S["ChannelAlpha2"] = (((man2 / np.sqrt(chan_grad)) ** S["Beta"]) * (S["ChanWettedPerimeterAlpha"] ** S["AlpPow"]))
+        S["InvChannelAlpha2"] = 1 / S["ChannelAlpha2"]
+        dsk = ldd_ops.downstream_index(S["LddKinematic"], mask)
+        avgdis = np.where(S["IsChannel"], 0.002 * ldd_ops.accuflux(dsk, np.where(S["IsChannel"], 1.0, 0.0)) + 0.01, 0.0)
+        S["QLimit"] = avgdis * 2.0
+        S["M3Limit"] = S["ChannelAlpha"] * S["ChanLength"] * (S["QLimit"] ** S["Beta"])
+        S["Chan2M3Start"] = S["ChannelAlpha2"] * S["ChanLength"] * (S["QLimit"] ** S["Beta"])
+        S["Chan2QStart"] = S["QLimit"] - ldd_ops.upstream_sum(dsk, S["QLimit"])
+        S["CrossSection2Area"] = np.zeros(n)
+        S["Sideflow1Chan"] = np.zeros(n)
+        S["Chan2M3Kin"] = S["CrossSection2Area"] * S["ChanLength"] + S["Chan2M3Start"]
+        S["ChanM3Kin"] = S["ChanM3"] - S["Chan2M3Kin"] + S["Chan2M3Start"]
+        S["ChanM3Kin"] = np.where((S["ChanM3Kin"] < 0.0) & (S["ChanM3Kin"] > -0.0000001), 0.0, S["ChanM3Kin"])
+        S["Chan2QKin"] = (S["Chan2M3Kin"] * S["InvChanLength"] * S["InvChannelAlpha2"]) ** S["InvBeta"]
+        S["ChanQKin"] = (S["ChanM3Kin"] * S["InvChanLength"] * S["InvChannelAlpha"]) ** S["InvBeta"]
+
+    # ---- overland flow (surface_routing.py:44-95; runoff order = Other, Forest, Direct)
+    grad = np.maximum(U(1e-3, 0.1), 1e-4)
+    nman = np.stack([U(0.05, 0.2), U(0.1, 0.4), np.full(n, 0.02)])
+    of_wp = S["PixelLength"] + 2 * S["MMtoM"] * 5.0
+    S["OFAlpha"] = np.ascontiguousarray(((nman / np.sqrt(grad)) ** S["Beta"]) * (of_wp ** S["AlpPow"]))
+    S["InvOFAlpha"] = 1 / S["OFAlpha"]
+    for k, nm in enumerate(("Other", "Forest", "Direct")):
+        S["OFM3" + nm] = np.zeros(n)
+        S["OFQ" + nm] = ((S["OFM3" + nm] * S["InvPixelLength"] * S["InvOFAlpha"][k]) ** S["InvBeta"]).astype(float)
+    return S
+
+
+def forcing(S, step, seed=0):
+    """Seeded meteorological forcing of model step `step`: intermittent Gamma rain,
+    ETRef/EWRef ~ U(0,6) mm/day, LAI ~ U(0,6), a few frozen pixels."""
+    n = S["N"]
+    rng = np.random.default_rng((seed + 1) * 100003 + step)
+    wet = rng.random(n) < 0.45
+    F = {"Rain": np.where(wet, rng.gamma(0.8, 8.0, n), 0.0) * S["DtDay"],
+         "SnowMelt": np.where(rng.random(n) < 0.1, rng.uniform(0, 3.0, n), 0.0) * S["DtDay"],
+         "ETRef": rng.uniform(0, 6.0, n) * S["DtDay"], "EWRef": rng.uniform(0, 6.0, n) * S["DtDay"],
+         "LAI": np.ascontiguousarray(rng.uniform(0, 6.0, (3, n))),
+         "isFrozenSoil": rng.random(n) < 0.05}
+    F["ESRef"] = (F["EWRef"] + F["ETRef"]) / 2
+    F["LAITerm"] = np.exp(-S["kgb"] * F["LAI"])
+    return F

@@ -24,6 +24,14 @@ def available():
 _loaded = {}
 
 
+def _load_module(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
 def load():
     """Returns (kwpt, kwp, soilloop) reference modules."""
     if _loaded:
@@ -34,9 +42,11 @@ def load():
     nx.__version__ = "stub"
 
     def _evaluate(expr, local_dict=None, global_dict=None):
+        # numexpr resolves names in the caller's frame unless the dicts are given
+        fr = sys._getframe(1)
         env = {}
-        env.update(global_dict or {})
-        env.update(local_dict or {})
+        env.update(fr.f_globals if global_dict is None else global_dict)
+        env.update(fr.f_locals if local_dict is None else local_dict)
         return eval(expr, {"__builtins__": {}}, env)
 
     nx.evaluate = _evaluate
@@ -55,13 +65,7 @@ def load():
         setattr(st, n, type(n, (), {}))
     sys.modules["lisflood.global_modules.settings"] = st
 
-    def _load(name, path):
-        spec = importlib.util.spec_from_file_location(name, path)
-        m = importlib.util.module_from_spec(spec)
-        sys.modules[name] = m
-        spec.loader.exec_module(m)
-        return m
-
+    _load = _load_module
     _load("lisflood.global_modules.errors", _R + "/global_modules/errors.py")
     kwpt = _load("lisflood.hydrological_modules.kinematic_wave_parallel_tools",
                  _R + "/hydrological_modules/kinematic_wave_parallel_tools.py")

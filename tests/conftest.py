@@ -52,3 +52,17 @@ def gpu_lib():
     L = _capi.lib()
     _capi.check(L.lf_device_init(0))
     return _capi
+
+
+def golden_model(name):
+    """(S, [F per step], [outputs per step]) of a model_* golden case."""
+    g = load_golden(name)
+    S, steps = {}, int(g["steps"])
+    for k, v in g.items():
+        if k.startswith("S__"):
+            S[k[3:]] = v.item() if v.ndim == 0 else v
+    S["N"], S["rows"], S["cols"], S["NoRoutSteps"] = int(S["N"]), int(S["rows"]), int(S["cols"]), int(S["NoRoutSteps"])
+    S["SplitRouting"] = bool(S["SplitRouting"])
+    F = [{k.split("__", 1)[1]: v for k, v in g.items() if k.startswith("F%d__" % t)} for t in range(steps)]
+    O = [{k.split("__", 1)[1]: v for k, v in g.items() if k.startswith("O%d__" % t)} for t in range(steps)]
+    return S, F, O

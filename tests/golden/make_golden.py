@@ -58,7 +58,48 @@ def routing_case(kwp, name, rows, cols, seed, noise, mask_fraction, dx_array, st
     print(name, "n=%d levels=%d K=%d" % (n, kw.order_start_stop.shape[0], kw.upstream_lookup.shape[1]))
 
 
+MODEL_KEYS_V = ["CumInterception", "W1a", "W1b", "W1", "W2", "UZ", "DSLR", "Interception", "TaInterception", "LeafDrainage",
+                "potential_transpiration", "Ta", "ESAct", "PrefFlow", "Infiltration", "AvailableWaterForInfiltration",
+                "SeepTopToSubA", "SeepTopToSubB", "SeepSubToGW", "Theta1a", "Theta1b", "Theta2", "Sat1a", "Sat1b", "Sat1",
+                "Sat2", "UZOutflow", "GwPercUZLZ", "RWS", "Theta", "SurfaceRunSoil"]
+MODEL_KEYS_N = ["CumInterSealed", "LZ", "LZInflowCUM", "DirectRunoff", "TASealed", "EWaterAct", "InterSealed", "RainSnowmelt",
+                "TaInterceptionAll", "TaPixel", "ESActPixel", "PrefFlowPixel", "InfiltrationPixel", "ThetaAll",
+                "SeepTopToSubPixelA", "SeepTopToSubPixelB", "SeepSubToGWPixel", "Theta1aPixel", "Theta1bPixel", "Theta2Pixel",
+                "UZOutflowPixel", "GwPercUZLZPixel", "GwLossLZ", "LZOutflow", "LZOutflowToChannelPixel", "LZAvInflow",
+                "SurfaceRunoff", "TotalRunoff", "OFQDirect", "OFQOther", "OFQForest", "OFM3Direct", "OFM3Other", "OFM3Forest",
+                "Qall", "M3all", "OFToChanM3", "WaterDepth", "ToChanM3Runoff", "ToChanM3RunoffDt", "ChanQKin", "ChanM3Kin",
+                "ChanQ", "sumDisDay", "FlowVelocity", "TravelDistance", "ChanM3", "TotalCrossSectionArea", "ChanQAvg",
+                "sumDis", "DischargeM3Out", "TaCUM", "TaInterceptionCUM", "ESActCUM", "GwLossCUM"]
+MODEL_KEYS_SPLIT = ["Chan2QKin", "Chan2M3Kin", "CrossSection2Area", "Sideflow1Chan", "sumDisDay_NOTlast"]
+
+
+def model_case(name, rows, cols, seed, split, steps, **kw):
+    """Full hot-path step executed by the reference's OWN module classes (oracle/ref_modules.py)."""
+    from oracle import ref_modules
+    S = synthetic.full_stack(rows, cols, seed=seed, split_routing=split, **kw)
+    M = ref_modules.RefModel(S)
+    out = {}
+    for k, v in S.items():
+        out["S__" + k] = np.asarray(v)
+    keys = MODEL_KEYS_V + MODEL_KEYS_N + (MODEL_KEYS_SPLIT if split else [])
+    for t in range(steps):
+        F = synthetic.forcing(S, t, seed)
+        for k, v in F.items():
+            out["F%d__%s" % (t, k)] = v
+        M.step(F)
+        for k in keys:
+            out["O%d__%s" % (t, k)] = np.asarray(getattr(M.var, k)).copy()
+    out["steps"] = np.int64(steps)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "n=%d steps=%d split=%s channel fraction %.3f" % (S["N"], steps, split, S["IsChannel"].mean()))
+
+
 def main():
+    import warnings
+    warnings.simplefilter("ignore")
+    model_case("model_26x34_single", 26, 34, 41, False, 3, mask_fraction=0.08, channel_threshold=12)
+    model_case("model_30x28_split", 30, 28, 42, True, 3, mask_fraction=0.05, channel_threshold=10)
+    model_case("model_20x22_6h", 20, 22, 43, False, 2, channel_threshold=8, dt_sec=21600.0)
     kwpt, kwp, sl = ref_loader.load()
     # known-answer vector of SURVEY.md §8c: 4x4, all south, bottom row pits
     ldd = np.full((4, 4), 2.0)
