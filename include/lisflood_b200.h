@@ -38,7 +38,6 @@ extern "C" {
 
 typedef struct lf_graph lf_graph;   /* D8 drainage graph + routing order, device resident */
 typedef struct lf_router lf_router; /* one kinematicWave object */
-typedef struct lf_soil lf_soil;     /* fused per-cell soil / runoff state + parameters */
 typedef struct lf_model lf_model;   /* full hot-path step: soil -> overland -> channel sub-steps */
 
 const char *lf_last_error(void);
@@ -105,6 +104,52 @@ int lf_router_set_inflow(lf_router *r, int section, const double *specific_later
  * host f64[nsteps]).  Same arithmetic per (pixel, step) as nsteps calls of lf_router_route. */
 int lf_router_run(lf_router *r, int section, int nsteps, const double *q_scale, int *nonfinite);
 void lf_router_destroy(lf_router *r);
+
+/* ---------------------------------------------------------------------------------------------
+ * Full hot-path step on device-resident state.  One lf_model holds what the reference keeps on the
+ * shared model object `self.var` for these modules (attribute names: SURVEY.md A.3) and replaces, per
+ * model time step (Lisflood_dynamic.py:114-229):
+ *   lf_model_soil            soilloop.dynamic_canopy + dynamic_soil   hydrological_modules/soilloop.py:519-665
+ *                            opensealed.dynamic                        hydrological_modules/opensealed.py:41-71
+ *                            soil.dynamic_perpixel                     hydrological_modules/soil.py:471-514
+ *                            groundwater.dynamic                       hydrological_modules/groundwater.py:134-180
+ *                            runoff components of surface_routing      hydrological_modules/surface_routing.py:122-149
+ *   lf_model_surface_routing surface_routing.dynamic (3 routers)       hydrological_modules/surface_routing.py:151-212
+ *   lf_model_channel         NoRoutSteps x routing.dynamic + post-loop hydrological_modules/routing.py:435-706,
+ *                                                                       Lisflood_dynamic.py:176-229
+ *   lf_model_step            the three stages in order.
+ * Options covered: kinematic wave (no dynamicWave), single or split routing, no structures / water use /
+ * inflow / transmission loss / open-water evaporation (out of scope).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lf_model_config {
+    int64_t rows, cols;
+    double DtSec;            /* model time step [s]; DtDay = DtSec / 86400 */
+    double Beta;             /* kinematic wave beta */
+    double PixelLength;      /* [m] (scalar, like the reference without gridSizeUserDefined) */
+    int32_t NoRoutSteps;     /* channel sub-steps per model step; DtRouting = DtSec / NoRoutSteps */
+    int32_t SplitRouting;    /* 0 single kinematic routing, 1 main channel + floodplain */
+    double CourantCrit, AvWaterThreshold, LeafDrainageK, DrainedFraction, SMaxSealed;
+    int32_t diagnostics;     /* 1: materialise every flux / diagnostic map of the reference (tests, reporting) */
+    int32_t reserved;
+} lf_model_config;
+
+/* land_mask u8[rows*cols]; ldd_to_chan, ldd_kinematic: f64[N] compressed keypad codes of LddToChan and
+ * LddKinematic (hydrological_modules/routing.py:118-153). */
+int lf_model_create(const lf_model_config *cfg, const uint8_t *land_mask, const double *ldd_to_chan,
+                    const double *ldd_kinematic, lf_model **out);
+int lf_model_info(const lf_model *m, int64_t *n_pixels, int64_t *levels_overland, int64_t *levels_channel,
+                  int64_t *isolated_channel_pixels, int64_t *device_bytes);
+/* Named maps in the reference's compressed order: count = N for per-pixel maps, 3*N for
+ * (vegetation|landuse|runoff, pixel) maps.  Unknown names -> LF_ERR_INVALID. */
+int lf_model_set(lf_model *m, const char *name, const double *values, int64_t count);
+int lf_model_get(lf_model *m, const char *name, double *values, int64_t count);
+/* boolean maps (u8[N]): "isFrozenSoil", "IsChannel", "IsChannelKinematic", "AtLastPointC" */
+int lf_model_set_flags(lf_model *m, const char *name, const uint8_t *values, int64_t count);
+int lf_model_soil(lf_model *m);
+int lf_model_surface_routing(lf_model *m);
+int lf_model_channel(lf_model *m);
+int lf_model_step(lf_model *m);
+void lf_model_destroy(lf_model *m);
 
 #ifdef __cplusplus
 }

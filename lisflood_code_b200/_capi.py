@@ -57,7 +57,27 @@ SIGNATURES = {
     "lf_router_set_inflow": (C.c_int, [_vp, C.c_int, _f64]),
     "lf_router_run": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
     "lf_router_destroy": (None, [_vp]),
+    "lf_model_create": (C.c_int, [_vp, _u8, _f64, _f64, C.POINTER(_vp)]),
+    "lf_model_info": (C.c_int, [_vp, C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s),
+                                C.POINTER(_i64s)]),
+    "lf_model_set": (C.c_int, [_vp, C.c_char_p, _f64, _i64s]),
+    "lf_model_get": (C.c_int, [_vp, C.c_char_p, _f64, _i64s]),
+    "lf_model_set_flags": (C.c_int, [_vp, C.c_char_p, _u8, _i64s]),
+    "lf_model_soil": (C.c_int, [_vp]),
+    "lf_model_surface_routing": (C.c_int, [_vp]),
+    "lf_model_channel": (C.c_int, [_vp]),
+    "lf_model_step": (C.c_int, [_vp]),
+    "lf_model_destroy": (None, [_vp]),
 }
+
+
+class ModelConfig(C.Structure):
+    """struct lf_model_config (include/lisflood_b200.h)."""
+    _fields_ = [("rows", C.c_int64), ("cols", C.c_int64), ("DtSec", C.c_double), ("Beta", C.c_double),
+                ("PixelLength", C.c_double), ("NoRoutSteps", C.c_int32), ("SplitRouting", C.c_int32),
+                ("CourantCrit", C.c_double), ("AvWaterThreshold", C.c_double), ("LeafDrainageK", C.c_double),
+                ("DrainedFraction", C.c_double), ("SMaxSealed", C.c_double), ("diagnostics", C.c_int32),
+                ("reserved", C.c_int32)]
 
 _lib = None
 

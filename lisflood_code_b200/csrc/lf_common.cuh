@@ -79,7 +79,7 @@ inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + thre
 struct lf_graph {
     int64_t rows = 0, cols = 0, n = 0;
     int32_t n_orders = 0, max_ups = 1;
-    int64_t n_pits = 0;
+    int64_t n_pits = 0, n_isolated = 0;  // isolated = pits without any upstream pixel (stored last)
     // raster-order members (kept for export and for building routers)
     lf::DevBuf<uint8_t> dir2d;        // [rows*cols] 0..7 direction, 8 pit, 9 off-mask
     lf::DevBuf<int32_t> land_points;  // [rows*cols] compressed index or -1

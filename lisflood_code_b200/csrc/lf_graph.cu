@@ -173,7 +173,11 @@ __global__ void k_level_start(const int32_t *__restrict__ sorted_lev, int32_t *_
     if (i == 0 || sorted_lev[i - 1] != k) ls[k] = (int32_t)i;
     if (i == n - 1) ls[nl] = (int32_t)n;
 }
-__global__ void k_top_level(const int32_t *__restrict__ ordered, int32_t *__restrict__ pix_of_pos,
+struct HasUpstream {
+    const uint8_t *nups;
+    __host__ __device__ bool operator()(const int32_t &p) const { return nups[p] != 0; }
+};
+__global__ void k_top_level(const int32_t *__restrict__ top, int32_t *__restrict__ pix_of_pos,
                             int32_t *__restrict__ pos_of_pix, int32_t *__restrict__ cfirst, int s, int e,
                             int64_t n, int ls0_end)
 {
@@ -183,7 +187,7 @@ __global__ void k_top_level(const int32_t *__restrict__ ordered, int32_t *__rest
     if (i == 0) cfirst[n] = s;
     int64_t j = s + i;
     if (j < e) {
-        int p = ordered[j];
+        int p = top[i];
         pix_of_pos[j] = p;
         pos_of_pix[p] = (int32_t)j;
     }
@@ -461,10 +465,29 @@ static int build_graph(const double *ldd_codes, const uint8_t *land_mask, int64_
     LF_CHECK(g->pos_of_pix.alloc(n));
     LF_CHECK(g->cfirst.alloc(n + 1));
     {
-        int64_t span = std::max<int64_t>(std::max<int64_t>(ls[nl] - ls[nl - 1], ls[1]), 1);
-        k_top_level<<<blocks_for(span, T), T, 0, st>>>(g->pixels_ordered.p, g->pix_of_pos.p, g->pos_of_pix.p,
-                                                       g->cfirst.p, ls[nl - 1], ls[nl], n, ls[1]);
+        // outlets with an upstream network first (pixel order), isolated pits (no link at all) last:
+        // the fused channel kernel advances isolated pixels through all sub-steps in registers
+        int64_t top_n = ls[nl] - ls[nl - 1];
+        DevBuf<int32_t> top;
+        LF_CHECK(top.alloc(top_n));
+        HasUpstream sel{g->nups_pix.p};
+        size_t sb = 0;
+        int *d_nsel = d_flag.p;
+        LF_CUDA(cub::DevicePartition::If(nullptr, sb, g->pixels_ordered.p + ls[nl - 1], top.p, d_nsel, (int)top_n, sel, st));
+        if (sb > tmp_bytes) {
+            LF_CHECK(d_tmp.alloc(sb));
+            tmp_bytes = sb;
+        }
+        LF_CUDA(cub::DevicePartition::If(d_tmp.p, sb, g->pixels_ordered.p + ls[nl - 1], top.p, d_nsel, (int)top_n, sel, st));
+        lf::count_launch(2);
+        LF_CUDA(cudaMemcpyAsync(h_flag, d_nsel, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LF_CUDA(cudaStreamSynchronize(st));
+        g->n_isolated = top_n - h_flag[0];
+        int64_t span = std::max<int64_t>(std::max<int64_t>(top_n, ls[1]), 1);
+        k_top_level<<<blocks_for(span, T), T, 0, st>>>(top.p, g->pix_of_pos.p, g->pos_of_pix.p, g->cfirst.p, ls[nl - 1],
+                                                       ls[nl], n, ls[1]);
         LF_LAUNCH_CHECK();
+        LF_CUDA(cudaStreamSynchronize(st));
     }
     const int SMALL = 8 * BFS_THREADS;
     DevBuf<int32_t> cnt, scn;

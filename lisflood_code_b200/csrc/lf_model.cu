@@ -1,0 +1,994 @@
+// lf_model.cu -- the full hot-path time step on device-resident state (C ABI: lf_model_*).
+//
+// Stages per model step (reference call order, Lisflood_dynamic.py:114-229):
+//   1. k_soil_step        fused canopy + soil column + open/sealed + per-pixel sums + groundwater
+//                         (lf_soil_kernel.cuh) -- one pass over the soil maps.
+//   2. k_of_level/k_of_post  the three overland-flow routers (Other, Forest, Direct) on LddToChan,
+//                         solved together in one level sweep (three independent Newton solves per thread),
+//                         then OFToChanM3 / ToChanM3RunoffDt written in channel order.
+//   3. k_chan_diagonal    NoRoutSteps channel sub-steps (routing.dynamic) as ONE space-time wavefront:
+//                         side-flow assembly, kinematic solve(s), volume / discharge post-processing and
+//                         sumDisDay accumulation fused per (pixel, sub-step);
+//      k_chan_isolated    pixels without any link (the ~90 % non-channel pixels of LddKinematic) advance
+//                         through all sub-steps in registers in a single launch;
+//      k_chan_post        ChanM3, TotalCrossSectionArea, ChanQAvg, sumDis, DischargeM3Out
+//                         (Lisflood_dynamic.py:194-229).
+// Storage: soil and overland maps live in the overland router's position order, channel maps in the
+// channel router's position order; lf_model_set/get translate from/to the reference's
+// compressed order.
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+
+#include "lf_common.cuh"
+#include "lf_kw_solve.cuh"
+#include "lf_soil_kernel.cuh"
+
+extern "C" int lf_ldd_build(const double *, const uint8_t *, int64_t, int64_t, lf_graph **);
+extern "C" void lf_graph_destroy(lf_graph *);
+
+namespace {
+
+enum Order { SOIL = 0, CHAN = 1 };
+
+struct Field {
+    lf::DevBuf<double> buf;
+    int rows = 1;
+    Order order = SOIL;
+    bool landuse = false;      // (landuse, pixel) parameter: rows may be shared
+    int row_index[3] = {0, 1, 2};  // storage row of land use r
+    bool diag = false;
+};
+
+struct ChanPtrs {
+    int32_t n;
+    const int32_t *lev, *cfirst;
+    double *Qk, *Qr0, *Qr1, *M3, *sumDis, *ChanQ;
+    const double *a, *L, *alpha, *sideDt;
+    const uint8_t *isChan;
+    // split routing
+    double *Q2k, *Q2r0, *Q2r1, *M32, *CS2A, *S1, *sumNotLast;
+    const double *a2, *alpha2, *QLimit, *M3Limit, *C2M3Start, *C2QStart;
+    double InvDtRouting;
+    int S, split;
+    lfkw::Params P;
+};
+
+__device__ __forceinline__ double pw(double x, double y) { return exp(y * log(x)); }
+
+// one routing.dynamic sub-step of one pixel (hydrological_modules/routing.py:462-604).
+// U1/U2: upstream inflow of the main channel / floodplain for this sub-step.
+struct ChanLocal {
+    double qk, m3, sum, q2k, m32, cs2a, s1, sumnl, chanq;
+};
+
+__device__ __forceinline__ void chan_substep(const ChanPtrs &C, int i, double U1, double U2, ChanLocal &X,
+                                             double L, double invL, double alpha, double a, double sideDt, bool isch,
+                                             double &qr1, double &qr2, double alpha2, double a2, double qlimit,
+                                             double m3limit, double c2start, double c2qstart)
+{
+    double side = isch ? sideDt * invL * C.InvDtRouting : 0.;  // :512
+    if (!C.split) {
+        if (isnan(side)) side = 0.;  // :523
+        double qn = lfkw::solve(U1, X.qk, side * L, a, C.P);
+        qr1 = qn;
+        X.m3 = fmax(L * alpha * pw(qn, C.P.beta), 0.0);          // :527-530
+        X.qk = pw(X.m3 * invL * (1 / alpha), C.P.inv_beta);      // :531
+        X.chanq = X.qk;
+        X.sum += X.chanq;                                         // :537
+    } else {
+        const double tot = X.m3 + X.m32;
+        const double ratio = tot > 0 ? X.m3 / tot : 0.0;          // :549
+        double s1 = (tot - c2start) > m3limit ? ratio * side : side;  // :558-559
+        s1 = fabs(side) < 1e-7 ? side : s1;                       // :564
+        X.s1 = s1;
+        double s2 = side - s1;
+        s2 = s2 + c2qstart * invL;                                // :566-568
+        double qn = lfkw::solve(U1, X.qk, s1 * L, a, C.P);        // :573
+        qr1 = qn;
+        X.m3 = fmax(L * alpha * pw(qn, C.P.beta), 0.0);
+        X.qk = pw(X.m3 * invL * (1 / alpha), C.P.inv_beta);
+        double qn2 = lfkw::solve(U2, X.q2k, s2 * L, a2, C.P);     // :583
+        qr2 = qn2;
+        double m32 = L * alpha2 * pw(qn2, C.P.beta);
+        if (m32 - c2start < 0.0) m32 = c2start;                   // :586-587
+        X.m32 = m32;
+        X.cs2a = (m32 - c2start) * invL;                          // :590
+        X.q2k = pw(m32 * invL * (1 / alpha2), C.P.inv_beta);      // :593
+        X.chanq = fmax(X.qk + X.q2k - qlimit, 0.0);               // :597
+        X.sumnl = X.sum;
+        X.sum += X.chanq;
+    }
+}
+
+constexpr int CH_THREADS = 128;
+
+// wavefront diagonal over channel-network pixels: positions [lo, hi), sub-step s = d - level
+__global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo, int hi, int d)
+{
+    int i = lo + blockIdx.x * CH_THREADS + threadIdx.x;
+    if (i >= hi) return;
+    int s = d - C.lev[i];
+    double *Qr = (s & 1) ? C.Qr1 : C.Qr0;
+    double *Q2r = (s & 1) ? C.Q2r1 : C.Q2r0;
+    int c0 = C.cfirst[i], c1 = C.cfirst[i + 1];
+    double U1 = 0., U2 = 0.;
+    for (int k = c0; k < c1; ++k) U1 += Qr[k];
+    ChanLocal X;
+    X.qk = C.Qk[i];
+    X.sum = s == 0 ? 0. : C.sumDis[i];  // sumDisDay = 0 before the sub-step loop, Lisflood_dynamic.py:177
+    const double L = C.L[i], alpha = C.alpha[i], a = C.a[i], sideDt = C.sideDt[i];
+    const bool isch = C.isChan[i] != 0;
+    double alpha2 = 0, a2 = 0, ql = 0, m3l = 0, c2s = 0, c2q = 0;
+    if (C.split) {
+        for (int k = c0; k < c1; ++k) U2 += Q2r[k];
+        X.m3 = C.M3[i];
+        X.m32 = C.M32[i];
+        X.q2k = C.Q2k[i];
+        alpha2 = C.alpha2[i];
+        a2 = C.a2[i];
+        ql = C.QLimit[i];
+        m3l = C.M3Limit[i];
+        c2s = C.C2M3Start[i];
+        c2q = C.C2QStart[i];
+    }
+    double qr1, qr2 = 0.;
+    chan_substep(C, i, U1, U2, X, L, 1 / L, alpha, a, sideDt, isch, qr1, qr2, alpha2, a2, ql, m3l, c2s, c2q);
+    Qr[i] = qr1;
+    C.Qk[i] = X.qk;
+    C.sumDis[i] = X.sum;
+    const bool last = s == C.S - 1;
+    if (C.split) {
+        Q2r[i] = qr2;
+        C.Q2k[i] = X.q2k;
+        C.M3[i] = X.m3;
+        C.M32[i] = X.m32;
+        if (last) {
+            C.CS2A[i] = X.cs2a;
+            C.S1[i] = X.s1;
+            C.sumNotLast[i] = X.sumnl;
+            C.ChanQ[i] = X.chanq;
+        }
+    } else if (last) {
+        C.M3[i] = X.m3;
+        C.ChanQ[i] = X.chanq;
+    }
+}
+
+// pixels with no upstream and no downstream link: all S sub-steps in registers
+__global__ void __launch_bounds__(CH_THREADS) k_chan_isolated(ChanPtrs C, int lo, int hi)
+{
+    int i = lo + blockIdx.x * CH_THREADS + threadIdx.x;
+    if (i >= hi) return;
+    ChanLocal X;
+    X.qk = C.Qk[i];
+    X.sum = 0.;
+    X.m3 = C.M3[i];
+    const double L = C.L[i], alpha = C.alpha[i], a = C.a[i], sideDt = C.sideDt[i];
+    const bool isch = C.isChan[i] != 0;
+    double alpha2 = 0, a2 = 0, ql = 0, m3l = 0, c2s = 0, c2q = 0;
+    if (C.split) {
+        X.m32 = C.M32[i];
+        X.q2k = C.Q2k[i];
+        alpha2 = C.alpha2[i];
+        a2 = C.a2[i];
+        ql = C.QLimit[i];
+        m3l = C.M3Limit[i];
+        c2s = C.C2M3Start[i];
+        c2q = C.C2QStart[i];
+    }
+    double qr1 = 0., qr2 = 0.;
+    const double invL = 1 / L;
+#pragma unroll 1
+    for (int s = 0; s < C.S; ++s)
+        chan_substep(C, i, 0., 0., X, L, invL, alpha, a, sideDt, isch, qr1, qr2, alpha2, a2, ql, m3l, c2s, c2q);
+    // the routed value of the last sub-step in both parity buffers (nobody reads it: no downstream)
+    C.Qr0[i] = qr1;
+    C.Qr1[i] = qr1;
+    C.Qk[i] = X.qk;
+    C.sumDis[i] = X.sum;
+    C.M3[i] = X.m3;
+    C.ChanQ[i] = X.chanq;
+    if (C.split) {
+        C.Q2r0[i] = qr2;
+        C.Q2r1[i] = qr2;
+        C.Q2k[i] = X.q2k;
+        C.M32[i] = X.m32;
+        C.CS2A[i] = X.cs2a;
+        C.S1[i] = X.s1;
+        C.sumNotLast[i] = X.sumnl;
+    }
+}
+
+// Lisflood_dynamic.py:194-229 and hydrological_modules/routing.py:695-703
+__global__ void k_chan_post(int n, int split, int S, double DtSec, const double *__restrict__ M3, const double *__restrict__ M32,
+                            const double *__restrict__ C2M3Start, const double *__restrict__ L,
+                            const double *__restrict__ sumDisDay, const double *__restrict__ ChanQ,
+                            const double *__restrict__ Qk, const uint8_t *__restrict__ atLast,
+                            const double *__restrict__ PixelArea_ch, double *__restrict__ ChanM3,
+                            double *__restrict__ TotalCS, double *__restrict__ sumDis, double *__restrict__ ChanQAvg,
+                            double *__restrict__ DischargeM3Out, double *__restrict__ FlowVelocity,
+                            double *__restrict__ TravelDistance)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double invL = 1 / L[i];
+    const double m3 = split ? M3[i] + M32[i] - C2M3Start[i] : M3[i];
+    ChanM3[i] = m3;
+    TotalCS[i] = m3 * invL;
+    const double sd = sumDisDay[i];
+    sumDis[i] += sd;
+    ChanQAvg[i] = sd / S;
+    DischargeM3Out[i] += atLast[i] ? ChanQ[i] * DtSec : 0.;
+    if (FlowVelocity) {
+        const double area = fmax(M3[i] * invL, 0.01);
+        const double q = Qk[i];
+        double fv = fmin(q / area, 0.36 * pw(q, 0.24));
+        fv *= fmin(sqrt(PixelArea_ch[i]) * invL, 1.);
+        FlowVelocity[i] = fv;
+        TravelDistance[i] = fv * DtSec;
+    }
+}
+
+// ---- overland flow: three routers in one sweep (surface_routing.py:143-153) ----
+struct OfPtrs {
+    const int32_t *cfirst;
+    const double *DirectRunoff, *SurfOther, *SurfForest, *MMtoM3;
+    const double *a[3];   // Other, Forest, Direct
+    double *Qnew[3];
+    const double *Qold[3];
+    double PixelLength, InvPixelLength, InvDtSec;
+    lfkw::Params P;
+};
+__global__ void __launch_bounds__(128) k_of_level(OfPtrs O, int lo, int hi)
+{
+    int i = lo + blockIdx.x * 128 + threadIdx.x;
+    if (i >= hi) return;
+    int c0 = O.cfirst[i], c1 = O.cfirst[i + 1];
+    const double mm2m3 = O.MMtoM3[i];
+    const double runoff[3] = {O.SurfOther[i], O.SurfForest[i], O.DirectRunoff[i]};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double U = 0.;
+        for (int k = c0; k < c1; ++k) U += O.Qnew[r][k];
+        const double side = runoff[r] * mm2m3 * O.InvPixelLength * O.InvDtSec;  // [m3 s-1 m-1], :143-149
+        O.Qnew[r][i] = lfkw::solve(U, O.Qold[r][i], side * O.PixelLength, O.a[r][i], O.P);
+    }
+}
+// surface_routing.py:191-212 (+ scatter of ToChanM3RunoffDt into channel order)
+__global__ void k_of_post(int n, const double *__restrict__ QO, const double *__restrict__ QF, const double *__restrict__ QD,
+                          const double *__restrict__ GwToChan, const double *__restrict__ MMtoM3,
+                          const uint8_t *__restrict__ isChannel, const int32_t *__restrict__ soil_to_chan, double DtSec,
+                          double InvNoRoutSteps, double *__restrict__ sideDt_chan, double *__restrict__ ToChanM3Runoff,
+                          double *__restrict__ OFToChanM3, double *__restrict__ Qall_out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double qall = QD[i] + QO[i] + QF[i];                       // :195
+    const double oftochan = isChannel[i] ? qall * DtSec : 0.;       // :199
+    const double tochan = GwToChan[i] * MMtoM3[i] + oftochan;      // :211
+    sideDt_chan[soil_to_chan[i]] = tochan * InvNoRoutSteps;         // :212
+    if (ToChanM3Runoff) {
+        ToChanM3Runoff[i] = tochan;
+        OFToChanM3[i] = oftochan;
+        Qall_out[i] = qall;
+    }
+}
+
+// ---- layout translation ----
+__global__ void k_rows_to_pos(const double *__restrict__ src, double *__restrict__ dst, const int32_t *__restrict__ pix_of_pos,
+                              int64_t n, int rows)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = pix_of_pos[i];
+    for (int r = 0; r < rows; ++r) dst[(int64_t)r * n + i] = src[(int64_t)r * n + p];
+}
+__global__ void k_rows_to_pix(const double *__restrict__ src, double *__restrict__ dst, const int32_t *__restrict__ pos_of_pix,
+                              int64_t n, int rows)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int i = pos_of_pix[p];
+    for (int r = 0; r < rows; ++r) dst[(int64_t)r * n + p] = src[(int64_t)r * n + i];
+}
+__global__ void k_u8_to_pos(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const int32_t *__restrict__ pix_of_pos,
+                            int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[pix_of_pos[i]];
+}
+__global__ void k_soil_to_chan(const int32_t *__restrict__ pix_of_pos_soil, const int32_t *__restrict__ pos_of_pix_chan,
+                               int32_t *__restrict__ soil_to_chan, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) soil_to_chan[i] = pos_of_pix_chan[pix_of_pos_soil[i]];
+}
+__global__ void k_make_a(const double *__restrict__ alpha, const double *__restrict__ dx, double dxs, double dt,
+                         double *__restrict__ a, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = alpha[i] * (dx ? dx[i] : dxs) / dt;  // a_dx_div_dt, kinematic_wave_parallel.py:126
+}
+__global__ void k_of_m3(const double *__restrict__ Q, const double *__restrict__ alpha, double PixelLength, double beta,
+                        double *__restrict__ M3, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) M3[i] = PixelLength * alpha[i] * pw(Q[i], beta);  // surface_routing.py:191-193
+}
+
+}  // namespace
+
+struct lf_model {
+    lf_model_config cfg;
+    int64_t n = 0;
+    double DtDay = 0, DtRouting = 0;
+    lf_graph *g_of = nullptr, *g_ch = nullptr;
+    std::map<std::string, std::unique_ptr<Field>> fields;
+    std::map<std::string, std::unique_ptr<lf::DevBuf<uint8_t>>> flags;
+    lf::DevBuf<double> stage;        // 3N staging (compressed order)
+    lf::DevBuf<uint8_t> stage_u8;
+    lf::DevBuf<int32_t> soil_to_chan;
+    int64_t steps = 0;               // model steps done (parity of the overland discharge buffers)
+    bool params_dirty = true;        // a_dx_div_dt arrays need a rebuild
+    int64_t bytes = 0;
+    ~lf_model()
+    {
+        if (g_of) lf_graph_destroy(g_of);
+        if (g_ch) lf_graph_destroy(g_ch);
+    }
+};
+
+namespace {
+
+struct FieldSpec {
+    const char *name;
+    int rows;
+    Order order;
+    bool landuse;
+    bool diag;
+};
+
+// every named map of the model (reference attribute names)
+const FieldSpec SPECS[] = {
+    // forcing
+    {"Rain", 1, SOIL, false, false}, {"SnowMelt", 1, SOIL, false, false}, {"ETRef", 1, SOIL, false, false},
+    {"EWRef", 1, SOIL, false, false}, {"ESRef", 1, SOIL, false, false}, {"LAI", 3, SOIL, false, false},
+    {"LAITerm", 3, SOIL, false, false},
+    // per-pixel parameters
+    {"b_Xinanjiang", 1, SOIL, false, false}, {"PowerPrefFlow", 1, SOIL, false, false}, {"UpperZoneK", 1, SOIL, false, false},
+    {"GwPercStep", 1, SOIL, false, false}, {"LowerZoneK", 1, SOIL, false, false}, {"LZThreshold", 1, SOIL, false, false},
+    {"GwLossStep", 1, SOIL, false, false}, {"SoilFraction", 3, SOIL, false, false},
+    {"DirectRunoffFraction", 1, SOIL, false, false}, {"WaterFraction", 1, SOIL, false, false},
+    {"MMtoM3", 1, SOIL, false, false}, {"PixelArea", 1, CHAN, false, false},
+    // land-use parameters
+    {"KSat1a", 3, SOIL, true, false}, {"KSat1b", 3, SOIL, true, false}, {"KSat2", 3, SOIL, true, false},
+    {"GenuInvM1a", 3, SOIL, true, false}, {"GenuInvM1b", 3, SOIL, true, false}, {"GenuInvM2", 3, SOIL, true, false},
+    {"WRes1a", 3, SOIL, true, false}, {"WRes1b", 3, SOIL, true, false}, {"WRes2", 3, SOIL, true, false},
+    {"WS1a", 3, SOIL, true, false}, {"WS1b", 3, SOIL, true, false}, {"WS2", 3, SOIL, true, false},
+    {"WWP1a", 3, SOIL, true, false}, {"WWP1b", 3, SOIL, true, false}, {"WWP2", 3, SOIL, true, true},
+    {"WFC1a", 3, SOIL, true, false}, {"WFC1b", 3, SOIL, true, false}, {"WFC2", 3, SOIL, true, true},
+    {"SoilDepth1a", 3, SOIL, true, true}, {"SoilDepth1b", 3, SOIL, true, true}, {"SoilDepth2", 3, SOIL, true, true},
+    {"CropCoef", 3, SOIL, true, false}, {"CropGroupNumber", 3, SOIL, true, false},
+    // soil state
+    {"CumInterception", 3, SOIL, false, false}, {"W1a", 3, SOIL, false, false}, {"W1b", 3, SOIL, false, false},
+    {"W2", 3, SOIL, false, false}, {"UZ", 3, SOIL, false, false}, {"DSLR", 3, SOIL, false, false},
+    {"LZ", 1, SOIL, false, false}, {"CumInterSealed", 1, SOIL, false, false}, {"LZInflowCUM", 1, SOIL, false, false},
+    {"TaCUM", 1, SOIL, false, false}, {"TaInterceptionCUM", 1, SOIL, false, false}, {"ESActCUM", 1, SOIL, false, false},
+    {"GwLossCUM", 1, SOIL, false, false},
+    // runoff components
+    {"DirectRunoff", 1, SOIL, false, false}, {"SurfOther", 1, SOIL, false, false}, {"SurfForest", 1, SOIL, false, false},
+    {"GwToChan", 1, SOIL, false, false},
+    // overland flow
+    {"OFAlpha", 3, SOIL, false, false}, {"OFQOther", 1, SOIL, false, false}, {"OFQForest", 1, SOIL, false, false},
+    {"OFQDirect", 1, SOIL, false, false},
+    // channel
+    {"ChanLength", 1, CHAN, false, false}, {"ChannelAlpha", 1, CHAN, false, false}, {"ChannelAlpha2", 1, CHAN, false, false},
+    {"ChanQKin", 1, CHAN, false, false}, {"ChanM3Kin", 1, CHAN, false, false}, {"ChanQ", 1, CHAN, false, false},
+    {"sumDisDay", 1, CHAN, false, false}, {"sumDis", 1, CHAN, false, false}, {"ChanQAvg", 1, CHAN, false, false},
+    {"ChanM3", 1, CHAN, false, false}, {"TotalCrossSectionArea", 1, CHAN, false, false},
+    {"DischargeM3Out", 1, CHAN, false, false}, {"ToChanM3RunoffDt", 1, CHAN, false, false},
+    {"Chan2QKin", 1, CHAN, false, false}, {"Chan2M3Kin", 1, CHAN, false, false}, {"CrossSection2Area", 1, CHAN, false, false},
+    {"Sideflow1Chan", 1, CHAN, false, false}, {"sumDisDay_NOTlast", 1, CHAN, false, false}, {"QLimit", 1, CHAN, false, false},
+    {"M3Limit", 1, CHAN, false, false}, {"Chan2M3Start", 1, CHAN, false, false}, {"Chan2QStart", 1, CHAN, false, false},
+    {"FlowVelocity", 1, CHAN, false, true}, {"TravelDistance", 1, CHAN, false, true},
+    // diagnostics (vegetation, pixel)
+    {"Interception", 3, SOIL, false, true}, {"TaInterception", 3, SOIL, false, true}, {"LeafDrainage", 3, SOIL, false, true},
+    {"potential_transpiration", 3, SOIL, false, true}, {"Ta", 3, SOIL, false, true}, {"ESAct", 3, SOIL, false, true},
+    {"PrefFlow", 3, SOIL, false, true}, {"Infiltration", 3, SOIL, false, true},
+    {"AvailableWaterForInfiltration", 3, SOIL, false, true}, {"SeepTopToSubA", 3, SOIL, false, true},
+    {"SeepTopToSubB", 3, SOIL, false, true}, {"SeepSubToGW", 3, SOIL, false, true}, {"Theta1a", 3, SOIL, false, true},
+    {"Theta1b", 3, SOIL, false, true}, {"Theta2", 3, SOIL, false, true}, {"Sat1a", 3, SOIL, false, true},
+    {"Sat1b", 3, SOIL, false, true}, {"Sat1", 3, SOIL, false, true}, {"Sat2", 3, SOIL, false, true},
+    {"UZOutflow", 3, SOIL, false, true}, {"GwPercUZLZ", 3, SOIL, false, true}, {"RWS", 3, SOIL, false, true},
+    {"Theta", 3, SOIL, false, true}, {"SurfaceRunSoil", 3, SOIL, false, true}, {"W1", 3, SOIL, false, true},
+    // diagnostics (pixel)
+    {"RainSnowmelt", 1, SOIL, false, true}, {"EWaterAct", 1, SOIL, false, true}, {"InterSealed", 1, SOIL, false, true},
+    {"TASealed", 1, SOIL, false, true}, {"TaInterceptionAll", 1, SOIL, false, true}, {"TaPixel", 1, SOIL, false, true},
+    {"ESActPixel", 1, SOIL, false, true}, {"PrefFlowPixel", 1, SOIL, false, true}, {"InfiltrationPixel", 1, SOIL, false, true},
+    {"ThetaAll", 1, SOIL, false, true}, {"SeepTopToSubPixelA", 1, SOIL, false, true},
+    {"SeepTopToSubPixelB", 1, SOIL, false, true}, {"SeepSubToGWPixel", 1, SOIL, false, true},
+    {"Theta1aPixel", 1, SOIL, false, true}, {"Theta1bPixel", 1, SOIL, false, true}, {"Theta2Pixel", 1, SOIL, false, true},
+    {"UZOutflowPixel", 1, SOIL, false, true}, {"GwPercUZLZPixel", 1, SOIL, false, true}, {"GwLossLZ", 1, SOIL, false, true},
+    {"LZOutflow", 1, SOIL, false, true}, {"LZAvInflow", 1, SOIL, false, true}, {"SurfaceRunoff", 1, SOIL, false, true},
+    {"TotalRunoff", 1, SOIL, false, true}, {"ToChanM3Runoff", 1, SOIL, false, true}, {"OFToChanM3", 1, SOIL, false, true},
+    {"Qall", 1, SOIL, false, true}, {"OFM3Other", 1, SOIL, false, true}, {"OFM3Forest", 1, SOIL, false, true},
+    {"OFM3Direct", 1, SOIL, false, true},
+};
+
+const FieldSpec *find_spec(const char *name)
+{
+    for (const FieldSpec &s : SPECS)
+        if (strcmp(s.name, name) == 0) return &s;
+    return nullptr;
+}
+
+// device buffer of a field, allocated (zero-filled) on first use
+int field(lf_model *m, const char *name, Field **out)
+{
+    auto it = m->fields.find(name);
+    if (it != m->fields.end()) {
+        *out = it->second.get();
+        return LF_OK;
+    }
+    const FieldSpec *s = find_spec(name);
+    if (!s) {
+        lf::set_error("unknown map name '%s'", name);
+        return LF_ERR_INVALID;
+    }
+    std::unique_ptr<Field> f(new Field());
+    f->rows = s->rows;
+    f->order = s->order;
+    f->landuse = s->landuse;
+    f->diag = s->diag;
+    LF_CHECK(f->buf.alloc((size_t)s->rows * m->n));
+    LF_CUDA(cudaMemsetAsync(f->buf.p, 0, (size_t)s->rows * m->n * sizeof(double), lf::stream()));
+    m->bytes += (int64_t)s->rows * m->n * 8;
+    *out = f.get();
+    m->fields[name] = std::move(f);
+    return LF_OK;
+}
+
+#define FIELD(var, name)              \
+    Field *var##_f = nullptr;         \
+    LF_CHECK(field(m, name, &var##_f)); \
+    double *var = var##_f->buf.p
+
+int flag_buf(lf_model *m, const char *name, uint8_t **out)
+{
+    auto it = m->flags.find(name);
+    if (it == m->flags.end()) {
+        std::unique_ptr<lf::DevBuf<uint8_t>> b(new lf::DevBuf<uint8_t>());
+        LF_CHECK(b->alloc(m->n));
+        LF_CUDA(cudaMemsetAsync(b->p, 0, m->n, lf::stream()));
+        m->bytes += m->n;
+        *out = b->p;
+        m->flags[name] = std::move(b);
+        return LF_OK;
+    }
+    *out = it->second->p;
+    return LF_OK;
+}
+
+// pointer of land-use row r of a (landuse, pixel) parameter
+const double *lu_row(lf_model *m, Field *f, int r) { return f->buf.p + (int64_t)f->row_index[r] * m->n; }
+
+int soil_stage(lf_model *m)
+{
+    using namespace lfsoil;
+    cudaStream_t st = lf::stream();
+    Ptrs P;
+    memset(&P, 0, sizeof(P));
+    Diag D;
+    memset(&D, 0, sizeof(D));
+    P.n = m->n;
+    {
+        FIELD(a, "Rain"); P.Rain = a;
+    }
+#define BIND(member, name)   \
+    {                        \
+        FIELD(_p, name);     \
+        P.member = _p;       \
+    }
+#define BINDLU(member, name)                                          \
+    {                                                                 \
+        FIELD(_p, name);                                              \
+        (void)_p;                                                     \
+        for (int r = 0; r < 3; ++r) P.member[r] = lu_row(m, _p_f, r); \
+    }
+#define BINDD(member, name)  \
+    {                        \
+        FIELD(_p, name);     \
+        D.member = _p;       \
+    }
+    BIND(SnowMelt, "SnowMelt") BIND(ETRef, "ETRef") BIND(EWRef, "EWRef") BIND(ESRef, "ESRef") BIND(LAI, "LAI")
+    BIND(LAITerm, "LAITerm") BIND(bX, "b_Xinanjiang") BIND(PowPref, "PowerPrefFlow") BIND(UZK, "UpperZoneK")
+    BIND(GwPercStep, "GwPercStep") BIND(LZK, "LowerZoneK") BIND(LZThreshold, "LZThreshold") BIND(GwLossStep, "GwLossStep")
+    BIND(SoilFraction, "SoilFraction") BIND(DirectRunoffFraction, "DirectRunoffFraction") BIND(WaterFraction, "WaterFraction")
+    BINDLU(KSat1a, "KSat1a") BINDLU(KSat1b, "KSat1b") BINDLU(KSat2, "KSat2") BINDLU(InvM1a, "GenuInvM1a")
+    BINDLU(InvM1b, "GenuInvM1b") BINDLU(InvM2, "GenuInvM2") BINDLU(WRes1a, "WRes1a") BINDLU(WRes1b, "WRes1b")
+    BINDLU(WRes2, "WRes2") BINDLU(WS1a, "WS1a") BINDLU(WS1b, "WS1b") BINDLU(WS2, "WS2") BINDLU(WWP1a, "WWP1a")
+    BINDLU(WWP1b, "WWP1b") BINDLU(WFC1a, "WFC1a") BINDLU(WFC1b, "WFC1b") BINDLU(CropCoef, "CropCoef")
+    BINDLU(CropGroup, "CropGroupNumber")
+    BIND(CumInterception, "CumInterception") BIND(W1a, "W1a") BIND(W1b, "W1b") BIND(W2, "W2") BIND(UZ, "UZ") BIND(DSLR, "DSLR")
+    BIND(LZ, "LZ") BIND(CumInterSealed, "CumInterSealed") BIND(LZInflowCUM, "LZInflowCUM") BIND(TaCUM, "TaCUM")
+    BIND(TaInterceptionCUM, "TaInterceptionCUM") BIND(ESActCUM, "ESActCUM") BIND(GwLossCUM, "GwLossCUM")
+    BIND(DirectRunoff, "DirectRunoff") BIND(SurfOther, "SurfOther") BIND(SurfForest, "SurfForest") BIND(GwToChan, "GwToChan")
+    uint8_t *frozen = nullptr;
+    LF_CHECK(flag_buf(m, "isFrozenSoil", &frozen));
+    P.frozen = frozen;
+    P.DtDay = m->DtDay;
+    P.InvDtDay = 1 / m->DtDay;
+    P.AvWaterThreshold = m->cfg.AvWaterThreshold;
+    P.CourantCrit = m->cfg.CourantCrit;
+    P.DrainedFraction = m->cfg.DrainedFraction;
+    P.LeafDrainageK = m->cfg.LeafDrainageK;
+    P.SMaxSealed = m->cfg.SMaxSealed;
+    P.TimeSinceStart = (double)(m->steps + 1);
+    unsigned grid = lf::blocks_for(m->n, 128);
+    if (m->cfg.diagnostics) {
+        BINDLU(WWP2, "WWP2") BINDLU(WFC2, "WFC2") BINDLU(Depth1a, "SoilDepth1a") BINDLU(Depth1b, "SoilDepth1b")
+        BINDLU(Depth2, "SoilDepth2")
+        BINDD(Interception, "Interception") BINDD(TaInterception, "TaInterception") BINDD(LeafDrainage, "LeafDrainage")
+        BINDD(potential_transpiration, "potential_transpiration") BINDD(Ta, "Ta") BINDD(ESAct, "ESAct")
+        BINDD(PrefFlow, "PrefFlow") BINDD(Infiltration, "Infiltration")
+        BINDD(AvailableWaterForInfiltration, "AvailableWaterForInfiltration") BINDD(SeepTopToSubA, "SeepTopToSubA")
+        BINDD(SeepTopToSubB, "SeepTopToSubB") BINDD(SeepSubToGW, "SeepSubToGW") BINDD(Theta1a, "Theta1a")
+        BINDD(Theta1b, "Theta1b") BINDD(Theta2, "Theta2") BINDD(Sat1a, "Sat1a") BINDD(Sat1b, "Sat1b") BINDD(Sat1, "Sat1")
+        BINDD(Sat2, "Sat2") BINDD(UZOutflow, "UZOutflow") BINDD(GwPercUZLZ, "GwPercUZLZ") BINDD(RWS, "RWS")
+        BINDD(Theta, "Theta") BINDD(SurfaceRunSoil, "SurfaceRunSoil") BINDD(W1, "W1")
+        BINDD(RainSnowmelt, "RainSnowmelt") BINDD(EWaterAct, "EWaterAct") BINDD(InterSealed, "InterSealed")
+        BINDD(TASealed, "TASealed") BINDD(TaInterceptionAll, "TaInterceptionAll") BINDD(TaPixel, "TaPixel")
+        BINDD(ESActPixel, "ESActPixel") BINDD(PrefFlowPixel, "PrefFlowPixel") BINDD(InfiltrationPixel, "InfiltrationPixel")
+        BINDD(ThetaAll, "ThetaAll") BINDD(SeepTopToSubPixelA, "SeepTopToSubPixelA")
+        BINDD(SeepTopToSubPixelB, "SeepTopToSubPixelB") BINDD(SeepSubToGWPixel, "SeepSubToGWPixel")
+        BINDD(Theta1aPixel, "Theta1aPixel") BINDD(Theta1bPixel, "Theta1bPixel") BINDD(Theta2Pixel, "Theta2Pixel")
+        BINDD(UZOutflowPixel, "UZOutflowPixel") BINDD(GwPercUZLZPixel, "GwPercUZLZPixel") BINDD(GwLossLZ, "GwLossLZ")
+        BINDD(LZOutflow, "LZOutflow") BINDD(LZAvInflow, "LZAvInflow") BINDD(SurfaceRunoff, "SurfaceRunoff")
+        BINDD(TotalRunoff, "TotalRunoff")
+        static_assert(sizeof(int32_t) * 2 == sizeof(double), "NoSubS shares a double-sized slot");
+        Field *ns = nullptr;
+        {
+            auto it = m->fields.find("__NoSubS");
+            if (it == m->fields.end()) {
+                std::unique_ptr<Field> f(new Field());
+                f->rows = 3;
+                LF_CHECK(f->buf.alloc((size_t)3 * m->n));
+                ns = f.get();
+                m->fields["__NoSubS"] = std::move(f);
+            } else {
+                ns = it->second.get();
+            }
+        }
+        D.NoSubS = (int32_t *)ns->buf.p;
+        k_soil_step<true><<<grid, 128, 0, st>>>(P, D);
+    } else {
+        // diagnostics-only parameter rows are never dereferenced in this instantiation
+        k_soil_step<false><<<grid, 128, 0, st>>>(P, D);
+    }
+    LF_LAUNCH_CHECK();
+    return LF_OK;
+}
+
+int build_a(lf_model *m, const char *alpha_name, int row, const double *dx, double dxs, double dt, const char *a_name,
+            int a_row)
+{
+    FIELD(al, alpha_name);
+    FIELD(a, a_name);
+    k_make_a<<<lf::blocks_for(m->n, 256), 256, 0, lf::stream()>>>(al + (int64_t)row * m->n, dx, dxs, dt,
+                                                                  a + (int64_t)a_row * m->n, m->n);
+    LF_LAUNCH_CHECK();
+    return LF_OK;
+}
+
+int refresh_params(lf_model *m)
+{
+    if (!m->params_dirty) return LF_OK;
+    // internal maps "__aOF" (3,N), "__aCh", "__aCh2"
+    for (const char *nm : {"__aOF", "__aCh", "__aCh2"}) {
+        if (m->fields.find(nm) == m->fields.end()) {
+            std::unique_ptr<Field> f(new Field());
+            f->rows = strcmp(nm, "__aOF") == 0 ? 3 : 1;
+            f->order = f->rows == 3 ? SOIL : CHAN;
+            LF_CHECK(f->buf.alloc((size_t)f->rows * m->n));
+            m->bytes += (int64_t)f->rows * m->n * 8;
+            m->fields[nm] = std::move(f);
+        }
+    }
+    for (int r = 0; r < 3; ++r)
+        LF_CHECK(build_a(m, "OFAlpha", r, nullptr, m->cfg.PixelLength, m->cfg.DtSec, "__aOF", r));
+    FIELD(L, "ChanLength");
+    LF_CHECK(build_a(m, "ChannelAlpha", 0, L, 0., m->DtRouting, "__aCh", 0));
+    if (m->cfg.SplitRouting) LF_CHECK(build_a(m, "ChannelAlpha2", 0, L, 0., m->DtRouting, "__aCh2", 0));
+    m->params_dirty = false;
+    return LF_OK;
+}
+
+// internal double-buffer of a discharge map: name + "__r0/__r1"
+int internal(lf_model *m, const std::string &name, Order order, double **out)
+{
+    auto it = m->fields.find(name);
+    if (it == m->fields.end()) {
+        std::unique_ptr<Field> f(new Field());
+        f->order = order;
+        LF_CHECK(f->buf.alloc(m->n));
+        LF_CUDA(cudaMemsetAsync(f->buf.p, 0, m->n * sizeof(double), lf::stream()));
+        m->bytes += m->n * 8;
+        *out = f->buf.p;
+        m->fields[name] = std::move(f);
+        return LF_OK;
+    }
+    *out = it->second->buf.p;
+    return LF_OK;
+}
+
+int surface_stage(lf_model *m)
+{
+    cudaStream_t st = lf::stream();
+    LF_CHECK(refresh_params(m));
+    lf_graph *g = m->g_of;
+    OfPtrs O;
+    O.cfirst = g->cfirst.p;
+    FIELD(dr, "DirectRunoff");
+    FIELD(so, "SurfOther");
+    FIELD(sf, "SurfForest");
+    FIELD(mm, "MMtoM3");
+    FIELD(aof, "__aOF");
+    O.DirectRunoff = dr;
+    O.SurfOther = so;
+    O.SurfForest = sf;
+    O.MMtoM3 = mm;
+    const char *names[3] = {"OFQOther", "OFQForest", "OFQDirect"};
+    double *qcur[3], *qalt[3];
+    for (int r = 0; r < 3; ++r) {
+        Field *f = nullptr;
+        LF_CHECK(field(m, names[r], &f));
+        qcur[r] = f->buf.p;  // the named map always holds the CURRENT discharge
+        LF_CHECK(internal(m, std::string(names[r]) + "__alt", SOIL, &qalt[r]));
+        O.a[r] = aof + (int64_t)r * m->n;
+        O.Qold[r] = qcur[r];
+        O.Qnew[r] = qalt[r];
+    }
+    O.PixelLength = m->cfg.PixelLength;
+    O.InvPixelLength = 1.0 / m->cfg.PixelLength;
+    O.InvDtSec = 1 / m->cfg.DtSec;
+    O.P.beta = m->cfg.Beta;
+    O.P.inv_beta = 1 / m->cfg.Beta;
+    O.P.b_minus_1 = m->cfg.Beta - 1;
+    const std::vector<int32_t> &ls = g->h_level_start;
+    for (int l = 0; l < g->n_orders; ++l) {
+        int lo = ls[l], hi = ls[l + 1];
+        if (hi <= lo) continue;
+        k_of_level<<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+        LF_LAUNCH_CHECK();
+    }
+    // swap: the named maps must hold the new discharge
+    for (int r = 0; r < 3; ++r) {
+        Field *f = m->fields[names[r]].get();
+        Field *alt = m->fields[std::string(names[r]) + "__alt"].get();
+        std::swap(f->buf.p, alt->buf.p);
+        std::swap(f->buf.n, alt->buf.n);
+    }
+    FIELD(qo, "OFQOther");
+    FIELD(qf, "OFQForest");
+    FIELD(qd, "OFQDirect");
+    FIELD(gw, "GwToChan");
+    FIELD(sideDt, "ToChanM3RunoffDt");
+    uint8_t *isch = nullptr;
+    LF_CHECK(flag_buf(m, "IsChannel", &isch));
+    double *tochan = nullptr, *oftochan = nullptr, *qall = nullptr;
+    if (m->cfg.diagnostics) {
+        FIELD(t1, "ToChanM3Runoff");
+        FIELD(t2, "OFToChanM3");
+        FIELD(t3, "Qall");
+        tochan = t1;
+        oftochan = t2;
+        qall = t3;
+        const char *m3n[3] = {"OFM3Other", "OFM3Forest", "OFM3Direct"};
+        const double *qs[3] = {qo, qf, qd};
+        FIELD(ofa, "OFAlpha");
+        for (int r = 0; r < 3; ++r) {
+            FIELD(m3, m3n[r]);
+            k_of_m3<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(qs[r], ofa + (int64_t)r * m->n, m->cfg.PixelLength, m->cfg.Beta,
+                                                               m3, m->n);
+            LF_LAUNCH_CHECK();
+        }
+    }
+    k_of_post<<<lf::blocks_for(m->n, 256), 256, 0, st>>>((int)m->n, qo, qf, qd, gw, mm, isch, m->soil_to_chan.p, m->cfg.DtSec,
+                                                         1 / (double)m->cfg.NoRoutSteps, sideDt, tochan, oftochan, qall);
+    LF_LAUNCH_CHECK();
+    return LF_OK;
+}
+
+int channel_stage(lf_model *m)
+{
+    cudaStream_t st = lf::stream();
+    LF_CHECK(refresh_params(m));
+    lf_graph *g = m->g_ch;
+    ChanPtrs C;
+    memset(&C, 0, sizeof(C));
+    C.n = (int32_t)m->n;
+    C.lev = g->lev_of_pos.p;
+    C.cfirst = g->cfirst.p;
+    FIELD(qk, "ChanQKin");
+    FIELD(m3, "ChanM3Kin");
+    FIELD(sd, "sumDisDay");
+    FIELD(cq, "ChanQ");
+    FIELD(a, "__aCh");
+    FIELD(L, "ChanLength");
+    FIELD(al, "ChannelAlpha");
+    FIELD(side, "ToChanM3RunoffDt");
+    C.Qk = qk;
+    C.M3 = m3;
+    C.sumDis = sd;
+    C.ChanQ = cq;
+    C.a = a;
+    C.L = L;
+    C.alpha = al;
+    C.sideDt = side;
+    LF_CHECK(internal(m, "ChanQKin__r0", CHAN, &C.Qr0));
+    LF_CHECK(internal(m, "ChanQKin__r1", CHAN, &C.Qr1));
+    uint8_t *isch = nullptr, *atlast = nullptr;
+    LF_CHECK(flag_buf(m, "IsChannelKinematic", &isch));
+    LF_CHECK(flag_buf(m, "AtLastPointC", &atlast));
+    C.isChan = isch;
+    C.InvDtRouting = 1 / m->DtRouting;
+    C.S = m->cfg.NoRoutSteps;
+    C.split = m->cfg.SplitRouting;
+    C.P.beta = m->cfg.Beta;
+    C.P.inv_beta = 1 / m->cfg.Beta;
+    C.P.b_minus_1 = m->cfg.Beta - 1;
+    double *m32 = nullptr, *c2s = nullptr;
+    if (C.split) {
+        FIELD(q2k, "Chan2QKin");
+        FIELD(m32_, "Chan2M3Kin");
+        FIELD(cs2a, "CrossSection2Area");
+        FIELD(s1, "Sideflow1Chan");
+        FIELD(snl, "sumDisDay_NOTlast");
+        FIELD(a2, "__aCh2");
+        FIELD(al2, "ChannelAlpha2");
+        FIELD(ql, "QLimit");
+        FIELD(ml, "M3Limit");
+        FIELD(c2s_, "Chan2M3Start");
+        FIELD(c2q, "Chan2QStart");
+        C.Q2k = q2k;
+        C.M32 = m32_;
+        C.CS2A = cs2a;
+        C.S1 = s1;
+        C.sumNotLast = snl;
+        C.a2 = a2;
+        C.alpha2 = al2;
+        C.QLimit = ql;
+        C.M3Limit = ml;
+        C.C2M3Start = c2s_;
+        C.C2QStart = c2q;
+        m32 = m32_;
+        c2s = c2s_;
+        LF_CHECK(internal(m, "Chan2QKin__r0", CHAN, &C.Q2r0));
+        LF_CHECK(internal(m, "Chan2QKin__r1", CHAN, &C.Q2r1));
+    }
+    // isolated pixels (no link at all): one launch, all sub-steps in registers
+    const std::vector<int32_t> &ls = g->h_level_start;
+    int Lc = g->n_orders, S = C.S;
+    int iso_lo = (int)(m->n - g->n_isolated), iso_hi = (int)m->n;
+    if (iso_hi > iso_lo) {
+        k_chan_isolated<<<lf::blocks_for(iso_hi - iso_lo, CH_THREADS), CH_THREADS, 0, st>>>(C, iso_lo, iso_hi);
+        LF_LAUNCH_CHECK();
+    }
+    // the connected network: space-time wavefront over (level, sub-step)
+    auto level_end = [&](int l) { return l == Lc - 1 ? iso_lo : ls[l + 1]; };
+    for (int d = 0; d < Lc + S - 1; ++d) {
+        int lo_lev = d - S + 1 > 0 ? d - S + 1 : 0;
+        int hi_lev = d < Lc - 1 ? d : Lc - 1;
+        int lo = ls[lo_lev], hi = level_end(hi_lev);
+        if (hi <= lo) continue;
+        k_chan_diagonal<<<lf::blocks_for(hi - lo, CH_THREADS), CH_THREADS, 0, st>>>(C, lo, hi, d);
+        LF_LAUNCH_CHECK();
+    }
+    FIELD(chm3, "ChanM3");
+    FIELD(tcs, "TotalCrossSectionArea");
+    FIELD(sdis, "sumDis");
+    FIELD(qavg, "ChanQAvg");
+    FIELD(dout, "DischargeM3Out");
+    double *fv = nullptr, *td = nullptr, *pa = nullptr;
+    if (m->cfg.diagnostics) {
+        FIELD(fv_, "FlowVelocity");
+        FIELD(td_, "TravelDistance");
+        FIELD(pa_, "PixelArea");
+        fv = fv_;
+        td = td_;
+        pa = pa_;
+    }
+    k_chan_post<<<lf::blocks_for(m->n, 256), 256, 0, st>>>((int)m->n, C.split, S, m->cfg.DtSec, m3, m32, c2s, L, sd, cq, qk, atlast,
+                                                           pa, chm3, tcs, sdis, qavg, dout, fv, td);
+    LF_LAUNCH_CHECK();
+    return LF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lf_model_create(const lf_model_config *cfg, const uint8_t *land_mask, const double *ldd_to_chan,
+                    const double *ldd_kinematic, lf_model **out)
+{
+    if (!cfg || !land_mask || !ldd_to_chan || !ldd_kinematic || !out) {
+        lf::set_error("lf_model_create: null pointer");
+        return LF_ERR_INVALID;
+    }
+    if (!(cfg->DtSec > 0) || !(cfg->Beta > 0) || cfg->NoRoutSteps < 1 || !(cfg->PixelLength > 0) ||
+        !(cfg->CourantCrit > 0)) {
+        lf::set_error("lf_model_create: DtSec, Beta, PixelLength, CourantCrit must be > 0 and NoRoutSteps >= 1");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    *out = nullptr;
+    std::unique_ptr<lf_model> m(new lf_model());
+    m->cfg = *cfg;
+    m->DtDay = cfg->DtSec / 86400.;
+    m->DtRouting = cfg->DtSec / cfg->NoRoutSteps;
+    LF_CHECK(lf_ldd_build(ldd_to_chan, land_mask, cfg->rows, cfg->cols, &m->g_of));
+    LF_CHECK(lf_ldd_build(ldd_kinematic, land_mask, cfg->rows, cfg->cols, &m->g_ch));
+    m->n = m->g_of->n;
+    LF_CHECK(m->stage.alloc((size_t)3 * m->n));
+    LF_CHECK(m->stage_u8.alloc(m->n));
+    LF_CHECK(m->soil_to_chan.alloc(m->n));
+    k_soil_to_chan<<<lf::blocks_for(m->n, 256), 256, 0, lf::stream()>>>(m->g_of->pix_of_pos.p, m->g_ch->pos_of_pix.p,
+                                                                        m->soil_to_chan.p, m->n);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaStreamSynchronize(lf::stream()));
+    *out = m.release();
+    return LF_OK;
+}
+
+int lf_model_info(const lf_model *m, int64_t *n_pixels, int64_t *levels_overland, int64_t *levels_channel,
+                  int64_t *isolated_channel_pixels, int64_t *device_bytes)
+{
+    if (!m) {
+        lf::set_error("lf_model_info: null model");
+        return LF_ERR_INVALID;
+    }
+    if (n_pixels) *n_pixels = m->n;
+    if (levels_overland) *levels_overland = m->g_of->n_orders;
+    if (levels_channel) *levels_channel = m->g_ch->n_orders;
+    if (isolated_channel_pixels) *isolated_channel_pixels = m->g_ch->n_isolated;
+    if (device_bytes) *device_bytes = m->bytes;
+    return LF_OK;
+}
+
+int lf_model_set(lf_model *m, const char *name, const double *values, int64_t count)
+{
+    if (!m || !name || !values) {
+        lf::set_error("lf_model_set: null pointer");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    Field *f = nullptr;
+    LF_CHECK(field(m, name, &f));
+    if (count != (int64_t)f->rows * m->n) {
+        lf::set_error("lf_model_set(%s): expected %lld values, got %lld", name, (long long)f->rows * m->n, (long long)count);
+        return LF_ERR_INVALID;
+    }
+    cudaStream_t st = lf::stream();
+    const int32_t *pop = f->order == SOIL ? m->g_of->pix_of_pos.p : m->g_ch->pix_of_pos.p;
+    LF_CUDA(cudaMemcpyAsync(m->stage.p, values, count * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_rows_to_pos<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(m->stage.p, f->buf.p, pop, m->n, f->rows);
+    LF_LAUNCH_CHECK();
+    if (f->landuse) {
+        // rows that repeat an earlier land use share its storage row (Irrigated == Rainfed without a third map,
+        // Lisflood_initial.py:371-391): the kernel then re-reads cached lines instead of new HBM bytes
+        for (int r = 0; r < 3; ++r) {
+            f->row_index[r] = r;
+            for (int q = 0; q < r; ++q)
+                if (memcmp(values + (int64_t)r * m->n, values + (int64_t)q * m->n, m->n * sizeof(double)) == 0) {
+                    f->row_index[r] = f->row_index[q];
+                    break;
+                }
+        }
+    }
+    if (strcmp(name, "OFAlpha") == 0 || strcmp(name, "ChannelAlpha") == 0 || strcmp(name, "ChannelAlpha2") == 0 ||
+        strcmp(name, "ChanLength") == 0)
+        m->params_dirty = true;
+    LF_CUDA(cudaStreamSynchronize(st));
+    return LF_OK;
+}
+
+int lf_model_get(lf_model *m, const char *name, double *values, int64_t count)
+{
+    if (!m || !name || !values) {
+        lf::set_error("lf_model_get: null pointer");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    Field *f = nullptr;
+    LF_CHECK(field(m, name, &f));
+    if (count != (int64_t)f->rows * m->n) {
+        lf::set_error("lf_model_get(%s): expected %lld values, got %lld", name, (long long)f->rows * m->n, (long long)count);
+        return LF_ERR_INVALID;
+    }
+    cudaStream_t st = lf::stream();
+    const int32_t *pos = f->order == SOIL ? m->g_of->pos_of_pix.p : m->g_ch->pos_of_pix.p;
+    k_rows_to_pix<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(f->buf.p, m->stage.p, pos, m->n, f->rows);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaMemcpyAsync(values, m->stage.p, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaStreamSynchronize(st));
+    return LF_OK;
+}
+
+int lf_model_set_flags(lf_model *m, const char *name, const uint8_t *values, int64_t count)
+{
+    if (!m || !name || !values) {
+        lf::set_error("lf_model_set_flags: null pointer");
+        return LF_ERR_INVALID;
+    }
+    Order order;
+    if (strcmp(name, "isFrozenSoil") == 0 || strcmp(name, "IsChannel") == 0) order = SOIL;
+    else if (strcmp(name, "IsChannelKinematic") == 0 || strcmp(name, "AtLastPointC") == 0) order = CHAN;
+    else {
+        lf::set_error("lf_model_set_flags: unknown flag map '%s'", name);
+        return LF_ERR_INVALID;
+    }
+    if (count != m->n) {
+        lf::set_error("lf_model_set_flags(%s): expected %lld values", name, (long long)m->n);
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    uint8_t *dst = nullptr;
+    LF_CHECK(flag_buf(m, name, &dst));
+    const int32_t *pop = order == SOIL ? m->g_of->pix_of_pos.p : m->g_ch->pix_of_pos.p;
+    LF_CUDA(cudaMemcpyAsync(m->stage_u8.p, values, count, cudaMemcpyHostToDevice, st));
+    k_u8_to_pos<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(m->stage_u8.p, dst, pop, m->n);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaStreamSynchronize(st));
+    return LF_OK;
+}
+
+int lf_model_soil(lf_model *m)
+{
+    if (!m) {
+        lf::set_error("lf_model_soil: null model");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    return soil_stage(m);
+}
+int lf_model_surface_routing(lf_model *m)
+{
+    if (!m) {
+        lf::set_error("lf_model_surface_routing: null model");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    return surface_stage(m);
+}
+int lf_model_channel(lf_model *m)
+{
+    if (!m) {
+        lf::set_error("lf_model_channel: null model");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    LF_CHECK(channel_stage(m));
+    m->steps += 1;
+    return LF_OK;
+}
+int lf_model_step(lf_model *m)
+{
+    if (!m) {
+        lf::set_error("lf_model_step: null model");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    LF_CHECK(soil_stage(m));
+    LF_CHECK(surface_stage(m));
+    LF_CHECK(channel_stage(m));
+    m->steps += 1;
+    return LF_OK;
+}
+
+void lf_model_destroy(lf_model *m) { delete m; }
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+"""HotPathModel -- the device-resident model object of the hot path.
+
+It plays the role of the reference's shared model object `self.var` for the modules on the hot path
+(reference: src/lisflood/Lisflood_dynamic.py:114-229; attribute names: SURVEY.md §A.3): every map lives in
+HBM inside one `lf_model` (C ABI, include/lisflood_b200.h) and is translated to / from the reference's
+compressed float64[N] (or (3, N)) NumPy arrays only when Python reads or writes the attribute.  The HydroModule
+mirrors in lisflood_code_b200/hydrological_modules/ drive it with the reference's call protocol.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .global_modules.add1 import NumpyModified
+
+VEG_DIMS = ["vegetation", "pixel"]
+LU_DIMS = ["landuse", "pixel"]
+
+# maps the model needs before the first step (name -> rows)
+PARAMETERS = {
+    "b_Xinanjiang": 1, "PowerPrefFlow": 1, "UpperZoneK": 1, "GwPercStep": 1, "LowerZoneK": 1, "LZThreshold": 1,
+    "GwLossStep": 1, "SoilFraction": 3, "DirectRunoffFraction": 1, "WaterFraction": 1, "MMtoM3": 1, "PixelArea": 1,
+    "KSat1a": 3, "KSat1b": 3, "KSat2": 3, "GenuInvM1a": 3, "GenuInvM1b": 3, "GenuInvM2": 3, "WRes1a": 3, "WRes1b": 3,
+    "WRes2": 3, "WS1a": 3, "WS1b": 3, "WS2": 3, "WWP1a": 3, "WWP1b": 3, "WWP2": 3, "WFC1a": 3, "WFC1b": 3, "WFC2": 3,
+    "SoilDepth1a": 3, "SoilDepth1b": 3, "SoilDepth2": 3, "CropCoef": 3, "CropGroupNumber": 3, "OFAlpha": 3,
+    "ChanLength": 1, "ChannelAlpha": 1,
+}
+SPLIT_PARAMETERS = {"ChannelAlpha2": 1, "QLimit": 1, "M3Limit": 1, "Chan2M3Start": 1, "Chan2QStart": 1}
+STATE = {
+    "CumInterception": 3, "W1a": 3, "W1b": 3, "W2": 3, "UZ": 3, "DSLR": 3, "LZ": 1, "CumInterSealed": 1, "LZInflowCUM": 1,
+    "OFQOther": 1, "OFQForest": 1, "OFQDirect": 1, "ChanQKin": 1, "ChanM3Kin": 1, "ChanQ": 1,
+}
+SPLIT_STATE = {"Chan2QKin": 1, "Chan2M3Kin": 1, "CrossSection2Area": 1, "Sideflow1Chan": 1}
+FORCING = {"Rain": 1, "SnowMelt": 1, "ETRef": 1, "EWRef": 1, "ESRef": 1, "LAI": 3, "LAITerm": 3}
+FLAGS = ("isFrozenSoil", "IsChannel", "IsChannelKinematic", "AtLastPointC")
+DIAGNOSTIC_ONLY = ("WWP2", "WFC2", "SoilDepth1a", "SoilDepth1b", "SoilDepth2", "PixelArea")
+
+
+class HotPathModel(object):
+    def __init__(self, S, diagnostics=False):
+        """S: dict with the reference's attribute names (see synthetic.full_stack for the full list)."""
+        L = _capi.lib()
+        mask = np.ascontiguousarray(S["mask"]).astype(np.uint8)
+        cfg = _capi.ModelConfig()
+        cfg.rows, cfg.cols = mask.shape
+        cfg.DtSec, cfg.Beta, cfg.PixelLength = float(S["DtSec"]), float(S["Beta"]), float(S["PixelLength"])
+        cfg.NoRoutSteps, cfg.SplitRouting = int(S["NoRoutSteps"]), 1 if S.get("SplitRouting") else 0
+        cfg.CourantCrit, cfg.AvWaterThreshold = float(S["CourantCrit"]), float(S["AvWaterThreshold"])
+        cfg.LeafDrainageK, cfg.DrainedFraction = float(S["LeafDrainageK"]), float(S["DrainedFraction"])
+        cfg.SMaxSealed = float(S["SMaxSealed"])
+        cfg.diagnostics = 1 if diagnostics else 0
+        self.__dict__["_h"] = C.c_void_p()
+        self.__dict__["diagnostics"] = bool(diagnostics)
+        self.__dict__["split"] = bool(S.get("SplitRouting"))
+        self.__dict__["N"] = int(mask.sum())
+        h = C.c_void_p()
+        _capi.check(L.lf_model_create(C.byref(cfg), mask.ravel(), np.ascontiguousarray(S["LddToChan"], np.float64),
+                                      np.ascontiguousarray(S["LddKinematic"], np.float64), C.byref(h)))
+        self.__dict__["_h"] = h
+        self.__dict__["_rows"] = {}
+        todo = dict(PARAMETERS)
+        todo.update(STATE)
+        if self.split:
+            todo.update(SPLIT_PARAMETERS)
+            todo.update(SPLIT_STATE)
+        for name, rows in todo.items():
+            if name in DIAGNOSTIC_ONLY and not diagnostics:
+                continue
+            if name in S:
+                self.set(name, S[name], rows)
+        for name in FLAGS:
+            if name in S:
+                self.set_flags(name, S[name])
+
+    # ---- raw access --------------------------------------------------------------------------------
+    def set(self, name, values, rows=None):
+        n = self.N
+        a = np.asarray(values, np.float64)
+        if rows is None:
+            rows = 3 if (a.ndim == 2) else 1
+        a = np.ascontiguousarray(np.broadcast_to(a, (rows, n) if rows > 1 else (n,)))
+        self._rows[name] = rows
+        _capi.check(_capi.lib().lf_model_set(self._h, name.encode(), a.ravel(), a.size))
+
+    def get(self, name, rows=None):
+        if rows is None:
+            rows = self._rows.get(name, 1)
+        out = np.empty((rows, self.N) if rows > 1 else (self.N,), np.float64)
+        _capi.check(_capi.lib().lf_model_get(self._h, name.encode(), out.reshape(-1), out.size))
+        return out
+
+    def set_flags(self, name, values):
+        a = np.ascontiguousarray(values).astype(np.uint8)
+        _capi.check(_capi.lib().lf_model_set_flags(self._h, name.encode(), a, a.size))
+
+    def set_forcing(self, F):
+        """Meteorological input of the coming step (what readmeteo/snow/frost/leafarea leave on self.var)."""
+        for name, rows in FORCING.items():
+            self.set(name, F[name], rows)
+        self.set_flags("isFrozenSoil", F["isFrozenSoil"])
+
+    # ---- stages ---------------------------------------------------------------------------------------
+    def soil(self):
+        _capi.check(_capi.lib().lf_model_soil(self._h))
+
+    def surface_routing(self):
+        _capi.check(_capi.lib().lf_model_surface_routing(self._h))
+
+    def channel(self):
+        _capi.check(_capi.lib().lf_model_channel(self._h))
+
+    def step(self, F=None):
+        if F is not None:
+            self.set_forcing(F)
+        _capi.check(_capi.lib().lf_model_step(self._h))
+
+    def info(self):
+        v = [C.c_int64() for _ in range(5)]
+        _capi.check(_capi.lib().lf_model_info(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("n_pixels", "levels_overland", "levels_channel", "isolated_channel_pixels", "device_bytes"),
+                        [x.value for x in v]))
+
+    # ---- attribute protocol of the reference's model object ----------------------------------------------
+    _THREE_ROWS = set(k for d in (PARAMETERS, STATE, FORCING) for k, r in d.items() if r == 3) | {
+        "Interception", "TaInterception", "LeafDrainage", "potential_transpiration", "Ta", "ESAct", "PrefFlow",
+        "Infiltration", "AvailableWaterForInfiltration", "SeepTopToSubA", "SeepTopToSubB", "SeepSubToGW", "Theta1a",
+        "Theta1b", "Theta2", "Sat1a", "Sat1b", "Sat1", "Sat2", "UZOutflow", "GwPercUZLZ", "RWS", "Theta", "SurfaceRunSoil",
+        "W1"}
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        rows = 3 if name in self._THREE_ROWS else 1
+        try:
+            a = self.get(name, rows)
+        except _capi.LisfloodB200Error as e:
+            if e.code == _capi.LF_ERR_INVALID:
+                raise AttributeError(name)
+            raise
+        return NumpyModified(a, VEG_DIMS) if rows == 3 else a
+
+    def __setattr__(self, name, value):
+        if name.startswith("_"):
+            self.__dict__[name] = value
+            return
+        if name in FLAGS:
+            self.set_flags(name, value)
+        else:
+            self.set(name, value, 3 if name in self._THREE_ROWS else 1)
+
+    def close(self):
+        L = _capi._lib
+        if L is not None and self.__dict__.get("_h"):
+            L.lf_model_destroy(self._h)
+            self.__dict__["_h"] = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
