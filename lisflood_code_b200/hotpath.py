@@ -36,6 +36,13 @@ FLAGS = ("isFrozenSoil", "IsChannel", "IsChannelKinematic", "AtLastPointC")
 DIAGNOSTIC_ONLY = ("WWP2", "WFC2", "SoilDepth1a", "SoilDepth1b", "SoilDepth2", "PixelArea")
 
 
+THREE_ROWS = frozenset(k for d in (PARAMETERS, STATE, FORCING) for k, r in d.items() if r == 3) | {
+    "Interception", "TaInterception", "LeafDrainage", "potential_transpiration", "Ta", "ESAct", "PrefFlow",
+    "Infiltration", "AvailableWaterForInfiltration", "SeepTopToSubA", "SeepTopToSubB", "SeepSubToGW", "Theta1a",
+    "Theta1b", "Theta2", "Sat1a", "Sat1b", "Sat1", "Sat2", "UZOutflow", "GwPercUZLZ", "RWS", "Theta", "SurfaceRunSoil",
+    "W1"}
+
+
 class HotPathModel(object):
     def __init__(self, S, diagnostics=False):
         """S: dict with the reference's attribute names (see synthetic.full_stack for the full list)."""
@@ -83,6 +90,12 @@ class HotPathModel(object):
         _capi.check(_capi.lib().lf_model_set(self._h, name.encode(), a.ravel(), a.size))
 
     def get(self, name, rows=None):
+        if name in ("LZOutflowToChannelPixel", "LZOutflowToChannel"):   # groundwater.py:142,180
+            name = "LZOutflow"
+        elif name == "M3all":                                           # surface_routing.py:196
+            return self.get("OFM3Direct") + self.get("OFM3Other") + self.get("OFM3Forest")
+        elif name == "WaterDepth":                                      # surface_routing.py:203
+            return self.get("M3all") * (1 / self.get("MMtoM3"))
         if rows is None:
             rows = self._rows.get(name, 1)
         out = np.empty((rows, self.N) if rows > 1 else (self.N,), np.float64)
@@ -121,16 +134,10 @@ class HotPathModel(object):
                         [x.value for x in v]))
 
     # ---- attribute protocol of the reference's model object ----------------------------------------------
-    _THREE_ROWS = set(k for d in (PARAMETERS, STATE, FORCING) for k, r in d.items() if r == 3) | {
-        "Interception", "TaInterception", "LeafDrainage", "potential_transpiration", "Ta", "ESAct", "PrefFlow",
-        "Infiltration", "AvailableWaterForInfiltration", "SeepTopToSubA", "SeepTopToSubB", "SeepSubToGW", "Theta1a",
-        "Theta1b", "Theta2", "Sat1a", "Sat1b", "Sat1", "Sat2", "UZOutflow", "GwPercUZLZ", "RWS", "Theta", "SurfaceRunSoil",
-        "W1"}
-
     def __getattr__(self, name):
         if name.startswith("_"):
             raise AttributeError(name)
-        rows = 3 if name in self._THREE_ROWS else 1
+        rows = 3 if name in THREE_ROWS else 1
         try:
             a = self.get(name, rows)
         except _capi.LisfloodB200Error as e:
@@ -146,7 +153,7 @@ class HotPathModel(object):
         if name in FLAGS:
             self.set_flags(name, value)
         else:
-            self.set(name, value, 3 if name in self._THREE_ROWS else 1)
+            self.set(name, value, 3 if name in THREE_ROWS else 1)
 
     def close(self):
         L = _capi._lib

@@ -56,3 +56,9 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_host_modules_import():
+    from lisflood_code_b200 import hotpath, synthetic  # noqa: F401
+    from lisflood_code_b200.global_modules import add1, ldd_ops  # noqa: F401
+    assert "W1a" in hotpath.THREE_ROWS and "LZ" not in hotpath.THREE_ROWS
