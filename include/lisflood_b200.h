@@ -11,6 +11,8 @@
  *     thread-local description of the last failure.  No C++ exception crosses the ABI.
  *   - opaque handles own device memory; host pointers are borrowed for the duration of a call.
  *   - thread-compatible, not thread-safe (the reference drives everything from one Python thread).
+ *   - array arguments may be HOST pointers or DEVICE pointers of the same CUDA context (unified virtual
+ *     addressing; the library copies with cudaMemcpyDefault) unless stated otherwise.
  *   - all floating point is IEEE float64; "compressed" arrays are the reference's 1-D arrays of
  *     active pixels in row-major order of the mask (global_modules/add1.py:268-282).
  *   - reference citations are relative to /root/reference/src/lisflood/.
@@ -77,6 +79,9 @@ int lf_graph_export(const lf_graph *g, int64_t *pixels_ordered, int64_t *order_s
 /* Internal storage order ("position" = breadth-first layout from the outlets):
  * pixel_of_position i32[N], level_start i32[n_orders+1].  For tests / diagnostics. */
 int lf_graph_layout(const lf_graph *g, int32_t *pixel_of_position, int32_t *level_start);
+/* PCRaster accuflux(ldd, x): downstream-accumulated sum of x including the cell itself, f64[N] compressed
+ * (init-time operator of the reference, hydrological_modules/routing.py:98). */
+int lf_graph_accuflux(const lf_graph *g, const double *x, double *out);
 void lf_graph_destroy(lf_graph *g);
 
 /* ---------------------------------------------------------------------------------------------
@@ -149,6 +154,10 @@ int lf_model_soil(lf_model *m);
 int lf_model_surface_routing(lf_model *m);
 int lf_model_channel(lf_model *m);
 int lf_model_step(lf_model *m);
+/* Device time (CUDA events on the library stream) spent in the three stages of lf_model_step since the last
+ * reset, in milliseconds, and the number of steps they cover.  Synchronises. */
+int lf_model_stage_times(lf_model *m, int reset, double *soil_ms, double *overland_ms, double *channel_ms,
+                         int64_t *steps);
 void lf_model_destroy(lf_model *m);
 
 #ifdef __cplusplus

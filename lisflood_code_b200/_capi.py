@@ -44,10 +44,11 @@ SIGNATURES = {
     "lf_launch_count": (C.c_int64, [C.c_int]),
     "lf_host_register": (C.c_int, [_vp, _i64s]),
     "lf_host_unregister": (C.c_int, [_vp]),
-    "lf_ldd_build": (C.c_int, [_f64, _u8, _i64s, _i64s, C.POINTER(_vp)]),
+    "lf_ldd_build": (C.c_int, [_vp, _vp, _i64s, _i64s, C.POINTER(_vp)]),
     "lf_graph_info": (C.c_int, [_vp, C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s)]),
     "lf_graph_export": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "lf_graph_layout": (C.c_int, [_vp, _vp, _vp]),
+    "lf_graph_accuflux": (C.c_int, [_vp, _vp, _vp]),
     "lf_graph_destroy": (None, [_vp]),
     "lf_router_create": (C.c_int, [_vp, _f64, C.c_double, _vp, C.c_double, C.c_double, _vp, C.c_int,
                                    C.POINTER(_vp)]),
@@ -57,16 +58,18 @@ SIGNATURES = {
     "lf_router_set_inflow": (C.c_int, [_vp, C.c_int, _f64]),
     "lf_router_run": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
     "lf_router_destroy": (None, [_vp]),
-    "lf_model_create": (C.c_int, [_vp, _u8, _f64, _f64, C.POINTER(_vp)]),
+    "lf_model_create": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "lf_model_info": (C.c_int, [_vp, C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s),
                                 C.POINTER(_i64s)]),
-    "lf_model_set": (C.c_int, [_vp, C.c_char_p, _f64, _i64s]),
-    "lf_model_get": (C.c_int, [_vp, C.c_char_p, _f64, _i64s]),
-    "lf_model_set_flags": (C.c_int, [_vp, C.c_char_p, _u8, _i64s]),
+    "lf_model_set": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
+    "lf_model_get": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
+    "lf_model_set_flags": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
     "lf_model_soil": (C.c_int, [_vp]),
     "lf_model_surface_routing": (C.c_int, [_vp]),
     "lf_model_channel": (C.c_int, [_vp]),
     "lf_model_step": (C.c_int, [_vp]),
+    "lf_model_stage_times": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double), C.POINTER(_i64s)]),
     "lf_model_destroy": (None, [_vp]),
 }
 
@@ -113,7 +116,14 @@ def check(rc):
 
 
 def ptr(a):
-    return None if a is None else a.ctypes.data_as(_vp)
+    """ctypes pointer of a NumPy array, a torch tensor (host or CUDA) or a raw address."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return _vp(a)
+    if hasattr(a, "data_ptr"):
+        return _vp(a.data_ptr())
+    return a.ctypes.data_as(_vp)
 
 
 def device_info():

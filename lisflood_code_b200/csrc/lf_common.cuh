@@ -69,6 +69,17 @@ struct DevBuf {
     }
 };
 
+// true when p is device (or managed) memory; host pointers (pageable or pinned) give false
+inline bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace lf

@@ -272,6 +272,22 @@ __global__ void k_bfs_place(const int32_t *__restrict__ scan, const uint8_t *__r
     if (nups[p]) place_children(p, first, dir2d, lp, cell_of_pix, pix_of_pos, pos_of_pix, rows, cols);
 }
 
+// accuflux: acc[i] = x[i] + sum of acc over the upstream positions (PCRaster accuflux)
+__global__ void k_accuflux_level(double *__restrict__ acc, const int32_t *__restrict__ cfirst, int lo, int hi)
+{
+    int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    double s = acc[i];
+    for (int k = cfirst[i]; k < cfirst[i + 1]; ++k) s += acc[k];
+    acc[i] = s;
+}
+__global__ void k_gather_f64(const double *__restrict__ src, double *__restrict__ dst, const int32_t *__restrict__ idx,
+                             int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
 // ---- export kernels (reference-shaped int64 / float64 arrays) ----
 __global__ void k_export_i64(const int32_t *__restrict__ src, int64_t *__restrict__ dst, int64_t n)
 {
@@ -322,7 +338,7 @@ static int build_graph(const double *ldd_codes, const uint8_t *land_mask, int64_
     // ---- 1. mask -> compressed indices
     DevBuf<uint8_t> d_mask;
     LF_CHECK(d_mask.alloc(ncell));
-    LF_CUDA(cudaMemcpyAsync(d_mask.p, land_mask, ncell, cudaMemcpyHostToDevice, st));
+    LF_CUDA(cudaMemcpyAsync(d_mask.p, land_mask, ncell, cudaMemcpyDefault, st));
     LF_CHECK(g->land_points.alloc(ncell + 1));
     DevBuf<uint8_t> d_tmp;
     size_t tmp_bytes = 0;
@@ -334,7 +350,8 @@ static int build_graph(const double *ldd_codes, const uint8_t *land_mask, int64_
         lf::count_launch(2);
     }
     int32_t last_scan = 0;
-    uint8_t last_mask = land_mask[ncell - 1];
+    uint8_t last_mask = 0;
+    LF_CUDA(cudaMemcpyAsync(&last_mask, d_mask.p + (ncell - 1), 1, cudaMemcpyDeviceToHost, st));
     LF_CUDA(cudaMemcpyAsync(&last_scan, g->land_points.p + (ncell - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     LF_CUDA(cudaStreamSynchronize(st));
     int64_t n = (int64_t)last_scan + (last_mask ? 1 : 0);
@@ -350,7 +367,7 @@ static int build_graph(const double *ldd_codes, const uint8_t *land_mask, int64_
     // ---- 2. decode
     DevBuf<double> d_codes;
     LF_CHECK(d_codes.alloc(n));
-    LF_CUDA(cudaMemcpyAsync(d_codes.p, ldd_codes, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    LF_CUDA(cudaMemcpyAsync(d_codes.p, ldd_codes, n * sizeof(double), cudaMemcpyDefault, st));
     LF_CHECK(g->dir2d.alloc(ncell));
     LF_CUDA(cudaMemsetAsync(g->dir2d.p, 9, ncell, st));
     DevBuf<int> d_flag;
@@ -639,6 +656,35 @@ int lf_graph_layout(const lf_graph *g, int32_t *pixel_of_position, int32_t *leve
         LF_CUDA(cudaStreamSynchronize(st));
     }
     if (level_start) memcpy(level_start, g->h_level_start.data(), (g->n_orders + 1) * sizeof(int32_t));
+    return LF_OK;
+}
+
+int lf_graph_accuflux(const lf_graph *g, const double *x, double *out)
+{
+    if (!g || !x || !out) {
+        lf::set_error("lf_graph_accuflux: null pointer");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    int64_t n = g->n;
+    DevBuf<double> a, b;
+    LF_CHECK(a.alloc(n));
+    LF_CHECK(b.alloc(n));
+    LF_CUDA(cudaMemcpyAsync(a.p, x, n * sizeof(double), cudaMemcpyDefault, st));
+    k_gather_f64<<<blocks_for(n, 256), 256, 0, st>>>(a.p, b.p, g->pix_of_pos.p, n);  // to position order
+    LF_LAUNCH_CHECK();
+    const std::vector<int32_t> &ls = g->h_level_start;
+    for (int l = 1; l < g->n_orders; ++l) {
+        int lo = ls[l], hi = ls[l + 1];
+        if (hi <= lo) continue;
+        k_accuflux_level<<<blocks_for(hi - lo, 256), 256, 0, st>>>(b.p, g->cfirst.p, lo, hi);
+        LF_LAUNCH_CHECK();
+    }
+    k_gather_f64<<<blocks_for(n, 256), 256, 0, st>>>(b.p, a.p, g->pos_of_pix.p, n);  // back to compressed order
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaMemcpyAsync(out, a.p, n * sizeof(double), cudaMemcpyDefault, st));
+    LF_CUDA(cudaStreamSynchronize(st));
     return LF_OK;
 }
 

@@ -192,7 +192,7 @@ int lf_router_create(lf_graph *g, const double *alpha, double beta, const double
         cudaMemsetAsync(r->q[s].p, 0, n * sizeof(double), st);
     }
     if (r->dx_is_array) {
-        cudaError_t e = cudaMemcpyAsync(r->stage_b.p, dx, n * sizeof(double), cudaMemcpyHostToDevice, st);
+        cudaError_t e = cudaMemcpyAsync(r->stage_b.p, dx, n * sizeof(double), cudaMemcpyDefault, st);
         if (e != cudaSuccess) {
             lf::set_error("lf_router_create: copy of space_delta failed: %s", cudaGetErrorString(e));
             return fail(LF_ERR_CUDA);
@@ -200,7 +200,7 @@ int lf_router_create(lf_graph *g, const double *alpha, double beta, const double
     }
     for (int s = 0; s < nsec; ++s) {
         const double *al = s == 0 ? alpha : alpha_floodplains;
-        cudaError_t e = cudaMemcpyAsync(r->stage_a.p, al, n * sizeof(double), cudaMemcpyHostToDevice, st);
+        cudaError_t e = cudaMemcpyAsync(r->stage_a.p, al, n * sizeof(double), cudaMemcpyDefault, st);
         if (e != cudaSuccess) {
             lf::set_error("lf_router_create: copy of alpha failed: %s", cudaGetErrorString(e));
             return fail(LF_ERR_CUDA);
@@ -229,7 +229,7 @@ int lf_router_set_discharge(lf_router *r, int section, const double *discharge)
     }
     LF_CHECK(lf::ensure_device());
     cudaStream_t st = lf::stream();
-    LF_CUDA(cudaMemcpyAsync(r->stage_a.p, discharge, r->n * sizeof(double), cudaMemcpyHostToDevice, st));
+    LF_CUDA(cudaMemcpyAsync(r->stage_a.p, discharge, r->n * sizeof(double), cudaMemcpyDefault, st));
     k_to_pos<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(r->stage_a.p, current_q(r, section), r->g->pix_of_pos.p, r->n);
     LF_LAUNCH_CHECK();
     LF_CUDA(cudaStreamSynchronize(st));
@@ -247,7 +247,7 @@ int lf_router_get_discharge(lf_router *r, int section, double *discharge)
     cudaStream_t st = lf::stream();
     k_to_pix<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(current_q(r, section), r->stage_a.p, r->g->pos_of_pix.p, r->n);
     LF_LAUNCH_CHECK();
-    LF_CUDA(cudaMemcpyAsync(discharge, r->stage_a.p, r->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaMemcpyAsync(discharge, r->stage_a.p, r->n * sizeof(double), cudaMemcpyDefault, st));
     LF_CUDA(cudaStreamSynchronize(st));
     return LF_OK;
 }
@@ -261,7 +261,7 @@ int lf_router_set_inflow(lf_router *r, int section, const double *specific_later
     }
     LF_CHECK(lf::ensure_device());
     cudaStream_t st = lf::stream();
-    LF_CUDA(cudaMemcpyAsync(r->stage_b.p, specific_lateral_inflow, r->n * sizeof(double), cudaMemcpyHostToDevice, st));
+    LF_CUDA(cudaMemcpyAsync(r->stage_b.p, specific_lateral_inflow, r->n * sizeof(double), cudaMemcpyDefault, st));
     k_to_pos<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(r->stage_b.p, r->q[section].p, r->g->pix_of_pos.p, r->n);
     LF_LAUNCH_CHECK();
     LF_CUDA(cudaStreamSynchronize(st));
@@ -282,7 +282,7 @@ int lf_router_run(lf_router *r, int section, int nsteps, const double *q_scale, 
     const double *d_scale = nullptr;
     if (q_scale) {
         if (r->scale.n < (size_t)nsteps) LF_CHECK(r->scale.alloc(nsteps));
-        LF_CUDA(cudaMemcpyAsync(r->scale.p, q_scale, nsteps * sizeof(double), cudaMemcpyHostToDevice, st));
+        LF_CUDA(cudaMemcpyAsync(r->scale.p, q_scale, nsteps * sizeof(double), cudaMemcpyDefault, st));
         d_scale = r->scale.p;
     }
     LF_CHECK(run_steps(r, section, nsteps, d_scale));
@@ -302,8 +302,8 @@ int lf_router_route(lf_router *r, double *discharge, const double *specific_late
     LF_CHECK(lf::ensure_device());
     cudaStream_t st = lf::stream();
     int64_t n = r->n;
-    LF_CUDA(cudaMemcpyAsync(r->stage_a.p, discharge, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    LF_CUDA(cudaMemcpyAsync(r->stage_b.p, specific_lateral_inflow, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    LF_CUDA(cudaMemcpyAsync(r->stage_a.p, discharge, n * sizeof(double), cudaMemcpyDefault, st));
+    LF_CUDA(cudaMemcpyAsync(r->stage_b.p, specific_lateral_inflow, n * sizeof(double), cudaMemcpyDefault, st));
     k_to_pos<<<lf::blocks_for(n, 256), 256, 0, st>>>(r->stage_a.p, current_q(r, section), r->g->pix_of_pos.p, n);
     LF_LAUNCH_CHECK();
     k_to_pos<<<lf::blocks_for(n, 256), 256, 0, st>>>(r->stage_b.p, r->q[section].p, r->g->pix_of_pos.p, n);

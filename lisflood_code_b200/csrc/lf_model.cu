@@ -21,6 +21,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "lf_common.cuh"
 #include "lf_kw_solve.cuh"
@@ -300,6 +301,11 @@ __global__ void k_u8_to_pos(const uint8_t *__restrict__ src, uint8_t *__restrict
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[pix_of_pos[i]];
 }
+__global__ void k_rows_differ(const double *__restrict__ a, const double *__restrict__ b, int64_t n, int *__restrict__ flag)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && a[i] != b[i]) *flag = 1;
+}
 __global__ void k_soil_to_chan(const int32_t *__restrict__ pix_of_pos_soil, const int32_t *__restrict__ pos_of_pix_chan,
                                int32_t *__restrict__ soil_to_chan, int64_t n)
 {
@@ -331,6 +337,12 @@ struct lf_model {
     lf::DevBuf<double> stage;        // 3N staging (compressed order)
     lf::DevBuf<uint8_t> stage_u8;
     lf::DevBuf<int32_t> soil_to_chan;
+    lf::DevBuf<int> flag;
+    // per-stage device timing (CUDA events on the library stream), accumulated on query
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_used;  // 4 events per recorded step: start, after soil, after overland, after channel
+    double t_soil = 0, t_of = 0, t_chan = 0;
+    int64_t t_steps = 0;
     int64_t steps = 0;               // model steps done (parity of the overland discharge buffers)
     bool params_dirty = true;        // a_dx_div_dt arrays need a rebuild
     int64_t bytes = 0;
@@ -338,6 +350,7 @@ struct lf_model {
     {
         if (g_of) lf_graph_destroy(g_of);
         if (g_ch) lf_graph_destroy(g_ch);
+        for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     }
 };
 
@@ -835,6 +848,7 @@ int lf_model_create(const lf_model_config *cfg, const uint8_t *land_mask, const 
     LF_CHECK(m->stage.alloc((size_t)3 * m->n));
     LF_CHECK(m->stage_u8.alloc(m->n));
     LF_CHECK(m->soil_to_chan.alloc(m->n));
+    LF_CHECK(m->flag.alloc(1));
     k_soil_to_chan<<<lf::blocks_for(m->n, 256), 256, 0, lf::stream()>>>(m->g_of->pix_of_pos.p, m->g_ch->pos_of_pix.p,
                                                                         m->soil_to_chan.p, m->n);
     LF_LAUNCH_CHECK();
@@ -873,19 +887,34 @@ int lf_model_set(lf_model *m, const char *name, const double *values, int64_t co
     }
     cudaStream_t st = lf::stream();
     const int32_t *pop = f->order == SOIL ? m->g_of->pix_of_pos.p : m->g_ch->pix_of_pos.p;
-    LF_CUDA(cudaMemcpyAsync(m->stage.p, values, count * sizeof(double), cudaMemcpyHostToDevice, st));
+    LF_CUDA(cudaMemcpyAsync(m->stage.p, values, count * sizeof(double), cudaMemcpyDefault, st));
     k_rows_to_pos<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(m->stage.p, f->buf.p, pop, m->n, f->rows);
     LF_LAUNCH_CHECK();
     if (f->landuse) {
         // rows that repeat an earlier land use share its storage row (Irrigated == Rainfed without a third map,
         // Lisflood_initial.py:371-391): the kernel then re-reads cached lines instead of new HBM bytes
+        const bool on_device = lf::is_device_ptr(values);
         for (int r = 0; r < 3; ++r) {
             f->row_index[r] = r;
-            for (int q = 0; q < r; ++q)
-                if (memcmp(values + (int64_t)r * m->n, values + (int64_t)q * m->n, m->n * sizeof(double)) == 0) {
+            for (int q = 0; q < r; ++q) {
+                bool same;
+                if (on_device) {
+                    int h = 0;
+                    LF_CUDA(cudaMemsetAsync(m->flag.p, 0, sizeof(int), st));
+                    k_rows_differ<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(m->stage.p + (int64_t)r * m->n,
+                                                                             m->stage.p + (int64_t)q * m->n, m->n, m->flag.p);
+                    LF_LAUNCH_CHECK();
+                    LF_CUDA(cudaMemcpyAsync(&h, m->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    LF_CUDA(cudaStreamSynchronize(st));
+                    same = h == 0;
+                } else {
+                    same = memcmp(values + (int64_t)r * m->n, values + (int64_t)q * m->n, m->n * sizeof(double)) == 0;
+                }
+                if (same) {
                     f->row_index[r] = f->row_index[q];
                     break;
                 }
+            }
         }
     }
     if (strcmp(name, "OFAlpha") == 0 || strcmp(name, "ChannelAlpha") == 0 || strcmp(name, "ChannelAlpha2") == 0 ||
@@ -912,7 +941,7 @@ int lf_model_get(lf_model *m, const char *name, double *values, int64_t count)
     const int32_t *pos = f->order == SOIL ? m->g_of->pos_of_pix.p : m->g_ch->pos_of_pix.p;
     k_rows_to_pix<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(f->buf.p, m->stage.p, pos, m->n, f->rows);
     LF_LAUNCH_CHECK();
-    LF_CUDA(cudaMemcpyAsync(values, m->stage.p, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaMemcpyAsync(values, m->stage.p, count * sizeof(double), cudaMemcpyDefault, st));
     LF_CUDA(cudaStreamSynchronize(st));
     return LF_OK;
 }
@@ -939,7 +968,7 @@ int lf_model_set_flags(lf_model *m, const char *name, const uint8_t *values, int
     uint8_t *dst = nullptr;
     LF_CHECK(flag_buf(m, name, &dst));
     const int32_t *pop = order == SOIL ? m->g_of->pix_of_pos.p : m->g_ch->pix_of_pos.p;
-    LF_CUDA(cudaMemcpyAsync(m->stage_u8.p, values, count, cudaMemcpyHostToDevice, st));
+    LF_CUDA(cudaMemcpyAsync(m->stage_u8.p, values, count, cudaMemcpyDefault, st));
     k_u8_to_pos<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(m->stage_u8.p, dst, pop, m->n);
     LF_LAUNCH_CHECK();
     LF_CUDA(cudaStreamSynchronize(st));
@@ -975,6 +1004,20 @@ int lf_model_channel(lf_model *m)
     m->steps += 1;
     return LF_OK;
 }
+static int mark(lf_model *m)
+{
+    size_t k = m->ev_used.size();
+    if (k >= 4096) return LF_OK;  // stop recording, keep running
+    if (k >= m->ev_pool.size()) {
+        cudaEvent_t e;
+        LF_CUDA(cudaEventCreate(&e));
+        m->ev_pool.push_back(e);
+    }
+    LF_CUDA(cudaEventRecord(m->ev_pool[k], lf::stream()));
+    m->ev_used.push_back((int)k);
+    return LF_OK;
+}
+
 int lf_model_step(lf_model *m)
 {
     if (!m) {
@@ -982,10 +1025,45 @@ int lf_model_step(lf_model *m)
         return LF_ERR_INVALID;
     }
     LF_CHECK(lf::ensure_device());
+    LF_CHECK(mark(m));
     LF_CHECK(soil_stage(m));
+    LF_CHECK(mark(m));
     LF_CHECK(surface_stage(m));
+    LF_CHECK(mark(m));
     LF_CHECK(channel_stage(m));
+    LF_CHECK(mark(m));
     m->steps += 1;
+    return LF_OK;
+}
+
+int lf_model_stage_times(lf_model *m, int reset, double *soil_ms, double *overland_ms, double *channel_ms,
+                         int64_t *steps)
+{
+    if (!m) {
+        lf::set_error("lf_model_stage_times: null model");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    LF_CUDA(cudaStreamSynchronize(lf::stream()));
+    for (size_t k = 0; k + 3 < m->ev_used.size(); k += 4) {
+        float a = 0, b = 0, c = 0;
+        LF_CUDA(cudaEventElapsedTime(&a, m->ev_pool[k], m->ev_pool[k + 1]));
+        LF_CUDA(cudaEventElapsedTime(&b, m->ev_pool[k + 1], m->ev_pool[k + 2]));
+        LF_CUDA(cudaEventElapsedTime(&c, m->ev_pool[k + 2], m->ev_pool[k + 3]));
+        m->t_soil += a;
+        m->t_of += b;
+        m->t_chan += c;
+        m->t_steps += 1;
+    }
+    m->ev_used.clear();
+    if (soil_ms) *soil_ms = m->t_soil;
+    if (overland_ms) *overland_ms = m->t_of;
+    if (channel_ms) *channel_ms = m->t_chan;
+    if (steps) *steps = m->t_steps;
+    if (reset) {
+        m->t_soil = m->t_of = m->t_chan = 0;
+        m->t_steps = 0;
+    }
     return LF_OK;
 }
 

@@ -47,9 +47,14 @@ class HotPathModel(object):
     def __init__(self, S, diagnostics=False):
         """S: dict with the reference's attribute names (see synthetic.full_stack for the full list)."""
         L = _capi.lib()
-        mask = np.ascontiguousarray(S["mask"]).astype(np.uint8)
+        if "mask_device" in S:
+            mask = None
+            rows_cols, n_active = (int(S["rows"]), int(S["cols"])), int(S["N"])
+        else:
+            mask = np.ascontiguousarray(S["mask"]).astype(np.uint8)
+            rows_cols, n_active = mask.shape, int(mask.sum())
         cfg = _capi.ModelConfig()
-        cfg.rows, cfg.cols = mask.shape
+        cfg.rows, cfg.cols = rows_cols
         cfg.DtSec, cfg.Beta, cfg.PixelLength = float(S["DtSec"]), float(S["Beta"]), float(S["PixelLength"])
         cfg.NoRoutSteps, cfg.SplitRouting = int(S["NoRoutSteps"]), 1 if S.get("SplitRouting") else 0
         cfg.CourantCrit, cfg.AvWaterThreshold = float(S["CourantCrit"]), float(S["AvWaterThreshold"])
@@ -59,10 +64,15 @@ class HotPathModel(object):
         self.__dict__["_h"] = C.c_void_p()
         self.__dict__["diagnostics"] = bool(diagnostics)
         self.__dict__["split"] = bool(S.get("SplitRouting"))
-        self.__dict__["N"] = int(mask.sum())
+        self.__dict__["N"] = n_active
         h = C.c_void_p()
-        _capi.check(L.lf_model_create(C.byref(cfg), mask.ravel(), np.ascontiguousarray(S["LddToChan"], np.float64),
-                                      np.ascontiguousarray(S["LddKinematic"], np.float64), C.byref(h)))
+        ldd_oc, ldd_kin = S["LddToChan"], S["LddKinematic"]
+        if not hasattr(ldd_oc, "data_ptr"):   # NumPy input; torch CUDA tensors are passed through as they are
+            ldd_oc = np.ascontiguousarray(ldd_oc, np.float64)
+            ldd_kin = np.ascontiguousarray(ldd_kin, np.float64)
+        mask_arg = S["mask_device"] if "mask_device" in S else mask
+        _capi.check(L.lf_model_create(C.byref(cfg), _capi.ptr(mask_arg), _capi.ptr(ldd_oc), _capi.ptr(ldd_kin),
+                                      C.byref(h)))
         self.__dict__["_h"] = h
         self.__dict__["_rows"] = {}
         todo = dict(PARAMETERS)
@@ -82,12 +92,19 @@ class HotPathModel(object):
     # ---- raw access --------------------------------------------------------------------------------
     def set(self, name, values, rows=None):
         n = self.N
+        if hasattr(values, "data_ptr"):   # torch tensor (host or CUDA), float64, contiguous, compressed order
+            assert values.is_contiguous() and values.element_size() == 8
+            rows = rows or (3 if values.dim() == 2 else 1)
+            assert values.numel() == rows * n, (name, values.shape)
+            self._rows[name] = rows
+            _capi.check(_capi.lib().lf_model_set(self._h, name.encode(), _capi.ptr(values), values.numel()))
+            return
         a = np.asarray(values, np.float64)
         if rows is None:
             rows = 3 if (a.ndim == 2) else 1
         a = np.ascontiguousarray(np.broadcast_to(a, (rows, n) if rows > 1 else (n,)))
         self._rows[name] = rows
-        _capi.check(_capi.lib().lf_model_set(self._h, name.encode(), a.ravel(), a.size))
+        _capi.check(_capi.lib().lf_model_set(self._h, name.encode(), _capi.ptr(a), a.size))
 
     def get(self, name, rows=None):
         if name in ("LZOutflowToChannelPixel", "LZOutflowToChannel"):   # groundwater.py:142,180
@@ -98,13 +115,21 @@ class HotPathModel(object):
             return self.get("M3all") * (1 / self.get("MMtoM3"))
         if rows is None:
             rows = self._rows.get(name, 1)
-        out = np.empty((rows, self.N) if rows > 1 else (self.N,), np.float64)
-        _capi.check(_capi.lib().lf_model_get(self._h, name.encode(), out.reshape(-1), out.size))
+        return self.get_into(name, np.empty((rows, self.N) if rows > 1 else (self.N,), np.float64))
+
+    def get_into(self, name, out):
+        """Copies a map into `out` (NumPy array or torch tensor, host or CUDA, float64, contiguous)."""
+        size = out.numel() if hasattr(out, "numel") else out.size
+        _capi.check(_capi.lib().lf_model_get(self._h, name.encode(), _capi.ptr(out), size))
         return out
 
     def set_flags(self, name, values):
+        if hasattr(values, "data_ptr"):
+            assert values.element_size() == 1 and values.is_contiguous()
+            _capi.check(_capi.lib().lf_model_set_flags(self._h, name.encode(), _capi.ptr(values), values.numel()))
+            return
         a = np.ascontiguousarray(values).astype(np.uint8)
-        _capi.check(_capi.lib().lf_model_set_flags(self._h, name.encode(), a, a.size))
+        _capi.check(_capi.lib().lf_model_set_flags(self._h, name.encode(), _capi.ptr(a), a.size))
 
     def set_forcing(self, F):
         """Meteorological input of the coming step (what readmeteo/snow/frost/leafarea leave on self.var)."""
@@ -126,6 +151,13 @@ class HotPathModel(object):
         if F is not None:
             self.set_forcing(F)
         _capi.check(_capi.lib().lf_model_step(self._h))
+
+    def stage_times(self, reset=False):
+        """Device milliseconds spent in (soil, overland, channel) stages of step() since the last reset."""
+        a, b, c, k = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        _capi.check(_capi.lib().lf_model_stage_times(self._h, 1 if reset else 0, C.byref(a), C.byref(b), C.byref(c),
+                                                     C.byref(k)))
+        return {"soil_ms": a.value, "overland_ms": b.value, "channel_ms": c.value, "steps": k.value}
 
     def info(self):
         v = [C.c_int64() for _ in range(5)]

@@ -40,7 +40,7 @@ class kinematicWave:
             raise ValueError("compressed_encoded_ldd has %d values, land_mask has %d active pixels" % (ldd.size, n))
         self.num_pixels = n
         g = C.c_void_p()
-        _capi.check(L.lf_ldd_build(ldd, mask.ravel(), mask.shape[0], mask.shape[1], C.byref(g)))
+        _capi.check(L.lf_ldd_build(_capi.ptr(ldd), _capi.ptr(mask), mask.shape[0], mask.shape[1], C.byref(g)))
         self._graph = g
         self._router = C.c_void_p()
         alpha = self._as_map(alpha_channel)
@@ -136,6 +136,13 @@ class kinematicWave:
         if out is None:
             out = np.empty(self.num_pixels, np.float64)
         _capi.check(_capi.lib().lf_router_get_discharge(self._router, self._section(section), out))
+        return out
+
+    def accuflux(self, x):
+        """PCRaster accuflux on this router's graph (downstream-accumulated sum, including the cell)."""
+        x = self._as_map(x)
+        out = np.empty_like(x)
+        _capi.check(_capi.lib().lf_graph_accuflux(self._graph, _capi.ptr(x), _capi.ptr(out)))
         return out
 
     def close(self):
