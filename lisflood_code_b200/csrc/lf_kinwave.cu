@@ -40,6 +40,24 @@ __global__ void k_to_pos(const double *__restrict__ src, double *__restrict__ ds
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[pix_of_pos[i]];
 }
+// discharge in: compressed order -> position order, Q -> z = Q^(1/5) when the router runs in 3/5 mode
+__global__ void k_q_to_pos(const double *__restrict__ src, double *__restrict__ dst,
+                           const int32_t *__restrict__ pix_of_pos, int64_t n, int quintic)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double q = src[pix_of_pos[i]];
+    dst[i] = quintic ? lfkw::z_of_q(q) : q;
+}
+// discharge out: position order -> compressed order, z -> Q = z^5
+__global__ void k_q_to_pix(const double *__restrict__ src, double *__restrict__ dst,
+                           const int32_t *__restrict__ pos_of_pix, int64_t n, int quintic)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    double v = src[pos_of_pix[p]];
+    dst[p] = quintic ? lfkw::pow5(v) : v;
+}
 // alpha -> a_dx_div_dt = alpha * dx / dt   (kinematic_wave_parallel.py:126)
 __global__ void k_make_a(const double *__restrict__ alpha, const double *__restrict__ dx, double dx_scalar,
                          double dt, double *__restrict__ a, double *__restrict__ dx_pos,
@@ -67,6 +85,7 @@ __global__ void k_nonfinite(const double *__restrict__ v, int64_t n, int *__rest
 
 // One diagonal of the space-time wavefront.  Positions [lo, hi) = levels d-S+1..d.
 constexpr int KW_THREADS = 128;
+template <bool QZ>
 __global__ void __launch_bounds__(KW_THREADS)
     k_kw_diagonal(int lo, int hi, int d, int64_t g0, const int32_t *__restrict__ lev,
                   const int32_t *__restrict__ cfirst, const double *__restrict__ a, const double *__restrict__ dx,
@@ -86,8 +105,13 @@ __global__ void __launch_bounds__(KW_THREADS)
     double lateral = qs * (dx ? dx[i] : dx_scalar);  // lateral_inflow = q * dx, kinematic_wave_parallel.py:163
     double ai = a[i];
     double U = 0.0;
-    for (int k = c0; k < c1; ++k) U += Qnew[k];  // upstream discharge of this step, slot order (tools:57-58)
-    Qnew[i] = lfkw::solve(U, qo, lateral, ai, P);
+    if (QZ) {
+        for (int k = c0; k < c1; ++k) U += lfkw::pow5(Qnew[k]);  // buffers hold z = Q^(1/5)
+        Qnew[i] = lfkw::solve_z(U, qo, lateral, ai);
+    } else {
+        for (int k = c0; k < c1; ++k) U += Qnew[k];  // upstream discharge of this step, slot order (tools:57-58)
+        Qnew[i] = lfkw::solve(U, qo, lateral, ai, P);
+    }
 }
 
 int run_steps(lf_router *r, int sec, int nsteps, const double *d_scale)
@@ -101,9 +125,15 @@ int run_steps(lf_router *r, int sec, int nsteps, const double *d_scale)
         int lo_lev = d - nsteps + 1 > 0 ? d - nsteps + 1 : 0;
         int hi_lev = d < L - 1 ? d : L - 1;
         int lo = ls[lo_lev], hi = ls[hi_lev + 1];
-        k_kw_diagonal<<<lf::blocks_for(hi - lo, KW_THREADS), KW_THREADS, 0, st>>>(
-            lo, hi, d, g0, g->lev_of_pos.p, g->cfirst.p, r->a[sec].p, r->dx_is_array ? r->dx.p : nullptr, r->dx_scalar,
-            r->q[sec].p, d_scale, r->Q[sec][0].p, r->Q[sec][1].p, r->P);
+        if (hi <= lo) continue;
+        if (r->P.quintic)
+            k_kw_diagonal<true><<<lf::blocks_for(hi - lo, KW_THREADS), KW_THREADS, 0, st>>>(
+                lo, hi, d, g0, g->lev_of_pos.p, g->cfirst.p, r->a[sec].p, r->dx_is_array ? r->dx.p : nullptr, r->dx_scalar,
+                r->q[sec].p, d_scale, r->Q[sec][0].p, r->Q[sec][1].p, r->P);
+        else
+            k_kw_diagonal<false><<<lf::blocks_for(hi - lo, KW_THREADS), KW_THREADS, 0, st>>>(
+                lo, hi, d, g0, g->lev_of_pos.p, g->cfirst.p, r->a[sec].p, r->dx_is_array ? r->dx.p : nullptr, r->dx_scalar,
+                r->q[sec].p, d_scale, r->Q[sec][0].p, r->Q[sec][1].p, r->P);
         LF_LAUNCH_CHECK();
     }
     r->steps_done[sec] = g0 + nsteps;
@@ -166,9 +196,7 @@ int lf_router_create(lf_graph *g, const double *alpha, double beta, const double
     *out = nullptr;
     r->g = g;
     r->n = g->n;
-    r->P.beta = beta;
-    r->P.inv_beta = 1 / beta;   // kinematic_wave_parallel.py:124
-    r->P.b_minus_1 = beta - 1;  // :125
+    r->P = lfkw::make_params(beta);
     r->dt = dt;
     r->dx_scalar = dx_scalar;
     r->dx_is_array = dx != nullptr;
@@ -230,7 +258,8 @@ int lf_router_set_discharge(lf_router *r, int section, const double *discharge)
     LF_CHECK(lf::ensure_device());
     cudaStream_t st = lf::stream();
     LF_CUDA(cudaMemcpyAsync(r->stage_a.p, discharge, r->n * sizeof(double), cudaMemcpyDefault, st));
-    k_to_pos<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(r->stage_a.p, current_q(r, section), r->g->pix_of_pos.p, r->n);
+    k_q_to_pos<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(r->stage_a.p, current_q(r, section), r->g->pix_of_pos.p, r->n,
+                                                          r->P.quintic);
     LF_LAUNCH_CHECK();
     LF_CUDA(cudaStreamSynchronize(st));
     return LF_OK;
@@ -245,7 +274,8 @@ int lf_router_get_discharge(lf_router *r, int section, double *discharge)
     }
     LF_CHECK(lf::ensure_device());
     cudaStream_t st = lf::stream();
-    k_to_pix<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(current_q(r, section), r->stage_a.p, r->g->pos_of_pix.p, r->n);
+    k_q_to_pix<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(current_q(r, section), r->stage_a.p, r->g->pos_of_pix.p, r->n,
+                                                          r->P.quintic);
     LF_LAUNCH_CHECK();
     LF_CUDA(cudaMemcpyAsync(discharge, r->stage_a.p, r->n * sizeof(double), cudaMemcpyDefault, st));
     LF_CUDA(cudaStreamSynchronize(st));
@@ -304,14 +334,16 @@ int lf_router_route(lf_router *r, double *discharge, const double *specific_late
     int64_t n = r->n;
     LF_CUDA(cudaMemcpyAsync(r->stage_a.p, discharge, n * sizeof(double), cudaMemcpyDefault, st));
     LF_CUDA(cudaMemcpyAsync(r->stage_b.p, specific_lateral_inflow, n * sizeof(double), cudaMemcpyDefault, st));
-    k_to_pos<<<lf::blocks_for(n, 256), 256, 0, st>>>(r->stage_a.p, current_q(r, section), r->g->pix_of_pos.p, n);
+    k_q_to_pos<<<lf::blocks_for(n, 256), 256, 0, st>>>(r->stage_a.p, current_q(r, section), r->g->pix_of_pos.p, n,
+                                                       r->P.quintic);
     LF_LAUNCH_CHECK();
     k_to_pos<<<lf::blocks_for(n, 256), 256, 0, st>>>(r->stage_b.p, r->q[section].p, r->g->pix_of_pos.p, n);
     LF_LAUNCH_CHECK();
     LF_CHECK(run_steps(r, section, 1, nullptr));
-    k_to_pix<<<lf::blocks_for(n, 256), 256, 0, st>>>(current_q(r, section), r->stage_a.p, r->g->pos_of_pix.p, n);
+    k_q_to_pix<<<lf::blocks_for(n, 256), 256, 0, st>>>(current_q(r, section), r->stage_a.p, r->g->pos_of_pix.p, n,
+                                                       r->P.quintic);
     LF_LAUNCH_CHECK();
-    LF_CUDA(cudaMemcpyAsync(discharge, r->stage_a.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaMemcpyAsync(discharge, r->stage_a.p, n * sizeof(double), cudaMemcpyDefault, st));
     LF_CHECK(nan_check(r, section, nonfinite));
     LF_CUDA(cudaStreamSynchronize(st));
     return LF_OK;

@@ -1,33 +1,61 @@
 // lf_kw_solve.cuh -- per-pixel kinematic-wave solve (device).
 //
 // Restates solve1Pixel / closureError of the reference
-// (hydrological_modules/kinematic_wave_parallel_tools.py:48-92): bracketed initial guess, then
-// Newton-Raphson on f(Q) = Q + a*Q^beta - C with Q clamped at 1e-12.
+// (hydrological_modules/kinematic_wave_parallel_tools.py:48-92): find Q >= 0 with
+//     f(Q) = Q + a*Q^beta - C = 0,   C = upstream inflow + a*Qold^beta + lateral inflow,
+// Q clamped at 1e-12 and mapped to 0 there, C <= 1e-12 -> 0.
 //
-// Differences in evaluation, all far inside the 1e-6 parity tolerance:
-//   * x^y is evaluated as exp(y*log(x)) in float64 (about 50 instructions instead of the ~200 of
-//     CUDA's pow(); relative error <= |y ln x| * 2^-52).
-//   * one power per Newton iteration: Q^beta = Q * Q^(beta-1) re-uses the derivative's power.
-//   * the reference stops when |f| <= 1e-12, when Q stops changing, or after 3000 iterations.  The
-//     same tests are kept; in addition the loop leaves as soon as the relative Newton step is below
-//     1e-8 (the iterate is then converged to < 1e-16 relative because Newton's error constant for
-//     this f is <= 0.2/Q), which avoids the reference's last "no change" confirmation iteration and
-//     its rare two-value limit cycles that would otherwise pin a whole warp for 3000 iterations.
+// Two evaluations of the same root:
+//
+//  * general beta: the reference's bracketed initial guess and Newton iteration in Q, with
+//    x^y from lf_math.cuh, one power per iteration (Q^beta = Q * Q^(beta-1)), and an extra exit when
+//    the relative Newton step is below 1e-8 (then converged to < 1e-16: the error constant of this f is
+//    <= 0.2/Q), which removes the reference's confirmation iteration and its rare 2-value limit cycles.
+//
+//  * beta == 0.6 (Manning's 3/5 -- the value LISFLOOD ships, settings `beta`): with z = Q^(1/5) every power the
+//    iteration needs is a product: Q^beta = z^3, Q^(beta-1) = 1/z^2.  The SAME Newton iterates in Q are formed
+//    (same update, clamp and stopping tests), and z is refreshed after each update by a fifth root (float seed +
+//    two Newton steps, ~20 instructions) -- no log/exp at all.  The state carried between routing steps is z, so
+//    a*Qold^beta = a*z^3 is free and the discharge handed downstream is z^5.  The reference's bracketed initial
+//    guess is evaluated in float: it only seeds the iteration, and because Newton contracts differences
+//    quadratically the iterates coincide with the reference's to < 1e-15 after three steps, so the stopping
+//    decisions (|f| <= 1e-12) fall on the same iterate.  (A pure Newton on the quintic z^5 + a z^3 - C would be
+//    cheaper still but stops on different iterates: its results differ from the reference's by up to the
+//    reference's own 1e-12 absolute tolerance, i.e. 1e-4 relative on near-dry pixels -- rejected.)
+//    ~200 instructions per solve instead of ~1400: the routing kernels move from FP64-bound towards HBM-bound.
 #pragma once
+#include "lf_math.cuh"
 
 namespace lfkw {
 
 constexpr double NEWTON_TOL = 1e-12;  // tools:26
 constexpr int MAX_ITERS = 3000;       // tools:27
+constexpr double Z_MIN = 0.0039810717055349725;  // (1e-12)^(1/5)
 
 struct Params {
     double beta, inv_beta, b_minus_1;
+    int quintic;  // beta == 0.6: state is z = Q^(1/5)
 };
 
-__device__ __forceinline__ double pw(double x, double y) { return exp(y * log(x)); }
+__host__ __device__ inline Params make_params(double beta)
+{
+    Params P;
+    P.beta = beta;
+    P.inv_beta = 1 / beta;   // kinematic_wave_parallel.py:124
+    P.b_minus_1 = beta - 1;  // :125
+    P.quintic = (beta == 0.6) ? 1 : 0;
+    return P;
+}
 
+__device__ __forceinline__ double pw(double x, double y) { return lfm::pw(x, y); }
+__device__ __forceinline__ double pow5(double z)
+{
+    const double z2 = z * z;
+    return z2 * z2 * z;
+}
+
+// ---- general beta: state is Q --------------------------------------------------------------------
 // U: sum of the (new) discharge of the upstream pixels, in slot order.
-// Returns the new discharge; *iters (optional) receives the Newton iteration count.
 __device__ __forceinline__ double solve(double U, double q_old, double lateral, double a, const Params &P)
 {
     // constant = a_dx_div_dt * Qold**b + lateral_inflow   (kinematic_wave_parallel.py:174-175)
@@ -52,6 +80,63 @@ __device__ __forceinline__ double solve(double U, double q_old, double lateral, 
     }
     if (q == NEWTON_TOL) q = 0.0;  // tools:79-80
     return q;
+}
+
+// ---- beta == 3/5: state is z = Q^(1/5) -----------------------------------------------------------
+// fifth root of q > 0 (q >= 1e-30): float seed + two Newton steps with a float reciprocal (error ~1e-16)
+__device__ __forceinline__ double root5(double q)
+{
+    double w = (double)__powf((float)q, 0.2f);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double w2 = w * w, w4 = w2 * w2;
+        const double r = (double)__frcp_rn((float)(5.0 * w4));
+        w = lfm::fma_(-lfm::fma_(w4, w, -q), r, w);
+    }
+    return w;
+}
+// z of a discharge supplied by the caller (any magnitude, 0 -> 0, negative / NaN -> NaN)
+__device__ __forceinline__ double z_of_q(double q)
+{
+    if (q > 1e-30 && q < 1e30) return root5(q);
+    if (q == 0.0) return 0.0;
+    return lfm::pw(q, 0.2);
+}
+
+// U: sum of z_k^5 over the upstream pixels; returns z_new (0 when the discharge is 0).
+// Same iterates as the reference's Newton in Q (tools:64-80); Q^beta = z^3 and Q^(beta-1) = 1/z^2 come from
+// z = Q^(1/5), refreshed after every update by root5().
+__device__ __forceinline__ double solve_z(double U, double z_old, double lateral, double a)
+{
+    const double c = U + (a * (z_old * z_old * z_old) + lateral);
+    if (c <= NEWTON_TOL) return 0.0;  // tools:60-62
+    if (!(c < 1.0e300)) return c;     // NaN / Inf propagate like in the reference (flagnancheck reports them)
+    // bracketed initial guess (tools:64-70) in float: it only seeds the iteration, the iterates merge with the
+    // reference's to < 1e-15 within three Newton steps (quadratic contraction)
+    const float cf = (float)c, af = (float)a;
+    const float t = 0.6f * af * __powf(cf, -0.4f);
+    const float secant = t <= 1.0f ? __fdividef(cf, 1.0f + t) : __fdividef(cf, 1.0f + __powf(t, 1.6666666f));
+    const float other = __powf(__fdividef(cf - secant, af), 1.6666666f);
+    const float q0 = 0.5f * (secant + other);
+    double q = (q0 > 1e-30f && q0 < 1e30f) ? (double)q0 : fmin(c, 1e30);  // degenerate a (0, inf, NaN): start at C
+    q = fmax(q, NEWTON_TOL);
+    const double ba = 0.6 * a;
+    double z = root5(q);
+    double err = q + a * (z * z * z) - c;
+    int count = 0;
+    while (fabs(err) > NEWTON_TOL && count < MAX_ITERS) {
+        const double z2 = z * z;
+        double qn = q - err * z2 / (z2 + ba);  // q - err / (1 + b*a*q^(b-1))
+        qn = fmax(qn, NEWTON_TOL);
+        const bool small = fabs(qn - q) <= 1e-8 * qn;  // includes q == prev
+        q = qn;
+        z = root5(q);
+        if (small) break;
+        err = q + a * (z * z * z) - c;
+        ++count;
+    }
+    if (q == NEWTON_TOL) return 0.0;  // tools:79-80
+    return z;
 }
 
 }  // namespace lfkw

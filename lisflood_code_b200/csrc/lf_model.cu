@@ -41,6 +41,7 @@ struct Field {
     bool landuse = false;      // (landuse, pixel) parameter: rows may be shared
     int row_index[3] = {0, 1, 2};  // storage row of land use r
     bool diag = false;
+    bool as_z = false;  // discharge map stored as z = Q^(1/5) (3/5 mode)
 };
 
 struct ChanPtrs {
@@ -51,34 +52,72 @@ struct ChanPtrs {
     const uint8_t *isChan;
     // split routing
     double *Q2k, *Q2r0, *Q2r1, *M32, *CS2A, *S1, *sumNotLast;
-    const double *a2, *alpha2, *QLimit, *M3Limit, *C2M3Start, *C2QStart;
+    const double *a2, *alpha2, *QLimit, *M3Limit, *C2M3Start, *C2QStart, *z2floor;
     double InvDtRouting;
     int S, split;
     lfkw::Params P;
 };
 
-__device__ __forceinline__ double pw(double x, double y) { return exp(y * log(x)); }
+__device__ __forceinline__ double pw(double x, double y) { return lfm::pw(x, y); }
 
 // one routing.dynamic sub-step of one pixel (hydrological_modules/routing.py:462-604).
 // U1/U2: upstream inflow of the main channel / floodplain for this sub-step.
+// In 3/5 mode (QZ) qk / q2k / qr1 / qr2 hold z = Q^(1/5) (lf_kw_solve.cuh): Q^beta = z^3 makes the volume
+// L*alpha*Q^beta free, and the reference's re-derivation ChanQKin = (ChanM3Kin/(L*alpha))^(1/beta) (:531) is the
+// identity on z except where the floodplain volume is floored at Chan2M3Start (:586-593), where z becomes z2floor.
 struct ChanLocal {
     double qk, m3, sum, q2k, m32, cs2a, s1, sumnl, chanq;
 };
 
+template <bool QZ>
 __device__ __forceinline__ void chan_substep(const ChanPtrs &C, int i, double U1, double U2, ChanLocal &X,
                                              double L, double invL, double alpha, double a, double sideDt, bool isch,
                                              double &qr1, double &qr2, double alpha2, double a2, double qlimit,
-                                             double m3limit, double c2start, double c2qstart)
+                                             double m3limit, double c2start, double c2qstart, double z2floor)
 {
     double side = isch ? sideDt * invL * C.InvDtRouting : 0.;  // :512
     if (!C.split) {
         if (isnan(side)) side = 0.;  // :523
-        double qn = lfkw::solve(U1, X.qk, side * L, a, C.P);
-        qr1 = qn;
-        X.m3 = fmax(L * alpha * pw(qn, C.P.beta), 0.0);          // :527-530
-        X.qk = pw(X.m3 * invL * (1 / alpha), C.P.inv_beta);      // :531
-        X.chanq = X.qk;
+        if (QZ) {
+            const double zn = lfkw::solve_z(U1, X.qk, side * L, a);
+            qr1 = zn;
+            X.m3 = fmax(L * alpha * (zn * zn * zn), 0.0);  // ChanLength * ChannelAlpha * ChanQKin**Beta, :527-530
+            X.qk = zn;                                     // :531 is the identity on z
+            X.chanq = lfkw::pow5(zn);
+        } else {
+            double qn = lfkw::solve(U1, X.qk, side * L, a, C.P);
+            qr1 = qn;
+            X.m3 = fmax(L * alpha * pw(qn, C.P.beta), 0.0);          // :527-530
+            X.qk = pw(X.m3 * invL * (1 / alpha), C.P.inv_beta);      // :531
+            X.chanq = X.qk;
+        }
         X.sum += X.chanq;                                         // :537
+    } else if (QZ) {
+        const double tot = X.m3 + X.m32;
+        const double ratio = tot > 0 ? X.m3 / tot : 0.0;
+        double s1 = (tot - c2start) > m3limit ? ratio * side : side;
+        s1 = fabs(side) < 1e-7 ? side : s1;
+        X.s1 = s1;
+        double s2 = side - s1;
+        s2 = s2 + c2qstart * invL;
+        const double zn = lfkw::solve_z(U1, X.qk, s1 * L, a);
+        qr1 = zn;
+        X.m3 = fmax(L * alpha * (zn * zn * zn), 0.0);
+        X.qk = zn;
+        const double zn2 = lfkw::solve_z(U2, X.q2k, s2 * L, a2);
+        qr2 = zn2;
+        double m32 = L * alpha2 * (zn2 * zn2 * zn2);
+        double z2 = zn2;
+        if (m32 - c2start < 0.0) {  // :586-587: volume floored at Chan2M3Start, discharge re-derived from it (:593)
+            m32 = c2start;
+            z2 = z2floor;
+        }
+        X.m32 = m32;
+        X.cs2a = (m32 - c2start) * invL;
+        X.q2k = z2;
+        X.chanq = fmax(lfkw::pow5(zn) + lfkw::pow5(z2) - qlimit, 0.0);
+        X.sumnl = X.sum;
+        X.sum += X.chanq;
     } else {
         const double tot = X.m3 + X.m32;
         const double ratio = tot > 0 ? X.m3 / tot : 0.0;          // :549
@@ -107,6 +146,7 @@ __device__ __forceinline__ void chan_substep(const ChanPtrs &C, int i, double U1
 constexpr int CH_THREADS = 128;
 
 // wavefront diagonal over channel-network pixels: positions [lo, hi), sub-step s = d - level
+template <bool QZ>
 __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo, int hi, int d)
 {
     int i = lo + blockIdx.x * CH_THREADS + threadIdx.x;
@@ -116,15 +156,16 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo
     double *Q2r = (s & 1) ? C.Q2r1 : C.Q2r0;
     int c0 = C.cfirst[i], c1 = C.cfirst[i + 1];
     double U1 = 0., U2 = 0.;
-    for (int k = c0; k < c1; ++k) U1 += Qr[k];
+    for (int k = c0; k < c1; ++k) U1 += QZ ? lfkw::pow5(Qr[k]) : Qr[k];
     ChanLocal X;
     X.qk = C.Qk[i];
     X.sum = s == 0 ? 0. : C.sumDis[i];  // sumDisDay = 0 before the sub-step loop, Lisflood_dynamic.py:177
     const double L = C.L[i], alpha = C.alpha[i], a = C.a[i], sideDt = C.sideDt[i];
     const bool isch = C.isChan[i] != 0;
-    double alpha2 = 0, a2 = 0, ql = 0, m3l = 0, c2s = 0, c2q = 0;
+    double alpha2 = 0, a2 = 0, ql = 0, m3l = 0, c2s = 0, c2q = 0, z2f = 0;
     if (C.split) {
-        for (int k = c0; k < c1; ++k) U2 += Q2r[k];
+        for (int k = c0; k < c1; ++k) U2 += QZ ? lfkw::pow5(Q2r[k]) : Q2r[k];
+        if (QZ) z2f = C.z2floor[i];
         X.m3 = C.M3[i];
         X.m32 = C.M32[i];
         X.q2k = C.Q2k[i];
@@ -136,7 +177,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo
         c2q = C.C2QStart[i];
     }
     double qr1, qr2 = 0.;
-    chan_substep(C, i, U1, U2, X, L, 1 / L, alpha, a, sideDt, isch, qr1, qr2, alpha2, a2, ql, m3l, c2s, c2q);
+    chan_substep<QZ>(C, i, U1, U2, X, L, 1 / L, alpha, a, sideDt, isch, qr1, qr2, alpha2, a2, ql, m3l, c2s, c2q, z2f);
     Qr[i] = qr1;
     C.Qk[i] = X.qk;
     C.sumDis[i] = X.sum;
@@ -159,6 +200,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo
 }
 
 // pixels with no upstream and no downstream link: all S sub-steps in registers
+template <bool QZ>
 __global__ void __launch_bounds__(CH_THREADS) k_chan_isolated(ChanPtrs C, int lo, int hi)
 {
     int i = lo + blockIdx.x * CH_THREADS + threadIdx.x;
@@ -169,8 +211,9 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_isolated(ChanPtrs C, int lo
     X.m3 = C.M3[i];
     const double L = C.L[i], alpha = C.alpha[i], a = C.a[i], sideDt = C.sideDt[i];
     const bool isch = C.isChan[i] != 0;
-    double alpha2 = 0, a2 = 0, ql = 0, m3l = 0, c2s = 0, c2q = 0;
+    double alpha2 = 0, a2 = 0, ql = 0, m3l = 0, c2s = 0, c2q = 0, z2f = 0;
     if (C.split) {
+        if (QZ) z2f = C.z2floor[i];
         X.m32 = C.M32[i];
         X.q2k = C.Q2k[i];
         alpha2 = C.alpha2[i];
@@ -184,7 +227,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_isolated(ChanPtrs C, int lo
     const double invL = 1 / L;
 #pragma unroll 1
     for (int s = 0; s < C.S; ++s)
-        chan_substep(C, i, 0., 0., X, L, invL, alpha, a, sideDt, isch, qr1, qr2, alpha2, a2, ql, m3l, c2s, c2q);
+        chan_substep<QZ>(C, i, 0., 0., X, L, invL, alpha, a, sideDt, isch, qr1, qr2, alpha2, a2, ql, m3l, c2s, c2q, z2f);
     // the routed value of the last sub-step in both parity buffers (nobody reads it: no downstream)
     C.Qr0[i] = qr1;
     C.Qr1[i] = qr1;
@@ -204,7 +247,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_isolated(ChanPtrs C, int lo
 }
 
 // Lisflood_dynamic.py:194-229 and hydrological_modules/routing.py:695-703
-__global__ void k_chan_post(int n, int split, int S, double DtSec, const double *__restrict__ M3, const double *__restrict__ M32,
+__global__ void k_chan_post(int n, int split, int qz, int S, double DtSec, const double *__restrict__ M3, const double *__restrict__ M32,
                             const double *__restrict__ C2M3Start, const double *__restrict__ L,
                             const double *__restrict__ sumDisDay, const double *__restrict__ ChanQ,
                             const double *__restrict__ Qk, const uint8_t *__restrict__ atLast,
@@ -225,7 +268,7 @@ __global__ void k_chan_post(int n, int split, int S, double DtSec, const double 
     DischargeM3Out[i] += atLast[i] ? ChanQ[i] * DtSec : 0.;
     if (FlowVelocity) {
         const double area = fmax(M3[i] * invL, 0.01);
-        const double q = Qk[i];
+        const double q = qz ? lfkw::pow5(Qk[i]) : Qk[i];
         double fv = fmin(q / area, 0.36 * pw(q, 0.24));
         fv *= fmin(sqrt(PixelArea_ch[i]) * invL, 1.);
         FlowVelocity[i] = fv;
@@ -243,6 +286,7 @@ struct OfPtrs {
     double PixelLength, InvPixelLength, InvDtSec;
     lfkw::Params P;
 };
+template <bool QZ>
 __global__ void __launch_bounds__(128) k_of_level(OfPtrs O, int lo, int hi)
 {
     int i = lo + blockIdx.x * 128 + threadIdx.x;
@@ -253,21 +297,27 @@ __global__ void __launch_bounds__(128) k_of_level(OfPtrs O, int lo, int hi)
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         double U = 0.;
-        for (int k = c0; k < c1; ++k) U += O.Qnew[r][k];
         const double side = runoff[r] * mm2m3 * O.InvPixelLength * O.InvDtSec;  // [m3 s-1 m-1], :143-149
-        O.Qnew[r][i] = lfkw::solve(U, O.Qold[r][i], side * O.PixelLength, O.a[r][i], O.P);
+        if (QZ) {
+            for (int k = c0; k < c1; ++k) U += lfkw::pow5(O.Qnew[r][k]);
+            O.Qnew[r][i] = lfkw::solve_z(U, O.Qold[r][i], side * O.PixelLength, O.a[r][i]);
+        } else {
+            for (int k = c0; k < c1; ++k) U += O.Qnew[r][k];
+            O.Qnew[r][i] = lfkw::solve(U, O.Qold[r][i], side * O.PixelLength, O.a[r][i], O.P);
+        }
     }
 }
 // surface_routing.py:191-212 (+ scatter of ToChanM3RunoffDt into channel order)
 __global__ void k_of_post(int n, const double *__restrict__ QO, const double *__restrict__ QF, const double *__restrict__ QD,
                           const double *__restrict__ GwToChan, const double *__restrict__ MMtoM3,
-                          const uint8_t *__restrict__ isChannel, const int32_t *__restrict__ soil_to_chan, double DtSec,
-                          double InvNoRoutSteps, double *__restrict__ sideDt_chan, double *__restrict__ ToChanM3Runoff,
+                          const uint8_t *__restrict__ isChannel, const int32_t *__restrict__ soil_to_chan, int qz,
+                          double DtSec, double InvNoRoutSteps, double *__restrict__ sideDt_chan, double *__restrict__ ToChanM3Runoff,
                           double *__restrict__ OFToChanM3, double *__restrict__ Qall_out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double qall = QD[i] + QO[i] + QF[i];                       // :195
+    const double qall = qz ? lfkw::pow5(QD[i]) + lfkw::pow5(QO[i]) + lfkw::pow5(QF[i])
+                           : QD[i] + QO[i] + QF[i];  // :195
     const double oftochan = isChannel[i] ? qall * DtSec : 0.;       // :199
     const double tochan = GwToChan[i] * MMtoM3[i] + oftochan;      // :211
     sideDt_chan[soil_to_chan[i]] = tochan * InvNoRoutSteps;         // :212
@@ -319,10 +369,30 @@ __global__ void k_make_a(const double *__restrict__ alpha, const double *__restr
     if (i < n) a[i] = alpha[i] * (dx ? dx[i] : dxs) / dt;  // a_dx_div_dt, kinematic_wave_parallel.py:126
 }
 __global__ void k_of_m3(const double *__restrict__ Q, const double *__restrict__ alpha, double PixelLength, double beta,
-                        double *__restrict__ M3, int64_t n)
+                        int qz, double *__restrict__ M3, int64_t n)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) M3[i] = PixelLength * alpha[i] * pw(Q[i], beta);  // surface_routing.py:191-193
+    if (i >= n) return;
+    const double z = Q[i];
+    M3[i] = PixelLength * alpha[i] * (qz ? z * z * z : pw(z, beta));  // surface_routing.py:191-193
+}
+// discharge maps are stored as z = Q^(1/5) in 3/5 mode: conversions at the API boundary
+__global__ void k_q_to_z(double *__restrict__ v, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = lfkw::z_of_q(v[i]);
+}
+__global__ void k_z_to_q(double *__restrict__ v, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = lfkw::pow5(v[i]);
+}
+// (Chan2M3Start / (L * alpha2))^(1/3): z of the discharge re-derived from the floored floodplain volume
+__global__ void k_z2floor(const double *__restrict__ c2start, const double *__restrict__ L, const double *__restrict__ alpha2,
+                          double *__restrict__ out, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pw(c2start[i] * (1 / L[i]) * (1 / alpha2[i]), 1.0 / 3.0);
 }
 
 }  // namespace
@@ -343,6 +413,7 @@ struct lf_model {
     std::vector<int> ev_used;  // 4 events per recorded step: start, after soil, after overland, after channel
     double t_soil = 0, t_of = 0, t_chan = 0;
     int64_t t_steps = 0;
+    bool quintic = false;            // Beta == 0.6: discharge state held as z = Q^(1/5)
     int64_t steps = 0;               // model steps done (parity of the overland discharge buffers)
     bool params_dirty = true;        // a_dx_div_dt arrays need a rebuild
     int64_t bytes = 0;
@@ -456,6 +527,8 @@ int field(lf_model *m, const char *name, Field **out)
     f->order = s->order;
     f->landuse = s->landuse;
     f->diag = s->diag;
+    f->as_z = m->quintic && (strcmp(name, "OFQOther") == 0 || strcmp(name, "OFQForest") == 0 ||
+                             strcmp(name, "OFQDirect") == 0 || strcmp(name, "ChanQKin") == 0 || strcmp(name, "Chan2QKin") == 0);
     LF_CHECK(f->buf.alloc((size_t)s->rows * m->n));
     LF_CUDA(cudaMemsetAsync(f->buf.p, 0, (size_t)s->rows * m->n * sizeof(double), lf::stream()));
     m->bytes += (int64_t)s->rows * m->n * 8;
@@ -596,6 +669,8 @@ int build_a(lf_model *m, const char *alpha_name, int row, const double *dx, doub
     return LF_OK;
 }
 
+int internal(lf_model *m, const std::string &name, Order order, double **out);
+
 int refresh_params(lf_model *m)
 {
     if (!m->params_dirty) return LF_OK;
@@ -614,7 +689,17 @@ int refresh_params(lf_model *m)
         LF_CHECK(build_a(m, "OFAlpha", r, nullptr, m->cfg.PixelLength, m->cfg.DtSec, "__aOF", r));
     FIELD(L, "ChanLength");
     LF_CHECK(build_a(m, "ChannelAlpha", 0, L, 0., m->DtRouting, "__aCh", 0));
-    if (m->cfg.SplitRouting) LF_CHECK(build_a(m, "ChannelAlpha2", 0, L, 0., m->DtRouting, "__aCh2", 0));
+    if (m->cfg.SplitRouting) {
+        LF_CHECK(build_a(m, "ChannelAlpha2", 0, L, 0., m->DtRouting, "__aCh2", 0));
+        if (m->quintic) {
+            double *zf = nullptr;
+            LF_CHECK(internal(m, "__z2floor", CHAN, &zf));
+            FIELD(c2s, "Chan2M3Start");
+            FIELD(al2, "ChannelAlpha2");
+            k_z2floor<<<lf::blocks_for(m->n, 256), 256, 0, lf::stream()>>>(c2s, L, al2, zf, m->n);
+            LF_LAUNCH_CHECK();
+        }
+    }
     m->params_dirty = false;
     return LF_OK;
 }
@@ -667,14 +752,13 @@ int surface_stage(lf_model *m)
     O.PixelLength = m->cfg.PixelLength;
     O.InvPixelLength = 1.0 / m->cfg.PixelLength;
     O.InvDtSec = 1 / m->cfg.DtSec;
-    O.P.beta = m->cfg.Beta;
-    O.P.inv_beta = 1 / m->cfg.Beta;
-    O.P.b_minus_1 = m->cfg.Beta - 1;
+    O.P = lfkw::make_params(m->cfg.Beta);
     const std::vector<int32_t> &ls = g->h_level_start;
     for (int l = 0; l < g->n_orders; ++l) {
         int lo = ls[l], hi = ls[l + 1];
         if (hi <= lo) continue;
-        k_of_level<<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+        if (m->quintic) k_of_level<true><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+        else k_of_level<false><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
         LF_LAUNCH_CHECK();
     }
     // swap: the named maps must hold the new discharge
@@ -705,11 +789,12 @@ int surface_stage(lf_model *m)
         for (int r = 0; r < 3; ++r) {
             FIELD(m3, m3n[r]);
             k_of_m3<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(qs[r], ofa + (int64_t)r * m->n, m->cfg.PixelLength, m->cfg.Beta,
-                                                               m3, m->n);
+                                                               m->quintic ? 1 : 0, m3, m->n);
             LF_LAUNCH_CHECK();
         }
     }
-    k_of_post<<<lf::blocks_for(m->n, 256), 256, 0, st>>>((int)m->n, qo, qf, qd, gw, mm, isch, m->soil_to_chan.p, m->cfg.DtSec,
+    k_of_post<<<lf::blocks_for(m->n, 256), 256, 0, st>>>((int)m->n, qo, qf, qd, gw, mm, isch, m->soil_to_chan.p,
+                                                         m->quintic ? 1 : 0, m->cfg.DtSec,
                                                          1 / (double)m->cfg.NoRoutSteps, sideDt, tochan, oftochan, qall);
     LF_LAUNCH_CHECK();
     return LF_OK;
@@ -750,9 +835,7 @@ int channel_stage(lf_model *m)
     C.InvDtRouting = 1 / m->DtRouting;
     C.S = m->cfg.NoRoutSteps;
     C.split = m->cfg.SplitRouting;
-    C.P.beta = m->cfg.Beta;
-    C.P.inv_beta = 1 / m->cfg.Beta;
-    C.P.b_minus_1 = m->cfg.Beta - 1;
+    C.P = lfkw::make_params(m->cfg.Beta);
     double *m32 = nullptr, *c2s = nullptr;
     if (C.split) {
         FIELD(q2k, "Chan2QKin");
@@ -781,13 +864,19 @@ int channel_stage(lf_model *m)
         c2s = c2s_;
         LF_CHECK(internal(m, "Chan2QKin__r0", CHAN, &C.Q2r0));
         LF_CHECK(internal(m, "Chan2QKin__r1", CHAN, &C.Q2r1));
+        if (m->quintic) {
+            double *zf = nullptr;
+            LF_CHECK(internal(m, "__z2floor", CHAN, &zf));
+            C.z2floor = zf;
+        }
     }
     // isolated pixels (no link at all): one launch, all sub-steps in registers
     const std::vector<int32_t> &ls = g->h_level_start;
     int Lc = g->n_orders, S = C.S;
     int iso_lo = (int)(m->n - g->n_isolated), iso_hi = (int)m->n;
     if (iso_hi > iso_lo) {
-        k_chan_isolated<<<lf::blocks_for(iso_hi - iso_lo, CH_THREADS), CH_THREADS, 0, st>>>(C, iso_lo, iso_hi);
+        if (m->quintic) k_chan_isolated<true><<<lf::blocks_for(iso_hi - iso_lo, CH_THREADS), CH_THREADS, 0, st>>>(C, iso_lo, iso_hi);
+        else k_chan_isolated<false><<<lf::blocks_for(iso_hi - iso_lo, CH_THREADS), CH_THREADS, 0, st>>>(C, iso_lo, iso_hi);
         LF_LAUNCH_CHECK();
     }
     // the connected network: space-time wavefront over (level, sub-step)
@@ -797,7 +886,8 @@ int channel_stage(lf_model *m)
         int hi_lev = d < Lc - 1 ? d : Lc - 1;
         int lo = ls[lo_lev], hi = level_end(hi_lev);
         if (hi <= lo) continue;
-        k_chan_diagonal<<<lf::blocks_for(hi - lo, CH_THREADS), CH_THREADS, 0, st>>>(C, lo, hi, d);
+        if (m->quintic) k_chan_diagonal<true><<<lf::blocks_for(hi - lo, CH_THREADS), CH_THREADS, 0, st>>>(C, lo, hi, d);
+        else k_chan_diagonal<false><<<lf::blocks_for(hi - lo, CH_THREADS), CH_THREADS, 0, st>>>(C, lo, hi, d);
         LF_LAUNCH_CHECK();
     }
     FIELD(chm3, "ChanM3");
@@ -814,7 +904,7 @@ int channel_stage(lf_model *m)
         td = td_;
         pa = pa_;
     }
-    k_chan_post<<<lf::blocks_for(m->n, 256), 256, 0, st>>>((int)m->n, C.split, S, m->cfg.DtSec, m3, m32, c2s, L, sd, cq, qk, atlast,
+    k_chan_post<<<lf::blocks_for(m->n, 256), 256, 0, st>>>((int)m->n, C.split, m->quintic ? 1 : 0, S, m->cfg.DtSec, m3, m32, c2s, L, sd, cq, qk, atlast,
                                                            pa, chm3, tcs, sdis, qavg, dout, fv, td);
     LF_LAUNCH_CHECK();
     return LF_OK;
@@ -842,6 +932,7 @@ int lf_model_create(const lf_model_config *cfg, const uint8_t *land_mask, const 
     m->cfg = *cfg;
     m->DtDay = cfg->DtSec / 86400.;
     m->DtRouting = cfg->DtSec / cfg->NoRoutSteps;
+    m->quintic = lfkw::make_params(cfg->Beta).quintic != 0;
     LF_CHECK(lf_ldd_build(ldd_to_chan, land_mask, cfg->rows, cfg->cols, &m->g_of));
     LF_CHECK(lf_ldd_build(ldd_kinematic, land_mask, cfg->rows, cfg->cols, &m->g_ch));
     m->n = m->g_of->n;
@@ -890,6 +981,10 @@ int lf_model_set(lf_model *m, const char *name, const double *values, int64_t co
     LF_CUDA(cudaMemcpyAsync(m->stage.p, values, count * sizeof(double), cudaMemcpyDefault, st));
     k_rows_to_pos<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(m->stage.p, f->buf.p, pop, m->n, f->rows);
     LF_LAUNCH_CHECK();
+    if (f->as_z) {
+        k_q_to_z<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(f->buf.p, m->n);
+        LF_LAUNCH_CHECK();
+    }
     if (f->landuse) {
         // rows that repeat an earlier land use share its storage row (Irrigated == Rainfed without a third map,
         // Lisflood_initial.py:371-391): the kernel then re-reads cached lines instead of new HBM bytes
@@ -918,7 +1013,7 @@ int lf_model_set(lf_model *m, const char *name, const double *values, int64_t co
         }
     }
     if (strcmp(name, "OFAlpha") == 0 || strcmp(name, "ChannelAlpha") == 0 || strcmp(name, "ChannelAlpha2") == 0 ||
-        strcmp(name, "ChanLength") == 0)
+        strcmp(name, "ChanLength") == 0 || strcmp(name, "Chan2M3Start") == 0)
         m->params_dirty = true;
     LF_CUDA(cudaStreamSynchronize(st));
     return LF_OK;
@@ -941,6 +1036,10 @@ int lf_model_get(lf_model *m, const char *name, double *values, int64_t count)
     const int32_t *pos = f->order == SOIL ? m->g_of->pos_of_pix.p : m->g_ch->pos_of_pix.p;
     k_rows_to_pix<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(f->buf.p, m->stage.p, pos, m->n, f->rows);
     LF_LAUNCH_CHECK();
+    if (f->as_z) {
+        k_z_to_q<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(m->stage.p, m->n);
+        LF_LAUNCH_CHECK();
+    }
     LF_CUDA(cudaMemcpyAsync(values, m->stage.p, count * sizeof(double), cudaMemcpyDefault, st));
     LF_CUDA(cudaStreamSynchronize(st));
     return LF_OK;

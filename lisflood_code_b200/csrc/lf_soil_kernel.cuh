@@ -13,6 +13,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "lf_math.cuh"
+
 namespace lfsoil {
 
 struct Ptrs {
@@ -51,7 +53,7 @@ struct Diag {
     int32_t *NoSubS;  // (V,N)
 };
 
-__device__ __forceinline__ double pw(double x, double y) { return exp(y * log(x)); }
+__device__ __forceinline__ double pw(double x, double y) { return lfm::pw(x, y); }
 
 // saturationDegree + unsaturatedConductivity, soilloop.py:360-383
 __device__ __forceinline__ double unsat_k(double w, bool pore, double wres, double ws, double ksat, double invm, double m)

@@ -77,7 +77,7 @@ def mualem(w_res, w_sat, genu_alpha, genu_n, genu_m, head_cm):
 
 
 def full_stack(rows, cols, seed=0, ldd_noise=0.5, mask_fraction=0.0, channel_threshold=60, split_routing=False,
-               dt_sec=86400.0, dt_sec_channel=3600.0, frozen_fraction=0.05):
+               dt_sec=86400.0, dt_sec_channel=3600.0, frozen_fraction=0.05, beta=0.6):
     """Static parameters + initial state of the hot path on a seeded synthetic catchment.
 
     Keys follow the reference's `self.var.<name>` attributes.  (V, N) / (L, N) arrays are
@@ -111,7 +111,7 @@ def full_stack(rows, cols, seed=0, ldd_noise=0.5, mask_fraction=0.0, channel_thr
     S["MMtoM"] = 0.001
     S["MMtoM3"] = 0.001 * S["PixelArea"]
     S["M3toMM"] = 1 / S["MMtoM3"]
-    S["Beta"] = 0.6
+    S["Beta"] = float(beta)
     S["InvBeta"] = 1 / S["Beta"]
     S["AlpPow"] = 2.0 / 3.0 * S["Beta"]
 

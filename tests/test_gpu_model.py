@@ -29,11 +29,12 @@ def test_golden_model_step(gpu_lib, case):
         assert not bad, (case, t, bad)
 
 
-@pytest.mark.parametrize("rows,cols,split,seed", [(150, 120, False, 7), (130, 160, True, 8)])
-def test_model_vs_oracle(gpu_lib, oracle, rows, cols, split, seed):
+@pytest.mark.parametrize("rows,cols,split,seed,beta", [(150, 120, False, 7, 0.6), (130, 160, True, 8, 0.6),
+                                                       (90, 110, True, 9, 0.7)])   # beta != 3/5: general-power path
+def test_model_vs_oracle(gpu_lib, oracle, rows, cols, split, seed, beta):
     from lisflood_code_b200 import synthetic
     from oracle import lisf_oracle_model as om
-    S = synthetic.full_stack(rows, cols, seed=seed, split_routing=split, ldd_noise=0.4, mask_fraction=0.1)
+    S = synthetic.full_stack(rows, cols, seed=seed, split_routing=split, ldd_noise=0.4, mask_fraction=0.1, beta=beta)
     O = om.OracleModel(S)
     M = _model(gpu_lib, S)
     keys = ["W1a", "W1b", "W2", "UZ", "LZ", "DSLR", "CumInterception", "Infiltration", "PrefFlow", "ESAct", "Ta",

@@ -1,0 +1,25 @@
+"""Accuracy of the float64 power function used by the CUDA kernels (lisflood_code_b200/csrc/lf_math.cuh),
+checked on the HOST: the header compiles as plain C++ (same arithmetic, fma() instead of __fma_rn)."""
+import os
+import re
+import subprocess
+
+from conftest import ROOT
+
+
+def test_pw_accuracy_against_libm(tmp_path):
+    exe = str(tmp_path / "lf_math_host_test")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "lisflood_code_b200", "csrc"),
+                           "-o", exe, os.path.join(ROOT, "tests", "lf_math_host_test.cpp")])
+    out = subprocess.check_output([exe], text=True)
+    m = re.search(r"max rel err ([0-9.e+-]+) .*>1e-13: (\d+)", out)
+    assert m, out
+    # |y log2 x| reaches ~200 in the sampled range: 200 * 2^-52 = 4.4e-14
+    assert float(m.group(1)) < 6e-14 and int(m.group(2)) == 0
+    m = re.search(r"log2 max rel ([0-9.e+-]+) exp2 max rel ([0-9.e+-]+)", out)
+    assert float(m.group(1)) < 1e-15 and float(m.group(2)) < 5e-16
+    # special values follow pow() for x >= 0
+    for line in out.splitlines():
+        mm = re.match(r"pw\((\S+),(\S+)\)=(\S+) pow=(\S+)", line)
+        if mm and mm.group(1) not in ("-1", "nan"):
+            assert mm.group(3).lstrip("-") == mm.group(4).lstrip("-"), line
