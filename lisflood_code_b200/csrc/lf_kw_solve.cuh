@@ -16,13 +16,14 @@
 //    iteration needs is a product: Q^beta = z^3, Q^(beta-1) = 1/z^2.  The SAME Newton iterates in Q are formed
 //    (same update, clamp and stopping tests), and z is refreshed after each update by a fifth root (float seed +
 //    two Newton steps, ~20 instructions) -- no log/exp at all.  The state carried between routing steps is z, so
-//    a*Qold^beta = a*z^3 is free and the discharge handed downstream is z^5.  The reference's bracketed initial
-//    guess is evaluated in float: it only seeds the iteration, and because Newton contracts differences
-//    quadratically the iterates coincide with the reference's to < 1e-15 after three steps, so the stopping
-//    decisions (|f| <= 1e-12) fall on the same iterate.  (A pure Newton on the quintic z^5 + a z^3 - C would be
-//    cheaper still but stops on different iterates: its results differ from the reference's by up to the
-//    reference's own 1e-12 absolute tolerance, i.e. 1e-4 relative on near-dry pixels -- rejected.)
-//    ~200 instructions per solve instead of ~1400: the routing kernels move from FP64-bound towards HBM-bound.
+//    a*Qold^beta = a*z^3 is free and the discharge handed downstream is z^5.  The bracketed initial guess is the
+//    reference's too (C^(-2/5) from a fifth root, the two 5/3 powers from cube roots), in float64: the
+//    reference stops as soon as |f| <= 1e-12, which for near-dry pixels happens after 0-2 iterations, so the
+//    returned value depends on the guess and on every iterate -- they must be reproduced, not just the root.
+//    (A pure Newton on the quintic z^5 + a z^3 - C, or a float-precision guess, is cheaper but returns values that
+//    differ from the reference's by up to its own 1e-12 absolute tolerance, i.e. 1e-4 relative on near-dry
+//    pixels and 100 % on the derived volumes there -- measured and rejected.)
+//    ~250 instructions per solve instead of ~1400: the routing kernels move from FP64-bound towards HBM-bound.
 #pragma once
 #include "lf_math.cuh"
 
@@ -95,33 +96,49 @@ __device__ __forceinline__ double root5(double q)
     }
     return w;
 }
-// z of a discharge supplied by the caller (any magnitude, 0 -> 0, negative / NaN -> NaN)
+// cube root of x > 0 within the float range, same scheme
+__device__ __forceinline__ double root3(double x)
+{
+    double w = (double)__powf((float)x, 0.33333334f);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double w2 = w * w;
+        const double r = (double)__frcp_rn((float)(3.0 * w2));
+        w = lfm::fma_(-lfm::fma_(w2, w, -x), r, w);
+    }
+    return w;
+}
+__device__ __forceinline__ bool in_float_range(double x) { return x > 1e-30 && x < 1e30; }
+// z of a discharge (any magnitude, 0 -> 0, negative / NaN -> NaN)
 __device__ __forceinline__ double z_of_q(double q)
 {
-    if (q > 1e-30 && q < 1e30) return root5(q);
+    if (in_float_range(q)) return root5(q);
     if (q == 0.0) return 0.0;
     return lfm::pw(q, 0.2);
 }
+// x^(5/3) for x >= 0
+__device__ __forceinline__ double pow_5_3(double x)
+{
+    if (in_float_range(x)) return pow5(root3(x));
+    return lfm::pw(x, 1.6666666666666667);
+}
 
 // U: sum of z_k^5 over the upstream pixels; returns z_new (0 when the discharge is 0).
-// Same iterates as the reference's Newton in Q (tools:64-80); Q^beta = z^3 and Q^(beta-1) = 1/z^2 come from
-// z = Q^(1/5), refreshed after every update by root5().
+// Same initial guess and Newton iterates as the reference (tools:64-80), in float64; Q^beta = z^3 and
+// Q^(beta-1) = 1/z^2 come from z = Q^(1/5), refreshed after every update by root5().
 __device__ __forceinline__ double solve_z(double U, double z_old, double lateral, double a)
 {
     const double c = U + (a * (z_old * z_old * z_old) + lateral);
     if (c <= NEWTON_TOL) return 0.0;  // tools:60-62
-    if (!(c < 1.0e300)) return c;     // NaN / Inf propagate like in the reference (flagnancheck reports them)
-    // bracketed initial guess (tools:64-70) in float: it only seeds the iteration, the iterates merge with the
-    // reference's to < 1e-15 within three Newton steps (quadratic contraction)
-    const float cf = (float)c, af = (float)a;
-    const float t = 0.6f * af * __powf(cf, -0.4f);
-    const float secant = t <= 1.0f ? __fdividef(cf, 1.0f + t) : __fdividef(cf, 1.0f + __powf(t, 1.6666666f));
-    const float other = __powf(__fdividef(cf - secant, af), 1.6666666f);
-    const float q0 = 0.5f * (secant + other);
-    double q = (q0 > 1e-30f && q0 < 1e30f) ? (double)q0 : fmin(c, 1e30);  // degenerate a (0, inf, NaN): start at C
-    q = fmax(q, NEWTON_TOL);
+    if (!(c < 1.0e30)) return c < 1.0e300 ? lfm::pw(c, 0.2) : c;  // absurd / NaN / Inf inflow: propagate
+    // bracketed initial guess, tools:64-70
     const double ba = 0.6 * a;
-    double z = root5(q);
+    const double zc = root5(c);
+    const double t = ba / (zc * zc);  // b*a * C^(b-1)
+    const double secant = (t <= 1.0) ? c / (1.0 + t) : c / (1.0 + pow_5_3(t));
+    const double other = pow_5_3((c - secant) / a);
+    double q = (secant + other) / 2.0;
+    double z = z_of_q(q);
     double err = q + a * (z * z * z) - c;
     int count = 0;
     while (fabs(err) > NEWTON_TOL && count < MAX_ITERS) {

@@ -1,8 +1,8 @@
 // lf_model.cu -- the full hot-path time step on device-resident state (C ABI: lf_model_*).
 //
 // Stages per model step (reference call order, Lisflood_dynamic.py:114-229):
-//   1. k_soil_step        fused canopy + soil column + open/sealed + per-pixel sums + groundwater
-//                         (lf_soil_kernel.cuh) -- one pass over the soil maps.
+//   1. k_soil_veg / k_soil_veg_deferred / k_soil_pixel   fused canopy + soil column per (fraction, pixel),
+//                         then open/sealed + per-pixel sums + groundwater per pixel (lf_soil_kernel.cuh).
 //   2. k_of_level/k_of_post  the three overland-flow routers (Other, Forest, Direct) on LddToChan,
 //                         solved together in one level sweep (three independent Newton solves per thread),
 //                         then OFToChanM3 / ToChanM3RunoffDt written in channel order.
@@ -408,6 +408,8 @@ struct lf_model {
     lf::DevBuf<uint8_t> stage_u8;
     lf::DevBuf<int32_t> soil_to_chan;
     lf::DevBuf<int> flag;
+    lf::DevBuf<int32_t> soil_list, soil_list_cnt;  // deferred soil columns (lf_soil_kernel.cuh)
+    int32_t soil_list_cap = 0;
     // per-stage device timing (CUDA events on the library stream), accumulated on query
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_used;  // 4 events per recorded step: start, after soil, after overland, after channel
@@ -613,7 +615,37 @@ int soil_stage(lf_model *m)
     P.LeafDrainageK = m->cfg.LeafDrainageK;
     P.SMaxSealed = m->cfg.SMaxSealed;
     P.TimeSinceStart = (double)(m->steps + 1);
-    unsigned grid = lf::blocks_for(m->n, 128);
+    // contributions handed from the column kernel to the pixel kernel, and the deferred-column lists
+    {
+        const char *cn[8] = {"__cTaInt", "__cTa", "__cES", "__cPref", "__cInf", "__cUZout", "__cGwPerc", "__cSurf"};
+        double **dst[8] = {&P.cTaInt, &P.cTa, &P.cES, &P.cPref, &P.cInf, &P.cUZout, &P.cGwPerc, &P.cSurf};
+        for (int c = 0; c < 8; ++c) {
+            auto it = m->fields.find(cn[c]);
+            if (it == m->fields.end()) {
+                std::unique_ptr<Field> f(new Field());
+                f->rows = 3;
+                LF_CHECK(f->buf.alloc((size_t)3 * m->n));
+                m->bytes += (int64_t)3 * m->n * 8;
+                it = m->fields.emplace(cn[c], std::move(f)).first;
+            }
+            *dst[c] = it->second->buf.p;
+        }
+        if (!m->soil_list.p) {
+            // capacity per bucket: a quarter of the columns (typically ~6 % of all columns are deferred in total);
+            // a full list degrades gracefully: the column is integrated in the first pass
+            m->soil_list_cap = (int32_t)std::max<int64_t>(1024, (3 * m->n) / 4);
+            LF_CHECK(m->soil_list.alloc((size_t)lfsoil::NBUCKET * m->soil_list_cap));
+            LF_CHECK(m->soil_list_cnt.alloc(lfsoil::NBUCKET));
+            m->bytes += (int64_t)lfsoil::NBUCKET * m->soil_list_cap * 4;
+        }
+        P.list = m->soil_list.p;
+        P.list_cnt = m->soil_list_cnt.p;
+        P.list_cap = m->soil_list_cap;
+        LF_CUDA(cudaMemsetAsync(m->soil_list_cnt.p, 0, lfsoil::NBUCKET * sizeof(int32_t), st));
+    }
+    const unsigned grid_veg = lf::blocks_for(3 * m->n, lfsoil::SOIL_THREADS);
+    const unsigned grid_def = lf::blocks_for(m->soil_list_cap, lfsoil::SOIL_THREADS);
+    const unsigned grid_pix = lf::blocks_for(m->n, 256);
     if (m->cfg.diagnostics) {
         BINDLU(WWP2, "WWP2") BINDLU(WFC2, "WFC2") BINDLU(Depth1a, "SoilDepth1a") BINDLU(Depth1b, "SoilDepth1b")
         BINDLU(Depth2, "SoilDepth2")
@@ -649,10 +681,22 @@ int soil_stage(lf_model *m)
             }
         }
         D.NoSubS = (int32_t *)ns->buf.p;
-        k_soil_step<true><<<grid, 128, 0, st>>>(P, D);
+        k_soil_veg<true><<<grid_veg, lfsoil::SOIL_THREADS, 0, st>>>(P, D);
+        LF_LAUNCH_CHECK();
+        for (int b = 0; b < lfsoil::NBUCKET; ++b) {
+            k_soil_veg_deferred<true><<<grid_def, lfsoil::SOIL_THREADS, 0, st>>>(P, D, b);
+            LF_LAUNCH_CHECK();
+        }
+        k_soil_pixel<true><<<grid_pix, 256, 0, st>>>(P, D);
     } else {
-        // diagnostics-only parameter rows are never dereferenced in this instantiation
-        k_soil_step<false><<<grid, 128, 0, st>>>(P, D);
+        // diagnostics-only parameter rows are never dereferenced in these instantiations
+        k_soil_veg<false><<<grid_veg, lfsoil::SOIL_THREADS, 0, st>>>(P, D);
+        LF_LAUNCH_CHECK();
+        for (int b = 0; b < lfsoil::NBUCKET; ++b) {
+            k_soil_veg_deferred<false><<<grid_def, lfsoil::SOIL_THREADS, 0, st>>>(P, D, b);
+            LF_LAUNCH_CHECK();
+        }
+        k_soil_pixel<false><<<grid_pix, 256, 0, st>>>(P, D);
     }
     LF_LAUNCH_CHECK();
     return LF_OK;
