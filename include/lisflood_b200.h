@@ -147,6 +147,11 @@ int lf_model_info(const lf_model *m, int64_t *n_pixels, int64_t *levels_overland
 /* Named maps in the reference's compressed order: count = N for per-pixel maps, 3*N for
  * (vegetation|landuse|runoff, pixel) maps.  Unknown names -> LF_ERR_INVALID. */
 int lf_model_set(lf_model *m, const char *name, const double *values, int64_t count);
+/* Like lf_model_set for per-pixel / (vegetation, pixel) maps, but returns immediately: the host-to-device copy
+ * runs on a separate copy stream (so it overlaps the kernels of the step in flight) and the map takes its new
+ * value after all work already queued.  `values` must stay valid and unchanged until the next synchronising call
+ * (lf_model_get, lf_synchronize); use page-locked memory for a truly asynchronous copy. */
+int lf_model_set_async(lf_model *m, const char *name, const double *values, int64_t count);
 int lf_model_get(lf_model *m, const char *name, double *values, int64_t count);
 /* boolean maps (u8[N]): "isFrozenSoil", "IsChannel", "IsChannelKinematic", "AtLastPointC" */
 int lf_model_set_flags(lf_model *m, const char *name, const uint8_t *values, int64_t count);
@@ -158,6 +163,11 @@ int lf_model_step(lf_model *m);
  * reset, in milliseconds, and the number of steps they cover.  Synchronises. */
 int lf_model_stage_times(lf_model *m, int reset, double *soil_ms, double *overland_ms, double *channel_ms,
                          int64_t *steps);
+/* Soil-stage statistics of the last step: deferred_columns[6] = number of (fraction, pixel) columns that needed
+ * 2-3, 4-7, 8-15, 16-31, 32-63, 64+ Darcy sub-steps; kernel_ms[8] = device time of k_soil_veg, the six
+ * k_soil_veg_deferred launches and k_soil_pixel (zeros unless timing was enabled by an earlier call with
+ * enable_timing = 1).  Either pointer may be NULL.  Synchronises. */
+int lf_model_soil_stats(lf_model *m, int enable_timing, int64_t *deferred_columns, double *kernel_ms);
 void lf_model_destroy(lf_model *m);
 
 #ifdef __cplusplus

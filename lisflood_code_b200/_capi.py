@@ -62,6 +62,7 @@ SIGNATURES = {
     "lf_model_info": (C.c_int, [_vp, C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s),
                                 C.POINTER(_i64s)]),
     "lf_model_set": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
+    "lf_model_set_async": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
     "lf_model_get": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
     "lf_model_set_flags": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
     "lf_model_soil": (C.c_int, [_vp]),
@@ -70,6 +71,7 @@ SIGNATURES = {
     "lf_model_step": (C.c_int, [_vp]),
     "lf_model_stage_times": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(_i64s)]),
+    "lf_model_soil_stats": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "lf_model_destroy": (None, [_vp]),
 }
 

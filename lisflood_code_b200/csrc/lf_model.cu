@@ -16,6 +16,7 @@
 // Storage: soil and overland maps live in the overland router's position order, channel maps in the
 // channel router's position order; lf_model_set/get translate from/to the reference's
 // compressed order.
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -410,6 +411,13 @@ struct lf_model {
     lf::DevBuf<int> flag;
     lf::DevBuf<int32_t> soil_list, soil_list_cnt;  // deferred soil columns (lf_soil_kernel.cuh)
     int32_t soil_list_cap = 0;
+    // asynchronous input path (lf_model_set_async): H2D on a copy stream into a per-map staging buffer, layout
+    // translation on the compute stream once the copy has landed
+    cudaStream_t copy_stream = nullptr;
+    std::map<std::string, std::unique_ptr<lf::DevBuf<double>>> async_stage;
+    std::map<std::string, cudaEvent_t> async_copied, async_consumed;
+    bool soil_profile = false;            // time the kernels of the soil stage individually (lf_model_soil_stats)
+    std::vector<cudaEvent_t> soil_ev;     // 9 events
     // per-stage device timing (CUDA events on the library stream), accumulated on query
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_used;  // 4 events per recorded step: start, after soil, after overland, after channel
@@ -424,6 +432,10 @@ struct lf_model {
         if (g_of) lf_graph_destroy(g_of);
         if (g_ch) lf_graph_destroy(g_ch);
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+        for (cudaEvent_t e : soil_ev) cudaEventDestroy(e);
+        for (auto &kv : async_copied) cudaEventDestroy(kv.second);
+        for (auto &kv : async_consumed) cudaEventDestroy(kv.second);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 };
 
@@ -643,6 +655,10 @@ int soil_stage(lf_model *m)
         P.list_cap = m->soil_list_cap;
         LF_CUDA(cudaMemsetAsync(m->soil_list_cnt.p, 0, lfsoil::NBUCKET * sizeof(int32_t), st));
     }
+    auto tick = [&](int k) {
+        if (m->soil_profile) cudaEventRecord(m->soil_ev[k], st);
+    };
+    tick(0);
     const unsigned grid_veg = lf::blocks_for(3 * m->n, lfsoil::SOIL_THREADS);
     const unsigned grid_def = lf::blocks_for(m->soil_list_cap, lfsoil::SOIL_THREADS);
     const unsigned grid_pix = lf::blocks_for(m->n, 256);
@@ -681,24 +697,38 @@ int soil_stage(lf_model *m)
             }
         }
         D.NoSubS = (int32_t *)ns->buf.p;
-        k_soil_veg<true><<<grid_veg, lfsoil::SOIL_THREADS, 0, st>>>(P, D);
-        LF_LAUNCH_CHECK();
-        for (int b = 0; b < lfsoil::NBUCKET; ++b) {
-            k_soil_veg_deferred<true><<<grid_def, lfsoil::SOIL_THREADS, 0, st>>>(P, D, b);
-            LF_LAUNCH_CHECK();
-        }
+    }
+    // resident blocks per SM requested from the compiler for the column kernels (registers vs occupancy):
+    // 4 -> ~108 registers, 6 -> 80, 8 -> 64 (with local-memory spills).  LF_SOIL_MINBLOCKS overrides (tuning).
+    static int minb = [] {
+        const char *e = getenv("LF_SOIL_MINBLOCKS");
+        int v = e ? atoi(e) : 6;
+        return (v == 4 || v == 6 || v == 8) ? v : 6;
+    }();
+#define LF_SOIL_LAUNCH(DG, MB)                                                                        \
+    do {                                                                                              \
+        k_soil_veg<DG, MB><<<grid_veg, lfsoil::SOIL_THREADS, 0, st>>>(P, D);                          \
+        LF_LAUNCH_CHECK();                                                                            \
+        tick(1);                                                                                      \
+        for (int b = 0; b < lfsoil::NBUCKET; ++b) {                                                   \
+            k_soil_veg_deferred<DG, MB><<<grid_def, lfsoil::SOIL_THREADS, 0, st>>>(P, D, b);          \
+            LF_LAUNCH_CHECK();                                                                        \
+            tick(2 + b);                                                                              \
+        }                                                                                             \
+    } while (0)
+    if (m->cfg.diagnostics) {
+        LF_SOIL_LAUNCH(true, 4);
         k_soil_pixel<true><<<grid_pix, 256, 0, st>>>(P, D);
     } else {
         // diagnostics-only parameter rows are never dereferenced in these instantiations
-        k_soil_veg<false><<<grid_veg, lfsoil::SOIL_THREADS, 0, st>>>(P, D);
-        LF_LAUNCH_CHECK();
-        for (int b = 0; b < lfsoil::NBUCKET; ++b) {
-            k_soil_veg_deferred<false><<<grid_def, lfsoil::SOIL_THREADS, 0, st>>>(P, D, b);
-            LF_LAUNCH_CHECK();
-        }
+        if (minb == 4) LF_SOIL_LAUNCH(false, 4);
+        else if (minb == 8) LF_SOIL_LAUNCH(false, 8);
+        else LF_SOIL_LAUNCH(false, 6);
         k_soil_pixel<false><<<grid_pix, 256, 0, st>>>(P, D);
     }
+#undef LF_SOIL_LAUNCH
     LF_LAUNCH_CHECK();
+    tick(8);
     return LF_OK;
 }
 
@@ -1063,6 +1093,59 @@ int lf_model_set(lf_model *m, const char *name, const double *values, int64_t co
     return LF_OK;
 }
 
+int lf_model_set_async(lf_model *m, const char *name, const double *values, int64_t count)
+{
+    if (!m || !name || !values) {
+        lf::set_error("lf_model_set_async: null pointer");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    Field *f = nullptr;
+    LF_CHECK(field(m, name, &f));
+    if (count != (int64_t)f->rows * m->n) {
+        lf::set_error("lf_model_set_async(%s): expected %lld values, got %lld", name, (long long)f->rows * m->n,
+                      (long long)count);
+        return LF_ERR_INVALID;
+    }
+    if (f->landuse) {
+        lf::set_error("lf_model_set_async(%s): land-use parameters are set with lf_model_set", name);
+        return LF_ERR_INVALID;
+    }
+    if (!m->copy_stream) LF_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    auto it = m->async_stage.find(name);
+    if (it == m->async_stage.end()) {
+        std::unique_ptr<lf::DevBuf<double>> b(new lf::DevBuf<double>());
+        LF_CHECK(b->alloc(count));
+        m->bytes += count * 8;
+        it = m->async_stage.emplace(name, std::move(b)).first;
+        cudaEvent_t e1, e2;
+        LF_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        LF_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        m->async_copied[name] = e1;
+        m->async_consumed[name] = e2;
+        LF_CUDA(cudaEventRecord(e2, lf::stream()));
+    }
+    cudaStream_t st = lf::stream();
+    double *stg = it->second->p;
+    // the staging buffer is free again once the previous translation kernel has run
+    LF_CUDA(cudaStreamWaitEvent(m->copy_stream, m->async_consumed[name], 0));
+    LF_CUDA(cudaMemcpyAsync(stg, values, count * sizeof(double), cudaMemcpyDefault, m->copy_stream));
+    LF_CUDA(cudaEventRecord(m->async_copied[name], m->copy_stream));
+    LF_CUDA(cudaStreamWaitEvent(st, m->async_copied[name], 0));
+    const int32_t *pop = f->order == SOIL ? m->g_of->pix_of_pos.p : m->g_ch->pix_of_pos.p;
+    k_rows_to_pos<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(stg, f->buf.p, pop, m->n, f->rows);
+    LF_LAUNCH_CHECK();
+    if (f->as_z) {
+        k_q_to_z<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(f->buf.p, m->n);
+        LF_LAUNCH_CHECK();
+    }
+    LF_CUDA(cudaEventRecord(m->async_consumed[name], st));
+    if (strcmp(name, "OFAlpha") == 0 || strcmp(name, "ChannelAlpha") == 0 || strcmp(name, "ChannelAlpha2") == 0 ||
+        strcmp(name, "ChanLength") == 0 || strcmp(name, "Chan2M3Start") == 0)
+        m->params_dirty = true;
+    return LF_OK;
+}
+
 int lf_model_get(lf_model *m, const char *name, double *values, int64_t count)
 {
     if (!m || !name || !values) {
@@ -1207,6 +1290,40 @@ int lf_model_stage_times(lf_model *m, int reset, double *soil_ms, double *overla
         m->t_soil = m->t_of = m->t_chan = 0;
         m->t_steps = 0;
     }
+    return LF_OK;
+}
+
+int lf_model_soil_stats(lf_model *m, int enable_timing, int64_t *deferred_columns, double *kernel_ms)
+{
+    if (!m) {
+        lf::set_error("lf_model_soil_stats: null model");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    LF_CUDA(cudaStreamSynchronize(lf::stream()));
+    if (deferred_columns) {
+        int32_t h[lfsoil::NBUCKET] = {0};
+        if (m->soil_list_cnt.p)
+            LF_CUDA(cudaMemcpy(h, m->soil_list_cnt.p, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int b = 0; b < lfsoil::NBUCKET; ++b) deferred_columns[b] = h[b];
+    }
+    if (kernel_ms) {
+        for (int k = 0; k < 8; ++k) kernel_ms[k] = 0.;
+        if (m->soil_profile && m->soil_ev.size() == 9)
+            for (int k = 0; k < 8; ++k) {
+                float t = 0.f;
+                if (cudaEventElapsedTime(&t, m->soil_ev[k], m->soil_ev[k + 1]) == cudaSuccess) kernel_ms[k] = t;
+                else cudaGetLastError();
+            }
+    }
+    if (enable_timing && m->soil_ev.empty()) {
+        for (int k = 0; k < 9; ++k) {
+            cudaEvent_t e;
+            LF_CUDA(cudaEventCreate(&e));
+            m->soil_ev.push_back(e);
+        }
+    }
+    m->soil_profile = enable_timing != 0;
     return LF_OK;
 }
 

@@ -319,8 +319,8 @@ __device__ __forceinline__ void soil_column(const Ptrs &P, const Diag &D, int64_
 constexpr int SOIL_THREADS = 128;
 
 // first pass: every (vegetation fraction, pixel) column
-template <bool DIAG>
-__global__ void __launch_bounds__(SOIL_THREADS) k_soil_veg(Ptrs P, Diag D)
+template <bool DIAG, int MINB>
+__global__ void __launch_bounds__(SOIL_THREADS, MINB) k_soil_veg(Ptrs P, Diag D)
 {
     const int64_t k = (int64_t)blockIdx.x * SOIL_THREADS + threadIdx.x;
     if (k >= 3 * P.n) return;
@@ -328,8 +328,8 @@ __global__ void __launch_bounds__(SOIL_THREADS) k_soil_veg(Ptrs P, Diag D)
     soil_column<DIAG>(P, D, k, v, k - (int64_t)v * P.n, true);
 }
 // second pass: the columns of one bucket list
-template <bool DIAG>
-__global__ void __launch_bounds__(SOIL_THREADS) k_soil_veg_deferred(Ptrs P, Diag D, int bucket)
+template <bool DIAG, int MINB>
+__global__ void __launch_bounds__(SOIL_THREADS, MINB) k_soil_veg_deferred(Ptrs P, Diag D, int bucket)
 {
     const int j = blockIdx.x * SOIL_THREADS + threadIdx.x;
     const int cnt = min(P.list_cnt[bucket], P.list_cap);

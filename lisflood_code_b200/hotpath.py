@@ -106,6 +106,12 @@ class HotPathModel(object):
         self._rows[name] = rows
         _capi.check(_capi.lib().lf_model_set(self._h, name.encode(), _capi.ptr(a), a.size))
 
+    def set_async(self, name, values):
+        """Queue a new value for a map without waiting (see lf_model_set_async); `values`: contiguous float64
+        NumPy array or torch tensor that stays untouched until the next get()."""
+        size = values.numel() if hasattr(values, "numel") else values.size
+        _capi.check(_capi.lib().lf_model_set_async(self._h, name.encode(), _capi.ptr(values), size))
+
     def get(self, name, rows=None):
         if name in ("LZOutflowToChannelPixel", "LZOutflowToChannel"):   # groundwater.py:142,180
             name = "LZOutflow"
@@ -158,6 +164,15 @@ class HotPathModel(object):
         _capi.check(_capi.lib().lf_model_stage_times(self._h, 1 if reset else 0, C.byref(a), C.byref(b), C.byref(c),
                                                      C.byref(k)))
         return {"soil_ms": a.value, "overland_ms": b.value, "channel_ms": c.value, "steps": k.value}
+
+    def soil_stats(self, enable_timing=True):
+        """Deferred-column counts per sub-step bucket and per-kernel device time of the last soil stage."""
+        cnt = np.zeros(6, np.int64)
+        ms = np.zeros(8, np.float64)
+        _capi.check(_capi.lib().lf_model_soil_stats(self._h, 1 if enable_timing else 0, _capi.ptr(cnt), _capi.ptr(ms)))
+        return {"deferred_columns": cnt.tolist(), "deferred_fraction": float(cnt.sum()) / (3.0 * self.N),
+                "kernel_ms": dict(zip(["k_soil_veg"] + ["deferred_%d" % b for b in range(6)] + ["k_soil_pixel"],
+                                      [round(x, 3) for x in ms.tolist()]))}
 
     def info(self):
         v = [C.c_int64() for _ in range(5)]

@@ -84,3 +84,22 @@ def test_stage_calls_equal_fused_step(gpu_lib):
     assert np.array_equal(A.get("ChanQAvg"), B.get("ChanQAvg"))
     with pytest.raises(AttributeError):
         A.NoSuchMap
+
+
+def test_async_input_path_equals_sync(gpu_lib):
+    """lf_model_set_async (copy stream + deferred layout translation) feeds the same values as lf_model_set."""
+    from lisflood_code_b200 import synthetic
+    S = synthetic.full_stack(70, 90, seed=13)
+    A, B = _model(gpu_lib, S, False), _model(gpu_lib, S, False)
+    for t in range(3):
+        F = synthetic.forcing(S, t, 13)
+        A.step(F)
+        keep = {k: np.ascontiguousarray(F[k], np.float64) for k in ("Rain", "SnowMelt", "ETRef", "EWRef", "ESRef", "LAI",
+                                                                    "LAITerm")}
+        for k, a in keep.items():
+            B.set_async(k, a)
+        B.set_flags("isFrozenSoil", F["isFrozenSoil"])
+        B.step()
+        assert np.array_equal(A.get("ChanQAvg"), B.get("ChanQAvg")), t
+    st = A.soil_stats(enable_timing=False)
+    assert sum(st["deferred_columns"]) > 0 and 0 < st["deferred_fraction"] < 0.5
