@@ -124,6 +124,11 @@ def ptr(a):
     if isinstance(a, int):
         return _vp(a)
     if hasattr(a, "data_ptr"):
+        if getattr(a, "is_cuda", False):
+            # the library works on its own stream: whatever torch kernels produce / still read this tensor
+            # must have finished before the pointer is used
+            import torch
+            torch.cuda.current_stream(a.device).synchronize()
         return _vp(a.data_ptr())
     return a.ctypes.data_as(_vp)
 
