@@ -702,8 +702,8 @@ int soil_stage(lf_model *m)
     // 4 -> ~108 registers, 6 -> 80, 8 -> 64 (with local-memory spills).  LF_SOIL_MINBLOCKS overrides (tuning).
     static int minb = [] {
         const char *e = getenv("LF_SOIL_MINBLOCKS");
-        int v = e ? atoi(e) : 6;
-        return (v == 4 || v == 6 || v == 8) ? v : 6;
+        int v = e ? atoi(e) : 8;
+        return (v == 4 || v == 6 || v == 8) ? v : 8;
     }();
 #define LF_SOIL_LAUNCH(DG, MB)                                                                        \
     do {                                                                                              \
@@ -722,8 +722,8 @@ int soil_stage(lf_model *m)
     } else {
         // diagnostics-only parameter rows are never dereferenced in these instantiations
         if (minb == 4) LF_SOIL_LAUNCH(false, 4);
-        else if (minb == 8) LF_SOIL_LAUNCH(false, 8);
-        else LF_SOIL_LAUNCH(false, 6);
+        else if (minb == 6) LF_SOIL_LAUNCH(false, 6);
+        else LF_SOIL_LAUNCH(false, 8);  // measured best on B200
         k_soil_pixel<false><<<grid_pix, 256, 0, st>>>(P, D);
     }
 #undef LF_SOIL_LAUNCH
