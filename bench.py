@@ -429,6 +429,79 @@ def run_reference_c3(args):
                       "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def run_c4(args):
+    """BASELINE.json configs[3]: kinematic routing on ONE raster cut along the drainage graph across the ranks
+    (lisflood_code_b200/parallel.py), NCCL exchange of boundary discharges only.  Strong scaling: the raster is
+    fixed (--c4-rows, default 6000x6000; the named 20000x20000 needs the partitioner's host arrays in int32)."""
+    rank, world, local = dist_env()
+    import torch
+    import torch.distributed as dist
+    from lisflood_code_b200 import _capi, synthetic
+    from lisflood_code_b200.parallel import DistributedKinematicWave
+    torch.cuda.set_device(local)
+    _capi.check(_capi.lib().lf_device_init(local))
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    R = args.c4_rows
+    ldd2, mask = synthetic.random_ldd(R, R, seed=400, noise=args.ldd_noise)
+    n = int(mask.sum())
+    alpha, q0, q = synthetic.routing_fields(n, 400)
+    tps = 48
+    t0 = time.time()
+    D = DistributedKinematicWave(ldd2[mask], mask, alpha, 0.6, 5000.0, 3600.0, max_steps=tps)
+    t_init = time.time() - t0
+    D.set_discharge(q0)
+    D.set_lateral_inflow(q)
+    scales = np.random.default_rng(9).uniform(0.5, 1.5, (8, tps))
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        dist.barrier()
+        _capi.synchronize()
+
+    for w in range(W):
+        D.run(tps, inflow_scale=scales[w % 8])
+    barrier()
+    _capi.launch_count(reset=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        t0 = time.perf_counter()
+        _capi.timer_start()
+        for k in range(K):
+            D.run(tps, inflow_scale=scales[(W + k) % 8])
+        ms = _capi.timer_stop()
+        barrier()
+        wall = time.perf_counter() - t0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = _capi.launch_count()
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        value = n * tps * K / (ms * 1e-3)
+        ach = ALG_BYTES_ROUTING * max(D.part.loads) * tps * K / (ms * 1e-3) / 1e9
+        print(json.dumps({"metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K,
+                          "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "C4 synthetic %dx%d raster, kinematic routing only, LDD-cut across %d GPUs "
+                                                 "(sub-trees bin-packed, trunk on rank 0), NCCL exchange of boundary "
+                                                 "discharges" % (R, R, world), "cells": n, "timesteps_per_step": tps,
+                                     "cells_per_rank": D.part.loads, "cut_edges_per_rank": D.part.n_cut,
+                                     "trunk_pixels": int(D.part.trunk.sum()),
+                                     "bytes_exchanged_per_step": int(sum(D.part.n_cut) * tps * 8)},
+                          "e2e": {"value": n * tps * K / wall, "unit": "cell-updates/s", "h2d_bytes_per_step": tps * 8,
+                                  "d2h_bytes_per_step": 0, "note": "host wall clock around the same K steps (inputs are "
+                                  "the 48 inflow multipliers per step)"},
+                          "gpu_launches": int(launches), "clocks": clk.summary(),
+                          "roofline": {"bound": "hbm", "kernel": "k_kw_diagonal<true,true> (busiest rank)",
+                                       "achieved": round(ach, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                                       "frac": round(ach / peak, 4), "traffic": None},
+                          "cpu_baseline": None, "init_s": round(t_init, 2)}))
+    dist.destroy_process_group()
+
+
 def best_threads(ora, wl, lisf_oracle):
     """Thread count that maximises the oracle's throughput on this host (level-synchronous OpenMP
     does not always scale to every hardware thread); 2 timesteps per candidate."""
@@ -501,7 +574,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"])
+    ap.add_argument("--c4-rows", type=int, default=6000)
     ap.add_argument("--rows", type=int, default=10000)
     ap.add_argument("--cols", type=int, default=10000)
     ap.add_argument("--ldd-noise", type=float, default=0.5)
@@ -511,7 +585,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e and CPU legs (for runs under ncu)")
     args = ap.parse_args()
-    if args.workload == "c3":
+    if args.workload == "c4" and args.impl != "reference":
+        run_c4(args)
+    elif args.workload == "c3":
         if args.impl == "reference":
             run_reference_c3(args)
         else:

@@ -108,6 +108,14 @@ int lf_router_set_inflow(lf_router *r, int section, const double *specific_later
  * wavefront: step s uses lateral inflow q * q_scale[s] (q_scale NULL = all ones;
  * host f64[nsteps]).  Same arithmetic per (pixel, step) as nsteps calls of lf_router_route. */
 int lf_router_run(lf_router *r, int section, int nsteps, const double *q_scale, int *nonfinite);
+/* LDD-cut domain decomposition (one router per GPU on its sub-mask; lisflood_code_b200/parallel.py):
+ * xslot i32[N] (compressed order of this router): -1 plain pixel; k >= 0: the pixel's new discharge of every step
+ * of lf_router_run is ALSO written to export_buf[k * cap_steps + step]; k <= -2: ghost of a pixel owned by another
+ * rank, not solved -- its value of each step is read from import_buf[(-2 - k) * cap_steps + step].  Both buffers are
+ * DEVICE memory owned by the caller (e.g. torch tensors handed to NCCL) and hold the router's native state
+ * representation (z = Q^(1/5) when beta == 0.6, else Q), so a cut network reproduces the uncut one bit for bit. */
+int lf_router_set_exchange(lf_router *r, const int32_t *xslot, int32_t n_export, int32_t n_import, double *export_buf,
+                           const double *import_buf, int32_t cap_steps);
 void lf_router_destroy(lf_router *r);
 
 /* ---------------------------------------------------------------------------------------------

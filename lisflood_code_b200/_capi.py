@@ -57,6 +57,7 @@ SIGNATURES = {
     "lf_router_get_discharge": (C.c_int, [_vp, C.c_int, _f64]),
     "lf_router_set_inflow": (C.c_int, [_vp, C.c_int, _f64]),
     "lf_router_run": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
+    "lf_router_set_exchange": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32]),
     "lf_router_destroy": (None, [_vp]),
     "lf_model_create": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "lf_model_info": (C.c_int, [_vp, C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s),

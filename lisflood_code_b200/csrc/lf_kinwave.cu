@@ -29,6 +29,12 @@ struct lf_router {
     lf::DevBuf<double> stage_a, stage_b;  // compressed (user) order staging
     lf::DevBuf<double> scale;
     lf::DevBuf<int> flag;
+    // LDD-cut exchange (multi-GPU): per position -1 = plain pixel, >= 0 = export slot (its new value of every step
+    // is also written to xport), <= -2 = ghost of a pixel owned by another rank (value read from xin, not solved)
+    lf::DevBuf<int32_t> xslot;
+    double *xport = nullptr;
+    const double *xin = nullptr;
+    int32_t x_cap_steps = 0, n_export = 0, n_import = 0;
 };
 
 namespace {
@@ -84,13 +90,19 @@ __global__ void k_nonfinite(const double *__restrict__ v, int64_t n, int *__rest
 }
 
 // One diagonal of the space-time wavefront.  Positions [lo, hi) = levels d-S+1..d.
+struct XPtrs {
+    const int32_t *xslot;
+    double *xport;
+    const double *xin;
+    int32_t cap_steps;
+};
 constexpr int KW_THREADS = 128;
-template <bool QZ>
+template <bool QZ, bool HASX>
 __global__ void __launch_bounds__(KW_THREADS)
     k_kw_diagonal(int lo, int hi, int d, int64_t g0, const int32_t *__restrict__ lev,
                   const int32_t *__restrict__ cfirst, const double *__restrict__ a, const double *__restrict__ dx,
                   double dx_scalar, const double *__restrict__ q, const double *__restrict__ scale, double *Q0,
-                  double *Q1, lfkw::Params P)
+                  double *Q1, lfkw::Params P, XPtrs X)
 {
     int i = lo + blockIdx.x * KW_THREADS + threadIdx.x;
     if (i >= hi) return;
@@ -98,6 +110,14 @@ __global__ void __launch_bounds__(KW_THREADS)
     int64_t gs = g0 + s;  // global index of this routing step; parity selects the buffer
     double *Qnew = (gs & 1) ? Q1 : Q0;
     const double *Qold = (gs & 1) ? Q0 : Q1;
+    int xs = -1;
+    if (HASX) {
+        xs = X.xslot[i];
+        if (xs <= -2) {  // ghost: the owner's value of this step (router-native representation), layout [slot][step]
+            Qnew[i] = X.xin[(int64_t)(-2 - xs) * X.cap_steps + s];
+            return;
+        }
+    }
     int c0 = cfirst[i], c1 = cfirst[i + 1];
     double qo = Qold[i];
     double qs = q[i];
@@ -105,17 +125,31 @@ __global__ void __launch_bounds__(KW_THREADS)
     double lateral = qs * (dx ? dx[i] : dx_scalar);  // lateral_inflow = q * dx, kinematic_wave_parallel.py:163
     double ai = a[i];
     double U = 0.0;
+    double out;
     if (QZ) {
         for (int k = c0; k < c1; ++k) U += lfkw::pow5(Qnew[k]);  // buffers hold z = Q^(1/5)
-        Qnew[i] = lfkw::solve_z(U, qo, lateral, ai);
+        out = lfkw::solve_z(U, qo, lateral, ai);
     } else {
         for (int k = c0; k < c1; ++k) U += Qnew[k];  // upstream discharge of this step, slot order (tools:57-58)
-        Qnew[i] = lfkw::solve(U, qo, lateral, ai, P);
+        out = lfkw::solve(U, qo, lateral, ai, P);
     }
+    Qnew[i] = out;
+    if (HASX && xs >= 0) X.xport[(int64_t)xs * X.cap_steps + s] = out;
+}
+
+__global__ void k_i32_to_pos(const int32_t *__restrict__ src, int32_t *__restrict__ dst,
+                             const int32_t *__restrict__ pix_of_pos, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[pix_of_pos[i]];
 }
 
 int run_steps(lf_router *r, int sec, int nsteps, const double *d_scale)
 {
+    if (r->xslot.p && nsteps > r->x_cap_steps) {
+        lf::set_error("lf_router_run: %d steps exceed the exchange buffers (%d steps)", nsteps, r->x_cap_steps);
+        return LF_ERR_INVALID;
+    }
     lf_graph *g = r->g;
     cudaStream_t st = lf::stream();
     const std::vector<int32_t> &ls = g->h_level_start;
@@ -126,14 +160,20 @@ int run_steps(lf_router *r, int sec, int nsteps, const double *d_scale)
         int hi_lev = d < L - 1 ? d : L - 1;
         int lo = ls[lo_lev], hi = ls[hi_lev + 1];
         if (hi <= lo) continue;
-        if (r->P.quintic)
-            k_kw_diagonal<true><<<lf::blocks_for(hi - lo, KW_THREADS), KW_THREADS, 0, st>>>(
-                lo, hi, d, g0, g->lev_of_pos.p, g->cfirst.p, r->a[sec].p, r->dx_is_array ? r->dx.p : nullptr, r->dx_scalar,
-                r->q[sec].p, d_scale, r->Q[sec][0].p, r->Q[sec][1].p, r->P);
-        else
-            k_kw_diagonal<false><<<lf::blocks_for(hi - lo, KW_THREADS), KW_THREADS, 0, st>>>(
-                lo, hi, d, g0, g->lev_of_pos.p, g->cfirst.p, r->a[sec].p, r->dx_is_array ? r->dx.p : nullptr, r->dx_scalar,
-                r->q[sec].p, d_scale, r->Q[sec][0].p, r->Q[sec][1].p, r->P);
+        const bool hasx = r->xslot.p != nullptr;
+        XPtrs X{r->xslot.p, r->xport, r->xin, r->x_cap_steps};
+#define LF_KW_LAUNCH(QZ_, HX_)                                                                                        \
+    k_kw_diagonal<QZ_, HX_><<<lf::blocks_for(hi - lo, KW_THREADS), KW_THREADS, 0, st>>>(                              \
+        lo, hi, d, g0, g->lev_of_pos.p, g->cfirst.p, r->a[sec].p, r->dx_is_array ? r->dx.p : nullptr, r->dx_scalar,   \
+        r->q[sec].p, d_scale, r->Q[sec][0].p, r->Q[sec][1].p, r->P, X)
+        if (r->P.quintic) {
+            if (hasx) LF_KW_LAUNCH(true, true);
+            else LF_KW_LAUNCH(true, false);
+        } else {
+            if (hasx) LF_KW_LAUNCH(false, true);
+            else LF_KW_LAUNCH(false, false);
+        }
+#undef LF_KW_LAUNCH
         LF_LAUNCH_CHECK();
     }
     r->steps_done[sec] = g0 + nsteps;
@@ -346,6 +386,35 @@ int lf_router_route(lf_router *r, double *discharge, const double *specific_late
     LF_CUDA(cudaMemcpyAsync(discharge, r->stage_a.p, n * sizeof(double), cudaMemcpyDefault, st));
     LF_CHECK(nan_check(r, section, nonfinite));
     LF_CUDA(cudaStreamSynchronize(st));
+    return LF_OK;
+}
+
+int lf_router_set_exchange(lf_router *r, const int32_t *xslot, int32_t n_export, int32_t n_import, double *export_buf,
+                           const double *import_buf, int32_t cap_steps)
+{
+    if (!r || !xslot || cap_steps < 1 || n_export < 0 || n_import < 0 || (n_export > 0 && !export_buf) ||
+        (n_import > 0 && !import_buf)) {
+        lf::set_error("lf_router_set_exchange: bad arguments");
+        return LF_ERR_INVALID;
+    }
+    if ((n_export > 0 && !lf::is_device_ptr(export_buf)) || (n_import > 0 && !lf::is_device_ptr(import_buf))) {
+        lf::set_error("lf_router_set_exchange: exchange buffers must be device memory");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    lf::DevBuf<int32_t> tmp;
+    LF_CHECK(tmp.alloc(r->n));
+    LF_CHECK(r->xslot.alloc(r->n));
+    LF_CUDA(cudaMemcpyAsync(tmp.p, xslot, r->n * sizeof(int32_t), cudaMemcpyDefault, st));
+    k_i32_to_pos<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(tmp.p, r->xslot.p, r->g->pix_of_pos.p, r->n);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaStreamSynchronize(st));
+    r->xport = export_buf;
+    r->xin = import_buf;
+    r->x_cap_steps = cap_steps;
+    r->n_export = n_export;
+    r->n_import = n_import;
     return LF_OK;
 }
 

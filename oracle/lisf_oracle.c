@@ -174,10 +174,13 @@ static inline int solve_1_pixel(int64_t pix, double *discharge, const double *co
 }
 
 /* kinematicRouting, tools:34-46: serial over orders, parallel (prange -> OpenMP) within one. */
+/* `fixed` (optional, u8[N]): pixels whose discharge is PRESCRIBED (fixed_values) instead of solved -- the ghost
+ * pixels of an LDD-cut partition (tests of lisflood_code_b200/parallel.py); not part of the reference. */
 int64_t lfo_kinematic_routing(double *discharge, const double *constant, const int64_t *upstream,
                               int64_t ups_stride, const int64_t *num_ups, const int64_t *ordered,
                               const int64_t *start_stop, int64_t n_orders, double beta,
-                              const double *a_dx_div_dt, const double *b_a_dx_div_dt)
+                              const double *a_dx_div_dt, const double *b_a_dx_div_dt, const uint8_t *fixed,
+                              const double *fixed_values)
 {
     double inv_beta = 1.0 / beta, b_minus_1 = beta - 1.0;
     int64_t iters = 0;
@@ -192,9 +195,14 @@ int64_t lfo_kinematic_routing(double *discharge, const double *constant, const i
         int thr = (int)((last - first) / 128);
         thr = thr < 1 ? 1 : (thr > max_thr ? max_thr : thr);
 #pragma omp parallel for schedule(static) reduction(+ : iters) num_threads(thr) if (thr > 1)
-        for (int64_t i = first; i < last; ++i)
+        for (int64_t i = first; i < last; ++i) {
+            if (fixed && fixed[ordered[i]]) {
+                discharge[ordered[i]] = fixed_values[ordered[i]];
+                continue;
+            }
             iters += solve_1_pixel(ordered[i], discharge, constant, upstream, ups_stride, num_ups, a_dx_div_dt,
                                    b_a_dx_div_dt, beta, inv_beta, b_minus_1);
+        }
     }
     return iters;
 }
@@ -210,7 +218,7 @@ int64_t lfo_kinematic_wave_routing(double *discharge, const double *q_lat, int64
                                    double dx_scalar, const double *a_dx_div_dt, const double *b_a_dx_div_dt,
                                    double beta, const int64_t *upstream, int64_t ups_stride,
                                    const int64_t *num_ups, const int64_t *ordered, const int64_t *start_stop,
-                                   int64_t n_orders, double *work)
+                                   int64_t n_orders, double *work, const uint8_t *fixed, const double *fixed_values)
 {
 #pragma omp parallel for schedule(static)
     for (int64_t p = 0; p < n; ++p) {
@@ -218,5 +226,5 @@ int64_t lfo_kinematic_wave_routing(double *discharge, const double *q_lat, int64
         work[p] = a_dx_div_dt[p] * pow(discharge[p], beta) + ql;
     }
     return lfo_kinematic_routing(discharge, work, upstream, ups_stride, num_ups, ordered, start_stop, n_orders,
-                                 beta, a_dx_div_dt, b_a_dx_div_dt);
+                                 beta, a_dx_div_dt, b_a_dx_div_dt, fixed, fixed_values);
 }

@@ -37,7 +37,7 @@ def lib():
         L.lfo_ldd_graph.restype = C.c_int
         L.lfo_kinematic_wave_routing.argtypes = [_f64p, _f64p, C.c_int64, C.c_void_p, C.c_double, _f64p, _f64p,
                                                  C.c_double, _i64p, C.c_int64, _i64p, _i64p, _i64p, C.c_int64,
-                                                 _f64p]
+                                                 _f64p, C.c_void_p, C.c_void_p]
         L.lfo_kinematic_wave_routing.restype = C.c_int64
         _LIB = L
     return _LIB
@@ -89,7 +89,10 @@ class KinematicWaveOracle:
         self.kinematic_wave_warning_printed = False
         self.last_newton_iterations = 0
 
-    def kinematicWaveRouting(self, discharge, specific_lateral_inflow, section="main_channel"):
+    def kinematicWaveRouting(self, discharge, specific_lateral_inflow, section="main_channel", fixed=None,
+                             fixed_values=None):
+        """`fixed` / `fixed_values` (optional): pixels whose discharge is prescribed instead of solved -- the
+        ghost pixels of an LDD-cut partition; not part of the reference API."""
         if section == "main_channel":
             a, ba = self.a_dx_div_dt_channel, self.b_a_dx_div_dt_channel
         elif section == "floodplains":
@@ -103,11 +106,14 @@ class KinematicWaveOracle:
         else:
             dxp, dxs = None, float(self.space_delta)
         q = np.ascontiguousarray(specific_lateral_inflow, np.float64)
+        fx = None if fixed is None else np.ascontiguousarray(fixed, np.uint8)
+        fv = None if fixed_values is None else np.ascontiguousarray(fixed_values, np.float64)
         assert discharge.dtype == np.float64 and discharge.flags.c_contiguous
         self.last_newton_iterations = lib().lfo_kinematic_wave_routing(
             discharge, q, n, dxp, dxs, a, ba, self.beta, self.upstream_lookup, self.upstream_lookup.shape[1],
             self.num_upstream_pixels, self.pixels_ordered, self.order_start_stop.ravel(),
-            self.order_start_stop.shape[0], self._work)
+            self.order_start_stop.shape[0], self._work,
+            None if fx is None else fx.ctypes.data, None if fv is None else fv.ctypes.data)
         if self.flagnancheck and not self.kinematic_wave_warning_printed:
             if not np.all(np.isfinite(discharge)):
                 import warnings
