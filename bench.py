@@ -445,7 +445,7 @@ def run_c4(args):
         os.environ.setdefault("MASTER_PORT", "29533")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     R = args.c4_rows
-    ldd2, mask = synthetic.random_ldd(R, R, seed=400, noise=args.ldd_noise)
+    ldd2, mask = synthetic.random_ldd(R, R, seed=400, noise=args.ldd_noise, single_outlet=True)   # ONE basin: must be cut
     n = int(mask.sum())
     alpha, q0, q = synthetic.routing_fields(n, 400)
     tps = 48

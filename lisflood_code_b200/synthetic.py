@@ -14,12 +14,14 @@ import numpy as np
 _NEIGH = [(-1, -1, 7), (-1, 0, 8), (-1, 1, 9), (0, -1, 4), (0, 1, 6), (1, -1, 1), (1, 0, 2), (1, 1, 3)]
 
 
-def random_ldd(rows, cols, seed=0, noise=3.0, tilt=1.0, mask_fraction=0.0):
+def random_ldd(rows, cols, seed=0, noise=3.0, tilt=1.0, mask_fraction=0.0, single_outlet=False):
     """Random D8 drainage forest: elevation = tilted plane + Gaussian noise, every cell drains to
     its steepest-descent neighbour, a cell with no strictly lower neighbour is a pit (code 5).
 
     noise/tilt ~ 3   -> shallow forest (tens of levels, many pits)
     noise/tilt ~ 0.3 -> deep trees (about `rows` levels)
+    single_outlet: the south edge collects everything into one outlet (one basin that must be CUT to be shared
+    between GPUs).
     Returns (ldd_codes float64[rows, cols], land_mask bool[rows, cols]); cells outside the mask
     carry code 0.
     """
@@ -45,6 +47,15 @@ def random_ldd(rows, cols, seed=0, noise=3.0, tilt=1.0, mask_fraction=0.0):
         better = drop > best
         best = np.where(better, drop, best)
         code = np.where(better, float(k), code)
+    if single_outlet:
+        # one big basin: the south edge becomes a collector that drains to its centre cell (the only outlet of
+        # everything that reaches the edge); interior sinks remain separate small catchments
+        c0 = cols // 2
+        code[rows - 1, :c0] = 6.0
+        code[rows - 1, c0 + 1:] = 4.0
+        code[rows - 1, c0] = 5.0
+        land = land.copy()
+        land[rows - 1, :] = True
     code[~land] = 0.0
     return code, land
 

@@ -11,7 +11,7 @@ from conftest import ROOT
 
 def _case(rows=60, cols=48, seed=5, noise=0.3, maskf=0.1):
     from lisflood_code_b200 import synthetic
-    ldd, mask = synthetic.random_ldd(rows, cols, seed=seed, noise=noise, mask_fraction=maskf)
+    ldd, mask = synthetic.random_ldd(rows, cols, seed=seed, noise=noise, mask_fraction=maskf, single_outlet=True)
     n = int(mask.sum())
     alpha, q0, q = synthetic.routing_fields(n, seed)
     dx = np.random.default_rng(seed).uniform(3000, 7000, n)
