@@ -16,6 +16,7 @@ D2H of the resulting discharge map inside the timed region), `roofline` for the 
 import argparse
 import json
 import os
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's banner out of stdout: the JSON line must be the last line
 import subprocess
 import sys
 import threading
@@ -223,7 +224,7 @@ def run_ours(args):
                         "h2d_bytes_per_step": int(wl.n * 8 + tps * 8), "d2h_bytes_per_step": int(wl.n * 8)},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
                 "init_s": round(t_init, 3)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if use_dist:
         dist.destroy_process_group()
 
@@ -371,7 +372,7 @@ def run_c3(args):
                 "roofline_stencil": roof_soil, "roofline_routing": roof_chan, "stage_ms_per_step": stage,
                 "soil_stats": soil_stats,
                 "cpu_baseline": cpu, "init_s": round(t_init, 2)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if use_dist:
         dist.destroy_process_group()
 
@@ -445,7 +446,7 @@ def run_c4(args):
         os.environ.setdefault("MASTER_PORT", "29533")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     R = args.c4_rows
-    ldd2, mask = synthetic.random_ldd(R, R, seed=400, noise=args.ldd_noise, single_outlet=True)   # ONE basin: must be cut
+    ldd2, mask = synthetic.random_ldd(R, R, seed=400, noise=args.c4_noise, single_outlet=True)   # ONE basin: must be cut
     n = int(mask.sum())
     alpha, q0, q = synthetic.routing_fields(n, 400)
     tps = 48
@@ -498,7 +499,7 @@ def run_c4(args):
                           "roofline": {"bound": "hbm", "kernel": "k_kw_diagonal<true,true> (busiest rank)",
                                        "achieved": round(ach, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                                        "frac": round(ach / peak, 4), "traffic": None},
-                          "cpu_baseline": None, "init_s": round(t_init, 2)}))
+                          "cpu_baseline": None, "init_s": round(t_init, 2)}), flush=True)
     dist.destroy_process_group()
 
 
@@ -576,6 +577,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"])
     ap.add_argument("--c4-rows", type=int, default=6000)
+    ap.add_argument("--c4-noise", type=float, default=0.2, help="noise/tilt of the C4 basin (0.2: a single catchment)")
     ap.add_argument("--rows", type=int, default=10000)
     ap.add_argument("--cols", type=int, default=10000)
     ap.add_argument("--ldd-noise", type=float, default=0.5)

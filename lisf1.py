@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""lisf1.py settings.xml [-q -v -l -c -h -t -d -n -i -s]
+
+Entry surface of LISFLOOD (reference: src/lisf1.py, src/lisflood/main.py:164-226) for the B200 hot path.  The
+settings file has the reference's structure (<lfoptions>, <lfuser>, <lfbinding>, $(var) substitution).  Because
+PCRaster / NetCDF IO is out of scope here, the bindings of this entry point name NumPy archives:
+
+    MaskMap        .npy  bool[rows, cols]            StateFile    .npz  every static map / initial state by its
+    ForcingFile    .npz  Rain, SnowMelt, ETRef ...         (reference attribute name, see synthetic.full_stack)
+                         stacked as (steps, ...)      DisOut       .npy  written: ChanQAvg (= dis) per step
+    StepStart, StepEnd   1-based step numbers
+"""
+import sys
+
+import numpy as np
+
+
+def main(*args):
+    argv = list(args) if args else sys.argv[1:]
+    if not argv:
+        print(__doc__)
+        return 1
+    from lisflood_code_b200.global_modules.settings import LisSettings
+    from lisflood_code_b200.hotpath import HotPathModel
+    from lisflood_code_b200.Lisflood_dynamic import LisfloodModel_dyn
+    settings = LisSettings(argv[0], argv[1:])
+    settings.check_supported()
+    b, flags = settings.binding, settings.flags
+    S = {k: (v.item() if v.ndim == 0 else v) for k, v in np.load(b["StateFile"], allow_pickle=False).items()}
+    S["mask"] = np.load(b["MaskMap"]).astype(bool)
+    S["SplitRouting"] = bool(settings.options["SplitRouting"]) and not settings.options["InitLisflood"]
+    for k in ("N", "rows", "cols", "NoRoutSteps"):
+        if k in S:
+            S[k] = int(S[k])
+    if flags["initonly"]:
+        return 0
+    var = HotPathModel(S)
+    model = LisfloodModel_dyn(var)
+    forcing = np.load(b["ForcingFile"])
+    first, last = int(b.get("StepStart", 1)), int(b.get("StepEnd", forcing["Rain"].shape[0]))
+    dis = []
+    for step in range(first, last + 1):
+        F = {k: forcing[k][step - 1] for k in forcing.files}
+        model.dynamic(F)
+        dis.append(var.get("ChanQAvg"))
+        if flags["loud"]:
+            print("%-6i %10.2f" % (step, float(dis[-1].max())))
+        elif not (flags["quiet"] or flags["veryquiet"]):
+            sys.stdout.write("\r%d" % step)
+            sys.stdout.flush()
+        if flags["nancheck"] and not np.all(np.isfinite(dis[-1])):
+            import warnings
+            from lisflood_code_b200.global_modules.errors import LisfloodWarning
+            warnings.warn(LisfloodWarning("Warning: NaN or Inf values after kinematicRouting module."))
+    np.save(b["DisOut"], np.stack(dis))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,32 @@
+"""Per-step call order of the hot path (reference: src/lisflood/Lisflood_dynamic.py:114-229), driving the
+HydroModule mirrors on a device-resident HotPathModel.  Feeder modules (readmeteo, snow, frost, leafarea ...)
+are out of scope: their products of the step are handed in as `forcing`."""
+from .hydrological_modules.groundwater import groundwater
+from .hydrological_modules.opensealed import opensealed
+from .hydrological_modules.routing import routing
+from .hydrological_modules.soil import soil
+from .hydrological_modules.soilloop import soilloop
+from .hydrological_modules.surface_routing import surface_routing
+
+
+class LisfloodModel_dyn(object):
+    def __init__(self, var):
+        self.var = var
+        self.soilloop_module = soilloop(var)
+        self.soil_module = soil(var)
+        self.opensealed_module = opensealed(var)
+        self.groundwater_module = groundwater(var)
+        self.surface_routing_module = surface_routing(var)
+        self.routing_module = routing(var)
+        self.NoRoutSteps = var.NoRoutSteps
+
+    def dynamic(self, forcing):
+        self.var.set_forcing(forcing)
+        self.soilloop_module.dynamic_canopy()        # :114
+        self.soilloop_module.dynamic_soil()          # :123
+        self.opensealed_module.dynamic()             # :129
+        self.soil_module.dynamic_perpixel()          # :147
+        self.groundwater_module.dynamic()            # :149
+        self.surface_routing_module.dynamic()        # :165
+        for NoRoutingExecuted in range(self.NoRoutSteps):   # :179-180
+            self.routing_module.dynamic(NoRoutingExecuted)

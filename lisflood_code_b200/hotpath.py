@@ -75,6 +75,8 @@ class HotPathModel(object):
                                       C.byref(h)))
         self.__dict__["_h"] = h
         self.__dict__["_rows"] = {}
+        self.__dict__["NoRoutSteps"] = int(S["NoRoutSteps"])
+        self.__dict__["_soil_calls"] = []
         todo = dict(PARAMETERS)
         todo.update(STATE)
         if self.split:
@@ -142,6 +144,27 @@ class HotPathModel(object):
         for name, rows in FORCING.items():
             self.set(name, F[name], rows)
         self.set_flags("isFrozenSoil", F["isFrozenSoil"])
+
+    # ---- HydroModule call protocol (hydrological_modules/*.py mirrors) ----------------------------------
+    _SOIL_SEQUENCE = ("dynamic_canopy", "dynamic_soil", "opensealed", "dynamic_perpixel", "groundwater")
+
+    def _soil_stage_call(self, who):
+        """The five soil-stage module calls of a step (Lisflood_dynamic.py:114-149) in the reference's order; the
+        first one runs the fused device stage."""
+        calls = self._soil_calls
+        expected = self._SOIL_SEQUENCE[len(calls) % 5]
+        if who != expected:
+            raise RuntimeError("%s called out of order (expected %s): the hot-path modules follow "
+                               "Lisflood_dynamic.py:114-149" % (who, expected))
+        if len(calls) % 5 == 0:
+            del calls[:]
+            self.soil()
+        calls.append(who)
+
+    def _require_soil_stage_done(self):
+        if len(self._soil_calls) != 5:
+            raise RuntimeError("surface_routing.dynamic before the soil-stage modules of this step have all run")
+        del self._soil_calls[:]
 
     # ---- stages ---------------------------------------------------------------------------------------
     def soil(self):

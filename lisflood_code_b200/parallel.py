@@ -17,8 +17,8 @@ the raster is cut along the drainage graph, not along raster tiles:
 
 Every rank builds its router on its own sub-mask of the global raster (links that leave the sub-mask vanish in
 lf_ldd_build exactly like in the reference), so the cut network reproduces the uncut one BIT FOR BIT: same
-upstream slots, same summation order, same values (checked by tests/test_parallel_cpu.py on gloo with the CPU
-oracle as compute stand-in and by tools/run_dist_check.py on NCCL).
+upstream slots, same summation order, same values (checked by tests/test_parallel_cpu.py on gloo with a CPU
+stand-in router injected by the test, and by tools/run_dist_check.py on NCCL with the real routers).
 """
 import heapq
 
@@ -116,24 +116,62 @@ class _Comm(object):
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
 
 
+class GpuRouterBackend(object):
+    """Routers of this package + NCCL.  A backend builds the local router of a rank and runs its steps; the CPU
+    tests inject a stand-in with the same protocol (tests/test_parallel_cpu.py) to exercise the host logic."""
+    device = "cuda"
+
+    def __init__(self, ldd_local, sub_mask, alpha, beta, dx, dt, xslot, n_exp, n_imp, export, imported, max_steps, world):
+        from . import _capi
+        from .hydrological_modules.kinematic_wave_parallel import kinematicWave
+        self._capi = _capi
+        self.kw = kinematicWave(ldd_local, sub_mask, alpha, beta, dx, dt)
+        if world > 1:
+            _capi.check(_capi.lib().lf_router_set_exchange(self.kw._router, _capi.ptr(xslot), n_exp, n_imp,
+                                                           _capi.ptr(export), _capi.ptr(imported), max_steps))
+
+    def set_discharge(self, q):
+        self.kw.set_discharge(q)
+
+    def set_lateral_inflow(self, q):
+        self.kw.set_lateral_inflow(q)
+
+    def run(self, nsteps, inflow_scale):
+        self.kw.run(nsteps, inflow_scale=inflow_scale)
+
+    def get_discharge(self):
+        return self.kw.get_discharge()
+
+    def before_send(self):
+        self._capi.synchronize()       # the export buffer is written on the library's stream
+
+    def after_recv(self):
+        import torch
+        torch.cuda.current_stream().synchronize()
+
+    @staticmethod
+    def global_graph(ldd, mask, beta):
+        from .hydrological_modules.kinematic_wave_parallel import kinematicWave
+        return kinematicWave(ldd, mask, np.ones(int(np.asarray(mask).sum())), beta, 1.0, 1.0)
+
+
 class DistributedKinematicWave(object):
     """kinematicWave over an LDD-cut partition: same constructor arguments as the reference class
     (global arrays on every rank), device-resident protocol set_discharge / set_lateral_inflow / run /
-    gather_discharge.  backend="gpu": lisflood_code_b200 routers + NCCL; backend="oracle": the CPU oracle +
-    gloo (tests only)."""
+    gather_discharge.  `backend`: class with the protocol of GpuRouterBackend (default)."""
 
     def __init__(self, compressed_encoded_ldd, land_mask, alpha_channel, beta, space_delta, time_delta, max_steps=64,
-                 backend="gpu", subtree_fraction=0.25):
+                 backend=None, subtree_fraction=0.25):
         import torch
         self.torch = torch
         self.comm = _Comm()
         rank, world = self.comm.rank, self.comm.world
+        backend = backend or GpuRouterBackend
         mask = np.asarray(land_mask, bool)
         ldd = np.asarray(compressed_encoded_ldd, np.float64)
         graph = None
-        if backend == "gpu" and world > 1:
-            from .hydrological_modules.kinematic_wave_parallel import kinematicWave as _KW
-            graph = _KW(ldd, mask, np.ones(int(mask.sum())), beta, 1.0, 1.0)   # global graph, used for the partition only
+        if world > 1 and hasattr(backend, "global_graph"):
+            graph = backend.global_graph(ldd, mask, beta)   # global graph, used for the partition only
         self.part = P = Partition(ldd, mask, world, subtree_fraction, graph=graph)
         if graph is not None:
             graph.close()
@@ -144,49 +182,24 @@ class DistributedKinematicWave(object):
         gmask[loc] = True
         sub = np.zeros(mask.shape, bool)
         sub[mask] = gmask
-        self.backend, self.max_steps = backend, int(max_steps)
+        self.max_steps = int(max_steps)
         pick = lambda v: v if np.ndim(v) == 0 else np.ascontiguousarray(np.asarray(v, np.float64)[loc])
         self.xslot = P.local_xslot(rank)
         n_exp = P.n_cut[rank] if rank != 0 else 0
         n_imp = P.n_import if rank == 0 else 0
-        dev = "cuda" if backend == "gpu" else "cpu"
+        dev = backend.device
         self.export = torch.zeros(max(n_exp, 1) * self.max_steps, dtype=torch.float64, device=dev)
         self.imported = torch.zeros(max(n_imp, 1) * self.max_steps, dtype=torch.float64, device=dev)
         self.n_exp, self.n_imp = n_exp, n_imp
-        if backend == "gpu":
-            import ctypes as C
-            from . import _capi
-            from .hydrological_modules.kinematic_wave_parallel import kinematicWave
-            self.kw = kinematicWave(ldd[loc], sub, pick(alpha_channel), beta, pick(space_delta), time_delta)
-            if world > 1:
-                _capi.check(_capi.lib().lf_router_set_exchange(self.kw._router, _capi.ptr(self.xslot), n_exp, n_imp,
-                                                               _capi.ptr(self.export), _capi.ptr(self.imported),
-                                                               self.max_steps))
-            self._capi = _capi
-        else:
-            from oracle import lisf_oracle
-            self.kw = lisf_oracle.KinematicWaveOracle(ldd[loc], sub, pick(alpha_channel), beta, pick(space_delta), time_delta)
-            self.Q = np.zeros(loc.size)
-            self.q = np.zeros(loc.size)
-            self.fixed = (self.xslot <= -2).astype(np.uint8)
-            self.ghost_slot = np.where(self.xslot <= -2, -2 - self.xslot, 0)
-            self.export_idx = np.flatnonzero(self.xslot >= 0)
-            self.export_slot = self.xslot[self.export_idx]
+        self.router = backend(ldd[loc], sub, pick(alpha_channel), beta, pick(space_delta), time_delta, self.xslot, n_exp,
+                              n_imp, self.export, self.imported, self.max_steps, world)
         self.beta = beta
 
     def set_discharge(self, discharge_global):
-        q = np.ascontiguousarray(np.asarray(discharge_global, np.float64)[self.loc])
-        if self.backend == "gpu":
-            self.kw.set_discharge(q)
-        else:
-            self.Q = q
+        self.router.set_discharge(np.ascontiguousarray(np.asarray(discharge_global, np.float64)[self.loc]))
 
     def set_lateral_inflow(self, q_global):
-        q = np.ascontiguousarray(np.asarray(q_global, np.float64)[self.loc])
-        if self.backend == "gpu":
-            self.kw.set_lateral_inflow(q)
-        else:
-            self.q = q
+        self.router.set_lateral_inflow(np.ascontiguousarray(np.asarray(q_global, np.float64)[self.loc]))
 
     def _exchange_in(self):
         """rank 0: receive every other rank's export block of this run."""
@@ -195,13 +208,11 @@ class DistributedKinematicWave(object):
             if P.n_cut[r]:
                 o = int(P.import_offset[r]) * cap
                 self.comm.dist.recv(self.imported[o:o + P.n_cut[r] * cap], src=r)
-        if self.backend == "gpu":
-            self.torch.cuda.current_stream().synchronize()
+        self.router.after_recv()
 
     def _exchange_out(self):
         if self.n_exp:
-            if self.backend == "gpu":
-                self._capi.synchronize()
+            self.router.before_send()
             self.comm.dist.send(self.export[:self.n_exp * self.max_steps], dst=0)
 
     def run(self, nsteps, inflow_scale=None):
@@ -210,23 +221,12 @@ class DistributedKinematicWave(object):
         rank, world = self.comm.rank, self.comm.world
         if world > 1 and rank == 0 and self.n_imp:
             self._exchange_in()
-        if self.backend == "gpu":
-            self.kw.run(nsteps, inflow_scale=inflow_scale)
-        else:
-            cap = self.max_steps
-            imp = self.imported.numpy().reshape(-1, cap)
-            exp = self.export.numpy().reshape(-1, cap)
-            for s in range(nsteps):
-                q = self.q if inflow_scale is None else self.q * inflow_scale[s]
-                fv = imp[self.ghost_slot, s] if self.n_imp else None
-                self.kw.kinematicWaveRouting(self.Q, q, fixed=self.fixed if self.n_imp else None, fixed_values=fv)
-                if self.n_exp:
-                    exp[self.export_slot, s] = self.Q[self.export_idx]
+        self.router.run(nsteps, inflow_scale)
         if world > 1 and rank != 0:
             self._exchange_out()
 
     def local_discharge(self):
-        return self.kw.get_discharge() if self.backend == "gpu" else self.Q.copy()
+        return self.router.get_discharge()
 
     def gather_discharge(self):
         """Global discharge map on rank 0 (None elsewhere) -- for output / tests, not on the hot path."""
@@ -235,7 +235,7 @@ class DistributedKinematicWave(object):
         own = self.owned_local
         mine = torch.from_numpy(np.ascontiguousarray(q[own]))
         idx = self.loc[own]
-        dev = "cuda" if self.backend == "gpu" else "cpu"
+        dev = self.export.device
         if self.comm.rank == 0:
             out = np.empty(self.n_global)
             out[idx] = mine.numpy()

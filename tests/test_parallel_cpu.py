@@ -42,6 +42,48 @@ def test_partition_invariants(world):
         assert (x <= -2).sum() == (P.n_import if r == 0 else 0)
 
 
+class CpuStandInBackend(object):
+    """Router protocol of lisflood_code_b200.parallel.GpuRouterBackend on top of the CPU oracle (test stand-in:
+    it lets the partition / exchange host logic run under gloo without a GPU)."""
+    device = "cpu"
+
+    def __init__(self, ldd_local, sub_mask, alpha, beta, dx, dt, xslot, n_exp, n_imp, export, imported, max_steps, world):
+        from oracle import lisf_oracle
+        self.kw = lisf_oracle.KinematicWaveOracle(ldd_local, sub_mask, alpha, beta, dx, dt)
+        self.Q = np.zeros(xslot.size)
+        self.q = np.zeros(xslot.size)
+        self.cap, self.n_exp, self.n_imp = max_steps, n_exp, n_imp
+        self.exp = export.numpy().reshape(-1, max_steps)
+        self.imp = imported.numpy().reshape(-1, max_steps)
+        self.fixed = (xslot <= -2).astype(np.uint8)
+        self.ghost_slot = np.where(xslot <= -2, -2 - xslot, 0)
+        self.export_idx = np.flatnonzero(xslot >= 0)
+        self.export_slot = xslot[self.export_idx]
+
+    def set_discharge(self, q):
+        self.Q = q.copy()
+
+    def set_lateral_inflow(self, q):
+        self.q = q.copy()
+
+    def run(self, nsteps, inflow_scale):
+        for s in range(nsteps):
+            q = self.q if inflow_scale is None else self.q * inflow_scale[s]
+            fv = self.imp[self.ghost_slot, s] if self.n_imp else None
+            self.kw.kinematicWaveRouting(self.Q, q, fixed=self.fixed if self.n_imp else None, fixed_values=fv)
+            if self.n_exp:
+                self.exp[self.export_slot, s] = self.Q[self.export_idx]
+
+    def get_discharge(self):
+        return self.Q.copy()
+
+    def before_send(self):
+        pass
+
+    def after_recv(self):
+        pass
+
+
 def _worker(rank, world, port, tmp):
     import sys
     sys.path.insert(0, ROOT)
@@ -50,7 +92,9 @@ def _worker(rank, world, port, tmp):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from lisflood_code_b200.parallel import DistributedKinematicWave
     ldd, mask, alpha, q0, q, dx = _case()
-    D = DistributedKinematicWave(ldd, mask, alpha, 0.6, dx, 3600.0, max_steps=8, backend="oracle")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_parallel_cpu import CpuStandInBackend
+    D = DistributedKinematicWave(ldd, mask, alpha, 0.6, dx, 3600.0, max_steps=8, backend=CpuStandInBackend)
     D.set_discharge(q0)
     D.set_lateral_inflow(q)
     rng = np.random.default_rng(3)

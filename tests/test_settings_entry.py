@@ -1,0 +1,83 @@
+"""Settings-XML surface and HydroModule call protocol (CPU parts) + the lisf1.py entry on the GPU."""
+import os
+
+import numpy as np
+import pytest
+
+XML = """<?xml version="1.0" encoding="UTF-8"?>
+<lfsettings>
+  <lfoptions><setoption name="SplitRouting" choice="%d"/><setoption name="InitLisflood" choice="0"/></lfoptions>
+  <lfuser>
+    <textvar name="PathRoot" value="%s"/><textvar name="StepStart" value="1"/><textvar name="StepEnd" value="%d"/>
+  </lfuser>
+  <lfbinding>
+    <textvar name="MaskMap" value="$(PathRoot)/mask.npy"/><textvar name="StateFile" value="$(PathRoot)/state.npz"/>
+    <textvar name="ForcingFile" value="$(PathRoot)/forcing.npz"/><textvar name="DisOut" value="$(PathRoot)/dis.npy"/>
+    <textvar name="StepStart" value="$(StepStart)"/><textvar name="StepEnd" value="$(StepEnd)"/>
+  </lfbinding>
+</lfsettings>
+"""
+
+
+def _write_case(tmp, split, steps=2):
+    from lisflood_code_b200 import synthetic
+    S = synthetic.full_stack(40, 36, seed=21, split_routing=split)
+    np.save(tmp / "mask.npy", S["mask"])
+    np.savez(tmp / "state.npz", **{k: v for k, v in S.items() if k != "mask"})
+    Fs = [synthetic.forcing(S, t, 21) for t in range(steps)]
+    np.savez(tmp / "forcing.npz", **{k: np.stack([F[k] for F in Fs]) for k in Fs[0]})
+    xml = tmp / "settings.xml"
+    xml.write_text(XML % (1 if split else 0, str(tmp), steps))
+    return S, Fs, str(xml)
+
+
+def test_settings_xml_parsing(tmp_path):
+    from lisflood_code_b200.global_modules.settings import LisSettings
+    S, Fs, xml = _write_case(tmp_path, True)
+    st = LisSettings(xml, ["-q", "--nancheck"])
+    assert st.options["SplitRouting"] is True and st.options["nonInit"] is True and st.options["wateruse"] is False
+    assert st.binding["MaskMap"] == str(tmp_path / "mask.npy") and st.binding["StepEnd"] == "2"
+    assert st.flags["quiet"] and st.flags["nancheck"] and not st.flags["loud"]
+    assert LisSettings.instance() is st
+    st.check_supported()
+    st.options["wateruse"] = True
+    with pytest.raises(NotImplementedError):
+        st.check_supported()
+
+
+def test_module_call_order_is_enforced():
+    from lisflood_code_b200.hotpath import HotPathModel
+    from lisflood_code_b200.hydrological_modules.opensealed import opensealed
+
+    class Fake(HotPathModel):
+        def __init__(self):
+            self.__dict__["_soil_calls"] = []
+            self.__dict__["ran"] = 0
+
+        def soil(self):
+            self.__dict__["ran"] += 1
+
+    v = Fake()
+    with pytest.raises(RuntimeError):
+        opensealed(v).dynamic()          # before soilloop.dynamic_canopy
+    for who in HotPathModel._SOIL_SEQUENCE:
+        v._soil_stage_call(who)
+    assert v.ran == 1
+    v._require_soil_stage_done()
+    with pytest.raises(RuntimeError):
+        v._require_soil_stage_done()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("split", [False, True])
+def test_lisf1_entry_matches_oracle(gpu_lib, oracle, tmp_path, split):
+    import lisf1
+    from oracle import lisf_oracle_model as om
+    S, Fs, xml = _write_case(tmp_path, split, steps=3)
+    assert lisf1.main(xml, "-v") == 0
+    dis = np.load(tmp_path / "dis.npy")
+    O = om.OracleModel(S)
+    for t, F in enumerate(Fs):
+        O.step(F)
+        want = O.var.ChanQAvg
+        assert np.max(np.abs(dis[t] - want) / np.maximum(np.abs(want), 1e-12)) < 1e-8, t
