@@ -414,6 +414,8 @@ struct lf_model {
     // asynchronous input path (lf_model_set_async): H2D on a copy stream into a per-map staging buffer, layout
     // translation on the compute stream once the copy has landed
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // the channel wavefront runs here, concurrently with k_chan_isolated
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::map<std::string, std::unique_ptr<lf::DevBuf<double>>> async_stage;
     std::map<std::string, cudaEvent_t> async_copied, async_consumed;
     bool soil_profile = false;            // time the kernels of the soil stage individually (lf_model_soil_stats)
@@ -436,6 +438,9 @@ struct lf_model {
         for (auto &kv : async_copied) cudaEventDestroy(kv.second);
         for (auto &kv : async_consumed) cudaEventDestroy(kv.second);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (side_stream) cudaStreamDestroy(side_stream);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
     }
 };
 
@@ -944,6 +949,18 @@ int channel_stage(lf_model *m)
             C.z2floor = zf;
         }
     }
+    // The connected network (many small, dependent launches) and the isolated pixels (one big launch) touch
+    // disjoint pixels: the wavefront is issued on a side stream and overlaps the isolated kernel.
+    if (!m->side_stream) {
+        int prio_lo = 0, prio_hi = 0;   // high priority: its small blocks take SM slots as the big kernel's blocks retire
+        LF_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        LF_CUDA(cudaStreamCreateWithPriority(&m->side_stream, cudaStreamNonBlocking, prio_hi));
+        LF_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+        LF_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    }
+    cudaStream_t sw = m->side_stream;
+    LF_CUDA(cudaEventRecord(m->ev_fork, st));
+    LF_CUDA(cudaStreamWaitEvent(sw, m->ev_fork, 0));
     // isolated pixels (no link at all): one launch, all sub-steps in registers
     const std::vector<int32_t> &ls = g->h_level_start;
     int Lc = g->n_orders, S = C.S;
@@ -960,10 +977,12 @@ int channel_stage(lf_model *m)
         int hi_lev = d < Lc - 1 ? d : Lc - 1;
         int lo = ls[lo_lev], hi = level_end(hi_lev);
         if (hi <= lo) continue;
-        if (m->quintic) k_chan_diagonal<true><<<lf::blocks_for(hi - lo, CH_THREADS), CH_THREADS, 0, st>>>(C, lo, hi, d);
-        else k_chan_diagonal<false><<<lf::blocks_for(hi - lo, CH_THREADS), CH_THREADS, 0, st>>>(C, lo, hi, d);
+        if (m->quintic) k_chan_diagonal<true><<<lf::blocks_for(hi - lo, CH_THREADS), CH_THREADS, 0, sw>>>(C, lo, hi, d);
+        else k_chan_diagonal<false><<<lf::blocks_for(hi - lo, CH_THREADS), CH_THREADS, 0, sw>>>(C, lo, hi, d);
         LF_LAUNCH_CHECK();
     }
+    LF_CUDA(cudaEventRecord(m->ev_join, sw));
+    LF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
     FIELD(chm3, "ChanM3");
     FIELD(tcs, "TotalCrossSectionArea");
     FIELD(sdis, "sumDis");
