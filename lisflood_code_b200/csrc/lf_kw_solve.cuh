@@ -134,16 +134,16 @@ __device__ __forceinline__ double solve_z(double U, double z_old, double lateral
     // bracketed initial guess, tools:64-70
     const double ba = 0.6 * a;
     const double zc = root5(c);
-    const double t = lfm::div_fast(ba, zc * zc);  // b*a * C^(b-1)
-    const double secant = (t <= 1.0) ? lfm::div_fast(c, 1.0 + t) : lfm::div_fast(c, 1.0 + pow_5_3(t));
-    const double other = pow_5_3(lfm::div_fast(c - secant, a));
+    const double t = ba / (zc * zc);  // b*a * C^(b-1)
+    const double secant = (t <= 1.0) ? c / (1.0 + t) : c / (1.0 + pow_5_3(t));
+    const double other = pow_5_3((c - secant) / a);
     double q = (secant + other) / 2.0;
     double z = z_of_q(q);
     double err = q + a * (z * z * z) - c;
     int count = 0;
     while (fabs(err) > NEWTON_TOL && count < MAX_ITERS) {
         const double z2 = z * z;
-        double qn = q - lfm::div_fast(err * z2, z2 + ba);  // q - err / (1 + b*a*q^(b-1))
+        double qn = q - err * z2 / (z2 + ba);  // q - err / (1 + b*a*q^(b-1))
         qn = fmax(qn, NEWTON_TOL);
         const bool small = fabs(qn - q) <= 1e-8 * qn;  // includes q == prev
         q = qn;

@@ -81,24 +81,6 @@ LF_HD double div_small(double f, double d)
 #endif
 }
 
-// a / d to about one ulp without the slow-path call of the compiler's division: float reciprocal seed, two
-// Newton steps on the reciprocal, one correction of the quotient.  Falls back to the true division outside the
-// float range (and on the host).
-LF_HD double div_fast(double a, double d)
-{
-#ifdef __CUDA_ARCH__
-    const double ad = fabs(d);
-    if (ad > 1e-30 && ad < 1e30 && fabs(a) < 1e270) {
-        double r = (double)__frcp_rn((float)d);
-        r = fma_(fma_(-d, r, 1.0), r, r);
-        r = fma_(fma_(-d, r, 1.0), r, r);
-        const double q = a * r;
-        return fma_(fma_(-d, q, a), r, q);
-    }
-#endif
-    return a / d;
-}
-
 // log2 of a positive, finite, normal double
 LF_HD double log2_fast(double x)
 {

@@ -148,7 +148,7 @@ constexpr int CH_THREADS = 128;
 
 // wavefront diagonal over channel-network pixels: positions [lo, hi), sub-step s = d - level
 template <bool QZ>
-__global__ void __launch_bounds__(CH_THREADS, 8) k_chan_diagonal(ChanPtrs C, int lo, int hi, int d)
+__global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo, int hi, int d)
 {
     int i = lo + blockIdx.x * CH_THREADS + threadIdx.x;
     if (i >= hi) return;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(CH_THREADS, 8) k_chan_diagonal(ChanPtrs C, int
 
 // pixels with no upstream and no downstream link: all S sub-steps in registers
 template <bool QZ>
-__global__ void __launch_bounds__(CH_THREADS, 8) k_chan_isolated(ChanPtrs C, int lo, int hi)
+__global__ void __launch_bounds__(CH_THREADS) k_chan_isolated(ChanPtrs C, int lo, int hi)
 {
     int i = lo + blockIdx.x * CH_THREADS + threadIdx.x;
     if (i >= hi) return;

@@ -72,7 +72,7 @@ __device__ __forceinline__ double pw(double x, double y) { return lfm::pw(x, y);
 // saturationDegree + unsaturatedConductivity, soilloop.py:360-383
 __device__ __forceinline__ double unsat_k(double w, bool pore, double wres, double ws, double ksat, double invm, double m)
 {
-    double sat = pore ? fmax(fmin(lfm::div_fast(w - wres, ws - wres), 1.), 0.) : 0.;
+    double sat = pore ? fmax(fmin((w - wres) / (ws - wres), 1.), 0.) : 0.;
     double t = 1. - pw(1. - pw(sat, invm), m);
     return ksat * sqrt(sat) * (t * t);
 }
@@ -196,9 +196,9 @@ __device__ __forceinline__ void soil_column(const Ptrs &P, const Diag &D, int64_
     double k2 = unsat_k(w2, pore2, wres2, ws2, ks2, im2, m2);
     double av1a = w1a - wres1a, av1b = w1b - wres1b, av2 = w2 - wres2;
     double cap1 = ws1b - w1b, cap2 = ws2 - w2;
-    const double cA = av1a == 0 ? 0. : lfm::div_fast(k1a * P.DtDay, av1a);
-    const double cB = av1b == 0 ? 0. : lfm::div_fast(k1b * P.DtDay, av1b);
-    const double cG = av2 == 0 ? 0. : lfm::div_fast(k2 * P.DtDay, av2);
+    const double cA = av1a == 0 ? 0. : k1a * P.DtDay / av1a;
+    const double cB = av1b == 0 ? 0. : k1b * P.DtDay / av1b;
+    const double cG = av2 == 0 ? 0. : k2 * P.DtDay / av2;
     const double courant = fmax(fmax(cA, cB), cG);
     const int nsub = (int)fmin(fmax(1., ceil(courant / P.CourantCrit)), 2.0e9);
     // ---- columns that need several sub-steps go to the bucket lists (first pass only) ----
