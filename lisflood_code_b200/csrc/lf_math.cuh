@@ -12,7 +12,7 @@
 // against libm pow by tests/test_lf_math.py; the parity tolerance of the model is 1e-6).
 // Special values follow pow() for x >= 0: pw(0, y>0) = 0, pw(0, y<0) = inf, pw(x, 0) = 1, pw(inf, y>0) = inf,
 // pw(inf, y<0) = 0; NaN propagates; x < 0 gives NaN (never produced by the model); results below 2^-1021
-// flush to 0.
+// and arguments below 1e-300 flush (to 0 resp. to 1e-300).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -115,36 +115,23 @@ LF_HD double exp2_fast(double t)
     return p * bits_to_double((uint64_t)(ni + 1023) << 52);
 }
 
-// rare inputs: zero, denormal, inf, NaN, negative
-#ifdef __CUDA_ARCH__
-__device__ __noinline__ double pw_special(double x, double y)
-#else
-static inline double pw_special(double x, double y)
-#endif
-{
-    if (x != x || y != y) return x + y;
-    if (y == 0.0) return 1.0;
-    if (x < 0.0) return bits_to_double(0x7ff8000000000000ull);
-    if (x == 0.0) return y > 0.0 ? 0.0 : bits_to_double(0x7ff0000000000000ull);
-    if (x > 1.7976931348623157e308) return y > 0.0 ? x : 0.0;
-    // denormal: renormalise
-    const double t = y * (log2_fast(x * 18014398509481984.0) - 54.0);
-    if (t < -1021.0) return 0.0;
-    if (t > 1023.5) return bits_to_double(0x7ff0000000000000ull);
-    return exp2_fast(t);
-}
-
+// Branch-free: the fast path is evaluated unconditionally on a clamped argument and the special values are
+// patched in with selects, so the compiler can interleave several independent pw() chains (the three soil layers,
+// the three overland routers) instead of serialising them at basic-block boundaries.
 LF_HD double pw(double x, double y)
 {
-    const uint64_t u = double_to_bits(x);
-    if ((u >> 52) - 1ull < 0x7feull) {  // positive, normal, finite
-        const double t = y * log2_fast(x);
-        if (t >= -1021.0 && t <= 1023.5) return exp2_fast(t);
-        if (t < -1021.0) return 0.0;
-        if (t > 1023.5) return bits_to_double(0x7ff0000000000000ull);
-        return t;  // NaN exponent
-    }
-    return pw_special(x, y);
+    const double INF = bits_to_double(0x7ff0000000000000ull);
+    const double xs = fmin(fmax(x, 1e-300), 1.7976931348623157e308);  // zero / denormal / inf are patched below
+    const double t = y * log2_fast(xs);
+    double r = exp2_fast(fmin(fmax(t, -1021.0), 1023.0));
+    r = t < -1021.0 ? 0.0 : r;
+    r = t > 1023.0 ? INF : r;
+    const double at_zero = y > 0.0 ? 0.0 : (y < 0.0 ? INF : 1.0);
+    const double at_inf = y > 0.0 ? INF : (y < 0.0 ? 0.0 : 1.0);
+    r = x == 0.0 ? at_zero : r;
+    r = x > 1.7976931348623157e308 ? at_inf : r;
+    r = (x >= 0.0 && y == y) ? r : (y == 0.0 ? 1.0 : bits_to_double(0x7ff8000000000000ull));  // NaN / negative base
+    return r;
 }
 
 }  // namespace lfm

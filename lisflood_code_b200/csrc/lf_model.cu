@@ -664,7 +664,7 @@ int soil_stage(lf_model *m)
         if (m->soil_profile) cudaEventRecord(m->soil_ev[k], st);
     };
     tick(0);
-    const unsigned grid_veg = lf::blocks_for(3 * m->n, lfsoil::SOIL_THREADS);
+    const dim3 grid_veg(lf::blocks_for(m->n, lfsoil::SOIL_THREADS), 3);   // y = vegetation fraction
     const unsigned grid_def = lf::blocks_for(m->soil_list_cap, lfsoil::SOIL_THREADS);
     const unsigned grid_pix = lf::blocks_for(m->n, 256);
     if (m->cfg.diagnostics) {

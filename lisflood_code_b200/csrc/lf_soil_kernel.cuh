@@ -88,9 +88,11 @@ __device__ __forceinline__ int bucket_of(int nsub)
 // One soil column (vegetation fraction v of pixel i, k = v*N + i).  `may_defer`: columns needing more than one
 // Darcy sub-step are queued instead of integrated (first pass).
 template <bool DIAG>
-__device__ __forceinline__ void soil_column(const Ptrs &P, const Diag &D, int64_t k, int v, int64_t i, bool may_defer)
+__device__ __forceinline__ void soil_column(const Ptrs &P, const Diag &D, int v, int i, bool may_defer)
 {
+    // 32-bit pixel index + one 64-bit row offset: the ~50 map accesses of a column then cost one IMAD.WIDE each
     const int64_t N = P.n;
+    const int64_t k = (int64_t)v * N + i;
     const double rain = P.Rain[i], etref = P.ETRef[i], ewref = P.EWRef[i];
     const bool frozen = P.frozen[i] != 0;
     const double bX = P.bX[i];
@@ -322,10 +324,9 @@ constexpr int SOIL_THREADS = 128;
 template <bool DIAG, int MINB>
 __global__ void __launch_bounds__(SOIL_THREADS, MINB) k_soil_veg(Ptrs P, Diag D)
 {
-    const int64_t k = (int64_t)blockIdx.x * SOIL_THREADS + threadIdx.x;
-    if (k >= 3 * P.n) return;
-    const int v = (int)(k / P.n);
-    soil_column<DIAG>(P, D, k, v, k - (int64_t)v * P.n, true);
+    const int64_t i = (int64_t)blockIdx.x * SOIL_THREADS + threadIdx.x;   // blockIdx.y = vegetation fraction
+    if (i >= P.n) return;
+    soil_column<DIAG>(P, D, (int)blockIdx.y, (int)i, true);
 }
 // second pass: the columns of one bucket list
 template <bool DIAG, int MINB>
@@ -335,8 +336,8 @@ __global__ void __launch_bounds__(SOIL_THREADS, MINB) k_soil_veg_deferred(Ptrs P
     const int cnt = min(P.list_cnt[bucket], P.list_cap);
     if (j >= cnt) return;
     const int64_t k = P.list[(int64_t)bucket * P.list_cap + j];
-    const int v = (int)(k / P.n);
-    soil_column<DIAG>(P, D, k, v, k - (int64_t)v * P.n, false);
+    const int v = k >= 2 * P.n ? 2 : (k >= P.n ? 1 : 0);
+    soil_column<DIAG>(P, D, v, (int)(k - (int64_t)v * P.n), false);
 }
 
 // per pixel: sums over the fractions, open water / sealed soil, groundwater, runoff components
