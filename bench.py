@@ -367,7 +367,10 @@ def run_c3(args):
                            "l2_policy": "every map is %.0f MB (> 126 MB L2 for rasters above ~4000^2); two forcing sets "
                                         "alternate between steps" % (n * 8 / 1e6)},
                 "e2e": {"value": e2e_value, "unit": "cell-updates/s", "steps": Ke, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h)},
+                        "d2h_bytes_per_step": int(d2h),
+                        "note": "per step: Rain, SnowMelt, ETRef, EWRef, ESRef (f64) + isFrozenSoil (u8) from pinned host "
+                                "memory through HotPathModel.set_async/set_flags, discharge map ChanQAvg back to the host; "
+                                "the 10-day LAI maps stay resident"},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
                 "roofline_stencil": roof_soil, "roofline_routing": roof_chan, "stage_ms_per_step": stage,
                 "soil_stats": soil_stats,
