@@ -76,3 +76,26 @@ def makenumpy(v, maskinfo=None):
     if np.ndim(v) == 0:
         return np.full(mi.num_pixels, float(v))
     return np.ascontiguousarray(v, np.float64)
+
+
+def loadmap(name, binding=None, maskinfo=None):
+    """Static input by binding name with the reference's return convention (add1.py:318-541): a Python float
+    when the binding is a number, else a compressed float64[N] array -- several modules branch on
+    `isinstance(x, float)` (soil.py:355,372; groundwater.py:54,60).  Map files here are NumPy `.npy` archives
+    (2-D rasters are compressed with the mask, 1-D arrays are taken as already compressed); PCRaster / NetCDF
+    readers are out of scope."""
+    import os
+    if binding is None:
+        from .settings import LisSettings
+        binding = LisSettings.instance().binding
+    value = binding[name]
+    try:
+        return float(value)
+    except (TypeError, ValueError):
+        pass
+    if not os.path.exists(value):
+        raise FileNotFoundError("binding %s -> %s" % (name, value))
+    a = np.load(value)
+    if a.ndim == 2:
+        return compressArray(a, maskinfo).astype(np.float64)
+    return np.ascontiguousarray(a, np.float64)

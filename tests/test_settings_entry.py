@@ -81,3 +81,22 @@ def test_lisf1_entry_matches_oracle(gpu_lib, oracle, tmp_path, split):
         O.step(F)
         want = O.var.ChanQAvg
         assert np.max(np.abs(dis[t] - want) / np.maximum(np.abs(want), 1e-12)) < 1e-8, t
+
+
+def test_map_api_roundtrip(tmp_path):
+    from lisflood_code_b200.global_modules import add1
+    rng = np.random.default_rng(0)
+    excluded = rng.random((7, 9)) < 0.3
+    mi = add1.MaskInfo(excluded)
+    m2 = rng.random((7, 9))
+    c = add1.compressArray(m2)
+    assert c.shape == (mi.num_pixels,) and np.array_equal(c, m2[~excluded])
+    d = add1.decompress(c)
+    assert np.array_equal(d[~excluded], c) and np.all(d[excluded] == -9999.0)
+    assert mi.in_zero().shape == (mi.num_pixels,) and add1.makenumpy(2.5)[0] == 2.5
+    np.save(tmp_path / "m.npy", m2)
+    binding = {"beta": "0.6", "SomeMap": str(tmp_path / "m.npy")}
+    assert isinstance(add1.loadmap("beta", binding), float) and add1.loadmap("beta", binding) == 0.6
+    assert np.array_equal(add1.loadmap("SomeMap", binding), c)
+    nm = add1.NumpyModified(np.zeros((3, 4)), ["vegetation", "pixel"])
+    assert nm.values is nm and nm.dims == ["vegetation", "pixel"] and nm[1:].dims == ["vegetation", "pixel"]
