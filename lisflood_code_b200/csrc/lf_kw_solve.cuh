@@ -84,44 +84,68 @@ __device__ __forceinline__ double solve(double U, double q_old, double lateral, 
 }
 
 // ---- beta == 3/5: state is z = Q^(1/5) -----------------------------------------------------------
-// fifth root of q > 0 (q >= 1e-30): float seed + two Newton steps with a float reciprocal (error ~1e-16)
+// hardware approximations used only as SEEDS (every seed is refined in float64 below)
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ double rcp64_approx(double x)  // MUFU.RCP64H: ~20 good bits, no conversions
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+// a / d (d normal, non-zero) to ~1 ulp: reciprocal seed, two Newton steps, one correction of the quotient.
+// Branch-free, 9 instructions (the compiler's division carries a slow-path test and call).
+__device__ __forceinline__ double div_nr(double a, double d)
+{
+    double r = rcp64_approx(d);
+    r = lfm::fma_(lfm::fma_(-d, r, 1.0), r, r);
+    r = lfm::fma_(lfm::fma_(-d, r, 1.0), r, r);
+    const double q = a * r;
+    return lfm::fma_(lfm::fma_(-d, q, a), r, q);
+}
+// fifth root of q in [1e-30, 1e30]: approximate seed (rel. error ~1e-6) + two Newton steps whose divisions use the
+// approximate reciprocal (Newton is self-correcting): error ~1e-16
 __device__ __forceinline__ double root5(double q)
 {
-    double w = (double)__powf((float)q, 0.2f);
+    double w = (double)ex2_approx(0.2f * lg2_approx((float)q));
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const double w2 = w * w, w4 = w2 * w2;
-        const double r = (double)__frcp_rn((float)(5.0 * w4));
-        w = lfm::fma_(-lfm::fma_(w4, w, -q), r, w);
+        w = lfm::fma_(-lfm::fma_(w4, w, -q), rcp64_approx(5.0 * w4), w);
     }
     return w;
 }
-// cube root of x > 0 within the float range, same scheme
+// cube root of x in [1e-30, 1e30], same scheme
 __device__ __forceinline__ double root3(double x)
 {
-    double w = (double)__powf((float)x, 0.33333334f);
+    double w = (double)ex2_approx(0.33333334f * lg2_approx((float)x));
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const double w2 = w * w;
-        const double r = (double)__frcp_rn((float)(3.0 * w2));
-        w = lfm::fma_(-lfm::fma_(w2, w, -x), r, w);
+        w = lfm::fma_(-lfm::fma_(w2, w, -x), rcp64_approx(3.0 * w2), w);
     }
     return w;
 }
 __device__ __forceinline__ bool in_float_range(double x) { return x > 1e-30 && x < 1e30; }
-// z of a discharge (any magnitude, 0 -> 0, negative / NaN -> NaN)
+// z of a discharge handed in by the caller (any magnitude, 0 -> 0, negative / NaN -> NaN)
 __device__ __forceinline__ double z_of_q(double q)
 {
     if (in_float_range(q)) return root5(q);
     if (q == 0.0) return 0.0;
     return lfm::pw(q, 0.2);
 }
-// x^(5/3) for x >= 0
-__device__ __forceinline__ double pow_5_3(double x)
-{
-    if (in_float_range(x)) return pow5(root3(x));
-    return lfm::pw(x, 1.6666666666666667);
-}
+// x^(5/3) for 0 <= x < 1e30 (below 1e-30 the result, < 1e-50, is taken as 0)
+__device__ __forceinline__ double pow_5_3(double x) { return x > 1e-30 ? pow5(root3(x)) : 0.0; }
 
 // U: sum of z_k^5 over the upstream pixels; returns z_new (0 when the discharge is 0).
 // Same initial guess and Newton iterates as the reference (tools:64-80), in float64; Q^beta = z^3 and
@@ -134,16 +158,16 @@ __device__ __forceinline__ double solve_z(double U, double z_old, double lateral
     // bracketed initial guess, tools:64-70
     const double ba = 0.6 * a;
     const double zc = root5(c);
-    const double t = ba / (zc * zc);  // b*a * C^(b-1)
-    const double secant = (t <= 1.0) ? c / (1.0 + t) : c / (1.0 + pow_5_3(t));
-    const double other = pow_5_3((c - secant) / a);
+    const double t = div_nr(ba, zc * zc);  // b*a * C^(b-1)
+    const double secant = div_nr(c, 1.0 + ((t <= 1.0) ? t : pow_5_3(fmin(t, 1e30))));
+    const double other = pow_5_3(fmin(div_nr(c - secant, a), 1e29));
     double q = (secant + other) / 2.0;
-    double z = z_of_q(q);
+    double z = root5(fmin(fmax(q, 1e-30), 1e30));  // q >= C / (2 (1 + t^(5/3))) > 0
     double err = q + a * (z * z * z) - c;
     int count = 0;
     while (fabs(err) > NEWTON_TOL && count < MAX_ITERS) {
         const double z2 = z * z;
-        double qn = q - err * z2 / (z2 + ba);  // q - err / (1 + b*a*q^(b-1))
+        double qn = q - div_nr(err * z2, z2 + ba);  // q - err / (1 + b*a*q^(b-1))
         qn = fmax(qn, NEWTON_TOL);
         const bool small = fabs(qn - q) <= 1e-8 * qn;  // includes q == prev
         q = qn;
