@@ -103,16 +103,7 @@ __device__ __forceinline__ double rcp64_approx(double x)  // MUFU.RCP64H: ~20 go
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     return r;
 }
-// a / d (d normal, non-zero) to ~1 ulp: reciprocal seed, two Newton steps, one correction of the quotient.
-// Branch-free, 9 instructions (the compiler's division carries a slow-path test and call).
-__device__ __forceinline__ double div_nr(double a, double d)
-{
-    double r = rcp64_approx(d);
-    r = lfm::fma_(lfm::fma_(-d, r, 1.0), r, r);
-    r = lfm::fma_(lfm::fma_(-d, r, 1.0), r, r);
-    const double q = a * r;
-    return lfm::fma_(lfm::fma_(-d, q, a), r, q);
-}
+__device__ __forceinline__ double div_nr(double a, double d) { return lfm::div_nr(a, d); }
 // fifth root of q in [1e-30, 1e30]: approximate seed (rel. error ~1e-6) + two Newton steps whose divisions use the
 // approximate reciprocal (Newton is self-correcting): error ~1e-16
 __device__ __forceinline__ double root5(double q)

@@ -67,19 +67,23 @@ LF_HD double fma_(double a, double b, double c)
     return fma(a, b, c);
 #endif
 }
-// f / d for d in [1.7, 2.42]
-LF_HD double div_small(double f, double d)
+// a / d for a finite and d a normal, non-zero double, to ~1 ulp: hardware reciprocal seed (MUFU.RCP64H, ~20 bits),
+// two Newton steps on the reciprocal, one correction of the quotient.  Branch-free, 9 instructions (the compiler's
+// division carries a slow-path test and call).  On the host: the plain division.
+LF_HD double div_nr(double a, double d)
 {
 #ifdef __CUDA_ARCH__
-    double r = (double)__frcp_rn((float)d);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
     r = fma_(fma_(-d, r, 1.0), r, r);
     r = fma_(fma_(-d, r, 1.0), r, r);
-    double s = f * r;
-    return fma_(fma_(-d, s, f), r, s);
+    const double q = a * r;
+    return fma_(fma_(-d, q, a), r, q);
 #else
-    return f / d;
+    return a / d;
 #endif
 }
+LF_HD double div_small(double f, double d) { return div_nr(f, d); }  // d in [1.7, 2.42]
 
 // log2 of a positive, finite, normal double
 LF_HD double log2_fast(double x)

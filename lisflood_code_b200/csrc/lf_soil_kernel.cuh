@@ -72,7 +72,7 @@ __device__ __forceinline__ double pw(double x, double y) { return lfm::pw(x, y);
 // saturationDegree + unsaturatedConductivity, soilloop.py:360-383
 __device__ __forceinline__ double unsat_k(double w, bool pore, double wres, double ws, double ksat, double invm, double m)
 {
-    double sat = pore ? fmax(fmin((w - wres) / (ws - wres), 1.), 0.) : 0.;
+    double sat = pore ? fmax(fmin(lfm::div_nr(w - wres, ws - wres), 1.), 0.) : 0.;
     double t = 1. - pw(1. - pw(sat, invm), m);
     return ksat * sqrt(sat) * (t * t);
 }
@@ -138,7 +138,7 @@ __device__ __forceinline__ void soil_column(const Ptrs &P, const Diag &D, int v,
     const double wc1a = ((1 - p) * (wfc1a - wwp1a)) + wwp1a;
     const double wc1b = ((1 - p) * (wfc1b - wwp1b)) + wwp1b;
     double w1 = w1a + w1b;
-    double rws = (wc1 - wwp1) > 0 ? (w1 - wwp1) / (wc1 - wwp1) : 1.;
+    double rws = (wc1 - wwp1) > 0 ? lfm::div_nr(w1 - wwp1, wc1 - wwp1) : 1.;
     rws = fmax(fmin(rws, 1.), 0.);
     double ta = fmin(rws * pot_t, fmax(w1 - wwp1, 0.));
     if (frozen) ta = 0.;
@@ -150,7 +150,7 @@ __device__ __forceinline__ void soil_column(const Ptrs &P, const Diag &D, int v,
         rest = fmax(rest - ta1b, 0.);
         const double sa = fmax(w1a - ta1a - wwp1a, 0.), sb = fmax(w1b - ta1b - wwp1b, 0.);
         const double tot = sa + sb;
-        const double fa = tot > 0 ? sa / tot : 0., fb = tot > 0 ? sb / tot : 0.;
+        const double fa = tot > 0 ? lfm::div_nr(sa, tot) : 0., fb = tot > 0 ? lfm::div_nr(sb, tot) : 0.;
         ta1a += fa * rest;
         ta1b += fb * rest;
         w1a -= ta1a;
@@ -177,7 +177,7 @@ __device__ __forceinline__ void soil_column(const Ptrs &P, const Diag &D, int v,
     w1 = w1a + w1b;
     const bool pore1a = ws1a != 0, pore1b = ws1b != 0, pore2 = ws2 != 0;  // PoreSpaceNotZero (depth != 0 && WS != 0)
     const double ws1 = ws1a + ws1b;
-    const double relsat1 = pore1a ? fmin(w1 / ws1, 1.0) : 0.0;
+    const double relsat1 = pore1a ? fmin(lfm::div_nr(w1, ws1), 1.0) : 0.0;
     const double satfrac = 1.0 - pw(1.0 - relsat1, bX);
     const double store_max = ws1 / (bX + 1);      // StoreMaxPervious, soil.py:363
     const double powinf = (bX + 1) / bX;           // PowerInfPot, soil.py:361
@@ -192,15 +192,15 @@ __device__ __forceinline__ void soil_column(const Ptrs &P, const Diag &D, int v,
     }
     const double ks1a = P.KSat1a[v][i], ks1b = P.KSat1b[v][i], ks2 = P.KSat2[v][i];
     const double im1a = P.InvM1a[v][i], im1b = P.InvM1b[v][i], im2 = P.InvM2[v][i];
-    const double m1a = 1 / im1a, m1b = 1 / im1b, m2 = 1 / im2;
+    const double m1a = lfm::div_nr(1.0, im1a), m1b = lfm::div_nr(1.0, im1b), m2 = lfm::div_nr(1.0, im2);  // GenuM
     double k1a = unsat_k(w1a, pore1a, wres1a, ws1a, ks1a, im1a, m1a);
     double k1b = unsat_k(w1b, pore1b, wres1b, ws1b, ks1b, im1b, m1b);
     double k2 = unsat_k(w2, pore2, wres2, ws2, ks2, im2, m2);
     double av1a = w1a - wres1a, av1b = w1b - wres1b, av2 = w2 - wres2;
     double cap1 = ws1b - w1b, cap2 = ws2 - w2;
-    const double cA = av1a == 0 ? 0. : k1a * P.DtDay / av1a;
-    const double cB = av1b == 0 ? 0. : k1b * P.DtDay / av1b;
-    const double cG = av2 == 0 ? 0. : k2 * P.DtDay / av2;
+    const double cA = av1a == 0 ? 0. : lfm::div_nr(k1a * P.DtDay, av1a);
+    const double cB = av1b == 0 ? 0. : lfm::div_nr(k1b * P.DtDay, av1b);
+    const double cG = av2 == 0 ? 0. : lfm::div_nr(k2 * P.DtDay, av2);
     const double courant = fmax(fmax(cA, cB), cG);
     const int nsub = (int)fmin(fmax(1., ceil(courant / P.CourantCrit)), 2.0e9);
     // ---- columns that need several sub-steps go to the bucket lists (first pass only) ----
