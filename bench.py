@@ -340,7 +340,7 @@ def run_c3(args):
     chan_gbs = chan_bytes / (ch_ms * 1e-3) / 1e9
     stage = {"soil_ms": round(soil_ms, 3), "overland_ms": round(of_ms, 3), "channel_ms": round(ch_ms, 3)}
     dominant = max(stage, key=stage.get)
-    roof_soil = {"bound": "hbm", "kernel": "soil stage = k_soil_veg<false> + k_soil_veg_deferred<false> x6 + k_soil_pixel<false> "
+    roof_soil = {"bound": "hbm", "kernel": "soil stage = k_soil_fused<false> + k_soil_veg_deferred<false> x6 + k_soil_pixel_flagged<false> "
                  "(per-cell stencil: canopy+soil column+open/sealed+per-pixel sums+groundwater)", "achieved": round(soil_gbs, 1), "peak": peak, "peak_kind": peak_kind,
                  "unit": "GB/s", "frac": round(soil_gbs / peak, 4), "traffic": None, "alg_bytes_per_cell": ALG_BYTES_SOIL,
                  "avg_launch_ms": round(soil_ms, 3)}

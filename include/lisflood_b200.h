@@ -60,6 +60,11 @@ int64_t lf_launch_count(int reset);
 /* Page-locks / unlocks a host buffer the caller will pass repeatedly (faster H2D/D2H). */
 int lf_host_register(void *ptr, int64_t bytes);
 int lf_host_unregister(void *ptr);
+/* On-device accuracy check of the library's hand-written float64 math against the CUDA math library over n
+ * pseudo-random arguments: max_err[8] = maximum relative error of { Newton division, Newton square root, table x^y
+ * (normalised by 1 + |y log2 x|), table e^x (normalised by 1 + |x|), fifth root, cube root, polynomial x^y
+ * (normalised likewise), van Genuchten term 1 - (1 - s^(1/m))^m }.  Test infrastructure (tests/test_gpu_math.py). */
+int lf_math_selftest(int64_t n, uint64_t seed, double *max_err);
 
 /* ---------------------------------------------------------------------------------------------
  * Drainage graph.  Replaces kinematicWave.__init__'s graph part:

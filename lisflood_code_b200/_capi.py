@@ -44,6 +44,7 @@ SIGNATURES = {
     "lf_launch_count": (C.c_int64, [C.c_int]),
     "lf_host_register": (C.c_int, [_vp, _i64s]),
     "lf_host_unregister": (C.c_int, [_vp]),
+    "lf_math_selftest": (C.c_int, [_i64s, C.c_uint64, _f64]),
     "lf_ldd_build": (C.c_int, [_vp, _vp, _i64s, _i64s, C.POINTER(_vp)]),
     "lf_graph_info": (C.c_int, [_vp, C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s)]),
     "lf_graph_export": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -73,7 +73,7 @@ __device__ __forceinline__ double solve(double U, double q_old, double lateral, 
     while (fabs(err) > NEWTON_TOL && count < MAX_ITERS) {
         double prev = q;
         q -= err / (1.0 + ba * p);
-        q = fmax(q, NEWTON_TOL);
+        q = lfm::dmax(q, NEWTON_TOL);
         if (fabs(q - prev) <= 1e-8 * q) break;  // includes q == prev
         p = pw(q, P.b_minus_1);
         err = q + a * (q * p) - c;
@@ -150,16 +150,16 @@ __device__ __forceinline__ double solve_z(double U, double z_old, double lateral
     const double ba = 0.6 * a;
     const double zc = root5(c);
     const double t = div_nr(ba, zc * zc);  // b*a * C^(b-1)
-    const double secant = div_nr(c, 1.0 + ((t <= 1.0) ? t : pow_5_3(fmin(t, 1e30))));
-    const double other = pow_5_3(fmin(div_nr(c - secant, a), 1e29));
+    const double secant = div_nr(c, 1.0 + ((t <= 1.0) ? t : pow_5_3(lfm::dmin(t, 1e30))));
+    const double other = pow_5_3(lfm::dmin(div_nr(c - secant, a), 1e29));
     double q = (secant + other) / 2.0;
-    double z = root5(fmin(fmax(q, 1e-30), 1e30));  // q >= C / (2 (1 + t^(5/3))) > 0
+    double z = root5(lfm::dmin(lfm::dmax(q, 1e-30), 1e30));  // q >= C / (2 (1 + t^(5/3))) > 0
     double err = q + a * (z * z * z) - c;
     int count = 0;
     while (fabs(err) > NEWTON_TOL && count < MAX_ITERS) {
         const double z2 = z * z;
         double qn = q - div_nr(err * z2, z2 + ba);  // q - err / (1 + b*a*q^(b-1))
-        qn = fmax(qn, NEWTON_TOL);
+        qn = lfm::dmax(qn, NEWTON_TOL);
         const bool small = fabs(qn - q) <= 1e-8 * qn;  // includes q == prev
         q = qn;
         z = root5(q);

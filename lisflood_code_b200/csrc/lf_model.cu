@@ -1,8 +1,8 @@
 // lf_model.cu -- the full hot-path time step on device-resident state (C ABI: lf_model_*).
 //
 // Stages per model step (reference call order, Lisflood_dynamic.py:114-229):
-//   1. k_soil_veg / k_soil_veg_deferred / k_soil_pixel   fused canopy + soil column per (fraction, pixel),
-//                         then open/sealed + per-pixel sums + groundwater per pixel (lf_soil_kernel.cuh).
+//   1. k_soil_fused / k_soil_veg_deferred / k_soil_pixel_flagged   fused canopy + soil column per (fraction, pixel)
+//                         with open/sealed + per-pixel sums + groundwater per pixel (lf_soil_kernel.cuh).
 //   2. k_of_level/k_of_post  the three overland-flow routers (Other, Forest, Direct) on LddToChan,
 //                         solved together in one level sweep (three independent Newton solves per thread),
 //                         then OFToChanM3 / ToChanM3RunoffDt written in channel order.
@@ -82,13 +82,13 @@ __device__ __forceinline__ void chan_substep(const ChanPtrs &C, int i, double U1
         if (QZ) {
             const double zn = lfkw::solve_z(U1, X.qk, side * L, a);
             qr1 = zn;
-            X.m3 = fmax(L * alpha * (zn * zn * zn), 0.0);  // ChanLength * ChannelAlpha * ChanQKin**Beta, :527-530
+            X.m3 = lfm::dmax(L * alpha * (zn * zn * zn), 0.0);  // ChanLength * ChannelAlpha * ChanQKin**Beta, :527-530
             X.qk = zn;                                     // :531 is the identity on z
             X.chanq = lfkw::pow5(zn);
         } else {
             double qn = lfkw::solve(U1, X.qk, side * L, a, C.P);
             qr1 = qn;
-            X.m3 = fmax(L * alpha * pw(qn, C.P.beta), 0.0);          // :527-530
+            X.m3 = lfm::dmax(L * alpha * pw(qn, C.P.beta), 0.0);          // :527-530
             X.qk = pw(X.m3 * invL * (1 / alpha), C.P.inv_beta);      // :531
             X.chanq = X.qk;
         }
@@ -103,7 +103,7 @@ __device__ __forceinline__ void chan_substep(const ChanPtrs &C, int i, double U1
         s2 = s2 + c2qstart * invL;
         const double zn = lfkw::solve_z(U1, X.qk, s1 * L, a);
         qr1 = zn;
-        X.m3 = fmax(L * alpha * (zn * zn * zn), 0.0);
+        X.m3 = lfm::dmax(L * alpha * (zn * zn * zn), 0.0);
         X.qk = zn;
         const double zn2 = lfkw::solve_z(U2, X.q2k, s2 * L, a2);
         qr2 = zn2;
@@ -116,7 +116,7 @@ __device__ __forceinline__ void chan_substep(const ChanPtrs &C, int i, double U1
         X.m32 = m32;
         X.cs2a = (m32 - c2start) * invL;
         X.q2k = z2;
-        X.chanq = fmax(lfkw::pow5(zn) + lfkw::pow5(z2) - qlimit, 0.0);
+        X.chanq = lfm::dmax(lfkw::pow5(zn) + lfkw::pow5(z2) - qlimit, 0.0);
         X.sumnl = X.sum;
         X.sum += X.chanq;
     } else {
@@ -129,7 +129,7 @@ __device__ __forceinline__ void chan_substep(const ChanPtrs &C, int i, double U1
         s2 = s2 + c2qstart * invL;                                // :566-568
         double qn = lfkw::solve(U1, X.qk, s1 * L, a, C.P);        // :573
         qr1 = qn;
-        X.m3 = fmax(L * alpha * pw(qn, C.P.beta), 0.0);
+        X.m3 = lfm::dmax(L * alpha * pw(qn, C.P.beta), 0.0);
         X.qk = pw(X.m3 * invL * (1 / alpha), C.P.inv_beta);
         double qn2 = lfkw::solve(U2, X.q2k, s2 * L, a2, C.P);     // :583
         qr2 = qn2;
@@ -138,7 +138,7 @@ __device__ __forceinline__ void chan_substep(const ChanPtrs &C, int i, double U1
         X.m32 = m32;
         X.cs2a = (m32 - c2start) * invL;                          // :590
         X.q2k = pw(m32 * invL * (1 / alpha2), C.P.inv_beta);      // :593
-        X.chanq = fmax(X.qk + X.q2k - qlimit, 0.0);               // :597
+        X.chanq = lfm::dmax(X.qk + X.q2k - qlimit, 0.0);               // :597
         X.sumnl = X.sum;
         X.sum += X.chanq;
     }
@@ -268,10 +268,10 @@ __global__ void k_chan_post(int n, int split, int qz, int S, double DtSec, const
     ChanQAvg[i] = sd / S;
     DischargeM3Out[i] += atLast[i] ? ChanQ[i] * DtSec : 0.;
     if (FlowVelocity) {
-        const double area = fmax(M3[i] * invL, 0.01);
+        const double area = lfm::dmax(M3[i] * invL, 0.01);
         const double q = qz ? lfkw::pow5(Qk[i]) : Qk[i];
-        double fv = fmin(q / area, 0.36 * pw(q, 0.24));
-        fv *= fmin(sqrt(PixelArea_ch[i]) * invL, 1.);
+        double fv = lfm::dmin(q / area, 0.36 * pw(q, 0.24));
+        fv *= lfm::dmin(sqrt(PixelArea_ch[i]) * invL, 1.);
         FlowVelocity[i] = fv;
         TravelDistance[i] = fv * DtSec;
     }
@@ -637,6 +637,7 @@ int soil_stage(lf_model *m)
         const char *cn[8] = {"__cTaInt", "__cTa", "__cES", "__cPref", "__cInf", "__cUZout", "__cGwPerc", "__cSurf"};
         double **dst[8] = {&P.cTaInt, &P.cTa, &P.cES, &P.cPref, &P.cInf, &P.cUZout, &P.cGwPerc, &P.cSurf};
         for (int c = 0; c < 8; ++c) {
+            if (!m->cfg.diagnostics && (c == 3 || c == 4)) continue;  // PrefFlowPixel / InfiltrationPixel: diagnostics only
             auto it = m->fields.find(cn[c]);
             if (it == m->fields.end()) {
                 std::unique_ptr<Field> f(new Field());
@@ -647,6 +648,9 @@ int soil_stage(lf_model *m)
             }
             *dst[c] = it->second->buf.p;
         }
+        uint8_t *pdef = nullptr;
+        LF_CHECK(flag_buf(m, "__pix_deferred", &pdef));
+        P.pix_deferred = pdef;
         if (!m->soil_list.p) {
             // capacity per bucket: a quarter of the columns (typically ~6 % of all columns are deferred in total);
             // a full list degrades gracefully: the column is integrated in the first pass
@@ -664,7 +668,6 @@ int soil_stage(lf_model *m)
         if (m->soil_profile) cudaEventRecord(m->soil_ev[k], st);
     };
     tick(0);
-    const dim3 grid_veg(lf::blocks_for(m->n, lfsoil::SOIL_THREADS), 3);   // y = vegetation fraction
     const unsigned grid_def = lf::blocks_for(m->soil_list_cap, lfsoil::SOIL_THREADS);
     const unsigned grid_pix = lf::blocks_for(m->n, 256);
     if (m->cfg.diagnostics) {
@@ -703,33 +706,34 @@ int soil_stage(lf_model *m)
         }
         D.NoSubS = (int32_t *)ns->buf.p;
     }
-    // resident blocks per SM requested from the compiler for the column kernels (registers vs occupancy):
-    // 4 -> ~108 registers, 6 -> 80, 8 -> 64 (with local-memory spills).  LF_SOIL_MINBLOCKS overrides (tuning).
-    static int minb = [] {
-        const char *e = getenv("LF_SOIL_MINBLOCKS");
-        int v = e ? atoi(e) : 8;
-        return (v == 4 || v == 6 || v == 8) ? v : 8;
-    }();
-#define LF_SOIL_LAUNCH(DG, MB)                                                                        \
+    // Tile (pixels per block; the block has 3x as many threads) and resident blocks per SM requested from the
+    // compiler (registers vs occupancy).  LF_SOIL_VARIANT overrides (tuning): 0 = 64 px x 5 blocks (64 registers),
+    // 1 = 64 px x 4 (80 registers), 2 = 128 px x 2 (80 registers), 3 = 64 px x 3 (112 registers).
+    int variant = 1;
+    if (const char *e = getenv("LF_SOIL_VARIANT")) {  // read per call: tools/soil_variants.py switches it between runs
+        const int v = atoi(e);
+        if (v >= 0 && v <= 3) variant = v;
+    }
+#define LF_SOIL_LAUNCH(DG, TILE, MB, MBD)                                                              \
     do {                                                                                              \
-        k_soil_veg<DG, MB><<<grid_veg, lfsoil::SOIL_THREADS, 0, st>>>(P, D);                          \
+        k_soil_fused<DG, TILE, MB><<<lf::blocks_for(m->n, TILE), 3 * TILE, 0, st>>>(P, D);            \
         LF_LAUNCH_CHECK();                                                                            \
         tick(1);                                                                                      \
         for (int b = 0; b < lfsoil::NBUCKET; ++b) {                                                   \
-            k_soil_veg_deferred<DG, MB><<<grid_def, lfsoil::SOIL_THREADS, 0, st>>>(P, D, b);          \
+            k_soil_veg_deferred<DG, MBD><<<grid_def, lfsoil::SOIL_THREADS, 0, st>>>(P, D, b);         \
             LF_LAUNCH_CHECK();                                                                        \
             tick(2 + b);                                                                              \
         }                                                                                             \
+        k_soil_pixel_flagged<DG><<<grid_pix, 256, 0, st>>>(P, D);                                     \
     } while (0)
     if (m->cfg.diagnostics) {
-        LF_SOIL_LAUNCH(true, 4);
-        k_soil_pixel<true><<<grid_pix, 256, 0, st>>>(P, D);
+        LF_SOIL_LAUNCH(true, 64, 3, 4);
     } else {
         // diagnostics-only parameter rows are never dereferenced in these instantiations
-        if (minb == 4) LF_SOIL_LAUNCH(false, 4);
-        else if (minb == 6) LF_SOIL_LAUNCH(false, 6);
-        else LF_SOIL_LAUNCH(false, 8);  // measured best on B200
-        k_soil_pixel<false><<<grid_pix, 256, 0, st>>>(P, D);
+        if (variant == 0) LF_SOIL_LAUNCH(false, 64, 5, 8);
+        else if (variant == 2) LF_SOIL_LAUNCH(false, 128, 2, 8);
+        else if (variant == 3) LF_SOIL_LAUNCH(false, 64, 3, 8);
+        else LF_SOIL_LAUNCH(false, 64, 4, 8);
     }
 #undef LF_SOIL_LAUNCH
     LF_LAUNCH_CHECK();

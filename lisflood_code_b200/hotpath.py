@@ -194,7 +194,7 @@ class HotPathModel(object):
         ms = np.zeros(8, np.float64)
         _capi.check(_capi.lib().lf_model_soil_stats(self._h, 1 if enable_timing else 0, _capi.ptr(cnt), _capi.ptr(ms)))
         return {"deferred_columns": cnt.tolist(), "deferred_fraction": float(cnt.sum()) / (3.0 * self.N),
-                "kernel_ms": dict(zip(["k_soil_veg"] + ["deferred_%d" % b for b in range(6)] + ["k_soil_pixel"],
+                "kernel_ms": dict(zip(["k_soil_fused"] + ["deferred_%d" % b for b in range(6)] + ["k_soil_pixel_flagged"],
                                       [round(x, 3) for x in ms.tolist()]))}
 
     def info(self):

@@ -23,3 +23,10 @@ def test_pw_accuracy_against_libm(tmp_path):
         mm = re.match(r"pw\((\S+),(\S+)\)=(\S+) pow=(\S+)", line)
         if mm and mm.group(1) not in ("-1", "nan", "4.94066e-324", "1e-310"):   # denormal bases flush to 1e-300
             assert mm.group(3).lstrip("-") == mm.group(4).lstrip("-"), line
+    # table-driven variants used by the soil column kernel: error grows with |y log2 x| like any 2^(y log2 x)
+    m = re.search(r"pw_tab max rel err ([0-9.e+-]+) .* normalised by \(1\+\|y log2 x\|\) ([0-9.e+-]+) ; >1e-13: (\d+)", out)
+    assert m, out
+    assert float(m.group(2)) < 4e-16
+    m = re.search(r"log2_tab max err/\(1\+\|log2 x\|\) ([0-9.e+-]+) ; exp_neg_tab max rel/\(1\+\|x\|\) ([0-9.e+-]+)", out)
+    assert m and float(m.group(1)) < 4e-16 and float(m.group(2)) < 4e-16, out
+    assert "pw_tab(0,0.3)=0 pw_tab(1,7.5)=1 pw_tab(1e-200,9)=0" in out and "exp_neg_tab(0)=1 exp_neg_tab(-1000)=0" in out
