@@ -14,7 +14,7 @@ def test_device_math_accuracy(gpu_lib):
     names = ["div_nr", "sqrt_nr", "pw_tab", "exp_neg_tab", "root5", "root3", "pw", "van_genuchten_term"]
     got = dict(zip(names, err.tolist()))
     eps = 2.0 ** -52
-    limits = {"div_nr": 2 * eps, "sqrt_nr": 2 * eps, "pw_tab": 4 * eps, "exp_neg_tab": 4 * eps, "root5": 4 * eps,
-              "root3": 4 * eps, "pw": 4 * eps, "van_genuchten_term": 1e-9}
+    limits = {"div_nr": 2 * eps, "sqrt_nr": 2 * eps, "pw_tab": 4 * eps, "exp_neg_tab": 4 * eps, "root5": 8 * eps,
+              "root3": 8 * eps, "pw": 4 * eps, "van_genuchten_term": 1e-9}
     bad = {k: v for k, v in got.items() if not v <= limits[k]}
     assert not bad, (bad, got)
