@@ -653,8 +653,9 @@ int soil_stage(lf_model *m)
         P.pix_deferred = pdef;
         if (!m->soil_list.p) {
             // capacity per bucket: a quarter of the columns (typically ~6 % of all columns are deferred in total);
-            // a full list degrades gracefully: the column is integrated in the first pass
+            // a full list degrades gracefully: the column is integrated by k_soil_pixel_flagged
             m->soil_list_cap = (int32_t)std::max<int64_t>(1024, (3 * m->n) / 4);
+            if (const char *e = getenv("LF_SOIL_LIST_CAP")) m->soil_list_cap = std::max(1, atoi(e));  // tests: force the overflow path
             LF_CHECK(m->soil_list.alloc((size_t)lfsoil::NBUCKET * m->soil_list_cap));
             LF_CHECK(m->soil_list_cnt.alloc(lfsoil::NBUCKET));
             m->bytes += (int64_t)lfsoil::NBUCKET * m->soil_list_cap * 4;
@@ -706,17 +707,19 @@ int soil_stage(lf_model *m)
         }
         D.NoSubS = (int32_t *)ns->buf.p;
     }
-    // Tile (pixels per block; the block has 3x as many threads) and resident blocks per SM requested from the
-    // compiler (registers vs occupancy).  LF_SOIL_VARIANT overrides (tuning): 0 = 64 px x 5 blocks (64 registers),
-    // 1 = 64 px x 4 (80 registers), 2 = 128 px x 2 (80 registers), 3 = 64 px x 3 (112 registers).
-    int variant = 1;
+    // First pass of the lean build: k_soil_staged (inputs staged in shared memory by bulk async copies) unless
+    // LF_SOIL_VARIANT selects one of the direct-load launch shapes of k_soil_fused (tuning / fallback comparison):
+    //   0..5  k_soil_fused with 64 px x 5 / 64 x 4 / 128 x 2 / 64 x 3 / 64 x 6 / 64 x 7 resident blocks
+    //   10    k_soil_staged 32 px x 9 blocks    11  64 px x 4    12  32 px x 8    13  64 px x 5 (if it fits)
+    // Measured on C3 (profiles/): k_soil_fused is bound by global-load latency (61 % long-scoreboard stalls).
+    int variant = 13;
     if (const char *e = getenv("LF_SOIL_VARIANT")) {  // read per call: tools/soil_variants.py switches it between runs
         const int v = atoi(e);
-        if (v >= 0 && v <= 3) variant = v;
+        if ((v >= 0 && v <= 5) || (v >= 10 && v <= 13)) variant = v;
     }
-#define LF_SOIL_LAUNCH(DG, TILE, MB, MBD)                                                              \
+    const int force_plain = getenv("LF_SOIL_PLAIN") ? atoi(getenv("LF_SOIL_PLAIN")) : 0;
+#define LF_SOIL_REST(DG, MBD)                                                                         \
     do {                                                                                              \
-        k_soil_fused<DG, TILE, MB><<<lf::blocks_for(m->n, TILE), 3 * TILE, 0, st>>>(P, D);            \
         LF_LAUNCH_CHECK();                                                                            \
         tick(1);                                                                                      \
         for (int b = 0; b < lfsoil::NBUCKET; ++b) {                                                   \
@@ -726,16 +729,84 @@ int soil_stage(lf_model *m)
         }                                                                                             \
         k_soil_pixel_flagged<DG><<<grid_pix, 256, 0, st>>>(P, D);                                     \
     } while (0)
+#define LF_SOIL_LAUNCH(DG, TILE, MB, MBD)                                                              \
+    do {                                                                                              \
+        k_soil_fused<DG, TILE, MB><<<lf::blocks_for(m->n, TILE), 3 * TILE, 0, st>>>(P, D);            \
+        LF_SOIL_REST(DG, MBD);                                                                        \
+    } while (0)
+#define LF_SOIL_STAGED(TILE, MB)                                                                                          \
+    do {                                                                                                                  \
+        const size_t smem = lfsoil::staged_smem_bytes<TILE>(G.nrows);                                                     \
+        static bool attr_set = false;                                                                                     \
+        if (!attr_set) {                                                                                                  \
+            LF_CUDA(cudaFuncSetAttribute(k_soil_staged<TILE, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                         (int)lfsoil::staged_smem_bytes<TILE>(lfsoil::MAX_STAGE_ROWS)));                  \
+            LF_CUDA(cudaFuncSetAttribute(k_soil_staged<TILE, MB>, cudaFuncAttributePreferredSharedMemoryCarveout,         \
+                                         cudaSharedmemCarveoutMaxShared));                                                \
+            attr_set = true;                                                                                              \
+        }                                                                                                                 \
+        k_soil_staged<TILE, MB><<<lf::blocks_for(m->n, TILE), 3 * TILE, smem, st>>>(P, G, force_plain);                   \
+        LF_SOIL_REST(false, 8);                                                                                           \
+    } while (0)
     if (m->cfg.diagnostics) {
         LF_SOIL_LAUNCH(true, 64, 3, 4);
+    } else if (variant >= 10) {
+        // copy plan: per-pixel rows, (V,N) rows per fraction, land-use groups stored once per distinct pointer set
+        Stage G;
+        memset(&G, 0, sizeof(G));
+        int nr = 0;
+        const double *pix[lfsoil::NPIXROW] = {P.Rain, P.SnowMelt, P.ETRef, P.EWRef, P.ESRef, P.bX, P.PowPref, P.UZK,
+                                              P.GwPercStep, P.LZK, P.LZThreshold, P.GwLossStep, P.DirectRunoffFraction,
+                                              P.WaterFraction, P.LZ, P.CumInterSealed, P.LZInflowCUM, P.TaCUM,
+                                              P.TaInterceptionCUM, P.ESActCUM, P.GwLossCUM};
+        for (int r = 0; r < lfsoil::NPIXROW; ++r) G.src[nr++] = pix[r];
+        const double *veg[lfsoil::NVEGROW] = {P.SoilFraction, P.LAI, P.LAITerm, P.CumInterception, P.W1a, P.W1b, P.W2,
+                                              P.UZ, P.DSLR};
+        for (int v = 0; v < 3; ++v)
+            for (int r = 0; r < lfsoil::NVEGROW; ++r) G.src[nr++] = veg[r] + (int64_t)v * m->n;
+        const double *const *ga[lfsoil::NLUA] = {P.KSat1a, P.KSat1b, P.InvM1a, P.InvM1b, P.WRes1a, P.WRes1b,
+                                                 P.WS1a,   P.WS1b,   P.WWP1a,  P.WWP1b,  P.WFC1a,  P.WFC1b};
+        const double *const *gb[lfsoil::NLUB] = {P.KSat2, P.InvM2, P.WRes2, P.WS2};
+        const double *const *gc[lfsoil::NLUC] = {P.CropCoef, P.CropGroup};
+        auto add_group = [&](const double *const *const *rows, int nparam, int32_t *off) {
+            for (int v = 0; v < 3; ++v) {
+                int same = -1;
+                for (int u = 0; u < v && same < 0; ++u) {
+                    bool eq = true;
+                    for (int q = 0; q < nparam; ++q) eq = eq && rows[q][u] == rows[q][v];
+                    if (eq) same = u;
+                }
+                if (same >= 0) {
+                    off[v] = off[same];
+                } else {
+                    off[v] = nr;
+                    for (int q = 0; q < nparam; ++q) G.src[nr++] = rows[q][v];
+                }
+            }
+        };
+        add_group(ga, lfsoil::NLUA, G.offA);
+        add_group(gb, lfsoil::NLUB, G.offB);
+        add_group(gc, lfsoil::NLUC, G.offC);
+        G.nrows = nr;
+        bool aligned = (reinterpret_cast<uintptr_t>(P.frozen) & 15) == 0;
+        for (int r = 0; r < nr; ++r) aligned = aligned && (reinterpret_cast<uintptr_t>(G.src[r]) & 15) == 0;
+        G.bulk_ok = aligned ? 1 : 0;
+        if (variant == 11) LF_SOIL_STAGED(64, 4);
+        else if (variant == 12) LF_SOIL_STAGED(32, 8);
+        else if (variant == 10) LF_SOIL_STAGED(32, 9);
+        else LF_SOIL_STAGED(64, 5);  // 34 land-use rows (C3) leave room for five 64-pixel tiles per SM
     } else {
         // diagnostics-only parameter rows are never dereferenced in these instantiations
         if (variant == 0) LF_SOIL_LAUNCH(false, 64, 5, 8);
+        else if (variant == 4) LF_SOIL_LAUNCH(false, 64, 6, 8);
+        else if (variant == 5) LF_SOIL_LAUNCH(false, 64, 7, 8);
         else if (variant == 2) LF_SOIL_LAUNCH(false, 128, 2, 8);
         else if (variant == 3) LF_SOIL_LAUNCH(false, 64, 3, 8);
         else LF_SOIL_LAUNCH(false, 64, 4, 8);
     }
+#undef LF_SOIL_STAGED
 #undef LF_SOIL_LAUNCH
+#undef LF_SOIL_REST
     LF_LAUNCH_CHECK();
     tick(8);
     return LF_OK;

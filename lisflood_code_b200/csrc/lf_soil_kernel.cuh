@@ -93,6 +93,101 @@ struct Contrib {
     double taint, ta, es, pref, inf, uzout, gwperc, surf;
 };
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Input rows of one pixel tile.  The column / pixel code below reads every input through an accessor, so the same
+// source serves two feeds: InGlobal (plain global loads: deferred columns, diagnostics build) and InStaged (the tile's
+// rows staged in shared memory by bulk async copies, k_soil_staged).
+// ---------------------------------------------------------------------------------------------------------------
+enum PixRow {  // per-pixel maps (N); the first 9 are read by the columns, the rest by the per-pixel part
+    R_Rain, R_SnowMelt, R_ETRef, R_EWRef, R_ESRef, R_bX, R_PowPref, R_UZK, R_GwPercStep,
+    R_LZK, R_LZThreshold, R_GwLossStep, R_DRF, R_WF, R_LZ, R_CumInterSealed, R_LZInflowCUM, R_TaCUM, R_TaIntCUM,
+    R_ESActCUM, R_GwLossCUM, NPIXROW
+};
+enum VegRow { V_SoilFraction, V_LAI, V_LAITerm, V_CumInt, V_W1a, V_W1b, V_W2, V_UZ, V_DSLR, NVEGROW };  // (V,N) maps
+// land-use parameter rows in three groups that alias differently between land uses (Lisflood_initial.py:371-391):
+// A = layers 1a/1b (separate forest maps), B = layer 2 (one map for all land uses), C = crop maps (three maps)
+enum LuARow { A_KSat1a, A_KSat1b, A_InvM1a, A_InvM1b, A_WRes1a, A_WRes1b, A_WS1a, A_WS1b, A_WWP1a, A_WWP1b, A_WFC1a,
+              A_WFC1b, NLUA };
+enum LuBRow { B_KSat2, B_InvM2, B_WRes2, B_WS2, NLUB };
+enum LuCRow { C_CropCoef, C_CropGroup, NLUC };
+constexpr int MAX_STAGE_ROWS = NPIXROW + 3 * NVEGROW + 3 * (NLUA + NLUB + NLUC);
+
+// Copy plan of k_soil_staged, built on the host per launch (lf_model.cu::soil_stage): shared-memory row r of a tile
+// starting at pixel `base` is src[r][base .. base+TILE).  Rows 0..NPIXROW-1 are the per-pixel maps, then NVEGROW rows
+// per vegetation fraction, then the land-use groups; a group whose row pointers all equal those of an earlier land use
+// is stored once (offA/offB/offC give the first row of the group fraction v reads).
+struct Stage {
+    const double *src[MAX_STAGE_ROWS];
+    int32_t nrows;
+    int32_t offA[3], offB[3], offC[3];
+    int32_t bulk_ok;  // every src pointer (and the frozen flags) 16-byte aligned for every full tile (needs n even)
+};
+
+struct InGlobal {
+    const Ptrs &P;
+    int v, i;
+    int64_t k;
+    __device__ __forceinline__ InGlobal(const Ptrs &P_, int v_, int i_) : P(P_), v(v_), i(i_), k((int64_t)v_ * P_.n + i_) {}
+#define LF_IN_PIX(name, member) __device__ __forceinline__ double name() const { return P.member[i]; }
+#define LF_IN_VEG(name, member) __device__ __forceinline__ double name() const { return P.member[k]; }
+#define LF_IN_LU(name, member) __device__ __forceinline__ double name() const { return P.member[v][i]; }
+    LF_IN_PIX(Rain, Rain) LF_IN_PIX(SnowMelt, SnowMelt) LF_IN_PIX(ETRef, ETRef) LF_IN_PIX(EWRef, EWRef)
+    LF_IN_PIX(ESRef, ESRef) LF_IN_PIX(bX, bX) LF_IN_PIX(PowPref, PowPref) LF_IN_PIX(UZK, UZK)
+    LF_IN_PIX(GwPercStep, GwPercStep) LF_IN_PIX(LZK, LZK) LF_IN_PIX(LZThreshold, LZThreshold)
+    LF_IN_PIX(GwLossStep, GwLossStep) LF_IN_PIX(DRF, DirectRunoffFraction) LF_IN_PIX(WF, WaterFraction)
+    LF_IN_PIX(LZ, LZ) LF_IN_PIX(CumInterSealed, CumInterSealed) LF_IN_PIX(LZInflowCUM, LZInflowCUM)
+    LF_IN_PIX(TaCUM, TaCUM) LF_IN_PIX(TaIntCUM, TaInterceptionCUM) LF_IN_PIX(ESActCUM, ESActCUM)
+    LF_IN_PIX(GwLossCUM, GwLossCUM)
+    LF_IN_VEG(SoilFraction, SoilFraction) LF_IN_VEG(LAI, LAI) LF_IN_VEG(LAITerm, LAITerm)
+    LF_IN_VEG(CumInt, CumInterception) LF_IN_VEG(W1a, W1a) LF_IN_VEG(W1b, W1b) LF_IN_VEG(W2, W2) LF_IN_VEG(UZ, UZ)
+    LF_IN_VEG(DSLR, DSLR)
+    LF_IN_LU(KSat1a, KSat1a) LF_IN_LU(KSat1b, KSat1b) LF_IN_LU(KSat2, KSat2) LF_IN_LU(InvM1a, InvM1a)
+    LF_IN_LU(InvM1b, InvM1b) LF_IN_LU(InvM2, InvM2) LF_IN_LU(WRes1a, WRes1a) LF_IN_LU(WRes1b, WRes1b)
+    LF_IN_LU(WRes2, WRes2) LF_IN_LU(WS1a, WS1a) LF_IN_LU(WS1b, WS1b) LF_IN_LU(WS2, WS2) LF_IN_LU(WWP1a, WWP1a)
+    LF_IN_LU(WWP1b, WWP1b) LF_IN_LU(WFC1a, WFC1a) LF_IN_LU(WFC1b, WFC1b) LF_IN_LU(CropCoef, CropCoef)
+    LF_IN_LU(CropGroup, CropGroup)
+#undef LF_IN_PIX
+#undef LF_IN_VEG
+#undef LF_IN_LU
+    __device__ __forceinline__ bool frozen() const { return P.frozen[i] != 0; }
+};
+
+// rows of the tile in shared memory: row r of local pixel pl is rows[r * TILE + pl]
+template <int TILE>
+struct InStaged {
+    const double *pp, *pv, *pa, *pb, *pc;  // pixel rows, this fraction's (V,N) rows, its land-use groups (all + pl)
+    bool fr;
+    __device__ __forceinline__ InStaged(const double *rows, const Stage &G, const uint8_t *frozen_row, int v, int pl)
+        : pp(rows + pl), pv(rows + (NPIXROW + NVEGROW * v) * TILE + pl), pa(rows + G.offA[v] * TILE + pl),
+          pb(rows + G.offB[v] * TILE + pl), pc(rows + G.offC[v] * TILE + pl), fr(frozen_row[pl] != 0) {}
+#define LF_IN_PIX(name, row) __device__ __forceinline__ double name() const { return pp[(row) * TILE]; }
+#define LF_IN_VEG(name, row) __device__ __forceinline__ double name() const { return pv[(row) * TILE]; }
+#define LF_IN_A(name, row) __device__ __forceinline__ double name() const { return pa[(row) * TILE]; }
+#define LF_IN_B(name, row) __device__ __forceinline__ double name() const { return pb[(row) * TILE]; }
+#define LF_IN_C(name, row) __device__ __forceinline__ double name() const { return pc[(row) * TILE]; }
+    LF_IN_PIX(Rain, R_Rain) LF_IN_PIX(SnowMelt, R_SnowMelt) LF_IN_PIX(ETRef, R_ETRef) LF_IN_PIX(EWRef, R_EWRef)
+    LF_IN_PIX(ESRef, R_ESRef) LF_IN_PIX(bX, R_bX) LF_IN_PIX(PowPref, R_PowPref) LF_IN_PIX(UZK, R_UZK)
+    LF_IN_PIX(GwPercStep, R_GwPercStep) LF_IN_PIX(LZK, R_LZK) LF_IN_PIX(LZThreshold, R_LZThreshold)
+    LF_IN_PIX(GwLossStep, R_GwLossStep) LF_IN_PIX(DRF, R_DRF) LF_IN_PIX(WF, R_WF) LF_IN_PIX(LZ, R_LZ)
+    LF_IN_PIX(CumInterSealed, R_CumInterSealed) LF_IN_PIX(LZInflowCUM, R_LZInflowCUM) LF_IN_PIX(TaCUM, R_TaCUM)
+    LF_IN_PIX(TaIntCUM, R_TaIntCUM) LF_IN_PIX(ESActCUM, R_ESActCUM) LF_IN_PIX(GwLossCUM, R_GwLossCUM)
+    LF_IN_VEG(SoilFraction, V_SoilFraction) LF_IN_VEG(LAI, V_LAI) LF_IN_VEG(LAITerm, V_LAITerm)
+    LF_IN_VEG(CumInt, V_CumInt) LF_IN_VEG(W1a, V_W1a) LF_IN_VEG(W1b, V_W1b) LF_IN_VEG(W2, V_W2) LF_IN_VEG(UZ, V_UZ)
+    LF_IN_VEG(DSLR, V_DSLR)
+    LF_IN_A(KSat1a, A_KSat1a) LF_IN_A(KSat1b, A_KSat1b) LF_IN_A(InvM1a, A_InvM1a) LF_IN_A(InvM1b, A_InvM1b)
+    LF_IN_A(WRes1a, A_WRes1a) LF_IN_A(WRes1b, A_WRes1b) LF_IN_A(WS1a, A_WS1a) LF_IN_A(WS1b, A_WS1b)
+    LF_IN_A(WWP1a, A_WWP1a) LF_IN_A(WWP1b, A_WWP1b) LF_IN_A(WFC1a, A_WFC1a) LF_IN_A(WFC1b, A_WFC1b)
+    LF_IN_B(KSat2, B_KSat2) LF_IN_B(InvM2, B_InvM2) LF_IN_B(WRes2, B_WRes2) LF_IN_B(WS2, B_WS2)
+    LF_IN_C(CropCoef, C_CropCoef) LF_IN_C(CropGroup, C_CropGroup)
+#undef LF_IN_PIX
+#undef LF_IN_VEG
+#undef LF_IN_A
+#undef LF_IN_B
+#undef LF_IN_C
+    __device__ __forceinline__ bool frozen() const { return fr; }
+};
+
 // saturationDegree + unsaturatedConductivity, soilloop.py:360-383
 __device__ __forceinline__ double unsat_k(double w, bool pore, double wres, double ws, double ksat, double invm, double m,
                                           const MathTab *MT)
@@ -113,33 +208,36 @@ __device__ __forceinline__ int bucket_of(int nsub)
 
 enum ColumnResult { COL_DONE = 0, COL_QUEUED = 1 };
 
-template <bool DIAG>
-__device__ __noinline__ void soil_column_overflow(const Ptrs &P, const Diag &D, const MathTab *MT, int v, int i);
+// A column whose bucket list is full (never seen in practice: each list holds a quarter of all columns) is marked by a
+// NaN in its cSurf slot; k_soil_pixel_flagged integrates it in place (soil_column_overflow) before summing the pixel.
+// Nothing is called from the first pass: a call there costs ~260 bytes of register spills on the common path.
+__device__ __forceinline__ double overflow_mark() { return __longlong_as_double(0x7ff8000000000b20ll); }
 
 // One soil column (vegetation fraction v of pixel i, k = v*N + i).
 // FIRST = true  (k_soil_fused): a column needing more than one Darcy sub-step is queued (COL_QUEUED; nothing written);
 //                otherwise the state is written and the contributions are returned in C (COL_DONE).
 // FIRST = false (k_soil_veg_deferred): integrates any number of sub-steps, writes state and the c* maps.
-template <bool DIAG, bool FIRST>
-__device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D, const MathTab *MT, int v, int i, Contrib &C)
+template <bool DIAG, bool FIRST, class IN>
+__device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D, const MathTab *MT, int v, int i, const IN &in,
+                                                    Contrib &C)
 {
-    // 32-bit pixel index + one 64-bit row offset: the ~50 map accesses of a column then cost one IMAD.WIDE each
+    // 32-bit pixel index + one 64-bit row offset: a map access then costs one IMAD.WIDE
     const int64_t N = P.n;
     const int64_t k = (int64_t)v * N + i;
-    const double rain = P.Rain[i], etref = P.ETRef[i], ewref = P.EWRef[i];
-    const bool frozen = P.frozen[i] != 0;
-    const double bX = P.bX[i];
-    const double rain_snow = rain + P.SnowMelt[i];
-    const double frac = P.SoilFraction[k];
-    const double lai = P.LAI[k], laiterm = P.LAITerm[k];
-    const double wres1a = P.WRes1a[v][i], wres1b = P.WRes1b[v][i], wres2 = P.WRes2[v][i];
-    const double ws1a = P.WS1a[v][i], ws1b = P.WS1b[v][i], ws2 = P.WS2[v][i];
-    const double wwp1a = P.WWP1a[v][i], wwp1b = P.WWP1b[v][i], wfc1a = P.WFC1a[v][i], wfc1b = P.WFC1b[v][i];
-    double w1a = P.W1a[k], w1b = P.W1b[k], w2 = P.W2[k];
+    const double rain = in.Rain(), etref = in.ETRef(), ewref = in.EWRef();
+    const bool frozen = in.frozen();
+    const double bX = in.bX();
+    const double rain_snow = rain + in.SnowMelt();
+    const double frac = in.SoilFraction();
+    const double lai = in.LAI(), laiterm = in.LAITerm();
+    const double wres1a = in.WRes1a(), wres1b = in.WRes1b(), wres2 = in.WRes2();
+    const double ws1a = in.WS1a(), ws1b = in.WS1b(), ws2 = in.WS2();
+    const double wwp1a = in.WWP1a(), wwp1b = in.WWP1b(), wfc1a = in.WFC1a(), wfc1b = in.WFC1b();
+    double w1a = in.W1a(), w1b = in.W1b(), w2 = in.W2();
     // ---------------- canopy: interception (soilloop.py:27-70) ----------------
     const double one_minus = 1. - laiterm;
     const double ta_int_max = ewref * one_minus;  // :531-532
-    double cum = P.CumInterception[k];
+    double cum = in.CumInt();
     double smax;
     if (lai <= .1) smax = 0.;
     else if (lai <= 43.3) smax = 0.935 + 0.498 * lai - 0.00575 * (lai * lai);
@@ -160,9 +258,9 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
         leafdr = 0.;
     }
     // ---------------- canopy: transpiration and soil water stress (:549-627) ----------------
-    const double transpir_max = P.CropCoef[v][i] * etref * one_minus;
+    const double transpir_max = in.CropCoef() * etref * one_minus;
     const double pot_t = dmax(transpir_max - ta_int, 0.);
-    const double cgn = P.CropGroup[v][i];
+    const double cgn = in.CropGroup();
     const double e_dep = dmin(0.1 * etref * P.InvDtDay, 1.0);
     double p = div_nr(1., 0.76 + 1.5 * e_dep) - 0.10 * (5 - cgn);
     if (cgn <= 2.5) p = p + div_nr(e_dep - 0.6, cgn * (cgn + 3));
@@ -193,14 +291,14 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
     }
     // ---------------- soil column (soilloop.py:105-355) ----------------
     double avail = dmax(rain_snow + leafdr - interception, 0.);  // :131
-    double dslr = P.DSLR[k];
+    double dslr = in.DSLR();
     if (avail > P.AvWaterThreshold) dslr = 1;
     else dslr += P.DtDay;  // :137-140
     double esact;
     if (frozen) {
         esact = 0.;
     } else {
-        const double esmax = P.ESRef[i] * laiterm;  // :638
+        const double esmax = in.ESRef() * laiterm;  // :638
         esact = esmax * (lfm::sqrt_nr(dslr) - lfm::sqrt_nr(dslr - 1));
         esact = dmax(dmin(esact, w1 - (wres1a + wres1b)), 0.);
         const double supply1a = w1a - wres1a;
@@ -217,7 +315,7 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
     const double store_max = div_nr(ws1, bX1);   // StoreMaxPervious, soil.py:363
     const double powinf = div_nr(bX1, bX);       // PowerInfPot, soil.py:361
     const double infpot = frozen ? 0.0 : store_max * lfm::pw_tab<true>(1. - satfrac, powinf, MT) * P.DtDay;
-    const double prefflow = lfm::pw_tab<true>(relsat1, P.PowPref[i], MT) * avail;
+    const double prefflow = lfm::pw_tab<true>(relsat1, in.PowPref(), MT) * avail;
     avail -= prefflow;
     double infil = dmax(dmin(avail, infpot), 0.);
     {
@@ -225,8 +323,8 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
         w1a = dmin(ws1a, test);
         w1b += dmax(test - ws1a, 0.);
     }
-    const double ks1a = P.KSat1a[v][i], ks1b = P.KSat1b[v][i], ks2 = P.KSat2[v][i];
-    const double im1a = P.InvM1a[v][i], im1b = P.InvM1b[v][i], im2 = P.InvM2[v][i];
+    const double ks1a = in.KSat1a(), ks1b = in.KSat1b(), ks2 = in.KSat2();
+    const double im1a = in.InvM1a(), im1b = in.InvM1b(), im2 = in.InvM2();
     const double m1a = div_nr(1.0, im1a), m1b = div_nr(1.0, im1b), m2 = div_nr(1.0, im2);  // GenuM
     double k1a = unsat_k(w1a, pore1a, wres1a, ws1a, ks1a, im1a, m1a, MT);
     double k1b = unsat_k(w1b, pore1b, wres1b, ws1b, ks1b, im1b, m1b, MT);
@@ -258,7 +356,7 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
                 if (b == bb) {
                     const int slot = base + __popc(mk & ((1u << lane) - 1));
                     if (slot < P.list_cap) P.list[(int64_t)bb * P.list_cap + slot] = (int32_t)k;
-                    else soil_column_overflow<DIAG>(P, D, MT, v, i);  // list full: integrate here (never seen in practice)
+                    else P.cSurf[k] = overflow_mark();  // list full: left to k_soil_pixel_flagged
                     queued = true;
                 }
             }
@@ -300,8 +398,8 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
     infil -= dmax(w1a - ws1a, 0.);
     w1a = dmin(w1a, ws1a);
     // upper zone (:340-354)
-    double uz = P.UZ[k];
-    double uzout = dmin(P.UZK[i] * uz, uz);
+    double uz = in.UZ();
+    double uzout = dmin(in.UZK() * uz, uz);
     uz = dmax(uz - uzout, 0.);
     if (v == 2 && P.DrainedFraction > 0) {  // is_irrigated[v] and DrainedFraction > 0 (:115)
         uzout += P.DrainedFraction * seepG;
@@ -309,7 +407,7 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
     } else {
         uz += seepG + prefflow;
     }
-    const double gwp = dmin(P.GwPercStep[i], uz);
+    const double gwp = dmin(in.GwPercStep(), uz);
     uz = dmax(uz - gwp, 0.);
     // ---- state ----
     P.CumInterception[k] = cum;
@@ -374,50 +472,50 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
 }
 
 template <bool DIAG>
-__device__ __noinline__ void soil_column_overflow(const Ptrs &P, const Diag &D, const MathTab *MT, int v, int i)
+__device__ __noinline__ void soil_column_overflow(const Ptrs &P, const Diag &D, int v, int i)
 {
     Contrib C;
-    soil_column<DIAG, false>(P, D, MT, v, i, C);
+    soil_column<DIAG, false>(P, D, &lfm::g_mathtab, v, i, InGlobal(P, v, i), C);  // tables read in place (rare path)
 }
 
 // per pixel: open water / sealed soil, totals over the fractions, groundwater, runoff components.
 // s*: sums over the three fractions in the reference's order, (c0 + c1) + c2.
-template <bool DIAG>
-__device__ __forceinline__ void soil_pixel(const Ptrs &P, const Diag &D, int64_t i, double sTaInt, double sTa, double sES,
-                                           double sUZout, double sGwPerc, double surfOther, double surfForest,
+template <bool DIAG, class IN>
+__device__ __forceinline__ void soil_pixel(const Ptrs &P, const Diag &D, int64_t i, const IN &in, double sTaInt, double sTa,
+                                           double sES, double sUZout, double sGwPerc, double surfOther, double surfForest,
                                            double sPref, double sInf)
 {
     const int64_t N = P.n;
-    const double ewref = P.EWRef[i];
-    const double rain_snow = P.Rain[i] + P.SnowMelt[i];
+    const double ewref = in.EWRef();
+    const double rain_snow = in.Rain() + in.SnowMelt();
     // ---------------- open water and sealed soil (opensealed.py:41-71) ----------------
     const double rsm = dmax(rain_snow, 0.);
     const double ewater = dmax(dmin(ewref, rsm) * 1.0, 0.);
-    double cums = P.CumInterSealed[i];
+    double cums = in.CumInterSealed();
     const double intersealed = dmin(dmax(P.SMaxSealed - cums, 0.), rsm);
     cums += intersealed;
     const double tasealed = dmax(dmin(cums, ewref), 0.);
     cums = dmax(cums - tasealed, 0.);
     P.CumInterSealed[i] = cums;
-    const double drf = P.DirectRunoffFraction[i], wf = P.WaterFraction[i];
+    const double drf = in.DRF(), wf = in.WF();
     const double direct = drf * (rsm - intersealed) + wf * (rsm - ewater);
     // ---------------- per-pixel totals (soil.py:475-486) ----------------
     const double taintall = sTaInt + drf * tasealed;
     const double esactpix = sES + wf * ewater;
-    P.TaInterceptionCUM[i] += taintall;
-    P.TaCUM[i] += sTa;
-    P.ESActCUM[i] += esactpix;
+    P.TaInterceptionCUM[i] = in.TaIntCUM() + taintall;
+    P.TaCUM[i] = in.TaCUM() + sTa;
+    P.ESActCUM[i] = in.ESActCUM() + esactpix;
     // ---------------- groundwater (groundwater.py:134-180) ----------------
-    double lz = P.LZ[i];
-    const double lzout = dmax(dmin(P.LZK[i] * lz, lz - P.LZThreshold[i]), 0.);
+    double lz = in.LZ();
+    const double lzout = dmax(dmin(in.LZK() * lz, lz - in.LZThreshold()), 0.);
     lz -= lzout;
     lz += sGwPerc;
-    const double gwloss = dmax(dmin(P.GwLossStep[i], lz), 0.0);
+    const double gwloss = dmax(dmin(in.GwLossStep(), lz), 0.0);
     lz = lz - gwloss;
     P.LZ[i] = lz;
-    const double lzcum = dmax(P.LZInflowCUM[i] + (sGwPerc - gwloss), 0.0);
+    const double lzcum = dmax(in.LZInflowCUM() + (sGwPerc - gwloss), 0.0);
     P.LZInflowCUM[i] = lzcum;
-    P.GwLossCUM[i] += gwloss;
+    P.GwLossCUM[i] = in.GwLossCUM() + gwloss;
     // ---------------- runoff components handed to the routers ----------------
     P.DirectRunoff[i] = direct;
     P.SurfOther[i] = surfOther;
@@ -476,7 +574,7 @@ __global__ void __launch_bounds__(3 * TILE, MINB) k_soil_fused(const __grid_cons
     Contrib C;
     bool done = false;
     if (inside) {
-        done = soil_column<DIAG, true>(P, D, &s_tab, v, (int)i, C) == COL_DONE;
+        done = soil_column<DIAG, true>(P, D, &s_tab, v, (int)i, InGlobal(P, v, (int)i), C) == COL_DONE;
         if (!done) s_def[pl] = 1;
     }
     if (done) {
@@ -514,7 +612,7 @@ __global__ void __launch_bounds__(3 * TILE, MINB) k_soil_fused(const __grid_cons
     if (v != 0) return;
     P.pix_deferred[i] = 0;
 #define LF_S3(c) ((s_c[c][0][pl] + s_c[c][1][pl]) + s_c[c][2][pl])
-    soil_pixel<DIAG>(P, D, i, LF_S3(0), LF_S3(1), LF_S3(2), LF_S3(3), LF_S3(4),
+    soil_pixel<DIAG>(P, D, i, InGlobal(P, 0, (int)i), LF_S3(0), LF_S3(1), LF_S3(2), LF_S3(3), LF_S3(4),
                      s_c[5][0][pl] + s_c[5][2][pl],  // Rainfed + Irrigated (surface_routing.py:145)
                      s_c[5][1][pl], DIAG ? LF_S3(NC - 2) : 0., DIAG ? LF_S3(NC - 1) : 0.);
 #undef LF_S3
@@ -536,22 +634,158 @@ __global__ void __launch_bounds__(SOIL_THREADS, MINB) k_soil_veg_deferred(const 
     const int64_t k = P.list[(int64_t)bucket * P.list_cap + j];
     const int v = k >= 2 * P.n ? 2 : (k >= P.n ? 1 : 0);
     Contrib C;
-    soil_column<DIAG, false>(P, D, &s_tab, v, (int)(k - (int64_t)v * P.n), C);
+    const int i = (int)(k - (int64_t)v * P.n);
+    soil_column<DIAG, false>(P, D, &s_tab, v, i, InGlobal(P, v, i), C);
 }
 
 // ---- kernel 3: per-pixel part of the flagged pixels (those with a deferred column; all pixels with diagnostics) ----
 template <bool DIAG>
-__global__ void __launch_bounds__(256) k_soil_pixel_flagged(Ptrs P, Diag D)
+__global__ void __launch_bounds__(256, 4) k_soil_pixel_flagged(const __grid_constant__ Ptrs P, const __grid_constant__ Diag D)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t N = P.n;
     if (i >= N) return;
     if (!P.pix_deferred[i]) return;
+    double s0 = P.cSurf[i], s1 = P.cSurf[N + i], s2 = P.cSurf[2 * N + i];
+    if (s0 != s0 || s1 != s1 || s2 != s2) {  // columns that found their bucket list full (overflow_mark)
+        if (s0 != s0) soil_column_overflow<DIAG>(P, D, 0, (int)i);
+        if (s1 != s1) soil_column_overflow<DIAG>(P, D, 1, (int)i);
+        if (s2 != s2) soil_column_overflow<DIAG>(P, D, 2, (int)i);
+        s0 = P.cSurf[i], s1 = P.cSurf[N + i], s2 = P.cSurf[2 * N + i];
+    }
 #define LF_SUM3(arr) ((arr[i] + arr[N + i]) + arr[2 * N + i])
-    soil_pixel<DIAG>(P, D, i, LF_SUM3(P.cTaInt), LF_SUM3(P.cTa), LF_SUM3(P.cES), LF_SUM3(P.cUZout), LF_SUM3(P.cGwPerc),
-                     P.cSurf[i] + P.cSurf[2 * N + i], P.cSurf[N + i], DIAG ? LF_SUM3(P.cPref) : 0.,
-                     DIAG ? LF_SUM3(P.cInf) : 0.);
+    soil_pixel<DIAG>(P, D, i, InGlobal(P, 0, (int)i), LF_SUM3(P.cTaInt), LF_SUM3(P.cTa), LF_SUM3(P.cES), LF_SUM3(P.cUZout),
+                     LF_SUM3(P.cGwPerc), s0 + s2, s1, DIAG ? LF_SUM3(P.cPref) : 0., DIAG ? LF_SUM3(P.cInf) : 0.);
 #undef LF_SUM3
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_soil_staged: the lean (no diagnostics) first pass with the tile's input rows staged in shared memory.
+//
+// k_soil_fused spends 61 % of its warp-stall samples waiting for global loads (profiles/r01_soil_fused_ncu.txt): the
+// ~54 loads of a column cannot all be in flight with 56-64 registers per thread.  Here a block first pulls every
+// input row of its TILE pixels into shared memory -- one `cp.async.bulk` (TMA, 1-D) of TILE*8 bytes per map, issued by
+// one lane per warp, all completing on one mbarrier -- and the three columns of each pixel then read their inputs with
+// LDS at immediate offsets (no pointer fetch, no 64-bit address arithmetic, ~30 cycles instead of a DRAM round trip).
+// The math tables arrive by the same mechanism.  While a block waits for its rows the other resident blocks of the SM
+// compute, so the copies overlap the arithmetic without a software pipeline.  The fraction-weighted column results are
+// exchanged through the column's own (already consumed) state rows.  Tiles that cannot use bulk copies (the ragged
+// last tile, odd N: the 16-byte alignment rule) are staged with ordinary loads by the whole block; results are
+// identical.  State and outputs are written straight to global memory as before.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// dynamic shared memory of k_soil_staged<TILE>: mbarrier (16 B) | rows | math tables | frozen flags | deferred flags
+template <int TILE>
+__host__ __device__ constexpr size_t staged_smem_bytes(int nrows)
+{
+    return 16 + (size_t)nrows * TILE * 8 + sizeof(MathTab) + TILE + TILE * 4;
+}
+
+template <int TILE, int MINB>
+__global__ void __launch_bounds__(3 * TILE, MINB) k_soil_staged(const __grid_constant__ Ptrs P, const __grid_constant__ Stage G, int force_plain)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *rows = reinterpret_cast<double *>(smem_raw + 16);
+    MathTab *tab = reinterpret_cast<MathTab *>(rows + (size_t)G.nrows * TILE);
+    uint8_t *s_frozen = reinterpret_cast<uint8_t *>(tab + 1);
+    int *s_def = reinterpret_cast<int *>(s_frozen + TILE);
+    const int tid = threadIdx.x;
+    const int v = tid / TILE, pl = tid - v * TILE;  // warp-uniform v (TILE is a multiple of 32)
+    const int64_t base = (int64_t)blockIdx.x * TILE;
+    const int64_t i = base + pl;
+    const bool inside = i < P.n;
+    const int cnt = (int)((P.n - base) < (int64_t)TILE ? (P.n - base) : (int64_t)TILE);
+    const bool bulk = G.bulk_ok && cnt == TILE && !force_plain;  // block-uniform
+    if (tid < TILE) s_def[tid] = 0;
+    if (bulk) {
+        const uint32_t bar_a = smem_addr(bar);
+        if (tid == 0) {
+            const uint32_t total = (uint32_t)(G.nrows * TILE * 8 + sizeof(MathTab) + TILE);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(total) : "memory");
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) {  // one lane per warp issues its share of the row copies
+            const int w = tid >> 5;
+            constexpr int NW = 3 * TILE / 32;
+            if (w == 0) {
+                bulk_g2s(tab, &lfm::g_mathtab, sizeof(MathTab), bar_a);
+                bulk_g2s(s_frozen, P.frozen + base, TILE, bar_a);
+            }
+            for (int r = w; r < G.nrows; r += NW) bulk_g2s(rows + (size_t)r * TILE, G.src[r] + base, TILE * 8, bar_a);
+        }
+        // every thread waits for phase 0 of the barrier (the copies' bytes); bounded so that a bug traps instead of hanging
+        uint32_t ok = 0;
+        const long long t0 = clock64();
+        while (true) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(bar_a)
+                : "memory");
+            if (ok) break;
+            if (clock64() - t0 > 4000000000ll) __trap();
+        }
+    } else {
+        lfm::tab_to_shared(tab, tid, 3 * TILE);
+        for (int idx = tid; idx < G.nrows * TILE; idx += 3 * TILE) {
+            const int r = idx / TILE, p = idx - r * TILE;
+            if (p < cnt) rows[idx] = G.src[r][base + p];
+        }
+        if (tid < cnt) s_frozen[tid] = P.frozen[base + tid];
+        __syncthreads();
+    }
+    Contrib C;
+    bool done = false;
+    double *mine = rows + (size_t)(NPIXROW + NVEGROW * v) * TILE + pl;  // this column's (V,N) rows
+    if (inside) {
+        const InStaged<TILE> in(rows, G, s_frozen, v, pl);
+        done = soil_column<false, true>(P, Diag(), tab, v, (int)i, in, C) == COL_DONE;
+        if (!done) s_def[pl] = 1;
+    }
+    if (done) {  // the column's own state rows are consumed: they carry its contributions to the per-pixel part
+        mine[0 * TILE] = C.taint;
+        mine[1 * TILE] = C.ta;
+        mine[2 * TILE] = C.es;
+        mine[3 * TILE] = C.uzout;
+        mine[4 * TILE] = C.gwperc;
+        mine[5 * TILE] = C.surf;
+    }
+    __syncthreads();
+    if (!inside) return;
+    if (s_def[pl] != 0) {
+        if (done) {  // park the finished column's contributions for k_soil_pixel_flagged
+            const int64_t k = (int64_t)v * P.n + i;
+            P.cTaInt[k] = C.taint;
+            P.cTa[k] = C.ta;
+            P.cES[k] = C.es;
+            P.cUZout[k] = C.uzout;
+            P.cGwPerc[k] = C.gwperc;
+            P.cSurf[k] = C.surf;
+        }
+        if (v == 0) P.pix_deferred[i] = 1;
+        return;
+    }
+    if (v != 0) return;
+    P.pix_deferred[i] = 0;
+    const double *c0 = rows + (size_t)NPIXROW * TILE + pl, *c1 = c0 + NVEGROW * TILE, *c2 = c1 + NVEGROW * TILE;
+#define LF_S3(c) ((c0[(c) * TILE] + c1[(c) * TILE]) + c2[(c) * TILE])
+    const InStaged<TILE> in(rows, G, s_frozen, 0, pl);
+    soil_pixel<false>(P, Diag(), i, in, LF_S3(0), LF_S3(1), LF_S3(2), LF_S3(3), LF_S3(4),
+                      c0[5 * TILE] + c2[5 * TILE],  // Rainfed + Irrigated (surface_routing.py:145)
+                      c1[5 * TILE], 0., 0.);
+#undef LF_S3
 }
 
 }  // namespace lfsoil

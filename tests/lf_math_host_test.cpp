@@ -39,8 +39,8 @@ int main() {
     // table-driven variants (soil column kernel): x in [0,1], y > 0
     {
         lfm::MathTab M;
-        memcpy(M.log2_tab, lfm::g_log2_tab, sizeof(M.log2_tab));
-        memcpy(M.exp2_tab, lfm::g_exp2_tab, sizeof(M.exp2_tab));
+        memcpy(M.log2_tab, lfm::g_mathtab.log2_tab, sizeof(M.log2_tab));
+        memcpy(M.exp2_tab, lfm::g_mathtab.exp2_tab, sizeof(M.exp2_tab));
         std::uniform_real_distribution<double> u01(0, 1), uyy(0.04, 25), uex(-60, 0);
         double wt = 0, wtn = 0, wx = 0, wy = 0, wlabs = 0, wexp = 0;
         long badt = 0;

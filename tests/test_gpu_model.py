@@ -103,3 +103,72 @@ def test_async_input_path_equals_sync(gpu_lib):
         assert np.array_equal(A.get("ChanQAvg"), B.get("ChanQAvg")), t
     st = A.soil_stats(enable_timing=False)
     assert sum(st["deferred_columns"]) > 0 and 0 < st["deferred_fraction"] < 0.5
+
+
+LEAN_STATE = ("W1a", "W1b", "W2", "UZ", "DSLR", "CumInterception")
+LEAN_PIXEL = ("LZ", "CumInterSealed", "LZInflowCUM", "TaCUM", "TaInterceptionCUM", "ESActCUM", "GwLossCUM", "ChanQAvg",
+              "ChanQKin", "OFQOther", "OFQForest", "OFQDirect")
+
+
+def _assert_same_state(A, B, tag):
+    for k in LEAN_STATE:
+        assert np.array_equal(A.get(k, 3), B.get(k, 3)), (tag, k)
+    for k in LEAN_PIXEL:
+        assert np.array_equal(A.get(k), B.get(k)), (tag, k)
+
+
+@pytest.mark.parametrize("rows,cols,maskf", [(96, 64, 0.0), (61, 71, 0.0), (80, 90, 0.15)])
+@pytest.mark.parametrize("variant,plain", [(10, 0), (10, 1), (11, 0), (12, 0), (13, 0), (0, 0), (4, 0)])
+def test_first_pass_launch_shapes_agree(gpu_lib, monkeypatch, rows, cols, maskf, variant, plain):
+    """The lean first pass of the soil stage -- inputs staged in shared memory by bulk async copies (variants 10-13),
+    staged by ordinary loads (LF_SOIL_PLAIN, and automatically for ragged tiles / odd N), or loaded directly
+    (k_soil_fused, variants 0-5) -- produces the bits of the diagnostics build, which the golden tests pin."""
+    from lisflood_code_b200 import synthetic
+    S = synthetic.full_stack(rows, cols, seed=21, split_routing=False, mask_fraction=maskf)
+    A = _model(gpu_lib, S, True)
+    monkeypatch.setenv("LF_SOIL_VARIANT", str(variant))
+    monkeypatch.setenv("LF_SOIL_PLAIN", str(plain))
+    B = _model(gpu_lib, S, False)
+    for t in range(3):
+        F = synthetic.forcing(S, t, 21)
+        A.step(F)
+        B.step(F)
+        _assert_same_state(A, B, (variant, plain, t))
+    st = B.soil_stats(enable_timing=False)
+    assert sum(st["deferred_columns"]) > 0
+
+
+def test_full_bucket_lists_fall_back_to_the_pixel_kernel(gpu_lib, monkeypatch):
+    """A column that finds its bucket list full is integrated by k_soil_pixel_flagged: same bits."""
+    from lisflood_code_b200 import synthetic
+    S = synthetic.full_stack(64, 64, seed=22, split_routing=True)
+    A = _model(gpu_lib, S, False)
+    monkeypatch.setenv("LF_SOIL_LIST_CAP", "3")
+    B = _model(gpu_lib, S, False)
+    for t in range(3):
+        F = synthetic.forcing(S, t, 22)
+        A.step(F)
+        B.step(F)
+        _assert_same_state(A, B, t)
+    assert sum(A.soil_stats(enable_timing=False)["deferred_columns"]) > 6 * 3
+
+
+@pytest.mark.parametrize("rows,cols,maskf", [(128, 96, 0.0), (75, 83, 0.2)])
+def test_lean_model_vs_oracle(gpu_lib, oracle, rows, cols, maskf):
+    """The production (lean) configuration against the CPU oracle, bulk-staged (even N, full tiles) and plain-staged."""
+    from lisflood_code_b200 import synthetic
+    from oracle import lisf_oracle_model as om
+    S = synthetic.full_stack(rows, cols, seed=23, split_routing=True, ldd_noise=0.4, mask_fraction=maskf)
+    O = om.OracleModel(S)
+    M = _model(gpu_lib, S, False)
+    for t in range(3):
+        F = synthetic.forcing(S, t, 23)
+        O.step(F)
+        M.step(F)
+        bad = {}
+        for k in LEAN_STATE + ("LZ", "TaCUM", "ESActCUM", "ChanQAvg", "ChanQKin", "Chan2QKin", "OFQOther", "OFQForest"):
+            want = np.asarray(getattr(O.var, k))
+            e = rel_err(M.get(k, 3 if want.ndim == 2 else 1), want)
+            if not e < TOL:
+                bad[k] = e
+        assert not bad, (t, bad)
