@@ -634,19 +634,17 @@ int soil_stage(lf_model *m)
     P.TimeSinceStart = (double)(m->steps + 1);
     // contributions handed from the column kernel to the pixel kernel, and the deferred-column lists
     {
-        const char *cn[8] = {"__cTaInt", "__cTa", "__cES", "__cPref", "__cInf", "__cUZout", "__cGwPerc", "__cSurf"};
-        double **dst[8] = {&P.cTaInt, &P.cTa, &P.cES, &P.cPref, &P.cInf, &P.cUZout, &P.cGwPerc, &P.cSurf};
-        for (int c = 0; c < 8; ++c) {
-            if (!m->cfg.diagnostics && (c == 3 || c == 4)) continue;  // PrefFlowPixel / InfiltrationPixel: diagnostics only
-            auto it = m->fields.find(cn[c]);
+        {
+            P.cstride = m->cfg.diagnostics ? 8 : 6;  // CS_PREF / CS_INF (PrefFlowPixel / InfiltrationPixel): diagnostics only
+            auto it = m->fields.find("__cbuf");
             if (it == m->fields.end()) {
                 std::unique_ptr<Field> f(new Field());
-                f->rows = 3;
-                LF_CHECK(f->buf.alloc((size_t)3 * m->n));
-                m->bytes += (int64_t)3 * m->n * 8;
-                it = m->fields.emplace(cn[c], std::move(f)).first;
+                f->rows = 3 * P.cstride;
+                LF_CHECK(f->buf.alloc((size_t)3 * P.cstride * m->n));
+                m->bytes += (int64_t)3 * P.cstride * m->n * 8;
+                it = m->fields.emplace("__cbuf", std::move(f)).first;
             }
-            *dst[c] = it->second->buf.p;
+            P.cbuf = it->second->buf.p;
         }
         uint8_t *pdef = nullptr;
         LF_CHECK(flag_buf(m, "__pix_deferred", &pdef));
@@ -669,7 +667,10 @@ int soil_stage(lf_model *m)
         if (m->soil_profile) cudaEventRecord(m->soil_ev[k], st);
     };
     tick(0);
-    const unsigned grid_def = lf::blocks_for(m->soil_list_cap, lfsoil::SOIL_THREADS);
+    // persistent grids of the deferred-column kernel: resident blocks per SM x SMs (never more than the lists can hold)
+    const unsigned grid_def_cap = lf::blocks_for((int64_t)lfsoil::NBUCKET * m->soil_list_cap, lfsoil::SOIL_THREADS);
+    const unsigned grid_def = std::min<unsigned>(grid_def_cap, (unsigned)(lf::sm_count() * (m->cfg.diagnostics ? 4 : 8)));
+    const unsigned grid_def6 = std::min<unsigned>(grid_def_cap, (unsigned)(lf::sm_count() * 6));
     const unsigned grid_pix = lf::blocks_for(m->n, 256);
     if (m->cfg.diagnostics) {
         BINDLU(WWP2, "WWP2") BINDLU(WFC2, "WFC2") BINDLU(Depth1a, "SoilDepth1a") BINDLU(Depth1b, "SoilDepth1b")
@@ -718,15 +719,17 @@ int soil_stage(lf_model *m)
         if ((v >= 0 && v <= 5) || (v >= 10 && v <= 13)) variant = v;
     }
     const int force_plain = getenv("LF_SOIL_PLAIN") ? atoi(getenv("LF_SOIL_PLAIN")) : 0;
+    const int def_mb = getenv("LF_SOIL_DEF_MB") ? atoi(getenv("LF_SOIL_DEF_MB")) : 6;  // resident blocks of the deferred kernel
 #define LF_SOIL_REST(DG, MBD)                                                                         \
     do {                                                                                              \
         LF_LAUNCH_CHECK();                                                                            \
         tick(1);                                                                                      \
-        for (int b = 0; b < lfsoil::NBUCKET; ++b) {                                                   \
-            k_soil_veg_deferred<DG, MBD><<<grid_def, lfsoil::SOIL_THREADS, 0, st>>>(P, D, b);         \
-            LF_LAUNCH_CHECK();                                                                        \
-            tick(2 + b);                                                                              \
-        }                                                                                             \
+        if (MBD == 8 && def_mb == 6)                                                                  \
+            k_soil_veg_deferred<DG, 6><<<grid_def6, lfsoil::SOIL_THREADS, 0, st>>>(P, D);             \
+        else                                                                                          \
+            k_soil_veg_deferred<DG, MBD><<<grid_def, lfsoil::SOIL_THREADS, 0, st>>>(P, D);            \
+        LF_LAUNCH_CHECK();                                                                            \
+        for (int b = 0; b < lfsoil::NBUCKET; ++b) tick(2 + b);                                        \
         k_soil_pixel_flagged<DG><<<grid_pix, 256, 0, st>>>(P, D);                                     \
     } while (0)
 #define LF_SOIL_LAUNCH(DG, TILE, MB, MBD)                                                              \

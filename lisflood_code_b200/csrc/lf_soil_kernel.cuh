@@ -24,10 +24,11 @@
 // 32 lanes (~12 on average, measured).  k_soil_fused therefore completes only the columns that need ONE
 // sub-step (~99 %) and appends the others, warp-aggregated, to one of six lists bucketed by sub-step count
 // (2-3, 4-7, 8-15, 16-31, 32-63, 64+); k_soil_veg_deferred then integrates each list with one thread per
-// column, so lanes of a warp differ by at most 2x in trip count.  Deferred columns recompute their (cheap)
-// prologue instead of spilling ~30 doubles of state.  A pixel with a deferred column is flagged (pix_deferred);
-// its finished columns park their contributions in the c* maps and k_soil_pixel_flagged completes it after the
-// deferred lists have run.  Results do not depend on list order.
+// column, so lanes of a warp differ by at most 2x in trip count.  A queued column is complete up to the infiltration:
+// it leaves a mid-column record in the maps it owns (see soil_column) and k_soil_veg_deferred resumes from it -- 23
+// gathered values instead of the column's 54, and none of the canopy / evaporation / infiltration arithmetic again.
+// A pixel with a deferred column is flagged (pix_deferred); its finished columns park their contributions in the c*
+// maps and k_soil_pixel_flagged completes it after the deferred lists have run.  Results do not depend on list order.
 //
 // Arithmetic: float64, unfused multiply-add like the reference (--fmad=false) except inside the library functions
 // of lf_math.cuh (table-driven x^y and e^x, Newton division and square root, 3-instruction min/max): the kernel is
@@ -59,10 +60,12 @@ struct Ptrs {
     double *LZ, *CumInterSealed, *LZInflowCUM, *TaCUM, *TaInterceptionCUM, *ESActCUM, *GwLossCUM;
     // outputs consumed by the routing stages
     double *DirectRunoff, *SurfOther, *SurfForest, *GwToChan;
-    // fraction-weighted per-column contributions of the pixels that have a deferred column, (V,N); written sparsely.
-    // cPref / cInf only exist (and are only touched) with diagnostics.
-    double *cTaInt, *cTa, *cES, *cPref, *cInf, *cUZout, *cGwPerc, *cSurf;
-    uint8_t *pix_deferred;  // (N): 1 = the per-pixel part is left to k_soil_pixel_flagged
+    // fraction-weighted per-column contributions of the pixels that have a deferred column; written sparsely.  One record
+    // of `cstride` doubles per column, the three columns of a pixel adjacent (record (i*3 + v)): a flagged pixel is summed
+    // from 144 contiguous bytes instead of 18 sectors.  Slots: enum CSlot (6 without diagnostics, 8 with).
+    double *cbuf;
+    int32_t cstride;
+    uint8_t *pix_deferred;  // (N): PIX_FLAGGED | overflow bits (see soil_column); 0 = pixel finished by the first pass
     // deferred columns: six lists of column indices (k = veg*N + pixel), bucketed by sub-step count
     int32_t *list;      // [6 * list_cap]
     int32_t *list_cnt;  // [6]
@@ -82,6 +85,9 @@ struct Diag {
         *SurfaceRunoff, *TotalRunoff;  // (N)
     int32_t *NoSubS;  // (V,N)
 };
+
+enum CSlot { CS_TAINT, CS_TA, CS_ES, CS_UZOUT, CS_GWPERC, CS_SURF, CS_PREF, CS_INF };
+__device__ __forceinline__ double *crec(const Ptrs &P, int v, int64_t i) { return P.cbuf + (i * 3 + v) * P.cstride; }
 
 using lfm::dmax;
 using lfm::dmin;
@@ -208,18 +214,93 @@ __device__ __forceinline__ int bucket_of(int nsub)
 
 enum ColumnResult { COL_DONE = 0, COL_QUEUED = 1 };
 
-// A column whose bucket list is full (never seen in practice: each list holds a quarter of all columns) is marked by a
-// NaN in its cSurf slot; k_soil_pixel_flagged integrates it in place (soil_column_overflow) before summing the pixel.
-// Nothing is called from the first pass: a call there costs ~260 bytes of register spills on the common path.
-__device__ __forceinline__ double overflow_mark() { return __longlong_as_double(0x7ff8000000000b20ll); }
+// flags of a pixel in pix_deferred: bit 0 = the per-pixel part is left to k_soil_pixel_flagged (a column of the pixel was
+// queued, or diagnostics are on); bits 1..3 = column v found its bucket list full (never seen in practice: each list holds
+// a quarter of all columns) and is integrated by k_soil_pixel_flagged itself.  Nothing is called from the first pass: a
+// call there costs ~260 bytes of register spills on the common path.
+constexpr int PIX_FLAGGED = 1;
+__device__ __forceinline__ int pix_overflow_bit(int v) { return 2 << v; }
 
-// One soil column (vegetation fraction v of pixel i, k = v*N + i).
-// FIRST = true  (k_soil_fused): a column needing more than one Darcy sub-step is queued (COL_QUEUED; nothing written);
-//                otherwise the state is written and the contributions are returned in C (COL_DONE).
-// FIRST = false (k_soil_veg_deferred): integrates any number of sub-steps, writes state and the c* maps.
-template <bool DIAG, bool FIRST, class IN>
+// ---- second half of a column: apply the seepage, upper zone, state and contributions (soilloop.py:314-354) ----
+template <bool DIAG>
+__device__ __forceinline__ void column_finish(const Ptrs &P, const Diag &D, int v, int i, int64_t k, bool frozen, double frac,
+                                              double w1a, double w1b, double w2, double seepA, double seepB, double seepG,
+                                              double avail, double infil, double prefflow, double ws1a, double uz,
+                                              double uzk, double gwpercstep, int nsub, Contrib &C)
+{
+    if (frozen) seepA = seepB = seepG = 0.;
+    w1a -= seepA;
+    w1b = w1b + seepA - seepB;
+    w2 = w2 + seepB - seepG;
+    const double w1 = w1a + w1b;
+    infil -= dmax(w1a - ws1a, 0.);
+    w1a = dmin(w1a, ws1a);
+    // upper zone (:340-354)
+    double uzout = dmin(uzk * uz, uz);
+    uz = dmax(uz - uzout, 0.);
+    if (v == 2 && P.DrainedFraction > 0) {  // is_irrigated[v] and DrainedFraction > 0 (:115)
+        uzout += P.DrainedFraction * seepG;
+        uz += (1 - P.DrainedFraction) * seepG + prefflow;
+    } else {
+        uz += seepG + prefflow;
+    }
+    const double gwp = dmin(gwpercstep, uz);
+    uz = dmax(uz - gwp, 0.);
+    P.W1a[k] = w1a;
+    P.W1b[k] = w1b;
+    P.W2[k] = w2;
+    P.UZ[k] = uz;
+    C.uzout = frac * uzout;
+    C.gwperc = frac * gwp;
+    C.surf = frac * dmax(avail - infil, 0.);  // SurfaceRunSoil, surface_routing.py:122-126
+    if (DIAG) {
+        C.inf = frac * infil;
+        D.Infiltration[k] = infil;
+        D.SeepTopToSubA[k] = seepA;
+        D.SeepTopToSubB[k] = seepB;
+        D.SeepSubToGW[k] = seepG;
+        const double d1a = P.Depth1a[v][i], d1b = P.Depth1b[v][i], d2 = P.Depth2[v][i];
+        const double wwp1a = P.WWP1a[v][i], wwp1b = P.WWP1b[v][i], wfc1a = P.WFC1a[v][i], wfc1b = P.WFC1b[v][i];
+        const double wfc1 = wfc1a + wfc1b, wwp1 = wwp1a + wwp1b;
+        D.Theta1a[k] = (P.WS1a[v][i] != 0 && d1a != 0) ? w1a / d1a : 0.;
+        D.Theta1b[k] = (P.WS1b[v][i] != 0 && d1b != 0) ? w1b / d1b : 0.;
+        D.Theta2[k] = (P.WS2[v][i] != 0 && d2 != 0) ? w2 / d2 : 0.;
+        D.Sat1a[k] = (w1a - wwp1a) / (wfc1a - wwp1a);
+        D.Sat1b[k] = (w1b - wwp1b) / (wfc1b - wwp1b);
+        D.Sat1[k] = (w1 - wwp1) / (wfc1 - wwp1);
+        D.Sat2[k] = (w2 - P.WWP2[v][i]) / (P.WFC2[v][i] - P.WWP2[v][i]);
+        D.UZOutflow[k] = uzout;
+        D.GwPercUZLZ[k] = gwp;
+        D.W1[k] = w1;
+        D.SurfaceRunSoil[k] = C.surf;
+        D.NoSubS[k] = nsub;
+        D.Theta[k] = frac * ((w1a + w1b) + w2) / ((d1a + d1b) + d2);  // soil.py:496-499
+    }
+}
+
+// Courant number of the column -> number of Darcy sub-steps (soilloop.py:218-236)
+__device__ __forceinline__ int substeps_of(const Ptrs &P, double k1a, double k1b, double k2, double av1a, double av1b,
+                                           double av2)
+{
+    const double cA = av1a == 0 ? 0. : div_nr(k1a * P.DtDay, av1a);
+    const double cB = av1b == 0 ? 0. : div_nr(k1b * P.DtDay, av1b);
+    const double cG = av2 == 0 ? 0. : div_nr(k2 * P.DtDay, av2);
+    const double courant = dmax(dmax(cA, cB), cG);
+    return (int)dmin(dmax(1., ceil(div_nr(courant, P.CourantCrit))), 2.0e9);
+}
+
+// ---- first pass over one soil column (vegetation fraction v of pixel i, k = v*N + i) ----
+// Canopy, transpiration, evaporation and infiltration (everything before the Darcy seepage) are final after this call
+// for EVERY column: CumInterception, DSLR and the contributions taint / ta / es (pref) are written or returned.
+//   one sub-step needed (~99 %): seepage, upper zone and state follow at once; contributions in C (COL_DONE);
+//   several sub-steps needed  : the column is appended to the bucket list of its sub-step count and its mid-column
+//     record is left in storage the column owns -- W1a/W1b/W2[k] = moisture after infiltration; in its contribution
+//     record CS_SURF = available water, CS_UZOUT = infiltration, CS_GWPERC = preferential flow, CS_TAINT/TA/ES(/PREF) =
+//     final contributions --
+//     for soil_column_resume (COL_QUEUED; *flags gets PIX_FLAGGED, plus the overflow bit if the list was full).
+template <bool DIAG, class IN>
 __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D, const MathTab *MT, int v, int i, const IN &in,
-                                                    Contrib &C)
+                                                    Contrib &C, int *flags)
 {
     // 32-bit pixel index + one 64-bit row offset: a map access then costs one IMAD.WIDE
     const int64_t N = P.n;
@@ -317,129 +398,20 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
     const double infpot = frozen ? 0.0 : store_max * lfm::pw_tab<true>(1. - satfrac, powinf, MT) * P.DtDay;
     const double prefflow = lfm::pw_tab<true>(relsat1, in.PowPref(), MT) * avail;
     avail -= prefflow;
-    double infil = dmax(dmin(avail, infpot), 0.);
+    const double infil = dmax(dmin(avail, infpot), 0.);
     {
         const double test = w1a + infil;
         w1a = dmin(ws1a, test);
         w1b += dmax(test - ws1a, 0.);
     }
-    const double ks1a = in.KSat1a(), ks1b = in.KSat1b(), ks2 = in.KSat2();
-    const double im1a = in.InvM1a(), im1b = in.InvM1b(), im2 = in.InvM2();
-    const double m1a = div_nr(1.0, im1a), m1b = div_nr(1.0, im1b), m2 = div_nr(1.0, im2);  // GenuM
-    double k1a = unsat_k(w1a, pore1a, wres1a, ws1a, ks1a, im1a, m1a, MT);
-    double k1b = unsat_k(w1b, pore1b, wres1b, ws1b, ks1b, im1b, m1b, MT);
-    double k2 = unsat_k(w2, pore2, wres2, ws2, ks2, im2, m2, MT);
-    double av1a = w1a - wres1a, av1b = w1b - wres1b, av2 = w2 - wres2;
-    double cap1 = ws1b - w1b, cap2 = ws2 - w2;
-    const double cA = av1a == 0 ? 0. : div_nr(k1a * P.DtDay, av1a);
-    const double cB = av1b == 0 ? 0. : div_nr(k1b * P.DtDay, av1b);
-    const double cG = av2 == 0 ? 0. : div_nr(k2 * P.DtDay, av2);
-    const double courant = dmax(dmax(cA, cB), cG);
-    const int nsub = (int)dmin(dmax(1., ceil(div_nr(courant, P.CourantCrit))), 2.0e9);
-    double seepA, seepB, seepG;
-    if (FIRST) {
-        // ---- columns that need several sub-steps go to the bucket lists ----
-        const unsigned act = __activemask();
-        const bool defer = nsub > 1;
-        if (__ballot_sync(act, defer)) {
-            const int b = defer ? bucket_of(nsub) : -1;
-            bool queued = false;
-#pragma unroll
-            for (int bb = 0; bb < NBUCKET; ++bb) {
-                const unsigned mk = __ballot_sync(act, b == bb);
-                if (mk == 0) continue;
-                const int lane = threadIdx.x & 31;
-                const int leader = __ffs(mk) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(P.list_cnt + bb, __popc(mk));
-                base = __shfl_sync(act, base, leader);
-                if (b == bb) {
-                    const int slot = base + __popc(mk & ((1u << lane) - 1));
-                    if (slot < P.list_cap) P.list[(int64_t)bb * P.list_cap + slot] = (int32_t)k;
-                    else P.cSurf[k] = overflow_mark();  // list full: left to k_soil_pixel_flagged
-                    queued = true;
-                }
-            }
-            if (queued) return COL_QUEUED;
-        }
-        // single sub-step (:237-312 with NoSubS == 1)
-        seepA = dmin(k1a * P.DtDay, cap1);
-        seepB = dmin(k1b * P.DtDay, cap2);
-        seepG = dmin(k2 * P.DtDay, av2);
-    } else {
-        const double dtsub = div_nr(P.DtDay, (double)nsub);
-        seepA = seepB = seepG = 0.;
-        double wt1a = w1a, wt1b = w1b, wt2 = w2;
-        for (int s = 0; s < nsub; ++s) {
-            if (s > 0) {
-                k1a = unsat_k(wt1a, pore1a, wres1a, ws1a, ks1a, im1a, m1a, MT);
-                k1b = unsat_k(wt1b, pore1b, wres1b, ws1b, ks1b, im1b, m1b, MT);
-                k2 = unsat_k(wt2, pore2, wres2, ws2, ks2, im2, m2, MT);
-            }
-            const double sA = dmin(k1a * dtsub, cap1), sB = dmin(k1b * dtsub, cap2), sG = dmin(k2 * dtsub, av2);
-            av1a -= sA;
-            av1b += sA - sB;
-            av2 += sB - sG;
-            wt1a = av1a + wres1a;
-            wt1b = av1b + wres1b;
-            wt2 = av2 + wres2;
-            cap1 = ws1b - wt1b;
-            cap2 = ws2 - wt2;
-            seepA += sA;
-            seepB += sB;
-            seepG += sG;
-        }
-    }
-    if (frozen) seepA = seepB = seepG = 0.;
-    w1a -= seepA;
-    w1b = w1b + seepA - seepB;
-    w2 = w2 + seepB - seepG;
-    w1 = w1a + w1b;
-    infil -= dmax(w1a - ws1a, 0.);
-    w1a = dmin(w1a, ws1a);
-    // upper zone (:340-354)
-    double uz = in.UZ();
-    double uzout = dmin(in.UZK() * uz, uz);
-    uz = dmax(uz - uzout, 0.);
-    if (v == 2 && P.DrainedFraction > 0) {  // is_irrigated[v] and DrainedFraction > 0 (:115)
-        uzout += P.DrainedFraction * seepG;
-        uz += (1 - P.DrainedFraction) * seepG + prefflow;
-    } else {
-        uz += seepG + prefflow;
-    }
-    const double gwp = dmin(in.GwPercStep(), uz);
-    uz = dmax(uz - gwp, 0.);
-    // ---- state ----
+    // ---- everything up to here is final: canopy state and the contributions that do not depend on the seepage ----
     P.CumInterception[k] = cum;
     P.DSLR[k] = dslr;
-    P.W1a[k] = w1a;
-    P.W1b[k] = w1b;
-    P.W2[k] = w2;
-    P.UZ[k] = uz;
-    // ---- fraction-weighted contributions to the pixel sums (deffraction, Lisflood_initial.py:393-396) ----
     C.taint = frac * ta_int;
     C.ta = frac * ta;
     C.es = frac * esact;
-    C.uzout = frac * uzout;
-    C.gwperc = frac * gwp;
-    C.surf = frac * dmax(avail - infil, 0.);  // SurfaceRunSoil, surface_routing.py:122-126
     if (DIAG) {
         C.pref = frac * prefflow;
-        C.inf = frac * infil;
-    }
-    if (!FIRST) {
-        P.cTaInt[k] = C.taint;
-        P.cTa[k] = C.ta;
-        P.cES[k] = C.es;
-        P.cUZout[k] = C.uzout;
-        P.cGwPerc[k] = C.gwperc;
-        P.cSurf[k] = C.surf;
-        if (DIAG) {
-            P.cPref[k] = C.pref;
-            P.cInf[k] = C.inf;
-        }
-    }
-    if (DIAG) {
         D.Interception[k] = interception;
         D.TaInterception[k] = ta_int;
         D.LeafDrainage[k] = leafdr;
@@ -447,35 +419,123 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
         D.Ta[k] = ta;
         D.ESAct[k] = esact;
         D.PrefFlow[k] = prefflow;
-        D.Infiltration[k] = infil;
         D.AvailableWaterForInfiltration[k] = avail;
-        D.SeepTopToSubA[k] = seepA;
-        D.SeepTopToSubB[k] = seepB;
-        D.SeepSubToGW[k] = seepG;
-        const double d1a = P.Depth1a[v][i], d1b = P.Depth1b[v][i], d2 = P.Depth2[v][i];
-        D.Theta1a[k] = (pore1a && d1a != 0) ? w1a / d1a : 0.;
-        D.Theta1b[k] = (pore1b && d1b != 0) ? w1b / d1b : 0.;
-        D.Theta2[k] = (pore2 && d2 != 0) ? w2 / d2 : 0.;
-        D.Sat1a[k] = (w1a - wwp1a) / (wfc1a - wwp1a);
-        D.Sat1b[k] = (w1b - wwp1b) / (wfc1b - wwp1b);
-        D.Sat1[k] = (w1 - wwp1) / (wfc1 - wwp1);
-        D.Sat2[k] = (w2 - P.WWP2[v][i]) / (P.WFC2[v][i] - P.WWP2[v][i]);
-        D.UZOutflow[k] = uzout;
-        D.GwPercUZLZ[k] = gwp;
         D.RWS[k] = rws;
-        D.W1[k] = w1;
-        D.SurfaceRunSoil[k] = C.surf;
-        D.NoSubS[k] = nsub;
-        D.Theta[k] = frac * ((w1a + w1b) + w2) / ((d1a + d1b) + d2);  // soil.py:496-499
     }
+    const double ks1a = in.KSat1a(), ks1b = in.KSat1b(), ks2 = in.KSat2();
+    const double im1a = in.InvM1a(), im1b = in.InvM1b(), im2 = in.InvM2();
+    const double m1a = div_nr(1.0, im1a), m1b = div_nr(1.0, im1b), m2 = div_nr(1.0, im2);  // GenuM
+    const double k1a = unsat_k(w1a, pore1a, wres1a, ws1a, ks1a, im1a, m1a, MT);
+    const double k1b = unsat_k(w1b, pore1b, wres1b, ws1b, ks1b, im1b, m1b, MT);
+    const double k2 = unsat_k(w2, pore2, wres2, ws2, ks2, im2, m2, MT);
+    const double av2 = w2 - wres2;
+    const int nsub = substeps_of(P, k1a, k1b, k2, w1a - wres1a, w1b - wres1b, av2);
+    // ---- columns that need several sub-steps go to the bucket lists ----
+    const unsigned act = __activemask();
+    const bool defer = nsub > 1;
+    if (__ballot_sync(act, defer)) {
+        const int b = defer ? bucket_of(nsub) : -1;
+#pragma unroll
+        for (int bb = 0; bb < NBUCKET; ++bb) {
+            const unsigned mk = __ballot_sync(act, b == bb);
+            if (mk == 0) continue;
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(mk) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(P.list_cnt + bb, __popc(mk));
+            base = __shfl_sync(act, base, leader);
+            if (b == bb) {
+                const int slot = base + __popc(mk & ((1u << lane) - 1));
+                if (slot < P.list_cap) {
+                    P.list[(int64_t)bb * P.list_cap + slot] = (int32_t)k;
+                    atomicOr(flags, PIX_FLAGGED);
+                } else {
+                    atomicOr(flags, PIX_FLAGGED | pix_overflow_bit(v));  // list full: left to k_soil_pixel_flagged
+                }
+            }
+        }
+        if (defer) {  // mid-column record
+            P.W1a[k] = w1a;
+            P.W1b[k] = w1b;
+            P.W2[k] = w2;
+            double *rec = crec(P, v, i);
+            rec[CS_SURF] = avail;
+            rec[CS_UZOUT] = infil;
+            rec[CS_GWPERC] = prefflow;
+            rec[CS_TAINT] = C.taint;
+            rec[CS_TA] = C.ta;
+            rec[CS_ES] = C.es;
+            if (DIAG) rec[CS_PREF] = C.pref;
+            return COL_QUEUED;
+        }
+    }
+    // single sub-step (:237-312 with NoSubS == 1)
+    const double seepA = dmin(k1a * P.DtDay, ws1b - w1b);
+    const double seepB = dmin(k1b * P.DtDay, ws2 - w2);
+    const double seepG = dmin(k2 * P.DtDay, av2);
+    column_finish<DIAG>(P, D, v, i, k, frozen, frac, w1a, w1b, w2, seepA, seepB, seepG, avail, infil, prefflow, ws1a, in.UZ(),
+                        in.UZK(), in.GwPercStep(), 1, C);
     return COL_DONE;
+}
+
+// ---- a queued column, resumed from its mid-column record: adaptive Darcy sub-steps (soilloop.py:237-312), then the
+// second half.  Writes the state and the remaining contributions (CS_UZOUT, CS_GWPERC, CS_SURF(, CS_INF)) over the record. ----
+template <bool DIAG>
+__device__ __forceinline__ void soil_column_resume(const Ptrs &P, const Diag &D, const MathTab *MT, int v, int i)
+{
+    const int64_t k = (int64_t)v * P.n + i;
+    const bool frozen = P.frozen[i] != 0;
+    const double w1a = P.W1a[k], w1b = P.W1b[k], w2 = P.W2[k];
+    double *rec = crec(P, v, i);
+    const double avail = rec[CS_SURF], infil = rec[CS_UZOUT], prefflow = rec[CS_GWPERC];
+    const double wres1a = P.WRes1a[v][i], wres1b = P.WRes1b[v][i], wres2 = P.WRes2[v][i];
+    const double ws1a = P.WS1a[v][i], ws1b = P.WS1b[v][i], ws2 = P.WS2[v][i];
+    const double ks1a = P.KSat1a[v][i], ks1b = P.KSat1b[v][i], ks2 = P.KSat2[v][i];
+    const double im1a = P.InvM1a[v][i], im1b = P.InvM1b[v][i], im2 = P.InvM2[v][i];
+    const double frac = P.SoilFraction[k], uz = P.UZ[k], uzk = P.UZK[i], gwpercstep = P.GwPercStep[i];
+    const bool pore1a = ws1a != 0, pore1b = ws1b != 0, pore2 = ws2 != 0;
+    const double m1a = div_nr(1.0, im1a), m1b = div_nr(1.0, im1b), m2 = div_nr(1.0, im2);  // GenuM
+    double k1a = unsat_k(w1a, pore1a, wres1a, ws1a, ks1a, im1a, m1a, MT);
+    double k1b = unsat_k(w1b, pore1b, wres1b, ws1b, ks1b, im1b, m1b, MT);
+    double k2 = unsat_k(w2, pore2, wres2, ws2, ks2, im2, m2, MT);
+    double av1a = w1a - wres1a, av1b = w1b - wres1b, av2 = w2 - wres2;
+    double cap1 = ws1b - w1b, cap2 = ws2 - w2;
+    const int nsub = substeps_of(P, k1a, k1b, k2, av1a, av1b, av2);
+    const double dtsub = div_nr(P.DtDay, (double)nsub);
+    double seepA = 0., seepB = 0., seepG = 0.;
+    double wt1a = w1a, wt1b = w1b, wt2 = w2;
+    for (int s = 0; s < nsub; ++s) {
+        if (s > 0) {
+            k1a = unsat_k(wt1a, pore1a, wres1a, ws1a, ks1a, im1a, m1a, MT);
+            k1b = unsat_k(wt1b, pore1b, wres1b, ws1b, ks1b, im1b, m1b, MT);
+            k2 = unsat_k(wt2, pore2, wres2, ws2, ks2, im2, m2, MT);
+        }
+        const double sA = dmin(k1a * dtsub, cap1), sB = dmin(k1b * dtsub, cap2), sG = dmin(k2 * dtsub, av2);
+        av1a -= sA;
+        av1b += sA - sB;
+        av2 += sB - sG;
+        wt1a = av1a + wres1a;
+        wt1b = av1b + wres1b;
+        wt2 = av2 + wres2;
+        cap1 = ws1b - wt1b;
+        cap2 = ws2 - wt2;
+        seepA += sA;
+        seepB += sB;
+        seepG += sG;
+    }
+    Contrib C;
+    column_finish<DIAG>(P, D, v, i, k, frozen, frac, w1a, w1b, w2, seepA, seepB, seepG, avail, infil, prefflow, ws1a, uz, uzk,
+                        gwpercstep, nsub, C);
+    rec[CS_UZOUT] = C.uzout;
+    rec[CS_GWPERC] = C.gwperc;
+    rec[CS_SURF] = C.surf;
+    if (DIAG) rec[CS_INF] = C.inf;
 }
 
 template <bool DIAG>
 __device__ __noinline__ void soil_column_overflow(const Ptrs &P, const Diag &D, int v, int i)
 {
-    Contrib C;
-    soil_column<DIAG, false>(P, D, &lfm::g_mathtab, v, i, InGlobal(P, v, i), C);  // tables read in place (rare path)
+    soil_column_resume<DIAG>(P, D, &lfm::g_mathtab, v, i);  // tables read in place (rare path)
 }
 
 // per pixel: open water / sealed soil, totals over the fractions, groundwater, runoff components.
@@ -574,8 +634,7 @@ __global__ void __launch_bounds__(3 * TILE, MINB) k_soil_fused(const __grid_cons
     Contrib C;
     bool done = false;
     if (inside) {
-        done = soil_column<DIAG, true>(P, D, &s_tab, v, (int)i, InGlobal(P, v, (int)i), C) == COL_DONE;
-        if (!done) s_def[pl] = 1;
+        done = soil_column<DIAG>(P, D, &s_tab, v, (int)i, InGlobal(P, v, (int)i), C, &s_def[pl]) == COL_DONE;
     }
     if (done) {
         s_c[0][v][pl] = C.taint;
@@ -591,22 +650,22 @@ __global__ void __launch_bounds__(3 * TILE, MINB) k_soil_fused(const __grid_cons
     }
     __syncthreads();
     if (!inside) return;
-    const bool pdef = s_def[pl] != 0;
-    if (pdef) {
+    const int fl = s_def[pl];
+    if (fl != 0) {
         if (done) {  // park the finished column's contributions for k_soil_pixel_flagged
-            const int64_t k = (int64_t)v * P.n + i;
-            P.cTaInt[k] = C.taint;
-            P.cTa[k] = C.ta;
-            P.cES[k] = C.es;
-            P.cUZout[k] = C.uzout;
-            P.cGwPerc[k] = C.gwperc;
-            P.cSurf[k] = C.surf;
+            double *rec = crec(P, v, i);
+            rec[CS_TAINT] = C.taint;
+            rec[CS_TA] = C.ta;
+            rec[CS_ES] = C.es;
+            rec[CS_UZOUT] = C.uzout;
+            rec[CS_GWPERC] = C.gwperc;
+            rec[CS_SURF] = C.surf;
             if (DIAG) {
-                P.cPref[k] = C.pref;
-                P.cInf[k] = C.inf;
+                rec[CS_PREF] = C.pref;
+                rec[CS_INF] = C.inf;
             }
         }
-        if (v == 0) P.pix_deferred[i] = 1;
+        if (v == 0) P.pix_deferred[i] = (uint8_t)fl;
         return;
     }
     if (v != 0) return;
@@ -620,22 +679,37 @@ __global__ void __launch_bounds__(3 * TILE, MINB) k_soil_fused(const __grid_cons
 
 constexpr int SOIL_THREADS = 128;
 
-// ---- kernel 2: the columns of one bucket list ----
+// ---- kernel 2: the queued columns of all bucket lists, one persistent launch ----
+// The grid is a fixed number of blocks (lf_model.cu sizes it to the SMs); threads stride over the concatenation of the
+// six lists, LONGEST sub-step counts first, so the few columns with 64+ sub-steps start at once and the many short ones
+// fill in behind them, and lanes of a warp stay within one bucket (trip counts within 2x).  Replaces six launches whose
+// grids had to cover the list capacity (millions of empty blocks) and whose small tails ran one after the other.
 template <bool DIAG, int MINB>
-__global__ void __launch_bounds__(SOIL_THREADS, MINB) k_soil_veg_deferred(const __grid_constant__ Ptrs P, const __grid_constant__ Diag D, int bucket)
+__global__ void __launch_bounds__(SOIL_THREADS, MINB) k_soil_veg_deferred(const __grid_constant__ Ptrs P, const __grid_constant__ Diag D)
 {
     __shared__ MathTab s_tab;
-    const int cnt = min(P.list_cnt[bucket], P.list_cap);
-    if ((int)(blockIdx.x * SOIL_THREADS) >= cnt) return;  // whole block beyond the list
     lfm::tab_to_shared(&s_tab, threadIdx.x, SOIL_THREADS);
     __syncthreads();
-    const int j = blockIdx.x * SOIL_THREADS + threadIdx.x;
-    if (j >= cnt) return;
-    const int64_t k = P.list[(int64_t)bucket * P.list_cap + j];
-    const int v = k >= 2 * P.n ? 2 : (k >= P.n ? 1 : 0);
-    Contrib C;
-    const int i = (int)(k - (int64_t)v * P.n);
-    soil_column<DIAG, false>(P, D, &s_tab, v, i, InGlobal(P, v, i), C);
+    int64_t end[NBUCKET];  // end[q]: items of the buckets NBUCKET-1 .. NBUCKET-1-q
+    int64_t total = 0;
+#pragma unroll
+    for (int q = 0; q < NBUCKET; ++q) {
+        total += min(P.list_cnt[NBUCKET - 1 - q], P.list_cap);
+        end[q] = total;
+    }
+    for (int64_t j = (int64_t)blockIdx.x * SOIL_THREADS + threadIdx.x; j < total; j += (int64_t)gridDim.x * SOIL_THREADS) {
+        int q = 0;
+        int64_t first = 0;
+#pragma unroll
+        for (int t = 0; t < NBUCKET - 1; ++t)
+            if (j >= end[t]) {
+                q = t + 1;
+                first = end[t];
+            }
+        const int64_t k = P.list[(int64_t)(NBUCKET - 1 - q) * P.list_cap + (j - first)];
+        const int v = k >= 2 * P.n ? 2 : (k >= P.n ? 1 : 0);
+        soil_column_resume<DIAG>(P, D, &s_tab, v, (int)(k - (int64_t)v * P.n));
+    }
 }
 
 // ---- kernel 3: per-pixel part of the flagged pixels (those with a deferred column; all pixels with diagnostics) ----
@@ -645,17 +719,17 @@ __global__ void __launch_bounds__(256, 4) k_soil_pixel_flagged(const __grid_cons
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t N = P.n;
     if (i >= N) return;
-    if (!P.pix_deferred[i]) return;
-    double s0 = P.cSurf[i], s1 = P.cSurf[N + i], s2 = P.cSurf[2 * N + i];
-    if (s0 != s0 || s1 != s1 || s2 != s2) {  // columns that found their bucket list full (overflow_mark)
-        if (s0 != s0) soil_column_overflow<DIAG>(P, D, 0, (int)i);
-        if (s1 != s1) soil_column_overflow<DIAG>(P, D, 1, (int)i);
-        if (s2 != s2) soil_column_overflow<DIAG>(P, D, 2, (int)i);
-        s0 = P.cSurf[i], s1 = P.cSurf[N + i], s2 = P.cSurf[2 * N + i];
+    const int fl = P.pix_deferred[i];
+    if (fl == 0) return;
+    if (fl & ~PIX_FLAGGED) {  // columns that found their bucket list full
+        for (int v = 0; v < 3; ++v)
+            if (fl & pix_overflow_bit(v)) soil_column_overflow<DIAG>(P, D, v, (int)i);
     }
-#define LF_SUM3(arr) ((arr[i] + arr[N + i]) + arr[2 * N + i])
-    soil_pixel<DIAG>(P, D, i, InGlobal(P, 0, (int)i), LF_SUM3(P.cTaInt), LF_SUM3(P.cTa), LF_SUM3(P.cES), LF_SUM3(P.cUZout),
-                     LF_SUM3(P.cGwPerc), s0 + s2, s1, DIAG ? LF_SUM3(P.cPref) : 0., DIAG ? LF_SUM3(P.cInf) : 0.);
+    const double *r0 = crec(P, 0, i), *r1 = r0 + P.cstride, *r2 = r1 + P.cstride;
+#define LF_SUM3(c) ((r0[c] + r1[c]) + r2[c])
+    soil_pixel<DIAG>(P, D, i, InGlobal(P, 0, (int)i), LF_SUM3(CS_TAINT), LF_SUM3(CS_TA), LF_SUM3(CS_ES), LF_SUM3(CS_UZOUT),
+                     LF_SUM3(CS_GWPERC), r0[CS_SURF] + r2[CS_SURF], r1[CS_SURF], DIAG ? LF_SUM3(CS_PREF) : 0.,
+                     DIAG ? LF_SUM3(CS_INF) : 0.);
 #undef LF_SUM3
 }
 
@@ -751,8 +825,7 @@ __global__ void __launch_bounds__(3 * TILE, MINB) k_soil_staged(const __grid_con
     double *mine = rows + (size_t)(NPIXROW + NVEGROW * v) * TILE + pl;  // this column's (V,N) rows
     if (inside) {
         const InStaged<TILE> in(rows, G, s_frozen, v, pl);
-        done = soil_column<false, true>(P, Diag(), tab, v, (int)i, in, C) == COL_DONE;
-        if (!done) s_def[pl] = 1;
+        done = soil_column<false>(P, Diag(), tab, v, (int)i, in, C, &s_def[pl]) == COL_DONE;
     }
     if (done) {  // the column's own state rows are consumed: they carry its contributions to the per-pixel part
         mine[0 * TILE] = C.taint;
@@ -764,17 +837,18 @@ __global__ void __launch_bounds__(3 * TILE, MINB) k_soil_staged(const __grid_con
     }
     __syncthreads();
     if (!inside) return;
-    if (s_def[pl] != 0) {
+    const int fl = s_def[pl];
+    if (fl != 0) {
         if (done) {  // park the finished column's contributions for k_soil_pixel_flagged
-            const int64_t k = (int64_t)v * P.n + i;
-            P.cTaInt[k] = C.taint;
-            P.cTa[k] = C.ta;
-            P.cES[k] = C.es;
-            P.cUZout[k] = C.uzout;
-            P.cGwPerc[k] = C.gwperc;
-            P.cSurf[k] = C.surf;
+            double *rec = crec(P, v, i);
+            rec[CS_TAINT] = C.taint;
+            rec[CS_TA] = C.ta;
+            rec[CS_ES] = C.es;
+            rec[CS_UZOUT] = C.uzout;
+            rec[CS_GWPERC] = C.gwperc;
+            rec[CS_SURF] = C.surf;
         }
-        if (v == 0) P.pix_deferred[i] = 1;
+        if (v == 0) P.pix_deferred[i] = (uint8_t)fl;
         return;
     }
     if (v != 0) return;
