@@ -265,8 +265,16 @@ def run_c3(args):
         return float(t.item())
 
     # ---- device-resident leg: forcing already in HBM, two alternating sets --------------------------
+    # Per step the meteorological maps (Rain, SnowMelt, ETRef, EWRef, ESRef, isFrozenSoil) change; LAI / LAITerm are
+    # 10-day maps in LISFLOOD (leafarea.py:76-90) and are set once, as in the end-to-end leg.  The synthetic initial
+    # state is cold (3.3 % of the soil columns need several Darcy sub-steps, 1.2 % once it has relaxed), so the model
+    # is spun up for `--spinup` untimed steps first, like the reference's pre-run (the W warm-up steps follow).
     Fdev = [dev.forcing_device(i) for i in range(2)]
     torch.cuda.synchronize()
+    M.step(Fdev[0])
+    Fdev = [{k: v for k, v in F.items() if k not in ("LAI", "LAITerm")} for F in Fdev]
+    for w in range(args.spinup):
+        M.step(Fdev[(w + 1) % 2])
     for w in range(W):
         M.step(Fdev[w % 2])
     barrier()
@@ -340,7 +348,7 @@ def run_c3(args):
     chan_gbs = chan_bytes / (ch_ms * 1e-3) / 1e9
     stage = {"soil_ms": round(soil_ms, 3), "overland_ms": round(of_ms, 3), "channel_ms": round(ch_ms, 3)}
     dominant = max(stage, key=stage.get)
-    roof_soil = {"bound": "hbm", "kernel": "soil stage = k_soil_fused<false> + k_soil_veg_deferred<false> x6 + k_soil_pixel_flagged<false> "
+    roof_soil = {"bound": "hbm", "kernel": "soil stage = k_soil_staged (TMA-staged first pass) + k_soil_veg_deferred + k_soil_pixel_flagged "
                  "(per-cell stencil: canopy+soil column+open/sealed+per-pixel sums+groundwater)", "achieved": round(soil_gbs, 1), "peak": peak, "peak_kind": peak_kind,
                  "unit": "GB/s", "frac": round(soil_gbs / peak, 4), "traffic": None, "alg_bytes_per_cell": ALG_BYTES_SOIL,
                  "avg_launch_ms": round(soil_ms, 3)}
@@ -584,6 +592,8 @@ def main():
     ap.add_argument("--rows", type=int, default=10000)
     ap.add_argument("--cols", type=int, default=10000)
     ap.add_argument("--ldd-noise", type=float, default=0.5)
+    ap.add_argument("--spinup", type=int, default=10, help="untimed model steps before the warm-up (C3: relaxes the cold "
+                    "synthetic initial state)")
     ap.add_argument("--cpu-rows", type=int, default=1000, help="edge of the crop the CPU baseline is timed on")
     ap.add_argument("--ldd", default="deep", choices=["deep", "shallow"])
     ap.add_argument("--cpu-timesteps", type=int, default=10)

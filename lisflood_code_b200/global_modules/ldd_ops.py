@@ -33,10 +33,17 @@ def lddrepair_codes(ldd_codes, land_mask):
     return out
 
 
-def lddmask_codes(ldd_codes, keep):
+def lddmask_codes(ldd_codes, keep, land_mask=None):
     """lddmask(ldd, keep): codes where `keep`, 0 (missing value -> isolated pit in kinematicWave,
-    kinematic_wave_parallel.py:68) elsewhere; kept cells draining into a dropped cell become pits."""
-    out = np.where(keep, np.asarray(ldd_codes, np.float64), 0.0)
+    kinematic_wave_parallel.py:68) elsewhere.  With `land_mask`, kept cells that drain into a dropped cell become
+    pits (PCRaster keeps the result a sound ldd)."""
+    codes = np.asarray(ldd_codes, np.float64)
+    keep = np.asarray(keep, bool)
+    out = np.where(keep, codes, 0.0)
+    if land_mask is not None:
+        ds = downstream_index(codes, land_mask)
+        cut = keep & (ds >= 0) & ~keep[np.maximum(ds, 0)]
+        out[cut] = 5.0
     return out
 
 
@@ -75,3 +82,20 @@ def upstream_sum(ds, x):
     has = ds >= 0
     np.add.at(out, ds[has], np.asarray(x, np.float64)[has])
     return out
+
+
+def catchment_of_pits(ds):
+    """catchment(ldd, nominal(uniqueid(pit(ldd)))) on compressed arrays (routing.py:162-164): every pixel gets the id
+    (1, 2, ... in row-major order of the pits) of the pit it drains to."""
+    ds = np.asarray(ds, np.int64)
+    n = ds.size
+    root = np.where(ds >= 0, ds, np.arange(n))
+    while True:  # pointer jumping
+        nxt = root[root]
+        if np.array_equal(nxt, root):
+            break
+        root = nxt
+    ids = np.zeros(n, np.int64)
+    pits = np.flatnonzero(ds < 0)
+    ids[pits] = np.arange(1, pits.size + 1)
+    return ids[root]

@@ -142,8 +142,10 @@ class HotPathModel(object):
     def set_forcing(self, F):
         """Meteorological input of the coming step (what readmeteo/snow/frost/leafarea leave on self.var)."""
         for name, rows in FORCING.items():
-            self.set(name, F[name], rows)
-        self.set_flags("isFrozenSoil", F["isFrozenSoil"])
+            if name in F:          # maps that did not change (the 10-day LAI maps, leafarea.py:76-90) may be left out
+                self.set(name, F[name], rows)
+        if "isFrozenSoil" in F:
+            self.set_flags("isFrozenSoil", F["isFrozenSoil"])
 
     # ---- HydroModule call protocol (hydrological_modules/*.py mirrors) ----------------------------------
     _SOIL_SEQUENCE = ("dynamic_canopy", "dynamic_soil", "opensealed", "dynamic_perpixel", "groundwater")
@@ -194,8 +196,8 @@ class HotPathModel(object):
         ms = np.zeros(8, np.float64)
         _capi.check(_capi.lib().lf_model_soil_stats(self._h, 1 if enable_timing else 0, _capi.ptr(cnt), _capi.ptr(ms)))
         return {"deferred_columns": cnt.tolist(), "deferred_fraction": float(cnt.sum()) / (3.0 * self.N),
-                "kernel_ms": dict(zip(["k_soil_fused"] + ["deferred_%d" % b for b in range(6)] + ["k_soil_pixel_flagged"],
-                                      [round(x, 3) for x in ms.tolist()]))}
+                "kernel_ms": {"first_pass": round(float(ms[0]), 3), "k_soil_veg_deferred": round(float(ms[1:7].sum()), 3),
+                              "k_soil_pixel_flagged": round(float(ms[7]), 3)}}
 
     def info(self):
         v = [C.c_int64() for _ in range(5)]

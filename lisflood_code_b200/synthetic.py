@@ -275,3 +275,52 @@ def forcing(S, step, seed=0):
     F["ESRef"] = (F["EWRef"] + F["ETRef"]) / 2
     F["LAITerm"] = np.exp(-S["kgb"] * F["LAI"])
     return F
+
+
+def raw_inputs(rows, cols, seed=0, ldd_noise=0.5, mask_fraction=0.1, channel_threshold=20, scalar_maps=False):
+    """Raw static inputs by BINDING name (what `loadmap` returns: float or float64[N]) for the soil and routing
+    modules' initial(), plus the attributes earlier modules leave on the model object.  Returns (mask, raw, state).
+    Used by tests/golden/make_golden.py (fed to the reference's own initial()) and by the init tests."""
+    from .global_modules import ldd_ops
+    rng = np.random.default_rng(seed + 977)
+    ldd, mask = random_ldd(rows, cols, seed=seed, noise=ldd_noise, mask_fraction=mask_fraction)
+    n = int(mask.sum())
+    U = lambda lo, hi: rng.uniform(lo, hi, n)
+    codes = ldd_ops.lddrepair_codes(ldd[mask].astype(np.float64), mask)
+    uparea = ldd_ops.accuflux(ldd_ops.downstream_index(codes, mask), np.ones(n))
+    raw = {"Ldd": codes, "Channels": (uparea >= channel_threshold).astype(np.float64), "beta": 0.6,
+           "ChanLength": 5000.0 * U(1.0, 1.4), "ChanGrad": U(0.0, 5e-3), "ChanGradMin": 1e-4, "CalChanMan": U(0.5, 2.0),
+           "ChanMan": U(0.02, 0.06), "ChanBottomWidth": 2.0 + 0.5 * np.sqrt(uparea), "ChanDepthThreshold": 0.5 + 0.05 * np.sqrt(uparea),
+           "ChanSdXdY": 1.0, "TotalCrossSectionAreaInitValue": np.where(rng.random(n) < 0.5, -9999.0, U(0.1, 3.0)),
+           "PrevDischarge": -9999.0, "CrossSection2AreaInitValue": np.where(rng.random(n) < 0.6, -9999.0, U(0.0, 0.5)),
+           "PrevSideflowInitValue": -9999.0, "CalChanMan2": U(1.0, 4.0), "QSplitMult": 2.0,
+           "AvgDis": np.where(uparea >= channel_threshold, 0.002 * uparea + 0.01, 0.0)}
+    for i, (lo, hi) in zip("123", ((40, 60), (200, 300), (500, 900))):
+        raw["SoilDepth" + i] = U(lo, hi)
+        raw["SoilDepth%sForest" % i] = U(lo, hi)
+        for stem, (a, b) in (("MapThetaSat", (.4, .5)), ("MapThetaRes", (.02, .08)), ("MapLambda", (.15, .45)),
+                             ("MapGenuAlpha", (.005, .05))):
+            raw[stem + i] = U(a, b)
+            if i != "3":
+                raw[stem + i + "Forest"] = U(a, b)
+        raw["MapKSat" + i] = np.exp(U(np.log(1.0), np.log(500.0)))
+        if i != "3":
+            raw["MapKSat%sForest" % i] = np.exp(U(np.log(1.0), np.log(500.0)))
+    raw["SoilDepth1"][rng.random(n) < 0.03] = 0.0   # soil-less pixels: PoreSpaceNotZero False
+    raw.update({"CourantCrit": 0.4, "LeafDrainageTimeConstant": 1.0, "AvWaterRateThreshold": 5.0, "MapCropCoef": U(.9, 1.1),
+                "MapForestCropCoef": U(.9, 1.3), "MapIrrigationCropCoef": U(.9, 1.2), "MapCropGroupNumber": U(1, 5),
+                "MapForestCropGroupNumber": U(2, 5), "MapIrrigationCropGroupNumber": U(1, 5), "MapN": U(.05, .2),
+                "MapForestN": U(.1, .4), "b_Xinanjiang": 0.3 if scalar_maps else U(.1, .7),
+                "PowerPrefFlow": 3.5 if scalar_maps else U(1, 5), "CumIntSealedInitValue": 0.0, "SMaxSealed": 1.0,
+                "DrainedFraction": 0.25})
+    for i in "123":
+        raw["ThetaInit%sValue" % i] = -9999.0
+        raw["ThetaForestInit%sValue" % i] = np.where(rng.random(n) < 0.5, -9999.0, U(.1, .4))
+        raw["ThetaIrrigationInit%sValue" % i] = 0.25
+    for stem, (lo, hi) in (("DSLR", (0.0, 6.0)), ("CumInt", (0.0, 0.5))):
+        raw[stem + "InitValue"], raw[stem + "ForestInitValue"], raw[stem + "IrrigationInitValue"] = U(lo, hi), U(lo, hi), U(lo, hi)
+    fr = rng.dirichlet([4.0, 3.0, 1.0, 0.6, 0.3, 0.2], n).T
+    state = {"SoilFraction": np.ascontiguousarray(fr[:3]), "OtherFraction": fr[0].copy(), "ForestFraction": fr[1].copy(),
+             "IrrigationFraction": fr[2].copy(), "DirectRunoffFraction": fr[3].copy(), "WaterFraction": fr[4].copy(),
+             "RiceFraction": fr[5].copy(), "PixelArea": np.full(n, 25.0e6)}
+    return mask, raw, state

@@ -1,0 +1,201 @@
+"""Runs the UNMODIFIED `initial()` / `initialSecond()` methods of the reference's soil and routing modules on
+synthetic inputs, to pin the init-time parameter derivation.
+TEST INFRASTRUCTURE ONLY (build container; needs /root/reference) -- used by tests/golden/make_golden.py.
+
+What is the reference's own arithmetic here: every NumPy expression of soil.initial (hydrological_modules/soil.py:76-470)
+and of routing.initial / initialSecond (routing.py:61-397): van Genuchten storages, channel geometry, kinematic-wave
+alpha, initial volume / discharge, split-routing limits.  What is NOT: PCRaster.  The ldd operators the reference
+calls (lddmask, lddrepair, accuflux, downstream, upstream, pit, catchment ...) are stubbed by the NumPy restatements of
+lisflood_code_b200/global_modules/ldd_ops.py working on compressed 1-D arrays, so the drainage-network outputs
+(LddKinematic, LddToChan, UpArea, Catchments, downstruct) are pinned only to the PCRaster manual's semantics.
+"""
+import sys
+from collections import OrderedDict
+
+import numpy as np
+
+from . import ref_modules
+
+
+class _Pcr(np.ndarray):
+    """A 'PCRaster map' of the harness: compressed 1-D array."""
+
+    def __new__(cls, a):
+        return np.asarray(a).view(cls)
+
+
+def _install(raw, land_mask):
+    """Binds loadmap / compressArray / decompress / the pcraster operators in the loaded reference modules."""
+    from lisflood_code_b200.global_modules import ldd_ops
+    M = ref_modules.load()
+    land = np.asarray(land_mask, bool)
+    n = int(land.sum())
+
+    def loadmap(name, pcr=False, lddflag=False, **kw):
+        v = raw[name]
+        if np.ndim(v) == 0:
+            return float(v)
+        return _Pcr(np.array(v, np.float64)) if pcr else np.array(v, np.float64)
+
+    def compress(m, *a, **k):
+        return np.asarray(m).copy()
+
+    def decompress(a, *aa, **k):
+        return _Pcr(np.asarray(a))
+
+    def lddmask(ldd, keep):
+        return _Pcr(ldd_ops.lddmask_codes(np.asarray(ldd, np.float64), np.asarray(keep) != 0, land))
+
+    def lddrepair(ldd):
+        return _Pcr(ldd_ops.lddrepair_codes(np.asarray(ldd, np.float64), land))
+
+    def ds_of(ldd):
+        return ldd_ops.downstream_index(np.asarray(ldd, np.float64), land)
+
+    def accuflux(ldd, x):
+        return _Pcr(ldd_ops.accuflux(ds_of(ldd), np.broadcast_to(np.asarray(x, np.float64), (n,))))
+
+    def boolean(x):
+        return _Pcr(np.asarray(x) != 0)
+
+    def pit(ldd):
+        d = ds_of(ldd)
+        out = np.zeros(n, np.int64)
+        p = np.flatnonzero(d < 0)
+        out[p] = np.arange(1, p.size + 1)
+        return _Pcr(out)
+
+    def ifthenelse(c, a, b):
+        return _Pcr(np.where(np.asarray(c) != 0, a, b))
+
+    def downstream(ldd, x):
+        d = ds_of(ldd)
+        x = np.asarray(x)
+        return _Pcr(np.where(d >= 0, x[np.maximum(d, 0)], x))
+
+    def upstream(ldd, x):
+        return _Pcr(ldd_ops.upstream_sum(ds_of(ldd), np.asarray(x, np.float64)))
+
+    def uniqueid(b):
+        b = np.asarray(b) != 0
+        out = np.zeros(n, np.int64)
+        out[b] = np.arange(1, int(b.sum()) + 1)
+        return _Pcr(out)
+
+    def nominal(x):
+        return _Pcr(np.asarray(x).astype(np.int64))
+
+    def catchment(ldd, points):
+        d = ds_of(ldd)
+        root = np.where(d >= 0, d, np.arange(n))
+        while True:
+            nxt = root[root]
+            if np.array_equal(nxt, root):
+                break
+            root = nxt
+        return _Pcr(np.asarray(points)[root])
+
+    soil_mod = sys.modules["lisflood.hydrological_modules.soil"]
+    rout_mod = sys.modules["lisflood.hydrological_modules.routing"]
+    soil_mod.loadmap = loadmap
+    for k, f in dict(loadmap=loadmap, loadmap_base=loadmap, compressArray=compress, decompress=decompress, lddmask=lddmask,
+                     lddrepair=lddrepair, accuflux=accuflux, boolean=boolean, pit=pit, ifthenelse=ifthenelse,
+                     downstream=downstream, upstream=upstream, uniqueid=uniqueid, nominal=nominal,
+                     catchment=catchment).items():
+        setattr(rout_mod, k, f)
+    if not hasattr(np, "bool8"):
+        np.bool8 = np.bool_   # the reference predates NumPy 2
+    return M, loadmap
+
+
+class _InitVar(object):
+    """Model object of the reference during initial(): helper API restated from Lisflood_initial.py:266-396."""
+
+    def __init__(self, land_mask, raw, loadmap, options, DtSec, DtSecChannel):
+        from lisflood_code_b200.global_modules.add1 import NumpyModified
+        self._NM = NumpyModified
+        self._loadmap, self._raw = loadmap, raw
+        sett = ref_modules._FakeSettings.instance()
+        sett.options.clear()
+        sett.options.update(options)
+        self.settings = sett
+        self.maskinfo = ref_modules._FakeMaskInfo.set(land_mask)
+        n = int(np.asarray(land_mask).sum())
+        self.SOIL_USES = ["Rainfed", "Forest", "Irrigated"]
+        self.PRESCRIBED_VEGETATION = [u + "_prescribed" for u in self.SOIL_USES]
+        self.prescribed_vegetation = list(self.PRESCRIBED_VEGETATION)
+        self.vegetation = list(self.PRESCRIBED_VEGETATION)
+        self.VEGETATION_LANDUSE = OrderedDict(zip(self.PRESCRIBED_VEGETATION, self.SOIL_USES))
+        self.dim_pixel = ("pixel", np.arange(n))
+        self.dim_landuse = ("landuse", self.SOIL_USES[:])
+        self.dim_runoff = ("runoff", ["Other", "Forest", "Direct"])
+        self.coord_landuse = OrderedDict([self.dim_landuse, self.dim_pixel])
+        self.DtSec, self.DtSecChannel = float(DtSec), float(DtSecChannel)
+        self.DtDay = self.DtSec / 86400.0
+
+    def allocateDataArray(self, dimensions, dtype=float):
+        coords = OrderedDict(dimensions)
+        return self._NM(np.zeros([len(v) for v in coords.values()], dtype), coords.keys())
+
+    def allocateVariableAllVegetation(self, dtype=float):
+        return self.allocateDataArray([("vegetation", self.vegetation[:]), self.dim_pixel], dtype)
+
+    def defsoil(self, name_1, name_2=None, name_3=None, coords=None):   # Lisflood_initial.py:371-391 (non-EPIC branch)
+        if coords is None:
+            coords = self.coord_landuse
+        data = self.allocateDataArray(coords)
+
+        def read(name, backup=None):   # readInputWithBackup
+            if name is None:
+                return backup
+            if isinstance(name, str):
+                return self._loadmap(name) if name in self._raw else backup
+            return float(name)
+        v1 = read(name_1)
+        data.values[0][:] = v1
+        data.values[1][:] = read(name_2, v1)
+        data.values[2][:] = read(name_3, v1)
+        return data
+
+
+def _collect(var):
+    out = {}
+    for k, v in var.__dict__.items():
+        if k.startswith("_") or k in ("settings", "maskinfo"):
+            continue
+        if isinstance(v, (float, int, np.floating, np.integer)) and not isinstance(v, bool):
+            out[k] = np.float64(v)
+        elif isinstance(v, np.ndarray) and v.dtype.kind in "fiub":
+            out[k] = np.asarray(v)
+    return out
+
+
+def soil_initial(land_mask, raw, state, options=None, DtSec=86400.0):
+    """Outputs of the reference's soil.initial() as {attribute: array}.  `state`: attributes other modules set before
+    (SoilFraction (3,N), RiceFraction, WaterFraction, OtherFraction, IrrigationFraction, ForestFraction,
+    DirectRunoffFraction)."""
+    M, loadmap = _install(raw, land_mask)
+    var = _InitVar(land_mask, raw, loadmap, dict(options or {}), DtSec, 3600.0)
+    for k, v in state.items():
+        setattr(var, k, var._NM(np.array(v, np.float64), ["vegetation", "pixel"]) if np.ndim(v) == 2 else np.array(v, np.float64))
+    before = set(var.__dict__)
+    M["soil"](var).initial()
+    return {k: v for k, v in _collect(var).items() if k not in before or k == "SoilFraction"}
+
+
+def routing_initial(land_mask, raw, state, options=None, DtSec=86400.0, DtSecChannel=3600.0):
+    """Outputs of the reference's routing.initial() + initialSecond() (the kinematicWave object it builds is dropped)."""
+    M, loadmap = _install(raw, land_mask)
+    opts = dict(options or {})
+    var = _InitVar(land_mask, raw, loadmap, opts, DtSec, DtSecChannel)
+    n = int(np.asarray(land_mask).sum())
+    var.MaskMap = _Pcr(np.ones(n, bool))
+    for k, v in state.items():
+        setattr(var, k, np.array(v, np.float64))
+    var.PixelAreaPcr = _Pcr(var.PixelArea)
+    before = set(var.__dict__)
+    r = M["routing"](var)
+    r.initial()
+    r.initialSecond()
+    out = {k: v for k, v in _collect(var).items() if k not in before}
+    return out

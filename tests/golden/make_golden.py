@@ -94,9 +94,31 @@ def model_case(name, rows, cols, seed, split, steps, **kw):
     print(name, "n=%d steps=%d split=%s channel fraction %.3f" % (S["N"], steps, split, S["IsChannel"].mean()))
 
 
+def init_case(name, rows, cols, seed, split, scalar_maps=False, dt_sec=86400.0):
+    """soil.initial() and routing.initial()/initialSecond() executed by the reference's OWN classes (oracle/ref_init.py)
+    on raw inputs by binding name; stores inputs and every attribute they set."""
+    from oracle import ref_init
+    mask, raw, state = synthetic.raw_inputs(rows, cols, seed=seed, scalar_maps=scalar_maps)
+    opts = {"SplitRouting": split, "drainedIrrigation": split}
+    out = {"mask": mask, "DtSec": np.float64(dt_sec), "SplitRouting": np.bool_(split)}
+    out.update({"raw__" + k: np.asarray(v) for k, v in raw.items()})
+    out.update({"state__" + k: np.asarray(v) for k, v in state.items()})
+    soil_state = {k: v for k, v in state.items() if k != "PixelArea"}
+    out.update({"soil__" + k: v for k, v in ref_init.soil_initial(mask, raw, soil_state, opts, DtSec=dt_sec).items()})
+    out.update({"routing__" + k: v for k, v in ref_init.routing_initial(mask, raw, {"PixelArea": state["PixelArea"]}, opts,
+                                                                        DtSec=dt_sec).items()})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "n=%d soil maps=%d routing maps=%d" % (int(mask.sum()), sum(k.startswith("soil__") for k in out),
+                                                      sum(k.startswith("routing__") for k in out)))
+
+
 def main():
     import warnings
     warnings.simplefilter("ignore")
+    if len(sys.argv) > 1 and sys.argv[1] == "init":
+        init_case("init_24x31_split", 24, 31, 61, True)
+        init_case("init_19x23_single_6h", 19, 23, 62, False, scalar_maps=True, dt_sec=21600.0)
+        return
     model_case("model_26x34_single", 26, 34, 41, False, 3, mask_fraction=0.08, channel_threshold=12)
     model_case("model_30x28_split", 30, 28, 42, True, 3, mask_fraction=0.05, channel_threshold=10)
     model_case("model_20x22_6h", 20, 22, 43, False, 2, channel_threshold=8, dt_sec=21600.0)

@@ -1,0 +1,78 @@
+"""Init-time parameter derivation against golden vectors made by the reference's OWN
+soil.initial() / routing.initial() / routing.initialSecond() (tests/golden/make_golden.py init, oracle/ref_init.py).
+
+The derivations are NumPy expressions in the same order as the reference, so the comparison is bit-exact for every
+map both sides define (tolerance written here: 0).  The drainage-network maps come from the PCRaster operators, which
+the golden run stubs with the same ldd_ops restatement (see oracle/ref_init.py): they check consistency, not PCRaster."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden
+
+NETWORK = {"Ldd", "LddToChan", "LddKinematic", "UpArea", "InvUpArea", "Catchments", "InvCatchArea", "downstruct",
+           "AtLastPointC", "IsChannel", "IsChannelKinematic", "IsStructureKinematic"}
+# attributes the reference's initial() sets that are outside the hot path (reporting / other modules) and not mirrored
+NOT_MIRRORED = {"AtLastPoint", "MaskMap", "IsChannelPcr", "avgdis", "Theta1a", "Theta1b", "Theta2", "TaInterception",
+                "Interception", "LeafDrainage", "potential_transpiration", "Ta", "ESAct", "PrefFlow", "Infiltration",
+                "SeepTopToSubA", "SeepTopToSubB", "SeepSubToGW", "Theta", "AvailableWaterForInfiltration", "RWS",
+                "SoilMoistureStressDays"}
+
+
+def _build(case):
+    from lisflood_code_b200.Lisflood_initial import InitialVariables
+    from lisflood_code_b200.global_modules.add1 import NumpyModified
+    from lisflood_code_b200.hydrological_modules.routing import routing
+    from lisflood_code_b200.hydrological_modules.soil import soil
+    g = load_golden(case)
+    raw = {k[5:]: (float(v) if v.ndim == 0 else v) for k, v in g.items() if k.startswith("raw__")}
+    split = bool(g["SplitRouting"])
+    var = InitialVariables(g["mask"], raw, {"SplitRouting": split, "drainedIrrigation": split}, DtSec=float(g["DtSec"]))
+    for k, v in g.items():
+        if k.startswith("state__"):
+            setattr(var, k[7:], NumpyModified(v.copy(), ["vegetation", "pixel"]) if v.ndim == 2 else v.copy())
+    soil(var).initial()
+    r = routing(var)
+    r.initial()
+    r.initialSecond()
+    return g, var
+
+
+@pytest.mark.parametrize("case", golden_cases("init_"))
+def test_initial_matches_reference(case):
+    g, var = _build(case)
+    checked, missing = 0, []
+    for key, want in g.items():
+        if not (key.startswith("soil__") or key.startswith("routing__")):
+            continue
+        name = key.split("__", 1)[1]
+        if name in NOT_MIRRORED:
+            continue
+        if not hasattr(var, name) or getattr(var, name) is None:
+            missing.append(name)
+            continue
+        got = np.asarray(getattr(var, name))
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        if name == "downstruct":   # off-channel pixels are missing values in the reference's LddKinematic: undefined there
+            on = np.asarray(var.LddKinematic) != 0
+            got, want = got[on], want[on]
+        if want.dtype.kind == "f":
+            assert np.array_equal(got.astype(np.float64), want, equal_nan=True), (name, float(np.nanmax(np.abs(got - want))))
+        else:
+            assert np.array_equal(got, want), name
+        checked += 1
+    assert not missing, missing
+    assert checked >= 80
+
+
+@pytest.mark.parametrize("case", golden_cases("init_"))
+def test_state_feeds_the_device_model_layout(case):
+    """InitialVariables.state() carries every parameter / state map HotPathModel uploads for the soil stage."""
+    from lisflood_code_b200 import hotpath
+    g, var = _build(case)
+    S = var.state()
+    need = [k for k in list(hotpath.PARAMETERS) + list(hotpath.STATE)
+            if k.startswith(("W", "KSat", "Genu", "CropCoef", "CropGroup", "b_X", "PowerPref", "DSLR", "CumInter"))]
+    assert need and not [k for k in need if k not in S], [k for k in need if k not in S]
+    n = int(g["mask"].sum())
+    for k in need:
+        assert np.ndim(S[k]) == 0 or np.asarray(S[k]).shape[-1] == n, k
