@@ -348,9 +348,17 @@ def run_c3(args):
     chan_gbs = chan_bytes / (ch_ms * 1e-3) / 1e9
     stage = {"soil_ms": round(soil_ms, 3), "overland_ms": round(of_ms, 3), "channel_ms": round(ch_ms, 3)}
     dominant = max(stage, key=stage.get)
+    traffic = None   # measured DRAM bytes of the soil stage per step from the committed ncu capture (same raster size only)
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_soil_stage_c3_traffic.json")) as f:
+            tj = json.load(f)
+        if int(tj["cells"]) == int(n):
+            traffic = int(tj["soil_stage_bytes"])
+    except (OSError, ValueError, KeyError):
+        pass
     roof_soil = {"bound": "hbm", "kernel": "soil stage = k_soil_staged (TMA-staged first pass) + k_soil_veg_deferred + k_soil_pixel_flagged "
                  "(per-cell stencil: canopy+soil column+open/sealed+per-pixel sums+groundwater)", "achieved": round(soil_gbs, 1), "peak": peak, "peak_kind": peak_kind,
-                 "unit": "GB/s", "frac": round(soil_gbs / peak, 4), "traffic": None, "alg_bytes_per_cell": ALG_BYTES_SOIL,
+                 "unit": "GB/s", "frac": round(soil_gbs / peak, 4), "traffic": traffic, "alg_bytes_per_cell": ALG_BYTES_SOIL,
                  "avg_launch_ms": round(soil_ms, 3)}
     roof_chan = {"bound": "hbm", "kernel": "k_chan_diagonal + k_chan_isolated (24 fused channel sub-steps)",
                  "achieved": round(chan_gbs, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
@@ -372,8 +380,9 @@ def run_c3(args):
                            "levels_channel": info["levels_channel"], "channel_fraction": round(dev.channel_fraction, 4),
                            "isolated_channel_pixels": info["isolated_channel_pixels"],
                            "device_bytes_maps": info["device_bytes"],
-                           "l2_policy": "every map is %.0f MB (> 126 MB L2 for rasters above ~4000^2); two forcing sets "
-                                        "alternate between steps" % (n * 8 / 1e6)},
+                           "l2_policy": "every map is %.0f MB (> 126 MB L2 for rasters above ~4000^2); two meteo forcing sets "
+                                        "alternate between steps, the 10-day LAI maps stay resident" % (n * 8 / 1e6),
+                           "spinup_steps": args.spinup},
                 "e2e": {"value": e2e_value, "unit": "cell-updates/s", "steps": Ke, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h),
                         "note": "per step: Rain, SnowMelt, ETRef, EWRef, ESRef (f64) + isFrozenSoil (u8) from pinned host "

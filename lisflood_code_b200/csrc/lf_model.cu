@@ -330,13 +330,27 @@ __global__ void k_of_post(int n, const double *__restrict__ QO, const double *__
 }
 
 // ---- layout translation ----
-__global__ void k_rows_to_pos(const double *__restrict__ src, double *__restrict__ dst, const int32_t *__restrict__ pix_of_pos,
-                              int64_t n, int rows)
+// reference (compressed row-major) order -> position order: a gather.  Four positions per thread: the four index loads
+// and then the four gathered values are in flight together (the kernel is bound by the latency of the scattered reads).
+constexpr int PERM_U = 4;
+__global__ void __launch_bounds__(256) k_rows_to_pos(const double *__restrict__ src, double *__restrict__ dst,
+                                                     const int32_t *__restrict__ pix_of_pos, int64_t n, int rows)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int p = pix_of_pos[i];
-    for (int r = 0; r < rows; ++r) dst[(int64_t)r * n + i] = src[(int64_t)r * n + p];
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PERM_U;
+    if (i0 >= n) return;
+    int p[PERM_U];
+#pragma unroll
+    for (int u = 0; u < PERM_U; ++u) p[u] = i0 + u < n ? pix_of_pos[i0 + u] : 0;
+    for (int r = 0; r < rows; ++r) {
+        const double *s = src + (int64_t)r * n;
+        double *d = dst + (int64_t)r * n;
+        double x[PERM_U];
+#pragma unroll
+        for (int u = 0; u < PERM_U; ++u) x[u] = s[p[u]];
+#pragma unroll
+        for (int u = 0; u < PERM_U; ++u)
+            if (i0 + u < n) d[i0 + u] = x[u];
+    }
 }
 __global__ void k_rows_to_pix(const double *__restrict__ src, double *__restrict__ dst, const int32_t *__restrict__ pos_of_pix,
                               int64_t n, int rows)
@@ -349,8 +363,14 @@ __global__ void k_rows_to_pix(const double *__restrict__ src, double *__restrict
 __global__ void k_u8_to_pos(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const int32_t *__restrict__ pix_of_pos,
                             int64_t n)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[pix_of_pos[i]];
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PERM_U;
+    if (i0 >= n) return;
+    uint8_t x[PERM_U];
+#pragma unroll
+    for (int u = 0; u < PERM_U; ++u) x[u] = src[i0 + u < n ? pix_of_pos[i0 + u] : 0];
+#pragma unroll
+    for (int u = 0; u < PERM_U; ++u)
+        if (i0 + u < n) dst[i0 + u] = x[u];
 }
 __global__ void k_rows_differ(const double *__restrict__ a, const double *__restrict__ b, int64_t n, int *__restrict__ flag)
 {
@@ -635,7 +655,7 @@ int soil_stage(lf_model *m)
     // contributions handed from the column kernel to the pixel kernel, and the deferred-column lists
     {
         {
-            P.cstride = m->cfg.diagnostics ? 8 : 6;  // CS_PREF / CS_INF (PrefFlowPixel / InfiltrationPixel): diagnostics only
+            P.cstride = m->cfg.diagnostics ? 8 : 3;  // lean: CS_UZOUT, CS_GWPERC, CS_SURF (the rest is summed in the first pass)
             auto it = m->fields.find("__cbuf");
             if (it == m->fields.end()) {
                 std::unique_ptr<Field> f(new Field());
@@ -708,15 +728,15 @@ int soil_stage(lf_model *m)
         }
         D.NoSubS = (int32_t *)ns->buf.p;
     }
-    // First pass of the lean build: k_soil_staged (inputs staged in shared memory by bulk async copies) unless
-    // LF_SOIL_VARIANT selects one of the direct-load launch shapes of k_soil_fused (tuning / fallback comparison):
-    //   0..5  k_soil_fused with 64 px x 5 / 64 x 4 / 128 x 2 / 64 x 3 / 64 x 6 / 64 x 7 resident blocks
-    //   10    k_soil_staged 32 px x 9 blocks    11  64 px x 4    12  32 px x 8    13  64 px x 5 (if it fits)
-    // Measured on C3 (profiles/): k_soil_fused is bound by global-load latency (61 % long-scoreboard stalls).
+    // First pass of the lean build: k_soil_staged (inputs staged in shared memory by bulk async copies); the diagnostics
+    // build uses k_soil_fused (direct loads: it writes 50 more maps and is not a performance configuration).
+    // LF_SOIL_VARIANT selects the launch shape (tuning): 13 = 64 px x 5 blocks/SM (default), 11 = 64 x 4, 10 = 32 x 9,
+    // 12 = 32 x 8.  Measured on C3 (profiles/): direct loads spend 61 % of the warp-stall samples on global-load latency
+    // (first pass 29.4 ms at best); staged: 18 ms.
     int variant = 13;
     if (const char *e = getenv("LF_SOIL_VARIANT")) {  // read per call: tools/soil_variants.py switches it between runs
         const int v = atoi(e);
-        if ((v >= 0 && v <= 5) || (v >= 10 && v <= 13)) variant = v;
+        if (v >= 10 && v <= 13) variant = v;
     }
     const int force_plain = getenv("LF_SOIL_PLAIN") ? atoi(getenv("LF_SOIL_PLAIN")) : 0;
     const int def_mb = getenv("LF_SOIL_DEF_MB") ? atoi(getenv("LF_SOIL_DEF_MB")) : 6;  // resident blocks of the deferred kernel
@@ -753,7 +773,7 @@ int soil_stage(lf_model *m)
     } while (0)
     if (m->cfg.diagnostics) {
         LF_SOIL_LAUNCH(true, 64, 3, 4);
-    } else if (variant >= 10) {
+    } else {
         // copy plan: per-pixel rows, (V,N) rows per fraction, land-use groups stored once per distinct pointer set
         Stage G;
         memset(&G, 0, sizeof(G));
@@ -798,14 +818,6 @@ int soil_stage(lf_model *m)
         else if (variant == 12) LF_SOIL_STAGED(32, 8);
         else if (variant == 10) LF_SOIL_STAGED(32, 9);
         else LF_SOIL_STAGED(64, 5);  // 34 land-use rows (C3) leave room for five 64-pixel tiles per SM
-    } else {
-        // diagnostics-only parameter rows are never dereferenced in these instantiations
-        if (variant == 0) LF_SOIL_LAUNCH(false, 64, 5, 8);
-        else if (variant == 4) LF_SOIL_LAUNCH(false, 64, 6, 8);
-        else if (variant == 5) LF_SOIL_LAUNCH(false, 64, 7, 8);
-        else if (variant == 2) LF_SOIL_LAUNCH(false, 128, 2, 8);
-        else if (variant == 3) LF_SOIL_LAUNCH(false, 64, 3, 8);
-        else LF_SOIL_LAUNCH(false, 64, 4, 8);
     }
 #undef LF_SOIL_STAGED
 #undef LF_SOIL_LAUNCH
@@ -1149,8 +1161,14 @@ int lf_model_set(lf_model *m, const char *name, const double *values, int64_t co
     }
     cudaStream_t st = lf::stream();
     const int32_t *pop = f->order == SOIL ? m->g_of->pix_of_pos.p : m->g_ch->pix_of_pos.p;
-    LF_CUDA(cudaMemcpyAsync(m->stage.p, values, count * sizeof(double), cudaMemcpyDefault, st));
-    k_rows_to_pos<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(m->stage.p, f->buf.p, pop, m->n, f->rows);
+    // host data goes through the staging buffer; device data is gathered straight from the caller's buffer
+    const bool values_on_device = lf::is_device_ptr(values);
+    const double *from = values;
+    if (!values_on_device || f->landuse) {
+        LF_CUDA(cudaMemcpyAsync(m->stage.p, values, count * sizeof(double), cudaMemcpyDefault, st));
+        from = m->stage.p;
+    }
+    k_rows_to_pos<<<lf::blocks_for((m->n + PERM_U - 1) / PERM_U, 256), 256, 0, st>>>(from, f->buf.p, pop, m->n, f->rows);
     LF_LAUNCH_CHECK();
     if (f->as_z) {
         k_q_to_z<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(f->buf.p, m->n);
@@ -1230,7 +1248,7 @@ int lf_model_set_async(lf_model *m, const char *name, const double *values, int6
     LF_CUDA(cudaEventRecord(m->async_copied[name], m->copy_stream));
     LF_CUDA(cudaStreamWaitEvent(st, m->async_copied[name], 0));
     const int32_t *pop = f->order == SOIL ? m->g_of->pix_of_pos.p : m->g_ch->pix_of_pos.p;
-    k_rows_to_pos<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(stg, f->buf.p, pop, m->n, f->rows);
+    k_rows_to_pos<<<lf::blocks_for((m->n + PERM_U - 1) / PERM_U, 256), 256, 0, st>>>(stg, f->buf.p, pop, m->n, f->rows);
     LF_LAUNCH_CHECK();
     if (f->as_z) {
         k_q_to_z<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(f->buf.p, m->n);
@@ -1292,7 +1310,7 @@ int lf_model_set_flags(lf_model *m, const char *name, const uint8_t *values, int
     LF_CHECK(flag_buf(m, name, &dst));
     const int32_t *pop = order == SOIL ? m->g_of->pix_of_pos.p : m->g_ch->pix_of_pos.p;
     LF_CUDA(cudaMemcpyAsync(m->stage_u8.p, values, count, cudaMemcpyDefault, st));
-    k_u8_to_pos<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(m->stage_u8.p, dst, pop, m->n);
+    k_u8_to_pos<<<lf::blocks_for((m->n + PERM_U - 1) / PERM_U, 256), 256, 0, st>>>(m->stage_u8.p, dst, pop, m->n);
     LF_LAUNCH_CHECK();
     LF_CUDA(cudaStreamSynchronize(st));
     return LF_OK;

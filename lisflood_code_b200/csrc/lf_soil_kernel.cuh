@@ -62,7 +62,7 @@ struct Ptrs {
     double *DirectRunoff, *SurfOther, *SurfForest, *GwToChan;
     // fraction-weighted per-column contributions of the pixels that have a deferred column; written sparsely.  One record
     // of `cstride` doubles per column, the three columns of a pixel adjacent (record (i*3 + v)): a flagged pixel is summed
-    // from 144 contiguous bytes instead of 18 sectors.  Slots: enum CSlot (6 without diagnostics, 8 with).
+    // from 72 contiguous bytes instead of 9 sectors.  Slots: enum CSlot (3 without diagnostics, 8 with).
     double *cbuf;
     int32_t cstride;
     uint8_t *pix_deferred;  // (N): PIX_FLAGGED | overflow bits (see soil_column); 0 = pixel finished by the first pass
@@ -86,7 +86,7 @@ struct Diag {
     int32_t *NoSubS;  // (V,N)
 };
 
-enum CSlot { CS_TAINT, CS_TA, CS_ES, CS_UZOUT, CS_GWPERC, CS_SURF, CS_PREF, CS_INF };
+enum CSlot { CS_UZOUT, CS_GWPERC, CS_SURF, CS_TAINT, CS_TA, CS_ES, CS_PREF, CS_INF };  // the first 3 without diagnostics
 __device__ __forceinline__ double *crec(const Ptrs &P, int v, int64_t i) { return P.cbuf + (i * 3 + v) * P.cstride; }
 
 using lfm::dmax;
@@ -295,8 +295,8 @@ __device__ __forceinline__ int substeps_of(const Ptrs &P, double k1a, double k1b
 //   one sub-step needed (~99 %): seepage, upper zone and state follow at once; contributions in C (COL_DONE);
 //   several sub-steps needed  : the column is appended to the bucket list of its sub-step count and its mid-column
 //     record is left in storage the column owns -- W1a/W1b/W2[k] = moisture after infiltration; in its contribution
-//     record CS_SURF = available water, CS_UZOUT = infiltration, CS_GWPERC = preferential flow, CS_TAINT/TA/ES(/PREF) =
-//     final contributions --
+//     record CS_SURF = available water, CS_UZOUT = infiltration, CS_GWPERC = preferential flow (with diagnostics also
+//     the final CS_TAINT/TA/ES/PREF) --
 //     for soil_column_resume (COL_QUEUED; *flags gets PIX_FLAGGED, plus the overflow bit if the list was full).
 template <bool DIAG, class IN>
 __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D, const MathTab *MT, int v, int i, const IN &in,
@@ -462,10 +462,12 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
             rec[CS_SURF] = avail;
             rec[CS_UZOUT] = infil;
             rec[CS_GWPERC] = prefflow;
-            rec[CS_TAINT] = C.taint;
-            rec[CS_TA] = C.ta;
-            rec[CS_ES] = C.es;
-            if (DIAG) rec[CS_PREF] = C.pref;
+            if (DIAG) {  // (without diagnostics the first pass itself sums taint / ta / es of every pixel)
+                rec[CS_TAINT] = C.taint;
+                rec[CS_TA] = C.ta;
+                rec[CS_ES] = C.es;
+                rec[CS_PREF] = C.pref;
+            }
             return COL_QUEUED;
         }
     }
@@ -540,47 +542,59 @@ __device__ __noinline__ void soil_column_overflow(const Ptrs &P, const Diag &D, 
 
 // per pixel: open water / sealed soil, totals over the fractions, groundwater, runoff components.
 // s*: sums over the three fractions in the reference's order, (c0 + c1) + c2.
-template <bool DIAG, class IN>
+// PART: PIX_EARLY = what is final after the first pass for EVERY pixel (open water / sealed soil, evaporation totals,
+// DirectRunoff: they need taint / ta / es only); PIX_LATE = what needs the seepage of all three columns (groundwater,
+// SurfOther / SurfForest / GwToChan).  A pixel with a queued column gets PIX_EARLY from the first pass, where its inputs
+// sit in shared memory, and only PIX_LATE (15 gathered values instead of 39) from k_soil_pixel_flagged.
+enum PixelPart { PIX_ALL, PIX_EARLY, PIX_LATE };
+template <bool DIAG, int PART = PIX_ALL, class IN>
 __device__ __forceinline__ void soil_pixel(const Ptrs &P, const Diag &D, int64_t i, const IN &in, double sTaInt, double sTa,
                                            double sES, double sUZout, double sGwPerc, double surfOther, double surfForest,
                                            double sPref, double sInf)
 {
+    static_assert(!DIAG || PART == PIX_ALL, "diagnostics need the whole per-pixel part in one call");
     const int64_t N = P.n;
-    const double ewref = in.EWRef();
-    const double rain_snow = in.Rain() + in.SnowMelt();
-    // ---------------- open water and sealed soil (opensealed.py:41-71) ----------------
-    const double rsm = dmax(rain_snow, 0.);
-    const double ewater = dmax(dmin(ewref, rsm) * 1.0, 0.);
-    double cums = in.CumInterSealed();
-    const double intersealed = dmin(dmax(P.SMaxSealed - cums, 0.), rsm);
-    cums += intersealed;
-    const double tasealed = dmax(dmin(cums, ewref), 0.);
-    cums = dmax(cums - tasealed, 0.);
-    P.CumInterSealed[i] = cums;
-    const double drf = in.DRF(), wf = in.WF();
-    const double direct = drf * (rsm - intersealed) + wf * (rsm - ewater);
-    // ---------------- per-pixel totals (soil.py:475-486) ----------------
-    const double taintall = sTaInt + drf * tasealed;
-    const double esactpix = sES + wf * ewater;
-    P.TaInterceptionCUM[i] = in.TaIntCUM() + taintall;
-    P.TaCUM[i] = in.TaCUM() + sTa;
-    P.ESActCUM[i] = in.ESActCUM() + esactpix;
-    // ---------------- groundwater (groundwater.py:134-180) ----------------
-    double lz = in.LZ();
-    const double lzout = dmax(dmin(in.LZK() * lz, lz - in.LZThreshold()), 0.);
-    lz -= lzout;
-    lz += sGwPerc;
-    const double gwloss = dmax(dmin(in.GwLossStep(), lz), 0.0);
-    lz = lz - gwloss;
-    P.LZ[i] = lz;
-    const double lzcum = dmax(in.LZInflowCUM() + (sGwPerc - gwloss), 0.0);
-    P.LZInflowCUM[i] = lzcum;
-    P.GwLossCUM[i] = in.GwLossCUM() + gwloss;
-    // ---------------- runoff components handed to the routers ----------------
-    P.DirectRunoff[i] = direct;
-    P.SurfOther[i] = surfOther;
-    P.SurfForest[i] = surfForest;
-    P.GwToChan[i] = sUZout + lzout;  // UZOutflowPixel + LZOutflowToChannelPixel (surface_routing.py:211)
+    double rsm = 0., ewater = 0., intersealed = 0., tasealed = 0., taintall = 0., esactpix = 0., direct = 0.;
+    if (PART != PIX_LATE) {
+        const double ewref = in.EWRef();
+        const double rain_snow = in.Rain() + in.SnowMelt();
+        // ---------------- open water and sealed soil (opensealed.py:41-71) ----------------
+        rsm = dmax(rain_snow, 0.);
+        ewater = dmax(dmin(ewref, rsm) * 1.0, 0.);
+        double cums = in.CumInterSealed();
+        intersealed = dmin(dmax(P.SMaxSealed - cums, 0.), rsm);
+        cums += intersealed;
+        tasealed = dmax(dmin(cums, ewref), 0.);
+        cums = dmax(cums - tasealed, 0.);
+        P.CumInterSealed[i] = cums;
+        const double drf = in.DRF(), wf = in.WF();
+        direct = drf * (rsm - intersealed) + wf * (rsm - ewater);
+        // ---------------- per-pixel totals (soil.py:475-486) ----------------
+        taintall = sTaInt + drf * tasealed;
+        esactpix = sES + wf * ewater;
+        P.TaInterceptionCUM[i] = in.TaIntCUM() + taintall;
+        P.TaCUM[i] = in.TaCUM() + sTa;
+        P.ESActCUM[i] = in.ESActCUM() + esactpix;
+        P.DirectRunoff[i] = direct;
+    }
+    double lzout = 0., gwloss = 0., lzcum = 0.;
+    if (PART != PIX_EARLY) {
+        // ---------------- groundwater (groundwater.py:134-180) ----------------
+        double lz = in.LZ();
+        lzout = dmax(dmin(in.LZK() * lz, lz - in.LZThreshold()), 0.);
+        lz -= lzout;
+        lz += sGwPerc;
+        gwloss = dmax(dmin(in.GwLossStep(), lz), 0.0);
+        lz = lz - gwloss;
+        P.LZ[i] = lz;
+        lzcum = dmax(in.LZInflowCUM() + (sGwPerc - gwloss), 0.0);
+        P.LZInflowCUM[i] = lzcum;
+        P.GwLossCUM[i] = in.GwLossCUM() + gwloss;
+        // ---------------- runoff components handed to the routers ----------------
+        P.SurfOther[i] = surfOther;
+        P.SurfForest[i] = surfForest;
+        P.GwToChan[i] = sUZout + lzout;  // UZOutflowPixel + LZOutflowToChannelPixel (surface_routing.py:211)
+    }
     if (DIAG) {
         const double f0 = P.SoilFraction[i], f1 = P.SoilFraction[N + i], f2 = P.SoilFraction[2 * N + i];
 #define LF_SUM3(arr) ((arr[i] + arr[N + i]) + arr[2 * N + i])
@@ -620,6 +634,7 @@ __device__ __forceinline__ void soil_pixel(const Ptrs &P, const Diag &D, int64_t
 template <bool DIAG, int TILE, int MINB>
 __global__ void __launch_bounds__(3 * TILE, MINB) k_soil_fused(const __grid_constant__ Ptrs P, const __grid_constant__ Diag D)
 {
+    static_assert(DIAG, "the lean build runs k_soil_staged (its first pass also does the early per-pixel part)");
     constexpr int NC = DIAG ? 8 : 6;
     __shared__ MathTab s_tab;
     __shared__ double s_c[NC][3][TILE];
@@ -727,9 +742,13 @@ __global__ void __launch_bounds__(256, 4) k_soil_pixel_flagged(const __grid_cons
     }
     const double *r0 = crec(P, 0, i), *r1 = r0 + P.cstride, *r2 = r1 + P.cstride;
 #define LF_SUM3(c) ((r0[c] + r1[c]) + r2[c])
-    soil_pixel<DIAG>(P, D, i, InGlobal(P, 0, (int)i), LF_SUM3(CS_TAINT), LF_SUM3(CS_TA), LF_SUM3(CS_ES), LF_SUM3(CS_UZOUT),
-                     LF_SUM3(CS_GWPERC), r0[CS_SURF] + r2[CS_SURF], r1[CS_SURF], DIAG ? LF_SUM3(CS_PREF) : 0.,
-                     DIAG ? LF_SUM3(CS_INF) : 0.);
+    if (DIAG)
+        soil_pixel<DIAG, DIAG ? PIX_ALL : PIX_LATE>(P, D, i, InGlobal(P, 0, (int)i), LF_SUM3(CS_TAINT), LF_SUM3(CS_TA),
+                                                    LF_SUM3(CS_ES), LF_SUM3(CS_UZOUT), LF_SUM3(CS_GWPERC),
+                                                    r0[CS_SURF] + r2[CS_SURF], r1[CS_SURF], LF_SUM3(CS_PREF), LF_SUM3(CS_INF));
+    else
+        soil_pixel<false, PIX_LATE>(P, D, i, InGlobal(P, 0, (int)i), 0., 0., 0., LF_SUM3(CS_UZOUT), LF_SUM3(CS_GWPERC),
+                                    r0[CS_SURF] + r2[CS_SURF], r1[CS_SURF], 0., 0.);
 #undef LF_SUM3
 }
 
@@ -836,10 +855,13 @@ __global__ void __launch_bounds__(3 * TILE, MINB) k_soil_staged(const __grid_con
         const InStaged<TILE> in(rows, G, s_frozen, v, pl);
         done = soil_column<false>(P, Diag(), tab, v, (int)i, in, C, &s_def[pl]) == COL_DONE;
     }
-    if (done) {  // the column's own state rows are consumed: they carry its contributions to the per-pixel part
+    // the column's own state rows are consumed: they carry its contributions to the per-pixel part
+    if (inside) {  // final for every column, queued or not
         mine[0 * TILE] = C.taint;
         mine[1 * TILE] = C.ta;
         mine[2 * TILE] = C.es;
+    }
+    if (done) {
         mine[3 * TILE] = C.uzout;
         mine[4 * TILE] = C.gwperc;
         mine[5 * TILE] = C.surf;
@@ -847,23 +869,24 @@ __global__ void __launch_bounds__(3 * TILE, MINB) k_soil_staged(const __grid_con
     __syncthreads();
     if (!inside) return;
     const int fl = s_def[pl];
+    const double *c0 = rows + (size_t)NPIXROW * TILE + pl, *c1 = c0 + NVEGROW * TILE, *c2 = c1 + NVEGROW * TILE;
+#define LF_S3(c) ((c0[(c) * TILE] + c1[(c) * TILE]) + c2[(c) * TILE])
     if (fl != 0) {
-        if (done) {  // park the finished column's contributions for k_soil_pixel_flagged
+        if (done) {  // park what the late per-pixel part needs from a finished column
             double *rec = crec(P, v, i);
-            rec[CS_TAINT] = C.taint;
-            rec[CS_TA] = C.ta;
-            rec[CS_ES] = C.es;
             rec[CS_UZOUT] = C.uzout;
             rec[CS_GWPERC] = C.gwperc;
             rec[CS_SURF] = C.surf;
         }
-        if (v == 0) P.pix_deferred[i] = (uint8_t)fl;
+        if (v == 0) {  // the early per-pixel part does not wait for the queued columns
+            P.pix_deferred[i] = (uint8_t)fl;
+            const InStaged<TILE> in(rows, G, s_frozen, 0, pl);
+            soil_pixel<false, PIX_EARLY>(P, Diag(), i, in, LF_S3(0), LF_S3(1), LF_S3(2), 0., 0., 0., 0., 0., 0.);
+        }
         return;
     }
     if (v != 0) return;
     P.pix_deferred[i] = 0;
-    const double *c0 = rows + (size_t)NPIXROW * TILE + pl, *c1 = c0 + NVEGROW * TILE, *c2 = c1 + NVEGROW * TILE;
-#define LF_S3(c) ((c0[(c) * TILE] + c1[(c) * TILE]) + c2[(c) * TILE])
     const InStaged<TILE> in(rows, G, s_frozen, 0, pl);
     soil_pixel<false>(P, Diag(), i, in, LF_S3(0), LF_S3(1), LF_S3(2), LF_S3(3), LF_S3(4),
                       c0[5 * TILE] + c2[5 * TILE],  // Rainfed + Irrigated (surface_routing.py:145)

@@ -118,11 +118,11 @@ def _assert_same_state(A, B, tag):
 
 
 @pytest.mark.parametrize("rows,cols,maskf", [(96, 64, 0.0), (61, 71, 0.0), (80, 90, 0.15)])
-@pytest.mark.parametrize("variant,plain", [(10, 0), (10, 1), (11, 0), (12, 0), (13, 0), (0, 0), (4, 0)])
+@pytest.mark.parametrize("variant,plain", [(13, 0), (13, 1), (10, 0), (11, 0), (12, 0)])
 def test_first_pass_launch_shapes_agree(gpu_lib, monkeypatch, rows, cols, maskf, variant, plain):
     """The lean first pass of the soil stage -- inputs staged in shared memory by bulk async copies (variants 10-13),
-    staged by ordinary loads (LF_SOIL_PLAIN, and automatically for ragged tiles / odd N), or loaded directly
-    (k_soil_fused, variants 0-5) -- produces the bits of the diagnostics build, which the golden tests pin."""
+    or staged by ordinary loads (LF_SOIL_PLAIN, and automatically for ragged tiles / odd N) -- produces the bits of the
+    diagnostics build (k_soil_fused, direct loads), which the golden tests pin."""
     from lisflood_code_b200 import synthetic
     S = synthetic.full_stack(rows, cols, seed=21, split_routing=False, mask_fraction=maskf)
     A = _model(gpu_lib, S, True)

@@ -1,4 +1,4 @@
-"""Times the soil stage of the C3 workload for each tile / occupancy variant of k_soil_fused (LF_SOIL_VARIANT).
+"""Times the soil stage of the C3 workload for each tile / occupancy variant of k_soil_staged (LF_SOIL_VARIANT).
 
   python tools/soil_variants.py [--rows 10000 --cols 10000 --steps 5]
 
@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--rows", type=int, default=10000)
     ap.add_argument("--cols", type=int, default=10000)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--variants", default="4,10,11,12,13,4")
+    ap.add_argument("--variants", default="13,11,10,12,13")
     ap.add_argument("--spinup", type=int, default=10, help="model steps before the first variant (the deferred fraction "
                     "settles from 3.3 % to ~1.2 % over the first ~10 steps; repeat a variant at both ends to bracket drift)")
     args = ap.parse_args()
