@@ -177,8 +177,9 @@ int lf_model_step(lf_model *m);
 int lf_model_stage_times(lf_model *m, int reset, double *soil_ms, double *overland_ms, double *channel_ms,
                          int64_t *steps);
 /* Soil-stage statistics of the last step: deferred_columns[6] = number of (fraction, pixel) columns that needed
- * 2-3, 4-7, 8-15, 16-31, 32-63, 64+ Darcy sub-steps; kernel_ms[8] = device time of k_soil_veg, the six
- * k_soil_veg_deferred launches and k_soil_pixel (zeros unless timing was enabled by an earlier call with
+ * 2-3, 4-7, 8-15, 16-31, 32-63, 64+ Darcy sub-steps; kernel_ms[8] = device time of the first pass (k_soil_staged;
+ * k_soil_fused with diagnostics) in [0], of k_soil_veg_deferred (one persistent launch over all six lists) in [1],
+ * zeros in [2..6], of k_soil_pixel_flagged in [7] (all zeros unless timing was enabled by an earlier call with
  * enable_timing = 1).  Either pointer may be NULL.  Synchronises. */
 int lf_model_soil_stats(lf_model *m, int enable_timing, int64_t *deferred_columns, double *kernel_ms);
 void lf_model_destroy(lf_model *m);
