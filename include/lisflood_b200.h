@@ -184,6 +184,58 @@ int lf_model_stage_times(lf_model *m, int reset, double *soil_ms, double *overla
 int lf_model_soil_stats(lf_model *m, int enable_timing, int64_t *deferred_columns, double *kernel_ms);
 void lf_model_destroy(lf_model *m);
 
+/* ---- The two Numba kernels of the reference as stand-alone operators (hydrological_modules/soilloop.py) ----
+ * Same arguments, same in-place semantics; arrays are C-contiguous float64 (bool arrays: uint8), host or device
+ * pointers.  (V,N) = (vegetation fraction, pixel), (L,N) = (land use, pixel), (N) = per pixel.  Host arrays are copied to
+ * the device, updated there and copied back: the stand-alone operators exist for drop-in parity at the kernel level;
+ * residency (and speed) is won one level up, in lf_model_soil. */
+
+/* interception_water_balance(Interception, TaInterception, LeafDrainage, CumInterception, LAI, Rain, TaInterceptionMax,
+ * drainageK), soilloop.py:27-70.  Writes Interception, TaInterception, LeafDrainage; updates CumInterception. */
+int lf_interception_water_balance(double *Interception, double *TaInterception, double *LeafDrainage, double *CumInterception,
+                                  const double *LAI, const double *Rain, const double *TaInterceptionMax, double drainageK,
+                                  int64_t num_vegs, int64_t num_pixs);
+
+/* soilColumnsWaterBalance(index_landuse_all, is_irrigated, is_paddy_irrig, paddy_inactive, DtDay, ...), soilloop.py:78-355:
+ * the 73 arguments in the reference's order (paddy rice belongs to the EPIC crop module, out of scope: is_paddy_irrig
+ * must be all false, paddy_inactive is ignored).  In/out: AvailableWaterForInfiltration, DSLR, ESAct, PrefFlow,
+ * Infiltration, W1a, W1b, W1, W2, Theta*, Sat*, SeepTopToSubA/B, SeepSubToGW, UZOutflow, UZ, GwPercUZLZ. */
+typedef struct lf_soil_columns_args {
+    int64_t num_vegs, num_pixs, num_landuses;
+    const int64_t *index_landuse_all; /* (V) */
+    const uint8_t *is_irrigated;      /* (V) */
+    const uint8_t *is_paddy_irrig;    /* (V), all 0 */
+    double DtDay;
+    double *AvailableWaterForInfiltration;                    /* (V,N) out */
+    const double *Rain, *SnowMelt;                            /* (N) */
+    const double *LeafDrainage, *Interception;                /* (V,N) */
+    double *DSLR;                                             /* (V,N) in/out */
+    double AvWaterThreshold;
+    double *ESAct;                                            /* (V,N) out */
+    const double *ESMax;                                      /* (V,N) */
+    const uint8_t *isFrozenSoil;                              /* (N) */
+    const double *b_Xinanjiang;                               /* (N) */
+    const double *StoreMaxPervious;                           /* (L,N) */
+    const double *PowerInfPot;                                /* (N) */
+    double *PrefFlow;                                         /* (V,N) out */
+    const double *PowerPrefFlow;                              /* (N) */
+    double *Infiltration;                                     /* (V,N) out */
+    double CourantCrit;
+    const uint8_t *PoreSpaceNotZero1a, *PoreSpaceNotZero1b, *PoreSpaceNotZero2; /* (L,N) */
+    const double *KSat1a, *KSat1b, *KSat2, *GenuInvM1a, *GenuInvM1b, *GenuInvM2, *GenuM1a, *GenuM1b, *GenuM2; /* (L,N) */
+    double *W1a, *W1b, *W1, *W2;                              /* (V,N) in/out */
+    double *Theta1a, *Theta1b, *Theta2, *Sat1a, *Sat1b, *Sat1, *Sat2; /* (V,N) out */
+    double *SeepTopToSubA, *SeepTopToSubB, *SeepSubToGW;      /* (V,N) out */
+    const double *WRes1a, *WRes1b, *WRes1, *WRes2, *WWP1a, *WWP1b, *WWP1, *WWP2, *WFC1a, *WFC1b, *WFC1, *WFC2; /* (L,N) */
+    const double *SoilDepth1a, *SoilDepth1b, *SoilDepth2, *WS1a, *WS1b, *WS1, *WS2; /* (L,N) */
+    const double *UpperZoneK;                                 /* (N) */
+    double DrainedFraction;
+    const double *GwPercStep;                                 /* (N) */
+    double *UZOutflow, *UZ, *GwPercUZLZ;                      /* (V,N) out, in/out, out */
+    int64_t *NoSubS_out;                                      /* optional (V,N): Darcy sub-steps taken */
+} lf_soil_columns_args;
+int lf_soil_columns_water_balance(const lf_soil_columns_args *args);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,8 @@ SIGNATURES = {
                                        C.POINTER(C.c_double), C.POINTER(_i64s)]),
     "lf_model_soil_stats": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "lf_model_destroy": (None, [_vp]),
+    "lf_interception_water_balance": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _i64s, _i64s]),
+    "lf_soil_columns_water_balance": (C.c_int, [_vp]),
 }
 
 
@@ -85,6 +87,28 @@ class ModelConfig(C.Structure):
                 ("CourantCrit", C.c_double), ("AvWaterThreshold", C.c_double), ("LeafDrainageK", C.c_double),
                 ("DrainedFraction", C.c_double), ("SMaxSealed", C.c_double), ("diagnostics", C.c_int32),
                 ("reserved", C.c_int32)]
+
+_D, _U, _I = C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int64)
+
+
+class SoilColumnsArgs(C.Structure):
+    """struct lf_soil_columns_args (include/lisflood_b200.h): the 73 arguments of soilColumnsWaterBalance."""
+    _fields_ = ([("num_vegs", C.c_int64), ("num_pixs", C.c_int64), ("num_landuses", C.c_int64), ("index_landuse_all", _I),
+                 ("is_irrigated", _U), ("is_paddy_irrig", _U), ("DtDay", C.c_double),
+                 ("AvailableWaterForInfiltration", _D), ("Rain", _D), ("SnowMelt", _D), ("LeafDrainage", _D),
+                 ("Interception", _D), ("DSLR", _D), ("AvWaterThreshold", C.c_double), ("ESAct", _D), ("ESMax", _D),
+                 ("isFrozenSoil", _U), ("b_Xinanjiang", _D), ("StoreMaxPervious", _D), ("PowerInfPot", _D),
+                 ("PrefFlow", _D), ("PowerPrefFlow", _D), ("Infiltration", _D), ("CourantCrit", C.c_double),
+                 ("PoreSpaceNotZero1a", _U), ("PoreSpaceNotZero1b", _U), ("PoreSpaceNotZero2", _U)]
+                + [(k, _D) for k in ("KSat1a", "KSat1b", "KSat2", "GenuInvM1a", "GenuInvM1b", "GenuInvM2", "GenuM1a", "GenuM1b",
+                                     "GenuM2", "W1a", "W1b", "W1", "W2", "Theta1a", "Theta1b", "Theta2", "Sat1a", "Sat1b",
+                                     "Sat1", "Sat2", "SeepTopToSubA", "SeepTopToSubB", "SeepSubToGW", "WRes1a", "WRes1b",
+                                     "WRes1", "WRes2", "WWP1a", "WWP1b", "WWP1", "WWP2", "WFC1a", "WFC1b", "WFC1", "WFC2",
+                                     "SoilDepth1a", "SoilDepth1b", "SoilDepth2", "WS1a", "WS1b", "WS1", "WS2",
+                                     "UpperZoneK")]
+                + [("DrainedFraction", C.c_double), ("GwPercStep", _D), ("UZOutflow", _D), ("UZ", _D), ("GwPercUZLZ", _D),
+                   ("NoSubS_out", _I)])
+
 
 _lib = None
 

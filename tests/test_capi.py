@@ -62,3 +62,22 @@ def test_host_modules_import():
     from lisflood_code_b200 import hotpath, synthetic  # noqa: F401
     from lisflood_code_b200.global_modules import add1, ldd_ops  # noqa: F401
     assert "W1a" in hotpath.THREE_ROWS and "LZ" not in hotpath.THREE_ROWS
+
+
+def test_soil_columns_args_layout_matches_the_header(tmp_path):
+    """ctypes mirror of struct lf_soil_columns_args: same size and field offsets as the C header (checked with gcc)."""
+    import subprocess
+    from lisflood_code_b200 import _capi
+    names = [n for n, _ in _capi.SoilColumnsArgs._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lisflood_b200.h"\nint main(void){\n'
+                   'printf("%zu\\n", sizeof(lf_soil_columns_args));\n'
+                   + "".join('printf("%%zu\\n", offsetof(lf_soil_columns_args, %s));\n' % n for n in names)
+                   + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == C.sizeof(_capi.SoilColumnsArgs)
+    assert out[1:] == [getattr(_capi.SoilColumnsArgs, n).offset for n in names]
+    from lisflood_code_b200.hydrological_modules import soilloop
+    assert len(soilloop._SOIL_ARG_ORDER) == 73
