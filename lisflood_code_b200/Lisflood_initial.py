@@ -41,6 +41,24 @@ class InitialVariables(object):
         self.DtDay = self.DtSec / 86400.0
         self.InvDtSec, self.InvDtDay = 1 / self.DtSec, 1 / self.DtDay
 
+    def misc_initial(self):
+        """The numeric part of miscInitial.initial() the hot path needs (reference: hydrological_modules/miscInitial.py:
+        52-133): grid size from the 'PixelLengthUser' / 'PixelAreaUser' inputs (option gridSizeUserDefined; scalars or
+        maps), unit multipliers, groundwater percolation / loss per step."""
+        zeros = self.maskinfo.in_zero
+        self.PixelLength = self.loadmap('PixelLengthUser')
+        area = self.loadmap('PixelAreaUser') if self._has('PixelAreaUser') else self.PixelLength ** 2
+        self.PixelArea = zeros() + area if isinstance(area, float) else area
+        self.InvPixelLength = 1.0 / self.PixelLength
+        self.MMtoM, self.MtoMM = 0.001, 1000
+        self.MMtoM3 = 0.001 * self.PixelArea
+        self.M3toMM = 1 / self.MMtoM3
+        loss = self.loadmap('GwLoss')
+        self.GwLoss = zeros() + loss if isinstance(loss, float) else loss
+        self.GwPerc = np.maximum(self.loadmap('GwPercValue'), self.GwLoss)
+        self.GwPercStep = self.GwPerc * self.DtDay
+        self.GwLossStep = self.GwLoss * self.DtDay
+
     # ---- inputs ----
     def option(self, name):
         return bool(self.options.get(name, False))

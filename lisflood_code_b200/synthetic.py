@@ -277,7 +277,8 @@ def forcing(S, step, seed=0):
     return F
 
 
-def raw_inputs(rows, cols, seed=0, ldd_noise=0.5, mask_fraction=0.1, channel_threshold=20, scalar_maps=False):
+def raw_inputs(rows, cols, seed=0, ldd_noise=0.5, mask_fraction=0.1, channel_threshold=20, scalar_maps=False,
+               soilless_fraction=0.03):
     """Raw static inputs by BINDING name (what `loadmap` returns: float or float64[N]) for the soil and routing
     modules' initial(), plus the attributes earlier modules leave on the model object.  Returns (mask, raw, state).
     Used by tests/golden/make_golden.py (fed to the reference's own initial()) and by the init tests."""
@@ -291,8 +292,8 @@ def raw_inputs(rows, cols, seed=0, ldd_noise=0.5, mask_fraction=0.1, channel_thr
     raw = {"Ldd": codes, "Channels": (uparea >= channel_threshold).astype(np.float64), "beta": 0.6,
            "ChanLength": 5000.0 * U(1.0, 1.4), "ChanGrad": U(0.0, 5e-3), "ChanGradMin": 1e-4, "CalChanMan": U(0.5, 2.0),
            "ChanMan": U(0.02, 0.06), "ChanBottomWidth": 2.0 + 0.5 * np.sqrt(uparea), "ChanDepthThreshold": 0.5 + 0.05 * np.sqrt(uparea),
-           "ChanSdXdY": 1.0, "TotalCrossSectionAreaInitValue": np.where(rng.random(n) < 0.5, -9999.0, U(0.1, 3.0)),
-           "PrevDischarge": -9999.0, "CrossSection2AreaInitValue": np.where(rng.random(n) < 0.6, -9999.0, U(0.0, 0.5)),
+           "ChanSdXdY": 1.0, "TotalCrossSectionAreaInitValue": np.where(rng.random(n) < 0.5, -9999.0, U(0.5, 3.0)),
+           "PrevDischarge": -9999.0, "CrossSection2AreaInitValue": np.where(rng.random(n) < 0.6, -9999.0, U(0.0, 0.05)),
            "PrevSideflowInitValue": -9999.0, "CalChanMan2": U(1.0, 4.0), "QSplitMult": 2.0,
            "AvgDis": np.where(uparea >= channel_threshold, 0.002 * uparea + 0.01, 0.0)}
     for i, (lo, hi) in zip("123", ((40, 60), (200, 300), (500, 900))):
@@ -306,7 +307,7 @@ def raw_inputs(rows, cols, seed=0, ldd_noise=0.5, mask_fraction=0.1, channel_thr
         raw["MapKSat" + i] = np.exp(U(np.log(1.0), np.log(500.0)))
         if i != "3":
             raw["MapKSat%sForest" % i] = np.exp(U(np.log(1.0), np.log(500.0)))
-    raw["SoilDepth1"][rng.random(n) < 0.03] = 0.0   # soil-less pixels: PoreSpaceNotZero False
+    raw["SoilDepth1"][rng.random(n) < soilless_fraction] = 0.0   # soil-less pixels: PoreSpaceNotZero False
     raw.update({"CourantCrit": 0.4, "LeafDrainageTimeConstant": 1.0, "AvWaterRateThreshold": 5.0, "MapCropCoef": U(.9, 1.1),
                 "MapForestCropCoef": U(.9, 1.3), "MapIrrigationCropCoef": U(.9, 1.2), "MapCropGroupNumber": U(1, 5),
                 "MapForestCropGroupNumber": U(2, 5), "MapIrrigationCropGroupNumber": U(1, 5), "MapN": U(.05, .2),
@@ -323,4 +324,11 @@ def raw_inputs(rows, cols, seed=0, ldd_noise=0.5, mask_fraction=0.1, channel_thr
     state = {"SoilFraction": np.ascontiguousarray(fr[:3]), "OtherFraction": fr[0].copy(), "ForestFraction": fr[1].copy(),
              "IrrigationFraction": fr[2].copy(), "DirectRunoffFraction": fr[3].copy(), "WaterFraction": fr[4].copy(),
              "RiceFraction": fr[5].copy(), "PixelArea": np.full(n, 25.0e6)}
+    # overland flow, groundwater, grid size (drawn last: the earlier inputs keep their values)
+    raw.update({"OFOtherInitValue": 0.0, "OFForestInitValue": U(0.0, 50.0), "OFDirectInitValue": 0.0, "Grad": U(0.0, 0.1),
+                "GradMin": 1e-3, "OFDepRef": 5.0, "UpperZoneTimeConstant": 10.0 if scalar_maps else U(5.0, 20.0),
+                "LowerZoneTimeConstant": U(50.0, 500.0), "LZAvInflowMap": U(0.0, 2.0),
+                "LZInitValue": np.where(rng.random(n) < 0.5, -9999.0, U(20.0, 200.0)), "LZThreshold": U(0.0, 20.0),
+                "UZInitValue": 0.0, "UZForestInitValue": U(0.0, 10.0), "UZIrrigationInitValue": 2.5,
+                "PixelLengthUser": 5000.0, "GwLoss": 0.0 if scalar_maps else U(0.0, 0.3), "GwPercValue": U(0.2, 1.5)})
     return mask, raw, state

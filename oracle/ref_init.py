@@ -98,6 +98,13 @@ def _install(raw, land_mask):
     soil_mod = sys.modules["lisflood.hydrological_modules.soil"]
     rout_mod = sys.modules["lisflood.hydrological_modules.routing"]
     soil_mod.loadmap = loadmap
+
+    def makenumpy(m):   # global_modules/add1.py: scalar -> array over the mask
+        return np.zeros(n) + m if np.ndim(m) == 0 else np.asarray(m, np.float64)
+    for name in ("surface_routing", "groundwater"):
+        mod = sys.modules["lisflood.hydrological_modules." + name]
+        mod.loadmap, mod.loadmap_base, mod.makenumpy, mod.compressArray, mod.decompress = (loadmap, loadmap, makenumpy,
+                                                                                            compress, decompress)
     for k, f in dict(loadmap=loadmap, loadmap_base=loadmap, compressArray=compress, decompress=decompress, lddmask=lddmask,
                      lddrepair=lddrepair, accuflux=accuflux, boolean=boolean, pit=pit, ifthenelse=ifthenelse,
                      downstream=downstream, upstream=upstream, uniqueid=uniqueid, nominal=nominal,
@@ -199,3 +206,22 @@ def routing_initial(land_mask, raw, state, options=None, DtSec=86400.0, DtSecCha
     r.initialSecond()
     out = {k: v for k, v in _collect(var).items() if k not in before}
     return out
+
+
+def surface_and_groundwater_initial(land_mask, raw, state, options=None, DtSec=86400.0):
+    """Outputs of the reference's surface_routing.initial() and groundwater.initial().  `state`: what miscInitial,
+    soil.initial and routing.initial leave on the model object (PixelLength, InvPixelLength, MMtoM, NManning (3,N), Beta,
+    InvBeta, AlpPow, GwPerc, GwLoss)."""
+    M, loadmap = _install(raw, land_mask)
+    var = _InitVar(land_mask, raw, loadmap, dict(options or {}), DtSec, 3600.0)
+    for k, v in state.items():
+        if np.ndim(v) == 2:
+            setattr(var, k, var._NM(np.array(v, np.float64), ["runoff", "pixel"]))
+        elif np.ndim(v) == 1:
+            setattr(var, k, np.array(v, np.float64))
+        else:
+            setattr(var, k, float(v))
+    before = set(var.__dict__)
+    M["surface_routing"](var).initial()
+    M["groundwater"](var).initial()
+    return {k: v for k, v in _collect(var).items() if k not in before}

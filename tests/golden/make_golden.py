@@ -94,11 +94,11 @@ def model_case(name, rows, cols, seed, split, steps, **kw):
     print(name, "n=%d steps=%d split=%s channel fraction %.3f" % (S["N"], steps, split, S["IsChannel"].mean()))
 
 
-def init_case(name, rows, cols, seed, split, scalar_maps=False, dt_sec=86400.0):
+def init_case(name, rows, cols, seed, split, scalar_maps=False, dt_sec=86400.0, soilless_fraction=0.03):
     """soil.initial() and routing.initial()/initialSecond() executed by the reference's OWN classes (oracle/ref_init.py)
     on raw inputs by binding name; stores inputs and every attribute they set."""
     from oracle import ref_init
-    mask, raw, state = synthetic.raw_inputs(rows, cols, seed=seed, scalar_maps=scalar_maps)
+    mask, raw, state = synthetic.raw_inputs(rows, cols, seed=seed, scalar_maps=scalar_maps, soilless_fraction=soilless_fraction)
     opts = {"SplitRouting": split, "drainedIrrigation": split}
     out = {"mask": mask, "DtSec": np.float64(dt_sec), "SplitRouting": np.bool_(split)}
     out.update({"raw__" + k: np.asarray(v) for k, v in raw.items()})
@@ -107,7 +107,15 @@ def init_case(name, rows, cols, seed, split, scalar_maps=False, dt_sec=86400.0):
     out.update({"soil__" + k: v for k, v in ref_init.soil_initial(mask, raw, soil_state, opts, DtSec=dt_sec).items()})
     out.update({"routing__" + k: v for k, v in ref_init.routing_initial(mask, raw, {"PixelArea": state["PixelArea"]}, opts,
                                                                         DtSec=dt_sec).items()})
+    # surface_routing.initial / groundwater.initial need what miscInitial, soil.initial and routing.initial left behind
+    n = int(mask.sum())
+    gwloss = np.zeros(n) + raw["GwLoss"]
+    st2 = {"PixelLength": raw["PixelLengthUser"], "InvPixelLength": 1.0 / raw["PixelLengthUser"], "MMtoM": 0.001,
+           "NManning": out["soil__NManning"], "Beta": out["routing__Beta"], "InvBeta": out["routing__InvBeta"],
+           "AlpPow": out["routing__AlpPow"], "GwLoss": gwloss, "GwPerc": np.maximum(raw["GwPercValue"], gwloss)}
+    out.update({"surfgw__" + k: v for k, v in ref_init.surface_and_groundwater_initial(mask, raw, st2, opts, DtSec=dt_sec).items()})
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "surface/groundwater maps=%d" % sum(k.startswith("surfgw__") for k in out))
     print(name, "n=%d soil maps=%d routing maps=%d" % (int(mask.sum()), sum(k.startswith("soil__") for k in out),
                                                       sum(k.startswith("routing__") for k in out)))
 
@@ -117,7 +125,8 @@ def main():
     warnings.simplefilter("ignore")
     if len(sys.argv) > 1 and sys.argv[1] == "init":
         init_case("init_24x31_split", 24, 31, 61, True)
-        init_case("init_19x23_single_6h", 19, 23, 62, False, scalar_maps=True, dt_sec=21600.0)
+        init_case("init_19x23_single_6h", 19, 23, 62, False, scalar_maps=True, dt_sec=21600.0, soilless_fraction=0.0)
+        init_case("init_21x26_split_sound", 21, 26, 63, True, soilless_fraction=0.0)
         return
     model_case("model_26x34_single", 26, 34, 41, False, 3, mask_fraction=0.08, channel_threshold=12)
     model_case("model_30x28_split", 30, 28, 42, True, 3, mask_fraction=0.05, channel_threshold=10)

@@ -21,8 +21,10 @@ NOT_MIRRORED = {"AtLastPoint", "MaskMap", "IsChannelPcr", "avgdis", "Theta1a", "
 def _build(case):
     from lisflood_code_b200.Lisflood_initial import InitialVariables
     from lisflood_code_b200.global_modules.add1 import NumpyModified
+    from lisflood_code_b200.hydrological_modules.groundwater import groundwater
     from lisflood_code_b200.hydrological_modules.routing import routing
     from lisflood_code_b200.hydrological_modules.soil import soil
+    from lisflood_code_b200.hydrological_modules.surface_routing import surface_routing
     g = load_golden(case)
     raw = {k[5:]: (float(v) if v.ndim == 0 else v) for k, v in g.items() if k.startswith("raw__")}
     split = bool(g["SplitRouting"])
@@ -30,9 +32,13 @@ def _build(case):
     for k, v in g.items():
         if k.startswith("state__"):
             setattr(var, k[7:], NumpyModified(v.copy(), ["vegetation", "pixel"]) if v.ndim == 2 else v.copy())
+    # the reference's order (Lisflood_initial.py:174-262): misc, ..., groundwater, soil, routing, surface routing
+    var.misc_initial()
     soil(var).initial()
     r = routing(var)
     r.initial()
+    groundwater(var).initial()
+    surface_routing(var).initial()
     r.initialSecond()
     return g, var
 
@@ -42,7 +48,7 @@ def test_initial_matches_reference(case):
     g, var = _build(case)
     checked, missing = 0, []
     for key, want in g.items():
-        if not (key.startswith("soil__") or key.startswith("routing__")):
+        if not key.startswith(("soil__", "routing__", "surfgw__")):
             continue
         name = key.split("__", 1)[1]
         if name in NOT_MIRRORED:
@@ -61,18 +67,48 @@ def test_initial_matches_reference(case):
             assert np.array_equal(got, want), name
         checked += 1
     assert not missing, missing
-    assert checked >= 80
+    assert checked >= 100
 
 
 @pytest.mark.parametrize("case", golden_cases("init_"))
 def test_state_feeds_the_device_model_layout(case):
-    """InitialVariables.state() carries every parameter / state map HotPathModel uploads for the soil stage."""
+    """InitialVariables.state() after the modules' initial() carries every scalar, parameter, state and flag map
+    HotPathModel uploads (the dictionary synthetic.full_stack builds by hand)."""
     from lisflood_code_b200 import hotpath
     g, var = _build(case)
     S = var.state()
-    need = [k for k in list(hotpath.PARAMETERS) + list(hotpath.STATE)
-            if k.startswith(("W", "KSat", "Genu", "CropCoef", "CropGroup", "b_X", "PowerPref", "DSLR", "CumInter"))]
-    assert need and not [k for k in need if k not in S], [k for k in need if k not in S]
+    split = bool(g["SplitRouting"])
+    need = list(hotpath.PARAMETERS) + list(hotpath.STATE) + ["IsChannel", "IsChannelKinematic", "AtLastPointC", "LddToChan",
+                                                             "LddKinematic", "DtSec", "Beta", "PixelLength", "NoRoutSteps",
+                                                             "CourantCrit", "AvWaterThreshold", "LeafDrainageK",
+                                                             "DrainedFraction", "SMaxSealed", "mask"]
+    if split:
+        need += list(hotpath.SPLIT_PARAMETERS) + list(hotpath.SPLIT_STATE)
+    assert not [k for k in need if k not in S], [k for k in need if k not in S]
     n = int(g["mask"].sum())
-    for k in need:
-        assert np.ndim(S[k]) == 0 or np.asarray(S[k]).shape[-1] == n, k
+    for k in list(hotpath.PARAMETERS) + list(hotpath.STATE):
+        a = np.asarray(S[k], np.float64)
+        assert a.ndim == 0 or a.shape[-1] == n, k
+        assert np.all(np.isfinite(a)), k
+        if hotpath.PARAMETERS.get(k, hotpath.STATE.get(k)) == 3:
+            assert a.shape == (3, n), k
+
+
+@pytest.mark.parametrize("case", golden_cases("init_"))
+def test_initialised_state_runs_through_the_oracle_model(case, oracle):
+    """The state derived by the initial() mirrors is a complete model state: the CPU oracle steps it and conserves
+    finiteness (no GPU needed: HotPathModel takes the same dictionary)."""
+    from lisflood_code_b200 import synthetic
+    from oracle import lisf_oracle_model as om
+    g, var = _build(case)
+    S = var.state()
+    S["SplitRouting"] = bool(g["SplitRouting"])
+    S["kgb"] = 0.75 * 0.72
+    for k in ("W1a", "W1b", "W2"):          # soil-less pixels of the raw inputs divide by zero in the reference's satFun
+        assert np.all(np.isfinite(S[k]))
+    pore = np.asarray(S["PoreSpaceNotZero1a"]).all(axis=0)
+    if not pore.all():
+        pytest.skip("synthetic inputs with soil-less pixels: the reference's own kernel raises ZeroDivisionError there")
+    O = om.OracleModel(S)
+    O.step(synthetic.forcing(S, 0, 7))
+    assert np.all(np.isfinite(O.var.ChanQAvg)) and np.all(np.isfinite(O.var.W1a))
