@@ -426,26 +426,41 @@ def cpu_baseline_c3(args):
 
 
 def run_reference_c3(args):
+    """Reference arm of the default workload: the reference's CPU algorithm (C/OpenMP kernels + NumPy glue, executed as
+    the reference executes them; the Python/Numba reference itself cannot travel to the GPU box) on the host cores, at
+    the best of the thread counts tried, each step a bounded sample (a crop of the same generator) of the C3 step."""
     rank, world, local = dist_env()
     if rank != 0:
         return
     S, O, synthetic, lisf_oracle = _c3_oracle(args)
-    nthr = lisf_oracle.set_threads(min(os.cpu_count() or 1, 64))
-    for w in range(max(1, args.warmup)):
-        O.step(synthetic.forcing(S, w, 300))
+    cores = os.cpu_count() or 1
+    best = None
+    for i, thr in enumerate(sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})):   # untimed: also the warm-up
+        lisf_oracle.set_threads(thr)
+        t0 = time.perf_counter()
+        O.step(synthetic.forcing(S, i, 300))
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, thr)
+    nthr = lisf_oracle.set_threads(best[1])
+    for w in range(args.warmup):
+        O.step(synthetic.forcing(S, 5 + w, 300))
     t0 = time.perf_counter()
     for k in range(args.steps):
         O.step(synthetic.forcing(S, 10 + k, 300))
     dt = time.perf_counter() - t0
     value = S["N"] * args.steps / dt
     cpu = {"value": value, "unit": "cell-updates/s", "cores": nthr, "kind": "port",
-           "sample": "%d model steps on a %dx%d crop of the same generator (per-cell throughput)" % (args.steps, args.cpu_rows,
-                                                                                               args.cpu_rows)}
+           "sample": "%d model steps (24 sub-steps each) on a %dx%d crop of the same generator, per-cell throughput; best of "
+                     "the thread counts tried" % (args.steps, args.cpu_rows, args.cpu_rows)}
     print(json.dumps({"impl": "reference", "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s",
                       "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": "C3 full stack, CPU port of the reference algorithm on a %dx%d crop" % (
-                          args.cpu_rows, args.cpu_rows), "cells": S["N"], "no_rout_steps": 24},
+                      "config": {"workload": "C3 synthetic %dx%d raster, full soil+infiltration+overland+channel stack, "
+                                             "24 channel sub-steps per model step, single kinematic routing, random D8 LDD "
+                                             "(noise/tilt %.2f)" % (args.rows, args.cols, args.ldd_noise),
+                                 "sample": "%dx%d crop of the same generator per step" % (args.cpu_rows, args.cpu_rows),
+                                 "cells": S["N"], "no_rout_steps": 24},
                       "cpu_baseline": cpu,
                       "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
