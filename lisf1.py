@@ -3,16 +3,40 @@
 
 Entry surface of LISFLOOD (reference: src/lisf1.py, src/lisflood/main.py:164-226) for the B200 hot path.  The
 settings file has the reference's structure (<lfoptions>, <lfuser>, <lfbinding>, $(var) substitution).  Because
-PCRaster / NetCDF IO is out of scope here, the bindings of this entry point name NumPy archives:
+PCRaster / NetCDF IO is out of scope here, map bindings name NumPy files (.npy: a 2-D raster or an already compressed
+1-D array) or numbers, as `loadmap` accepts them:
 
-    MaskMap        .npy  bool[rows, cols]            StateFile    .npz  every static map / initial state by its
-    ForcingFile    .npz  Rain, SnowMelt, ETRef ...         (reference attribute name, see synthetic.full_stack)
-                         stacked as (steps, ...)      DisOut       .npy  written: ChanQAvg (= dis) per step
-    StepStart, StepEnd   1-based step numbers
+    MaskMap        .npy  bool[rows, cols]
+    every static input of the hot-path modules by its reference binding name (Ldd, Channels, ChanGrad, MapKSat1,
+    SoilDepth1, b_Xinanjiang, ForestFraction ... -- the `input_files_keys` of the module mirrors), DtSec, DtSecChannel:
+                   the modules' initial() derive the parameter maps as the reference does (Lisflood_initial.py);
+    or StateFile   .npz  the derived maps / initial state by reference attribute name (see synthetic.full_stack)
+    ForcingFile    .npz  Rain, SnowMelt, ETRef ... stacked as (steps, ...)     DisOut  .npy  written: ChanQAvg (= dis)
+    StepStart, StepEnd   1-based step numbers                                          per step
 """
 import sys
 
 import numpy as np
+
+
+def model_state(settings):
+    """The dictionary HotPathModel takes: from the StateFile binding if there is one, else derived from the raw
+    static inputs by the modules' initial() (lisflood_code_b200/Lisflood_initial.py::initialise)."""
+    b = settings.binding
+    mask = np.load(b["MaskMap"]).astype(bool)
+    split = bool(settings.options["SplitRouting"]) and not settings.options["InitLisflood"]
+    if "StateFile" in b:
+        S = {k: (v.item() if v.ndim == 0 else v) for k, v in np.load(b["StateFile"], allow_pickle=False).items()}
+    else:
+        from lisflood_code_b200.Lisflood_initial import initialise
+        var = initialise(mask, {}, settings.options, DtSec=float(b["DtSec"]), DtSecChannel=float(b["DtSecChannel"]))
+        S = var.state()
+    S["mask"] = mask
+    S["SplitRouting"] = split
+    for k in ("N", "rows", "cols", "NoRoutSteps"):
+        if k in S:
+            S[k] = int(S[k])
+    return S
 
 
 def main(*args):
@@ -26,12 +50,7 @@ def main(*args):
     settings = LisSettings(argv[0], argv[1:])
     settings.check_supported()
     b, flags = settings.binding, settings.flags
-    S = {k: (v.item() if v.ndim == 0 else v) for k, v in np.load(b["StateFile"], allow_pickle=False).items()}
-    S["mask"] = np.load(b["MaskMap"]).astype(bool)
-    S["SplitRouting"] = bool(settings.options["SplitRouting"]) and not settings.options["InitLisflood"]
-    for k in ("N", "rows", "cols", "NoRoutSteps"):
-        if k in S:
-            S[k] = int(S[k])
+    S = model_state(settings)
     if flags["initonly"]:
         return 0
     var = HotPathModel(S)

@@ -59,6 +59,17 @@ class InitialVariables(object):
         self.GwPercStep = self.GwPerc * self.DtDay
         self.GwLossStep = self.GwLoss * self.DtDay
 
+    def landuse_initial(self):
+        """Land-use fractions (reference: hydrological_modules/landusechange.py:53-93, static maps): SoilFraction rows =
+        Other (rainfed), Forest, Irrigation."""
+        for nm in ("Forest", "DirectRunoff", "Water", "Irrigation", "Rice", "Other"):
+            x = self.loadmap(nm + "Fraction")
+            setattr(self, nm + "Fraction", self.maskinfo.in_zero() + x if isinstance(x, float) else x.copy())
+        self.SoilFraction = self.allocateVariableAllVegetation()
+        self.SoilFraction[0] = self.OtherFraction
+        self.SoilFraction[1] = self.ForestFraction
+        self.SoilFraction[2] = self.IrrigationFraction
+
     # ---- inputs ----
     def option(self, name):
         return bool(self.options.get(name, False))
@@ -142,3 +153,23 @@ class InitialVariables(object):
         out["N"] = self.num_pixel
         out["rows"], out["cols"] = self.maskinfo.shape
         return out
+
+
+def initialise(land_mask, maps=None, options=None, DtSec=86400.0, DtSecChannel=3600.0):
+    """Runs the hot-path modules' initial() in the reference's order (Lisflood_initial.py:174-262: misc, land use,
+    soil, routing, groundwater, surface routing, routing second part) on raw inputs by binding name and returns the
+    InitialVariables object; `.state()` is what HotPathModel takes."""
+    from .hydrological_modules.groundwater import groundwater
+    from .hydrological_modules.routing import routing
+    from .hydrological_modules.soil import soil
+    from .hydrological_modules.surface_routing import surface_routing
+    var = InitialVariables(land_mask, maps or {}, options, DtSec=DtSec, DtSecChannel=DtSecChannel)
+    var.misc_initial()
+    var.landuse_initial()
+    soil(var).initial()
+    r = routing(var)
+    r.initial()
+    groundwater(var).initial()
+    surface_routing(var).initial()
+    r.initialSecond()
+    return var
