@@ -1,8 +1,9 @@
 // lf_model.cu -- the full hot-path time step on device-resident state (C ABI: lf_model_*).
 //
 // Stages per model step (reference call order, Lisflood_dynamic.py:114-229):
-//   1. k_soil_fused / k_soil_veg_deferred / k_soil_pixel_flagged   fused canopy + soil column per (fraction, pixel)
-//                         with open/sealed + per-pixel sums + groundwater per pixel (lf_soil_kernel.cuh).
+//   1. k_soil_staged (k_soil_fused with diagnostics) / k_soil_veg_deferred / k_soil_pixel_flagged   fused canopy +
+//                         soil column per (fraction, pixel) with open/sealed + per-pixel sums + groundwater per pixel
+//                         (lf_soil_kernel.cuh).
 //   2. k_of_level/k_of_post  the three overland-flow routers (Other, Forest, Direct) on LddToChan,
 //                         solved together in one level sweep (three independent Newton solves per thread),
 //                         then OFToChanM3 / ToChanM3RunoffDt written in channel order.

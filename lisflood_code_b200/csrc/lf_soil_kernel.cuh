@@ -1,38 +1,49 @@
-// lf_soil_kernel.cuh -- fused per-cell kernel of the soil / canopy / groundwater stack (device).
+// lf_soil_kernel.cuh -- fused per-cell kernels of the soil / canopy / groundwater stack (device).
 //
-// ONE fused kernel (k_soil_fused) replaces the stages the reference executes as separate NumPy/Numba passes:
+// ONE fused stage replaces what the reference executes as separate NumPy/Numba passes:
 //   soilloop.dynamic_canopy     hydrological_modules/soilloop.py:519-627 (+ kernel :27-70)
 //   soilloop.dynamic_soil       hydrological_modules/soilloop.py:630-665 (+ kernel :78-355)
 //   opensealed.dynamic          hydrological_modules/opensealed.py:41-71
 //   soil.dynamic_perpixel       hydrological_modules/soil.py:471-514 (deffraction: Lisflood_initial.py:393-396)
 //   groundwater.dynamic         hydrological_modules/groundwater.py:134-180
 //   surface_routing.dynamic     hydrological_modules/surface_routing.py:122-149 (runoff components only)
-// There is no neighbour access anywhere in these stages: the kernel is a pure stream over
+// There is no neighbour access anywhere in these stages: the kernels are pure streams over
 // SoA float64 maps stored in the overland-flow router's position order.
 //
-// Work decomposition: a block owns a tile of TILE consecutive pixels and has 3*TILE threads; warp-uniform
-// v = thread / TILE is the vegetation fraction, so a thread integrates one (fraction, pixel) soil column.  The three
-// columns of a pixel run in the same block at the same time: the per-pixel maps (forcing, Xinanjiang b, ...) and the
-// land-use parameter rows shared between fractions are fetched from DRAM once (the 2nd and 3rd reader hit L1/L2), the
-// fraction-weighted column results are exchanged through shared memory, and the v == 0 thread of the pixel finishes
-// the per-pixel part (open water / sealed soil, sums over fractions, groundwater, runoff components).  DRAM traffic
-// is the algorithmic 889 B per cell; the first version (separate column and pixel kernels over a
-// (fraction, pixel) grid) moved twice that.
+// Kernels:
+//   k_soil_staged         first pass of the lean (production) build: the input rows of a 64-pixel tile are staged in
+//                         shared memory by bulk async copies (TMA, one mbarrier), 3 x 64 threads integrate the three
+//                         columns of each pixel, the v == 0 thread finishes the per-pixel part;
+//   k_soil_fused          first pass of the diagnostics build (direct global loads, writes every flux map of self.var);
+//   k_soil_veg_deferred   the columns that need several Darcy sub-steps, resumed from their mid-column records, one
+//                         persistent launch over six bucket lists;
+//   k_soil_pixel_flagged  the (late) per-pixel part of the pixels that had a queued column.
+//
+// Work decomposition of the first pass: a block owns a tile of TILE consecutive pixels and has 3*TILE threads;
+// warp-uniform v = thread / TILE is the vegetation fraction, so a thread integrates one (fraction, pixel) soil column.
+// The three columns of a pixel run in the same block at the same time: the per-pixel maps (forcing, Xinanjiang b, ...)
+// and the land-use parameter rows shared between fractions are fetched from DRAM once, the fraction-weighted column
+// results are exchanged through shared memory, and the v == 0 thread of the pixel finishes the per-pixel part (open
+// water / sealed soil, sums over fractions, groundwater, runoff components).  DRAM traffic of the first pass is the
+// algorithmic 889 B per cell; the first version (separate column and pixel kernels over a (fraction, pixel) grid) moved
+// twice that.
 //
 // Divergence control (the adaptive Darcy sub-stepping, soilloop.py:237-312): the number of sub-steps is
 // per column (mean ~1.5, 99th percentile ~20, max ~100), so a warp that simply loops pays the maximum of its
-// 32 lanes (~12 on average, measured).  k_soil_fused therefore completes only the columns that need ONE
+// 32 lanes (~12 on average, measured).  The first pass therefore completes only the columns that need ONE
 // sub-step (~99 %) and appends the others, warp-aggregated, to one of six lists bucketed by sub-step count
-// (2-3, 4-7, 8-15, 16-31, 32-63, 64+); k_soil_veg_deferred then integrates each list with one thread per
+// (2-3, 4-7, 8-15, 16-31, 32-63, 64+); k_soil_veg_deferred then integrates the lists with one thread per
 // column, so lanes of a warp differ by at most 2x in trip count.  A queued column is complete up to the infiltration:
-// it leaves a mid-column record in the maps it owns (see soil_column) and k_soil_veg_deferred resumes from it -- 23
+// it leaves a mid-column record in storage it owns (see soil_column) and k_soil_veg_deferred resumes from it -- 23
 // gathered values instead of the column's 54, and none of the canopy / evaporation / infiltration arithmetic again.
-// A pixel with a deferred column is flagged (pix_deferred); its finished columns park their contributions in the c*
-// maps and k_soil_pixel_flagged completes it after the deferred lists have run.  Results do not depend on list order.
+// A pixel with a queued column is flagged (pix_deferred); its finished columns park their contributions in the
+// pixel's contribution record and k_soil_pixel_flagged completes it after the lists have run.  Results do not depend
+// on list order.
 //
 // Arithmetic: float64, unfused multiply-add like the reference (--fmad=false) except inside the library functions
-// of lf_math.cuh (table-driven x^y and e^x, Newton division and square root, 3-instruction min/max): the kernel is
-// bound by instruction issue, not by HBM, so every function call in the column is a hand-counted sequence.
+// of lf_math.cuh (table-driven x^y and e^x, Newton division and square root, 3-instruction min/max): the first pass is
+// bound by instruction issue (70 % of the issue slots busy), so every function call in the column is a hand-counted
+// sequence.
 #pragma once
 #include <stdint.h>
 
