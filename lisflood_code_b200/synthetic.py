@@ -332,3 +332,94 @@ def raw_inputs(rows, cols, seed=0, ldd_noise=0.5, mask_fraction=0.1, channel_thr
                 "UZInitValue": 0.0, "UZForestInitValue": U(0.0, 10.0), "UZIrrigationInitValue": 2.5,
                 "PixelLengthUser": 5000.0, "GwLoss": 0.0 if scalar_maps else U(0.0, 0.3), "GwPercValue": U(0.2, 1.5)})
     return mask, raw, state
+
+
+def add_structures(S, n_reservoirs=3, n_lakes=2, seed=0):
+    """Adds reservoirs and lakes to a full_stack() dictionary: the per-structure ("CC") parameter and
+    state arrays with the reference's attribute names (hydrological_modules/reservoir.py:60-170, lakes.py:60-196), the
+    structures' LDD surgery (structures.py:43-61: cells just upstream of a structure become pits of LddKinematic, inflow
+    is gathered through `downstruct` built on the unmodified network, routing.py:151-157).  Sites are channel pixels
+    with upstream channel cells, away from outlets and from each other."""
+    from .global_modules import ldd_ops
+    rng = np.random.default_rng(seed + 555)
+    n, mask = S["N"], S["mask"]
+    ldd_kin = np.asarray(S["LddKinematic"], np.float64)
+    dsk = ldd_ops.downstream_index(ldd_kin, mask)
+    nups = np.bincount(dsk[dsk >= 0], minlength=n)
+    cand = np.flatnonzero(S["IsChannel"] & (dsk >= 0) & (nups > 0))
+    rng.shuffle(cand)
+    sites, taken = [], np.zeros(n, bool)
+    for p in cand:
+        if taken[p] or taken[dsk[p]] or taken[np.flatnonzero(dsk == p)].any():
+            continue
+        sites.append(int(p))
+        taken[p] = True
+        taken[dsk[p]] = True
+        taken[np.flatnonzero(dsk == p)] = True
+        if len(sites) == n_reservoirs + n_lakes:
+            break
+    if len(sites) < n_reservoirs + n_lakes:
+        raise ValueError("catchment too small for %d structures" % (n_reservoirs + n_lakes))
+    res = np.sort(np.array(sites[:n_reservoirs], np.int64))
+    lak = np.sort(np.array(sites[n_reservoirs:], np.int64))
+    S["downstruct"] = np.where(dsk >= 0, dsk, n).astype(np.int32)       # routing.py:151-157 (pits get N)
+    struct = np.zeros(n, bool)
+    struct[res] = True
+    struct[lak] = True
+    S["IsStructureKinematic"] = struct
+    ups = (dsk >= 0) & struct[np.maximum(dsk, 0)]                       # structures.py:51-55
+    S["IsUpsOfStructureKinematicC"] = ups
+    S["LddStructuresKinematic"] = ldd_kin.copy()
+    S["LddKinematic"] = np.where(ups, 5.0, ldd_kin)                     # structures.py:59
+    q_site = lambda idx: np.maximum(np.bincount(S["downstruct"], weights=S["ChanQ"], minlength=n + 1)[idx], 0.05)
+    R = res.size
+    if R:
+        S["simulateReservoirs"] = True
+        S["ReservoirIndex"] = res
+        sc = np.zeros(n)
+        sc[res] = np.arange(1, R + 1)
+        S["ReservoirSitesC"] = sc
+        qn = q_site(res)
+        S["TotalReservoirStorageM3CC"] = qn * 86400.0 * rng.uniform(3.0, 30.0, R)
+        S["ConservativeStorageLimitCC"] = rng.uniform(0.05, 0.15, R)
+        S["NormalStorageLimitCC"] = rng.uniform(0.4, 0.6, R)
+        S["FloodStorageLimitCC"] = rng.uniform(0.85, 0.97, R)
+        S["MinReservoirOutflowCC"] = qn * rng.uniform(0.05, 0.2, R)
+        S["NonDamagingReservoirOutflowCC"] = qn * rng.uniform(3.0, 6.0, R)
+        norm = qn * rng.uniform(0.6, 1.2, R)                              # reservoir.py:141-145
+        norm = np.where(norm > S["MinReservoirOutflowCC"], norm, S["MinReservoirOutflowCC"] + 0.01)
+        S["NormalReservoirOutflowCC"] = np.where(norm < S["NonDamagingReservoirOutflowCC"], norm,
+                                                 S["NonDamagingReservoirOutflowCC"] - 0.01)
+        S["Normal_FloodStorageLimitCC"] = S["NormalStorageLimitCC"] + 0.5 * (S["FloodStorageLimitCC"] - S["NormalStorageLimitCC"])
+        S["DeltaO"] = S["NormalReservoirOutflowCC"] - S["MinReservoirOutflowCC"]
+        S["DeltaLN"] = S["NormalStorageLimitCC"] - 2 * S["ConservativeStorageLimitCC"]
+        S["DeltaLF"] = S["FloodStorageLimitCC"] - S["NormalStorageLimitCC"]
+        S["DeltaNFL"] = S["FloodStorageLimitCC"] - S["Normal_FloodStorageLimitCC"]
+        fill = rng.uniform(0.1, 1.0, R)                                   # spans all four outflow regimes
+        S["ReservoirFillCC"] = fill
+        S["ReservoirStorageM3CC"] = fill * S["TotalReservoirStorageM3CC"]
+        S["ReservoirStorageM3"] = np.zeros(n)
+        S["ReservoirStorageM3"][res] = S["ReservoirStorageM3CC"]
+    Lk = lak.size
+    if Lk:
+        S["simulateLakes"] = True
+        S["LakeIndex"] = lak
+        sc = np.zeros(n)
+        sc[lak] = np.arange(1, Lk + 1)
+        S["LakeSitesC2"] = sc
+        ql = q_site(lak)
+        S["LakeAreaCC"] = rng.uniform(2.0e6, 5.0e7, Lk)
+        S["LakeACC"] = rng.uniform(5.0, 60.0, Lk)
+        S["LakeAvNetCC"] = ql.copy()
+        storage = S["LakeAreaCC"] * np.sqrt(S["LakeAvNetCC"] / S["LakeACC"])       # lakes.py:113-117
+        S["LakeLevelCC"] = storage / S["LakeAreaCC"]
+        S["LakeInflowOldCC"] = np.bincount(S["downstruct"], weights=S["ChanQ"], minlength=n + 1)[lak]
+        S["LakeFactor"] = S["LakeAreaCC"] / (S["DtRouting"] * np.sqrt(S["LakeACC"]))
+        S["LakeFactorSqr"] = np.square(S["LakeFactor"])
+        indicator = storage / S["DtRouting"] + S["LakeAvNetCC"] / 2
+        S["LakeOutflowCC"] = np.square(-S["LakeFactor"] + np.sqrt(S["LakeFactorSqr"] + 2 * indicator))
+        S["LakeStorageM3CC"] = storage.copy()
+        S["LakeStorageM3BalanceCC"] = storage.copy()
+        S["LakeStorageM3"] = np.zeros(n)
+        S["LakeStorageM3"][lak] = storage
+    return S

@@ -245,10 +245,82 @@ class OracleModel(object):
         v.ToChanM3Runoff = (v.UZOutflowPixel + v.LZOutflowToChannelPixel) * v.MMtoM3 + v.OFToChanM3
         v.ToChanM3RunoffDt = v.ToChanM3Runoff * v.InvNoRoutSteps
 
-    # -- routing.dynamic, routing.py:435-706 (options: kinematic wave only, no structures) -------------
-    def routing_substep(self):
+    # -- lakes.dynamic_inloop, lakes.py:199-297 (Modified Puls; per-lake "CC" arrays) ---------------------
+    def lakes_inloop(self, s):
         v = self.var
+        if s == 0:
+            v.LakeStorageM3CC = np.compress(v.LakeSitesC2 > 0, v.LakeStorageM3)
+        v.LakeInflowCC = np.bincount(v.downstruct, weights=v.ChanQ)[v.LakeIndex]
+        lake_in = (v.LakeInflowCC + v.LakeInflowOldCC) * 0.5
+        v.LakeInflowOldCC = v.LakeInflowCC.copy()
+        indicator = v.LakeStorageM3CC / v.DtRouting - 0.5 * v.LakeOutflowCC + lake_in
+        v.LakeOutflowCC = np.square(-v.LakeFactor + np.sqrt(v.LakeFactorSqr + 2 * indicator))
+        out_m3 = v.LakeOutflowCC * v.DtRouting
+        v.LakeStorageM3CC = (indicator - v.LakeOutflowCC * 0.5) * v.DtRouting
+        bad = np.isnan(v.LakeStorageM3CC) | (v.LakeStorageM3CC < 0)
+        v.LakeStorageM3CC[bad] = 0
+        v.LakeStorageM3BalanceCC = v.LakeStorageM3BalanceCC + (lake_in * v.DtRouting - out_m3)
+        v.LakeLevelCC = v.LakeStorageM3CC / v.LakeAreaCC
+        v.QLakeOutM3Dt = np.zeros(v.N)
+        np.put(v.QLakeOutM3Dt, v.LakeIndex, out_m3)
+        if s == v.NoRoutSteps - 1:
+            for name in ("LakeStorageM3Balance", "LakeStorageM3", "LakeLevel", "LakeInflowOld", "LakeOutflow"):
+                full = np.zeros(v.N)
+                np.put(full, v.LakeIndex, getattr(v, name + "CC"))
+                setattr(v, name, full)
+
+    # -- reservoir.dynamic_inloop, reservoir.py:173-322 (four-regime outflow rule) -------------------------
+    def reservoir_inloop(self, s):
+        v = self.var
+        inv_day = 1 / float(86400)
+        inflow = np.bincount(v.downstruct, weights=v.ChanQ)[v.ReservoirIndex]
+        in_m3 = inflow * v.DtRouting
+        if s == 0:
+            v.ReservoirStorageM3CC = np.compress(v.ReservoirSitesC > 0, v.ReservoirStorageM3)
+        v.ReservoirStorageM3CC = v.ReservoirStorageM3CC + in_m3
+        fill = v.ReservoirStorageM3CC / v.TotalReservoirStorageM3CC
+        o1 = np.minimum(v.MinReservoirOutflowCC, v.ReservoirStorageM3CC * inv_day)
+        o2 = v.MinReservoirOutflowCC + v.DeltaO * (fill - 2 * v.ConservativeStorageLimitCC) / v.DeltaLN
+        o3a = v.NormalReservoirOutflowCC
+        o3b = v.NormalReservoirOutflowCC + ((fill - v.Normal_FloodStorageLimitCC) / v.DeltaNFL) * (
+            v.NonDamagingReservoirOutflowCC - v.NormalReservoirOutflowCC)
+        temp = np.minimum(v.NonDamagingReservoirOutflowCC, np.maximum(inflow * 1.2, v.NormalReservoirOutflowCC))
+        o4 = np.maximum((fill - v.FloodStorageLimitCC - 0.01) * v.TotalReservoirStorageM3CC * inv_day, temp)
+        out = o1.copy()
+        out = np.where(fill > 2 * v.ConservativeStorageLimitCC, o2, out)
+        out = np.where(fill > v.NormalStorageLimitCC, o3a, out)
+        out = np.where(fill > v.Normal_FloodStorageLimitCC, o3b, out)
+        out = np.where(fill > v.FloodStorageLimitCC, o4, out)
+        temp = np.minimum(out, np.maximum(inflow, v.NormalReservoirOutflowCC))
+        out = np.where((out > 1.2 * inflow) & (out > v.NormalReservoirOutflowCC) & (fill < v.FloodStorageLimitCC), temp, out)
+        out_m3 = out * v.DtRouting
+        out_m3 = np.minimum(out_m3, v.ReservoirStorageM3CC)
+        out_m3 = np.maximum(out_m3, v.ReservoirStorageM3CC - v.TotalReservoirStorageM3CC)
+        v.ReservoirStorageM3CC = v.ReservoirStorageM3CC - out_m3
+        v.ReservoirFillCC = v.ReservoirStorageM3CC / v.TotalReservoirStorageM3CC
+        v.ReservoirFillCC[np.isnan(v.ReservoirFillCC)] = 0
+        v.ReservoirFillCC[v.ReservoirFillCC < 0] = 0
+        v.QResOutM3Dt = np.zeros(v.N)
+        np.put(v.QResOutM3Dt, v.ReservoirIndex, out_m3)
+        if s == v.NoRoutSteps - 1:
+            v.ReservoirStorageM3 = np.zeros(v.N)
+            v.ReservoirFill = np.zeros(v.N)
+            np.put(v.ReservoirStorageM3, v.ReservoirIndex, v.ReservoirStorageM3CC)
+            np.put(v.ReservoirFill, v.ReservoirIndex, v.ReservoirFillCC)
+
+    # -- routing.dynamic, routing.py:435-706 (kinematic wave; structures = lakes + reservoirs when present) ----
+    def routing_substep(self, s=0):
+        v = self.var
+        lakes_on, res_on = bool(getattr(v, "simulateLakes", False)), bool(getattr(v, "simulateReservoirs", False))
+        if lakes_on:
+            self.lakes_inloop(s)          # :441-443: lakes first, then reservoirs, both on the previous ChanQ
+        if res_on:
+            self.reservoir_inloop(s)
         side_m3 = v.ToChanM3RunoffDt.copy()
+        if lakes_on:
+            side_m3 += v.QLakeOutM3Dt     # :472-475
+        if res_on:
+            side_m3 += v.QResOutM3Dt
         side = np.where(v.IsChannelKinematic, side_m3 * v.InvChanLength * v.InvDtRouting, 0)
         if not v.SplitRouting:
             side[np.isnan(side)] = 0
@@ -300,8 +372,8 @@ class OracleModel(object):
         v = self.var
         self.surface_routing()
         v.sumDisDay = np.zeros(v.N)
-        for _ in range(v.NoRoutSteps):
-            self.routing_substep()
+        for s in range(v.NoRoutSteps):
+            self.routing_substep(s)
         v.ChanM3 = v.ChanM3Kin.copy() if not v.SplitRouting else v.ChanM3Kin + v.Chan2M3Kin - v.Chan2M3Start
         v.TotalCrossSectionArea = v.ChanM3 * v.InvChanLength
         v.sumDis = v.sumDis + v.sumDisDay

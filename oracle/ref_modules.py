@@ -115,11 +115,16 @@ def load():
         setattr(add1, n, None)
     sys.modules["lisflood.global_modules.add1"] = add1
     hm = sys.modules["lisflood.hydrological_modules"]
-    for sub in ("lakes", "reservoir", "polder", "inflow", "transmission"):
+    for sub in ("polder", "inflow", "transmission"):
         m = types.ModuleType("lisflood.hydrological_modules." + sub)
         setattr(m, sub, _NoOpSubModule)
         sys.modules[m.__name__] = m
         setattr(hm, sub, m)
+    # lakes / reservoir: the real classes (their dynamic_inloop() return at once unless the option is switched on)
+    for sub in ("lakes", "reservoir"):
+        m = ref_loader._load_module("lisflood.hydrological_modules." + sub, _R + "/hydrological_modules/%s.py" % sub)
+        setattr(hm, sub, m)
+        _mods[sub] = getattr(m, sub)
     # soilloop was imported by ref_loader before the settings stand-ins existed: rebind its globals
     sl_kernels.LisSettings, sl_kernels.MaskInfo, sl_kernels.EPICSettings = _FakeSettings, _FakeMaskInfo, _EPIC
     _mods["soilloop"] = sl_kernels.soilloop

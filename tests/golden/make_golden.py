@@ -94,6 +94,34 @@ def model_case(name, rows, cols, seed, split, steps, **kw):
     print(name, "n=%d steps=%d split=%s channel fraction %.3f" % (S["N"], steps, split, S["IsChannel"].mean()))
 
 
+STRUCTURE_KEYS = ["ReservoirStorageM3", "ReservoirFill", "QResOutM3Dt", "LakeStorageM3", "LakeLevel", "LakeOutflow",
+                  "LakeInflowOld", "LakeStorageM3Balance", "QLakeOutM3Dt"]
+STRUCTURE_KEYS_CC = ["ReservoirStorageM3CC", "ReservoirFillCC", "LakeStorageM3CC", "LakeOutflowCC", "LakeLevelCC"]
+
+
+def structures_case(name, rows, cols, seed, split, steps, n_res, n_lakes, **kw):
+    """Model steps with reservoirs and lakes in the routing sub-step loop, executed by the
+    reference's OWN classes: routing.dynamic -> lakes.dynamic_inloop / reservoir.dynamic_inloop (oracle/ref_modules.py).
+    Named structures_* (not model_*): the device path does not take structures yet, the CPU oracle does."""
+    from oracle import ref_modules
+    S = synthetic.full_stack(rows, cols, seed=seed, split_routing=split, **kw)
+    synthetic.add_structures(S, n_res, n_lakes, seed=seed)
+    M = ref_modules.RefModel(S, options={"simulateLakes": n_lakes > 0, "simulateReservoirs": n_res > 0})
+    out = {"S__" + k: np.asarray(v) for k, v in S.items()}
+    keys = MODEL_KEYS_V + MODEL_KEYS_N + (MODEL_KEYS_SPLIT if split else []) + STRUCTURE_KEYS + STRUCTURE_KEYS_CC
+    for t in range(steps):
+        F = synthetic.forcing(S, t, seed)
+        for k, v in F.items():
+            out["F%d__%s" % (t, k)] = v
+        M.step(F)
+        for k in keys:
+            out["O%d__%s" % (t, k)] = np.asarray(getattr(M.var, k)).copy()
+    out["steps"] = np.int64(steps)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "n=%d steps=%d reservoirs=%s lakes=%s fill %s" % (S["N"], steps, S["ReservoirIndex"], S["LakeIndex"],
+                                                                  np.round(M.var.ReservoirFillCC, 3)))
+
+
 def init_case(name, rows, cols, seed, split, scalar_maps=False, dt_sec=86400.0, soilless_fraction=0.03):
     """soil.initial() and routing.initial()/initialSecond() executed by the reference's OWN classes (oracle/ref_init.py)
     on raw inputs by binding name; stores inputs and every attribute they set."""
@@ -123,6 +151,10 @@ def init_case(name, rows, cols, seed, split, scalar_maps=False, dt_sec=86400.0, 
 def main():
     import warnings
     warnings.simplefilter("ignore")
+    if len(sys.argv) > 1 and sys.argv[1] == "structures":
+        structures_case("structures_40x46_single", 40, 46, 71, False, 4, 3, 2, channel_threshold=10)
+        structures_case("structures_36x44_split_6h", 36, 44, 72, True, 4, 2, 2, channel_threshold=10, dt_sec=21600.0)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "init":
         init_case("init_24x31_split", 24, 31, 61, True)
         init_case("init_19x23_single_6h", 19, 23, 62, False, scalar_maps=True, dt_sec=21600.0, soilless_fraction=0.0)
