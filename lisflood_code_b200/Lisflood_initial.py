@@ -88,6 +88,14 @@ class InitialVariables(object):
         from .global_modules.add1 import loadmap
         return loadmap(name, maskinfo=self.maskinfo)
 
+    def loadtable(self, name):
+        """A PCRaster lookup table (`TabTotStorage` ...) as a two-column array [site id, value]: from `maps` or, through
+        the settings binding, from a .npy file."""
+        if name in self.maps:
+            return np.asarray(self.maps[name], np.float64).reshape(-1, 2)
+        from .global_modules.settings import LisSettings
+        return np.load(LisSettings.instance().binding[name]).astype(np.float64).reshape(-1, 2)
+
     def _has(self, name):
         if name is None:
             return False

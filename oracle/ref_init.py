@@ -225,3 +225,67 @@ def surface_and_groundwater_initial(land_mask, raw, state, options=None, DtSec=8
     M["surface_routing"](var).initial()
     M["groundwater"](var).initial()
     return {k: v for k, v in _collect(var).items() if k not in before}
+
+
+def structures_initial(land_mask, raw, tables, state, options=None, DtSec=86400.0, DtSecChannel=3600.0):
+    """Outputs of the reference's reservoir.initial() and lakes.initial() (reservoir.py:52-170, lakes.py:52-196).
+    `tables`: binding name -> two-column array [site id, value] (PCRaster lookup tables); `state`: IsChannel,
+    IsStructureKinematic, LddKinematic, downstruct, ChanQ, DtRouting as routing.initial leaves them.  The PCRaster calls
+    (ifthen, defined, boolean, cover, downstream, lookupscalar) are stubbed on compressed arrays like in _install()."""
+    from lisflood_code_b200.global_modules import ldd_ops
+    from lisflood_code_b200.hydrological_modules.reservoir import lookupscalar as lookup_restated
+    M, loadmap = _install(raw, land_mask)
+    land = np.asarray(land_mask, bool)
+    n = int(land.sum())
+    opts = dict(options or {})
+    var = _InitVar(land_mask, raw, loadmap, opts, DtSec, DtSecChannel)
+    var.settings.binding = {k: k for k in tables}
+    for k, v in state.items():
+        setattr(var, k, np.array(v) if np.ndim(v) else v)
+
+    def makenumpy(m):
+        return np.zeros(n) + m if np.ndim(m) == 0 else np.asarray(m, np.float64)
+
+    def compress(m, *a, **k):
+        return np.asarray(m, np.float64).copy()
+
+    def decompress(a, *aa, **k):
+        return _Pcr(np.asarray(a))
+
+    fns = dict(
+        ifthen=lambda c, x: _Pcr(np.where(np.asarray(c) != 0, np.asarray(x, np.float64), np.nan)),
+        defined=lambda x: _Pcr(~np.isnan(np.asarray(x, np.float64))),
+        boolean=lambda x: _Pcr(np.nan_to_num(np.asarray(x, np.float64)) != 0),
+        cover=lambda x, y: _Pcr(np.where(np.isnan(np.asarray(x, np.float64)), y, x)),
+        lookupscalar=lambda name, sites: _Pcr(lookup_restated(tables[str(name)], np.asarray(sites, np.float64))),
+        downstream=lambda ldd, x: _Pcr(np.where(ldd_ops.downstream_index(np.asarray(ldd, np.float64), land) >= 0,
+                                                np.asarray(x)[np.maximum(ldd_ops.downstream_index(np.asarray(ldd, np.float64), land), 0)],
+                                                np.asarray(x))))
+    pcr = sys.modules["pcraster"]
+    for name in ("reservoir", "lakes"):
+        mod = sys.modules["lisflood.hydrological_modules." + name]
+        mod.loadmap, mod.compressArray, mod.decompress, mod.makenumpy = loadmap, compress, decompress, makenumpy
+        for k, f in fns.items():
+            setattr(mod, k, f)
+    saved = {k: pcr.__dict__.get(k) for k in fns}
+    for k, f in fns.items():
+        setattr(pcr, k, f)
+    try:
+        before = set(var.__dict__)
+        M["lakes"](var).initial()
+        M["reservoir"](var).initial()
+    finally:
+        for k, f in saved.items():
+            if f is None:
+                pcr.__dict__.pop(k, None)
+            else:
+                setattr(pcr, k, f)
+    out = {}
+    for k, v in var.__dict__.items():
+        if k in before and k != "IsStructureKinematic":
+            continue
+        if isinstance(v, tuple):                       # reservoir.py:155: a stray comma makes the cold-start fill a 1-tuple
+            v = np.asarray(v[0])
+        if isinstance(v, np.ndarray) and v.dtype.kind in "fiub":
+            out[k] = np.squeeze(np.asarray(v)) if v.ndim == 2 and v.shape[0] == 1 else np.asarray(v)
+    return out

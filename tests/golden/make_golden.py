@@ -122,6 +122,44 @@ def structures_case(name, rows, cols, seed, split, steps, n_res, n_lakes, **kw):
                                                                   np.round(M.var.ReservoirFillCC, 3)))
 
 
+def structures_init_case(name, rows, cols, seed, warm):
+    """reservoir.initial() and lakes.initial() executed by the reference's OWN classes (oracle/ref_init.py) on site maps
+    and lookup tables; cold start (initial values -9999) or warm start (state maps)."""
+    from oracle import ref_init
+    S = synthetic.full_stack(rows, cols, seed=seed, split_routing=False, channel_threshold=10)
+    ldd0 = S["LddKinematic"].copy()
+    synthetic.add_structures(S, 3, 3, seed=seed)
+    n, mask = S["N"], S["mask"]
+    rng = np.random.default_rng(seed)
+    res_sites, lake_sites = np.zeros(n), np.zeros(n)
+    res_sites[S["ReservoirIndex"]] = [11, 12, 13]
+    lake_sites[S["LakeIndex"]] = [5, 6, 7]
+    off = np.flatnonzero(~S["IsChannel"])[:2]
+    res_sites[off[0]], lake_sites[off[1]] = 14, 8          # sites off the channel network are dropped
+    ids_r, ids_l = np.array([11., 12., 13., 14.]), np.array([5., 6., 7., 8.])
+    T = lambda ids, lo, hi: np.stack([ids, rng.uniform(lo, hi, ids.size)], 1)
+    tables = {"TabTotStorage": T(ids_r, 1e6, 5e7), "TabConservativeStorageLimit": T(ids_r, .05, .15),
+              "TabNormalStorageLimit": T(ids_r, .4, .6), "TabFloodStorageLimit": T(ids_r, .85, .97),
+              "TabNonDamagingOutflowQ": T(ids_r, 20., 60.), "TabNormalOutflowQ": T(ids_r, 2., 70.),
+              "TabMinOutflowQ": T(ids_r, .5, 3.), "TabLakeArea": T(ids_l, 2e6, 5e7), "TabLakeA": T(ids_l, 5., 60.),
+              "TabLakeAvNetInflowEstimate": T(ids_l, .5, 20.)}
+    U = lambda lo, hi: rng.uniform(lo, hi, n)
+    raw = {"ReservoirSites": res_sites, "LakeSites": lake_sites, "adjust_Normal_Flood": 0.5, "ReservoirRnormqMult": U(.8, 1.2),
+           "LakeMultiplier": 1.1, "PrevDischarge": U(.1, 9.),
+           "ReservoirInitialFillValue": U(.2, .9) if warm else -9999.0, "LakeInitialLevelValue": U(.2, 3.) if warm else -9999.0,
+           "LakePrevInflowValue": U(.1, 9.) if warm else -9999.0, "LakePrevOutflowValue": U(.1, 9.) if warm else -9999.0}
+    state = {"IsChannel": S["IsChannel"], "IsStructureKinematic": np.zeros(n, bool), "LddKinematic": ldd0,
+             "downstruct": S["downstruct"], "ChanQ": S["ChanQ"], "DtRouting": S["DtRouting"]}
+    opts = {"simulateLakes": True, "simulateReservoirs": True}
+    out = {"mask": mask, "DtSec": np.float64(S["DtSec"])}
+    out.update({"raw__" + k: np.asarray(v) for k, v in raw.items()})
+    out.update({"table__" + k: v for k, v in tables.items()})
+    out.update({"state__" + k: np.asarray(v) for k, v in state.items()})
+    out.update({"out__" + k: v for k, v in ref_init.structures_initial(mask, raw, tables, state, opts, DtSec=S["DtSec"]).items()})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "n=%d outputs=%d" % (n, sum(k.startswith("out__") for k in out)))
+
+
 def init_case(name, rows, cols, seed, split, scalar_maps=False, dt_sec=86400.0, soilless_fraction=0.03):
     """soil.initial() and routing.initial()/initialSecond() executed by the reference's OWN classes (oracle/ref_init.py)
     on raw inputs by binding name; stores inputs and every attribute they set."""
@@ -151,6 +189,10 @@ def init_case(name, rows, cols, seed, split, scalar_maps=False, dt_sec=86400.0, 
 def main():
     import warnings
     warnings.simplefilter("ignore")
+    if len(sys.argv) > 1 and sys.argv[1] == "structinit":
+        structures_init_case("structinit_40x46_cold", 40, 46, 81, False)
+        structures_init_case("structinit_38x42_warm", 38, 42, 82, True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "structures":
         structures_case("structures_40x46_single", 40, 46, 71, False, 4, 3, 2, channel_threshold=10)
         structures_case("structures_36x44_split_6h", 36, 44, 72, True, 4, 2, 2, channel_threshold=10, dt_sec=21600.0)
