@@ -2,7 +2,7 @@
 
 Reservoirs act inside the routing sub-step loop (`dynamic_inloop`, reservoir.py:173-322).  Round 1 provides the
 parameter derivation on the host (this file; pinned to the reference's own `initial()`) and the CPU restatement of the
-sub-step rule with reference-made goldens (tests/test_oracle_structures_golden.py); the device side is planned in
+sub-step rule with reference-made goldens; the device side is planned in
 DESIGN.md §9.1, so `simulateReservoirs` is still refused by `LisSettings.check_supported()`.
 PCRaster lookup tables (`TabTotStorage` ...) are two-column arrays here: site id, value."""
 import warnings
