@@ -288,17 +288,33 @@ def run_c3(args):
         ms = _capi.timer_stop()
         barrier()
     launches = _capi.launch_count()
+    st_overlapped = M.stage_times(reset=True)
+    # Second timed region, same K steps, with the co-scheduling switched off: every stage then runs alone on the GPU, so
+    # its CUDA-event time is the kernel's own duration (in the first region the early launch of the isolated channel
+    # pixels shares the SMs with the soil stage: each stage's events then also contain the other's work).
+    M.set_option("overlap_isolated", 0)
+    M.step(Fdev[0])
+    barrier()
+    M.stage_times(reset=True)
+    _capi.timer_start()
+    for k in range(K):
+        M.step(Fdev[(k + 1) % 2])
+    ms_serial = _capi.timer_stop()
     st = M.stage_times(reset=True)
     M.soil_stats(enable_timing=True)      # one extra (untimed) step with per-kernel events in the soil stage
     M.step(Fdev[0])
     soil_stats = M.soil_stats(enable_timing=False)
+    M.set_option("overlap_isolated", 1)
     ms = max_over_ranks(ms)
     total_cells = n * world
     value = total_cells * K / (ms * 1e-3)
     if args.no_e2e:
         if rank == 0:
             print(json.dumps({"profile_only": True, "value": value, "ms_per_step": ms / K, "gpu_launches": launches,
+                              "ms_per_step_serial": ms_serial / K,
                               "stage_ms_per_step": {k: v / max(st["steps"], 1) for k, v in st.items() if k != "steps"},
+                              "stage_ms_per_step_overlapped": {k: v / max(st_overlapped["steps"], 1)
+                                                               for k, v in st_overlapped.items() if k != "steps"},
                               "soil_stats": soil_stats}))
         return
 
@@ -346,8 +362,16 @@ def run_c3(args):
     soil_gbs = ALG_BYTES_SOIL * n / (soil_ms * 1e-3) / 1e9
     chan_bytes = n * 24 * ALG_BYTES_CHANNEL_SUBSTEP
     chan_gbs = chan_bytes / (ch_ms * 1e-3) / 1e9
-    stage = {"soil_ms": round(soil_ms, 3), "overland_ms": round(of_ms, 3), "channel_ms": round(ch_ms, 3)}
-    dominant = max(stage, key=stage.get)
+    stage = {"soil_ms": round(soil_ms, 3), "overland_ms": round(of_ms, 3), "channel_ms": round(ch_ms, 3),
+             "step_ms": round(ms_serial / K, 3),
+             "note": "stages timed alone (second timed region of the same K steps, co-scheduling off)"}
+    nso = max(st_overlapped["steps"], 1)
+    stage_overlapped = {"soil_ms": round(st_overlapped["soil_ms"] / nso, 3),
+                        "overland_ms": round(st_overlapped["overland_ms"] / nso, 3),
+                        "channel_ms": round(st_overlapped["channel_ms"] / nso, 3), "step_ms": round(ms / K, 3),
+                        "note": "the timed region of `value`: the isolated non-channel pixels' sub-steps start at the top of "
+                                "the step and share the SMs with the soil and overland stages"}
+    dominant = "soil_ms" if soil_ms >= ch_ms else "channel_ms"
     traffic = None   # measured DRAM bytes of the soil stage per step from the committed ncu capture (same raster size only)
     try:
         with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_soil_stage_c3_traffic.json")) as f:
@@ -390,6 +414,7 @@ def run_c3(args):
                                 "the 10-day LAI maps stay resident"},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
                 "roofline_stencil": roof_soil, "roofline_routing": roof_chan, "stage_ms_per_step": stage,
+                "stage_ms_per_step_overlapped": stage_overlapped,
                 "soil_stats": soil_stats,
                 "cpu_baseline": cpu, "init_s": round(t_init, 2)}
         print(json.dumps(line), flush=True)
@@ -397,15 +422,27 @@ def run_c3(args):
         dist.destroy_process_group()
 
 
+class _C3Crop(object):
+    """The bench's own generator (synthetic_gpu.c3_generate: same code, seed and torch random streams as the device
+    raster) at the crop size, collected on the host -- no library call -- with a cyclic list of forcing sets."""
+
+    def __init__(self, args, rows=None, nforcing=6):
+        from lisflood_code_b200 import synthetic_gpu
+        r = rows or args.cpu_rows
+        self.S, self.F = synthetic_gpu.c3_host_stack(r, r, seed=300, nforcing=nforcing, ldd_noise=args.ldd_noise,
+                                                     no_rout_steps=24)
+
+    def forcing(self, S, i, seed=None):
+        return self.F[i % len(self.F)]
+
+
 def _c3_oracle(args, rows=None):
-    """CPU restatement of the same stack on a crop of the same generator (C3 is CPU-timed on a
-    crop and scaled per cell)."""
-    from lisflood_code_b200 import synthetic
+    """CPU restatement of the same stack on a crop-sized raster of the SAME generator (C3 is CPU-timed on
+    a crop and scaled per cell; tests/test_gpu_bench_configs.py checks the device path against it on these data)."""
     from oracle import lisf_oracle, lisf_oracle_model as om
-    r = rows or args.cpu_rows
-    S = synthetic.full_stack(r, r, seed=300, ldd_noise=args.ldd_noise)
+    crop = _C3Crop(args, rows)
     lisf_oracle.set_threads(os.cpu_count() or 1)
-    return S, om.OracleModel(S), synthetic, lisf_oracle
+    return crop.S, om.OracleModel(crop.S), crop, lisf_oracle
 
 
 def cpu_baseline_c3(args):
@@ -421,8 +458,9 @@ def cpu_baseline_c3(args):
         if best is None or dt < best[0]:
             best = (dt, thr)
     return {"value": S["N"] / best[0], "unit": "cell-updates/s", "cores": best[1], "kind": "port",
-            "sample": "1 model step (24 sub-steps) on a %dx%d crop of the same generator; C/OpenMP kernels + NumPy glue "
-                      "exactly as the reference executes them; best of the thread counts tried" % (args.cpu_rows, args.cpu_rows)}
+            "sample": "1 model step (24 sub-steps) on a %dx%d raster of the bench's own generator (synthetic_gpu.c3_generate, "
+                      "random streams on %s); C/OpenMP kernels + NumPy glue exactly as the reference executes them; best of "
+                      "the thread counts tried" % (args.cpu_rows, args.cpu_rows, S["rng_device"])}
 
 
 def run_reference_c3(args):
@@ -451,8 +489,9 @@ def run_reference_c3(args):
     dt = time.perf_counter() - t0
     value = S["N"] * args.steps / dt
     cpu = {"value": value, "unit": "cell-updates/s", "cores": nthr, "kind": "port",
-           "sample": "%d model steps (24 sub-steps each) on a %dx%d crop of the same generator, per-cell throughput; best of "
-                     "the thread counts tried" % (args.steps, args.cpu_rows, args.cpu_rows)}
+           "sample": "%d model steps (24 sub-steps each) on a %dx%d raster of the bench's own generator "
+                     "(synthetic_gpu.c3_generate, random streams on %s), per-cell throughput; best of the thread counts tried"
+                     % (args.steps, args.cpu_rows, args.cpu_rows, S["rng_device"])}
     print(json.dumps({"impl": "reference", "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s",
                       "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -182,6 +182,17 @@ int lf_model_stage_times(lf_model *m, int reset, double *soil_ms, double *overla
  * zeros in [2..6], of k_soil_pixel_flagged in [7] (all zeros unless timing was enabled by an earlier call with
  * enable_timing = 1).  Either pointer may be NULL.  Synchronises. */
 int lf_model_soil_stats(lf_model *m, int enable_timing, int64_t *deferred_columns, double *kernel_ms);
+/* Execution options of a model (name, value):
+ *   "overlap_isolated"     1 (default): lf_model_step starts the sub-steps of the non-channel isolated pixels of
+ *                          LddKinematic (no side flow, routing.py:512) at the top of the step, on a low-priority
+ *                          stream alongside the soil stage; 0: everything of the channel stage runs inside it.
+ *   "early_blocks_per_sm"  resident blocks per SM of that early launch (default 2).
+ *   "flagnancheck"         1: the `-n` option of the reference (kinematic_wave_parallel.py:180-184) for the model's
+ *                          channel discharge: a non-finite ChanQ raises a flag read by lf_model_nonfinite. */
+int lf_model_set_option(lf_model *m, const char *name, double value);
+/* *nonfinite = 1 when a NaN/Inf channel discharge was produced since the last call (needs "flagnancheck");
+ * the reference warns once and goes on (kinematic_wave_parallel.py:180-184).  Synchronises. */
+int lf_model_nonfinite(lf_model *m, int *nonfinite);
 void lf_model_destroy(lf_model *m);
 
 /* ---- The two Numba kernels of the reference as stand-alone operators (hydrological_modules/soilloop.py) ----

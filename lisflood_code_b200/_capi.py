@@ -74,6 +74,8 @@ SIGNATURES = {
     "lf_model_stage_times": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(_i64s)]),
     "lf_model_soil_stats": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "lf_model_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
+    "lf_model_nonfinite": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "lf_model_destroy": (None, [_vp]),
     "lf_interception_water_balance": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _i64s, _i64s]),
     "lf_soil_columns_water_balance": (C.c_int, [_vp]),

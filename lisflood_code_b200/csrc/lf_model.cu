@@ -10,8 +10,9 @@
 //   3. k_chan_diagonal    NoRoutSteps channel sub-steps (routing.dynamic) as ONE space-time wavefront:
 //                         side-flow assembly, kinematic solve(s), volume / discharge post-processing and
 //                         sumDisDay accumulation fused per (pixel, sub-step);
-//      k_chan_isolated    pixels without any link (the ~90 % non-channel pixels of LddKinematic) advance
-//                         through all sub-steps in registers in a single launch;
+//      k_chan_isolated_ws pixels without any link (the ~90 % non-channel pixels of LddKinematic) advance
+//                         through all sub-steps in registers; a chunk queue drained by an early launch that
+//                         shares the SMs with the soil stage and a late one in the channel stage;
 //      k_chan_post        ChanM3, TotalCrossSectionArea, ChanQAvg, sumDis, DischargeM3Out
 //                         (Lisflood_dynamic.py:194-229).
 // Storage: soil and overland maps live in the overland router's position order, channel maps in the
@@ -201,18 +202,82 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo
     }
 }
 
-// pixels with no upstream and no downstream link: all S sub-steps in registers
+// Isolated pixels that are NOT channel pixels (the bulk of LddKinematic: ~89 % of C3) receive no side flow
+// (routing.py:512), so their sub-steps do not depend on this step's runoff: they are queued in chunks of CH_THREADS
+// positions behind one atomic counter and drained by TWO launches of this kernel -- an early one with a small
+// persistent grid that shares the SMs with the soil stage (FP64 pipe and issue slots the HBM-bound stencil leaves
+// idle), and a machine-filling one in the channel stage that takes whatever is left.  Channel pixels of a chunk are
+// skipped here and handled by k_chan_isolated_list once their side flow exists.
 template <bool QZ>
-__global__ void __launch_bounds__(CH_THREADS) k_chan_isolated(ChanPtrs C, int lo, int hi)
+__global__ void __launch_bounds__(CH_THREADS) k_chan_isolated_ws(ChanPtrs C, int lo, int hi, int *__restrict__ next)
 {
-    int i = lo + blockIdx.x * CH_THREADS + threadIdx.x;
-    if (i >= hi) return;
+    __shared__ int s_chunk;
+    const int nchunks = (hi - lo + CH_THREADS - 1) / CH_THREADS;
+    for (;;) {
+        if (threadIdx.x == 0) s_chunk = atomicAdd(next, 1);
+        __syncthreads();
+        const int chunk = s_chunk;
+        __syncthreads();
+        if (chunk >= nchunks) return;
+        const int i = lo + chunk * CH_THREADS + threadIdx.x;
+        if (i >= hi || C.isChan[i]) continue;
+        ChanLocal X;
+        X.qk = C.Qk[i];
+        X.sum = 0.;
+        X.m3 = C.M3[i];
+        const double L = C.L[i], alpha = C.alpha[i], a = C.a[i];
+        double alpha2 = 0, a2 = 0, ql = 0, m3l = 0, c2s = 0, c2q = 0, z2f = 0;
+        if (C.split) {
+            if (QZ) z2f = C.z2floor[i];
+            X.m32 = C.M32[i];
+            X.q2k = C.Q2k[i];
+            alpha2 = C.alpha2[i];
+            a2 = C.a2[i];
+            ql = C.QLimit[i];
+            m3l = C.M3Limit[i];
+            c2s = C.C2M3Start[i];
+            c2q = C.C2QStart[i];
+        }
+        double qr1 = 0., qr2 = 0.;
+        const double invL = 1 / L;
+#pragma unroll 1
+        for (int s = 0; s < C.S; ++s)
+            chan_substep<QZ>(C, i, 0., 0., X, L, invL, alpha, a, 0., false, qr1, qr2, alpha2, a2, ql, m3l, c2s, c2q, z2f);
+        C.Qr0[i] = qr1;
+        C.Qr1[i] = qr1;
+        C.Qk[i] = X.qk;
+        C.sumDis[i] = X.sum;
+        C.M3[i] = X.m3;
+        C.ChanQ[i] = X.chanq;
+        if (C.split) {
+            C.Q2r0[i] = qr2;
+            C.Q2r1[i] = qr2;
+            C.Q2k[i] = X.q2k;
+            C.M32[i] = X.m32;
+            C.CS2A[i] = X.cs2a;
+            C.S1[i] = X.s1;
+            C.sumNotLast[i] = X.sumnl;
+        }
+    }
+}
+// positions of the isolated pixels that ARE channel pixels (rare: one-pixel channels), any order
+__global__ void k_chan_iso_collect(const uint8_t *__restrict__ isChan, int lo, int hi, int32_t *__restrict__ list,
+                                   int *__restrict__ count)
+{
+    int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < hi && isChan[i]) list[atomicAdd(count, 1)] = i;
+}
+template <bool QZ>
+__global__ void __launch_bounds__(CH_THREADS) k_chan_isolated_list(ChanPtrs C, const int32_t *__restrict__ list, int count)
+{
+    int k = blockIdx.x * CH_THREADS + threadIdx.x;
+    if (k >= count) return;
+    const int i = list[k];
     ChanLocal X;
     X.qk = C.Qk[i];
     X.sum = 0.;
     X.m3 = C.M3[i];
     const double L = C.L[i], alpha = C.alpha[i], a = C.a[i], sideDt = C.sideDt[i];
-    const bool isch = C.isChan[i] != 0;
     double alpha2 = 0, a2 = 0, ql = 0, m3l = 0, c2s = 0, c2q = 0, z2f = 0;
     if (C.split) {
         if (QZ) z2f = C.z2floor[i];
@@ -229,8 +294,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_isolated(ChanPtrs C, int lo
     const double invL = 1 / L;
 #pragma unroll 1
     for (int s = 0; s < C.S; ++s)
-        chan_substep<QZ>(C, i, 0., 0., X, L, invL, alpha, a, sideDt, isch, qr1, qr2, alpha2, a2, ql, m3l, c2s, c2q, z2f);
-    // the routed value of the last sub-step in both parity buffers (nobody reads it: no downstream)
+        chan_substep<QZ>(C, i, 0., 0., X, L, invL, alpha, a, sideDt, true, qr1, qr2, alpha2, a2, ql, m3l, c2s, c2q, z2f);
     C.Qr0[i] = qr1;
     C.Qr1[i] = qr1;
     C.Qk[i] = X.qk;
@@ -256,10 +320,13 @@ __global__ void k_chan_post(int n, int split, int qz, int S, double DtSec, const
                             const double *__restrict__ PixelArea_ch, double *__restrict__ ChanM3,
                             double *__restrict__ TotalCS, double *__restrict__ sumDis, double *__restrict__ ChanQAvg,
                             double *__restrict__ DischargeM3Out, double *__restrict__ FlowVelocity,
-                            double *__restrict__ TravelDistance)
+                            double *__restrict__ TravelDistance, int *__restrict__ nonfinite)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // the -n option of the reference (flagnancheck, kinematic_wave_parallel.py:180-184): non-finite discharge is
+    // reported once, it does not stop the run
+    if (nonfinite && !isfinite(ChanQ[i])) *nonfinite = 1;
     const double invL = 1 / L[i];
     const double m3 = split ? M3[i] + M32[i] - C2M3Start[i] : M3[i];
     ChanM3[i] = m3;
@@ -437,6 +504,17 @@ struct lf_model {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;   // the channel wavefront runs here, concurrently with k_chan_isolated
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // non-channel isolated pixels: chunk queue drained by an early launch (low-priority stream, alongside the soil
+    // stage) and by a late launch in the channel stage
+    cudaStream_t early_stream = nullptr;
+    cudaEvent_t ev_early_fork = nullptr, ev_early_join = nullptr;
+    lf::DevBuf<int> iso_next;             // [0] next chunk, [1] length of iso_chan_list, [2] non-finite flag
+    lf::DevBuf<int32_t> iso_chan_list;    // isolated pixels that are channel pixels
+    int iso_chan_count = 0;
+    bool iso_list_dirty = true, early_in_flight = false;
+    int overlap_isolated = 1;             // option "overlap_isolated"
+    int early_blocks_per_sm = 2;          // option "early_blocks_per_sm"
+    int nancheck = 0;                     // option "flagnancheck"
     std::map<std::string, std::unique_ptr<lf::DevBuf<double>>> async_stage;
     std::map<std::string, cudaEvent_t> async_copied, async_consumed;
     bool soil_profile = false;            // time the kernels of the soil stage individually (lf_model_soil_stats)
@@ -460,6 +538,9 @@ struct lf_model {
         for (auto &kv : async_consumed) cudaEventDestroy(kv.second);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (side_stream) cudaStreamDestroy(side_stream);
+        if (early_stream) cudaStreamDestroy(early_stream);
+        if (ev_early_fork) cudaEventDestroy(ev_early_fork);
+        if (ev_early_join) cudaEventDestroy(ev_early_join);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
     }
@@ -970,12 +1051,11 @@ int surface_stage(lf_model *m)
     return LF_OK;
 }
 
-int channel_stage(lf_model *m)
+// pointers of the channel stage (shared by the early launch of the isolated pixels and the stage itself)
+int chan_ptrs(lf_model *m, ChanPtrs &C, double **m32_out, double **c2s_out)
 {
-    cudaStream_t st = lf::stream();
     LF_CHECK(refresh_params(m));
     lf_graph *g = m->g_ch;
-    ChanPtrs C;
     memset(&C, 0, sizeof(C));
     C.n = (int32_t)m->n;
     C.lev = g->lev_of_pos.p;
@@ -998,15 +1078,15 @@ int channel_stage(lf_model *m)
     C.sideDt = side;
     LF_CHECK(internal(m, "ChanQKin__r0", CHAN, &C.Qr0));
     LF_CHECK(internal(m, "ChanQKin__r1", CHAN, &C.Qr1));
-    uint8_t *isch = nullptr, *atlast = nullptr;
+    uint8_t *isch = nullptr;
     LF_CHECK(flag_buf(m, "IsChannelKinematic", &isch));
-    LF_CHECK(flag_buf(m, "AtLastPointC", &atlast));
     C.isChan = isch;
     C.InvDtRouting = 1 / m->DtRouting;
     C.S = m->cfg.NoRoutSteps;
     C.split = m->cfg.SplitRouting;
     C.P = lfkw::make_params(m->cfg.Beta);
-    double *m32 = nullptr, *c2s = nullptr;
+    if (m32_out) *m32_out = nullptr;
+    if (c2s_out) *c2s_out = nullptr;
     if (C.split) {
         FIELD(q2k, "Chan2QKin");
         FIELD(m32_, "Chan2M3Kin");
@@ -1030,8 +1110,8 @@ int channel_stage(lf_model *m)
         C.M3Limit = ml;
         C.C2M3Start = c2s_;
         C.C2QStart = c2q;
-        m32 = m32_;
-        c2s = c2s_;
+        if (m32_out) *m32_out = m32_;
+        if (c2s_out) *c2s_out = c2s_;
         LF_CHECK(internal(m, "Chan2QKin__r0", CHAN, &C.Q2r0));
         LF_CHECK(internal(m, "Chan2QKin__r1", CHAN, &C.Q2r1));
         if (m->quintic) {
@@ -1040,26 +1120,93 @@ int channel_stage(lf_model *m)
             C.z2floor = zf;
         }
     }
+    return LF_OK;
+}
+
+int chan_streams(lf_model *m)
+{
+    if (m->side_stream) return LF_OK;
+    int prio_lo = 0, prio_hi = 0;   // high priority: its small blocks take SM slots as the big kernel's blocks retire
+    LF_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    LF_CUDA(cudaStreamCreateWithPriority(&m->side_stream, cudaStreamNonBlocking, prio_hi));
+    LF_CUDA(cudaStreamCreateWithPriority(&m->early_stream, cudaStreamNonBlocking, prio_lo));
+    LF_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    LF_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    LF_CUDA(cudaEventCreateWithFlags(&m->ev_early_fork, cudaEventDisableTiming));
+    LF_CUDA(cudaEventCreateWithFlags(&m->ev_early_join, cudaEventDisableTiming));
+    LF_CHECK(m->iso_next.alloc(4));
+    LF_CUDA(cudaMemsetAsync(m->iso_next.p, 0, 4 * sizeof(int), lf::stream()));
+    return LF_OK;
+}
+
+// Starts the sub-steps of the non-channel isolated pixels of this model step on the low-priority stream (they need
+// nothing the step computes).  Called at the top of lf_model_step; channel_stage() launches the machine-filling
+// second drain of the same queue and joins.
+int early_isolated(lf_model *m)
+{
+    m->early_in_flight = false;
+    lf_graph *g = m->g_ch;
+    const int iso_lo = (int)(m->n - g->n_isolated), iso_hi = (int)m->n;
+    if (!m->overlap_isolated || iso_hi <= iso_lo) return LF_OK;
+    cudaStream_t st = lf::stream();
+    LF_CHECK(chan_streams(m));
+    ChanPtrs C;
+    LF_CHECK(chan_ptrs(m, C, nullptr, nullptr));
+    LF_CUDA(cudaMemsetAsync(m->iso_next.p, 0, sizeof(int), st));
+    LF_CUDA(cudaEventRecord(m->ev_early_fork, st));
+    LF_CUDA(cudaStreamWaitEvent(m->early_stream, m->ev_early_fork, 0));
+    const unsigned nchunks = lf::blocks_for(iso_hi - iso_lo, CH_THREADS);
+    const unsigned grid = std::min<unsigned>(nchunks, (unsigned)(lf::sm_count() * std::max(1, m->early_blocks_per_sm)));
+    if (m->quintic) k_chan_isolated_ws<true><<<grid, CH_THREADS, 0, m->early_stream>>>(C, iso_lo, iso_hi, m->iso_next.p);
+    else k_chan_isolated_ws<false><<<grid, CH_THREADS, 0, m->early_stream>>>(C, iso_lo, iso_hi, m->iso_next.p);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaEventRecord(m->ev_early_join, m->early_stream));
+    m->early_in_flight = true;
+    return LF_OK;
+}
+
+int channel_stage(lf_model *m)
+{
+    cudaStream_t st = lf::stream();
+    lf_graph *g = m->g_ch;
+    ChanPtrs C;
+    double *m32 = nullptr, *c2s = nullptr;
+    LF_CHECK(chan_ptrs(m, C, &m32, &c2s));
+    uint8_t *atlast = nullptr;
+    LF_CHECK(flag_buf(m, "AtLastPointC", &atlast));
     // The connected network (many small, dependent launches) and the isolated pixels (one big launch) touch
     // disjoint pixels: the wavefront is issued on a side stream and overlaps the isolated kernel.
-    if (!m->side_stream) {
-        int prio_lo = 0, prio_hi = 0;   // high priority: its small blocks take SM slots as the big kernel's blocks retire
-        LF_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        LF_CUDA(cudaStreamCreateWithPriority(&m->side_stream, cudaStreamNonBlocking, prio_hi));
-        LF_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
-        LF_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
-    }
+    LF_CHECK(chan_streams(m));
     cudaStream_t sw = m->side_stream;
-    LF_CUDA(cudaEventRecord(m->ev_fork, st));
-    LF_CUDA(cudaStreamWaitEvent(sw, m->ev_fork, 0));
-    // isolated pixels (no link at all): one launch, all sub-steps in registers
     const std::vector<int32_t> &ls = g->h_level_start;
     int Lc = g->n_orders, S = C.S;
     int iso_lo = (int)(m->n - g->n_isolated), iso_hi = (int)m->n;
-    if (iso_hi > iso_lo) {
-        if (m->quintic) k_chan_isolated<true><<<lf::blocks_for(iso_hi - iso_lo, CH_THREADS), CH_THREADS, 0, st>>>(C, iso_lo, iso_hi);
-        else k_chan_isolated<false><<<lf::blocks_for(iso_hi - iso_lo, CH_THREADS), CH_THREADS, 0, st>>>(C, iso_lo, iso_hi);
+    if (iso_hi > iso_lo && m->iso_list_dirty) {   // isolated pixels that are channel pixels: compact list, rebuilt when the flags change
+        if (m->iso_chan_list.n < (size_t)(iso_hi - iso_lo)) LF_CHECK(m->iso_chan_list.alloc(iso_hi - iso_lo));
+        LF_CUDA(cudaMemsetAsync(m->iso_next.p + 1, 0, sizeof(int), st));
+        k_chan_iso_collect<<<lf::blocks_for(iso_hi - iso_lo, 256), 256, 0, st>>>(C.isChan, iso_lo, iso_hi, m->iso_chan_list.p,
+                                                                                  m->iso_next.p + 1);
         LF_LAUNCH_CHECK();
+        LF_CUDA(cudaMemcpyAsync(&m->iso_chan_count, m->iso_next.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LF_CUDA(cudaStreamSynchronize(st));
+        m->iso_list_dirty = false;
+    }
+    if (!m->early_in_flight && iso_hi > iso_lo) LF_CUDA(cudaMemsetAsync(m->iso_next.p, 0, sizeof(int), st));
+    LF_CUDA(cudaEventRecord(m->ev_fork, st));
+    LF_CUDA(cudaStreamWaitEvent(sw, m->ev_fork, 0));
+    if (iso_hi > iso_lo) {
+        // second drain of the chunk queue: fills the machine (7 resident blocks per SM at 69 registers)
+        const unsigned nchunks = lf::blocks_for(iso_hi - iso_lo, CH_THREADS);
+        const unsigned grid = std::min<unsigned>(nchunks, (unsigned)(lf::sm_count() * 8));
+        if (m->quintic) k_chan_isolated_ws<true><<<grid, CH_THREADS, 0, st>>>(C, iso_lo, iso_hi, m->iso_next.p);
+        else k_chan_isolated_ws<false><<<grid, CH_THREADS, 0, st>>>(C, iso_lo, iso_hi, m->iso_next.p);
+        LF_LAUNCH_CHECK();
+        if (m->iso_chan_count > 0) {
+            const unsigned gl = lf::blocks_for(m->iso_chan_count, CH_THREADS);
+            if (m->quintic) k_chan_isolated_list<true><<<gl, CH_THREADS, 0, st>>>(C, m->iso_chan_list.p, m->iso_chan_count);
+            else k_chan_isolated_list<false><<<gl, CH_THREADS, 0, st>>>(C, m->iso_chan_list.p, m->iso_chan_count);
+            LF_LAUNCH_CHECK();
+        }
     }
     // the connected network: space-time wavefront over (level, sub-step)
     auto level_end = [&](int l) { return l == Lc - 1 ? iso_lo : ls[l + 1]; };
@@ -1074,6 +1221,10 @@ int channel_stage(lf_model *m)
     }
     LF_CUDA(cudaEventRecord(m->ev_join, sw));
     LF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
+    if (m->early_in_flight) {
+        LF_CUDA(cudaStreamWaitEvent(st, m->ev_early_join, 0));
+        m->early_in_flight = false;
+    }
     FIELD(chm3, "ChanM3");
     FIELD(tcs, "TotalCrossSectionArea");
     FIELD(sdis, "sumDis");
@@ -1088,8 +1239,9 @@ int channel_stage(lf_model *m)
         td = td_;
         pa = pa_;
     }
-    k_chan_post<<<lf::blocks_for(m->n, 256), 256, 0, st>>>((int)m->n, C.split, m->quintic ? 1 : 0, S, m->cfg.DtSec, m3, m32, c2s, L, sd, cq, qk, atlast,
-                                                           pa, chm3, tcs, sdis, qavg, dout, fv, td);
+    k_chan_post<<<lf::blocks_for(m->n, 256), 256, 0, st>>>((int)m->n, C.split, m->quintic ? 1 : 0, S, m->cfg.DtSec, C.M3, m32, c2s, C.L,
+                                                           C.sumDis, C.ChanQ, C.Qk, atlast, pa, chm3, tcs, sdis, qavg, dout, fv, td,
+                                                           m->nancheck ? m->iso_next.p + 2 : nullptr);
     LF_LAUNCH_CHECK();
     return LF_OK;
 }
@@ -1310,6 +1462,7 @@ int lf_model_set_flags(lf_model *m, const char *name, const uint8_t *values, int
     uint8_t *dst = nullptr;
     LF_CHECK(flag_buf(m, name, &dst));
     const int32_t *pop = order == SOIL ? m->g_of->pix_of_pos.p : m->g_ch->pix_of_pos.p;
+    if (strcmp(name, "IsChannelKinematic") == 0) m->iso_list_dirty = true;
     LF_CUDA(cudaMemcpyAsync(m->stage_u8.p, values, count, cudaMemcpyDefault, st));
     k_u8_to_pos<<<lf::blocks_for((m->n + PERM_U - 1) / PERM_U, 256), 256, 0, st>>>(m->stage_u8.p, dst, pop, m->n);
     LF_LAUNCH_CHECK();
@@ -1368,6 +1521,7 @@ int lf_model_step(lf_model *m)
     }
     LF_CHECK(lf::ensure_device());
     LF_CHECK(mark(m));
+    LF_CHECK(early_isolated(m));
     LF_CHECK(soil_stage(m));
     LF_CHECK(mark(m));
     LF_CHECK(surface_stage(m));
@@ -1440,6 +1594,38 @@ int lf_model_soil_stats(lf_model *m, int enable_timing, int64_t *deferred_column
         }
     }
     m->soil_profile = enable_timing != 0;
+    return LF_OK;
+}
+
+int lf_model_set_option(lf_model *m, const char *name, double value)
+{
+    if (!m || !name) {
+        lf::set_error("lf_model_set_option: null pointer");
+        return LF_ERR_INVALID;
+    }
+    if (strcmp(name, "overlap_isolated") == 0) m->overlap_isolated = value != 0;
+    else if (strcmp(name, "early_blocks_per_sm") == 0) m->early_blocks_per_sm = (int)value;
+    else if (strcmp(name, "flagnancheck") == 0) m->nancheck = value != 0;
+    else {
+        lf::set_error("lf_model_set_option: unknown option '%s'", name);
+        return LF_ERR_INVALID;
+    }
+    return LF_OK;
+}
+
+int lf_model_nonfinite(lf_model *m, int *nonfinite)
+{
+    if (!m || !nonfinite) {
+        lf::set_error("lf_model_nonfinite: null pointer");
+        return LF_ERR_INVALID;
+    }
+    *nonfinite = 0;
+    if (!m->nancheck || !m->iso_next.p) return LF_OK;
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    LF_CUDA(cudaMemcpyAsync(nonfinite, m->iso_next.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaMemsetAsync(m->iso_next.p + 2, 0, sizeof(int), st));
+    LF_CUDA(cudaStreamSynchronize(st));
     return LF_OK;
 }
 

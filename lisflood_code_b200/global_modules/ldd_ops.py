@@ -53,7 +53,12 @@ def topological_order(ds):
     hops = np.zeros(n, np.int64)
     cur = ds.copy()
     active = cur >= 0
+    rounds = 0
     while active.any():
+        rounds += 1
+        if rounds > n:   # a pixel cannot be more than n-1 hops from its outlet: the map has a cycle (PCRaster: unsound ldd)
+            from .errors import LisfloodError
+            raise LisfloodError("the local drain direction map contains a cycle")
         hops[active] += 1
         cur[active] = ds[cur[active]]
         active = cur >= 0

@@ -77,6 +77,8 @@ class HotPathModel(object):
         self.__dict__["_rows"] = {}
         self.__dict__["NoRoutSteps"] = int(S["NoRoutSteps"])
         self.__dict__["_soil_calls"] = []
+        self.__dict__["_nancheck"] = False
+        self.__dict__["_nan_warned"] = False
         todo = dict(PARAMETERS)
         todo.update(STATE)
         if self.split:
@@ -182,6 +184,25 @@ class HotPathModel(object):
         if F is not None:
             self.set_forcing(F)
         _capi.check(_capi.lib().lf_model_step(self._h))
+        if self._nancheck:
+            self.check_finite()
+
+    def set_option(self, name, value):
+        """Execution options of lf_model_set_option ("overlap_isolated", "early_blocks_per_sm", "flagnancheck")."""
+        _capi.check(_capi.lib().lf_model_set_option(self._h, name.encode(), float(value)))
+        if name == "flagnancheck":
+            self.__dict__["_nancheck"] = bool(value)
+
+    def check_finite(self):
+        """The reference's `-n` check (kinematic_wave_parallel.py:180-184) on the channel discharge: warns ONCE."""
+        import warnings
+        from .global_modules.errors import LisfloodWarning
+        flag = C.c_int()
+        _capi.check(_capi.lib().lf_model_nonfinite(self._h, C.byref(flag)))
+        if flag.value and not self._nan_warned:
+            self.__dict__["_nan_warned"] = True
+            warnings.warn(LisfloodWarning("Non-finite discharge values found in the channel routing output"))
+        return not flag.value
 
     def stage_times(self, reset=False):
         """Device milliseconds spent in (soil, overland, channel) stages of step() since the last reset."""

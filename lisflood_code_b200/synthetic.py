@@ -261,6 +261,49 @@ def full_stack(rows, cols, seed=0, ldd_noise=0.5, mask_fraction=0.0, channel_thr
     return S
 
 
+def complete_stack(S):
+    """Adds the derived maps / scalars the reference keeps on `self.var` next to the base maps (sums over the two
+    top-soil layers, inverses, unit factors; soil.py:212-228,361-363, routing.py:184-253) to a dictionary that holds
+    only what the device model is given.  Existing keys are left untouched."""
+    n = int(S["N"])
+    D = dict(S)
+
+    def need(k, f):
+        if k not in D:
+            D[k] = f()
+
+    need("DtDay", lambda: D["DtSec"] / 86400.0)
+    need("InvDtSec", lambda: 1 / D["DtSec"])
+    need("InvDtDay", lambda: 1 / D["DtDay"])
+    need("DtRouting", lambda: D["DtSec"] / D["NoRoutSteps"])
+    need("InvDtRouting", lambda: 1 / D["DtRouting"])
+    need("InvNoRoutSteps", lambda: 1 / float(D["NoRoutSteps"]))
+    need("InvPixelLength", lambda: 1.0 / D["PixelLength"])
+    need("PixelArea", lambda: np.full(n, D["PixelLength"] ** 2))
+    need("MMtoM", lambda: 0.001)
+    need("MMtoM3", lambda: 0.001 * D["PixelArea"])
+    need("M3toMM", lambda: 1 / D["MMtoM3"])
+    need("InvBeta", lambda: 1 / D["Beta"])
+    need("kgb", lambda: 0.75 * 0.72)
+    for lay in ("1a", "1b", "2"):
+        need("GenuM" + lay, lambda: 1 / D["GenuInvM" + lay])
+        need("PoreSpaceNotZero" + lay, lambda: np.logical_and(D["SoilDepth" + lay] != 0, D["WS" + lay] != 0))
+    for nm in ("WS", "WRes", "WFC", "WWP", "W"):
+        need(nm + "1", lambda: D[nm + "1a"] + D[nm + "1b"])
+    need("SoilDepthTotal", lambda: D["SoilDepth1a"] + D["SoilDepth1b"] + D["SoilDepth2"])
+    need("PowerInfPot", lambda: (D["b_Xinanjiang"] + 1) / D["b_Xinanjiang"])
+    need("StoreMaxPervious", lambda: D["WS1"] / (D["b_Xinanjiang"] + 1))
+    need("LZInflowCUM", lambda: np.zeros(n))
+    need("InvChanLength", lambda: 1 / D["ChanLength"])
+    need("InvChannelAlpha", lambda: 1 / D["ChannelAlpha"])
+    if D.get("SplitRouting"):
+        need("InvChannelAlpha2", lambda: 1 / D["ChannelAlpha2"])
+    need("ChanQ", lambda: D["ChanQKin"].copy())
+    for nm in ("Direct", "Other", "Forest"):
+        need("OFQ" + nm, lambda: np.zeros(n))
+    return D
+
+
 def forcing(S, step, seed=0):
     """Seeded meteorological forcing of model step `step`: intermittent Gamma rain,
     ETRef/EWRef ~ U(0,6) mm/day, LAI ~ U(0,6), a few frozen pixels."""

@@ -12,17 +12,17 @@ import math
 import numpy as np
 
 
-def _ldd_gpu(torch, rows, cols, seed, noise, tilt=1.0):
-    g = torch.Generator(device="cuda")
+def _ldd_gpu(torch, rows, cols, seed, noise, tilt=1.0, device="cuda"):
+    g = torch.Generator(device=device)
     g.manual_seed(seed)
-    elev = torch.randn((rows, cols), generator=g, device="cuda", dtype=torch.float32) * noise
-    elev += tilt * torch.arange(rows - 1, -1, -1, device="cuda", dtype=torch.float32)[:, None]
-    elev += 0.05 * tilt * (torch.arange(cols, device="cuda", dtype=torch.float32) - cols / 2).abs()[None, :]
+    elev = torch.randn((rows, cols), generator=g, device=device, dtype=torch.float32) * noise
+    elev += tilt * torch.arange(rows - 1, -1, -1, device=device, dtype=torch.float32)[:, None]
+    elev += 0.05 * tilt * (torch.arange(cols, device=device, dtype=torch.float32) - cols / 2).abs()[None, :]
     big = 3.0e38
-    pad = torch.full((rows + 2, cols + 2), big, device="cuda", dtype=torch.float32)
+    pad = torch.full((rows + 2, cols + 2), big, device=device, dtype=torch.float32)
     pad[1:-1, 1:-1] = elev
-    best = torch.zeros((rows, cols), device="cuda", dtype=torch.float32)
-    code = torch.full((rows, cols), 5.0, device="cuda", dtype=torch.float64)
+    best = torch.zeros((rows, cols), device=device, dtype=torch.float32)
+    code = torch.full((rows, cols), 5.0, device=device, dtype=torch.float64)
     for dr, dc, k in [(-1, -1, 7), (-1, 0, 8), (-1, 1, 9), (0, -1, 4), (0, 1, 6), (1, -1, 1), (1, 0, 2), (1, 1, 3)]:
         nb = pad[1 + dr:1 + dr + rows, 1 + dc:1 + dc + cols]
         drop = (elev - nb) / math.sqrt(dr * dr + dc * dc)
@@ -35,11 +35,191 @@ def _ldd_gpu(torch, rows, cols, seed, noise, tilt=1.0):
     return code.reshape(-1)
 
 
+def _host_accuflux_ones(ldd, rows, cols):
+    """Upstream area (cells) on the host: the library-free twin of lf_graph_accuflux(ones) for the CPU arm."""
+    from .global_modules import ldd_ops
+    mask = np.ones((rows, cols), bool)
+    ds = ldd_ops.downstream_index(ldd, mask)
+    return ldd_ops.accuflux(ds, np.ones(rows * cols))
+
+
+def c3_generate(torch, rows, cols, seed, emit, ldd_noise=0.5, channel_threshold=60, no_rout_steps=24, dt_sec=86400.0,
+                diagnostics=False, accuflux=None, device="cuda"):
+    """The C3 generator: every map of the catchment, one after the other, handed to `emit(kind, name, value)`.
+
+    kind "config": value = dict of the scalars + the mask / LddToChan / LddKinematic tensors (first call);
+    kind "map": float64 tensor, (n,) or (3, n), compressed order; kind "flags": uint8 (n,).
+    The same code feeds the device model of bench.py (C3Device) and the host dictionary of the CPU arm / the
+    parity test (c3_host_stack): same distributions, same seeds, same random streams on the same torch device.
+    accuflux(ldd_tensor) -> upstream area tensor; default: the host operator."""
+    n = rows * cols
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + 4242)
+    U = lambda lo, hi, shape=(n,): torch.rand(shape, generator=g, device=device, dtype=torch.float64) * (hi - lo) + lo
+    ldd = _ldd_gpu(torch, rows, cols, seed, ldd_noise, device=device)
+    mask = torch.ones(n, dtype=torch.uint8, device=device)
+    if accuflux is None:
+        uparea = torch.from_numpy(_host_accuflux_ones(ldd.cpu().numpy(), rows, cols)).to(device)
+    else:
+        uparea = accuflux(ldd, mask)
+    is_chan = uparea >= channel_threshold
+    ldd_kin = torch.where(is_chan, ldd, torch.zeros_like(ldd))
+    ldd_toc = torch.where(is_chan, torch.full_like(ldd, 5.0), ldd)
+    S = {"rows": rows, "cols": cols, "N": n, "mask_device": mask, "LddToChan": ldd_toc, "LddKinematic": ldd_kin,
+         "DtSec": dt_sec, "Beta": 0.6, "PixelLength": 5000.0, "NoRoutSteps": no_rout_steps, "SplitRouting": False,
+         "CourantCrit": 0.4, "AvWaterThreshold": 5.0 * dt_sec / 86400.0, "LeafDrainageK": min(dt_sec / 86400.0, 1.0),
+         "DrainedFraction": 0.0, "SMaxSealed": 1.0}
+    emit("config", "S", S)
+    del ldd_kin, ldd_toc
+    put = lambda name, t: emit("map", name, t.contiguous())
+    dtday = dt_sec / 86400.0
+    beta, alppow = 0.6, 2.0 / 3.0 * 0.6
+    # ---- fractions (normalised gammas == Dirichlet) ----
+    conc = torch.tensor([4.0, 3.0, 1.0, 0.6, 0.3], device=device, dtype=torch.float64)
+    fr = torch._standard_gamma(conc[:, None].expand(5, n).contiguous(), generator=g)
+    fr = fr / fr.sum(0, keepdim=True)
+    put("SoilFraction", fr[:3])
+    put("DirectRunoffFraction", fr[3])
+    put("WaterFraction", fr[4])
+    del fr
+
+    def lu3(a, b):
+        return torch.stack([a, b, a]).contiguous()
+
+    # ---- soil hydraulic parameters (soil.py:109-228); Irrigated shares the Rainfed maps ----
+    for lay, (d_lo, d_hi) in (("1a", (40, 60)), ("1b", (200, 300)), ("2", (500, 900))):
+        if lay == "2":
+            x = U(d_lo, d_hi)
+            depth = lu3(x, x)
+            mk = lambda lo, hi, log=False: (lambda t: lu3(t, t))(torch.exp(U(math.log(lo), math.log(hi))) if log else U(lo, hi))
+        else:
+            depth = lu3(U(d_lo, d_hi), U(d_lo, d_hi))
+            mk = lambda lo, hi, log=False: lu3(torch.exp(U(math.log(lo), math.log(hi))) if log else U(lo, hi),
+                                               torch.exp(U(math.log(lo), math.log(hi))) if log else U(lo, hi))
+        ths, thr, lam, gal, ks = mk(.4, .5), mk(.02, .08), mk(.15, .45), mk(.005, .05), mk(1.0, 500.0, True)
+        gn = 1 + lam
+        gm = lam / gn
+        ws, wres = ths * depth, thr * depth
+        mual = lambda h: wres + (ws - wres) / ((1 + (gal * h) ** gn) ** gm)
+        wfc_l, wwp_l = mual(100), mual(15000)
+        put("KSat" + lay, ks)
+        put("GenuInvM" + lay, 1 / gm)
+        put("WRes" + lay, wres)
+        put("WS" + lay, ws)
+        if lay != "2" or diagnostics:
+            put("WWP" + lay, wwp_l)
+            put("WFC" + lay, wfc_l)
+        if diagnostics:
+            put("SoilDepth" + lay, depth)
+        # initial soil moisture ~ field capacity (soil.py:268-277)
+        w = torch.minimum(wfc_l * U(0.7, 1.1, (3, n)), ws)
+        put("W" + lay, w)
+        del depth, ths, thr, lam, gal, ks, gn, gm, ws, wres, wfc_l, wwp_l, w
+    put("b_Xinanjiang", U(.1, .7))
+    put("PowerPrefFlow", U(1.0, 5.0))
+    put("CropCoef", torch.stack([U(.9, 1.1), U(.9, 1.3), U(.9, 1.2)]))
+    put("CropGroupNumber", torch.stack([U(1.0, 5.0), U(2.0, 5.0), U(1.0, 5.0)]))
+    # ---- groundwater ----
+    put("UpperZoneK", torch.clamp(dtday * (1 / U(5.0, 20.0)), max=1.0))
+    put("LowerZoneK", torch.clamp(dtday * (1 / U(50.0, 500.0)), max=1.0))
+    put("GwPercStep", U(0.2, 1.5) * dtday)
+    put("GwLossStep", torch.zeros(n, dtype=torch.float64, device=device))
+    put("LZThreshold", U(0.0, 20.0))
+    put("UZ", U(0.0, 10.0, (3, n)))
+    put("LZ", U(20.0, 200.0))
+    put("DSLR", torch.floor(U(1.0, 6.0, (3, n))))
+    put("CumInterception", U(0.0, 0.5, (3, n)))
+    put("CumInterSealed", U(0.0, 0.5))
+    pa = torch.full((n,), 5000.0 ** 2, dtype=torch.float64, device=device)
+    put("MMtoM3", 0.001 * pa)
+    if diagnostics:
+        put("PixelArea", pa)
+    del pa
+    # ---- channel geometry (routing.py:184-253) ----
+    chan_len = 5000.0 * U(1.0, 1.4)
+    grad = torch.clamp(U(1e-4, 5e-3), min=1e-5)
+    man = U(0.02, 0.06)
+    width = 2.0 + 0.5 * torch.sqrt(uparea)
+    dthr = 0.5 + 0.05 * torch.sqrt(uparea)
+    upper = width + 2 * 1.0 * dthr
+    half_bank = 0.5 * (0.5 * dthr * (upper + width))
+    wd = torch.where(is_chan, 0.5 * dthr, torch.zeros_like(dthr))
+    wp = width + 2 * torch.sqrt(wd * wd + (wd * 1.0) ** 2)
+    alpha = ((man / torch.sqrt(grad)) ** beta) * (wp ** alppow)
+    put("ChanLength", chan_len)
+    put("ChannelAlpha", alpha)
+    put("ChanM3Kin", half_bank * chan_len)
+    qk = (half_bank / alpha) ** (1 / beta)
+    put("ChanQKin", qk)
+    put("ChanQ", qk)
+    del chan_len, grad, man, width, dthr, upper, half_bank, wd, wp, alpha, qk, uparea
+    # ---- overland flow (surface_routing.py:69-83) ----
+    ograd = torch.clamp(U(1e-3, 0.1), min=1e-4)
+    nman = torch.stack([U(0.05, 0.2), U(0.1, 0.4), torch.full((n,), 0.02, dtype=torch.float64, device=device)])
+    put("OFAlpha", ((nman / torch.sqrt(ograd)) ** beta) * ((5000.0 + 2 * 0.001 * 5.0) ** alppow))
+    del ograd, nman
+    is_chan_u8 = is_chan.to(torch.uint8)
+    emit("flags", "IsChannel", is_chan_u8)
+    emit("flags", "IsChannelKinematic", is_chan_u8)
+    emit("flags", "AtLastPointC", (ldd == 5.0).to(torch.uint8))
+    emit("stat", "channel_fraction", float(is_chan.double().mean().item()))
+    return g
+
+
+def c3_forcing(torch, g, n, dt_sec, device="cuda"):
+    """Forcing of one model step from the generator's random stream (tensors on `device`)."""
+    R = lambda shape=(n,): torch.rand(shape, generator=g, device=device, dtype=torch.float64)
+    dtday = dt_sec / 86400.0
+    rain = torch.where(R() < 0.45, torch._standard_gamma(torch.full((n,), 0.8, device=device, dtype=torch.float64),
+                                                         generator=g) * 8.0,
+                       torch.zeros(n, device=device, dtype=torch.float64)) * dtday
+    F = {"Rain": rain, "SnowMelt": torch.where(R() < 0.1, R() * 3.0, torch.zeros_like(rain)) * dtday,
+         "ETRef": R() * 6.0 * dtday, "EWRef": R() * 6.0 * dtday, "LAI": R((3, n)) * 6.0,
+         "isFrozenSoil": (R() < 0.05).to(torch.uint8)}
+    F["ESRef"] = (F["EWRef"] + F["ETRef"]) / 2
+    F["LAITerm"] = torch.exp(-(0.75 * 0.72) * F["LAI"])
+    return F
+
+
+def c3_host_stack(rows, cols, seed=0, nforcing=0, device=None, **kw):
+    """The same generator collected into host NumPy arrays: (S, [F0, F1, ...]) with S complete for the CPU restatement
+    of the step (synthetic.complete_stack adds the derived maps).  No library call: usable by the CPU arm of bench.py.
+    device: torch device of the random streams (default: cuda when available -- the streams of the bench's own raster)."""
+    import torch
+    from . import synthetic
+    if device is None:
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+    S = {}
+
+    def emit(kind, name, value):
+        if kind == "config":
+            for k, v in value.items():
+                if k == "mask_device":
+                    S["mask"] = v.cpu().numpy().astype(bool).reshape(rows, cols)
+                else:
+                    S[k] = v.cpu().numpy() if hasattr(v, "cpu") else v
+        elif kind == "map":
+            S[name] = value.cpu().numpy()
+        elif kind == "flags":
+            S[name] = value.cpu().numpy().astype(bool)
+
+    kw.setdefault("diagnostics", True)    # the CPU restatement wants every parameter map
+    g = c3_generate(torch, rows, cols, seed, emit, device=device, **kw)
+    S = synthetic.complete_stack(S)
+    F = []
+    for _ in range(nforcing):
+        f = c3_forcing(torch, g, rows * cols, S["DtSec"], device)
+        F.append({k: (v.cpu().numpy().astype(bool) if k == "isFrozenSoil" else v.cpu().numpy()) for k, v in f.items()})
+    S["rng_device"] = device
+    return S, F
+
+
 class C3Device(object):
-    """Builds a HotPathModel for a rows x cols catchment entirely on the device."""
+    """Builds a HotPathModel for a rows x cols catchment entirely on the device.  keep_host=True also keeps a host copy
+    of everything handed to the model (parity test of the bench's own data on a crop-sized raster)."""
 
     def __init__(self, rows, cols, seed=0, ldd_noise=0.5, channel_threshold=60, no_rout_steps=24, dt_sec=86400.0,
-                 diagnostics=False):
+                 diagnostics=False, keep_host=False):
         import torch
         from . import _capi
         from .hotpath import HotPathModel
@@ -47,140 +227,52 @@ class C3Device(object):
         L = _capi.lib()
         n = rows * cols
         self.n, self.rows, self.cols = n, rows, cols
-        g = torch.Generator(device="cuda")
-        g.manual_seed(seed + 4242)
-        self.gen = g
-        U = lambda lo, hi, shape=(n,): torch.rand(shape, generator=g, device="cuda", dtype=torch.float64) * (hi - lo) + lo
-        ldd = _ldd_gpu(torch, rows, cols, seed, ldd_noise)
-        mask = torch.ones(n, dtype=torch.uint8, device="cuda")
-        # upstream area on the full LDD -> channel mask (routing.py:98, 110-118)
-        gh = C.c_void_p()
-        _capi.check(L.lf_ldd_build(_capi.ptr(ldd), _capi.ptr(mask), rows, cols, C.byref(gh)))
-        ones = torch.ones(n, dtype=torch.float64, device="cuda")
-        uparea = torch.empty(n, dtype=torch.float64, device="cuda")
-        _capi.check(L.lf_graph_accuflux(gh, _capi.ptr(ones), _capi.ptr(uparea)))
-        no, k, npx, pits = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
-        _capi.check(L.lf_graph_info(gh, C.byref(npx), C.byref(no), C.byref(k), C.byref(pits)))
-        self.ldd_levels, self.ldd_pits = no.value, pits.value
-        L.lf_graph_destroy(gh)
-        del ones
-        is_chan = uparea >= channel_threshold
-        ldd_kin = torch.where(is_chan, ldd, torch.zeros_like(ldd))
-        ldd_toc = torch.where(is_chan, torch.full_like(ldd, 5.0), ldd)
-        S = {"rows": rows, "cols": cols, "N": n, "mask_device": mask, "LddToChan": ldd_toc, "LddKinematic": ldd_kin,
-             "DtSec": dt_sec, "Beta": 0.6, "PixelLength": 5000.0, "NoRoutSteps": no_rout_steps, "SplitRouting": False,
-             "CourantCrit": 0.4, "AvWaterThreshold": 5.0 * dt_sec / 86400.0, "LeafDrainageK": min(dt_sec / 86400.0, 1.0),
-             "DrainedFraction": 0.0, "SMaxSealed": 1.0}
-        self.S = S
-        M = HotPathModel(S, diagnostics=diagnostics)
-        self.model = M
-        del ldd_kin, ldd_toc
-        dtday = dt_sec / 86400.0
-        beta, alppow = 0.6, 2.0 / 3.0 * 0.6
-        # ---- fractions (normalised gammas == Dirichlet) ----
-        conc = torch.tensor([4.0, 3.0, 1.0, 0.6, 0.3], device="cuda", dtype=torch.float64)
-        fr = torch._standard_gamma(conc[:, None].expand(5, n).contiguous())
-        fr = fr / fr.sum(0, keepdim=True)
-        M.set("SoilFraction", fr[:3].contiguous(), 3)
-        M.set("DirectRunoffFraction", fr[3].contiguous())
-        M.set("WaterFraction", fr[4].contiguous())
-        del fr
+        self.host = {} if keep_host else None
 
-        def lu3(a, b):
-            return torch.stack([a, b, a]).contiguous()
+        def accuflux(ldd, mask):
+            # upstream area on the full LDD -> channel mask (routing.py:98, 110-118)
+            gh = C.c_void_p()
+            _capi.check(L.lf_ldd_build(_capi.ptr(ldd), _capi.ptr(mask), rows, cols, C.byref(gh)))
+            ones = torch.ones(n, dtype=torch.float64, device="cuda")
+            uparea = torch.empty(n, dtype=torch.float64, device="cuda")
+            _capi.check(L.lf_graph_accuflux(gh, _capi.ptr(ones), _capi.ptr(uparea)))
+            no, k, npx, pits = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+            _capi.check(L.lf_graph_info(gh, C.byref(npx), C.byref(no), C.byref(k), C.byref(pits)))
+            self.ldd_levels, self.ldd_pits = no.value, pits.value
+            L.lf_graph_destroy(gh)
+            return uparea
 
-        # ---- soil hydraulic parameters (soil.py:109-228); Irrigated shares the Rainfed maps ----
-        ws1 = wfc = None
-        store = {}
-        for lay, (d_lo, d_hi) in (("1a", (40, 60)), ("1b", (200, 300)), ("2", (500, 900))):
-            if lay == "2":
-                x = U(d_lo, d_hi)
-                depth = lu3(x, x)
-                mk = lambda lo, hi, log=False: (lambda t: lu3(t, t))(torch.exp(U(math.log(lo), math.log(hi))) if log else U(lo, hi))
-            else:
-                depth = lu3(U(d_lo, d_hi), U(d_lo, d_hi))
-                mk = lambda lo, hi, log=False: lu3(torch.exp(U(math.log(lo), math.log(hi))) if log else U(lo, hi),
-                                                   torch.exp(U(math.log(lo), math.log(hi))) if log else U(lo, hi))
-            ths, thr, lam, gal, ks = mk(.4, .5), mk(.02, .08), mk(.15, .45), mk(.005, .05), mk(1.0, 500.0, True)
-            gn = 1 + lam
-            gm = lam / gn
-            ws, wres = ths * depth, thr * depth
-            mual = lambda h: wres + (ws - wres) / ((1 + (gal * h) ** gn) ** gm)
-            wfc_l, wwp_l = mual(100), mual(15000)
-            M.set("KSat" + lay, ks, 3)
-            M.set("GenuInvM" + lay, (1 / gm).contiguous(), 3)
-            M.set("WRes" + lay, wres, 3)
-            M.set("WS" + lay, ws, 3)
-            if lay != "2" or diagnostics:
-                M.set("WWP" + lay, wwp_l, 3)
-                M.set("WFC" + lay, wfc_l, 3)
-            if diagnostics:
-                M.set("SoilDepth" + lay, depth, 3)
-            # initial soil moisture ~ field capacity (soil.py:268-277)
-            w = torch.minimum(wfc_l * U(0.7, 1.1, (3, n)), ws)
-            M.set("W" + lay, w.contiguous(), 3)
-            del depth, ths, thr, lam, gal, ks, gn, gm, ws, wres, wfc_l, wwp_l, w
-        M.set("b_Xinanjiang", U(.1, .7))
-        M.set("PowerPrefFlow", U(1.0, 5.0))
-        M.set("CropCoef", torch.stack([U(.9, 1.1), U(.9, 1.3), U(.9, 1.2)]).contiguous(), 3)
-        M.set("CropGroupNumber", torch.stack([U(1.0, 5.0), U(2.0, 5.0), U(1.0, 5.0)]).contiguous(), 3)
-        # ---- groundwater ----
-        M.set("UpperZoneK", torch.clamp(dtday * (1 / U(5.0, 20.0)), max=1.0))
-        M.set("LowerZoneK", torch.clamp(dtday * (1 / U(50.0, 500.0)), max=1.0))
-        M.set("GwPercStep", U(0.2, 1.5) * dtday)
-        M.set("GwLossStep", torch.zeros(n, dtype=torch.float64, device="cuda"))
-        M.set("LZThreshold", U(0.0, 20.0))
-        M.set("UZ", U(0.0, 10.0, (3, n)), 3)
-        M.set("LZ", U(20.0, 200.0))
-        M.set("DSLR", torch.floor(U(1.0, 6.0, (3, n))), 3)
-        M.set("CumInterception", U(0.0, 0.5, (3, n)), 3)
-        M.set("CumInterSealed", U(0.0, 0.5))
-        pa = torch.full((n,), 5000.0 ** 2, dtype=torch.float64, device="cuda")
-        M.set("MMtoM3", 0.001 * pa)
-        if diagnostics:
-            M.set("PixelArea", pa)
-        del pa
-        # ---- channel geometry (routing.py:184-253) ----
-        chan_len = 5000.0 * U(1.0, 1.4)
-        grad = torch.clamp(U(1e-4, 5e-3), min=1e-5)
-        man = U(0.02, 0.06)
-        width = 2.0 + 0.5 * torch.sqrt(uparea)
-        dthr = 0.5 + 0.05 * torch.sqrt(uparea)
-        upper = width + 2 * 1.0 * dthr
-        half_bank = 0.5 * (0.5 * dthr * (upper + width))
-        wd = torch.where(is_chan, 0.5 * dthr, torch.zeros_like(dthr))
-        wp = width + 2 * torch.sqrt(wd * wd + (wd * 1.0) ** 2)
-        alpha = ((man / torch.sqrt(grad)) ** beta) * (wp ** alppow)
-        M.set("ChanLength", chan_len)
-        M.set("ChannelAlpha", alpha)
-        M.set("ChanM3Kin", half_bank * chan_len)
-        qk = (half_bank / alpha) ** (1 / beta)
-        M.set("ChanQKin", qk)
-        M.set("ChanQ", qk)
-        del chan_len, grad, man, width, dthr, upper, half_bank, wd, wp, alpha, qk, uparea
-        # ---- overland flow (surface_routing.py:69-83) ----
-        ograd = torch.clamp(U(1e-3, 0.1), min=1e-4)
-        nman = torch.stack([U(0.05, 0.2), U(0.1, 0.4), torch.full((n,), 0.02, dtype=torch.float64, device="cuda")])
-        M.set("OFAlpha", (((nman / torch.sqrt(ograd)) ** beta) * ((5000.0 + 2 * 0.001 * 5.0) ** alppow)).contiguous(), 3)
-        del ograd, nman
-        is_chan_u8 = is_chan.to(torch.uint8)
-        M.set_flags("IsChannel", is_chan_u8)
-        M.set_flags("IsChannelKinematic", is_chan_u8)
-        M.set_flags("AtLastPointC", (ldd == 5.0).to(torch.uint8))
-        self.channel_fraction = float(is_chan.double().mean().item())
-        del is_chan, is_chan_u8, ldd
+        def emit(kind, name, value):
+            if kind == "config":
+                self.S = value
+                self.model = HotPathModel(value, diagnostics=diagnostics)
+                if keep_host:
+                    for k, v in value.items():
+                        if k == "mask_device":
+                            self.host["mask"] = v.cpu().numpy().astype(bool).reshape(rows, cols)
+                        else:
+                            self.host[k] = v.cpu().numpy() if hasattr(v, "cpu") else v
+            elif kind == "map":
+                self.model.set(name, value, 3 if value.dim() == 2 else 1)
+                if keep_host:
+                    self.host[name] = value.cpu().numpy()
+            elif kind == "flags":
+                self.model.set_flags(name, value)
+                if keep_host:
+                    self.host[name] = value.cpu().numpy().astype(bool)
+            elif kind == "stat":
+                setattr(self, name, value)
+
+        self.gen = c3_generate(torch, rows, cols, seed, emit, ldd_noise=ldd_noise, channel_threshold=channel_threshold,
+                               no_rout_steps=no_rout_steps, dt_sec=dt_sec, diagnostics=diagnostics or keep_host,
+                               accuflux=accuflux)
         torch.cuda.empty_cache()
 
     def forcing_device(self, step):
         """Forcing of one step as CUDA tensors (device-resident leg)."""
-        torch, n, g = self.torch, self.n, self.gen
-        R = lambda shape=(n,): torch.rand(shape, generator=g, device="cuda", dtype=torch.float64)
-        dtday = self.S["DtSec"] / 86400.0
-        rain = torch.where(R() < 0.45, torch._standard_gamma(torch.full((n,), 0.8, device="cuda", dtype=torch.float64)) * 8.0,
-                           torch.zeros(n, device="cuda", dtype=torch.float64)) * dtday
-        F = {"Rain": rain, "SnowMelt": torch.where(R() < 0.1, R() * 3.0, torch.zeros_like(rain)) * dtday,
-             "ETRef": R() * 6.0 * dtday, "EWRef": R() * 6.0 * dtday, "LAI": R((3, n)) * 6.0,
-             "isFrozenSoil": (R() < 0.05).to(torch.uint8)}
-        F["ESRef"] = (F["EWRef"] + F["ETRef"]) / 2
-        F["LAITerm"] = torch.exp(-(0.75 * 0.72) * F["LAI"])
-        return F
+        return c3_forcing(self.torch, self.gen, self.n, self.S["DtSec"])
+
+    def host_stack(self):
+        """Host copy of the model's inputs completed with the derived maps (keep_host=True)."""
+        from . import synthetic
+        return synthetic.complete_stack(dict(self.host))

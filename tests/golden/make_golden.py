@@ -186,9 +186,38 @@ def init_case(name, rows, cols, seed, split, scalar_maps=False, dt_sec=86400.0, 
                                                       sum(k.startswith("routing__") for k in out)))
 
 
+def adversarial_case(kwp, name, beta):
+    """Inputs chosen against the solver's stopping rule (kinematic_wave_parallel_tools.py:73-80): discharges up to 1e9
+    (the 1e-12 absolute tolerance is far below one ulp there, so the reference leaves its loop through `Q == previous`
+    or wanders between two neighbouring values for 3000 iterations), down to 1e-13 (the tolerance is met by the initial
+    guess), alpha / dx / dt over six decades, negative and zero side flow, long chains and wide confluences."""
+    rng = np.random.default_rng(977)
+    rows, cols = 24, 160
+    ldd = np.full((rows, cols), 6.0)            # every row is a chain to the east ...
+    ldd[:, -1] = 2.0                            # ... collected by the last column
+    ldd[-1, -1] = 5.0
+    ldd[::3, ::7] = 5.0                         # some pits: short chains, isolated pixels
+    mask = np.ones((rows, cols), bool)
+    n = rows * cols
+    logu = lambda lo, hi: np.exp(rng.uniform(np.log(lo), np.log(hi), n))
+    alpha = logu(1e-3, 1e3)
+    dx = logu(10.0, 1e5)
+    q0 = logu(1e-13, 1e9)
+    q0[rng.random(n) < 0.1] = 0.0
+    q = np.where(rng.random(n) < 0.5, logu(1e-12, 1e2), -logu(1e-9, 1e-2))
+    q[rng.random(n) < 0.1] = 0.0
+    routing_case(kwp, name, rows, cols, 977, 0, 0, True, 5, False, beta=beta, dt=600.0, ldd=ldd, mask=mask, alpha=alpha, q0=q0,
+                 q=q, dx=dx)
+
+
 def main():
     import warnings
     warnings.simplefilter("ignore")
+    if len(sys.argv) > 1 and sys.argv[1] == "adversarial":
+        kwpt, kwp, sl = ref_loader.load()
+        adversarial_case(kwp, "kwadv_24x160_beta06", 0.6)
+        adversarial_case(kwp, "kwadv_24x160_beta07", 0.7)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "structinit":
         structures_init_case("structinit_40x46_cold", 40, 46, 81, False)
         structures_init_case("structinit_38x42_warm", 38, 42, 82, True)

@@ -57,6 +57,29 @@ def test_golden_routing(gpu_lib, case):
     assert rel_err(kw.get_discharge(), g["Q_main"][-1]) < TOL
 
 
+@pytest.mark.parametrize("case", golden_cases("kwadv_"))
+def test_solver_stopping_rule_adversarial(gpu_lib, case):
+    """Inputs chosen against the stopping rule (tests/golden/make_golden.py::adversarial_case): discharges from 1e-13
+    to 1e9, where the reference leaves its Newton loop through `Q == previous` or wanders between two neighbouring
+    values until its 3000-iteration cap (kinematic_wave_parallel_tools.py:73-80), while the device solver also stops
+    when the relative Newton step is <= 1e-8 (lf_kw_solve.cuh).  The values the UNMODIFIED reference returned are the
+    golden; the device result may differ from them only at the rounding level."""
+    g = load_golden(case)
+    kw = _kw(gpu_lib)(g["ldd"], g["mask"], g["alpha"], float(g["beta"]), _dx(g), float(g["dt"]))
+    Q = g["q0"].copy()
+    worst = 0.0
+    for s in range(g["Q_main"].shape[0]):
+        kw.kinematicWaveRouting(Q, g["q"])
+        assert np.array_equal(Q == 0, g["Q_main"][s] == 0), (case, s)     # the dry / wet decision is the reference's
+        worst = max(worst, rel_err(Q, g["Q_main"][s]))
+    print("%s: worst rel. deviation from the reference %.2e" % (case, worst))
+    assert worst < 1e-12, (case, worst)
+    kw.set_discharge(g["q0"])
+    kw.set_lateral_inflow(g["q"])
+    kw.run(g["Q_main"].shape[0])
+    assert rel_err(kw.get_discharge(), g["Q_main"][-1]) < 1e-12
+
+
 @pytest.mark.parametrize("rows,cols,noise,maskf,seed,dxmap", [
     (257, 190, 3.0, 0.0, 21, True),     # shallow forest
     (300, 211, 0.3, 0.15, 22, False),   # deep trees with holes

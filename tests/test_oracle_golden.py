@@ -40,6 +40,18 @@ def test_routing_matches_reference(oracle, case):
             assert rel_err(Q2, g["Q_fp"][s]) < 1e-11, (case, s)
 
 
+@pytest.mark.parametrize("case", golden_cases("kwadv_"))
+def test_routing_adversarial_inputs(oracle, case):
+    """Stopping-rule stress (tests/golden/make_golden.py::adversarial_case): Q from 1e-13 to 1e9, alpha / dx over six decades."""
+    g = load_golden(case)
+    kw = oracle.KinematicWaveOracle(g["ldd"], g["mask"], g["alpha"], float(g["beta"]), _dx(g), float(g["dt"]))
+    Q = g["q0"].copy()
+    for s in range(g["Q_main"].shape[0]):
+        kw.kinematicWaveRouting(Q, g["q"], "main_channel")
+        assert np.array_equal(Q == 0, g["Q_main"][s] == 0)
+        assert rel_err(Q, g["Q_main"][s]) < 1e-13, (case, s)
+
+
 def test_known_answer_vector(oracle):
     """4x4, all south; rows after one call = 0.31022586, 0.5392451, 0.71516453, 0.85306031."""
     g = load_golden("kw_4x4_south")
