@@ -246,6 +246,8 @@ def run_c3(args):
     t0 = time.time()
     dev = C3Device(rows, cols, seed=300 + rank, ldd_noise=args.ldd_noise, no_rout_steps=24)
     M = dev.model
+    if os.environ.get("LF_EARLY_BPS"):      # tuning runs: resident blocks per SM of the early isolated-pixel launch
+        M.set_option("early_blocks_per_sm", int(os.environ["LF_EARLY_BPS"]))
     _capi.synchronize()
     t_init = time.time() - t0
     info = M.info()

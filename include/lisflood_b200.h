@@ -41,6 +41,7 @@ extern "C" {
 typedef struct lf_graph lf_graph;   /* D8 drainage graph + routing order, device resident */
 typedef struct lf_router lf_router; /* one kinematicWave object */
 typedef struct lf_model lf_model;   /* full hot-path step: soil -> overland -> channel sub-steps */
+typedef struct lf_xchg lf_xchg;     /* exchange region of one rank (LDD-cut decomposition across the GPUs of a node) */
 
 const char *lf_last_error(void);
 int lf_version(void);
@@ -113,14 +114,7 @@ int lf_router_set_inflow(lf_router *r, int section, const double *specific_later
  * wavefront: step s uses lateral inflow q * q_scale[s] (q_scale NULL = all ones;
  * host f64[nsteps]).  Same arithmetic per (pixel, step) as nsteps calls of lf_router_route. */
 int lf_router_run(lf_router *r, int section, int nsteps, const double *q_scale, int *nonfinite);
-/* LDD-cut domain decomposition (one router per GPU on its sub-mask; lisflood_code_b200/parallel.py):
- * xslot i32[N] (compressed order of this router): -1 plain pixel; k >= 0: the pixel's new discharge of every step
- * of lf_router_run is ALSO written to export_buf[k * cap_steps + step]; k <= -2: ghost of a pixel owned by another
- * rank, not solved -- its value of each step is read from import_buf[(-2 - k) * cap_steps + step].  Both buffers are
- * DEVICE memory owned by the caller (e.g. torch tensors handed to NCCL) and hold the router's native state
- * representation (z = Q^(1/5) when beta == 0.6, else Q), so a cut network reproduces the uncut one bit for bit. */
-int lf_router_set_exchange(lf_router *r, const int32_t *xslot, int32_t n_export, int32_t n_import, double *export_buf,
-                           const double *import_buf, int32_t cap_steps);
+/* LDD-cut domain decomposition: see the "Multi-GPU" block below (lf_xchg_*, lf_router_set_exchange). */
 void lf_router_destroy(lf_router *r);
 
 /* ---------------------------------------------------------------------------------------------
@@ -194,6 +188,66 @@ int lf_model_set_option(lf_model *m, const char *name, double value);
  * the reference warns once and goes on (kinematic_wave_parallel.py:180-184).  Synchronises. */
 int lf_model_nonfinite(lf_model *m, int *nonfinite);
 void lf_model_destroy(lf_model *m);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: ONE catchment raster cut along its drainage graph over the GPUs of a node, one process per GPU
+ * (the reference shows that sub-catchment runs reproduce the full run bit for bit,
+ * tests/test_subcatchments.py:111-112).  Host side: lisflood_code_b200/parallel.py.
+ *
+ *   lf_graph_partition   owner rank of every pixel of a (global) graph: pixels whose upstream area exceeds
+ *                        subtree_fraction * N / world form the trunk, the sub-trees hanging off it (and whole small
+ *                        catchments) are bin-packed over the ranks, largest first; a trunk pixel joins the rank of its
+ *                        largest tributary.  Deterministic: every rank computes the same map.  owner i32[N]
+ *                        (compressed order, host or device); loads i64[world], n_trunk, n_roots may be NULL.
+ *   lf_graph_cut_edges   the links (u -> d) of a graph whose ends have different owners, sorted by u: host arrays
+ *                        edge_u / edge_d i32[cap] (compressed indices); *n_edges = total number found.
+ *   lf_graph_restrict    the graph restricted to keep[N] != 0 (a rank's own pixels + the ghosts of the upstream ends
+ *                        of its incoming cut edges).  Compressed indices of the result = rank of the pixel among the
+ *                        kept ones; storage order and routing LEVELS stay the global ones, so the wavefront diagonals
+ *                        of all ranks line up and sums over upstream pixels keep the reference's slot order: the cut
+ *                        network reproduces the uncut one bit for bit.
+ *   lf_xchg_*            one exchange region per rank (device memory: header + import_doubles float64 slots), made
+ *                        visible to the other ranks through CUDA IPC (64-byte handles, exchanged by the host layer
+ *                        over torch.distributed); the routing kernels store boundary discharges straight into the
+ *                        consumer's region over NVLink and ghost pixels poll their slot (csrc/lf_xchg.cuh).
+ *                        lf_xchg_set_peer_local wires two regions of ONE process to each other (single-GPU tests).
+ *   lf_router_set_exchange / lf_model_set_exchange
+ *                        xslot i32[N] (compressed order of the restricted graph): -1 plain pixel; k >= 0: upstream end
+ *                        of outgoing cut edge k (export_peer[k] = consumer rank, export_offset[k] = offset in doubles of
+ *                        (parity 0, that edge, section 0, step 0) inside the consumer's import area,
+ *                        export_parity_stride[k] = doubles between the consumer's two parity copies); k <= -2: ghost of
+ *                        incoming edge -2-k; INT32_MIN: ghost that has no link in this graph.  import_offset: offset in
+ *                        doubles of this handle's import block in the own region; a block holds
+ *                        [2 parities][n_import edges][sections][steps] with (sections, steps) = (1, cap_steps) for a
+ *                        router, (3, 1) for the model's overland graph (which = 0) and (1 or 2, NoRoutSteps) for its
+ *                        channel graph (which = 1).
+ * ------------------------------------------------------------------------------------------- */
+int lf_graph_partition(const lf_graph *g, int32_t world, double subtree_fraction, int32_t *owner, int64_t *loads,
+                       int64_t *n_trunk, int64_t *n_roots);
+int lf_graph_cut_edges(const lf_graph *g, const int32_t *owner, int64_t cap, int32_t *edge_u, int32_t *edge_d,
+                       int64_t *n_edges);
+int lf_graph_restrict(const lf_graph *g, const uint8_t *keep, lf_graph **out);
+int lf_xchg_create(int32_t rank, int32_t world, int64_t import_doubles, lf_xchg **out);
+int lf_xchg_ipc_handle(lf_xchg *x, void *handle64);
+int lf_xchg_open_peer(lf_xchg *x, int32_t peer, const void *handle64);
+int lf_xchg_set_peer_local(lf_xchg *x, int32_t peer, lf_xchg *other);
+/* device address of a rank's region as seen from this process (peer = -1: the own region) */
+int lf_xchg_peer_base(lf_xchg *x, int32_t peer, uint64_t *address);
+/* Flow control around one run (a lf_router_run / a model step do this themselves): begin waits, on the device, until
+ * every peer has finished the run before the previous one; end publishes the completion of this run. */
+int lf_xchg_begin(lf_xchg *x, int32_t *parity);
+int lf_xchg_end(lf_xchg *x);
+/* aborted = 1 when a poll gave up (a peer stopped feeding its cut edges for ~10 s).  Synchronises. */
+int lf_xchg_status(lf_xchg *x, int32_t *aborted, int64_t *epoch);
+void lf_xchg_destroy(lf_xchg *x);
+int lf_router_set_exchange(lf_router *r, lf_xchg *x, const int32_t *xslot, int32_t n_export, const int32_t *export_peer,
+                           const int64_t *export_offset, const int64_t *export_parity_stride, int32_t n_import,
+                           int64_t import_offset, int32_t cap_steps);
+/* A model on two restricted graphs of the same pixel subset (LddToChan and LddKinematic); the model owns them. */
+int lf_model_create_from_graphs(const lf_model_config *cfg, lf_graph *g_overland, lf_graph *g_channel, lf_model **out);
+int lf_model_set_exchange(lf_model *m, lf_xchg *x, int32_t which, const int32_t *xslot, int32_t n_export,
+                          const int32_t *export_peer, const int64_t *export_offset, const int64_t *export_parity_stride,
+                          int32_t n_import, int64_t import_offset);
 
 /* ---- The two Numba kernels of the reference as stand-alone operators (hydrological_modules/soilloop.py) ----
  * Same arguments, same in-place semantics; arrays are C-contiguous float64 (bool arrays: uint8), host or device

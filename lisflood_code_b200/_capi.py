@@ -51,14 +51,28 @@ SIGNATURES = {
     "lf_graph_layout": (C.c_int, [_vp, _vp, _vp]),
     "lf_graph_accuflux": (C.c_int, [_vp, _vp, _vp]),
     "lf_graph_destroy": (None, [_vp]),
-    "lf_router_create": (C.c_int, [_vp, _f64, C.c_double, _vp, C.c_double, C.c_double, _vp, C.c_int,
+    "lf_router_create": (C.c_int, [_vp, _vp, C.c_double, _vp, C.c_double, C.c_double, _vp, C.c_int,
                                    C.POINTER(_vp)]),
     "lf_router_route": (C.c_int, [_vp, _f64, _f64, C.c_int, C.POINTER(C.c_int)]),
-    "lf_router_set_discharge": (C.c_int, [_vp, C.c_int, _f64]),
-    "lf_router_get_discharge": (C.c_int, [_vp, C.c_int, _f64]),
-    "lf_router_set_inflow": (C.c_int, [_vp, C.c_int, _f64]),
+    "lf_router_set_discharge": (C.c_int, [_vp, C.c_int, _vp]),
+    "lf_router_get_discharge": (C.c_int, [_vp, C.c_int, _vp]),
+    "lf_router_set_inflow": (C.c_int, [_vp, C.c_int, _vp]),
     "lf_router_run": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
-    "lf_router_set_exchange": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32]),
+    "lf_router_set_exchange": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32, _i64s, C.c_int32]),
+    "lf_graph_partition": (C.c_int, [_vp, C.c_int32, C.c_double, _vp, _vp, C.POINTER(_i64s), C.POINTER(_i64s)]),
+    "lf_graph_cut_edges": (C.c_int, [_vp, _vp, _i64s, _vp, _vp, C.POINTER(_i64s)]),
+    "lf_graph_restrict": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "lf_xchg_create": (C.c_int, [C.c_int32, C.c_int32, _i64s, C.POINTER(_vp)]),
+    "lf_xchg_ipc_handle": (C.c_int, [_vp, C.c_char_p]),
+    "lf_xchg_open_peer": (C.c_int, [_vp, C.c_int32, C.c_char_p]),
+    "lf_xchg_set_peer_local": (C.c_int, [_vp, C.c_int32, _vp]),
+    "lf_xchg_peer_base": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_uint64)]),
+    "lf_xchg_begin": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
+    "lf_xchg_end": (C.c_int, [_vp]),
+    "lf_xchg_status": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(_i64s)]),
+    "lf_xchg_destroy": (None, [_vp]),
+    "lf_model_create_from_graphs": (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    "lf_model_set_exchange": (C.c_int, [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32, _i64s]),
     "lf_router_destroy": (None, [_vp]),
     "lf_model_create": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "lf_model_info": (C.c_int, [_vp, C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s),

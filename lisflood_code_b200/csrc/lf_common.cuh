@@ -103,6 +103,8 @@ struct lf_graph {
     lf::DevBuf<int32_t> pix_of_pos;   // [n]
     lf::DevBuf<int32_t> pos_of_pix;   // [n]
     lf::DevBuf<int32_t> cfirst;       // [n+1] children of position i are positions cfirst[i]..cfirst[i+1]-1
+    lf::DevBuf<int32_t> cend;         // restricted graphs only (lf_graph_restrict): children of i are cfirst[i]..cend[i]-1
+    bool restricted = false;          // no raster members: the reference-shaped exports are not available
     lf::DevBuf<int32_t> lev_of_pos;   // [n]
     lf::DevBuf<int32_t> level_start;  // [n_orders+1] (device copy)
     std::vector<int32_t> h_level_start;  // host copy

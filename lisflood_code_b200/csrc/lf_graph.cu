@@ -18,6 +18,11 @@
 // CUB (shipped with the CUDA toolkit) is used for the init-time scan / radix sort only.
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <functional>
+#include <memory>
+#include <queue>
+
 #include "lf_common.cuh"
 
 namespace {
@@ -286,6 +291,142 @@ __global__ void k_gather_f64(const double *__restrict__ src, double *__restrict_
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[idx[i]];
+}
+
+
+// ---- LDD-cut partition (multi-GPU): everything in position order ----
+// parent position of every position (-1: outlet)
+__global__ void k_parent_pos(const int32_t *__restrict__ pix_of_pos, const int32_t *__restrict__ pos_of_pix,
+                             const int32_t *__restrict__ ds, int32_t *__restrict__ ppos, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = ds[pix_of_pos[i]];
+    ppos[i] = d >= 0 ? pos_of_pix[d] : -1;
+}
+// trunk = upstream area above the threshold; root = non-trunk pixel hanging off the trunk or draining to an outlet
+__global__ void k_part_flags(const double *__restrict__ size, const int32_t *__restrict__ ppos, double thr,
+                             uint8_t *__restrict__ trunk, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) trunk[i] = size[i] > thr;
+}
+// one level, outlets first: a non-trunk pixel carries the position of the root of its sub-tree
+__global__ void k_part_label(const uint8_t *__restrict__ trunk, const int32_t *__restrict__ ppos, int32_t *__restrict__ label,
+                             int lo, int hi)
+{
+    int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    if (trunk[i]) {
+        label[i] = -1;
+        return;
+    }
+    const int pp = ppos[i];
+    label[i] = (pp < 0 || trunk[pp]) ? i : label[pp];
+}
+struct IsRoot {
+    const int32_t *label;
+    __host__ __device__ bool operator()(const int32_t &i) const { return label[i] == i; }
+};
+__global__ void k_iota(int32_t *__restrict__ v, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int32_t)i;
+}
+__global__ void k_root_info(const int32_t *__restrict__ roots, const double *__restrict__ size,
+                            const int32_t *__restrict__ pix_of_pos, double *__restrict__ rsize, int32_t *__restrict__ rpix,
+                            int64_t nr)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nr) return;
+    rsize[k] = size[roots[k]];
+    rpix[k] = pix_of_pos[roots[k]];
+}
+__global__ void k_scatter_root_owner(const int32_t *__restrict__ roots, const int32_t *__restrict__ rown,
+                                     int32_t *__restrict__ owner, int64_t nr)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nr) owner[roots[k]] = rown[k];
+}
+__global__ void k_owner_from_label(const int32_t *__restrict__ label, int32_t *__restrict__ owner, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = label[i];
+    if (l >= 0 && l != i) owner[i] = owner[l];   // roots already carry their owner; label[l] == l is never rewritten
+}
+// one level, headwaters first: a trunk pixel joins the rank of its largest tributary (first in slot order on ties)
+__global__ void k_trunk_owner(const uint8_t *__restrict__ trunk, const double *__restrict__ size,
+                              const int32_t *__restrict__ cfirst, int32_t *__restrict__ owner, int lo, int hi)
+{
+    int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi || !trunk[i]) return;
+    double best = -1.0;
+    int own = 0;
+    for (int k = cfirst[i]; k < cfirst[i + 1]; ++k)
+        if (size[k] > best) {
+            best = size[k];
+            own = owner[k];
+        }
+    owner[i] = own;
+}
+__global__ void k_i32_to_pix(const int32_t *__restrict__ src, int32_t *__restrict__ dst, const int32_t *__restrict__ pos_of_pix,
+                             int64_t n)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) dst[p] = src[pos_of_pix[p]];
+}
+// cut edges: links whose two ends have different owners (owner in PIXEL order)
+__global__ void k_cut_edges(const int32_t *__restrict__ ds, const int32_t *__restrict__ owner, int64_t n, int64_t cap,
+                            int32_t *__restrict__ eu, int32_t *__restrict__ ed, unsigned long long *__restrict__ count)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int d = ds[p];
+    if (d < 0 || owner[p] == owner[d]) return;
+    const unsigned long long k = atomicAdd(count, 1ull);
+    if ((int64_t)k < cap) {
+        eu[k] = (int32_t)p;
+        ed[k] = d;
+    }
+}
+// ---- restriction of a graph to a subset of its pixels (the layout keeps the global order and the global levels) ----
+struct KeepAtPosSafe {   // index n (one past the end) counts as dropped
+    const uint8_t *keep;
+    const int32_t *pix_of_pos;
+    int32_t n;
+    __host__ __device__ int32_t operator()(const int32_t &i) const { return (i < n && keep[pix_of_pos[i]]) ? 1 : 0; }
+};
+__global__ void k_fill_f64(double *__restrict__ v, double x, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = x;
+}
+struct U8ToInt {
+    __host__ __device__ int32_t operator()(const uint8_t &m) const { return m ? 1 : 0; }
+};
+__global__ void k_restrict(const uint8_t *__restrict__ keep, const int32_t *__restrict__ pix_of_pos_g,
+                           const int32_t *__restrict__ cfirst_g, const int32_t *__restrict__ lev_g,
+                           const int32_t *__restrict__ scan_pos, const int32_t *__restrict__ scan_pix,
+                           int32_t *__restrict__ pix_of_pos, int32_t *__restrict__ pos_of_pix, int32_t *__restrict__ cfirst,
+                           int32_t *__restrict__ cend, int32_t *__restrict__ lev, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = pix_of_pos_g[i];
+    if (!keep[p]) return;
+    const int j = scan_pos[i], q = scan_pix[p];
+    pix_of_pos[j] = q;
+    pos_of_pix[q] = j;
+    lev[j] = lev_g[i];
+    cfirst[j] = scan_pos[cfirst_g[i]];       // kept positions before the first child
+    cend[j] = scan_pos[cfirst_g[i + 1]];     // ... before the end of the children: dropped children vanish
+}
+__global__ void k_restrict_levels(const int32_t *__restrict__ ls_g, const int32_t *__restrict__ scan_pos, int32_t *__restrict__ ls,
+                                  int nl)
+{
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l <= nl) ls[l] = scan_pos[ls_g[l]];
 }
 
 // ---- export kernels (reference-shaped int64 / float64 arrays) ----
@@ -600,6 +741,10 @@ int lf_graph_export(const lf_graph *g, int64_t *pixels_ordered, int64_t *order_s
         lf::set_error("lf_graph_export: null graph");
         return LF_ERR_INVALID;
     }
+    if (g->restricted) {
+        lf::set_error("lf_graph_export: a restricted graph (lf_graph_restrict) has no reference-shaped arrays");
+        return LF_ERR_STATE;
+    }
     LF_CHECK(lf::ensure_device());
     cudaStream_t st = lf::stream();
     const int T = 256;
@@ -685,6 +830,262 @@ int lf_graph_accuflux(const lf_graph *g, const double *x, double *out)
     LF_LAUNCH_CHECK();
     LF_CUDA(cudaMemcpyAsync(out, a.p, n * sizeof(double), cudaMemcpyDefault, st));
     LF_CUDA(cudaStreamSynchronize(st));
+    return LF_OK;
+}
+
+
+int lf_graph_partition(const lf_graph *g, int32_t world, double subtree_fraction, int32_t *owner, int64_t *loads,
+                       int64_t *n_trunk, int64_t *n_roots)
+{
+    if (!g || !owner || world < 1 || !(subtree_fraction > 0)) {
+        lf::set_error("lf_graph_partition: bad arguments");
+        return LF_ERR_INVALID;
+    }
+    if (g->restricted) {
+        lf::set_error("lf_graph_partition: needs a graph built by lf_ldd_build");
+        return LF_ERR_STATE;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    const int T = 256;
+    const int64_t n = g->n;
+    const std::vector<int32_t> &ls = g->h_level_start;
+    const int nl = g->n_orders;
+    // upstream area in cells, position order
+    DevBuf<double> size;
+    LF_CHECK(size.alloc(n));
+    k_fill_f64<<<blocks_for(n, T), T, 0, st>>>(size.p, 1.0, n);
+    LF_LAUNCH_CHECK();
+    for (int l = 1; l < nl; ++l) {
+        int lo = ls[l], hi = ls[l + 1];
+        if (hi <= lo) continue;
+        k_accuflux_level<<<blocks_for(hi - lo, T), T, 0, st>>>(size.p, g->cfirst.p, lo, hi);
+        LF_LAUNCH_CHECK();
+    }
+    DevBuf<int32_t> ppos, label, own;
+    DevBuf<uint8_t> trunk;
+    LF_CHECK(ppos.alloc(n));
+    LF_CHECK(label.alloc(n));
+    LF_CHECK(own.alloc(n));
+    LF_CHECK(trunk.alloc(n));
+    k_parent_pos<<<blocks_for(n, T), T, 0, st>>>(g->pix_of_pos.p, g->pos_of_pix.p, g->downstream.p, ppos.p, n);
+    LF_LAUNCH_CHECK();
+    const double thr = world > 1 ? std::max(1.0, subtree_fraction * (double)n / world) : 1e300;
+    k_part_flags<<<blocks_for(n, T), T, 0, st>>>(size.p, ppos.p, thr, trunk.p, n);
+    LF_LAUNCH_CHECK();
+    for (int l = nl - 1; l >= 0; --l) {   // outlets first
+        int lo = ls[l], hi = ls[l + 1];
+        if (hi <= lo) continue;
+        k_part_label<<<blocks_for(hi - lo, T), T, 0, st>>>(trunk.p, ppos.p, label.p, lo, hi);
+        LF_LAUNCH_CHECK();
+    }
+    // the roots, in position order
+    DevBuf<int32_t> iota, roots;
+    DevBuf<int> d_cnt;
+    LF_CHECK(iota.alloc(n));
+    LF_CHECK(roots.alloc(n));
+    LF_CHECK(d_cnt.alloc(1));
+    k_iota<<<blocks_for(n, T), T, 0, st>>>(iota.p, n);
+    LF_LAUNCH_CHECK();
+    {
+        IsRoot sel{label.p};
+        size_t sb = 0;
+        DevBuf<uint8_t> tmp;
+        LF_CUDA(cub::DeviceSelect::If(nullptr, sb, iota.p, roots.p, d_cnt.p, (int)n, sel, st));
+        LF_CHECK(tmp.alloc(sb));
+        LF_CUDA(cub::DeviceSelect::If(tmp.p, sb, iota.p, roots.p, d_cnt.p, (int)n, sel, st));
+        lf::count_launch(2);
+        LF_CUDA(cudaStreamSynchronize(st));
+    }
+    int nr = 0;
+    LF_CUDA(cudaMemcpy(&nr, d_cnt.p, sizeof(int), cudaMemcpyDeviceToHost));
+    iota.release();
+    DevBuf<double> rsize;
+    DevBuf<int32_t> rpix, rown;
+    LF_CHECK(rsize.alloc(nr));
+    LF_CHECK(rpix.alloc(nr));
+    LF_CHECK(rown.alloc(nr));
+    if (nr > 0) {
+        k_root_info<<<blocks_for(nr, T), T, 0, st>>>(roots.p, size.p, g->pix_of_pos.p, rsize.p, rpix.p, nr);
+        LF_LAUNCH_CHECK();
+    }
+    std::vector<double> h_size(nr);
+    std::vector<int32_t> h_pix(nr), h_own(nr);
+    LF_CUDA(cudaMemcpyAsync(h_size.data(), rsize.p, nr * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaMemcpyAsync(h_pix.data(), rpix.p, nr * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaStreamSynchronize(st));
+    // longest-processing-time bin packing of the sub-trees over the ranks (deterministic: size descending, pixel ascending)
+    {
+        std::vector<int32_t> idx(nr);
+        for (int k = 0; k < nr; ++k) idx[k] = k;
+        std::sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) {
+            if (h_size[a] != h_size[b]) return h_size[a] > h_size[b];
+            return h_pix[a] < h_pix[b];
+        });
+        typedef std::pair<double, int> Load;   // (load, rank): smallest load first, then smallest rank
+        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+        for (int r = 0; r < world; ++r) heap.push(Load(0.0, r));
+        for (int32_t k : idx) {
+            Load l = heap.top();
+            heap.pop();
+            h_own[k] = l.second;
+            heap.push(Load(l.first + h_size[k], l.second));
+        }
+    }
+    LF_CUDA(cudaMemcpyAsync(rown.p, h_own.data(), nr * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    LF_CUDA(cudaMemsetAsync(own.p, 0, n * sizeof(int32_t), st));
+    if (nr > 0) {
+        k_scatter_root_owner<<<blocks_for(nr, T), T, 0, st>>>(roots.p, rown.p, own.p, nr);
+        LF_LAUNCH_CHECK();
+    }
+    k_owner_from_label<<<blocks_for(n, T), T, 0, st>>>(label.p, own.p, n);
+    LF_LAUNCH_CHECK();
+    int64_t ntr = 0;
+    if (world > 1) {
+        for (int l = 1; l < nl; ++l) {   // headwaters first: children carry their owner already
+            int lo = ls[l], hi = ls[l + 1];
+            if (hi <= lo) continue;
+            k_trunk_owner<<<blocks_for(hi - lo, T), T, 0, st>>>(trunk.p, size.p, g->cfirst.p, own.p, lo, hi);
+            LF_LAUNCH_CHECK();
+        }
+    }
+    // to pixel order, to the caller
+    DevBuf<int32_t> own_pix;
+    LF_CHECK(own_pix.alloc(n));
+    k_i32_to_pix<<<blocks_for(n, T), T, 0, st>>>(own.p, own_pix.p, g->pos_of_pix.p, n);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaMemcpyAsync(owner, own_pix.p, n * sizeof(int32_t), cudaMemcpyDefault, st));
+    LF_CUDA(cudaStreamSynchronize(st));
+    if (loads || n_trunk) {
+        std::vector<int32_t> h(n);
+        std::vector<uint8_t> ht(n);
+        LF_CUDA(cudaMemcpy(h.data(), own.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        LF_CUDA(cudaMemcpy(ht.data(), trunk.p, n, cudaMemcpyDeviceToHost));
+        if (loads)
+            for (int r = 0; r < world; ++r) loads[r] = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            if (loads && h[i] >= 0 && h[i] < world) loads[h[i]] += 1;
+            ntr += ht[i];
+        }
+    }
+    if (n_trunk) *n_trunk = ntr;
+    if (n_roots) *n_roots = nr;
+    return LF_OK;
+}
+
+int lf_graph_cut_edges(const lf_graph *g, const int32_t *owner, int64_t cap, int32_t *edge_u, int32_t *edge_d, int64_t *n_edges)
+{
+    if (!g || !owner || !n_edges || cap < 0 || (cap > 0 && (!edge_u || !edge_d))) {
+        lf::set_error("lf_graph_cut_edges: bad arguments");
+        return LF_ERR_INVALID;
+    }
+    if (g->restricted) {
+        lf::set_error("lf_graph_cut_edges: needs a graph built by lf_ldd_build");
+        return LF_ERR_STATE;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    const int64_t n = g->n;
+    DevBuf<int32_t> d_owner, eu, ed;
+    DevBuf<unsigned long long> cnt;
+    LF_CHECK(d_owner.alloc(n));
+    LF_CHECK(eu.alloc(std::max<int64_t>(cap, 1)));
+    LF_CHECK(ed.alloc(std::max<int64_t>(cap, 1)));
+    LF_CHECK(cnt.alloc(1));
+    LF_CUDA(cudaMemcpyAsync(d_owner.p, owner, n * sizeof(int32_t), cudaMemcpyDefault, st));
+    LF_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), st));
+    k_cut_edges<<<blocks_for(n, 256), 256, 0, st>>>(g->downstream.p, d_owner.p, n, cap, eu.p, ed.p, cnt.p);
+    LF_LAUNCH_CHECK();
+    unsigned long long h = 0;
+    LF_CUDA(cudaMemcpyAsync(&h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaStreamSynchronize(st));
+    *n_edges = (int64_t)h;
+    const int64_t m = std::min<int64_t>((int64_t)h, cap);
+    if (m > 0) {
+        std::vector<int32_t> hu(m), hd(m);
+        LF_CUDA(cudaMemcpy(hu.data(), eu.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        LF_CUDA(cudaMemcpy(hd.data(), ed.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        std::vector<int64_t> idx(m);
+        for (int64_t k = 0; k < m; ++k) idx[k] = k;
+        std::sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return hu[a] < hu[b]; });   // a pixel has one downstream link
+        for (int64_t k = 0; k < m; ++k) {
+            edge_u[k] = hu[idx[k]];
+            edge_d[k] = hd[idx[k]];
+        }
+    }
+    return LF_OK;
+}
+
+int lf_graph_restrict(const lf_graph *g, const uint8_t *keep, lf_graph **out)
+{
+    if (!g || !keep || !out) {
+        lf::set_error("lf_graph_restrict: null pointer");
+        return LF_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (g->restricted) {
+        lf::set_error("lf_graph_restrict: needs a graph built by lf_ldd_build");
+        return LF_ERR_STATE;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    const int T = 256;
+    const int64_t n = g->n;
+    DevBuf<uint8_t> d_keep, tmp;
+    DevBuf<int32_t> scan_pos, scan_pix;
+    LF_CHECK(d_keep.alloc(n + 1));
+    LF_CHECK(scan_pos.alloc(n + 1));
+    LF_CHECK(scan_pix.alloc(n + 1));
+    LF_CUDA(cudaMemcpyAsync(d_keep.p, keep, n, cudaMemcpyDefault, st));
+    LF_CUDA(cudaMemsetAsync(d_keep.p + n, 0, 1, st));
+    {
+        // kept positions before every position 0..n (position order) and kept pixels before every pixel (pixel order)
+        cub::CountingInputIterator<int32_t> cnt_it(0);
+        KeepAtPosSafe op{d_keep.p, g->pix_of_pos.p, (int32_t)n};
+        cub::TransformInputIterator<int32_t, KeepAtPosSafe, cub::CountingInputIterator<int32_t>> it(cnt_it, op);
+        cub::TransformInputIterator<int32_t, U8ToInt, const uint8_t *> it2(d_keep.p, U8ToInt());
+        size_t sb = 0, sb2 = 0;
+        LF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, it, scan_pos.p, (int)(n + 1), st));
+        LF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb2, it2, scan_pix.p, (int)(n + 1), st));
+        LF_CHECK(tmp.alloc(std::max(sb, sb2)));
+        LF_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, sb, it, scan_pos.p, (int)(n + 1), st));
+        LF_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, sb2, it2, scan_pix.p, (int)(n + 1), st));
+        lf::count_launch(4);
+    }
+    int32_t nloc = 0, iso_before = 0;
+    LF_CUDA(cudaMemcpyAsync(&nloc, scan_pos.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaMemcpyAsync(&iso_before, scan_pos.p + (n - g->n_isolated), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaStreamSynchronize(st));
+    if (nloc <= 0) {
+        lf::set_error("lf_graph_restrict: the subset is empty");
+        return LF_ERR_INVALID;
+    }
+    std::unique_ptr<lf_graph> q(new lf_graph());
+    q->rows = g->rows;
+    q->cols = g->cols;
+    q->n = nloc;
+    q->n_orders = g->n_orders;
+    q->max_ups = g->max_ups;
+    q->n_isolated = nloc - iso_before;
+    q->restricted = true;
+    LF_CHECK(q->pix_of_pos.alloc(nloc));
+    LF_CHECK(q->pos_of_pix.alloc(nloc));
+    LF_CHECK(q->cfirst.alloc(nloc + 1));
+    LF_CHECK(q->cend.alloc(nloc));
+    LF_CHECK(q->lev_of_pos.alloc(nloc));
+    LF_CHECK(q->level_start.alloc(g->n_orders + 1));
+    LF_CUDA(cudaMemsetAsync(q->cfirst.p + nloc, 0, sizeof(int32_t), st));
+    k_restrict<<<blocks_for(n, T), T, 0, st>>>(d_keep.p, g->pix_of_pos.p, g->cfirst.p, g->lev_of_pos.p, scan_pos.p, scan_pix.p,
+                                               q->pix_of_pos.p, q->pos_of_pix.p, q->cfirst.p, q->cend.p, q->lev_of_pos.p, n);
+    LF_LAUNCH_CHECK();
+    k_restrict_levels<<<blocks_for(g->n_orders + 1, T), T, 0, st>>>(g->level_start.p, scan_pos.p, q->level_start.p, g->n_orders);
+    LF_LAUNCH_CHECK();
+    q->h_level_start.resize(g->n_orders + 1);
+    LF_CUDA(cudaMemcpyAsync(q->h_level_start.data(), q->level_start.p, (g->n_orders + 1) * sizeof(int32_t),
+                            cudaMemcpyDeviceToHost, st));
+    LF_CUDA(cudaStreamSynchronize(st));
+    q->n_pits = q->h_level_start[g->n_orders] - q->h_level_start[g->n_orders - 1];
+    *out = q.release();
     return LF_OK;
 }
 

@@ -11,8 +11,17 @@
 //     is executed as L+S-1 "diagonal" launches instead of L*S level launches, each over ONE
 //     contiguous span of positions (the levels d-S+1..d), with discharge double-buffered by step
 //     parity.  S = 1 degenerates to the reference's level-by-level sweep.
+#include <string.h>
+
+#include <vector>
+
 #include "lf_common.cuh"
 #include "lf_kw_solve.cuh"
+#include "lf_xchg.cuh"
+
+extern "C" int lf_xchg_begin(lf_xchg *, int32_t *);
+extern "C" int lf_xchg_end(lf_xchg *);
+extern "C" int lf_xchg_peer_base(lf_xchg *, int32_t, uint64_t *);
 
 struct lf_router {
     lf_graph *g = nullptr;
@@ -29,11 +38,15 @@ struct lf_router {
     lf::DevBuf<double> stage_a, stage_b;  // compressed (user) order staging
     lf::DevBuf<double> scale;
     lf::DevBuf<int> flag;
-    // LDD-cut exchange (multi-GPU): per position -1 = plain pixel, >= 0 = export slot (its new value of every step
-    // is also written to xport), <= -2 = ghost of a pixel owned by another rank (value read from xin, not solved)
+    // LDD-cut exchange (multi-GPU, lf_xchg.cuh): per position -1 = plain pixel, k >= 0 = export edge k (its new value of
+    // every step is also stored into the consumer rank's region), <= -2 = ghost of a pixel owned by another rank (value
+    // taken from this rank's import block, not solved)
     lf::DevBuf<int32_t> xslot;
-    double *xport = nullptr;
-    const double *xin = nullptr;
+    lf_xchg *xchg = nullptr;
+    lf::DevBuf<double *> exp_dst;
+    lf::DevBuf<long long> exp_stride;
+    double *imp = nullptr;
+    long long imp_parity_stride = 0;
     int32_t x_cap_steps = 0, n_export = 0, n_import = 0;
 };
 
@@ -90,19 +103,13 @@ __global__ void k_nonfinite(const double *__restrict__ v, int64_t n, int *__rest
 }
 
 // One diagonal of the space-time wavefront.  Positions [lo, hi) = levels d-S+1..d.
-struct XPtrs {
-    const int32_t *xslot;
-    double *xport;
-    const double *xin;
-    int32_t cap_steps;
-};
 constexpr int KW_THREADS = 128;
 template <bool QZ, bool HASX>
 __global__ void __launch_bounds__(KW_THREADS)
     k_kw_diagonal(int lo, int hi, int d, int64_t g0, const int32_t *__restrict__ lev,
-                  const int32_t *__restrict__ cfirst, const double *__restrict__ a, const double *__restrict__ dx,
-                  double dx_scalar, const double *__restrict__ q, const double *__restrict__ scale, double *Q0,
-                  double *Q1, lfkw::Params P, XPtrs X)
+                  const int32_t *__restrict__ cfirst, const int32_t *__restrict__ cend, const double *__restrict__ a,
+                  const double *__restrict__ dx, double dx_scalar, const double *__restrict__ q,
+                  const double *__restrict__ scale, double *Q0, double *Q1, lfkw::Params P, lfx::View X)
 {
     int i = lo + blockIdx.x * KW_THREADS + threadIdx.x;
     if (i >= hi) return;
@@ -113,12 +120,12 @@ __global__ void __launch_bounds__(KW_THREADS)
     int xs = -1;
     if (HASX) {
         xs = X.xslot[i];
-        if (xs <= -2) {  // ghost: the owner's value of this step (router-native representation), layout [slot][step]
-            Qnew[i] = X.xin[(int64_t)(-2 - xs) * X.cap_steps + s];
+        if (xs <= -2) {  // ghost: the owner's value of this step (router-native representation)
+            Qnew[i] = xs == lfx::INERT ? 0.0 : lfx::take(lfx::import_slot(X, -2 - xs, 0, s), X.abort_flag);
             return;
         }
     }
-    int c0 = cfirst[i], c1 = cfirst[i + 1];
+    int c0 = cfirst[i], c1 = cend ? cend[i] : cfirst[i + 1];
     double qo = Qold[i];
     double qs = q[i];
     if (scale) qs *= scale[s];
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(KW_THREADS)
         out = lfkw::solve(U, qo, lateral, ai, P);
     }
     Qnew[i] = out;
-    if (HASX && xs >= 0) X.xport[(int64_t)xs * X.cap_steps + s] = out;
+    if (HASX && xs >= 0) lfx::push(lfx::export_slot(X, xs, 0, s), out);
 }
 
 __global__ void k_i32_to_pos(const int32_t *__restrict__ src, int32_t *__restrict__ dst,
@@ -155,16 +162,31 @@ int run_steps(lf_router *r, int sec, int nsteps, const double *d_scale)
     const std::vector<int32_t> &ls = g->h_level_start;
     int L = g->n_orders;
     int64_t g0 = r->steps_done[sec];
+    lfx::View X;
+    memset(&X, 0, sizeof(X));
+    if (r->xslot.p) {
+        int32_t parity = 0;
+        LF_CHECK(lf_xchg_begin(r->xchg, &parity));
+        X.xslot = r->xslot.p;
+        X.exp_dst = r->exp_dst.p;
+        X.exp_stride = r->exp_stride.p;
+        X.imp = r->imp;
+        X.imp_parity_stride = r->imp_parity_stride;
+        X.cap = r->x_cap_steps;
+        X.nsec = 1;
+        X.parity = parity;
+        LF_CHECK(lf::xchg_view_base(r->xchg, &X.abort_flag));
+    }
     for (int d = 0; d < L + nsteps - 1; ++d) {
         int lo_lev = d - nsteps + 1 > 0 ? d - nsteps + 1 : 0;
         int hi_lev = d < L - 1 ? d : L - 1;
         int lo = ls[lo_lev], hi = ls[hi_lev + 1];
         if (hi <= lo) continue;
         const bool hasx = r->xslot.p != nullptr;
-        XPtrs X{r->xslot.p, r->xport, r->xin, r->x_cap_steps};
 #define LF_KW_LAUNCH(QZ_, HX_)                                                                                        \
     k_kw_diagonal<QZ_, HX_><<<lf::blocks_for(hi - lo, KW_THREADS), KW_THREADS, 0, st>>>(                              \
-        lo, hi, d, g0, g->lev_of_pos.p, g->cfirst.p, r->a[sec].p, r->dx_is_array ? r->dx.p : nullptr, r->dx_scalar,   \
+        lo, hi, d, g0, g->lev_of_pos.p, g->cfirst.p, g->cend.p, r->a[sec].p, r->dx_is_array ? r->dx.p : nullptr,      \
+        r->dx_scalar,                                                                                                 \
         r->q[sec].p, d_scale, r->Q[sec][0].p, r->Q[sec][1].p, r->P, X)
         if (r->P.quintic) {
             if (hasx) LF_KW_LAUNCH(true, true);
@@ -177,6 +199,7 @@ int run_steps(lf_router *r, int sec, int nsteps, const double *d_scale)
         LF_LAUNCH_CHECK();
     }
     r->steps_done[sec] = g0 + nsteps;
+    if (r->xslot.p) LF_CHECK(lf_xchg_end(r->xchg));
     return LF_OK;
 }
 
@@ -389,16 +412,13 @@ int lf_router_route(lf_router *r, double *discharge, const double *specific_late
     return LF_OK;
 }
 
-int lf_router_set_exchange(lf_router *r, const int32_t *xslot, int32_t n_export, int32_t n_import, double *export_buf,
-                           const double *import_buf, int32_t cap_steps)
+int lf_router_set_exchange(lf_router *r, lf_xchg *x, const int32_t *xslot, int32_t n_export, const int32_t *export_peer,
+                           const int64_t *export_offset, const int64_t *export_parity_stride, int32_t n_import,
+                           int64_t import_offset, int32_t cap_steps)
 {
-    if (!r || !xslot || cap_steps < 1 || n_export < 0 || n_import < 0 || (n_export > 0 && !export_buf) ||
-        (n_import > 0 && !import_buf)) {
+    if (!r || !x || !xslot || cap_steps < 1 || n_export < 0 || n_import < 0 ||
+        (n_export > 0 && (!export_peer || !export_offset || !export_parity_stride)) || import_offset < 0) {
         lf::set_error("lf_router_set_exchange: bad arguments");
-        return LF_ERR_INVALID;
-    }
-    if ((n_export > 0 && !lf::is_device_ptr(export_buf)) || (n_import > 0 && !lf::is_device_ptr(import_buf))) {
-        lf::set_error("lf_router_set_exchange: exchange buffers must be device memory");
         return LF_ERR_INVALID;
     }
     LF_CHECK(lf::ensure_device());
@@ -409,9 +429,24 @@ int lf_router_set_exchange(lf_router *r, const int32_t *xslot, int32_t n_export,
     LF_CUDA(cudaMemcpyAsync(tmp.p, xslot, r->n * sizeof(int32_t), cudaMemcpyDefault, st));
     k_i32_to_pos<<<lf::blocks_for(r->n, 256), 256, 0, st>>>(tmp.p, r->xslot.p, r->g->pix_of_pos.p, r->n);
     LF_LAUNCH_CHECK();
+    std::vector<double *> dst(std::max(n_export, 1), nullptr);
+    std::vector<long long> stride(std::max(n_export, 1), 0);
+    for (int k = 0; k < n_export; ++k) {
+        uint64_t base = 0;
+        LF_CHECK(lf_xchg_peer_base(x, export_peer[k], &base));
+        dst[k] = (double *)(uintptr_t)(base + lfx::HEADER_BYTES) + export_offset[k];
+        stride[k] = export_parity_stride[k];
+    }
+    LF_CHECK(r->exp_dst.alloc(dst.size()));
+    LF_CHECK(r->exp_stride.alloc(stride.size()));
+    LF_CUDA(cudaMemcpyAsync(r->exp_dst.p, dst.data(), dst.size() * sizeof(double *), cudaMemcpyHostToDevice, st));
+    LF_CUDA(cudaMemcpyAsync(r->exp_stride.p, stride.data(), stride.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
     LF_CUDA(cudaStreamSynchronize(st));
-    r->xport = export_buf;
-    r->xin = import_buf;
+    uint64_t own = 0;
+    LF_CHECK(lf_xchg_peer_base(x, -1, &own));
+    r->imp = (double *)(uintptr_t)(own + lfx::HEADER_BYTES) + import_offset;
+    r->imp_parity_stride = (long long)n_import * cap_steps;
+    r->xchg = x;
     r->x_cap_steps = cap_steps;
     r->n_export = n_export;
     r->n_import = n_import;

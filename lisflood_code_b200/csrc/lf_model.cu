@@ -29,9 +29,13 @@
 #include "lf_common.cuh"
 #include "lf_kw_solve.cuh"
 #include "lf_soil_kernel.cuh"
+#include "lf_xchg.cuh"
 
 extern "C" int lf_ldd_build(const double *, const uint8_t *, int64_t, int64_t, lf_graph **);
 extern "C" void lf_graph_destroy(lf_graph *);
+extern "C" int lf_xchg_begin(lf_xchg *, int32_t *);
+extern "C" int lf_xchg_end(lf_xchg *);
+extern "C" int lf_xchg_peer_base(lf_xchg *, int32_t, uint64_t *);
 
 namespace {
 
@@ -49,7 +53,8 @@ struct Field {
 
 struct ChanPtrs {
     int32_t n;
-    const int32_t *lev, *cfirst;
+    const int32_t *lev, *cfirst, *cend;   // cend: restricted graphs only (lf_graph_restrict), else children end at cfirst[i+1]
+    lfx::View X;                           // LDD-cut exchange (multi-GPU), X.xslot == nullptr otherwise
     double *Qk, *Qr0, *Qr1, *M3, *sumDis, *ChanQ;
     const double *a, *L, *alpha, *sideDt;
     const uint8_t *isChan;
@@ -149,7 +154,7 @@ __device__ __forceinline__ void chan_substep(const ChanPtrs &C, int i, double U1
 constexpr int CH_THREADS = 128;
 
 // wavefront diagonal over channel-network pixels: positions [lo, hi), sub-step s = d - level
-template <bool QZ>
+template <bool QZ, bool HASX>
 __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo, int hi, int d)
 {
     int i = lo + blockIdx.x * CH_THREADS + threadIdx.x;
@@ -157,7 +162,17 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo
     int s = d - C.lev[i];
     double *Qr = (s & 1) ? C.Qr1 : C.Qr0;
     double *Q2r = (s & 1) ? C.Q2r1 : C.Q2r0;
-    int c0 = C.cfirst[i], c1 = C.cfirst[i + 1];
+    int xs = -1;
+    if (HASX) {
+        xs = C.X.xslot[i];
+        if (xs <= -2) {   // ghost of a pixel another rank owns: its routed discharge of this sub-step, not solved here
+            const bool inert = xs == lfx::INERT;
+            Qr[i] = inert ? 0.0 : lfx::take(lfx::import_slot(C.X, -2 - xs, 0, s), C.X.abort_flag);
+            if (C.split) Q2r[i] = inert ? 0.0 : lfx::take(lfx::import_slot(C.X, -2 - xs, 1, s), C.X.abort_flag);
+            return;
+        }
+    }
+    int c0 = C.cfirst[i], c1 = C.cend ? C.cend[i] : C.cfirst[i + 1];
     double U1 = 0., U2 = 0.;
     for (int k = c0; k < c1; ++k) U1 += QZ ? lfkw::pow5(Qr[k]) : Qr[k];
     ChanLocal X;
@@ -182,6 +197,10 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo
     double qr1, qr2 = 0.;
     chan_substep<QZ>(C, i, U1, U2, X, L, 1 / L, alpha, a, sideDt, isch, qr1, qr2, alpha2, a2, ql, m3l, c2s, c2q, z2f);
     Qr[i] = qr1;
+    if (HASX && xs >= 0) {
+        lfx::push(lfx::export_slot(C.X, xs, 0, s), qr1);
+        if (C.split) lfx::push(lfx::export_slot(C.X, xs, 1, s), qr2);
+    }
     C.Qk[i] = X.qk;
     C.sumDis[i] = X.sum;
     const bool last = s == C.S - 1;
@@ -347,7 +366,8 @@ __global__ void k_chan_post(int n, int split, int qz, int S, double DtSec, const
 
 // ---- overland flow: three routers in one sweep (surface_routing.py:143-153) ----
 struct OfPtrs {
-    const int32_t *cfirst;
+    const int32_t *cfirst, *cend;
+    lfx::View X;
     const double *DirectRunoff, *SurfOther, *SurfForest, *MMtoM3;
     const double *a[3];   // Other, Forest, Direct
     double *Qnew[3];
@@ -355,12 +375,21 @@ struct OfPtrs {
     double PixelLength, InvPixelLength, InvDtSec;
     lfkw::Params P;
 };
-template <bool QZ>
+template <bool QZ, bool HASX>
 __global__ void __launch_bounds__(128) k_of_level(OfPtrs O, int lo, int hi)
 {
     int i = lo + blockIdx.x * 128 + threadIdx.x;
     if (i >= hi) return;
-    int c0 = O.cfirst[i], c1 = O.cfirst[i + 1];
+    int xs = -1;
+    if (HASX) {
+        xs = O.X.xslot[i];
+        if (xs <= -2) {   // ghost: the owner's new discharge of the three routers
+            for (int r = 0; r < 3; ++r)
+                O.Qnew[r][i] = xs == lfx::INERT ? 0.0 : lfx::take(lfx::import_slot(O.X, -2 - xs, r, 0), O.X.abort_flag);
+            return;
+        }
+    }
+    int c0 = O.cfirst[i], c1 = O.cend ? O.cend[i] : O.cfirst[i + 1];
     const double mm2m3 = O.MMtoM3[i];
     const double runoff[3] = {O.SurfOther[i], O.SurfForest[i], O.DirectRunoff[i]};
 #pragma unroll
@@ -369,11 +398,13 @@ __global__ void __launch_bounds__(128) k_of_level(OfPtrs O, int lo, int hi)
         const double side = runoff[r] * mm2m3 * O.InvPixelLength * O.InvDtSec;  // [m3 s-1 m-1], :143-149
         if (QZ) {
             for (int k = c0; k < c1; ++k) U += lfkw::pow5(O.Qnew[r][k]);
-            O.Qnew[r][i] = lfkw::solve_z(U, O.Qold[r][i], side * O.PixelLength, O.a[r][i]);
+            U = lfkw::solve_z(U, O.Qold[r][i], side * O.PixelLength, O.a[r][i]);
         } else {
             for (int k = c0; k < c1; ++k) U += O.Qnew[r][k];
-            O.Qnew[r][i] = lfkw::solve(U, O.Qold[r][i], side * O.PixelLength, O.a[r][i], O.P);
+            U = lfkw::solve(U, O.Qold[r][i], side * O.PixelLength, O.a[r][i], O.P);
         }
+        O.Qnew[r][i] = U;
+        if (HASX && xs >= 0) lfx::push(lfx::export_slot(O.X, xs, r, 0), U);
     }
 }
 // surface_routing.py:191-212 (+ scatter of ToChanM3RunoffDt into channel order)
@@ -439,6 +470,12 @@ __global__ void k_u8_to_pos(const uint8_t *__restrict__ src, uint8_t *__restrict
 #pragma unroll
     for (int u = 0; u < PERM_U; ++u)
         if (i0 + u < n) dst[i0 + u] = x[u];
+}
+__global__ void k_i32_rows_to_pos(const int32_t *__restrict__ src, int32_t *__restrict__ dst, const int32_t *__restrict__ pix_of_pos,
+                                  int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[pix_of_pos[i]];
 }
 __global__ void k_rows_differ(const double *__restrict__ a, const double *__restrict__ b, int64_t n, int *__restrict__ flag)
 {
@@ -512,6 +549,18 @@ struct lf_model {
     lf::DevBuf<int32_t> iso_chan_list;    // isolated pixels that are channel pixels
     int iso_chan_count = 0;
     bool iso_list_dirty = true, early_in_flight = false;
+    // LDD-cut exchange (multi-GPU): one region, one import block per graph (overland: 3 routers x 1 step per edge;
+    // channel: 1 or 2 sections x NoRoutSteps per edge)
+    lf_xchg *xchg = nullptr;
+    struct XSide {
+        lf::DevBuf<int32_t> xslot;
+        lf::DevBuf<double *> exp_dst;
+        lf::DevBuf<long long> exp_stride;
+        double *imp = nullptr;
+        long long imp_parity_stride = 0;
+        int32_t n_export = 0, n_import = 0;
+    } xs_of, xs_ch;
+    int32_t x_parity = 0;
     int overlap_isolated = 1;             // option "overlap_isolated"
     int early_blocks_per_sm = 2;          // option "early_blocks_per_sm"
     int nancheck = 0;                     // option "flagnancheck"
@@ -973,13 +1022,32 @@ int internal(lf_model *m, const std::string &name, Order order, double **out)
     return LF_OK;
 }
 
+int make_view(lf_model *m, lf_model::XSide &xs, int cap, int nsec, lfx::View &X)
+{
+    memset(&X, 0, sizeof(X));
+    if (!m->xchg || !xs.xslot.p) return LF_OK;
+    X.xslot = xs.xslot.p;
+    X.exp_dst = xs.exp_dst.p;
+    X.exp_stride = xs.exp_stride.p;
+    X.imp = xs.imp;
+    X.imp_parity_stride = xs.imp_parity_stride;
+    X.cap = cap;
+    X.nsec = nsec;
+    X.parity = m->x_parity;
+    return lf::xchg_view_base(m->xchg, &X.abort_flag);
+}
+
 int surface_stage(lf_model *m)
 {
     cudaStream_t st = lf::stream();
     LF_CHECK(refresh_params(m));
     lf_graph *g = m->g_of;
     OfPtrs O;
+    if (m->xchg) LF_CHECK(lf_xchg_begin(m->xchg, &m->x_parity));   // closed at the end of the channel stage
+    LF_CHECK(make_view(m, m->xs_of, 1, 3, O.X));
+    const bool hasx = O.X.xslot != nullptr;
     O.cfirst = g->cfirst.p;
+    O.cend = g->cend.p;
     FIELD(dr, "DirectRunoff");
     FIELD(so, "SurfOther");
     FIELD(sf, "SurfForest");
@@ -1008,8 +1076,13 @@ int surface_stage(lf_model *m)
     for (int l = 0; l < g->n_orders; ++l) {
         int lo = ls[l], hi = ls[l + 1];
         if (hi <= lo) continue;
-        if (m->quintic) k_of_level<true><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
-        else k_of_level<false><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+        if (hasx) {
+            if (m->quintic) k_of_level<true, true><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+            else k_of_level<false, true><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+        } else {
+            if (m->quintic) k_of_level<true, false><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+            else k_of_level<false, false><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+        }
         LF_LAUNCH_CHECK();
     }
     // swap: the named maps must hold the new discharge
@@ -1060,6 +1133,8 @@ int chan_ptrs(lf_model *m, ChanPtrs &C, double **m32_out, double **c2s_out)
     C.n = (int32_t)m->n;
     C.lev = g->lev_of_pos.p;
     C.cfirst = g->cfirst.p;
+    C.cend = g->cend.p;
+    LF_CHECK(make_view(m, m->xs_ch, m->cfg.NoRoutSteps, m->cfg.SplitRouting ? 2 : 1, C.X));
     FIELD(qk, "ChanQKin");
     FIELD(m3, "ChanM3Kin");
     FIELD(sd, "sumDisDay");
@@ -1136,6 +1211,10 @@ int chan_streams(lf_model *m)
     LF_CUDA(cudaEventCreateWithFlags(&m->ev_early_join, cudaEventDisableTiming));
     LF_CHECK(m->iso_next.alloc(4));
     LF_CUDA(cudaMemsetAsync(m->iso_next.p, 0, 4 * sizeof(int), lf::stream()));
+    // Kernels share an SM only if they agree on its L1 / shared-memory split: the soil stage asks for the maximum
+    // shared-memory carve-out, so the kernels meant to run beside it ask for the same (they use no L1-resident reuse)
+    LF_CUDA(cudaFuncSetAttribute(k_chan_isolated_ws<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LF_CUDA(cudaFuncSetAttribute(k_chan_isolated_ws<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return LF_OK;
 }
 
@@ -1215,12 +1294,19 @@ int channel_stage(lf_model *m)
         int hi_lev = d < Lc - 1 ? d : Lc - 1;
         int lo = ls[lo_lev], hi = level_end(hi_lev);
         if (hi <= lo) continue;
-        if (m->quintic) k_chan_diagonal<true><<<lf::blocks_for(hi - lo, CH_THREADS), CH_THREADS, 0, sw>>>(C, lo, hi, d);
-        else k_chan_diagonal<false><<<lf::blocks_for(hi - lo, CH_THREADS), CH_THREADS, 0, sw>>>(C, lo, hi, d);
+        const unsigned gb = lf::blocks_for(hi - lo, CH_THREADS);
+        if (C.X.xslot) {
+            if (m->quintic) k_chan_diagonal<true, true><<<gb, CH_THREADS, 0, sw>>>(C, lo, hi, d);
+            else k_chan_diagonal<false, true><<<gb, CH_THREADS, 0, sw>>>(C, lo, hi, d);
+        } else {
+            if (m->quintic) k_chan_diagonal<true, false><<<gb, CH_THREADS, 0, sw>>>(C, lo, hi, d);
+            else k_chan_diagonal<false, false><<<gb, CH_THREADS, 0, sw>>>(C, lo, hi, d);
+        }
         LF_LAUNCH_CHECK();
     }
     LF_CUDA(cudaEventRecord(m->ev_join, sw));
     LF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
+    if (m->xchg) LF_CHECK(lf_xchg_end(m->xchg));
     if (m->early_in_flight) {
         LF_CUDA(cudaStreamWaitEvent(st, m->ev_early_join, 0));
         m->early_in_flight = false;
@@ -1281,6 +1367,90 @@ int lf_model_create(const lf_model_config *cfg, const uint8_t *land_mask, const 
     LF_LAUNCH_CHECK();
     LF_CUDA(cudaStreamSynchronize(lf::stream()));
     *out = m.release();
+    return LF_OK;
+}
+
+int lf_model_create_from_graphs(const lf_model_config *cfg, lf_graph *g_overland, lf_graph *g_channel, lf_model **out)
+{
+    if (!cfg || !g_overland || !g_channel || !out) {
+        lf::set_error("lf_model_create_from_graphs: null pointer");
+        return LF_ERR_INVALID;
+    }
+    if (g_overland->n != g_channel->n) {
+        lf::set_error("lf_model_create_from_graphs: the two graphs hold different pixel sets");
+        return LF_ERR_INVALID;
+    }
+    if (!(cfg->DtSec > 0) || !(cfg->Beta > 0) || cfg->NoRoutSteps < 1 || !(cfg->PixelLength > 0) ||
+        !(cfg->CourantCrit > 0)) {
+        lf::set_error("lf_model_create_from_graphs: DtSec, Beta, PixelLength, CourantCrit must be > 0 and NoRoutSteps >= 1");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    *out = nullptr;
+    std::unique_ptr<lf_model> m(new lf_model());
+    m->cfg = *cfg;
+    m->DtDay = cfg->DtSec / 86400.;
+    m->DtRouting = cfg->DtSec / cfg->NoRoutSteps;
+    m->quintic = lfkw::make_params(cfg->Beta).quintic != 0;
+    m->n = g_overland->n;
+    LF_CHECK(m->stage.alloc((size_t)3 * m->n));
+    LF_CHECK(m->stage_u8.alloc(m->n));
+    LF_CHECK(m->soil_to_chan.alloc(m->n));
+    LF_CHECK(m->flag.alloc(1));
+    k_soil_to_chan<<<lf::blocks_for(m->n, 256), 256, 0, lf::stream()>>>(g_overland->pix_of_pos.p, g_channel->pos_of_pix.p,
+                                                                        m->soil_to_chan.p, m->n);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaStreamSynchronize(lf::stream()));
+    m->g_of = g_overland;   // owned by the model from here on
+    m->g_ch = g_channel;
+    *out = m.release();
+    return LF_OK;
+}
+
+int lf_model_set_exchange(lf_model *m, lf_xchg *x, int32_t which, const int32_t *xslot, int32_t n_export,
+                          const int32_t *export_peer, const int64_t *export_offset, const int64_t *export_parity_stride,
+                          int32_t n_import, int64_t import_offset)
+{
+    if (!m || !x || !xslot || (which != 0 && which != 1) || n_export < 0 || n_import < 0 || import_offset < 0 ||
+        (n_export > 0 && (!export_peer || !export_offset || !export_parity_stride))) {
+        lf::set_error("lf_model_set_exchange: bad arguments");
+        return LF_ERR_INVALID;
+    }
+    if (m->xchg && m->xchg != x) {
+        lf::set_error("lf_model_set_exchange: both graphs must use the same exchange region");
+        return LF_ERR_STATE;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    lf_model::XSide &xs = which == 0 ? m->xs_of : m->xs_ch;
+    lf_graph *g = which == 0 ? m->g_of : m->g_ch;
+    const int cap = which == 0 ? 1 : m->cfg.NoRoutSteps, nsec = which == 0 ? 3 : (m->cfg.SplitRouting ? 2 : 1);
+    lf::DevBuf<int32_t> tmp;
+    LF_CHECK(tmp.alloc(m->n));
+    LF_CHECK(xs.xslot.alloc(m->n));
+    LF_CUDA(cudaMemcpyAsync(tmp.p, xslot, m->n * sizeof(int32_t), cudaMemcpyDefault, st));
+    k_i32_rows_to_pos<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(tmp.p, xs.xslot.p, g->pix_of_pos.p, m->n);
+    LF_LAUNCH_CHECK();
+    std::vector<double *> dst(std::max(n_export, 1), nullptr);
+    std::vector<long long> stride(std::max(n_export, 1), 0);
+    for (int k = 0; k < n_export; ++k) {
+        uint64_t base = 0;
+        LF_CHECK(lf_xchg_peer_base(x, export_peer[k], &base));
+        dst[k] = (double *)(uintptr_t)(base + lfx::HEADER_BYTES) + export_offset[k];
+        stride[k] = export_parity_stride[k];
+    }
+    LF_CHECK(xs.exp_dst.alloc(dst.size()));
+    LF_CHECK(xs.exp_stride.alloc(stride.size()));
+    LF_CUDA(cudaMemcpyAsync(xs.exp_dst.p, dst.data(), dst.size() * sizeof(double *), cudaMemcpyHostToDevice, st));
+    LF_CUDA(cudaMemcpyAsync(xs.exp_stride.p, stride.data(), stride.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+    LF_CUDA(cudaStreamSynchronize(st));
+    uint64_t own = 0;
+    LF_CHECK(lf_xchg_peer_base(x, -1, &own));
+    xs.imp = (double *)(uintptr_t)(own + lfx::HEADER_BYTES) + import_offset;
+    xs.imp_parity_stride = (long long)n_import * nsec * cap;
+    xs.n_export = n_export;
+    xs.n_import = n_import;
+    m->xchg = x;
     return LF_OK;
 }
 

@@ -44,10 +44,16 @@ THREE_ROWS = frozenset(k for d in (PARAMETERS, STATE, FORCING) for k, r in d.ite
 
 
 class HotPathModel(object):
-    def __init__(self, S, diagnostics=False):
-        """S: dict with the reference's attribute names (see synthetic.full_stack for the full list)."""
+    def __init__(self, S, diagnostics=False, graphs=None, n_active=None, pick=None):
+        """S: dict with the reference's attribute names (see synthetic.full_stack for the full list).
+        graphs=(overland, channel): two device graphs of the same pixel subset (lf_graph_restrict: the local part of a
+        raster cut over several GPUs, lisflood_code_b200/parallel.py) with n_active pixels; `pick` then maps a global
+        map of S to its local pixels."""
         L = _capi.lib()
-        if "mask_device" in S:
+        if graphs is not None:
+            mask = None
+            rows_cols = (int(S["rows"]), int(S["cols"]))
+        elif "mask_device" in S:
             mask = None
             rows_cols, n_active = (int(S["rows"]), int(S["cols"])), int(S["N"])
         else:
@@ -66,13 +72,18 @@ class HotPathModel(object):
         self.__dict__["split"] = bool(S.get("SplitRouting"))
         self.__dict__["N"] = n_active
         h = C.c_void_p()
-        ldd_oc, ldd_kin = S["LddToChan"], S["LddKinematic"]
-        if not hasattr(ldd_oc, "data_ptr"):   # NumPy input; torch CUDA tensors are passed through as they are
-            ldd_oc = np.ascontiguousarray(ldd_oc, np.float64)
-            ldd_kin = np.ascontiguousarray(ldd_kin, np.float64)
-        mask_arg = S["mask_device"] if "mask_device" in S else mask
-        _capi.check(L.lf_model_create(C.byref(cfg), _capi.ptr(mask_arg), _capi.ptr(ldd_oc), _capi.ptr(ldd_kin),
-                                      C.byref(h)))
+        if graphs is not None:
+            n_active = int(n_active)
+            self.__dict__["N"] = n_active
+            _capi.check(L.lf_model_create_from_graphs(C.byref(cfg), graphs[0], graphs[1], C.byref(h)))
+        else:
+            ldd_oc, ldd_kin = S["LddToChan"], S["LddKinematic"]
+            if not hasattr(ldd_oc, "data_ptr"):   # NumPy input; torch CUDA tensors are passed through as they are
+                ldd_oc = np.ascontiguousarray(ldd_oc, np.float64)
+                ldd_kin = np.ascontiguousarray(ldd_kin, np.float64)
+            mask_arg = S["mask_device"] if "mask_device" in S else mask
+            _capi.check(L.lf_model_create(C.byref(cfg), _capi.ptr(mask_arg), _capi.ptr(ldd_oc), _capi.ptr(ldd_kin),
+                                          C.byref(h)))
         self.__dict__["_h"] = h
         self.__dict__["_rows"] = {}
         self.__dict__["NoRoutSteps"] = int(S["NoRoutSteps"])
@@ -88,10 +99,10 @@ class HotPathModel(object):
             if name in DIAGNOSTIC_ONLY and not diagnostics:
                 continue
             if name in S:
-                self.set(name, S[name], rows)
+                self.set(name, pick(S[name]) if pick else S[name], rows)
         for name in FLAGS:
             if name in S:
-                self.set_flags(name, S[name])
+                self.set_flags(name, pick(S[name]) if pick else S[name])
 
     # ---- raw access --------------------------------------------------------------------------------
     def set(self, name, values, rows=None):

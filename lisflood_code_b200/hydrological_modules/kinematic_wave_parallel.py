@@ -4,11 +4,16 @@ through liblisf_b200.so.
 
 Same constructor signature, same `kinematicWaveRouting(discharge, specific_lateral_inflow, section)`
 contract (returns None, mutates `discharge` in place, raises Exception on a bad section, warns once on
-non-finite output when flagnancheck is set) and the same graph attributes (`downstream_lookup`,
+non-finite output when flagnancheck is set; `discharge` may be any array that supports in-place assignment -- the
+fast path is a C-contiguous float64 array) and the same graph attributes (`downstream_lookup`,
 `upstream_lookup`, `num_upstream_pixels`, `pixels_ordered`, `order_start_stop`; bit-identical, fetched
 lazily from the device).  Additional device-resident methods (`set_discharge`, `set_lateral_inflow`,
 `run`, `get_discharge`) keep the state in HBM across many routing steps and execute them as one
 space-time wavefront.
+
+Numerics: the solver reproduces the reference's initial guess and Newton iterates (csrc/lf_kw_solve.cuh) and adds one exit
+(relative Newton step <= 1e-8); results agree with the reference's to ~1e-13 relative (worst case pinned at < 1e-12 on
+adversarial inputs by tests/test_gpu_kinwave.py), the contract being 1e-6.  Only the graph arrays are bit-identical.
 """
 import ctypes as C
 import warnings
@@ -50,15 +55,49 @@ class kinematicWave:
         else:
             dx, dxs = self._as_map(space_delta), 0.0
         r = C.c_void_p()
-        _capi.check(L.lf_router_create(g, alpha, float(beta), _capi.ptr(dx), dxs, float(time_delta), _capi.ptr(alpha_fp),
-                                       1 if flagnancheck else 0, C.byref(r)))
+        _capi.check(L.lf_router_create(g, _capi.ptr(alpha), float(beta), _capi.ptr(dx), dxs, float(time_delta),
+                                       _capi.ptr(alpha_fp), 1 if flagnancheck else 0, C.byref(r)))
         self._router = r
         no, k, npix, pits = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         _capi.check(L.lf_graph_info(g, C.byref(npix), C.byref(no), C.byref(k), C.byref(pits)))
         self.num_orders, self.max_upstream, self.num_pits = no.value, k.value, pits.value
         self._cache = {}
 
+    @classmethod
+    def from_graph(cls, graph, num_pixels, alpha_channel, beta, space_delta, time_delta, alpha_floodplains=None,
+                   flagnancheck=False):
+        """A router on an existing device graph (ctypes handle, e.g. from lf_graph_restrict: the local part of a cut
+        network, lisflood_code_b200/parallel.py); the router owns the graph.  Maps: NumPy arrays or CUDA tensors in the
+        graph's compressed order."""
+        L = _capi.lib()
+        self = cls.__new__(cls)
+        self.kinematic_wave_warning_printed = False
+        self.flagnancheck = flagnancheck
+        self.space_delta = space_delta
+        self.beta, self.inv_beta, self.b_minus_1 = beta, 1 / beta, beta - 1
+        self.num_pixels = int(num_pixels)
+        self._graph = graph
+        self._router = C.c_void_p()
+        alpha = self._as_map(alpha_channel)
+        alpha_fp = None if alpha_floodplains is None else self._as_map(alpha_floodplains)
+        if np.ndim(space_delta) == 0 and not hasattr(space_delta, "data_ptr"):
+            dx, dxs = None, float(space_delta)
+        else:
+            dx, dxs = self._as_map(space_delta), 0.0
+        r = C.c_void_p()
+        _capi.check(L.lf_router_create(graph, _capi.ptr(alpha), float(beta), _capi.ptr(dx), dxs, float(time_delta),
+                                       _capi.ptr(alpha_fp), 1 if flagnancheck else 0, C.byref(r)))
+        self._router = r
+        no, k, npix, pits = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _capi.check(L.lf_graph_info(graph, C.byref(npix), C.byref(no), C.byref(k), C.byref(pits)))
+        self.num_orders, self.max_upstream, self.num_pits = no.value, k.value, pits.value
+        self._cache = {}
+        return self
+
     def _as_map(self, v):
+        if hasattr(v, "data_ptr"):       # torch tensor (host or CUDA): float64, contiguous, one value per pixel
+            assert v.is_contiguous() and v.element_size() == 8 and v.numel() == self.num_pixels
+            return v
         return np.ascontiguousarray(np.broadcast_to(np.asarray(v, np.float64), (self.num_pixels,)))
 
     # ---- graph attributes of the reference object (lazy; bit-identical) -------------------------
@@ -103,21 +142,30 @@ class kinematicWave:
     def kinematicWaveRouting(self, discharge, specific_lateral_inflow, section="main_channel"):
         """Kinematic wave routing of one step; `discharge` (float64[N]) is updated in place."""
         sec = self._section(section)
-        if not (isinstance(discharge, np.ndarray) and discharge.dtype == np.float64 and discharge.flags.c_contiguous
-                and discharge.size == self.num_pixels):
-            raise TypeError("discharge must be a C-contiguous float64 array of %d pixels" % self.num_pixels)
         q = self._as_map(specific_lateral_inflow)
         bad = C.c_int(0)
-        _capi.check(_capi.lib().lf_router_route(self._router, discharge, q, sec, C.byref(bad)))
+        fast = (isinstance(discharge, np.ndarray) and discharge.dtype == np.float64 and discharge.flags.c_contiguous
+                and discharge.size == self.num_pixels)
+        if fast:
+            _capi.check(_capi.lib().lf_router_route(self._router, discharge, q, sec, C.byref(bad)))
+        else:
+            # like the reference, any array-like that supports item assignment is accepted (float32, views, strided,
+            # NumpyModified): routed on a float64 copy, written back in place
+            if np.size(discharge) != self.num_pixels:
+                raise ValueError("discharge must hold %d pixels" % self.num_pixels)
+            tmp = np.ascontiguousarray(np.asarray(discharge, np.float64)).reshape(-1).copy()
+            _capi.check(_capi.lib().lf_router_route(self._router, tmp, q, sec, C.byref(bad)))
+            discharge[...] = tmp.reshape(np.shape(discharge))
         self._warn(bad.value)
 
     # ---- device-resident extension ---------------------------------------------------------------
     def set_discharge(self, discharge, section="main_channel"):
-        _capi.check(_capi.lib().lf_router_set_discharge(self._router, self._section(section), self._as_map(discharge)))
+        _capi.check(_capi.lib().lf_router_set_discharge(self._router, self._section(section),
+                                                        _capi.ptr(self._as_map(discharge))))
 
     def set_lateral_inflow(self, specific_lateral_inflow, section="main_channel"):
         _capi.check(_capi.lib().lf_router_set_inflow(self._router, self._section(section),
-                                                     self._as_map(specific_lateral_inflow)))
+                                                     _capi.ptr(self._as_map(specific_lateral_inflow))))
 
     def run(self, nsteps, inflow_scale=None, section="main_channel"):
         """nsteps consecutive kinematicWaveRouting calls on the resident state, executed as one
@@ -135,7 +183,7 @@ class kinematicWave:
     def get_discharge(self, section="main_channel", out=None):
         if out is None:
             out = np.empty(self.num_pixels, np.float64)
-        _capi.check(_capi.lib().lf_router_get_discharge(self._router, self._section(section), out))
+        _capi.check(_capi.lib().lf_router_get_discharge(self._router, self._section(section), _capi.ptr(out)))
         return out
 
     def accuflux(self, x):

@@ -1,5 +1,6 @@
-"""Host logic of the LDD-cut multi-GPU path on CPU: partition invariants, and a world_size-2 (and 3) gloo run
-with the CPU oracle as compute stand-in that must reproduce the single-process result BIT FOR BIT."""
+"""Host logic of the LDD-cut multi-GPU path on CPU: partition invariants, the exchange plan (ghost sets, import blocks,
+export targets), and world_size-2 / 3 gloo runs with the CPU oracle as compute stand-in that must reproduce the
+single-process result BIT FOR BIT (owner -> owner cut edges in any direction, no hub rank)."""
 import os
 import socket
 
@@ -18,92 +19,123 @@ def _case(rows=60, cols=48, seed=5, noise=0.3, maskf=0.1):
     return ldd[mask], mask, alpha, q0, q, dx
 
 
+def _plan(ldd, mask, world, nsec=1, cap=8):
+    from lisflood_code_b200.parallel import CutPlan, cut_edges_numpy, partition_numpy
+    owner = partition_numpy(ldd, mask, world)
+    eu, ed = cut_edges_numpy(ldd, mask, owner)
+    return owner, CutPlan({"kw": (eu, ed, owner[eu], owner[ed], nsec, cap)}, world)
+
+
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_partition_invariants(world):
-    from lisflood_code_b200.parallel import Partition
+    from lisflood_code_b200.global_modules import ldd_ops
     ldd, mask, *_ = _case(90, 70, 9, 0.3, 0.05)
-    P = Partition(ldd, mask, world)
-    n = P.n
-    assert sum(P.loads) == n and P.owner.min() >= 0 and P.owner.max() < world
-    ds = P.downstream
-    has = ds >= 0
-    crossing = has & (P.owner != P.owner[np.maximum(ds, 0)])
-    # every link that crosses ranks goes INTO rank 0 (the trunk) and is a registered cut edge
-    assert np.all(P.owner[ds[crossing]] == 0)
-    cut_all = np.concatenate([c for c in P.cut_pixels]) if world > 1 else np.array([], int)
-    assert set(np.flatnonzero(crossing)) == set(cut_all.tolist())
+    owner, plan = _plan(ldd, mask, world)
+    n = owner.size
+    loads = np.bincount(owner, minlength=world)
+    assert loads.sum() == n and owner.min() >= 0 and owner.max() < world
+    ds = ldd_ops.downstream_index(ldd, mask)
+    crossing = (ds >= 0) & (owner != owner[np.maximum(ds, 0)])
+    eu = plan.g["kw"][0]
+    assert set(np.flatnonzero(crossing)) == set(eu.tolist())
     if world > 1:
-        assert max(P.loads) <= 1.6 * n / world + 64          # balance
-        assert P.trunk.sum() < 0.2 * n
-    # xslot bookkeeping
+        assert loads.max() <= 1.6 * n / world + 64          # balance
+        assert crossing.sum() > 0
+        size = ldd_ops.accuflux(ds, np.ones(n))
+        trunk = size > 0.25 * n / world
+        assert trunk.sum() < 0.2 * n
+        # the trunk is spread over the ranks: a trunk pixel sits with its largest tributary
+        for p in np.flatnonzero(trunk)[:50]:
+            ups = np.flatnonzero(ds == p)
+            assert owner[p] == owner[ups[np.argmax(size[ups])]]
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_exchange_plan_is_consistent(world):
+    ldd, mask, *_ = _case(90, 70, 9, 0.3, 0.05)
+    owner, plan = _plan(ldd, mask, world, nsec=2, cap=6)
+    eu, ed, ou, od, nsec, cap = plan.g["kw"]
+    seen = {}
     for r in range(world):
-        x = P.local_xslot(r)
-        assert (x >= 0).sum() == (P.n_cut[r] if r else 0)
-        assert (x <= -2).sum() == (P.n_import if r == 0 else 0)
-
-
-class CpuStandInBackend(object):
-    """Router protocol of lisflood_code_b200.parallel.GpuRouterBackend on top of the CPU oracle (test stand-in:
-    it lets the partition / exchange host logic run under gloo without a GPU)."""
-    device = "cpu"
-
-    def __init__(self, ldd_local, sub_mask, alpha, beta, dx, dt, xslot, n_exp, n_imp, export, imported, max_steps, world):
-        from oracle import lisf_oracle
-        self.kw = lisf_oracle.KinematicWaveOracle(ldd_local, sub_mask, alpha, beta, dx, dt)
-        self.Q = np.zeros(xslot.size)
-        self.q = np.zeros(xslot.size)
-        self.cap, self.n_exp, self.n_imp = max_steps, n_exp, n_imp
-        self.exp = export.numpy().reshape(-1, max_steps)
-        self.imp = imported.numpy().reshape(-1, max_steps)
-        self.fixed = (xslot <= -2).astype(np.uint8)
-        self.ghost_slot = np.where(xslot <= -2, -2 - xslot, 0)
-        self.export_idx = np.flatnonzero(xslot >= 0)
-        self.export_slot = xslot[self.export_idx]
-
-    def set_discharge(self, q):
-        self.Q = q.copy()
-
-    def set_lateral_inflow(self, q):
-        self.q = q.copy()
-
-    def run(self, nsteps, inflow_scale):
-        for s in range(nsteps):
-            q = self.q if inflow_scale is None else self.q * inflow_scale[s]
-            fv = self.imp[self.ghost_slot, s] if self.n_imp else None
-            self.kw.kinematicWaveRouting(self.Q, q, fixed=self.fixed if self.n_imp else None, fixed_values=fv)
-            if self.n_exp:
-                self.exp[self.export_slot, s] = self.Q[self.export_idx]
-
-    def get_discharge(self):
-        return self.Q.copy()
-
-    def before_send(self):
-        pass
-
-    def after_recv(self):
-        pass
+        P = plan.rank_plan("kw", r)
+        loc = np.flatnonzero((owner == r) | np.isin(np.arange(owner.size), plan.ghosts[r]))
+        x = plan.xslot("kw", r, loc)
+        assert (x >= 0).sum() == P.n_export and ((x <= -2) & (x != -2 ** 31)).sum() == P.n_import
+        assert np.array_equal(loc[x >= 0][np.argsort(x[x >= 0])], P.export_pixels)
+        assert np.array_equal(owner[P.export_pixels], np.full(P.n_export, r))
+        assert np.all(owner[P.import_pixels] != r)
+        # the import block of this rank lies inside its region, blocks of 2 parities
+        assert P.import_offset + 2 * P.n_import * nsec * cap <= plan.region_doubles[r]
+        for k in range(P.n_export):
+            c = int(P.export_peer[k])
+            Pc = plan.rank_plan("kw", c)
+            slot, rem = divmod(int(P.export_offset[k]) - Pc.import_offset, nsec * cap)
+            assert rem == 0 and 0 <= slot < Pc.n_import
+            assert Pc.import_pixels[slot] == P.export_pixels[k]          # producer and consumer agree on the slot
+            assert P.export_parity_stride[k] == Pc.n_import * nsec * cap
+            seen[(c, slot)] = seen.get((c, slot), 0) + 1
+    assert len(seen) == eu.size and set(seen.values()) == {1}              # every import slot has exactly one producer
 
 
 def _worker(rank, world, port, tmp):
+    """Stand-in for the device path: every rank routes its sub-mask (own pixels + ghosts) with the CPU oracle, ghost
+    values prescribed; the ranks exchange the discharges of their cut edges through the plan's tables and repeat the
+    step until nothing changes (a value is final once its upstream path has been exchanged across all its cuts)."""
     import sys
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from lisflood_code_b200.parallel import DistributedKinematicWave
+    from oracle import lisf_oracle
     ldd, mask, alpha, q0, q, dx = _case()
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from test_parallel_cpu import CpuStandInBackend
-    D = DistributedKinematicWave(ldd, mask, alpha, 0.6, dx, 3600.0, max_steps=8, backend=CpuStandInBackend)
-    D.set_discharge(q0)
-    D.set_lateral_inflow(q)
+    owner, plan = _plan(ldd, mask, world)
+    n = owner.size
+    keep = owner == rank
+    keep[plan.ghosts[rank]] = True
+    loc = np.flatnonzero(keep)
+    sub = np.zeros(mask.shape, bool)
+    sub[mask] = keep
+    kw = lisf_oracle.KinematicWaveOracle(ldd[loc], sub, alpha[loc], 0.6, dx[loc], 3600.0)
+    P = plan.rank_plan("kw", rank)
+    x = plan.xslot("kw", rank, loc)
+    ghost = (x <= -2).astype(np.uint8)
+    ghost_pos = np.flatnonzero(x <= -2)
+    ghost_slot = -2 - x[ghost_pos]
+    exp_pos = np.flatnonzero(x >= 0)[np.argsort(x[x >= 0])]
+    remote_slot = (P.export_offset - plan.import_offset["kw"][P.export_peer]) // plan.g["kw"][5]
+    Q = np.ascontiguousarray(q0[loc])
     rng = np.random.default_rng(3)
-    for chunk in range(3):
-        D.run(5, inflow_scale=rng.uniform(0.5, 1.5, 5))
-    out = D.gather_discharge()
+    rounds_max = 0
+    for step in range(15):
+        scale = rng.uniform(0.5, 1.5)
+        Qold, imported, rounds = Q.copy(), np.zeros(max(P.n_import, 1)), 0
+        while True:
+            rounds += 1
+            Q = Qold.copy()
+            fv = np.zeros(loc.size)
+            fv[ghost_pos] = imported[ghost_slot]
+            kw.kinematicWaveRouting(Q, q[loc] * scale, fixed=ghost if P.n_import else None, fixed_values=fv if P.n_import else None)
+            out = [None] * world
+            dist.all_gather_object(out, [(int(P.export_peer[k]), int(remote_slot[k]), float(Q[exp_pos[k]])) for k in range(P.n_export)])
+            new = imported.copy()
+            for msgs in out:
+                for c, slot, val in msgs:
+                    if c == rank:
+                        new[slot] = val
+            changed = [None] * world
+            dist.all_gather_object(changed, bool(np.any(new != imported)))
+            imported = new
+            if not any(changed):
+                break
+        rounds_max = max(rounds_max, rounds)
+    parts = [None] * world
+    dist.all_gather_object(parts, (loc[owner[loc] == rank], Q[owner[loc] == rank]))
     if rank == 0:
-        np.save(os.path.join(tmp, "dist_w%d.npy" % world), out)
-        np.save(os.path.join(tmp, "cuts_w%d.npy" % world), np.array(D.part.n_cut))
+        full = np.empty(n)
+        for idx, val in parts:
+            full[idx] = val
+        np.save(os.path.join(tmp, "dist_w%d.npy" % world), full)
+        np.save(os.path.join(tmp, "meta_w%d.npy" % world), np.array([plan.g["kw"][0].size, rounds_max]))
     dist.destroy_process_group()
 
 
@@ -116,14 +148,12 @@ def test_gloo_cut_network_is_bit_identical(tmp_path, world, oracle):
     s.close()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     got = np.load(tmp_path / ("dist_w%d.npy" % world))
-    cuts = np.load(tmp_path / ("cuts_w%d.npy" % world))
-    assert cuts[1:].sum() > 0, "the test catchment must actually be cut"
+    ncut, rounds = np.load(tmp_path / ("meta_w%d.npy" % world))
+    assert ncut > 0, "the test catchment must actually be cut"
     ldd, mask, alpha, q0, q, dx = _case()
     ora = oracle.KinematicWaveOracle(ldd, mask, alpha, 0.6, dx, 3600.0)
     Q = q0.copy()
     rng = np.random.default_rng(3)
-    for chunk in range(3):
-        sc = rng.uniform(0.5, 1.5, 5)
-        for s_ in range(5):
-            ora.kinematicWaveRouting(Q, q * sc[s_])
+    for step in range(15):
+        ora.kinematicWaveRouting(Q, q * rng.uniform(0.5, 1.5))
     assert np.array_equal(got, Q)
