@@ -230,6 +230,9 @@ def run_ours(args):
 
 
 def run_c3(args):
+    """C3 = BASELINE.json configs[2]: 10000x10000, full soil + infiltration + overland + channel stack.  With N > 1 ranks
+    the SAME raster (same seeds) is cut along its drainage graph over the N GPUs (strong scaling; `--workload c3-replicas`
+    keeps the round-1 behaviour: one independent raster per rank, weak scaling)."""
     rank, world, local = dist_env()
     import torch
     from lisflood_code_b200 import _capi
@@ -238,20 +241,23 @@ def run_c3(args):
     torch.cuda.set_device(local)
     _capi.check(L.lf_device_init(local))
     use_dist = world > 1
+    cut = use_dist and args.workload == "c3"
     if use_dist:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.manual_seed(1234 + rank)
     rows, cols = args.rows, args.cols
     t0 = time.time()
-    dev = C3Device(rows, cols, seed=300 + rank, ldd_noise=args.ldd_noise, no_rout_steps=24)
+    dev = C3Device(rows, cols, seed=300 + (0 if cut or not use_dist else rank), ldd_noise=args.ldd_noise, no_rout_steps=24,
+                   distributed=cut)
     M = dev.model
     if os.environ.get("LF_EARLY_BPS"):      # tuning runs: resident blocks per SM of the early isolated-pixel launch
         M.set_option("early_blocks_per_sm", int(os.environ["LF_EARLY_BPS"]))
+    M.set_option("overlap_isolated", 1 if args.overlap else 0)
     _capi.synchronize()
     t_init = time.time() - t0
     info = M.info()
-    n, K, W = dev.n, args.steps, args.warmup
+    n, nl, K, W = dev.n, dev.n_local, args.steps, args.warmup
+    total_cells = n if (cut or not use_dist) else n * world
 
     def barrier():
         torch.cuda.synchronize()
@@ -259,26 +265,34 @@ def run_c3(args):
             dist.barrier()
         _capi.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op="max"):
         if not use_dist:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---- device-resident leg: forcing already in HBM, two alternating sets --------------------------
-    # Per step the meteorological maps (Rain, SnowMelt, ETRef, EWRef, ESRef, isFrozenSoil) change; LAI / LAITerm are
-    # 10-day maps in LISFLOOD (leafarea.py:76-90) and are set once, as in the end-to-end leg.  The synthetic initial
-    # state is cold (3.3 % of the soil columns need several Darcy sub-steps, 1.2 % once it has relaxed), so the model
-    # is spun up for `--spinup` untimed steps first, like the reference's pre-run (the W warm-up steps follow).
-    Fdev = [dev.forcing_device(i) for i in range(2)]
+    # ---- device-resident leg: the RAW meteo maps of the step (float32, as the NetCDF forcing holds them) are already in
+    #      HBM, two alternating sets; a step = feeder modules (readmeteo scaling + snow + frost) + soil + overland + 24
+    #      channel sub-steps.  LAI maps are 10-day maps in LISFLOOD (leafarea.py:76-90): set once, as in the e2e leg.  The
+    #      synthetic initial state is cold, so the model is spun up for `--spinup` untimed steps first, like the
+    #      reference's pre-run (the W warm-up steps follow).
+    M.set_lai(dev.lai_device(), **({"local": True} if cut else {}))
+    Fdev = [dev.forcing_device() for _ in range(2)]
     torch.cuda.synchronize()
-    M.step(Fdev[0])
-    Fdev = [{k: v for k, v in F.items() if k not in ("LAI", "LAITerm")} for F in Fdev]
+    feed = (lambda F, day, asynchronous=False: M.feed(F, day, asynchronous=asynchronous, local=True)) if cut else \
+        (lambda F, day, asynchronous=False: M.feed(F, day, asynchronous=asynchronous))
+    day = [20]
+
+    def one_step(F):
+        day[0] = day[0] % 365 + 1
+        feed(F, day[0])
+        M.step()
+
     for w in range(args.spinup):
-        M.step(Fdev[(w + 1) % 2])
+        one_step(Fdev[w % 2])
     for w in range(W):
-        M.step(Fdev[w % 2])
+        one_step(Fdev[w % 2])
     barrier()
     M.stage_times(reset=True)
     _capi.launch_count(reset=True)
@@ -286,99 +300,73 @@ def run_c3(args):
         barrier()
         _capi.timer_start()
         for k in range(K):
-            M.step(Fdev[k % 2])
+            one_step(Fdev[k % 2])
         ms = _capi.timer_stop()
         barrier()
     launches = _capi.launch_count()
-    st_overlapped = M.stage_times(reset=True)
-    # Second timed region, same K steps, with the co-scheduling switched off: every stage then runs alone on the GPU, so
-    # its CUDA-event time is the kernel's own duration (in the first region the early launch of the isolated channel
-    # pixels shares the SMs with the soil stage: each stage's events then also contain the other's work).
-    M.set_option("overlap_isolated", 0)
-    M.step(Fdev[0])
-    barrier()
-    M.stage_times(reset=True)
-    _capi.timer_start()
-    for k in range(K):
-        M.step(Fdev[(k + 1) % 2])
-    ms_serial = _capi.timer_stop()
     st = M.stage_times(reset=True)
     M.soil_stats(enable_timing=True)      # one extra (untimed) step with per-kernel events in the soil stage
-    M.step(Fdev[0])
+    one_step(Fdev[0])
     soil_stats = M.soil_stats(enable_timing=False)
-    M.set_option("overlap_isolated", 1)
-    ms = max_over_ranks(ms)
-    total_cells = n * world
+    ms = reduce_ranks(ms)
     value = total_cells * K / (ms * 1e-3)
+    nst = max(st["steps"], 1)
+    soil_ms, of_ms, ch_ms = st["soil_ms"] / nst, st["overland_ms"] / nst, st["channel_ms"] / nst
+    xstat = M.status() if cut else None
     if args.no_e2e:
         if rank == 0:
             print(json.dumps({"profile_only": True, "value": value, "ms_per_step": ms / K, "gpu_launches": launches,
-                              "ms_per_step_serial": ms_serial / K,
-                              "stage_ms_per_step": {k: v / max(st["steps"], 1) for k, v in st.items() if k != "steps"},
-                              "stage_ms_per_step_overlapped": {k: v / max(st_overlapped["steps"], 1)
-                                                               for k, v in st_overlapped.items() if k != "steps"},
-                              "soil_stats": soil_stats}))
+                              "stage_ms_per_step": {"soil_ms": soil_ms, "overland_ms": of_ms, "channel_ms": ch_ms},
+                              "soil_stats": soil_stats, "exchange_aborted": xstat[0] if xstat else None}))
+        if use_dist:
+            dist.destroy_process_group()
         return
 
-    # ---- end-to-end leg: per step the meteo forcing maps come from pinned HOST memory and the discharge map
-    #      (ChanQAvg = dis) goes back to the host; LAI maps are 10-day maps in LISFLOOD and stay resident ----
-    names = ("Rain", "SnowMelt", "ETRef", "EWRef", "ESRef")
+    # ---- end-to-end leg: per step the four RAW meteo maps (float32) come from pinned HOST memory -- copied on the copy
+    #      stream while the previous step computes -- and the discharge map (ChanQAvg = dis) goes back to the host; the
+    #      10-day LAI maps stay resident ----
+    names = ("Precipitation", "Tavg", "ET0", "E0")
     host_sets = []
     for i in range(2):
-        hs = {k: torch.empty(n, dtype=torch.float64, pin_memory=True) for k in names}
-        hs["isFrozenSoil"] = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        hs = {k: torch.empty(nl, dtype=torch.float32, pin_memory=True) for k in names}
         for k in hs:
             hs[k].copy_(Fdev[i][k])
         host_sets.append(hs)
-    dis_host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    dis_host = torch.empty(nl, dtype=torch.float64, pin_memory=True)
     torch.cuda.synchronize()
     Ke = max(2, min(K, 5))
 
-    def upload(i):
-        hs = host_sets[i % 2]
-        for k in names:
-            M.set_async(k, hs[k])                 # H2D on the copy stream, overlaps the step in flight
-        M.set_flags("isFrozenSoil", hs["isFrozenSoil"])
-
     def e2e_step(i):
-        M.step()                                  # forcing of step i was queued by upload(i)
-        upload(i + 1)                             # next step's forcing crosses PCIe while step i computes
+        M.step()                                  # forcing of step i was queued by the feed() of the previous call
+        day[0] = day[0] % 365 + 1
+        feed(host_sets[(i + 1) % 2], day[0], asynchronous=True)   # next step's raw maps cross PCIe while step i computes
         M.get_into("ChanQAvg", dis_host)          # D2H of this step's discharge map (synchronises)
 
-    upload(0)
+    feed(host_sets[0], day[0], asynchronous=True)
     e2e_step(0)
     barrier()
     t0 = time.perf_counter()
     for k in range(Ke):
         e2e_step(k + 1)
     barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s = reduce_ranks(time.perf_counter() - t0)
     e2e_value = total_cells * Ke / e2e_s
-    h2d = n * 8 * len(names) + n
-    d2h = n * 8
+    h2d = nl * 4 * len(names)
+    d2h = nl * 8
 
     # ---- rooflines ---------------------------------------------------------------------------------------
     peak, peak_kind = measured_peaks()
-    nst = max(st["steps"], 1)
-    soil_ms, of_ms, ch_ms = st["soil_ms"] / nst, st["overland_ms"] / nst, st["channel_ms"] / nst
-    soil_gbs = ALG_BYTES_SOIL * n / (soil_ms * 1e-3) / 1e9
-    chan_bytes = n * 24 * ALG_BYTES_CHANNEL_SUBSTEP
+    soil_gbs = ALG_BYTES_SOIL * nl / (soil_ms * 1e-3) / 1e9
+    chan_bytes = nl * 24 * ALG_BYTES_CHANNEL_SUBSTEP
     chan_gbs = chan_bytes / (ch_ms * 1e-3) / 1e9
     stage = {"soil_ms": round(soil_ms, 3), "overland_ms": round(of_ms, 3), "channel_ms": round(ch_ms, 3),
-             "step_ms": round(ms_serial / K, 3),
-             "note": "stages timed alone (second timed region of the same K steps, co-scheduling off)"}
-    nso = max(st_overlapped["steps"], 1)
-    stage_overlapped = {"soil_ms": round(st_overlapped["soil_ms"] / nso, 3),
-                        "overland_ms": round(st_overlapped["overland_ms"] / nso, 3),
-                        "channel_ms": round(st_overlapped["channel_ms"] / nso, 3), "step_ms": round(ms / K, 3),
-                        "note": "the timed region of `value`: the isolated non-channel pixels' sub-steps start at the top of "
-                                "the step and share the SMs with the soil and overland stages"}
+             "feeder_and_rest_ms": round(ms / K - soil_ms - of_ms - ch_ms, 3)}
     dominant = "soil_ms" if soil_ms >= ch_ms else "channel_ms"
     traffic = None   # measured DRAM bytes of the soil stage per step from the committed ncu capture (same raster size only)
     try:
         with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_soil_stage_c3_traffic.json")) as f:
             tj = json.load(f)
-        if int(tj["cells"]) == int(n):
+        if int(tj["cells"]) == int(nl):
             traffic = int(tj["soil_stage_bytes"])
     except (OSError, ValueError, KeyError):
         pass
@@ -386,37 +374,49 @@ def run_c3(args):
                  "(per-cell stencil: canopy+soil column+open/sealed+per-pixel sums+groundwater)", "achieved": round(soil_gbs, 1), "peak": peak, "peak_kind": peak_kind,
                  "unit": "GB/s", "frac": round(soil_gbs / peak, 4), "traffic": traffic, "alg_bytes_per_cell": ALG_BYTES_SOIL,
                  "avg_launch_ms": round(soil_ms, 3)}
-    roof_chan = {"bound": "hbm", "kernel": "k_chan_diagonal + k_chan_isolated (24 fused channel sub-steps)",
+    fp64 = fp64_roofline(nl, info, ch_ms, clk.summary())
+    roof_chan = {"bound": "hbm", "kernel": "k_chan_diagonal + k_chan_isolated_ws (24 fused channel sub-steps)",
                  "achieved": round(chan_gbs, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                  "frac": round(chan_gbs / peak, 4), "traffic": None,
                  "alg_bytes_per_cell_substep": ALG_BYTES_CHANNEL_SUBSTEP, "stage_ms": round(ch_ms, 3),
-                 "note": "FP64 Newton/pow bound, not HBM bound (DESIGN.md §4.2)"}
+                 "note": "this stage is bound by the FP64 pipe, not by HBM: see roofline_fp64 (DESIGN.md section 4.5)",
+                 "roofline_fp64": fp64}
     roofline = dict(roof_soil if dominant == "soil_ms" else roof_chan)
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_baseline_c3(args)
     if rank == 0:
+        config = {"workload": "C3 synthetic %dx%d raster, full stack per step: feeder modules (meteo scaling + snow + frost) + "
+                              "soil + infiltration + overland + 24 channel sub-steps, single kinematic routing, random D8 LDD "
+                              "(noise/tilt %.2f)%s" % (rows, cols, args.ldd_noise,
+                                                       "; ONE raster cut along its drainage graph over %d GPUs, boundary "
+                                                       "discharges exchanged in-kernel over NVLink peer memory" % world
+                                                       if cut else ("; one independent raster per GPU" if use_dist else "")),
+                  "cells": total_cells, "cells_per_gpu": nl, "no_rout_steps": 24, "levels_overland": info["levels_overland"],
+                  "levels_channel": info["levels_channel"], "channel_fraction": round(dev.channel_fraction, 4),
+                  "isolated_channel_pixels": info["isolated_channel_pixels"], "device_bytes_maps": info["device_bytes"],
+                  "l2_policy": "every map is %.0f MB per GPU (> 126 MB L2 for more than ~1.6e7 cells per GPU); two raw forcing "
+                               "sets alternate between steps, the 10-day LAI maps stay resident" % (nl * 8 / 1e6),
+                  "spinup_steps": args.spinup, "co_scheduled_isolated_pixels": bool(args.overlap)}
+        if cut:
+            summ = M.plan.summary()
+            config.update({"cells_per_rank": M.loads, "trunk_pixels": M.n_trunk, "subtrees": M.n_roots,
+                           "cut_edges": {g: summ[g]["cut_edges"] for g in summ},
+                           "cut_edges_in_per_rank": {g: summ[g]["imports_per_rank"] for g in summ},
+                           "bytes_exchanged_per_step": int(summ["overland"]["cut_edges"] * 3 * 8 +
+                                                           summ["channel"]["cut_edges"] * 24 * 8),
+                           "exchange_aborted": xstat[0]})
         line = {"metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K,
-                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "C3 synthetic %dx%d raster, full soil+infiltration+overland+channel stack, "
-                                       "24 channel sub-steps per model step, single kinematic routing, random D8 LDD "
-                                       "(noise/tilt %.2f)" % (rows, cols, args.ldd_noise),
-                           "cells": n, "cells_per_gpu": n, "no_rout_steps": 24, "levels_overland": info["levels_overland"],
-                           "levels_channel": info["levels_channel"], "channel_fraction": round(dev.channel_fraction, 4),
-                           "isolated_channel_pixels": info["isolated_channel_pixels"],
-                           "device_bytes_maps": info["device_bytes"],
-                           "l2_policy": "every map is %.0f MB (> 126 MB L2 for rasters above ~4000^2); two meteo forcing sets "
-                                        "alternate between steps, the 10-day LAI maps stay resident" % (n * 8 / 1e6),
-                           "spinup_steps": args.spinup},
+                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+                "scaling": "strong" if cut else "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": "cell-updates/s", "steps": Ke, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h),
-                        "note": "per step: Rain, SnowMelt, ETRef, EWRef, ESRef (f64) + isFrozenSoil (u8) from pinned host "
-                                "memory through HotPathModel.set_async/set_flags, discharge map ChanQAvg back to the host; "
-                                "the 10-day LAI maps stay resident"},
+                        "note": "per step and GPU: raw Precipitation, Tavg, ET0, E0 (float32, as the reference's NetCDF forcing) from "
+                                "pinned host memory through HotPathModel.feed (copy stream, overlapping the previous step), "
+                                "discharge map ChanQAvg (float64) back to the host; the 10-day LAI maps stay resident"},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
                 "roofline_stencil": roof_soil, "roofline_routing": roof_chan, "stage_ms_per_step": stage,
-                "stage_ms_per_step_overlapped": stage_overlapped,
                 "soil_stats": soil_stats,
                 "cpu_baseline": cpu, "init_s": round(t_init, 2)}
         print(json.dumps(line), flush=True)
@@ -424,18 +424,49 @@ def run_c3(args):
         dist.destroy_process_group()
 
 
+# FP64 instructions per pixel and channel sub-step of the isolated-pixel kernel, from the committed ncu capture
+# (profiles/r02_chan_isolated_fp64.json: sm__inst_executed_pipe_fp64 / (pixels x sub-steps)); the FP64 pipe of sm_100
+# issues 2 warp instructions per clock and SM (64 lanes: 37 TFLOP/s at 1.965 GHz).
+def fp64_roofline(n_local, info, ch_ms, clocks):
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_chan_isolated_fp64.json")) as f:
+            j = json.load(f)
+        per = float(j["fp64_warp_inst_per_pixel_substep"])
+    except (OSError, ValueError, KeyError):
+        return None
+    mhz = clocks.get("sm_mhz") or 1965.0
+    sms = 148
+    inst = per * info["isolated_channel_pixels"] * 24
+    peak = 2.0 * sms * mhz * 1e6
+    ach = inst / (ch_ms * 1e-3)
+    return {"bound": "fp64", "kernel": "k_chan_isolated_ws", "achieved": round(ach / 1e9, 2), "peak": round(peak / 1e9, 2),
+            "unit": "G warp-inst/s (FP64 pipe)", "frac": round(ach / peak, 4), "sm_mhz": mhz,
+            "fp64_warp_inst_per_pixel_substep": per,
+            "note": "lower bound of the pipe's utilisation: the wavefront kernels of the connected network run beside it"}
+
+
 class _C3Crop(object):
     """The bench's own generator (synthetic_gpu.c3_generate: same code, seed and torch random streams as the device
-    raster) at the crop size, collected on the host -- no library call -- with a cyclic list of forcing sets."""
+    raster) at the crop size, collected on the host -- no library call -- with a cyclic list of raw forcing sets and the
+    CPU restatement of the feeder modules in front of the model step."""
 
     def __init__(self, args, rows=None, nforcing=6):
         from lisflood_code_b200 import synthetic_gpu
+        from oracle.lisf_oracle_feeders import FeederOracle, lai_term
         r = rows or args.cpu_rows
-        self.S, self.F = synthetic_gpu.c3_host_stack(r, r, seed=300, nforcing=nforcing, ldd_noise=args.ldd_noise,
-                                                     no_rout_steps=24)
+        self.S, (P, state), lai, self.raw = synthetic_gpu.c3_host_stack(r, r, seed=300, nforcing=nforcing,
+                                                                       ldd_noise=args.ldd_noise, no_rout_steps=24)
+        n = self.S["N"]
+        Pm = {k: (np.full(n, v) if np.ndim(v) == 0 else v) for k, v in P.items() if k != "kgb"}
+        self.feeder = FeederOracle(Pm, state, self.S["DtSec"])
+        self.lai, self.laiterm = lai, lai_term(P["kgb"], lai)
+        self.day = 20
 
     def forcing(self, S, i, seed=None):
-        return self.F[i % len(self.F)]
+        self.day = self.day % 365 + 1
+        o = self.feeder.step(self.raw[i % len(self.raw)], self.day)
+        return {"Rain": o["Rain"], "SnowMelt": o["SnowMelt"], "ETRef": o["ETRef"], "EWRef": o["EWRef"], "ESRef": o["ESRef"],
+                "isFrozenSoil": o["isFrozenSoil"], "LAI": self.lai, "LAITerm": self.laiterm}
 
 
 def _c3_oracle(args, rows=None):
@@ -497,9 +528,9 @@ def run_reference_c3(args):
     print(json.dumps({"impl": "reference", "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s",
                       "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": "C3 synthetic %dx%d raster, full soil+infiltration+overland+channel stack, "
-                                             "24 channel sub-steps per model step, single kinematic routing, random D8 LDD "
-                                             "(noise/tilt %.2f)" % (args.rows, args.cols, args.ldd_noise),
+                      "config": {"workload": "C3 synthetic %dx%d raster, full stack per step: feeder modules (meteo scaling + snow + "
+                                             "frost) + soil + infiltration + overland + 24 channel sub-steps, single kinematic "
+                                             "routing, random D8 LDD (noise/tilt %.2f)" % (args.rows, args.cols, args.ldd_noise),
                                  "sample": "%dx%d crop of the same generator per step" % (args.cpu_rows, args.cpu_rows),
                                  "cells": S["N"], "no_rout_steps": 24},
                       "cpu_baseline": cpu,
@@ -651,7 +682,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c3-replicas", "c2", "c4"])
+    ap.add_argument("--overlap", type=int, default=0, help="1: co-schedule the isolated non-channel pixels with the soil stage")
     ap.add_argument("--c4-rows", type=int, default=6000)
     ap.add_argument("--c4-noise", type=float, default=0.2, help="noise/tilt of the C4 basin (0.2: a single catchment)")
     ap.add_argument("--rows", type=int, default=10000)
@@ -667,7 +699,7 @@ def main():
     args = ap.parse_args()
     if args.workload == "c4" and args.impl != "reference":
         run_c4(args)
-    elif args.workload == "c3":
+    elif args.workload in ("c3", "c3-replicas"):
         if args.impl == "reference":
             run_reference_c3(args)
         else:

@@ -176,6 +176,40 @@ int lf_model_stage_times(lf_model *m, int reset, double *soil_ms, double *overla
  * zeros in [2..6], of k_soil_pixel_flagged in [7] (all zeros unless timing was enabled by an earlier call with
  * enable_timing = 1).  Either pointer may be NULL.  Synchronises. */
 int lf_model_soil_stats(lf_model *m, int enable_timing, int64_t *deferred_columns, double *kernel_ms);
+/* Feeder modules of a step on the device: the scaling of readmeteo.dynamic
+ * (hydrological_modules/readmeteo.py:61-81), snow.dynamic (snow.py:95-187: three elevation zones, seasonal melt
+ * coefficient, summer ice melt) and frost.dynamic (frost.py:61-78), fused in one kernel that takes the RAW meteo maps of
+ * the step -- Precipitation [mm/day], Tavg [deg C], ET0, E0 [mm/day]; compressed order; dtype 0 = float64, 1 = float32
+ * (what the NetCDF forcing holds; widened to float64 exactly, all arithmetic is float64) -- and leaves Rain, SnowMelt,
+ * ETRef, EWRef, ESRef, isFrozenSoil for the soil stage, updates the states SnowCoverS (3,N), FrostIndex,
+ * TotalPrecipitation and (diagnostics build) writes Snow, SnowCover, Precipitation, Tavg.  The three season coefficients
+ * are the scalars of snow.py:104-117 for the calendar day (computed by the host mirror exactly as the reference does).
+ * Parameters by the reference's names -- PrScaling, CalEvaporation, DeltaTSnow, SnowSeason, TempSnow, SnowFactor,
+ * SnowMeltCoef, TempMelt, lat_rad, Kfrost, Afrost, FrostIndexThreshold, SnowWaterEquivalent, kgb -- are maps
+ * (lf_model_set) or scalars (lf_model_set_scalar), like the float-or-array results of the reference's loadmap.
+ * async = 1: host buffers (page-locked for a real overlap) are copied on the copy stream while the previous step computes
+ * and must stay untouched until the next synchronising call; two staging sets alternate.
+ * lf_model_set_lai: LAI (3,N) of the current 10-day interval and LAITerm = exp(-kgb * LAI) (leafarea.py:48,90). */
+int lf_model_set_scalar(lf_model *m, const char *name, double value);
+int lf_model_feed(lf_model *m, const void *precipitation, const void *tavg, const void *et0, const void *e0, int32_t dtype,
+                  double snowmelt_coeff, double ice_melt_coeff_north, double ice_melt_coeff_south, int32_t async);
+int lf_model_set_lai(lf_model *m, const double *lai, int64_t count);
+/* Structures inside the routing sub-step loop: reservoirs (four-regime outflow rule,
+ * hydrological_modules/reservoir.py:173-322) and lakes (Modified Puls, lakes.py:199-297), executed by the channel
+ * wavefront itself.  The model must have been created with ldd_kinematic = the channel network BEFORE
+ * structures.initial cuts it (`LddStructuresKinematic`, structures.py:43-61): the library applies the cut (nothing is
+ * routed into a structure pixel; its inflow is the ChanQ its upstream neighbours had after the previous sub-step,
+ * np.bincount(downstruct, ChanQ), reservoir.py:190 / lakes.py:215; its outflow joins the side flow, routing.py:472-476).
+ * reservoir_index / lake_index: compressed pixel indices (ReservoirIndex, LakeIndex), host arrays.
+ * lf_model_structure_array reads (set = 0) or writes (set = 1) a per-structure array (host or device pointer), in the
+ * order of the index arrays, by the reference's names: TotalReservoirStorageM3CC, ConservativeStorageLimitCC,
+ * NormalStorageLimitCC, Normal_FloodStorageLimitCC, FloodStorageLimitCC, MinReservoirOutflowCC, NormalReservoirOutflowCC,
+ * NonDamagingReservoirOutflowCC, DeltaO, DeltaLN, DeltaNFL, ReservoirStorageM3CC (state), ReservoirFillCC, QResOutM3DtCC
+ * (outputs of the last sub-step); LakeAreaCC, LakeFactor, LakeFactorSqr, LakeStorageM3CC, LakeOutflowCC, LakeInflowOldCC,
+ * LakeStorageM3BalanceCC (state), LakeLevelCC, QLakeOutM3DtCC (outputs). */
+int lf_model_set_structures(lf_model *m, int32_t n_reservoirs, const int64_t *reservoir_index, int32_t n_lakes,
+                            const int64_t *lake_index);
+int lf_model_structure_array(lf_model *m, const char *name, double *values, int64_t count, int32_t set);
 /* Execution options of a model (name, value):
  *   "overlap_isolated"     1 (default): lf_model_step starts the sub-steps of the non-channel isolated pixels of
  *                          LddKinematic (no side flow, routing.py:512) at the top of the step, on a low-priority

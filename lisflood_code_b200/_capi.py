@@ -88,6 +88,11 @@ SIGNATURES = {
     "lf_model_stage_times": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(_i64s)]),
     "lf_model_soil_stats": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "lf_model_set_scalar": (C.c_int, [_vp, C.c_char_p, C.c_double]),
+    "lf_model_feed": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32]),
+    "lf_model_set_lai": (C.c_int, [_vp, _vp, _i64s]),
+    "lf_model_set_structures": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, _vp]),
+    "lf_model_structure_array": (C.c_int, [_vp, C.c_char_p, _vp, _i64s, C.c_int32]),
     "lf_model_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "lf_model_nonfinite": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "lf_model_destroy": (None, [_vp]),

@@ -61,10 +61,76 @@ struct ChanPtrs {
     // split routing
     double *Q2k, *Q2r0, *Q2r1, *M32, *CS2A, *S1, *sumNotLast;
     const double *a2, *alpha2, *QLimit, *M3Limit, *C2M3Start, *C2QStart, *z2floor;
-    double InvDtRouting;
+    double InvDtRouting, DtRouting;
     int S, split;
     lfkw::Params P;
+    // structures in the sub-step loop (reservoir.py:173-322, lakes.py:199-297): sid[i] = +j+1 reservoir j, -(j+1) lake j,
+    // 0 none; feeds[i] != 0: the pixel drains into a structure (its ChanQ of every sub-step is kept in CQ[parity])
+    const int32_t *sid;
+    const uint8_t *feeds;
+    double *CQ0, *CQ1;
+    int gs0;                 // global index of sub-step 0 of this model step (parity of the CQ buffers)
+    struct Res {
+        double *Storage, *Fill, *OutM3;
+        const double *Total, *Cons, *Norm, *NormFlood, *Flood, *MinOut, *NormOut, *NonDam, *DeltaO, *DeltaLN, *DeltaNFL;
+    } res;
+    struct Lake {
+        double *Storage, *Outflow, *InflowOld, *Balance, *Level, *OutM3;
+        const double *Area, *Factor, *FactorSqr;
+    } lake;
 };
+
+// reservoir.dynamic_inloop, reservoir.py:173-322 (one reservoir, one routing sub-step): returns the outflow volume [m3]
+__device__ __forceinline__ double reservoir_substep(const ChanPtrs::Res &R, int j, double inflow, double DtRouting)
+{
+    const double inv_day = 1 / 86400.0;
+    const double total = R.Total[j], cons = R.Cons[j], flood = R.Flood[j], nflood = R.NormFlood[j];
+    const double omin = R.MinOut[j], onorm = R.NormOut[j], ondam = R.NonDam[j];
+    double storage = R.Storage[j] + inflow * DtRouting;                   // :196-200
+    const double fill = storage / total;                                    // :202
+    const double o1 = fmin(omin, storage * inv_day);                        // :205
+    const double o2 = omin + R.DeltaO[j] * (fill - 2 * cons) / R.DeltaLN[j];   // :209
+    const double o3a = onorm;
+    const double o3b = onorm + ((fill - nflood) / R.DeltaNFL[j]) * (ondam - onorm);   // :216-218
+    double temp = fmin(ondam, fmax(inflow * 1.2, onorm));                   // :222
+    const double o4 = fmax((fill - flood - 0.01) * total * inv_day, temp);  // :223
+    double out = o1;
+    out = fill > 2 * cons ? o2 : out;                                       // :232-240
+    out = fill > R.Norm[j] ? o3a : out;
+    out = fill > nflood ? o3b : out;
+    out = fill > flood ? o4 : out;
+    temp = fmin(out, fmax(inflow, onorm));                                  // :243
+    out = (out > 1.2 * inflow && out > onorm && fill < flood) ? temp : out; // :245-249
+    double out_m3 = out * DtRouting;                                        // :252
+    out_m3 = fmin(out_m3, storage);                                         // :258
+    out_m3 = fmax(out_m3, storage - total);                                 // :260
+    storage = storage - out_m3;                                             // :267
+    double f = storage / total;                                             // :271
+    f = (f != f || f < 0) ? 0.0 : f;                                        // :272-273
+    R.Storage[j] = storage;
+    R.Fill[j] = f;
+    R.OutM3[j] = out_m3;
+    return out_m3;
+}
+// lakes.dynamic_inloop, lakes.py:199-297 (Modified Puls): returns the outflow volume [m3]
+__device__ __forceinline__ double lake_substep(const ChanPtrs::Lake &K, int j, double inflow, double DtRouting)
+{
+    const double lake_in = (inflow + K.InflowOld[j]) * 0.5;                 // :224
+    K.InflowOld[j] = inflow;                                                // :227
+    const double factor = K.Factor[j];
+    const double indicator = K.Storage[j] / DtRouting - 0.5 * K.Outflow[j] + lake_in;   // :234
+    const double r = -factor + sqrt(K.FactorSqr[j] + 2 * indicator);        // :243
+    const double outflow = r * r;
+    const double out_m3 = outflow * DtRouting;                              // :248
+    double storage = (indicator - outflow * 0.5) * DtRouting;               // :252
+    storage = (storage != storage || storage < 0) ? 0.0 : storage;          // :255-256 (NaN / negative -> 0)
+    K.Balance[j] = K.Balance[j] + (lake_in * DtRouting - out_m3);           // :262
+    K.Outflow[j] = outflow;
+    K.Storage[j] = storage;
+    K.Level[j] = storage / K.Area[j];                                       // :266
+    K.OutM3[j] = out_m3;
+    return out_m3;
+}
 
 __device__ __forceinline__ double pw(double x, double y) { return lfm::pw(x, y); }
 
@@ -154,7 +220,7 @@ __device__ __forceinline__ void chan_substep(const ChanPtrs &C, int i, double U1
 constexpr int CH_THREADS = 128;
 
 // wavefront diagonal over channel-network pixels: positions [lo, hi), sub-step s = d - level
-template <bool QZ, bool HASX>
+template <bool QZ, bool HASX, bool HASS>
 __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo, int hi, int d)
 {
     int i = lo + blockIdx.x * CH_THREADS + threadIdx.x;
@@ -174,11 +240,26 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo
     }
     int c0 = C.cfirst[i], c1 = C.cend ? C.cend[i] : C.cfirst[i + 1];
     double U1 = 0., U2 = 0.;
+    double sideDt = C.sideDt[i];
+    int sid = 0;
+    if (HASS) sid = C.sid[i];
+    if (HASS && sid != 0) {
+        // A structure pixel: structures.initial turns the pixels draining into it into pits (structures.py:51-59), so
+        // nothing is routed into it (U = 0); its inflow is the ChanQ those pixels had after the PREVIOUS sub-step
+        // (np.bincount(downstruct, ChanQ), reservoir.py:190 / lakes.py:215 -- summed in pixel order = slot order), and
+        // the outflow volume of the sub-step joins its side flow (routing.py:472-476).
+        const double *CQprev = ((C.gs0 + s) & 1) ? C.CQ0 : C.CQ1;
+        double inflow = 0.;
+        for (int k = c0; k < c1; ++k) inflow += CQprev[k];
+        sideDt += sid > 0 ? reservoir_substep(C.res, sid - 1, inflow, C.DtRouting)
+                          : lake_substep(C.lake, -sid - 1, inflow, C.DtRouting);
+        c1 = c0;
+    }
     for (int k = c0; k < c1; ++k) U1 += QZ ? lfkw::pow5(Qr[k]) : Qr[k];
     ChanLocal X;
     X.qk = C.Qk[i];
     X.sum = s == 0 ? 0. : C.sumDis[i];  // sumDisDay = 0 before the sub-step loop, Lisflood_dynamic.py:177
-    const double L = C.L[i], alpha = C.alpha[i], a = C.a[i], sideDt = C.sideDt[i];
+    const double L = C.L[i], alpha = C.alpha[i], a = C.a[i];
     const bool isch = C.isChan[i] != 0;
     double alpha2 = 0, a2 = 0, ql = 0, m3l = 0, c2s = 0, c2q = 0, z2f = 0;
     if (C.split) {
@@ -201,6 +282,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo
         lfx::push(lfx::export_slot(C.X, xs, 0, s), qr1);
         if (C.split) lfx::push(lfx::export_slot(C.X, xs, 1, s), qr2);
     }
+    if (HASS && C.feeds[i]) (((C.gs0 + s) & 1) ? C.CQ1 : C.CQ0)[i] = X.chanq;
     C.Qk[i] = X.qk;
     C.sumDis[i] = X.sum;
     const bool last = s == C.S - 1;
@@ -428,6 +510,104 @@ __global__ void k_of_post(int n, const double *__restrict__ QO, const double *__
     }
 }
 
+
+// ---- feeder modules of a step, fused: readmeteo scaling (readmeteo.py:61-81), snow (snow.py:95-187),
+// frost (frost.py:61-78).  Raw meteo maps arrive in the reference's compressed order (float32 as read from NetCDF, or
+// float64) and are gathered into the soil stage's storage order here, so no separate layout translation is needed.
+struct ScalarOrMap {
+    const double *map;   // storage order, or nullptr
+    double value;
+    __device__ __forceinline__ double at(int64_t i) const { return map ? map[i] : value; }
+};
+struct FeedPtrs {
+    int64_t n;
+    const int32_t *pix_of_pos;
+    const void *prec, *tavg, *et0, *e0;
+    ScalarOrMap PrScaling, CalEvaporation, DeltaTSnow, SnowSeason, TempSnow, SnowFactor, SnowMeltCoef, TempMelt, lat_rad, Kfrost,
+        Afrost, FrostIndexThreshold, SnowWaterEquivalent;
+    double DtDay, snowmelt_coeff, ice_n, ice_s;
+    double *SnowCoverS, *FrostIndex, *TotalPrecipitation;       // state
+    double *Rain, *SnowMelt, *ETRef, *EWRef, *ESRef;            // forcing of the soil stage
+    uint8_t *frozen;
+    double *Snow, *SnowCover, *Precipitation, *Tavg;             // outputs kept for reporting (may be nullptr)
+};
+template <bool F32>
+__global__ void __launch_bounds__(256) k_feeder(FeedPtrs F)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F.n) return;
+    const int p = F.pix_of_pos[i];
+    double praw, tavg, et0, e0;
+    if (F32) {
+        praw = (double)((const float *)F.prec)[p];
+        tavg = (double)((const float *)F.tavg)[p];
+        et0 = (double)((const float *)F.et0)[p];
+        e0 = (double)((const float *)F.e0)[p];
+    } else {
+        praw = ((const double *)F.prec)[p];
+        tavg = ((const double *)F.tavg)[p];
+        et0 = ((const double *)F.et0)[p];
+        e0 = ((const double *)F.e0)[p];
+    }
+    const double dt = F.DtDay;
+    const double prec = praw * dt * F.PrScaling.at(i);               // readmeteo.py:66
+    const double cal = F.CalEvaporation.at(i);
+    const double etref = et0 * dt * cal, ewref = e0 * dt * cal;      // :68-69
+    F.ETRef[i] = etref;
+    F.EWRef[i] = ewref;
+    F.ESRef[i] = (ewref + etref) / 2;                                // :78
+    // snow.py:104-118
+    const bool north = F.lat_rad.at(i) > 0;
+    const double seas = F.SnowSeason.at(i) * (north ? F.snowmelt_coeff : -F.snowmelt_coeff) + F.SnowMeltCoef.at(i);
+    const double summer = north ? F.ice_n : F.ice_s;
+    const double dts = F.DeltaTSnow.at(i), tsnow = F.TempSnow.at(i), sfac = F.SnowFactor.at(i), tmelt = F.TempMelt.at(i);
+    double snow = 0., rain = 0., melt = 0., cover = 0.;
+#pragma unroll
+    for (int z = 0; z < 3; ++z) {                                    // :150-178, zones A (highest), B, C
+        const double tz = tavg + dts * (z - 1);
+        const double snow_s = tz < tsnow ? sfac * prec : 0.;
+        const double rain_s = tz >= tsnow ? prec : 0.;
+        double melt_s = (tz - tmelt) * seas * (1 + 0.01 * rain_s) * dt;
+        const double ice = (z < 2 ? tavg : tz) * 7.0 * dt * summer;
+        double sc = F.SnowCoverS[(int64_t)z * F.n + i];
+        melt_s = fmax(fmin(melt_s + ice, sc), 0.);
+        sc = sc + snow_s - melt_s;
+        F.SnowCoverS[(int64_t)z * F.n + i] = sc;
+        snow += snow_s;
+        rain += rain_s;
+        melt += melt_s;
+        cover += sc;
+    }
+    snow /= 3;
+    rain /= 3;
+    melt /= 3;
+    cover /= 3;
+    F.Rain[i] = rain;
+    F.SnowMelt[i] = melt;
+    F.TotalPrecipitation[i] = F.TotalPrecipitation[i] + (snow + rain);   // :186
+    // frost.py:66-73
+    double fi = F.FrostIndex[i];
+    const double rate = -(1 - F.Afrost.at(i)) * fi - tavg * exp(-0.04 * F.Kfrost.at(i) * cover / F.SnowWaterEquivalent.at(i));
+    fi = fmax(fi + rate * dt, 0.);
+    fi = fi > 57.0 ? 57.0 : fi;
+    F.FrostIndex[i] = fi;
+    F.frozen[i] = fi > F.FrostIndexThreshold.at(i) ? 1 : 0;
+    if (F.Snow) {
+        F.Snow[i] = snow;
+        F.SnowCover[i] = cover;
+        F.Precipitation[i] = prec;
+        F.Tavg[i] = tavg;
+    }
+}
+// LAITerm = exp(-kgb * LAI), leafarea.py:90
+__global__ void k_lai_term(const double *__restrict__ lai, ScalarOrMap kgb, double *__restrict__ out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double k = kgb.at(i);
+    for (int v = 0; v < 3; ++v) out[(int64_t)v * n + i] = exp(-k * lai[(int64_t)v * n + i]);
+}
+
 // ---- layout translation ----
 // reference (compressed row-major) order -> position order: a gather.  Four positions per thread: the four index loads
 // and then the four gathered values are in flight together (the kernel is bound by the latency of the scattered reads).
@@ -476,6 +656,21 @@ __global__ void k_i32_rows_to_pos(const int32_t *__restrict__ src, int32_t *__re
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[pix_of_pos[i]];
+}
+__global__ void k_struct_feeds(const int32_t *__restrict__ sid, const int32_t *__restrict__ cfirst, uint8_t *__restrict__ feeds,
+                               int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || sid[i] == 0) return;
+    for (int k = cfirst[i]; k < cfirst[i + 1]; ++k) feeds[k] = 1;
+}
+__global__ void k_struct_cq_init(const uint8_t *__restrict__ feeds, const double *__restrict__ ChanQ, double *__restrict__ CQ0,
+                                 double *__restrict__ CQ1, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !feeds[i]) return;
+    CQ0[i] = ChanQ[i];
+    CQ1[i] = ChanQ[i];
 }
 __global__ void k_rows_differ(const double *__restrict__ a, const double *__restrict__ b, int64_t n, int *__restrict__ flag)
 {
@@ -561,6 +756,20 @@ struct lf_model {
         int32_t n_export = 0, n_import = 0;
     } xs_of, xs_ch;
     int32_t x_parity = 0;
+    // feeder modules: scalar parameters (a map of the same name, when set, takes precedence) and the raw-forcing staging
+    std::map<std::string, double> scalars;
+    lf::DevBuf<uint8_t> raw_stage[2];      // 4 maps each, double-buffered: the upload of step k+1 overlaps step k
+    cudaEvent_t raw_copied[2] = {nullptr, nullptr}, raw_consumed[2] = {nullptr, nullptr};
+    int raw_turn = 0;
+    // structures in the routing sub-step loop (lf_model_set_structures)
+    struct Structures {
+        int32_t n_res = 0, n_lake = 0;
+        lf::DevBuf<int32_t> sid;
+        lf::DevBuf<uint8_t> feeds;
+        lf::DevBuf<double> CQ0, CQ1;
+        std::map<std::string, std::unique_ptr<lf::DevBuf<double>>> v;   // per-structure parameter / state arrays
+        bool cq_dirty = true;
+    } st;
     int overlap_isolated = 1;             // option "overlap_isolated"
     int early_blocks_per_sm = 2;          // option "early_blocks_per_sm"
     int nancheck = 0;                     // option "flagnancheck"
@@ -588,6 +797,10 @@ struct lf_model {
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (side_stream) cudaStreamDestroy(side_stream);
         if (early_stream) cudaStreamDestroy(early_stream);
+        for (int k = 0; k < 2; ++k) {
+            if (raw_copied[k]) cudaEventDestroy(raw_copied[k]);
+            if (raw_consumed[k]) cudaEventDestroy(raw_consumed[k]);
+        }
         if (ev_early_fork) cudaEventDestroy(ev_early_fork);
         if (ev_early_join) cudaEventDestroy(ev_early_join);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -611,6 +824,15 @@ const FieldSpec SPECS[] = {
     {"Rain", 1, SOIL, false, false}, {"SnowMelt", 1, SOIL, false, false}, {"ETRef", 1, SOIL, false, false},
     {"EWRef", 1, SOIL, false, false}, {"ESRef", 1, SOIL, false, false}, {"LAI", 3, SOIL, false, false},
     {"LAITerm", 3, SOIL, false, false},
+    // feeder modules (readmeteo scaling, snow, frost: lf_model_feed): parameters, state, outputs
+    {"PrScaling", 1, SOIL, false, false}, {"CalEvaporation", 1, SOIL, false, false}, {"DeltaTSnow", 1, SOIL, false, false},
+    {"SnowSeason", 1, SOIL, false, false}, {"TempSnow", 1, SOIL, false, false}, {"SnowFactor", 1, SOIL, false, false},
+    {"SnowMeltCoef", 1, SOIL, false, false}, {"TempMelt", 1, SOIL, false, false}, {"lat_rad", 1, SOIL, false, false},
+    {"Kfrost", 1, SOIL, false, false}, {"Afrost", 1, SOIL, false, false}, {"FrostIndexThreshold", 1, SOIL, false, false},
+    {"SnowWaterEquivalent", 1, SOIL, false, false}, {"kgb", 1, SOIL, false, false},
+    {"SnowCoverS", 3, SOIL, false, false}, {"FrostIndex", 1, SOIL, false, false}, {"TotalPrecipitation", 1, SOIL, false, false},
+    {"Snow", 1, SOIL, false, false}, {"SnowCover", 1, SOIL, false, false}, {"Precipitation", 1, SOIL, false, false},
+    {"Tavg", 1, SOIL, false, false},
     // per-pixel parameters
     {"b_Xinanjiang", 1, SOIL, false, false}, {"PowerPrefFlow", 1, SOIL, false, false}, {"UpperZoneK", 1, SOIL, false, false},
     {"GwPercStep", 1, SOIL, false, false}, {"LowerZoneK", 1, SOIL, false, false}, {"LZThreshold", 1, SOIL, false, false},
@@ -1157,9 +1379,50 @@ int chan_ptrs(lf_model *m, ChanPtrs &C, double **m32_out, double **c2s_out)
     LF_CHECK(flag_buf(m, "IsChannelKinematic", &isch));
     C.isChan = isch;
     C.InvDtRouting = 1 / m->DtRouting;
+    C.DtRouting = m->DtRouting;
     C.S = m->cfg.NoRoutSteps;
     C.split = m->cfg.SplitRouting;
     C.P = lfkw::make_params(m->cfg.Beta);
+    if (m->st.n_res + m->st.n_lake > 0) {
+        lf_model::Structures &T = m->st;
+        C.sid = T.sid.p;
+        C.feeds = T.feeds.p;
+        C.CQ0 = T.CQ0.p;
+        C.CQ1 = T.CQ1.p;
+        C.gs0 = (int)((m->steps * (int64_t)m->cfg.NoRoutSteps) & 1);
+        auto V = [&](const char *k) -> double * {
+            auto it = T.v.find(k);
+            return it == T.v.end() ? nullptr : it->second->p;
+        };
+        C.res.Storage = V("ReservoirStorageM3CC");
+        C.res.Fill = V("ReservoirFillCC");
+        C.res.OutM3 = V("QResOutM3DtCC");
+        C.res.Total = V("TotalReservoirStorageM3CC");
+        C.res.Cons = V("ConservativeStorageLimitCC");
+        C.res.Norm = V("NormalStorageLimitCC");
+        C.res.NormFlood = V("Normal_FloodStorageLimitCC");
+        C.res.Flood = V("FloodStorageLimitCC");
+        C.res.MinOut = V("MinReservoirOutflowCC");
+        C.res.NormOut = V("NormalReservoirOutflowCC");
+        C.res.NonDam = V("NonDamagingReservoirOutflowCC");
+        C.res.DeltaO = V("DeltaO");
+        C.res.DeltaLN = V("DeltaLN");
+        C.res.DeltaNFL = V("DeltaNFL");
+        C.lake.Storage = V("LakeStorageM3CC");
+        C.lake.Outflow = V("LakeOutflowCC");
+        C.lake.InflowOld = V("LakeInflowOldCC");
+        C.lake.Balance = V("LakeStorageM3BalanceCC");
+        C.lake.Level = V("LakeLevelCC");
+        C.lake.OutM3 = V("QLakeOutM3DtCC");
+        C.lake.Area = V("LakeAreaCC");
+        C.lake.Factor = V("LakeFactor");
+        C.lake.FactorSqr = V("LakeFactorSqr");
+        if (T.cq_dirty) {   // ChanQ of the feeder pixels before the first sub-step (np.bincount(downstruct, ChanQ) at s = 0)
+            k_struct_cq_init<<<lf::blocks_for(m->n, 256), 256, 0, lf::stream()>>>(T.feeds.p, cq, T.CQ0.p, T.CQ1.p, m->n);
+            LF_LAUNCH_CHECK();
+            T.cq_dirty = false;
+        }
+    }
     if (m32_out) *m32_out = nullptr;
     if (c2s_out) *c2s_out = nullptr;
     if (C.split) {
@@ -1295,13 +1558,18 @@ int channel_stage(lf_model *m)
         int lo = ls[lo_lev], hi = level_end(hi_lev);
         if (hi <= lo) continue;
         const unsigned gb = lf::blocks_for(hi - lo, CH_THREADS);
-        if (C.X.xslot) {
-            if (m->quintic) k_chan_diagonal<true, true><<<gb, CH_THREADS, 0, sw>>>(C, lo, hi, d);
-            else k_chan_diagonal<false, true><<<gb, CH_THREADS, 0, sw>>>(C, lo, hi, d);
+#define LF_CHAN_LAUNCH(QZ_, HX_, HS_) k_chan_diagonal<QZ_, HX_, HS_><<<gb, CH_THREADS, 0, sw>>>(C, lo, hi, d)
+        if (C.sid) {
+            if (m->quintic) LF_CHAN_LAUNCH(true, false, true);
+            else LF_CHAN_LAUNCH(false, false, true);
+        } else if (C.X.xslot) {
+            if (m->quintic) LF_CHAN_LAUNCH(true, true, false);
+            else LF_CHAN_LAUNCH(false, true, false);
         } else {
-            if (m->quintic) k_chan_diagonal<true, false><<<gb, CH_THREADS, 0, sw>>>(C, lo, hi, d);
-            else k_chan_diagonal<false, false><<<gb, CH_THREADS, 0, sw>>>(C, lo, hi, d);
+            if (m->quintic) LF_CHAN_LAUNCH(true, false, false);
+            else LF_CHAN_LAUNCH(false, false, false);
         }
+#undef LF_CHAN_LAUNCH
         LF_LAUNCH_CHECK();
     }
     LF_CUDA(cudaEventRecord(m->ev_join, sw));
@@ -1527,6 +1795,7 @@ int lf_model_set(lf_model *m, const char *name, const double *values, int64_t co
     if (strcmp(name, "OFAlpha") == 0 || strcmp(name, "ChannelAlpha") == 0 || strcmp(name, "ChannelAlpha2") == 0 ||
         strcmp(name, "ChanLength") == 0 || strcmp(name, "Chan2M3Start") == 0)
         m->params_dirty = true;
+    if (strcmp(name, "ChanQ") == 0) m->st.cq_dirty = true;
     LF_CUDA(cudaStreamSynchronize(st));
     return LF_OK;
 }
@@ -1764,6 +2033,268 @@ int lf_model_soil_stats(lf_model *m, int enable_timing, int64_t *deferred_column
         }
     }
     m->soil_profile = enable_timing != 0;
+    return LF_OK;
+}
+
+
+static const char *const FEED_PARAMS[] = {"PrScaling", "CalEvaporation", "DeltaTSnow", "SnowSeason", "TempSnow", "SnowFactor",
+                                          "SnowMeltCoef", "TempMelt", "lat_rad", "Kfrost", "Afrost", "FrostIndexThreshold",
+                                          "SnowWaterEquivalent", "kgb"};
+
+int lf_model_set_scalar(lf_model *m, const char *name, double value)
+{
+    if (!m || !name) {
+        lf::set_error("lf_model_set_scalar: null pointer");
+        return LF_ERR_INVALID;
+    }
+    for (const char *nm : FEED_PARAMS)
+        if (strcmp(nm, name) == 0) {
+            m->scalars[name] = value;
+            m->fields.erase(name);   // a scalar replaces a map set earlier
+            return LF_OK;
+        }
+    lf::set_error("lf_model_set_scalar: '%s' is not a scalar-or-map parameter", name);
+    return LF_ERR_INVALID;
+}
+
+static int scalar_or_map(lf_model *m, const char *name, ScalarOrMap *out)
+{
+    auto it = m->fields.find(name);
+    if (it != m->fields.end()) {
+        out->map = it->second->buf.p;
+        out->value = 0.;
+        return LF_OK;
+    }
+    auto is = m->scalars.find(name);
+    if (is == m->scalars.end()) {
+        lf::set_error("parameter '%s' is not set (lf_model_set for a map, lf_model_set_scalar for a scalar)", name);
+        return LF_ERR_STATE;
+    }
+    out->map = nullptr;
+    out->value = is->second;
+    return LF_OK;
+}
+
+int lf_model_feed(lf_model *m, const void *precipitation, const void *tavg, const void *et0, const void *e0, int32_t dtype,
+                  double snowmelt_coeff, double ice_melt_coeff_north, double ice_melt_coeff_south, int32_t async)
+{
+    if (!m || !precipitation || !tavg || !et0 || !e0 || (dtype != 0 && dtype != 1)) {
+        lf::set_error("lf_model_feed: null pointer or bad dtype (0 = float64, 1 = float32)");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    const size_t esz = dtype == 1 ? 4 : 8;
+    const size_t map_bytes = ((size_t)m->n * esz + 255) / 256 * 256;
+    const void *src[4] = {precipitation, tavg, et0, e0};
+    const void *dev[4];
+    const bool on_device = lf::is_device_ptr(precipitation);
+    if (on_device) {
+        for (int k = 0; k < 4; ++k) dev[k] = src[k];
+    } else {
+        const int turn = m->raw_turn;
+        m->raw_turn ^= 1;
+        if (m->raw_stage[turn].n < 4 * map_bytes) {
+            LF_CHECK(m->raw_stage[turn].alloc(4 * map_bytes));
+            m->bytes += 4 * map_bytes;
+        }
+        if (!m->raw_copied[turn]) {
+            LF_CUDA(cudaEventCreateWithFlags(&m->raw_copied[turn], cudaEventDisableTiming));
+            LF_CUDA(cudaEventCreateWithFlags(&m->raw_consumed[turn], cudaEventDisableTiming));
+            LF_CUDA(cudaEventRecord(m->raw_consumed[turn], st));
+        }
+        cudaStream_t cs = st;
+        if (async) {
+            if (!m->copy_stream) LF_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+            cs = m->copy_stream;
+            LF_CUDA(cudaStreamWaitEvent(cs, m->raw_consumed[turn], 0));   // the staging buffer is free again
+        }
+        for (int k = 0; k < 4; ++k) {
+            void *d = m->raw_stage[turn].p + k * map_bytes;
+            LF_CUDA(cudaMemcpyAsync(d, src[k], (size_t)m->n * esz, cudaMemcpyDefault, cs));
+            dev[k] = d;
+        }
+        if (async) {
+            LF_CUDA(cudaEventRecord(m->raw_copied[turn], cs));
+            LF_CUDA(cudaStreamWaitEvent(st, m->raw_copied[turn], 0));
+        }
+    }
+    FeedPtrs F;
+    memset(&F, 0, sizeof(F));
+    F.n = m->n;
+    F.pix_of_pos = m->g_of->pix_of_pos.p;
+    F.prec = dev[0];
+    F.tavg = dev[1];
+    F.et0 = dev[2];
+    F.e0 = dev[3];
+    LF_CHECK(scalar_or_map(m, "PrScaling", &F.PrScaling));
+    LF_CHECK(scalar_or_map(m, "CalEvaporation", &F.CalEvaporation));
+    LF_CHECK(scalar_or_map(m, "DeltaTSnow", &F.DeltaTSnow));
+    LF_CHECK(scalar_or_map(m, "SnowSeason", &F.SnowSeason));
+    LF_CHECK(scalar_or_map(m, "TempSnow", &F.TempSnow));
+    LF_CHECK(scalar_or_map(m, "SnowFactor", &F.SnowFactor));
+    LF_CHECK(scalar_or_map(m, "SnowMeltCoef", &F.SnowMeltCoef));
+    LF_CHECK(scalar_or_map(m, "TempMelt", &F.TempMelt));
+    LF_CHECK(scalar_or_map(m, "lat_rad", &F.lat_rad));
+    LF_CHECK(scalar_or_map(m, "Kfrost", &F.Kfrost));
+    LF_CHECK(scalar_or_map(m, "Afrost", &F.Afrost));
+    LF_CHECK(scalar_or_map(m, "FrostIndexThreshold", &F.FrostIndexThreshold));
+    LF_CHECK(scalar_or_map(m, "SnowWaterEquivalent", &F.SnowWaterEquivalent));
+    F.DtDay = m->DtDay;
+    F.snowmelt_coeff = snowmelt_coeff;
+    F.ice_n = ice_melt_coeff_north;
+    F.ice_s = ice_melt_coeff_south;
+    FIELD(scs, "SnowCoverS");
+    FIELD(fi, "FrostIndex");
+    FIELD(tp, "TotalPrecipitation");
+    FIELD(rain, "Rain");
+    FIELD(sm, "SnowMelt");
+    FIELD(etr, "ETRef");
+    FIELD(ewr, "EWRef");
+    FIELD(esr, "ESRef");
+    F.SnowCoverS = scs;
+    F.FrostIndex = fi;
+    F.TotalPrecipitation = tp;
+    F.Rain = rain;
+    F.SnowMelt = sm;
+    F.ETRef = etr;
+    F.EWRef = ewr;
+    F.ESRef = esr;
+    LF_CHECK(flag_buf(m, "isFrozenSoil", &F.frozen));
+    if (m->cfg.diagnostics) {
+        FIELD(sn, "Snow");
+        FIELD(sc, "SnowCover");
+        FIELD(pr, "Precipitation");
+        FIELD(ta, "Tavg");
+        F.Snow = sn;
+        F.SnowCover = sc;
+        F.Precipitation = pr;
+        F.Tavg = ta;
+    }
+    if (dtype == 1) k_feeder<true><<<lf::blocks_for(m->n, 256), 256, 0, st>>>(F);
+    else k_feeder<false><<<lf::blocks_for(m->n, 256), 256, 0, st>>>(F);
+    LF_LAUNCH_CHECK();
+    if (!on_device) {
+        LF_CUDA(cudaEventRecord(m->raw_consumed[m->raw_turn ^ 1], st));
+        if (!async) LF_CUDA(cudaStreamSynchronize(st));   // the host buffers are borrowed for the duration of the call
+    }
+    return LF_OK;
+}
+
+int lf_model_set_lai(lf_model *m, const double *lai, int64_t count)
+{
+    if (!m || !lai) {
+        lf::set_error("lf_model_set_lai: null pointer");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf_model_set(m, "LAI", lai, count));
+    ScalarOrMap kgb;
+    LF_CHECK(scalar_or_map(m, "kgb", &kgb));
+    FIELD(l, "LAI");
+    FIELD(t, "LAITerm");
+    k_lai_term<<<lf::blocks_for(m->n, 256), 256, 0, lf::stream()>>>(l, kgb, t, m->n);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaStreamSynchronize(lf::stream()));
+    return LF_OK;
+}
+
+static const char *const RES_NAMES[] = {"TotalReservoirStorageM3CC", "ConservativeStorageLimitCC", "NormalStorageLimitCC",
+                                        "Normal_FloodStorageLimitCC", "FloodStorageLimitCC", "MinReservoirOutflowCC",
+                                        "NormalReservoirOutflowCC", "NonDamagingReservoirOutflowCC", "DeltaO", "DeltaLN",
+                                        "DeltaNFL", "ReservoirStorageM3CC", "ReservoirFillCC", "QResOutM3DtCC"};
+static const char *const LAKE_NAMES[] = {"LakeAreaCC", "LakeFactor", "LakeFactorSqr", "LakeStorageM3CC", "LakeOutflowCC",
+                                         "LakeInflowOldCC", "LakeStorageM3BalanceCC", "LakeLevelCC", "QLakeOutM3DtCC"};
+
+int lf_model_set_structures(lf_model *m, int32_t n_reservoirs, const int64_t *reservoir_index, int32_t n_lakes,
+                            const int64_t *lake_index)
+{
+    if (!m || n_reservoirs < 0 || n_lakes < 0 || (n_reservoirs > 0 && !reservoir_index) || (n_lakes > 0 && !lake_index)) {
+        lf::set_error("lf_model_set_structures: bad arguments");
+        return LF_ERR_INVALID;
+    }
+    if (m->g_ch->restricted) {
+        lf::set_error("lf_model_set_structures: structures are not supported on a cut raster yet");
+        return LF_ERR_STATE;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    lf_model::Structures &T = m->st;
+    std::vector<int32_t> sid(m->n, 0);
+    for (int j = 0; j < n_reservoirs; ++j) {
+        const int64_t p = reservoir_index[j];
+        if (p < 0 || p >= m->n || sid[p] != 0) {
+            lf::set_error("lf_model_set_structures: reservoir %d: bad or duplicate pixel index %lld", j, (long long)p);
+            return LF_ERR_INVALID;
+        }
+        sid[p] = j + 1;
+    }
+    for (int j = 0; j < n_lakes; ++j) {
+        const int64_t p = lake_index[j];
+        if (p < 0 || p >= m->n || sid[p] != 0) {
+            lf::set_error("lf_model_set_structures: lake %d: bad or duplicate pixel index %lld", j, (long long)p);
+            return LF_ERR_INVALID;
+        }
+        sid[p] = -(j + 1);
+    }
+    lf::DevBuf<int32_t> tmp;
+    LF_CHECK(tmp.alloc(m->n));
+    LF_CHECK(T.sid.alloc(m->n));
+    LF_CHECK(T.feeds.alloc(m->n));
+    LF_CHECK(T.CQ0.alloc(m->n));
+    LF_CHECK(T.CQ1.alloc(m->n));
+    LF_CUDA(cudaMemcpyAsync(tmp.p, sid.data(), m->n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    k_i32_rows_to_pos<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(tmp.p, T.sid.p, m->g_ch->pix_of_pos.p, m->n);
+    LF_LAUNCH_CHECK();
+    LF_CUDA(cudaMemsetAsync(T.feeds.p, 0, m->n, st));
+    LF_CUDA(cudaMemsetAsync(T.CQ0.p, 0, m->n * sizeof(double), st));
+    LF_CUDA(cudaMemsetAsync(T.CQ1.p, 0, m->n * sizeof(double), st));
+    k_struct_feeds<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(T.sid.p, m->g_ch->cfirst.p, T.feeds.p, m->n);
+    LF_LAUNCH_CHECK();
+    T.v.clear();
+    for (const char *nm : RES_NAMES) {
+        std::unique_ptr<lf::DevBuf<double>> b(new lf::DevBuf<double>());
+        LF_CHECK(b->alloc(std::max(n_reservoirs, 1)));
+        LF_CUDA(cudaMemsetAsync(b->p, 0, std::max(n_reservoirs, 1) * sizeof(double), st));
+        T.v[nm] = std::move(b);
+    }
+    for (const char *nm : LAKE_NAMES) {
+        std::unique_ptr<lf::DevBuf<double>> b(new lf::DevBuf<double>());
+        LF_CHECK(b->alloc(std::max(n_lakes, 1)));
+        LF_CUDA(cudaMemsetAsync(b->p, 0, std::max(n_lakes, 1) * sizeof(double), st));
+        T.v[nm] = std::move(b);
+    }
+    LF_CUDA(cudaStreamSynchronize(st));
+    T.n_res = n_reservoirs;
+    T.n_lake = n_lakes;
+    T.cq_dirty = true;
+    return LF_OK;
+}
+
+int lf_model_structure_array(lf_model *m, const char *name, double *values, int64_t count, int32_t set)
+{
+    if (!m || !name || !values) {
+        lf::set_error("lf_model_structure_array: null pointer");
+        return LF_ERR_INVALID;
+    }
+    auto it = m->st.v.find(name);
+    if (it == m->st.v.end()) {
+        lf::set_error("lf_model_structure_array: unknown per-structure array '%s' (or no structures set)", name);
+        return LF_ERR_INVALID;
+    }
+    bool is_lake = false;
+    for (const char *nm : LAKE_NAMES) is_lake = is_lake || strcmp(nm, name) == 0;
+    const int64_t want = is_lake ? m->st.n_lake : m->st.n_res;
+    if (count != want) {
+        lf::set_error("lf_model_structure_array(%s): expected %lld values, got %lld", name, (long long)want, (long long)count);
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    cudaStream_t st = lf::stream();
+    if (count > 0) {
+        if (set) LF_CUDA(cudaMemcpyAsync(it->second->p, values, count * sizeof(double), cudaMemcpyDefault, st));
+        else LF_CUDA(cudaMemcpyAsync(values, it->second->p, count * sizeof(double), cudaMemcpyDefault, st));
+    }
+    LF_CUDA(cudaStreamSynchronize(st));
     return LF_OK;
 }
 

@@ -15,8 +15,7 @@ DEFAULT_OPTIONS = {"InitLisflood": False, "SplitRouting": False, "dynamicWave": 
                    "simulateReservoirs": False, "simulatePolders": False, "inflow": False, "TransLoss": False,
                    "openwaterevapo": False, "wateruse": False, "repMBTs": False, "drainedIrrigation": False,
                    "simulatePF": False, "cropsEPIC": False, "repStressDays": False}
-UNSUPPORTED_ON = ("dynamicWave", "simulateLakes", "simulateReservoirs", "simulatePolders", "inflow", "TransLoss",
-                  "openwaterevapo", "wateruse", "cropsEPIC")
+UNSUPPORTED_ON = ("dynamicWave", "simulatePolders", "inflow", "TransLoss", "openwaterevapo", "wateruse", "cropsEPIC")
 FLAG_TABLE = [("quiet", "q"), ("veryquiet", "v"), ("loud", "l"), ("checkfiles", "c"), ("noheader", "h"), ("printtime", "t"),
               ("debug", "d"), ("nancheck", "n"), ("initonly", "i"), ("skipvalreplace", "s")]
 

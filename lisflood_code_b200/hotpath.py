@@ -33,10 +33,24 @@ STATE = {
 SPLIT_STATE = {"Chan2QKin": 1, "Chan2M3Kin": 1, "CrossSection2Area": 1, "Sideflow1Chan": 1}
 FORCING = {"Rain": 1, "SnowMelt": 1, "ETRef": 1, "EWRef": 1, "ESRef": 1, "LAI": 3, "LAITerm": 3}
 FLAGS = ("isFrozenSoil", "IsChannel", "IsChannelKinematic", "AtLastPointC")
+# structures in the routing sub-step loop: per-structure arrays, the reference's names
+RESERVOIR_ARRAYS = ("TotalReservoirStorageM3CC", "ConservativeStorageLimitCC", "NormalStorageLimitCC",
+                    "Normal_FloodStorageLimitCC", "FloodStorageLimitCC", "MinReservoirOutflowCC", "NormalReservoirOutflowCC",
+                    "NonDamagingReservoirOutflowCC", "DeltaO", "DeltaLN", "DeltaNFL", "ReservoirStorageM3CC")
+LAKE_ARRAYS = ("LakeAreaCC", "LakeFactor", "LakeFactorSqr", "LakeStorageM3CC", "LakeOutflowCC", "LakeInflowOldCC",
+               "LakeStorageM3BalanceCC")
+STRUCTURE_OUTPUTS = ("ReservoirFillCC", "QResOutM3DtCC", "LakeLevelCC", "QLakeOutM3DtCC")
+# full maps the reference fills with np.put at the end of the sub-step loop (reservoir.py:300-322, lakes.py:280-297)
+STRUCTURE_MAPS = {"ReservoirStorageM3": ("ReservoirStorageM3CC", "res"), "ReservoirFill": ("ReservoirFillCC", "res"),
+                  "QResOutM3Dt": ("QResOutM3DtCC", "res"), "LakeStorageM3": ("LakeStorageM3CC", "lake"),
+                  "LakeLevel": ("LakeLevelCC", "lake"), "LakeOutflow": ("LakeOutflowCC", "lake"),
+                  "LakeInflowOld": ("LakeInflowOldCC", "lake"), "LakeStorageM3Balance": ("LakeStorageM3BalanceCC", "lake"),
+                  "QLakeOutM3Dt": ("QLakeOutM3DtCC", "lake")}
 DIAGNOSTIC_ONLY = ("WWP2", "WFC2", "SoilDepth1a", "SoilDepth1b", "SoilDepth2", "PixelArea")
 
 
 THREE_ROWS = frozenset(k for d in (PARAMETERS, STATE, FORCING) for k, r in d.items() if r == 3) | {
+    "SnowCoverS",
     "Interception", "TaInterception", "LeafDrainage", "potential_transpiration", "Ta", "ESAct", "PrefFlow",
     "Infiltration", "AvailableWaterForInfiltration", "SeepTopToSubA", "SeepTopToSubB", "SeepSubToGW", "Theta1a",
     "Theta1b", "Theta2", "Sat1a", "Sat1b", "Sat1", "Sat2", "UZOutflow", "GwPercUZLZ", "RWS", "Theta", "SurfaceRunSoil",
@@ -78,6 +92,10 @@ class HotPathModel(object):
             _capi.check(L.lf_model_create_from_graphs(C.byref(cfg), graphs[0], graphs[1], C.byref(h)))
         else:
             ldd_oc, ldd_kin = S["LddToChan"], S["LddKinematic"]
+            if S.get("simulateReservoirs") or S.get("simulateLakes"):
+                # the device graph is levelled on the network BEFORE structures.initial cuts it (structures.py:43-61); the
+                # cut itself is applied by the channel kernel (lf_model_set_structures)
+                ldd_kin = S["LddStructuresKinematic"]
             if not hasattr(ldd_oc, "data_ptr"):   # NumPy input; torch CUDA tensors are passed through as they are
                 ldd_oc = np.ascontiguousarray(ldd_oc, np.float64)
                 ldd_kin = np.ascontiguousarray(ldd_kin, np.float64)
@@ -103,6 +121,12 @@ class HotPathModel(object):
         for name in FLAGS:
             if name in S:
                 self.set_flags(name, pick(S[name]) if pick else S[name])
+        self.__dict__["_res_index"] = np.zeros(0, np.int64)
+        self.__dict__["_lake_index"] = np.zeros(0, np.int64)
+        if S.get("simulateReservoirs") or S.get("simulateLakes"):
+            if graphs is not None:
+                raise _capi.LisfloodB200Error(_capi.LF_ERR_STATE, "structures are not supported on a cut raster yet")
+            self.set_structures(S)
 
     # ---- raw access --------------------------------------------------------------------------------
     def set(self, name, values, rows=None):
@@ -121,6 +145,69 @@ class HotPathModel(object):
         self._rows[name] = rows
         _capi.check(_capi.lib().lf_model_set(self._h, name.encode(), _capi.ptr(a), a.size))
 
+    def set_structures(self, S):
+        """Reservoirs / lakes of the routing sub-step loop from the attributes reservoir.initial / lakes.initial leave on
+        the model object (reference: reservoir.py:52-170, lakes.py:57-197)."""
+        res = np.ascontiguousarray(S["ReservoirIndex"], np.int64) if S.get("simulateReservoirs") else np.zeros(0, np.int64)
+        lak = np.ascontiguousarray(S["LakeIndex"], np.int64) if S.get("simulateLakes") else np.zeros(0, np.int64)
+        self.__dict__["_res_index"], self.__dict__["_lake_index"] = res, lak
+        _capi.check(_capi.lib().lf_model_set_structures(self._h, res.size, _capi.ptr(res) if res.size else None, lak.size,
+                                                        _capi.ptr(lak) if lak.size else None))
+        for names, count in ((RESERVOIR_ARRAYS, res.size), (LAKE_ARRAYS, lak.size)):
+            if count:
+                for name in names:
+                    self.set_structure_array(name, S[name])
+
+    def set_structure_array(self, name, values):
+        a = np.ascontiguousarray(values, np.float64)
+        _capi.check(_capi.lib().lf_model_structure_array(self._h, name.encode(), _capi.ptr(a), a.size, 1))
+
+    def get_structure_array(self, name):
+        n = self._lake_index.size if (name in LAKE_ARRAYS or name in ("LakeLevelCC", "QLakeOutM3DtCC")) else self._res_index.size
+        a = np.zeros(n, np.float64)
+        _capi.check(_capi.lib().lf_model_structure_array(self._h, name.encode(), _capi.ptr(a), a.size, 0))
+        return a
+
+    # ---- feeder modules (readmeteo scaling + snow + frost fused; leafarea) --------------------------------
+    def set_feeder(self, P, state=None):
+        """Parameters of the feeder kernel by the reference's names (hydrological_modules/snow.py FEEDER_PARAMETERS): maps
+        or Python floats, like the float-or-array results of the reference's loadmap; state: SnowCoverS (3, N), FrostIndex."""
+        for name, v in P.items():
+            if np.ndim(v) == 0 and not hasattr(v, "data_ptr"):
+                _capi.check(_capi.lib().lf_model_set_scalar(self._h, name.encode(), float(v)))
+            else:
+                self.set(name, v, 1)
+        for name, v in (state or {}).items():
+            self.set(name, v, 3 if name == "SnowCoverS" else 1)
+
+    def feed(self, raw, calendar_day, asynchronous=False):
+        """Raw meteo maps of the step -> forcing of the soil stage (lf_model_feed).  raw: Precipitation, Tavg, ET0, E0;
+        float32 or float64; NumPy arrays or torch tensors (host or CUDA), compressed order."""
+        from .hydrological_modules.snow import season_coefficients
+        maps = [raw[k] for k in ("Precipitation", "Tavg", "ET0", "E0")]
+        size = lambda a: a.element_size() if hasattr(a, "element_size") else a.dtype.itemsize
+        count = lambda a: a.numel() if hasattr(a, "numel") else a.size
+        es = size(maps[0])
+        if es not in (4, 8) or any(size(a) != es or count(a) != self.N for a in maps):
+            raise ValueError("feed: four float32 or four float64 maps of %d pixels" % self.N)
+        if not hasattr(maps[0], "data_ptr"):
+            maps = [np.ascontiguousarray(a) for a in maps]
+            if asynchronous:
+                self.__dict__["_raw_keepalive"] = maps     # borrowed until the next synchronising call
+        c, ice_n, ice_s = season_coefficients(int(calendar_day))
+        _capi.check(_capi.lib().lf_model_feed(self._h, *[_capi.ptr(a) for a in maps], 1 if es == 4 else 0, c, ice_n, ice_s,
+                                              1 if asynchronous else 0))
+
+    def set_lai(self, lai):
+        """LAI maps (3, N) of the current 10-day interval; LAITerm = exp(-kgb LAI) is derived on the device."""
+        if hasattr(lai, "data_ptr"):
+            assert lai.is_contiguous() and lai.element_size() == 8 and lai.numel() == 3 * self.N
+            a = lai
+        else:
+            a = np.ascontiguousarray(lai, np.float64)
+        self._rows["LAI"], self._rows["LAITerm"] = 3, 3
+        _capi.check(_capi.lib().lf_model_set_lai(self._h, _capi.ptr(a), 3 * self.N))
+
     def set_async(self, name, values):
         """Queue a new value for a map without waiting (see lf_model_set_async); `values`: contiguous float64
         NumPy array or torch tensor that stays untouched until the next get()."""
@@ -128,6 +215,13 @@ class HotPathModel(object):
         _capi.check(_capi.lib().lf_model_set_async(self._h, name.encode(), _capi.ptr(values), size))
 
     def get(self, name, rows=None):
+        if name in RESERVOIR_ARRAYS or name in LAKE_ARRAYS or name in STRUCTURE_OUTPUTS:
+            return self.get_structure_array(name)
+        if name in STRUCTURE_MAPS:       # np.put(full map, index, per-structure values), reservoir.py:300-322
+            cc, kind = STRUCTURE_MAPS[name]
+            full = np.zeros(self.N)
+            np.put(full, self._res_index if kind == "res" else self._lake_index, self.get_structure_array(cc))
+            return full
         if name in ("LZOutflowToChannelPixel", "LZOutflowToChannel"):   # groundwater.py:142,180
             name = "LZOutflow"
         elif name == "M3all":                                           # surface_routing.py:196

@@ -1,9 +1,9 @@
 """lakes -- HydroModule mirror, initialisation part (reference: src/lisflood/hydrological_modules/lakes.py:52-196).
 
-Lakes act inside the routing sub-step loop (`dynamic_inloop`, lakes.py:199-297: Modified Puls).  Round 1 provides the
-parameter derivation on the host (this file; pinned to the reference's own `initial()`) and the CPU restatement of the
-sub-step rule with reference-made goldens; the device side is planned in DESIGN.md §9.1, so `simulateLakes` is still
-refused by `LisSettings.check_supported()`.  Lookup tables are two-column arrays: site id, value."""
+Lakes act inside the routing sub-step loop (`dynamic_inloop`, lakes.py:199-297: Modified Puls): on the device the rule
+is evaluated by the channel wavefront itself (csrc/lf_model.cu::lake_substep), GPU-tested against goldens made by the
+reference's own classes (tests/test_gpu_structures.py).  This file derives the parameters on the host (pinned bit for
+bit to the reference's own `initial()`).  Lookup tables are two-column arrays: site id, value."""
 import warnings
 
 import numpy as np
@@ -78,4 +78,8 @@ class lakes(HydroModule):
         v.EWLakeWBM3 = zeros()
 
     def dynamic_inloop(self, NoRoutingExecuted):
-        raise NotImplementedError("lakes in the device sub-step loop: round 2 (DESIGN.md section 9.1)")
+        """The sub-step rule (lakes.py:199-297) runs inside the device channel wavefront (csrc/lf_model.cu: the structure pixel's own
+        work item of every sub-step, lf_model_set_structures); the reference's call from routing.dynamic is kept as a
+        protocol check only.  State and outputs are read back through the model object (ReservoirStorageM3, LakeLevel ...)."""
+        if not 0 <= NoRoutingExecuted < self.var.NoRoutSteps:
+            raise RuntimeError("lakes.dynamic_inloop: sub-step %d out of range" % NoRoutingExecuted)

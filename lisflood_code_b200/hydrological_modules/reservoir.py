@@ -1,9 +1,9 @@
 """reservoir -- HydroModule mirror, initialisation part (reference: src/lisflood/hydrological_modules/reservoir.py:52-170).
 
-Reservoirs act inside the routing sub-step loop (`dynamic_inloop`, reservoir.py:173-322).  Round 1 provides the
-parameter derivation on the host (this file; pinned to the reference's own `initial()`) and the CPU restatement of the
-sub-step rule with reference-made goldens; the device side is planned in
-DESIGN.md §9.1, so `simulateReservoirs` is still refused by `LisSettings.check_supported()`.
+Reservoirs act inside the routing sub-step loop (`dynamic_inloop`, reservoir.py:173-322): on the device the
+four-regime outflow rule is evaluated by the channel wavefront itself (csrc/lf_model.cu::reservoir_substep), GPU-tested
+against goldens made by the reference's own classes (tests/test_gpu_structures.py).  This file derives the parameters on
+the host (pinned bit for bit to the reference's own `initial()`).
 PCRaster lookup tables (`TabTotStorage` ...) are two-column arrays here: site id, value."""
 import warnings
 
@@ -87,4 +87,8 @@ class reservoir(HydroModule):
         v.ReservoirStorageM3 = v.ReservoirStorageIniM3
 
     def dynamic_inloop(self, NoRoutingExecuted):
-        raise NotImplementedError("reservoirs in the device sub-step loop: round 2 (DESIGN.md section 9.1)")
+        """The sub-step rule (reservoir.py:173-322) runs inside the device channel wavefront (csrc/lf_model.cu: the structure pixel's own
+        work item of every sub-step, lf_model_set_structures); the reference's call from routing.dynamic is kept as a
+        protocol check only.  State and outputs are read back through the model object (ReservoirStorageM3, LakeLevel ...)."""
+        if not 0 <= NoRoutingExecuted < self.var.NoRoutSteps:
+            raise RuntimeError("reservoirs.dynamic_inloop: sub-step %d out of range" % NoRoutingExecuted)

@@ -1,0 +1,102 @@
+"""readmeteo / snow / frost / leafarea -- HydroModule mirrors of the feeder modules of a step (SURVEY.md §8 f3;
+reference: hydrological_modules/readmeteo.py:44-81, snow.py:53-187, frost.py:44-78, leafarea.py:44-90).
+
+On the device the scaling of the raw meteo maps, the three-zone snow model and the frost index are ONE kernel
+(csrc/lf_model.cu::k_feeder, C ABI lf_model_feed) that reads the raw float32 / float64 maps of the step and leaves Rain,
+SnowMelt, ETRef, EWRef, ESRef and isFrozenSoil where the soil stage reads them; only the raw maps cross PCIe.  The mirrors
+keep the reference's call protocol: readmeteo.dynamic() takes the step's raw maps, snow.dynamic() runs the fused kernel,
+frost.dynamic() checks the order, leafarea.dynamic() uploads the LAI maps when the 10-day interval changes.
+`self.var` is a lisflood_code_b200.hotpath.HotPathModel."""
+import numpy as np
+
+from . import HydroModule
+
+FEEDER_PARAMETERS = ("PrScaling", "CalEvaporation", "DeltaTSnow", "SnowSeason", "TempSnow", "SnowFactor", "SnowMeltCoef",
+                     "TempMelt", "lat_rad", "Kfrost", "Afrost", "FrostIndexThreshold", "SnowWaterEquivalent", "kgb")
+# snow.py:66-73
+SNOW_DAY_DEGREES = 360 / 365.25
+ICE_DAY_DEGREES = 2 * SNOW_DAY_DEGREES
+ICEMELT_START_N, ICEMELT_END_N, ICEMELT_START_S, ICEMELT_END_S = 165, 257, 347, 74
+# leafarea.py:50-51: first day of every interval over which the prescribed LAI is constant
+LAI_INTERVAL_START = [1, 11, 21, 32, 42, 52, 60, 70, 80, 91, 101, 111, 121, 131, 141, 152, 162, 172, 182, 192, 202, 213, 223,
+                      233, 244, 254, 264, 274, 284, 294, 305, 315, 325, 335, 345, 355, 370]
+
+
+def season_coefficients(calendar_day):
+    """The three scalars of snow.dynamic for a calendar day (snow.py:104-117): seasonal snow-melt coefficient and the
+    summer ice-melt coefficient of the northern / southern hemisphere."""
+    snowmelt_coeff = np.sin(np.radians((calendar_day - 81) * SNOW_DAY_DEGREES))
+    is_summer_icemelt_N = (calendar_day > ICEMELT_START_N) & (calendar_day < ICEMELT_END_N)
+    is_summer_icemelt_S = (calendar_day > ICEMELT_START_S) | (calendar_day < ICEMELT_END_S)
+    _ice_melt_coeff = np.sin(np.radians((calendar_day - ICEMELT_START_N) * ICE_DAY_DEGREES))
+    return float(snowmelt_coeff), float(_ice_melt_coeff if is_summer_icemelt_N else 0), \
+        float(_ice_melt_coeff if is_summer_icemelt_S else 0)
+
+
+def lai_interval(calendar_day):
+    """Index of the 10-day LAI interval of a calendar day (the L1 lookup list of leafarea.py:63-69)."""
+    j = 0
+    for i in range(calendar_day + 1):
+        if i >= LAI_INTERVAL_START[j + 1]:
+            j += 1
+    return j
+
+
+class readmeteo(HydroModule):
+    input_files_keys = {'all': ['PrecipitationMaps', 'TavgMaps', 'ET0Maps', 'E0Maps']}
+    module_name = 'ReadMeteo'
+
+    def __init__(self, readmeteo_variable):
+        self.var = readmeteo_variable
+
+    def dynamic(self, raw, calendar_day, asynchronous=False):
+        """raw: {'Precipitation', 'Tavg', 'ET0', 'E0'} maps of the step as stored in the forcing files (float32 or
+        float64, compressed order; NumPy arrays or torch tensors, host or CUDA).  The maps are only registered here; the
+        scaling (readmeteo.py:66-69,78) is applied by the fused kernel that snow.dynamic() launches."""
+        self.var.__dict__["_raw_meteo"] = (raw, int(calendar_day), bool(asynchronous))
+
+
+class snow(HydroModule):
+    input_files_keys = {'all': ['ElevationStD', 'TemperatureLapseRate', 'SnowSeasonAdj', 'TempSnow', 'SnowFactor', 'SnowMeltCoef',
+                                'TempMelt', 'SnowCoverAInitValue', 'SnowCoverBInitValue', 'SnowCoverCInitValue']}
+    module_name = 'Snow'
+
+    def __init__(self, snow_variable):
+        self.var = snow_variable
+
+    def dynamic(self):
+        pending = self.var.__dict__.pop("_raw_meteo", None)
+        if pending is None:
+            raise RuntimeError("snow.dynamic before readmeteo.dynamic of this step (Lisflood_dynamic.py:79-105)")
+        raw, day, asynchronous = pending
+        self.var.feed(raw, day, asynchronous=asynchronous)
+        self.var.__dict__["_frost_pending"] = True
+
+
+class frost(HydroModule):
+    input_files_keys = {'all': ['Kfrost', 'Afrost', 'FrostIndexThreshold', 'SnowWaterEquivalent', 'FrostIndexInitValue']}
+    module_name = 'Frost'
+
+    def __init__(self, frost_variable):
+        self.var = frost_variable
+
+    def dynamic(self):
+        if not self.var.__dict__.pop("_frost_pending", False):
+            raise RuntimeError("frost.dynamic before snow.dynamic of this step (Lisflood_dynamic.py:102-105)")
+
+
+class leafarea(HydroModule):
+    input_files_keys = {'all': ['kdf', 'LAIOtherMaps', 'LAIForestMaps', 'LAIIrrigationMaps']}
+    module_name = 'LeafArea'
+
+    def __init__(self, leafarea_variable):
+        self.var = leafarea_variable
+        self._interval = None
+
+    def dynamic(self, calendar_day, lai_of_interval):
+        """lai_of_interval(j) -> (3, N) LAI maps (Rainfed, Forest, Irrigated prescribed fractions) of interval j; called
+        only when the interval changes (the maps then stay resident on the device, with LAITerm = exp(-kgb LAI))."""
+        j = lai_interval(int(calendar_day))
+        if j != self._interval:
+            self.var.set_lai(lai_of_interval(j))
+            self._interval = j

@@ -412,8 +412,10 @@ class DistributedHotPathModel(object):
         dist.barrier()
 
     def _local(self, a):
-        """Local pixels of a global map (last axis = pixels)."""
+        """Local pixels of a global map (last axis = pixels); scalars and local-sized arrays pass through."""
         if hasattr(a, "data_ptr"):
+            if a.shape[-1] != self.n_global:
+                return a
             return a[..., self.loc_dev].contiguous() if a.is_cuda else a[..., self.torch.as_tensor(self.loc)].contiguous()
         a = np.asarray(a)
         return np.ascontiguousarray(a[..., self.loc]) if a.ndim and a.shape[-1] == self.n_global else a
@@ -429,6 +431,31 @@ class DistributedHotPathModel(object):
 
     def set_forcing(self, F):
         self.model.set_forcing({k: self._local(v) for k, v in F.items()})
+
+    def set_feeder(self, P, state=None):
+        self.model.set_feeder({k: self._local(v) for k, v in P.items()}, {k: self._local(v) for k, v in (state or {}).items()})
+
+    def feed(self, raw, calendar_day, asynchronous=False, local=False):
+        """Raw meteo maps of the step (global maps, or this rank's pixels with local=True)."""
+        self.model.feed(raw if local else {k: self._local(v) for k, v in raw.items()}, calendar_day, asynchronous=asynchronous)
+
+    def set_lai(self, lai, local=False):
+        self.model.set_lai(lai if local else self._local(lai))
+
+    def set_option(self, name, value):
+        self.model.set_option(name, value)
+
+    def stage_times(self, reset=False):
+        return self.model.stage_times(reset)
+
+    def soil_stats(self, enable_timing=True):
+        return self.model.soil_stats(enable_timing)
+
+    def info(self):
+        return self.model.info()
+
+    def get_into(self, name, out):
+        return self.model.get_into(name, out)
 
     def local_forcing(self, F):
         return {k: self._local(v) for k, v in F.items()}

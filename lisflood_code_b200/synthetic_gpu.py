@@ -65,7 +65,7 @@ def c3_generate(torch, rows, cols, seed, emit, ldd_noise=0.5, channel_threshold=
     is_chan = uparea >= channel_threshold
     ldd_kin = torch.where(is_chan, ldd, torch.zeros_like(ldd))
     ldd_toc = torch.where(is_chan, torch.full_like(ldd, 5.0), ldd)
-    S = {"rows": rows, "cols": cols, "N": n, "mask_device": mask, "LddToChan": ldd_toc, "LddKinematic": ldd_kin,
+    S = {"rows": rows, "cols": cols, "N": n, "mask_device": mask, "Ldd": ldd, "LddToChan": ldd_toc, "LddKinematic": ldd_kin,
          "DtSec": dt_sec, "Beta": 0.6, "PixelLength": 5000.0, "NoRoutSteps": no_rout_steps, "SplitRouting": False,
          "CourantCrit": 0.4, "AvWaterThreshold": 5.0 * dt_sec / 86400.0, "LeafDrainageK": min(dt_sec / 86400.0, 1.0),
          "DrainedFraction": 0.0, "SMaxSealed": 1.0}
@@ -163,33 +163,46 @@ def c3_generate(torch, rows, cols, seed, emit, ldd_noise=0.5, channel_threshold=
     emit("flags", "IsChannelKinematic", is_chan_u8)
     emit("flags", "AtLastPointC", (ldd == 5.0).to(torch.uint8))
     emit("stat", "channel_fraction", float(is_chan.double().mean().item()))
+    # ---- feeder modules (snow.py:53-93, frost.py:44-58, miscInitial.py:142-143,181, leafarea.py:48): LISFLOOD's usual
+    #      scalars, maps for the sub-pixel elevation spread and the latitude; no snow pack / frost at the start ----
+    emit("feeder", "parameters", {
+        "PrScaling": 1.0, "CalEvaporation": 1.0, "DeltaTSnow": 0.9674 * U(0.0, 300.0) * 0.0065, "SnowSeason": 1.0 * 0.5,
+        "TempSnow": 1.0, "SnowFactor": 1.0, "SnowMeltCoef": 4.0, "TempMelt": 0.0, "lat_rad": U(35.0, 70.0) * (math.pi / 180.0),
+        "Kfrost": 0.57, "Afrost": 0.97, "FrostIndexThreshold": 56.0, "SnowWaterEquivalent": 0.45, "kgb": 0.75 * 0.72})
+    emit("feeder", "state", {"SnowCoverS": torch.zeros((3, n), dtype=torch.float64, device=device),
+                             "FrostIndex": torch.zeros(n, dtype=torch.float64, device=device)})
     return g
 
 
-def c3_forcing(torch, g, n, dt_sec, device="cuda"):
-    """Forcing of one model step from the generator's random stream (tensors on `device`)."""
+def c3_forcing(torch, g, n, device="cuda"):
+    """RAW meteo maps of one model step from the generator's random stream, float32 like the NetCDF forcing of the
+    reference (tensors on `device`): intermittent Gamma precipitation [mm/day], a cool-season temperature field (snow falls
+    and melts somewhere on most steps, the frost index builds up slowly), ET0 / E0 [mm/day]."""
     R = lambda shape=(n,): torch.rand(shape, generator=g, device=device, dtype=torch.float64)
-    dtday = dt_sec / 86400.0
     rain = torch.where(R() < 0.45, torch._standard_gamma(torch.full((n,), 0.8, device=device, dtype=torch.float64),
                                                          generator=g) * 8.0,
-                       torch.zeros(n, device=device, dtype=torch.float64)) * dtday
-    F = {"Rain": rain, "SnowMelt": torch.where(R() < 0.1, R() * 3.0, torch.zeros_like(rain)) * dtday,
-         "ETRef": R() * 6.0 * dtday, "EWRef": R() * 6.0 * dtday, "LAI": R((3, n)) * 6.0,
-         "isFrozenSoil": (R() < 0.05).to(torch.uint8)}
-    F["ESRef"] = (F["EWRef"] + F["ETRef"]) / 2
-    F["LAITerm"] = torch.exp(-(0.75 * 0.72) * F["LAI"])
-    return F
+                       torch.zeros(n, device=device, dtype=torch.float64))
+    return {"Precipitation": rain.to(torch.float32), "Tavg": (R() * 24.0 - 6.0).to(torch.float32),
+            "ET0": (R() * 6.0).to(torch.float32), "E0": (R() * 6.0).to(torch.float32)}
+
+
+def c3_lai(torch, g, n, device="cuda"):
+    """LAI maps (3, n) of a 10-day interval."""
+    return torch.rand((3, n), generator=g, device=device, dtype=torch.float64) * 6.0
 
 
 def c3_host_stack(rows, cols, seed=0, nforcing=0, device=None, **kw):
-    """The same generator collected into host NumPy arrays: (S, [F0, F1, ...]) with S complete for the CPU restatement
-    of the step (synthetic.complete_stack adds the derived maps).  No library call: usable by the CPU arm of bench.py.
-    device: torch device of the random streams (default: cuda when available -- the streams of the bench's own raster)."""
+    """The same generator collected into host NumPy arrays: (S, feeder, lai, [raw0, raw1, ...]) with S complete for the
+    CPU restatement of the step (synthetic.complete_stack adds the derived maps), feeder = (parameters, state) of the feeder
+    modules, lai the (3, N) LAI maps, raw_k the float32 meteo maps of step k.  No library call: usable by the CPU arm of
+    bench.py.  device: torch device of the random streams (default: cuda when available -- the streams of the bench's own
+    raster)."""
     import torch
     from . import synthetic
     if device is None:
         device = "cuda" if torch.cuda.is_available() else "cpu"
-    S = {}
+    S, feeder = {}, {}
+    host = lambda v: v.cpu().numpy() if hasattr(v, "cpu") else v
 
     def emit(kind, name, value):
         if kind == "config":
@@ -197,29 +210,32 @@ def c3_host_stack(rows, cols, seed=0, nforcing=0, device=None, **kw):
                 if k == "mask_device":
                     S["mask"] = v.cpu().numpy().astype(bool).reshape(rows, cols)
                 else:
-                    S[k] = v.cpu().numpy() if hasattr(v, "cpu") else v
+                    S[k] = host(v)
         elif kind == "map":
             S[name] = value.cpu().numpy()
         elif kind == "flags":
             S[name] = value.cpu().numpy().astype(bool)
+        elif kind == "feeder":
+            feeder[name] = {k: host(v) for k, v in value.items()}
 
     kw.setdefault("diagnostics", True)    # the CPU restatement wants every parameter map
     g = c3_generate(torch, rows, cols, seed, emit, device=device, **kw)
     S = synthetic.complete_stack(S)
-    F = []
-    for _ in range(nforcing):
-        f = c3_forcing(torch, g, rows * cols, S["DtSec"], device)
-        F.append({k: (v.cpu().numpy().astype(bool) if k == "isFrozenSoil" else v.cpu().numpy()) for k, v in f.items()})
+    lai = c3_lai(torch, g, rows * cols, device).cpu().numpy()
+    raw = [{k: v.cpu().numpy() for k, v in c3_forcing(torch, g, rows * cols, device).items()} for _ in range(nforcing)]
     S["rng_device"] = device
-    return S, F
+    return S, (feeder["parameters"], feeder["state"]), lai, raw
 
 
 class C3Device(object):
-    """Builds a HotPathModel for a rows x cols catchment entirely on the device.  keep_host=True also keeps a host copy
-    of everything handed to the model (parity test of the bench's own data on a crop-sized raster)."""
+    """Builds the model of a rows x cols catchment entirely on the device: a HotPathModel, or -- under torch.distributed
+    with more than one rank and distributed=True -- this rank's part of the SAME raster cut along its drainage graph
+    (parallel.DistributedHotPathModel; every rank generates the same global maps from the same seeds and keeps its own
+    pixels).  keep_host=True also keeps a host copy of everything handed to the model (parity test of the bench's own data
+    on a crop-sized raster)."""
 
     def __init__(self, rows, cols, seed=0, ldd_noise=0.5, channel_threshold=60, no_rout_steps=24, dt_sec=86400.0,
-                 diagnostics=False, keep_host=False):
+                 diagnostics=False, keep_host=False, distributed=False):
         import torch
         from . import _capi
         from .hotpath import HotPathModel
@@ -228,6 +244,9 @@ class C3Device(object):
         n = rows * cols
         self.n, self.rows, self.cols = n, rows, cols
         self.host = {} if keep_host else None
+        self.feeder_host = {}
+        self.distributed = bool(distributed)
+        host = lambda v: v.cpu().numpy() if hasattr(v, "cpu") else v
 
         def accuflux(ldd, mask):
             # upstream area on the full LDD -> channel mask (routing.py:98, 110-118)
@@ -244,14 +263,18 @@ class C3Device(object):
 
         def emit(kind, name, value):
             if kind == "config":
-                self.S = value
-                self.model = HotPathModel(value, diagnostics=diagnostics)
+                self.S = {k: v for k, v in value.items() if k != "Ldd"}
+                if self.distributed:
+                    from .parallel import DistributedHotPathModel
+                    self.model = DistributedHotPathModel(value, diagnostics=diagnostics)
+                else:
+                    self.model = HotPathModel(self.S, diagnostics=diagnostics)
                 if keep_host:
                     for k, v in value.items():
                         if k == "mask_device":
                             self.host["mask"] = v.cpu().numpy().astype(bool).reshape(rows, cols)
                         else:
-                            self.host[k] = v.cpu().numpy() if hasattr(v, "cpu") else v
+                            self.host[k] = host(v)
             elif kind == "map":
                 self.model.set(name, value, 3 if value.dim() == 2 else 1)
                 if keep_host:
@@ -260,17 +283,31 @@ class C3Device(object):
                 self.model.set_flags(name, value)
                 if keep_host:
                     self.host[name] = value.cpu().numpy().astype(bool)
+            elif kind == "feeder":
+                if name == "parameters":
+                    self.model.set_feeder(value)
+                else:
+                    self.model.set_feeder({}, value)
+                if keep_host:
+                    self.feeder_host[name] = {k: host(v) for k, v in value.items()}
             elif kind == "stat":
                 setattr(self, name, value)
 
         self.gen = c3_generate(torch, rows, cols, seed, emit, ldd_noise=ldd_noise, channel_threshold=channel_threshold,
                                no_rout_steps=no_rout_steps, dt_sec=dt_sec, diagnostics=diagnostics or keep_host,
                                accuflux=accuflux)
+        self.n_local = self.model.n_local if self.distributed else n
         torch.cuda.empty_cache()
 
-    def forcing_device(self, step):
-        """Forcing of one step as CUDA tensors (device-resident leg)."""
-        return c3_forcing(self.torch, self.gen, self.n, self.S["DtSec"])
+    def _pick(self, t):
+        return self.model._local(t) if self.distributed else t
+
+    def forcing_device(self, step=None):
+        """RAW meteo maps of one step (float32 CUDA tensors: Precipitation, Tavg, ET0, E0) -- this rank's pixels."""
+        return {k: self._pick(v) for k, v in c3_forcing(self.torch, self.gen, self.n).items()}
+
+    def lai_device(self):
+        return self._pick(c3_lai(self.torch, self.gen, self.n))
 
     def host_stack(self):
         """Host copy of the model's inputs completed with the derived maps (keep_host=True)."""

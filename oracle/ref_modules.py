@@ -135,6 +135,18 @@ def load():
     return _mods
 
 
+def load_feeders():
+    """The reference's snow and frost classes (feeder modules): hydrological_modules/snow.py,
+    frost.py.  Their dynamic() parts are NumPy only."""
+    load()
+    out = {}
+    for name in ("snow", "frost"):
+        key = "lisflood.hydrological_modules." + name
+        m = sys.modules.get(key) or ref_loader._load_module(key, _R + "/hydrological_modules/%s.py" % name)
+        out[name] = getattr(m, name)
+    return out
+
+
 class _DA(np.ndarray):
     """(vegetation, pixel) array with the tiny xarray surface dynamic_canopy uses on LAITerm."""
 

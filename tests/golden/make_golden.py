@@ -210,9 +210,66 @@ def adversarial_case(kwp, name, beta):
                  q=q, dx=dx)
 
 
+def feeders_case(name, n, seed, steps, dt_sec, day0):
+    """Feeder modules of a step: snow.dynamic() and frost.dynamic() executed by the reference's OWN
+    classes (hydrological_modules/snow.py:95-187, frost.py:61-78) on raw meteo maps scaled as readmeteo.dynamic does
+    (readmeteo.py:61-81, four NumPy expressions restated here: the class needs xarray); both hemispheres, calendar days
+    that cross the summer ice-melt season limits, float32 forcing as read from NetCDF (widened to float64)."""
+    from types import SimpleNamespace
+    from oracle import ref_modules
+    M = ref_modules.load_feeders()
+    rng = np.random.default_rng(seed)
+    U = lambda lo, hi: rng.uniform(lo, hi, n)
+    P = {"PrScaling": U(0.8, 1.2), "CalEvaporation": U(0.8, 1.3), "DeltaTSnow": 0.9674 * U(0, 400.0) * 0.0065,
+         "SnowSeason": U(0.5, 2.0) * 0.5, "TempSnow": U(0.5, 1.5), "SnowFactor": U(0.9, 1.3), "SnowMeltCoef": U(2.0, 5.0),
+         "TempMelt": U(-0.5, 0.5), "lat_rad": np.radians(U(-60.0, 70.0)), "Kfrost": U(0.4, 0.7), "Afrost": U(0.95, 0.99),
+         "FrostIndexThreshold": U(40.0, 60.0), "SnowWaterEquivalent": U(0.05, 0.45)}
+    state0 = {"SnowCoverS": np.stack([U(0, 80.0) * (rng.random(n) < 0.6) for _ in range(3)]), "FrostIndex": U(0, 70.0) * (rng.random(n) < 0.7)}
+    v = SimpleNamespace(**{k: a.copy() for k, a in P.items()})
+    ref_modules._FakeMaskInfo.set(np.ones((1, n), bool))
+    v.DtDay = dt_sec / 86400.0
+    v.SnowCoverS = [state0["SnowCoverS"][i].copy() for i in range(3)]
+    v.FrostIndex = state0["FrostIndex"].copy()
+    v.TotalPrecipitation = np.zeros(n)
+    sn, fr = M["snow"](v), M["frost"](v)
+    v.SnowDayDegrees = 360 / 365.25                       # snow.initial, :66-75
+    sn.icemelt_start_N, sn.icemelt_end_N, sn.icemelt_start_S, sn.icemelt_end_S = 165, 257, 347, 74
+    v.IceDayDegrees = 2 * v.SnowDayDegrees
+    out = {"n": np.int64(n), "steps": np.int64(steps), "DtSec": np.float64(dt_sec)}
+    out.update({"P__" + k: a for k, a in P.items()})
+    out.update({"S__" + k: a for k, a in state0.items()})
+    for t in range(steps):
+        day = (day0 + int(t * v.DtDay * 37)) % 366 + 1    # strides through the year: both ice-melt seasons and winter
+        raw = {"Precipitation": (rng.gamma(0.8, 8.0, n) * (rng.random(n) < 0.5)).astype(np.float32),
+               "Tavg": rng.uniform(-25.0, 25.0, n).astype(np.float32), "ET0": rng.uniform(0, 6.0, n).astype(np.float32),
+               "E0": rng.uniform(0, 7.0, n).astype(np.float32)}
+        out["CalendarDay%d" % t] = np.int64(day)
+        for k, a in raw.items():
+            out["R%d__%s" % (t, k)] = a
+        v.CalendarDay = day
+        v.Precipitation = raw["Precipitation"].astype(np.float64) * v.DtDay * v.PrScaling   # readmeteo.py:66-69
+        v.Tavg = raw["Tavg"].astype(np.float64)
+        v.ETRef = raw["ET0"].astype(np.float64) * v.DtDay * v.CalEvaporation
+        v.EWRef = raw["E0"].astype(np.float64) * v.DtDay * v.CalEvaporation
+        v.ESRef = (v.EWRef + v.ETRef) / 2                                                    # :78
+        sn.dynamic()
+        fr.dynamic()
+        for k in ("Precipitation", "ETRef", "EWRef", "ESRef", "Rain", "Snow", "SnowMelt", "SnowCover", "FrostIndex",
+                  "isFrozenSoil", "TotalPrecipitation"):
+            out["O%d__%s" % (t, k)] = np.asarray(getattr(v, k)).copy()
+        out["O%d__SnowCoverS" % t] = np.stack(v.SnowCoverS)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "n=%d steps=%d frozen %.2f snow-covered %.2f" % (n, steps, out["O%d__isFrozenSoil" % (steps - 1)].mean(),
+                                                                 (out["O%d__SnowCover" % (steps - 1)] > 0).mean()))
+
+
 def main():
     import warnings
     warnings.simplefilter("ignore")
+    if len(sys.argv) > 1 and sys.argv[1] == "feeders":
+        feeders_case("feeders_daily", 900, 51, 10, 86400.0, 150)
+        feeders_case("feeders_6h", 600, 52, 8, 21600.0, 340)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "adversarial":
         kwpt, kwp, sl = ref_loader.load()
         adversarial_case(kwp, "kwadv_24x160_beta06", 0.6)

@@ -19,23 +19,35 @@ def test_c3_bench_data_parity(gpu_lib, oracle):
     import torch
     from lisflood_code_b200.synthetic_gpu import C3Device
     from oracle import lisf_oracle_model as om
+    from oracle.lisf_oracle_feeders import FeederOracle, lai_term
     torch.cuda.set_device(0)
     dev = C3Device(1000, 1000, seed=300, ldd_noise=0.5, no_rout_steps=24, keep_host=True)   # bench.py's generator and seed
     M = dev.model
     S = dev.host_stack()
+    n = S["N"]
     O = om.OracleModel(S)
+    P, state = dev.feeder_host["parameters"], dev.feeder_host["state"]
+    FO = FeederOracle({k: (np.full(n, v) if np.ndim(v) == 0 else v) for k, v in P.items() if k != "kgb"}, state, S["DtSec"])
+    lai_d = dev.lai_device()
+    M.set_lai(lai_d)
+    lai = lai_d.cpu().numpy()
+    laiterm = lai_term(P["kgb"], lai)
     keys1 = ["ChanQAvg", "ChanQ", "ChanQKin", "ChanM3Kin", "LZ", "CumInterSealed", "OFQOther", "OFQForest", "OFQDirect",
-             "ToChanM3RunoffDt", "TotalCrossSectionArea", "sumDis", "DischargeM3Out"]
-    keys3 = ["W1a", "W1b", "W2", "UZ", "DSLR", "CumInterception"]
+             "ToChanM3RunoffDt", "TotalCrossSectionArea", "sumDis", "DischargeM3Out", "FrostIndex", "Rain", "SnowMelt"]
+    keys3 = ["W1a", "W1b", "W2", "UZ", "DSLR", "CumInterception", "SnowCoverS"]
     worst = {}
     for t in range(3):
-        Fd = dev.forcing_device(t)
+        day = 21 + t                                  # bench.py starts its calendar there
+        Fd = dev.forcing_device()
         torch.cuda.synchronize()
-        Fh = {k: (v.cpu().numpy().astype(bool) if k == "isFrozenSoil" else v.cpu().numpy()) for k, v in Fd.items()}
-        M.step(Fd)
-        O.step(Fh)
+        raw = {k: v.cpu().numpy() for k, v in Fd.items()}
+        M.feed(Fd, day)
+        M.step()
+        fo = FO.step(raw, day)
+        O.step({"Rain": fo["Rain"], "SnowMelt": fo["SnowMelt"], "ETRef": fo["ETRef"], "EWRef": fo["EWRef"], "ESRef": fo["ESRef"],
+                "isFrozenSoil": fo["isFrozenSoil"], "LAI": lai, "LAITerm": laiterm})
         for k in keys1 + keys3:
-            want = np.asarray(getattr(O.var, k))
+            want = fo[k] if k in ("FrostIndex", "Rain", "SnowMelt", "SnowCoverS") else np.asarray(getattr(O.var, k))
             e = rel_err(M.get(k, 3 if want.ndim == 2 else 1), want)
             worst[k] = max(worst.get(k, 0.0), e)
     print("C3 bench-data parity at 1000x1000, 3 steps: worst rel. deviation per map:",

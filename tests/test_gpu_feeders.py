@@ -1,0 +1,64 @@
+"""Feeder modules on the device (readmeteo scaling + snow + frost fused, LAITerm) against goldens made
+by the reference's OWN snow / frost classes (tests/golden/make_golden.py::feeders_case), through the C ABI; float32 raw
+forcing (as in the NetCDF files), map and scalar parameters, synchronous and asynchronous upload."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, rel_err
+from test_oracle_feeders_golden import feeder_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(n, dt_sec, diagnostics=True):
+    """A model whose drainage network is irrelevant here: n pixels in one row, all pits."""
+    from lisflood_code_b200.hotpath import HotPathModel
+    S = {"mask": np.ones((1, n), bool), "LddToChan": np.full(n, 5.0), "LddKinematic": np.full(n, 5.0), "DtSec": dt_sec,
+         "Beta": 0.6, "PixelLength": 5000.0, "NoRoutSteps": 1, "SplitRouting": False, "CourantCrit": 0.4,
+         "AvWaterThreshold": 5.0, "LeafDrainageK": 1.0, "DrainedFraction": 0.0, "SMaxSealed": 1.0}
+    return HotPathModel(S, diagnostics=diagnostics)
+
+
+@pytest.mark.parametrize("case", golden_cases("feeders_"))
+@pytest.mark.parametrize("asynchronous", [False, True])
+def test_feeders_golden(gpu_lib, case, asynchronous):
+    P, S0, dt, R, days, O = feeder_case(case)
+    n = S0["FrostIndex"].size
+    M = _model(n, dt)
+    M.set_feeder(P, S0)
+    for t in range(len(R)):
+        M.feed(R[t], days[t], asynchronous=asynchronous)
+        gpu_lib.synchronize()
+        for k, want in O[t].items():
+            if k == "isFrozenSoil":
+                continue
+            got = M.get(k, 3 if want.ndim == 2 else 1)
+            assert rel_err(got, want) < 1e-12, (case, t, k, rel_err(got, want))
+        # the frozen-soil flag as the soil stage sees it: FrostIndex > threshold (bit-equal decisions away from ties)
+        fi = M.get("FrostIndex")
+        assert np.array_equal(fi > P["FrostIndexThreshold"], O[t]["isFrozenSoil"])
+
+
+def test_feeders_scalar_parameters_and_lai(gpu_lib):
+    from oracle.lisf_oracle_feeders import FeederOracle, lai_term
+    rng = np.random.default_rng(5)
+    n = 777
+    P = {"PrScaling": 1.0, "CalEvaporation": 1.1, "DeltaTSnow": 0.9674 * 120.0 * 0.0065, "SnowSeason": 0.5, "TempSnow": 1.0,
+         "SnowFactor": 1.0, "SnowMeltCoef": 4.0, "TempMelt": 0.0, "lat_rad": np.radians(rng.uniform(-40, 60, n)), "Kfrost": 0.57,
+         "Afrost": 0.97, "FrostIndexThreshold": 56.0, "SnowWaterEquivalent": 0.45, "kgb": 0.75 * 0.72}
+    S0 = {"SnowCoverS": rng.uniform(0, 50, (3, n)), "FrostIndex": rng.uniform(0, 60, n)}
+    M = _model(n, 86400.0)
+    M.set_feeder(P, S0)
+    Pm = {k: (np.full(n, v) if np.ndim(v) == 0 else v) for k, v in P.items() if k != "kgb"}
+    F = FeederOracle(Pm, S0, 86400.0)
+    for t, day in enumerate((10, 200, 300, 360)):
+        raw = {"Precipitation": rng.gamma(0.8, 8.0, n), "Tavg": rng.uniform(-20, 20, n), "ET0": rng.uniform(0, 6, n),
+               "E0": rng.uniform(0, 7, n)}                       # float64 raw maps this time
+        want = F.step(raw, day)
+        M.feed(raw, day)
+        for k in ("Rain", "SnowMelt", "ETRef", "EWRef", "ESRef", "SnowCoverS", "FrostIndex", "Snow", "SnowCover"):
+            assert rel_err(M.get(k, 3 if k == "SnowCoverS" else 1), want[k]) < 1e-12, (t, k)
+    lai = rng.uniform(0, 6, (3, n))
+    M.set_lai(lai)
+    assert rel_err(M.get("LAITerm", 3), lai_term(P["kgb"], lai)) < 1e-14
+    assert np.array_equal(M.get("LAI", 3), lai)
