@@ -215,6 +215,11 @@ int lf_model_structure_array(lf_model *m, const char *name, double *values, int6
  *                          LddKinematic (no side flow, routing.py:512) at the top of the step, on a low-priority
  *                          stream alongside the soil stage; 0: everything of the channel stage runs inside it.
  *   "early_blocks_per_sm"  resident blocks per SM of that early launch (default 2).
+ *   "cuda_graphs"          1 (default): the level sweep of the overland routers and the diagonals of the channel
+ *                          wavefront (hundreds of small dependent launches per step) are captured once per argument
+ *                          set and replayed as CUDA graphs; 0: plain launches.
+ *   "accumulate_discharge" 1: CumQ += ChanQ after every step (options InitLisflood / repAverageDis,
+ *                          Lisflood_dynamic.py:224-227); avgdis = CumQ / steps is the pre-run product `AvgDis`.
  *   "flagnancheck"         1: the `-n` option of the reference (kinematic_wave_parallel.py:180-184) for the model's
  *                          channel discharge: a non-finite ChanQ raises a flag read by lf_model_nonfinite. */
 int lf_model_set_option(lf_model *m, const char *name, double value);

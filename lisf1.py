@@ -54,12 +54,15 @@ def main(*args):
     if flags["initonly"]:
         return 0
     var = HotPathModel(S)
+    if flags["nancheck"]:
+        var.set_option("flagnancheck", 1)      # device-side watch of the channel discharge, warns once (-n)
     model = LisfloodModel_dyn(var)
-    forcing = np.load(b["ForcingFile"])
+    with np.load(b["ForcingFile"]) as z:       # every array is read (and decompressed) once, not once per step
+        forcing = {k: z[k] for k in z.files}
     first, last = int(b.get("StepStart", 1)), int(b.get("StepEnd", forcing["Rain"].shape[0]))
     dis = []
     for step in range(first, last + 1):
-        F = {k: forcing[k][step - 1] for k in forcing.files}
+        F = {k: a[step - 1] for k, a in forcing.items()}
         model.dynamic(F)
         dis.append(var.get("ChanQAvg"))
         if flags["loud"]:
@@ -67,10 +70,6 @@ def main(*args):
         elif not (flags["quiet"] or flags["veryquiet"]):
             sys.stdout.write("\r%d" % step)
             sys.stdout.flush()
-        if flags["nancheck"] and not np.all(np.isfinite(dis[-1])):
-            import warnings
-            from lisflood_code_b200.global_modules.errors import LisfloodWarning
-            warnings.warn(LisfloodWarning("Warning: NaN or Inf values after kinematicRouting module."))
     np.save(b["DisOut"], np.stack(dis))
     return 0
 

@@ -36,6 +36,7 @@ constexpr double Z_MIN = 0.0039810717055349725;  // (1e-12)^(1/5)
 struct Params {
     double beta, inv_beta, b_minus_1;
     int quintic;  // beta == 0.6: state is z = Q^(1/5)
+    int pad_;     // explicit: kernel-argument structs are compared byte-wise (CUDA-graph cache)
 };
 
 __host__ __device__ inline Params make_params(double beta)
@@ -45,6 +46,7 @@ __host__ __device__ inline Params make_params(double beta)
     P.inv_beta = 1 / beta;   // kinematic_wave_parallel.py:124
     P.b_minus_1 = beta - 1;  // :125
     P.quintic = (beta == 0.6) ? 1 : 0;
+    P.pad_ = 0;
     return P;
 }
 

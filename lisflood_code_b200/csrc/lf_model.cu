@@ -421,10 +421,11 @@ __global__ void k_chan_post(int n, int split, int qz, int S, double DtSec, const
                             const double *__restrict__ PixelArea_ch, double *__restrict__ ChanM3,
                             double *__restrict__ TotalCS, double *__restrict__ sumDis, double *__restrict__ ChanQAvg,
                             double *__restrict__ DischargeM3Out, double *__restrict__ FlowVelocity,
-                            double *__restrict__ TravelDistance, int *__restrict__ nonfinite)
+                            double *__restrict__ TravelDistance, int *__restrict__ nonfinite, double *__restrict__ CumQ)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (CumQ) CumQ[i] += ChanQ[i];   // InitLisflood / repAverageDis: avgdis = CumQ / TimeSinceStart, Lisflood_dynamic.py:224-227
     // the -n option of the reference (flagnancheck, kinematic_wave_parallel.py:180-184): non-finite discharge is
     // reported once, it does not stop the run
     if (nonfinite && !isfinite(ChanQ[i])) *nonfinite = 1;
@@ -718,6 +719,71 @@ __global__ void k_z2floor(const double *__restrict__ c2start, const double *__re
 
 }  // namespace
 
+
+// ---- CUDA-graph replay of launch-bound loops (the level sweep of the overland routers, the diagonals of the channel
+// wavefront: hundreds of small dependent launches per step).  A loop is captured once per distinct argument set (the
+// kernel arguments are part of the key: buffers that alternate between steps give two or four variants) and replayed
+// with one cudaGraphLaunch afterwards.
+struct GraphCache {
+    struct Entry {
+        std::vector<uint8_t> key;
+        cudaGraphExec_t exec = nullptr;
+        int64_t kernels = 0;
+        uint64_t last_use = 0;
+    };
+    std::vector<Entry> entries;
+    uint64_t tick = 0;
+    ~GraphCache()
+    {
+        for (Entry &e : entries)
+            if (e.exec) cudaGraphExecDestroy(e.exec);
+    }
+};
+template <class F>
+int run_captured(GraphCache &gc, const void *key, size_t keylen, cudaStream_t s, F &&enqueue)
+{
+    gc.tick += 1;
+    for (GraphCache::Entry &e : gc.entries)
+        if (e.key.size() == keylen && memcmp(e.key.data(), key, keylen) == 0) {
+            e.last_use = gc.tick;
+            LF_CUDA(cudaGraphLaunch(e.exec, s));
+            lf::count_launch(e.kernels);
+            return LF_OK;
+        }
+    const int64_t before = lf_launch_count(0);
+    LF_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc != LF_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != LF_OK) return rc;
+        lf::set_error("CUDA graph capture failed: %s", cudaGetErrorString(ce));
+        cudaGetLastError();
+        return LF_ERR_CUDA;
+    }
+    GraphCache::Entry e;
+    e.key.assign((const uint8_t *)key, (const uint8_t *)key + keylen);
+    e.kernels = lf_launch_count(0) - before;
+    e.last_use = gc.tick;
+    ce = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+        lf::set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+        return LF_ERR_CUDA;
+    }
+    if (gc.entries.size() >= 4) {   // drop the least recently used variant
+        size_t old = 0;
+        for (size_t k = 1; k < gc.entries.size(); ++k)
+            if (gc.entries[k].last_use < gc.entries[old].last_use) old = k;
+        cudaGraphExecDestroy(gc.entries[old].exec);
+        gc.entries.erase(gc.entries.begin() + old);
+    }
+    LF_CUDA(cudaGraphLaunch(e.exec, s));
+    gc.entries.push_back(e);
+    return LF_OK;
+}
+
 struct lf_model {
     lf_model_config cfg;
     int64_t n = 0;
@@ -770,6 +836,9 @@ struct lf_model {
         std::map<std::string, std::unique_ptr<lf::DevBuf<double>>> v;   // per-structure parameter / state arrays
         bool cq_dirty = true;
     } st;
+    GraphCache graphs_of, graphs_ch;
+    int use_graphs = 1;                   // option "cuda_graphs"
+    int accumulate_discharge = 0;         // option "accumulate_discharge" (InitLisflood / repAverageDis)
     int overlap_isolated = 1;             // option "overlap_isolated"
     int early_blocks_per_sm = 2;          // option "early_blocks_per_sm"
     int nancheck = 0;                     // option "flagnancheck"
@@ -865,7 +934,7 @@ const FieldSpec SPECS[] = {
     {"ChanQKin", 1, CHAN, false, false}, {"ChanM3Kin", 1, CHAN, false, false}, {"ChanQ", 1, CHAN, false, false},
     {"sumDisDay", 1, CHAN, false, false}, {"sumDis", 1, CHAN, false, false}, {"ChanQAvg", 1, CHAN, false, false},
     {"ChanM3", 1, CHAN, false, false}, {"TotalCrossSectionArea", 1, CHAN, false, false},
-    {"DischargeM3Out", 1, CHAN, false, false}, {"ToChanM3RunoffDt", 1, CHAN, false, false},
+    {"DischargeM3Out", 1, CHAN, false, false}, {"ToChanM3RunoffDt", 1, CHAN, false, false}, {"CumQ", 1, CHAN, false, false},
     {"Chan2QKin", 1, CHAN, false, false}, {"Chan2M3Kin", 1, CHAN, false, false}, {"CrossSection2Area", 1, CHAN, false, false},
     {"Sideflow1Chan", 1, CHAN, false, false}, {"sumDisDay_NOTlast", 1, CHAN, false, false}, {"QLimit", 1, CHAN, false, false},
     {"M3Limit", 1, CHAN, false, false}, {"Chan2M3Start", 1, CHAN, false, false}, {"Chan2QStart", 1, CHAN, false, false},
@@ -1265,6 +1334,7 @@ int surface_stage(lf_model *m)
     LF_CHECK(refresh_params(m));
     lf_graph *g = m->g_of;
     OfPtrs O;
+    memset(&O, 0, sizeof(O));
     if (m->xchg) LF_CHECK(lf_xchg_begin(m->xchg, &m->x_parity));   // closed at the end of the channel stage
     LF_CHECK(make_view(m, m->xs_of, 1, 3, O.X));
     const bool hasx = O.X.xslot != nullptr;
@@ -1295,18 +1365,23 @@ int surface_stage(lf_model *m)
     O.InvDtSec = 1 / m->cfg.DtSec;
     O.P = lfkw::make_params(m->cfg.Beta);
     const std::vector<int32_t> &ls = g->h_level_start;
-    for (int l = 0; l < g->n_orders; ++l) {
-        int lo = ls[l], hi = ls[l + 1];
-        if (hi <= lo) continue;
-        if (hasx) {
-            if (m->quintic) k_of_level<true, true><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
-            else k_of_level<false, true><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
-        } else {
-            if (m->quintic) k_of_level<true, false><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
-            else k_of_level<false, false><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+    auto sweep = [&]() -> int {
+        for (int l = 0; l < g->n_orders; ++l) {
+            int lo = ls[l], hi = ls[l + 1];
+            if (hi <= lo) continue;
+            if (hasx) {
+                if (m->quintic) k_of_level<true, true><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+                else k_of_level<false, true><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+            } else {
+                if (m->quintic) k_of_level<true, false><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+                else k_of_level<false, false><<<lf::blocks_for(hi - lo, 128), 128, 0, st>>>(O, lo, hi);
+            }
+            LF_LAUNCH_CHECK();
         }
-        LF_LAUNCH_CHECK();
-    }
+        return LF_OK;
+    };
+    if (m->use_graphs && g->n_orders > 4) LF_CHECK(run_captured(m->graphs_of, &O, sizeof(O), st, sweep));
+    else LF_CHECK(sweep());
     // swap: the named maps must hold the new discharge
     for (int r = 0; r < 3; ++r) {
         Field *f = m->fields[names[r]].get();
@@ -1552,26 +1627,31 @@ int channel_stage(lf_model *m)
     }
     // the connected network: space-time wavefront over (level, sub-step)
     auto level_end = [&](int l) { return l == Lc - 1 ? iso_lo : ls[l + 1]; };
-    for (int d = 0; d < Lc + S - 1; ++d) {
-        int lo_lev = d - S + 1 > 0 ? d - S + 1 : 0;
-        int hi_lev = d < Lc - 1 ? d : Lc - 1;
-        int lo = ls[lo_lev], hi = level_end(hi_lev);
-        if (hi <= lo) continue;
-        const unsigned gb = lf::blocks_for(hi - lo, CH_THREADS);
+    auto wavefront = [&]() -> int {
+        for (int d = 0; d < Lc + S - 1; ++d) {
+            int lo_lev = d - S + 1 > 0 ? d - S + 1 : 0;
+            int hi_lev = d < Lc - 1 ? d : Lc - 1;
+            int lo = ls[lo_lev], hi = level_end(hi_lev);
+            if (hi <= lo) continue;
+            const unsigned gb = lf::blocks_for(hi - lo, CH_THREADS);
 #define LF_CHAN_LAUNCH(QZ_, HX_, HS_) k_chan_diagonal<QZ_, HX_, HS_><<<gb, CH_THREADS, 0, sw>>>(C, lo, hi, d)
-        if (C.sid) {
-            if (m->quintic) LF_CHAN_LAUNCH(true, false, true);
-            else LF_CHAN_LAUNCH(false, false, true);
-        } else if (C.X.xslot) {
-            if (m->quintic) LF_CHAN_LAUNCH(true, true, false);
-            else LF_CHAN_LAUNCH(false, true, false);
-        } else {
-            if (m->quintic) LF_CHAN_LAUNCH(true, false, false);
-            else LF_CHAN_LAUNCH(false, false, false);
-        }
+            if (C.sid) {
+                if (m->quintic) LF_CHAN_LAUNCH(true, false, true);
+                else LF_CHAN_LAUNCH(false, false, true);
+            } else if (C.X.xslot) {
+                if (m->quintic) LF_CHAN_LAUNCH(true, true, false);
+                else LF_CHAN_LAUNCH(false, true, false);
+            } else {
+                if (m->quintic) LF_CHAN_LAUNCH(true, false, false);
+                else LF_CHAN_LAUNCH(false, false, false);
+            }
 #undef LF_CHAN_LAUNCH
-        LF_LAUNCH_CHECK();
-    }
+            LF_LAUNCH_CHECK();
+        }
+        return LF_OK;
+    };
+    if (m->use_graphs && Lc + S > 6) LF_CHECK(run_captured(m->graphs_ch, &C, sizeof(C), sw, wavefront));
+    else LF_CHECK(wavefront());
     LF_CUDA(cudaEventRecord(m->ev_join, sw));
     LF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
     if (m->xchg) LF_CHECK(lf_xchg_end(m->xchg));
@@ -1584,7 +1664,11 @@ int channel_stage(lf_model *m)
     FIELD(sdis, "sumDis");
     FIELD(qavg, "ChanQAvg");
     FIELD(dout, "DischargeM3Out");
-    double *fv = nullptr, *td = nullptr, *pa = nullptr;
+    double *fv = nullptr, *td = nullptr, *pa = nullptr, *cumq = nullptr;
+    if (m->accumulate_discharge) {
+        FIELD(cq_, "CumQ");
+        cumq = cq_;
+    }
     if (m->cfg.diagnostics) {
         FIELD(fv_, "FlowVelocity");
         FIELD(td_, "TravelDistance");
@@ -1595,7 +1679,7 @@ int channel_stage(lf_model *m)
     }
     k_chan_post<<<lf::blocks_for(m->n, 256), 256, 0, st>>>((int)m->n, C.split, m->quintic ? 1 : 0, S, m->cfg.DtSec, C.M3, m32, c2s, C.L,
                                                            C.sumDis, C.ChanQ, C.Qk, atlast, pa, chm3, tcs, sdis, qavg, dout, fv, td,
-                                                           m->nancheck ? m->iso_next.p + 2 : nullptr);
+                                                           m->nancheck ? m->iso_next.p + 2 : nullptr, cumq);
     LF_LAUNCH_CHECK();
     return LF_OK;
 }
@@ -2307,6 +2391,8 @@ int lf_model_set_option(lf_model *m, const char *name, double value)
     if (strcmp(name, "overlap_isolated") == 0) m->overlap_isolated = value != 0;
     else if (strcmp(name, "early_blocks_per_sm") == 0) m->early_blocks_per_sm = (int)value;
     else if (strcmp(name, "flagnancheck") == 0) m->nancheck = value != 0;
+    else if (strcmp(name, "cuda_graphs") == 0) m->use_graphs = value != 0;
+    else if (strcmp(name, "accumulate_discharge") == 0) m->accumulate_discharge = value != 0;
     else {
         lf::set_error("lf_model_set_option: unknown option '%s'", name);
         return LF_ERR_INVALID;
