@@ -160,6 +160,12 @@ int lf_model_set(lf_model *m, const char *name, const double *values, int64_t co
  * (lf_model_get, lf_synchronize); use page-locked memory for a truly asynchronous copy. */
 int lf_model_set_async(lf_model *m, const char *name, const double *values, int64_t count);
 int lf_model_get(lf_model *m, const char *name, double *values, int64_t count);
+/* Like lf_model_get, but returns at once: the map is brought to the reference's order on the compute stream (after all
+ * work already queued) and copied to `values` on a separate output stream, so the copy and whatever the host does with
+ * the previous step's map (writing dis.nc, time series) overlap the next step's kernels.  `values`
+ * (page-locked for a real overlap) is valid after lf_model_wait_outputs. */
+int lf_model_get_async(lf_model *m, const char *name, double *values, int64_t count);
+int lf_model_wait_outputs(lf_model *m);
 /* boolean maps (u8[N]): "isFrozenSoil", "IsChannel", "IsChannelKinematic", "AtLastPointC" */
 int lf_model_set_flags(lf_model *m, const char *name, const uint8_t *values, int64_t count);
 int lf_model_soil(lf_model *m);

@@ -80,6 +80,8 @@ SIGNATURES = {
     "lf_model_set": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
     "lf_model_set_async": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
     "lf_model_get": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
+    "lf_model_get_async": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
+    "lf_model_wait_outputs": (C.c_int, [_vp]),
     "lf_model_set_flags": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
     "lf_model_soil": (C.c_int, [_vp]),
     "lf_model_surface_routing": (C.c_int, [_vp]),

@@ -822,6 +822,11 @@ struct lf_model {
         int32_t n_export = 0, n_import = 0;
     } xs_of, xs_ch;
     int32_t x_parity = 0;
+    // asynchronous output path (lf_model_get_async): layout translation on the compute stream into a per-map staging
+    // buffer, device-to-host copy on its own stream
+    cudaStream_t out_stream = nullptr;
+    std::map<std::string, std::unique_ptr<lf::DevBuf<double>>> out_stage;
+    std::map<std::string, cudaEvent_t> out_ready, out_copied;
     // feeder modules: scalar parameters (a map of the same name, when set, takes precedence) and the raw-forcing staging
     std::map<std::string, double> scalars;
     lf::DevBuf<uint8_t> raw_stage[2];      // 4 maps each, double-buffered: the upload of step k+1 overlaps step k
@@ -866,6 +871,9 @@ struct lf_model {
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (side_stream) cudaStreamDestroy(side_stream);
         if (early_stream) cudaStreamDestroy(early_stream);
+        if (out_stream) cudaStreamDestroy(out_stream);
+        for (auto &kv : out_ready) cudaEventDestroy(kv.second);
+        for (auto &kv : out_copied) cudaEventDestroy(kv.second);
         for (int k = 0; k < 2; ++k) {
             if (raw_copied[k]) cudaEventDestroy(raw_copied[k]);
             if (raw_consumed[k]) cudaEventDestroy(raw_consumed[k]);
@@ -1960,6 +1968,61 @@ int lf_model_get(lf_model *m, const char *name, double *values, int64_t count)
     }
     LF_CUDA(cudaMemcpyAsync(values, m->stage.p, count * sizeof(double), cudaMemcpyDefault, st));
     LF_CUDA(cudaStreamSynchronize(st));
+    return LF_OK;
+}
+
+int lf_model_get_async(lf_model *m, const char *name, double *values, int64_t count)
+{
+    if (!m || !name || !values) {
+        lf::set_error("lf_model_get_async: null pointer");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    Field *f = nullptr;
+    LF_CHECK(field(m, name, &f));
+    if (count != (int64_t)f->rows * m->n) {
+        lf::set_error("lf_model_get_async(%s): expected %lld values, got %lld", name, (long long)f->rows * m->n, (long long)count);
+        return LF_ERR_INVALID;
+    }
+    cudaStream_t st = lf::stream();
+    if (!m->out_stream) LF_CUDA(cudaStreamCreateWithFlags(&m->out_stream, cudaStreamNonBlocking));
+    auto it = m->out_stage.find(name);
+    if (it == m->out_stage.end()) {
+        std::unique_ptr<lf::DevBuf<double>> b(new lf::DevBuf<double>());
+        LF_CHECK(b->alloc(count));
+        m->bytes += count * 8;
+        it = m->out_stage.emplace(name, std::move(b)).first;
+        cudaEvent_t e1, e2;
+        LF_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        LF_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        m->out_ready[name] = e1;
+        m->out_copied[name] = e2;
+        LF_CUDA(cudaEventRecord(e2, m->out_stream));
+    }
+    double *stg = it->second->p;
+    LF_CUDA(cudaStreamWaitEvent(st, m->out_copied[name], 0));   // the previous copy out of this staging buffer is done
+    const int32_t *pos = f->order == SOIL ? m->g_of->pos_of_pix.p : m->g_ch->pos_of_pix.p;
+    k_rows_to_pix<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(f->buf.p, stg, pos, m->n, f->rows);
+    LF_LAUNCH_CHECK();
+    if (f->as_z) {
+        k_z_to_q<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(stg, m->n);
+        LF_LAUNCH_CHECK();
+    }
+    LF_CUDA(cudaEventRecord(m->out_ready[name], st));
+    LF_CUDA(cudaStreamWaitEvent(m->out_stream, m->out_ready[name], 0));
+    LF_CUDA(cudaMemcpyAsync(values, stg, count * sizeof(double), cudaMemcpyDefault, m->out_stream));
+    LF_CUDA(cudaEventRecord(m->out_copied[name], m->out_stream));
+    return LF_OK;
+}
+
+int lf_model_wait_outputs(lf_model *m)
+{
+    if (!m) {
+        lf::set_error("lf_model_wait_outputs: null model");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    if (m->out_stream) LF_CUDA(cudaStreamSynchronize(m->out_stream));
     return LF_OK;
 }
 

@@ -1,0 +1,243 @@
+"""Output / forcing IO around the device-resident step, overlapped with it (reference:
+global_modules/output.py:68-167, netcdf.py:170-341,432-583, zusatz.py:196-405).
+
+  * MapStackWriter   a CF-1.6 map stack (time, y, x) like the reference's dis.nc: same dimensions, attributes, fill value
+                     and time axis (netcdf.py:432-583).  The reference writes NETCDF4/HDF5 through the netCDF4 package;
+                     neither it nor libhdf5 exists in this image, so the container is NetCDF-3 (64-bit offset, the
+                     record dimension `time` grows step by step), written with scipy.io.netcdf_file -- readable by
+                     netCDF4 / xarray like any other NetCDF file.
+  * TssWriter        a PCRaster timeoutput time series (dis.tss) in the reference's exact text layout (zusatz.py:201-297).
+  * OutputPipeline   per step: lf_model_get_async into one of two page-locked host buffers, then a writer thread
+                     decompresses the map to the raster and appends it to the files while the device computes the next
+                     step (the D2H copy runs on its own stream).
+  * ForcingStack     a float32 (time, y, x) NetCDF-3 forcing stack read through mmap; ForcingPrefetcher compresses the
+                     maps of the coming step into page-locked buffers on a thread and hands them to HotPathModel.feed
+                     (asynchronous H2D on the copy stream).
+"""
+import datetime
+import os
+import queue
+import threading
+import time as xtime
+
+import numpy as np
+
+FILL = -9999.0
+
+
+def time_units(dt_sec, start_date):
+    """netcdf.py:556-566."""
+    stamp = start_date.strftime("%Y-%m-%d %H:%M:%S.0")
+    if dt_sec >= 86400:
+        return "days since " + stamp, 86400.0
+    if dt_sec >= 3600:
+        return "hours since " + stamp, 3600.0
+    return "minutes since " + stamp, 60.0
+
+
+class MapStackWriter(object):
+    def __init__(self, path, var_name, land_mask, dt_sec, start_date, standard_name="", long_name="", units="",
+                 x=None, y=None, dtype="f8", settings_path="", calendar="proleptic_gregorian"):
+        from scipy.io import netcdf_file
+        self.mask = np.asarray(land_mask, bool)
+        rows, cols = self.mask.shape
+        self.nc = nc = netcdf_file(path, "w", version=2)
+        nc.settingsfile = os.path.realpath(settings_path) if settings_path else ""
+        nc.date_created = xtime.ctime(xtime.time())
+        nc.Source_Software = "lisflood_code_b200 (B200 hot path of Lisflood OS)"
+        nc.source = "Lisflood output maps"
+        nc.keywords = "Lisflood, EFAS, GLOFAS"
+        nc.Conventions = "CF-1.6"
+        nc.createDimension("time", None)
+        nc.createDimension("y", rows)
+        nc.createDimension("x", cols)
+        t = nc.createVariable("time", "f8", ("time",))
+        t.standard_name = "time"
+        t.calendar = calendar
+        t.units, self.unit_sec = time_units(dt_sec, start_date)
+        yv, xv = nc.createVariable("y", "f8", ("y",)), nc.createVariable("x", "f8", ("x",))
+        yv[:] = np.arange(rows, 0, -1, dtype=np.float64) if y is None else y      # y descending, x ascending
+        xv[:] = np.arange(cols, dtype=np.float64) if x is None else x
+        v = nc.createVariable(var_name, dtype, ("time", "y", "x"))
+        v._FillValue = np.array(FILL, dtype)
+        v.standard_name, v.long_name, v.units = standard_name, long_name, units
+        self.var, self.time, self.dt_sec, self.k = v, t, float(dt_sec), 0
+        self.raster = np.full((rows, cols), FILL, v.data.dtype if hasattr(v, "data") else np.float64)
+
+    def append(self, step, values):
+        """values: float64[N] compressed; step: 1-based model step (time stamp = start + (step - 1) * dt, netcdf.py:536)."""
+        self.raster[self.mask] = values                    # decompress (add1.py:287-305): -9999 outside the mask
+        self.var[self.k] = self.raster
+        self.time[self.k] = (step - 1) * self.dt_sec / self.unit_sec
+        self.k += 1
+
+    def close(self):
+        self.nc.close()
+
+
+class TssWriter(object):
+    """zusatz.py:201-297: header (spatial datatype, settings file, date; number of columns; 'timestep'; the gauge ids),
+    then one row per step: ' %8g' for the step and ' %14g' per gauge."""
+
+    def __init__(self, path, gauge_pixels, gauge_ids=None, settings_path="", datatype="scalar", header=True):
+        self.pix = np.asarray(gauge_pixels, np.int64)
+        ids = np.arange(1, self.pix.size + 1) if gauge_ids is None else np.asarray(gauge_ids)
+        self.f = open(path, "w")
+        if header:
+            self.f.write("timeseries {} settingsfile: {} date: {}\n".format(datatype, settings_path, xtime.ctime(xtime.time())))
+            self.f.write(str(self.pix.size + 1) + "\n")
+            self.f.write("timestep\n")
+            for i in ids:
+                self.f.write(str(i) + "\n")
+
+    def append(self, step, values):
+        row = " %8g" % step
+        for v in np.asarray(values)[self.pix]:
+            row += " %14g" % v
+        self.f.write(row + "\n")
+
+    def close(self):
+        self.f.close()
+
+
+def pinned(n, dtype=np.float64):
+    """A page-locked host array (registered with the CUDA driver through the library)."""
+    from .. import _capi
+    a = np.empty(n, dtype)
+    _capi.check(_capi.lib().lf_host_register(a.ctypes.data, a.nbytes))
+    return a
+
+
+class OutputPipeline(object):
+    """report(step) after every model step: the map leaves the device asynchronously and is written by a thread."""
+
+    def __init__(self, model, name, writers, pin=True):
+        self.M, self.name, self.writers = model, name, list(writers)
+        self.bufs = [pinned(model.N) if pin else np.empty(model.N) for _ in range(2)]
+        self.turn, self.pending = 0, None
+        self.q = queue.Queue(maxsize=2)
+        self.err = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            step, buf, done = item
+            try:
+                for w in self.writers:
+                    w.append(step, buf)
+            except Exception as e:       # surfaced by the next report() / close()
+                self.err = e
+            done.set()
+
+    def _flush_pending(self):
+        if self.pending is not None:
+            step, buf, done = self.pending
+            self.M.wait_outputs()                      # the D2H copy of that step has landed
+            self.q.put((step, buf, done))
+            self.pending = None
+
+    def report(self, step):
+        if self.err:
+            raise self.err
+        self._flush_pending()                          # hand the previous step's map to the writer thread
+        buf = self.bufs[self.turn]
+        done = getattr(self, "_done%d" % self.turn, None)
+        if done is not None:
+            done.wait()                                # the writer is finished with this buffer (two steps ago)
+        done = threading.Event()
+        setattr(self, "_done%d" % self.turn, done)
+        self.M.get_async(self.name, buf)               # queued behind the step's kernels; returns at once
+        self.pending = (step, buf, done)
+        self.turn ^= 1
+
+    def close(self):
+        self._flush_pending()
+        self.q.put(None)
+        self.thread.join()
+        for w in self.writers:
+            w.close()
+        if self.err:
+            raise self.err
+
+
+class ForcingStack(object):
+    """A (time, y, x) float32 stack in a NetCDF-3 file (what readmeteo's xarray reader delivers per step,
+    readmeteo.py:61-69, netcdf.py:170-341), memory-mapped; [k] gives the compressed float32 map of step k."""
+
+    def __init__(self, path, var_name, land_mask):
+        from scipy.io import netcdf_file
+        self.nc = netcdf_file(path, "r", mmap=True)
+        self.var = self.nc.variables[var_name]
+        self.mask = np.asarray(land_mask, bool)
+        v = self.var
+        self.scale = float(getattr(v, "scale_factor", 1.0))
+        self.offset = float(getattr(v, "add_offset", 0.0))
+
+    def __len__(self):
+        return self.var.shape[0]
+
+    def read_into(self, k, out):
+        a = self.var[k][self.mask]
+        if self.scale != 1.0 or self.offset != 0.0:
+            a = a * self.scale + self.offset
+        out[:] = a
+        return out
+
+    def close(self):
+        self.var = None
+        self.nc.close()
+
+
+def write_forcing_stack(path, var_name, land_mask, maps, dt_sec=86400.0, start_date=None):
+    """Writes compressed float32 maps [(N,), ...] as a (time, y, x) NetCDF-3 stack (test / example data)."""
+    from scipy.io import netcdf_file
+    mask = np.asarray(land_mask, bool)
+    rows, cols = mask.shape
+    nc = netcdf_file(path, "w", version=2)
+    nc.Conventions = "CF-1.6"
+    nc.createDimension("time", None)
+    nc.createDimension("y", rows)
+    nc.createDimension("x", cols)
+    t = nc.createVariable("time", "f8", ("time",))
+    t.units = time_units(dt_sec, start_date or datetime.datetime(2000, 1, 1))[0]
+    v = nc.createVariable(var_name, "f4", ("time", "y", "x"))
+    v._FillValue = np.float32(FILL)
+    ras = np.full((rows, cols), FILL, np.float32)
+    for k, m in enumerate(maps):
+        ras[mask] = m
+        v[k] = ras
+        t[k] = k
+    nc.close()
+
+
+class ForcingPrefetcher(object):
+    """Reads the four raw meteo maps of step k+1 from their stacks into page-locked float32 buffers on a thread while
+    step k runs; next() returns them (two buffer sets alternate: the set handed out stays valid until the call after
+    next, which is when HotPathModel.feed(..., asynchronous=True) has consumed it)."""
+    NAMES = ("Precipitation", "Tavg", "ET0", "E0")
+
+    def __init__(self, stacks, n, first=0, last=None, pin=True):
+        self.stacks = stacks
+        self.last = min(len(stacks[k]) for k in self.NAMES) if last is None else last
+        self.sets = [{k: (pinned(n, np.float32) if pin else np.empty(n, np.float32)) for k in self.NAMES} for _ in range(3)]
+        self.q = queue.Queue(maxsize=2)
+        self.thread = threading.Thread(target=self._run, args=(first,), daemon=True)
+        self.thread.start()
+
+    def _run(self, first):
+        for i, k in enumerate(range(first, self.last)):
+            s = self.sets[i % 3]
+            for name in self.NAMES:
+                self.stacks[name].read_into(k, s[name])
+            self.q.put((k, s))               # blocks while two sets are waiting: the third is the one in use
+        self.q.put(None)
+
+    def next(self):
+        item = self.q.get()
+        if item is None:
+            raise StopIteration
+        return item

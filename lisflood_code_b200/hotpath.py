@@ -238,6 +238,15 @@ class HotPathModel(object):
         _capi.check(_capi.lib().lf_model_get(self._h, name.encode(), _capi.ptr(out), size))
         return out
 
+    def get_async(self, name, out):
+        """Queues the copy of a map into `out` (page-locked NumPy array / torch tensor) without waiting; valid after
+        wait_outputs()."""
+        size = out.numel() if hasattr(out, "numel") else out.size
+        _capi.check(_capi.lib().lf_model_get_async(self._h, name.encode(), _capi.ptr(out), size))
+
+    def wait_outputs(self):
+        _capi.check(_capi.lib().lf_model_wait_outputs(self._h))
+
     def set_flags(self, name, values):
         if hasattr(values, "data_ptr"):
             assert values.element_size() == 1 and values.is_contiguous()
@@ -284,6 +293,8 @@ class HotPathModel(object):
 
     def channel(self):
         _capi.check(_capi.lib().lf_model_channel(self._h))
+        if self._nancheck:
+            self.check_finite()
 
     def step(self, F=None):
         if F is not None:
