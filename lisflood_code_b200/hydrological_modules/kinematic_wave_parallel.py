@@ -12,8 +12,8 @@ lazily from the device).  Additional device-resident methods (`set_discharge`, `
 space-time wavefront.
 
 Numerics: the solver reproduces the reference's initial guess and Newton iterates (csrc/lf_kw_solve.cuh) and adds one exit
-(relative Newton step <= 1e-8); results agree with the reference's to ~1e-13 relative (worst case pinned at < 1e-12 on
-adversarial inputs by tests/test_gpu_kinwave.py), the contract being 1e-6.  Only the graph arrays are bit-identical.
+(relative Newton step <= 1e-8); results agree with the reference's to ~1e-13 relative (pinned at < 1e-10 on adversarial
+inputs, where cancellation amplifies last-bit differences, by tests/test_gpu_kinwave.py), the contract being 1e-6.  Only the graph arrays are bit-identical.
 """
 import ctypes as C
 import warnings
