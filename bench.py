@@ -332,15 +332,18 @@ def run_c3(args):
         for k in hs:
             hs[k].copy_(Fdev[i][k])
         host_sets.append(hs)
-    dis_host = torch.empty(nl, dtype=torch.float64, pin_memory=True)
+    dis_host = [torch.empty(nl, dtype=torch.float64, pin_memory=True) for _ in range(2)]
     torch.cuda.synchronize()
     Ke = max(2, min(K, 5))
+    Mdev = M.model if cut else M
 
     def e2e_step(i):
         M.step()                                  # forcing of step i was queued by the feed() of the previous call
         day[0] = day[0] % 365 + 1
         feed(host_sets[(i + 1) % 2], day[0], asynchronous=True)   # next step's raw maps cross PCIe while step i computes
-        M.get_into("ChanQAvg", dis_host)          # D2H of this step's discharge map (synchronises)
+        Mdev.wait_outputs()                       # the discharge map of step i-1 has landed in its host buffer (the host
+        #                                           would hand it to the writer thread here: global_modules/output.py)
+        Mdev.get_async("ChanQAvg", dis_host[i % 2])   # D2H of this step's discharge map on the output stream
 
     feed(host_sets[0], day[0], asynchronous=True)
     e2e_step(0)
@@ -348,6 +351,7 @@ def run_c3(args):
     t0 = time.perf_counter()
     for k in range(Ke):
         e2e_step(k + 1)
+    Mdev.wait_outputs()                           # the last discharge map is on the host
     barrier()
     e2e_s = reduce_ranks(time.perf_counter() - t0)
     e2e_value = total_cells * Ke / e2e_s
@@ -414,7 +418,9 @@ def run_c3(args):
                         "d2h_bytes_per_step": int(d2h),
                         "note": "per step and GPU: raw Precipitation, Tavg, ET0, E0 (float32, as the reference's NetCDF forcing) from "
                                 "pinned host memory through HotPathModel.feed (copy stream, overlapping the previous step), "
-                                "discharge map ChanQAvg (float64) back to the host; the 10-day LAI maps stay resident"},
+                                "discharge map ChanQAvg (float64) back to the host on the output stream (HotPathModel.get_async, "
+                                "two host buffers; the timed region ends when the last map has landed); the 10-day LAI maps "
+                                "stay resident"},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
                 "roofline_stencil": roof_soil, "roofline_routing": roof_chan, "stage_ms_per_step": stage,
                 "soil_stats": soil_stats,
@@ -538,14 +544,16 @@ def run_reference_c3(args):
 
 
 def run_c4(args):
-    """BASELINE.json configs[3]: kinematic routing on ONE raster cut along the drainage graph across the ranks
-    (lisflood_code_b200/parallel.py), NCCL exchange of boundary discharges only.  Strong scaling: the raster is
-    fixed (--c4-rows, default 6000x6000; the named 20000x20000 needs the partitioner's host arrays in int32)."""
+    """BASELINE.json configs[3]: kinematic routing on ONE raster (default 20000x20000, 4e8 cells) cut along its drainage
+    graph across the ranks (lisflood_code_b200/parallel.py): every rank generates the same network on its GPU, the device
+    partitioner assigns the pixels, the routing kernels exchange boundary discharges over NVLink peer memory.  Strong
+    scaling; with one rank it is the plain single-GPU router on the same raster."""
     rank, world, local = dist_env()
     import torch
     import torch.distributed as dist
-    from lisflood_code_b200 import _capi, synthetic
+    from lisflood_code_b200 import _capi
     from lisflood_code_b200.parallel import DistributedKinematicWave
+    from lisflood_code_b200.synthetic_gpu import _ldd_gpu
     torch.cuda.set_device(local)
     _capi.check(_capi.lib().lf_device_init(local))
     if not dist.is_initialized():
@@ -553,19 +561,27 @@ def run_c4(args):
         os.environ.setdefault("MASTER_PORT", "29533")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     R = args.c4_rows
-    ldd2, mask = synthetic.random_ldd(R, R, seed=400, noise=args.c4_noise, single_outlet=True)   # ONE basin: must be cut
-    n = int(mask.sum())
-    alpha, q0, q = synthetic.routing_fields(n, 400)
-    tps = 48
+    n = R * R
     t0 = time.time()
-    D = DistributedKinematicWave(ldd2[mask], mask, alpha, 0.6, 5000.0, 3600.0, max_steps=tps)
-    t_init = time.time() - t0
+    ldd = _ldd_gpu(torch, R, R, 400, args.c4_noise)                      # same seed on every rank: the same network
+    mask = torch.ones(n, dtype=torch.uint8, device="cuda")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(400 + 7919)
+    U = lambda lo, hi: torch.rand(n, generator=g, device="cuda", dtype=torch.float64) * (hi - lo) + lo
+    alpha, q0, q = U(0.5, 3.0), U(0.1, 10.0), U(0.0, 1e-4)               # SURVEY.md 8d, C2 / C4 fields
+    tps = args.c4_steps
+    D = DistributedKinematicWave(ldd, mask, alpha, 0.6, 5000.0, 3600.0, max_steps=tps, rows=R, cols=R)
+    del ldd, mask
     D.set_discharge(q0)
     D.set_lateral_inflow(q)
+    del alpha, q0, q
+    torch.cuda.empty_cache()
+    t_init = time.time() - t0
     scales = np.random.default_rng(9).uniform(0.5, 1.5, (8, tps))
     K, W = args.steps, args.warmup
 
     def barrier():
+        torch.cuda.synchronize()
         dist.barrier()
         _capi.synchronize()
 
@@ -582,32 +598,88 @@ def run_c4(args):
         ms = _capi.timer_stop()
         barrier()
         wall = time.perf_counter() - t0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, wall], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, wall = float(t[0].item()), float(t[1].item())
     launches = _capi.launch_count()
+    aborted, runs = D.status()
     if rank == 0:
         peak, peak_kind = measured_peaks()
         value = n * tps * K / (ms * 1e-3)
-        ach = ALG_BYTES_ROUTING * max(D.part.loads) * tps * K / (ms * 1e-3) / 1e9
+        ach = ALG_BYTES_ROUTING * max(D.loads) * tps * K / (ms * 1e-3) / 1e9
         print(json.dumps({"metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K,
                           "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": "C4 synthetic %dx%d raster, kinematic routing only, LDD-cut across %d GPUs "
-                                                 "(sub-trees bin-packed, trunk on rank 0), NCCL exchange of boundary "
-                                                 "discharges" % (R, R, world), "cells": n, "timesteps_per_step": tps,
-                                     "cells_per_rank": D.part.loads, "cut_edges_per_rank": D.part.n_cut,
-                                     "trunk_pixels": int(D.part.trunk.sum()),
-                                     "bytes_exchanged_per_step": int(sum(D.part.n_cut) * tps * 8)},
+                          "config": {"workload": "C4 synthetic %dx%d raster, kinematic routing only, ONE network cut along its "
+                                                 "drainage graph over %d GPUs (sub-trees bin-packed, trunk spread over the ranks, "
+                                                 "owner-to-owner cut edges), boundary discharges exchanged in-kernel over NVLink "
+                                                 "peer memory" % (R, R, world), "cells": n, "timesteps_per_step": tps,
+                                     "levels": D.kw.num_orders, "cells_per_rank": D.loads, "cut_edges": D.cut_edges,
+                                     "trunk_pixels": D.n_trunk, "subtrees": D.n_roots,
+                                     "bytes_exchanged_per_step": int(D.cut_edges * tps * 8), "exchange_aborted": aborted,
+                                     "l2_policy": "6 float64 maps of %.0f MB per rank, far above the 126 MB L2" % (max(D.loads) * 8 / 1e6)},
                           "e2e": {"value": n * tps * K / wall, "unit": "cell-updates/s", "h2d_bytes_per_step": tps * 8,
-                                  "d2h_bytes_per_step": 0, "note": "host wall clock around the same K steps (inputs are "
-                                  "the 48 inflow multipliers per step)"},
+                                  "d2h_bytes_per_step": 0, "note": "host wall clock around the same K steps (per step the "
+                                  "host sends the inflow multipliers of its time steps; the state stays resident)"},
                           "gpu_launches": int(launches), "clocks": clk.summary(),
-                          "roofline": {"bound": "hbm", "kernel": "k_kw_diagonal<true,true> (busiest rank)",
+                          "roofline": {"bound": "hbm", "kernel": "k_kw_diagonal (busiest rank)",
                                        "achieved": round(ach, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                                       "frac": round(ach / peak, 4), "traffic": None},
+                                       "frac": round(ach / peak, 4), "traffic": None,
+                                       "note": "FP64-bound Newton solve: the HBM fraction is informational (DESIGN.md)"},
                           "cpu_baseline": None, "init_s": round(t_init, 2)}), flush=True)
+    D.close()
     dist.destroy_process_group()
+
+
+def run_c5(args):
+    """BASELINE.json configs[4] (EFAS-like): ~1000x950 raster with sea, 6-hourly steps, 6 routing sub-steps per step, split
+    routing, reservoirs and lakes inside the sub-step loop.  One GPU: a domain of ~5e5 cells is launch-latency bound (the
+    whole step is a few hundred small launches replayed as CUDA graphs), so spreading it over more GPUs cannot help."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    from lisflood_code_b200 import _capi, synthetic
+    from lisflood_code_b200.hotpath import HotPathModel
+    _capi.check(_capi.lib().lf_device_init(local))
+    t0 = time.time()
+    S = synthetic.full_stack(1000, 950, seed=500, split_routing=True, ldd_noise=0.5, mask_fraction=0.45, channel_threshold=25,
+                             dt_sec=21600.0)
+    synthetic.add_structures(S, 40, 20, seed=500)
+    M = HotPathModel(S)
+    info = M.info()
+    t_init = time.time() - t0
+    F = [synthetic.forcing(S, t, 500) for t in range(4)]
+    K, W = args.steps, args.warmup
+    results = {}
+    for graphs in (1, 0):
+        M.set_option("cuda_graphs", graphs)
+        for w in range(max(W, 3)):
+            M.step(F[w % 4])
+        _capi.synchronize()
+        _capi.launch_count(reset=True)
+        with ClockSampler(local) as clk:
+            _capi.timer_start()
+            t1 = time.perf_counter()
+            for k in range(K):
+                M.step(F[k % 4])
+            ms = _capi.timer_stop()
+            wall = time.perf_counter() - t1
+        results[graphs] = (ms / K, wall / K * 1e3, _capi.launch_count() / K, clk.summary())
+    ms, wall_ms, launches, clocks = results[1]
+    n = S["N"]
+    print(json.dumps({"metric": "cell-updates/s", "value": n / (ms * 1e-3), "unit": "cell-updates/s", "n_gpus": 1, "steps": K,
+                      "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "C5 EFAS-like synthetic 1000x950 raster with 45 % sea, 6-hourly steps, 6 routing "
+                                             "sub-steps, split routing, 40 reservoirs + 20 lakes in the sub-step loop", "cells": n,
+                                 "levels_overland": info["levels_overland"], "levels_channel": info["levels_channel"],
+                                 "forcing": "host NumPy maps set every step (the step includes their upload)"},
+                      "e2e": {"value": n / (wall_ms * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": int(n * 8 * 11 + n),
+                              "d2h_bytes_per_step": 0, "note": "host wall clock of the same steps"},
+                      "gpu_launches": int(launches * K), "kernels_per_step": launches, "clocks": clocks,
+                      "without_cuda_graphs": {"ms_per_step": results[0][0], "wall_ms_per_step": results[0][1]},
+                      "one_year_6_hourly_s": round(1460 * wall_ms / 1e3, 1),
+                      "roofline": None, "cpu_baseline": None, "init_s": round(t_init, 2)}), flush=True)
 
 
 def best_threads(ora, wl, lisf_oracle):
@@ -682,9 +754,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c3-replicas", "c2", "c4"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c3-replicas", "c2", "c4", "c5"])
+    ap.add_argument("--c4-steps", type=int, default=48, help="routing time steps per bench step (one wavefront run)")
     ap.add_argument("--overlap", type=int, default=0, help="1: co-schedule the isolated non-channel pixels with the soil stage")
-    ap.add_argument("--c4-rows", type=int, default=6000)
+    ap.add_argument("--c4-rows", type=int, default=20000)
     ap.add_argument("--c4-noise", type=float, default=0.2, help="noise/tilt of the C4 basin (0.2: a single catchment)")
     ap.add_argument("--rows", type=int, default=10000)
     ap.add_argument("--cols", type=int, default=10000)
@@ -699,6 +772,8 @@ def main():
     args = ap.parse_args()
     if args.workload == "c4" and args.impl != "reference":
         run_c4(args)
+    elif args.workload == "c5" and args.impl != "reference":
+        run_c5(args)
     elif args.workload in ("c3", "c3-replicas"):
         if args.impl == "reference":
             run_reference_c3(args)

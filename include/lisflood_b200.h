@@ -61,6 +61,10 @@ int64_t lf_launch_count(int reset);
 /* Page-locks / unlocks a host buffer the caller will pass repeatedly (faster H2D/D2H). */
 int lf_host_register(void *ptr, int64_t bytes);
 int lf_host_unregister(void *ptr);
+/* Page-locked host memory owned by the library (for buffers whose lifetime the caller cannot tie to an unregister call:
+ * a range that is freed while still registered poisons later copies from re-used addresses). */
+int lf_host_alloc(int64_t bytes, void **out);
+int lf_host_free(void *ptr);
 /* On-device accuracy check of the library's hand-written float64 math against the CUDA math library over n
  * pseudo-random arguments: max_err[8] = maximum relative error of { Newton division, Newton square root, table x^y
  * (normalised by 1 + |y log2 x|), table e^x (normalised by 1 + |x|), fifth root, cube root, polynomial x^y

@@ -44,6 +44,8 @@ SIGNATURES = {
     "lf_launch_count": (C.c_int64, [C.c_int]),
     "lf_host_register": (C.c_int, [_vp, _i64s]),
     "lf_host_unregister": (C.c_int, [_vp]),
+    "lf_host_alloc": (C.c_int, [_i64s, C.POINTER(_vp)]),
+    "lf_host_free": (C.c_int, [_vp]),
     "lf_math_selftest": (C.c_int, [_i64s, C.c_uint64, _f64]),
     "lf_ldd_build": (C.c_int, [_vp, _vp, _i64s, _i64s, C.POINTER(_vp)]),
     "lf_graph_info": (C.c_int, [_vp, C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s)]),
@@ -180,6 +182,36 @@ def ptr(a):
             torch.cuda.current_stream(a.device).synchronize()
         return _vp(a.data_ptr())
     return a.ctypes.data_as(_vp)
+
+
+class _PinnedBlock(object):
+    """cudaHostAlloc'ed memory, freed when the last array that views it is gone."""
+
+    def __init__(self, nbytes):
+        self.ptr = _vp()
+        check(lib().lf_host_alloc(int(nbytes), C.byref(self.ptr)))
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None:
+                _lib.lf_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+class PinnedArray(np.ndarray):
+    """NumPy array in page-locked host memory owned by the library (views keep the block alive through `.base`)."""
+    _block = None
+
+
+def pinned_empty(n, dtype=np.float64):
+    dt = np.dtype(dtype)
+    blk = _PinnedBlock(max(int(n) * dt.itemsize, 1))
+    buf = (C.c_char * blk.nbytes).from_address(blk.ptr.value)
+    a = np.frombuffer(buf, dt, count=int(n)).view(PinnedArray)
+    a._block = blk
+    return a
 
 
 def device_info():

@@ -147,6 +147,26 @@ int lf_host_register(void *ptr, int64_t bytes)
     return LF_OK;
 }
 
+int lf_host_alloc(int64_t bytes, void **out)
+{
+    if (!out || bytes <= 0) {
+        lf::set_error("lf_host_alloc: null pointer or empty size");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    *out = nullptr;
+    LF_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return LF_OK;
+}
+
+int lf_host_free(void *ptr)
+{
+    if (!ptr) return LF_OK;
+    LF_CHECK(lf::ensure_device());
+    LF_CUDA(cudaFreeHost(ptr));
+    return LF_OK;
+}
+
 int lf_host_unregister(void *ptr)
 {
     if (!ptr) return LF_OK;

@@ -101,11 +101,9 @@ class TssWriter(object):
 
 
 def pinned(n, dtype=np.float64):
-    """A page-locked host array (registered with the CUDA driver through the library)."""
+    """A page-locked host array (cudaHostAlloc through the library; freed with its last view)."""
     from .. import _capi
-    a = np.empty(n, dtype)
-    _capi.check(_capi.lib().lf_host_register(a.ctypes.data, a.nbytes))
-    return a
+    return _capi.pinned_empty(n, dtype)
 
 
 class OutputPipeline(object):
@@ -215,25 +213,27 @@ def write_forcing_stack(path, var_name, land_mask, maps, dt_sec=86400.0, start_d
 
 
 class ForcingPrefetcher(object):
-    """Reads the four raw meteo maps of step k+1 from their stacks into page-locked float32 buffers on a thread while
-    step k runs; next() returns them (two buffer sets alternate: the set handed out stays valid until the call after
-    next, which is when HotPathModel.feed(..., asynchronous=True) has consumed it)."""
+    """Reads the four raw meteo maps of the coming steps from their stacks into page-locked float32 buffers on a thread
+    while the current step runs; next() returns (step index, maps).  Four buffer sets rotate and at most two finished
+    sets wait in the queue, so the set handed out by next() is not refilled before next() has been called twice more:
+    by then the asynchronous upload HotPathModel.feed(..., asynchronous=True) started from it has long finished (the
+    caller synchronises with the device once per step, e.g. through OutputPipeline.report / wait_outputs)."""
     NAMES = ("Precipitation", "Tavg", "ET0", "E0")
 
     def __init__(self, stacks, n, first=0, last=None, pin=True):
         self.stacks = stacks
         self.last = min(len(stacks[k]) for k in self.NAMES) if last is None else last
-        self.sets = [{k: (pinned(n, np.float32) if pin else np.empty(n, np.float32)) for k in self.NAMES} for _ in range(3)]
-        self.q = queue.Queue(maxsize=2)
+        self.sets = [{k: (pinned(n, np.float32) if pin else np.empty(n, np.float32)) for k in self.NAMES} for _ in range(4)]
+        self.q = queue.Queue(maxsize=1)
         self.thread = threading.Thread(target=self._run, args=(first,), daemon=True)
         self.thread.start()
 
     def _run(self, first):
         for i, k in enumerate(range(first, self.last)):
-            s = self.sets[i % 3]
+            s = self.sets[i % 4]
             for name in self.NAMES:
                 self.stacks[name].read_into(k, s[name])
-            self.q.put((k, s))               # blocks while two sets are waiting: the third is the one in use
+            self.q.put((k, s))               # blocks while a finished set is waiting
         self.q.put(None)
 
     def next(self):
