@@ -210,7 +210,9 @@ int lf_model_set_lai(lf_model *m, const double *lai, int64_t count);
  * structures.initial cuts it (`LddStructuresKinematic`, structures.py:43-61): the library applies the cut (nothing is
  * routed into a structure pixel; its inflow is the ChanQ its upstream neighbours had after the previous sub-step,
  * np.bincount(downstruct, ChanQ), reservoir.py:190 / lakes.py:215; its outflow joins the side flow, routing.py:472-476).
- * reservoir_index / lake_index: compressed pixel indices (ReservoirIndex, LakeIndex), host arrays.
+ * reservoir_index / lake_index: compressed pixel indices (ReservoirIndex, LakeIndex), host arrays.  On a cut raster
+ * every rank passes the structures it owns (local indices); a structure and the pixels draining into it must sit on one
+ * rank (lisflood_code_b200/parallel.py arranges that).
  * lf_model_structure_array reads (set = 0) or writes (set = 1) a per-structure array (host or device pointer), in the
  * order of the index arrays, by the reference's names: TotalReservoirStorageM3CC, ConservativeStorageLimitCC,
  * NormalStorageLimitCC, Normal_FloodStorageLimitCC, FloodStorageLimitCC, MinReservoirOutflowCC, NormalReservoirOutflowCC,

@@ -658,12 +658,12 @@ __global__ void k_i32_rows_to_pos(const int32_t *__restrict__ src, int32_t *__re
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[pix_of_pos[i]];
 }
-__global__ void k_struct_feeds(const int32_t *__restrict__ sid, const int32_t *__restrict__ cfirst, uint8_t *__restrict__ feeds,
-                               int64_t n)
+__global__ void k_struct_feeds(const int32_t *__restrict__ sid, const int32_t *__restrict__ cfirst, const int32_t *__restrict__ cend,
+                               uint8_t *__restrict__ feeds, int64_t n)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || sid[i] == 0) return;
-    for (int k = cfirst[i]; k < cfirst[i + 1]; ++k) feeds[k] = 1;
+    for (int k = cfirst[i]; k < (cend ? cend[i] : cfirst[i + 1]); ++k) feeds[k] = 1;
 }
 __global__ void k_struct_cq_init(const uint8_t *__restrict__ feeds, const double *__restrict__ ChanQ, double *__restrict__ CQ0,
                                  double *__restrict__ CQ1, int64_t n)
@@ -1643,7 +1643,10 @@ int channel_stage(lf_model *m)
             if (hi <= lo) continue;
             const unsigned gb = lf::blocks_for(hi - lo, CH_THREADS);
 #define LF_CHAN_LAUNCH(QZ_, HX_, HS_) k_chan_diagonal<QZ_, HX_, HS_><<<gb, CH_THREADS, 0, sw>>>(C, lo, hi, d)
-            if (C.sid) {
+            if (C.sid && C.X.xslot) {
+                if (m->quintic) LF_CHAN_LAUNCH(true, true, true);
+                else LF_CHAN_LAUNCH(false, true, true);
+            } else if (C.sid) {
                 if (m->quintic) LF_CHAN_LAUNCH(true, false, true);
                 else LF_CHAN_LAUNCH(false, false, true);
             } else if (C.X.xslot) {
@@ -2359,10 +2362,8 @@ int lf_model_set_structures(lf_model *m, int32_t n_reservoirs, const int64_t *re
         lf::set_error("lf_model_set_structures: bad arguments");
         return LF_ERR_INVALID;
     }
-    if (m->g_ch->restricted) {
-        lf::set_error("lf_model_set_structures: structures are not supported on a cut raster yet");
-        return LF_ERR_STATE;
-    }
+    // On a cut raster (lf_model_create_from_graphs) the caller passes the structures this rank owns; the pixels that drain
+    // into them must be local too (lisflood_code_b200/parallel.py keeps a structure and its feeders on one rank).
     LF_CHECK(lf::ensure_device());
     cudaStream_t st = lf::stream();
     lf_model::Structures &T = m->st;
@@ -2395,7 +2396,7 @@ int lf_model_set_structures(lf_model *m, int32_t n_reservoirs, const int64_t *re
     LF_CUDA(cudaMemsetAsync(T.feeds.p, 0, m->n, st));
     LF_CUDA(cudaMemsetAsync(T.CQ0.p, 0, m->n * sizeof(double), st));
     LF_CUDA(cudaMemsetAsync(T.CQ1.p, 0, m->n * sizeof(double), st));
-    k_struct_feeds<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(T.sid.p, m->g_ch->cfirst.p, T.feeds.p, m->n);
+    k_struct_feeds<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(T.sid.p, m->g_ch->cfirst.p, m->g_ch->cend.p, T.feeds.p, m->n);
     LF_LAUNCH_CHECK();
     T.v.clear();
     for (const char *nm : RES_NAMES) {

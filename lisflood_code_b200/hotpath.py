@@ -123,10 +123,8 @@ class HotPathModel(object):
                 self.set_flags(name, pick(S[name]) if pick else S[name])
         self.__dict__["_res_index"] = np.zeros(0, np.int64)
         self.__dict__["_lake_index"] = np.zeros(0, np.int64)
-        if S.get("simulateReservoirs") or S.get("simulateLakes"):
-            if graphs is not None:
-                raise _capi.LisfloodB200Error(_capi.LF_ERR_STATE, "structures are not supported on a cut raster yet")
-            self.set_structures(S)
+        if (S.get("simulateReservoirs") or S.get("simulateLakes")) and graphs is None:
+            self.set_structures(S)     # on a cut raster the caller hands over this rank's structures (parallel.py)
 
     # ---- raw access --------------------------------------------------------------------------------
     def set(self, name, values, rows=None):

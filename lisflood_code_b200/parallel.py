@@ -381,8 +381,28 @@ class DistributedHotPathModel(object):
             owner, loads, ntrunk, nroots = D.partition(g, n, subtree_fraction)
         finally:
             D.L.lf_graph_destroy(g)
+        structures = bool(S.get("simulateReservoirs") or S.get("simulateLakes"))
+        ldd_kin = S["LddKinematic"]
+        if structures:
+            # The channel graph is levelled on the network before structures.initial cuts it (hotpath.py), and a structure
+            # stays on one rank with the pixels that drain into it (its inflow is their ChanQ of the previous sub-step,
+            # np.bincount(downstruct, ChanQ)): those pixels follow the structure's owner, so no cut edge enters a structure.
+            ldd_kin = S["LddStructuresKinematic"]
+            sites = np.concatenate([np.asarray(S["ReservoirIndex"], np.int64) if S.get("simulateReservoirs") else np.zeros(0, np.int64),
+                                    np.asarray(S["LakeIndex"], np.int64) if S.get("simulateLakes") else np.zeros(0, np.int64)])
+            down = np.asarray(S["downstruct"], np.int64)
+            feeders = np.flatnonzero(np.isin(down, sites))
+            if feeders.size:
+                f_dev = torch.as_tensor(feeders, device="cuda")
+                d_dev = torch.as_tensor(down[feeders], device="cuda")
+                for _ in range(64):                      # chains of structures feeding structures settle in a few rounds
+                    new = owner[d_dev]
+                    if bool((owner[f_dev] == new).all()):
+                        break
+                    owner[f_dev] = new
+                loads = torch.bincount(owner.to(torch.int64), minlength=self.world).cpu().numpy()
         g_of = D.build_graph(as_dev(S["LddToChan"], torch.float64), mask, rows, cols)
-        g_ch = D.build_graph(as_dev(S["LddKinematic"], torch.float64), mask, rows, cols)
+        g_ch = D.build_graph(as_dev(ldd_kin, torch.float64), mask, rows, cols)
         try:
             e_of, e_ch = D.cut_edges(g_of, owner), D.cut_edges(g_ch, owner)
             graphs = {"overland": (e_of[0], e_of[1], D.owners_of(owner, e_of[0]), D.owners_of(owner, e_of[1]), 3, 1),
@@ -399,8 +419,11 @@ class DistributedHotPathModel(object):
         self.loc = self.loc_dev.cpu().numpy()
         self.owned_local = (owner[self.loc_dev] == self.rank).cpu().numpy()
         self.n_local = int(self.loc.size)
+        owner_of_sites = D.owners_of(owner, sites) if structures else None
         del owner, keep
         self.model = HotPathModel(S, diagnostics=diagnostics, graphs=(l_of, l_ch), n_active=self.n_local, pick=self._local)
+        if structures:
+            self._set_local_structures(S, owner_of_sites)
         self.xchg = D.open_region(self.plan.region_doubles[self.rank])
         self._keep = []
         for which, name in enumerate(("overland", "channel")):
@@ -410,6 +433,26 @@ class DistributedHotPathModel(object):
             self._keep.append(keepalive)
             _capi.check(D.L.lf_model_set_exchange(self.model._h, self.xchg, which, _capi.ptr(xslot), ne, pp, po, ps, ni, io))
         dist.barrier()
+
+    def _set_local_structures(self, S, owner_of_sites):
+        """Hands this rank's reservoirs / lakes (local pixel indices, the matching slices of the per-structure arrays) to its
+        model; maps such as ReservoirStorageM3 then gather like any other map."""
+        from .hotpath import LAKE_ARRAYS, RESERVOIR_ARRAYS
+        nres = len(S["ReservoirIndex"]) if S.get("simulateReservoirs") else 0
+        sub = {"simulateReservoirs": False, "simulateLakes": False}
+        for flag, key, names, own in (("simulateReservoirs", "ReservoirIndex", RESERVOIR_ARRAYS, owner_of_sites[:nres]),
+                                      ("simulateLakes", "LakeIndex", LAKE_ARRAYS, owner_of_sites[nres:])):
+            if not S.get(flag):
+                continue
+            mine = np.flatnonzero(own == self.rank)
+            if mine.size == 0:
+                continue
+            sub[flag] = True
+            sub[key] = np.searchsorted(self.loc, np.asarray(S[key], np.int64)[mine]).astype(np.int64)
+            for name in names:
+                sub[name] = np.asarray(S[name], np.float64)[mine]
+        if sub["simulateReservoirs"] or sub["simulateLakes"]:
+            self.model.set_structures(sub)
 
     def _local(self, a):
         """Local pixels of a global map (last axis = pixels); scalars and local-sized arrays pass through."""

@@ -88,9 +88,12 @@ for (rows, cols, noise, maskf, beta, single) in (cases[:1] if stress else cases)
     dist.barrier()
 
 # ---- full model ------------------------------------------------------------------------------------------------
-model_cases = ((150, 120, False, 7), (130, 160, True, 8)) if not stress else ((90, 80, True, 9),)
-for (rows, cols, split, seed) in model_cases:
-    S = synthetic.full_stack(rows, cols, seed=seed, split_routing=split, ldd_noise=0.4, mask_fraction=0.1)
+model_cases = ((150, 120, False, 7, 0), (130, 160, True, 8, 0), (140, 150, True, 91, 11)) if not stress else ((90, 80, True, 9, 0),)
+for (rows, cols, split, seed, nstruct) in model_cases:
+    S = synthetic.full_stack(rows, cols, seed=seed, split_routing=split, ldd_noise=0.4, mask_fraction=0.1,
+                             **({"channel_threshold": 12, "dt_sec": 21600.0} if nstruct else {}))
+    if nstruct:                      # reservoirs and lakes in the sub-step loop, on a cut raster
+        synthetic.add_structures(S, nstruct // 2 + 1, nstruct // 2, seed=seed)
     M = DistributedHotPathModel(S, diagnostics=False, subtree_fraction=0.02)   # small sub-trees: the basins of these small rasters get cut
     nsteps = 12 if stress else 3
     for t in range(nsteps):
@@ -98,7 +101,8 @@ for (rows, cols, split, seed) in model_cases:
             time.sleep(0.05)
         M.step(synthetic.forcing(S, t, seed))
     keys = [("ChanQAvg", 1), ("ChanQKin", 1), ("ChanM3Kin", 1), ("OFQOther", 1), ("OFQDirect", 1), ("W1a", 3), ("UZ", 3),
-            ("LZ", 1), ("sumDis", 1)] + ([("Chan2QKin", 1), ("Chan2M3Kin", 1)] if split else [])
+            ("LZ", 1), ("sumDis", 1)] + ([("Chan2QKin", 1), ("Chan2M3Kin", 1)] if split else []) + \
+        ([("ReservoirStorageM3", 1), ("ReservoirFill", 1), ("QResOutM3Dt", 1), ("LakeStorageM3", 1), ("LakeOutflow", 1)] if nstruct else [])
     got = {k: M.gather(k, r) for k, r in keys}
     aborted, epochs = M.status()
     summ = M.plan.summary()
@@ -107,8 +111,8 @@ for (rows, cols, split, seed) in model_cases:
         for t in range(nsteps):
             R.step(synthetic.forcing(S, t, seed))
         diff = [k for k, r in keys if not np.array_equal(got[k], R.get(k, r))]
-        say("model %dx%d split=%s: loads %s, cut edges overland %d channel %d | maps that differ from 1 GPU: %s | aborted %s" % (
-            rows, cols, split, M.loads, summ["overland"]["cut_edges"], summ["channel"]["cut_edges"], diff or "none", aborted))
+        say("model %dx%d split=%s structures=%d: loads %s, cut edges overland %d channel %d | maps that differ from 1 GPU: %s | aborted %s" % (
+            rows, cols, split, nstruct, M.loads, summ["overland"]["cut_edges"], summ["channel"]["cut_edges"], diff or "none", aborted))
         ok = ok and not diff and not aborted and (world == 1 or summ["channel"]["cut_edges"] + summ["overland"]["cut_edges"] > 0)
         R.close()
     M.close()
