@@ -248,7 +248,7 @@ def run_c3(args):
     rows, cols = args.rows, args.cols
     t0 = time.time()
     dev = C3Device(rows, cols, seed=300 + (0 if cut or not use_dist else rank), ldd_noise=args.ldd_noise, no_rout_steps=24,
-                   distributed=cut)
+                   distributed=cut, single_outlet=args.basin == "single")
     M = dev.model
     if os.environ.get("LF_EARLY_BPS"):      # tuning runs: resident blocks per SM of the early isolated-pixel launch
         M.set_option("early_blocks_per_sm", int(os.environ["LF_EARLY_BPS"]))
@@ -401,7 +401,9 @@ def run_c3(args):
                   "isolated_channel_pixels": info["isolated_channel_pixels"], "device_bytes_maps": info["device_bytes"],
                   "l2_policy": "every map is %.0f MB per GPU (> 126 MB L2 for more than ~1.6e7 cells per GPU); two raw forcing "
                                "sets alternate between steps, the 10-day LAI maps stay resident" % (nl * 8 / 1e6),
-                  "spinup_steps": args.spinup, "co_scheduled_isolated_pixels": bool(args.overlap)}
+                  "spinup_steps": args.spinup, "co_scheduled_isolated_pixels": bool(args.overlap),
+                  "drainage": "one basin (south-edge collector)" if args.basin == "single" else
+                              "many catchments (steepest descent on tilted noise, every local sink is an outlet)"}
         if cut:
             summ = M.plan.summary()
             config.update({"cells_per_rank": M.loads, "trunk_pixels": M.n_trunk, "subtrees": M.n_roots,
@@ -425,6 +427,18 @@ def run_c3(args):
                 "roofline_stencil": roof_soil, "roofline_routing": roof_chan, "stage_ms_per_step": stage,
                 "soil_stats": soil_stats,
                 "cpu_baseline": cpu, "init_s": round(t_init, 2)}
+    # multi-GPU default run: the same invocation also measures C4 (BASELINE.json configs[3]: 20000x20000 routing only, ONE
+    # basin that has to be cut) and attaches its line, so the scaling record carries a workload with real cut edges too
+    c4 = None
+    if cut and not args.no_c4:
+        del Fdev, host_sets, dis_host
+        M.close()
+        dev.model = None
+        torch.cuda.empty_cache()
+        c4 = run_c4(args, attached=True)
+    if rank == 0:
+        if c4 is not None:
+            line["c4_cut"] = {k: c4[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "scaling", "config", "gpu_launches")}
         print(json.dumps(line), flush=True)
     if use_dist:
         dist.destroy_process_group()
@@ -543,7 +557,7 @@ def run_reference_c3(args):
                       "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def run_c4(args):
+def run_c4(args, attached=False):
     """BASELINE.json configs[3]: kinematic routing on ONE raster (default 20000x20000, 4e8 cells) cut along its drainage
     graph across the ranks (lisflood_code_b200/parallel.py): every rank generates the same network on its GPU, the device
     partitioner assigns the pixels, the routing kernels exchange boundary discharges over NVLink peer memory.  Strong
@@ -556,14 +570,15 @@ def run_c4(args):
     from lisflood_code_b200.synthetic_gpu import _ldd_gpu
     torch.cuda.set_device(local)
     _capi.check(_capi.lib().lf_device_init(local))
-    if not dist.is_initialized():
+    own_group = not dist.is_initialized()
+    if own_group:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29533")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     R = args.c4_rows
     n = R * R
     t0 = time.time()
-    ldd = _ldd_gpu(torch, R, R, 400, args.c4_noise)                      # same seed on every rank: the same network
+    ldd = _ldd_gpu(torch, R, R, 400, args.c4_noise, single_outlet=True)   # same seed on every rank: ONE basin
     mask = torch.ones(n, dtype=torch.uint8, device="cuda")
     g = torch.Generator(device="cuda")
     g.manual_seed(400 + 7919)
@@ -578,7 +593,7 @@ def run_c4(args):
     torch.cuda.empty_cache()
     t_init = time.time() - t0
     scales = np.random.default_rng(9).uniform(0.5, 1.5, (8, tps))
-    K, W = args.steps, args.warmup
+    K, W = (3, 2) if attached else (args.steps, max(args.warmup, 2))
 
     def barrier():
         torch.cuda.synchronize()
@@ -603,83 +618,149 @@ def run_c4(args):
     ms, wall = float(t[0].item()), float(t[1].item())
     launches = _capi.launch_count()
     aborted, runs = D.status()
+    line = None
     if rank == 0:
         peak, peak_kind = measured_peaks()
         value = n * tps * K / (ms * 1e-3)
         ach = ALG_BYTES_ROUTING * max(D.loads) * tps * K / (ms * 1e-3) / 1e9
-        print(json.dumps({"metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K,
-                          "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": "C4 synthetic %dx%d raster, kinematic routing only, ONE network cut along its "
-                                                 "drainage graph over %d GPUs (sub-trees bin-packed, trunk spread over the ranks, "
-                                                 "owner-to-owner cut edges), boundary discharges exchanged in-kernel over NVLink "
-                                                 "peer memory" % (R, R, world), "cells": n, "timesteps_per_step": tps,
-                                     "levels": D.kw.num_orders, "cells_per_rank": D.loads, "cut_edges": D.cut_edges,
-                                     "trunk_pixels": D.n_trunk, "subtrees": D.n_roots,
-                                     "bytes_exchanged_per_step": int(D.cut_edges * tps * 8), "exchange_aborted": aborted,
-                                     "l2_policy": "6 float64 maps of %.0f MB per rank, far above the 126 MB L2" % (max(D.loads) * 8 / 1e6)},
-                          "e2e": {"value": n * tps * K / wall, "unit": "cell-updates/s", "h2d_bytes_per_step": tps * 8,
-                                  "d2h_bytes_per_step": 0, "note": "host wall clock around the same K steps (per step the "
-                                  "host sends the inflow multipliers of its time steps; the state stays resident)"},
-                          "gpu_launches": int(launches), "clocks": clk.summary(),
-                          "roofline": {"bound": "hbm", "kernel": "k_kw_diagonal (busiest rank)",
-                                       "achieved": round(ach, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                                       "frac": round(ach / peak, 4), "traffic": None,
-                                       "note": "FP64-bound Newton solve: the HBM fraction is informational (DESIGN.md)"},
-                          "cpu_baseline": None, "init_s": round(t_init, 2)}), flush=True)
+        line = {"metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C4 synthetic %dx%d raster, kinematic routing only, ONE basin cut along its drainage "
+                                       "graph over %d GPU(s) (sub-trees bin-packed, trunk spread over the ranks, owner-to-owner cut "
+                                       "edges), boundary discharges exchanged in-kernel over NVLink peer memory" % (R, R, world),
+                           "cells": n, "timesteps_per_step": tps, "levels": D.kw.num_orders, "cells_per_rank": D.loads,
+                           "cut_edges": D.cut_edges, "trunk_pixels": D.n_trunk, "subtrees": D.n_roots,
+                           "bytes_exchanged_per_step": int(D.cut_edges * tps * 8), "exchange_aborted": aborted,
+                           "l2_policy": "6 float64 maps of %.0f MB per rank, far above the 126 MB L2" % (max(D.loads) * 8 / 1e6)},
+                "e2e": {"value": n * tps * K / wall, "unit": "cell-updates/s", "h2d_bytes_per_step": tps * 8,
+                        "d2h_bytes_per_step": 0, "note": "host wall clock around the same K steps (per step the host sends "
+                        "the inflow multipliers of its time steps; the state stays resident)"},
+                "gpu_launches": int(launches), "clocks": clk.summary(),
+                "roofline": {"bound": "hbm", "kernel": "k_kw_diagonal (busiest rank)", "achieved": round(ach, 1), "peak": peak,
+                             "peak_kind": peak_kind, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                             "note": "FP64-bound Newton solve: the HBM fraction is informational (DESIGN.md)"},
+                "cpu_baseline": None, "init_s": round(t_init, 2)}
+        if not attached:
+            print(json.dumps(line), flush=True)
     D.close()
-    dist.destroy_process_group()
+    if own_group:
+        dist.destroy_process_group()
+    return line
 
 
 def run_c5(args):
     """BASELINE.json configs[4] (EFAS-like): ~1000x950 raster with sea, 6-hourly steps, 6 routing sub-steps per step, split
-    routing, reservoirs and lakes inside the sub-step loop.  One GPU: a domain of ~5e5 cells is launch-latency bound (the
-    whole step is a few hundred small launches replayed as CUDA graphs), so spreading it over more GPUs cannot help."""
+    routing, reservoirs and lakes inside the sub-step loop.  A domain of ~5e5 cells is launch-latency bound: the step is
+    ~100 small kernels (replayed as CUDA graphs).  N > 1: the same raster cut over the ranks (a structure stays with its
+    feeders on one rank) -- reported for completeness; more GPUs cannot speed up a latency-bound step."""
     rank, world, local = dist_env()
-    if rank != 0:
-        return
+    import torch
     from lisflood_code_b200 import _capi, synthetic
     from lisflood_code_b200.hotpath import HotPathModel
+    torch.cuda.set_device(local)
     _capi.check(_capi.lib().lf_device_init(local))
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        from lisflood_code_b200.parallel import DistributedHotPathModel
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t0 = time.time()
     S = synthetic.full_stack(1000, 950, seed=500, split_routing=True, ldd_noise=0.5, mask_fraction=0.45, channel_threshold=25,
                              dt_sec=21600.0)
     synthetic.add_structures(S, 40, 20, seed=500)
-    M = HotPathModel(S)
-    info = M.info()
+    n = S["N"]
+    M = DistributedHotPathModel(S, subtree_fraction=0.05) if use_dist else HotPathModel(S)
+    Mdev = M.model if use_dist else M
+    nl = Mdev.N
+    rng = np.random.default_rng(500)
+    P = {"PrScaling": 1.0, "CalEvaporation": 1.0, "DeltaTSnow": 0.9674 * rng.uniform(0, 300.0, n) * 0.0065, "SnowSeason": 0.5,
+         "TempSnow": 1.0, "SnowFactor": 1.0, "SnowMeltCoef": 4.0, "TempMelt": 0.0, "lat_rad": np.radians(rng.uniform(35, 70, n)),
+         "Kfrost": 0.57, "Afrost": 0.97, "FrostIndexThreshold": 56.0, "SnowWaterEquivalent": 0.45, "kgb": 0.75 * 0.72}
+    M.set_feeder(P, {"SnowCoverS": np.zeros((3, n)), "FrostIndex": np.zeros(n)})
+    M.set_lai(rng.uniform(0, 6.0, (3, n)))
+    info = Mdev.info()
     t_init = time.time() - t0
-    F = [synthetic.forcing(S, t, 500) for t in range(4)]
-    K, W = args.steps, args.warmup
-    results = {}
-    for graphs in (1, 0):
-        M.set_option("cuda_graphs", graphs)
-        for w in range(max(W, 3)):
-            M.step(F[w % 4])
+    pick = M._local if use_dist else (lambda a: a)
+    raw_host = []
+    for i in range(4):
+        maps = {"Precipitation": (rng.gamma(0.8, 8.0, n) * (rng.random(n) < 0.45)).astype(np.float32),
+                "Tavg": rng.uniform(-6, 18, n).astype(np.float32), "ET0": rng.uniform(0, 6, n).astype(np.float32),
+                "E0": rng.uniform(0, 6, n).astype(np.float32)}
+        hs = {}
+        for k, a in maps.items():
+            hs[k] = _capi.pinned_empty(nl, np.float32)
+            hs[k][:] = pick(a)
+        raw_host.append(hs)
+    raw_dev = [{k: torch.as_tensor(np.asarray(a), device="cuda") for k, a in hs.items()} for hs in raw_host]
+    dis = [_capi.pinned_empty(nl, np.float64) for _ in range(2)]
+    K, W = args.steps, max(args.warmup, 3)
+
+    def sync():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
         _capi.synchronize()
+
+    results = {}
+    for graphs in (0, 1):
+        Mdev.set_option("cuda_graphs", graphs)
+        day = 40
+        for w in range(W):
+            Mdev.feed(raw_dev[w % 4], day + w)
+            Mdev.step()
+        sync()
         _capi.launch_count(reset=True)
         with ClockSampler(local) as clk:
             _capi.timer_start()
-            t1 = time.perf_counter()
             for k in range(K):
-                M.step(F[k % 4])
+                Mdev.feed(raw_dev[k % 4], day + k)
+                Mdev.step()
             ms = _capi.timer_stop()
-            wall = time.perf_counter() - t1
-        results[graphs] = (ms / K, wall / K * 1e3, _capi.launch_count() / K, clk.summary())
-    ms, wall_ms, launches, clocks = results[1]
-    n = S["N"]
-    print(json.dumps({"metric": "cell-updates/s", "value": n / (ms * 1e-3), "unit": "cell-updates/s", "n_gpus": 1, "steps": K,
-                      "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                      "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": "C5 EFAS-like synthetic 1000x950 raster with 45 % sea, 6-hourly steps, 6 routing "
-                                             "sub-steps, split routing, 40 reservoirs + 20 lakes in the sub-step loop", "cells": n,
-                                 "levels_overland": info["levels_overland"], "levels_channel": info["levels_channel"],
-                                 "forcing": "host NumPy maps set every step (the step includes their upload)"},
-                      "e2e": {"value": n / (wall_ms * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": int(n * 8 * 11 + n),
-                              "d2h_bytes_per_step": 0, "note": "host wall clock of the same steps"},
-                      "gpu_launches": int(launches * K), "kernels_per_step": launches, "clocks": clocks,
-                      "without_cuda_graphs": {"ms_per_step": results[0][0], "wall_ms_per_step": results[0][1]},
-                      "one_year_6_hourly_s": round(1460 * wall_ms / 1e3, 1),
-                      "roofline": None, "cpu_baseline": None, "init_s": round(t_init, 2)}), flush=True)
+        sync()
+        results[graphs] = (ms / K, _capi.launch_count() / K, clk.summary())
+    # end to end: raw float32 forcing from page-locked host memory (asynchronous), discharge map back every step
+    Mdev.feed(raw_host[0], 40, asynchronous=True)
+    sync()
+    t1 = time.perf_counter()
+    for k in range(K):
+        Mdev.step()
+        Mdev.feed(raw_host[(k + 1) % 4], 41 + k, asynchronous=True)
+        Mdev.wait_outputs()
+        Mdev.get_async("ChanQAvg", dis[k % 2])
+    Mdev.wait_outputs()
+    sync()
+    wall_ms = (time.perf_counter() - t1) / K * 1e3
+    ms, launches, clocks = results[1]
+    if use_dist:
+        t = torch.tensor([ms, wall_ms, results[0][0]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall_ms, ms_nograph = (float(x) for x in t.tolist())
+        aborted = M.status()[0]
+    else:
+        ms_nograph, aborted = results[0][0], None
+    if rank == 0:
+        cfg = {"workload": "C5 EFAS-like synthetic 1000x950 raster with 45 % sea, 6-hourly steps, feeder modules + soil + overland + "
+                           "6 routing sub-steps, split routing, 40 reservoirs + 20 lakes in the sub-step loop%s"
+                           % ("; ONE raster cut over %d GPUs" % world if use_dist else ""),
+               "cells": n, "cells_per_gpu": nl, "levels_overland": info["levels_overland"], "levels_channel": info["levels_channel"]}
+        if use_dist:
+            summ = M.plan.summary()
+            cfg.update({"cells_per_rank": M.loads, "cut_edges": {g: summ[g]["cut_edges"] for g in summ}, "exchange_aborted": aborted})
+        print(json.dumps({"metric": "cell-updates/s", "value": n / (ms * 1e-3), "unit": "cell-updates/s", "n_gpus": world, "steps": K,
+                          "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if use_dist else "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                          "e2e": {"value": n / (wall_ms * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": int(nl * 16),
+                                  "d2h_bytes_per_step": int(nl * 8), "ms_per_step": wall_ms,
+                                  "note": "raw float32 forcing from page-locked host memory (asynchronous), discharge map back "
+                                          "every step; host wall clock"},
+                          "gpu_launches": int(launches * K), "kernels_per_step": launches, "clocks": clocks,
+                          "without_cuda_graphs": {"ms_per_step": ms_nograph},
+                          "one_year_6_hourly_s": round(1460 * wall_ms / 1e3, 1),
+                          "roofline": None, "cpu_baseline": None, "init_s": round(t_init, 2)}), flush=True)
+    if use_dist:
+        M.close()
+        dist.destroy_process_group()
 
 
 def best_threads(ora, wl, lisf_oracle):
@@ -755,7 +836,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c3-replicas", "c2", "c4", "c5"])
-    ap.add_argument("--c4-steps", type=int, default=48, help="routing time steps per bench step (one wavefront run)")
+    ap.add_argument("--c4-steps", type=int, default=96, help="routing time steps per bench step (one wavefront run)")
+    ap.add_argument("--basin", default="many", choices=["many", "single"], help="C3 drainage network: many catchments "
+                    "(default, the round-1 raster) or ONE basin that has to be cut between the GPUs")
+    ap.add_argument("--no-c4", action="store_true", help="multi-GPU default run: skip the attached C4 leg")
     ap.add_argument("--overlap", type=int, default=0, help="1: co-schedule the isolated non-channel pixels with the soil stage")
     ap.add_argument("--c4-rows", type=int, default=20000)
     ap.add_argument("--c4-noise", type=float, default=0.2, help="noise/tilt of the C4 basin (0.2: a single catchment)")

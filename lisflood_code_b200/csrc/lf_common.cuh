@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
 #include <string>
 #include <vector>
 
@@ -81,6 +83,70 @@ inline bool is_device_ptr(const void *p)
 }
 
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ---- CUDA-graph replay of launch-bound loops (the level sweep of the overland routers, the diagonals of the channel
+// wavefront: hundreds of small dependent launches per step).  A loop is captured once per distinct argument set (the
+// kernel arguments are part of the key: buffers that alternate between steps give two or four variants) and replayed
+// with one cudaGraphLaunch afterwards.
+struct GraphCache {
+    struct Entry {
+        std::vector<uint8_t> key;
+        cudaGraphExec_t exec = nullptr;
+        int64_t kernels = 0;
+        uint64_t last_use = 0;
+    };
+    std::vector<Entry> entries;
+    uint64_t tick = 0;
+    ~GraphCache()
+    {
+        for (Entry &e : entries)
+            if (e.exec) cudaGraphExecDestroy(e.exec);
+    }
+};
+template <class F>
+inline int run_captured(GraphCache &gc, const void *key, size_t keylen, cudaStream_t s, F &&enqueue)
+{
+    gc.tick += 1;
+    for (GraphCache::Entry &e : gc.entries)
+        if (e.key.size() == keylen && memcmp(e.key.data(), key, keylen) == 0) {
+            e.last_use = gc.tick;
+            LF_CUDA(cudaGraphLaunch(e.exec, s));
+            lf::count_launch(e.kernels);
+            return LF_OK;
+        }
+    const int64_t before = lf_launch_count(0);
+    LF_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc != LF_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != LF_OK) return rc;
+        lf::set_error("CUDA graph capture failed: %s", cudaGetErrorString(ce));
+        cudaGetLastError();
+        return LF_ERR_CUDA;
+    }
+    GraphCache::Entry e;
+    e.key.assign((const uint8_t *)key, (const uint8_t *)key + keylen);
+    e.kernels = lf_launch_count(0) - before;
+    e.last_use = gc.tick;
+    ce = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+        lf::set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+        return LF_ERR_CUDA;
+    }
+    if (gc.entries.size() >= 4) {   // drop the least recently used variant
+        size_t old = 0;
+        for (size_t k = 1; k < gc.entries.size(); ++k)
+            if (gc.entries[k].last_use < gc.entries[old].last_use) old = k;
+        cudaGraphExecDestroy(gc.entries[old].exec);
+        gc.entries.erase(gc.entries.begin() + old);
+    }
+    LF_CUDA(cudaGraphLaunch(e.exec, s));
+    gc.entries.push_back(e);
+    return LF_OK;
+}
 
 }  // namespace lf
 

@@ -48,6 +48,7 @@ struct lf_router {
     double *imp = nullptr;
     long long imp_parity_stride = 0;
     int32_t x_cap_steps = 0, n_export = 0, n_import = 0;
+    lf::GraphCache graphs;   // CUDA-graph replay of the diagonals of a run (one variant per argument set)
 };
 
 namespace {
@@ -177,27 +178,45 @@ int run_steps(lf_router *r, int sec, int nsteps, const double *d_scale)
         X.parity = parity;
         LF_CHECK(lf::xchg_view_base(r->xchg, &X.abort_flag));
     }
-    for (int d = 0; d < L + nsteps - 1; ++d) {
-        int lo_lev = d - nsteps + 1 > 0 ? d - nsteps + 1 : 0;
-        int hi_lev = d < L - 1 ? d : L - 1;
-        int lo = ls[lo_lev], hi = ls[hi_lev + 1];
-        if (hi <= lo) continue;
-        const bool hasx = r->xslot.p != nullptr;
-#define LF_KW_LAUNCH(QZ_, HX_)                                                                                        \
-    k_kw_diagonal<QZ_, HX_><<<lf::blocks_for(hi - lo, KW_THREADS), KW_THREADS, 0, st>>>(                              \
-        lo, hi, d, g0, g->lev_of_pos.p, g->cfirst.p, g->cend.p, r->a[sec].p, r->dx_is_array ? r->dx.p : nullptr,      \
-        r->dx_scalar,                                                                                                 \
-        r->q[sec].p, d_scale, r->Q[sec][0].p, r->Q[sec][1].p, r->P, X)
-        if (r->P.quintic) {
-            if (hasx) LF_KW_LAUNCH(true, true);
-            else LF_KW_LAUNCH(true, false);
-        } else {
-            if (hasx) LF_KW_LAUNCH(false, true);
-            else LF_KW_LAUNCH(false, false);
+    auto diagonals = [&]() -> int {
+        for (int d = 0; d < L + nsteps - 1; ++d) {
+            int lo_lev = d - nsteps + 1 > 0 ? d - nsteps + 1 : 0;
+            int hi_lev = d < L - 1 ? d : L - 1;
+            int lo = ls[lo_lev], hi = ls[hi_lev + 1];
+            if (hi <= lo) continue;
+            const bool hasx = r->xslot.p != nullptr;
+    #define LF_KW_LAUNCH(QZ_, HX_)                                                                                        \
+        k_kw_diagonal<QZ_, HX_><<<lf::blocks_for(hi - lo, KW_THREADS), KW_THREADS, 0, st>>>(                              \
+            lo, hi, d, g0, g->lev_of_pos.p, g->cfirst.p, g->cend.p, r->a[sec].p, r->dx_is_array ? r->dx.p : nullptr,      \
+            r->dx_scalar,                                                                                                 \
+            r->q[sec].p, d_scale, r->Q[sec][0].p, r->Q[sec][1].p, r->P, X)
+            if (r->P.quintic) {
+                if (hasx) LF_KW_LAUNCH(true, true);
+                else LF_KW_LAUNCH(true, false);
+            } else {
+                if (hasx) LF_KW_LAUNCH(false, true);
+                else LF_KW_LAUNCH(false, false);
+            }
+    #undef LF_KW_LAUNCH
+            LF_LAUNCH_CHECK();
         }
-#undef LF_KW_LAUNCH
-        LF_LAUNCH_CHECK();
-    }
+        return LF_OK;
+    };
+    // key of the captured graph: everything the launches depend on
+    struct Key {
+        int sec, nsteps, parity_in, x_parity;
+        const double *scale;
+        lfx::View X;
+    } key;
+    memset(&key, 0, sizeof(key));
+    key.sec = sec;
+    key.nsteps = nsteps;
+    key.parity_in = (int)(g0 & 1);
+    key.x_parity = X.parity;
+    key.scale = d_scale;
+    key.X = X;
+    if (L + nsteps > 8) LF_CHECK(lf::run_captured(r->graphs, &key, sizeof(key), st, diagonals));
+    else LF_CHECK(diagonals());
     r->steps_done[sec] = g0 + nsteps;
     if (r->xslot.p) LF_CHECK(lf_xchg_end(r->xchg));
     return LF_OK;

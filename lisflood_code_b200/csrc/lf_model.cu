@@ -720,70 +720,6 @@ __global__ void k_z2floor(const double *__restrict__ c2start, const double *__re
 }  // namespace
 
 
-// ---- CUDA-graph replay of launch-bound loops (the level sweep of the overland routers, the diagonals of the channel
-// wavefront: hundreds of small dependent launches per step).  A loop is captured once per distinct argument set (the
-// kernel arguments are part of the key: buffers that alternate between steps give two or four variants) and replayed
-// with one cudaGraphLaunch afterwards.
-struct GraphCache {
-    struct Entry {
-        std::vector<uint8_t> key;
-        cudaGraphExec_t exec = nullptr;
-        int64_t kernels = 0;
-        uint64_t last_use = 0;
-    };
-    std::vector<Entry> entries;
-    uint64_t tick = 0;
-    ~GraphCache()
-    {
-        for (Entry &e : entries)
-            if (e.exec) cudaGraphExecDestroy(e.exec);
-    }
-};
-template <class F>
-int run_captured(GraphCache &gc, const void *key, size_t keylen, cudaStream_t s, F &&enqueue)
-{
-    gc.tick += 1;
-    for (GraphCache::Entry &e : gc.entries)
-        if (e.key.size() == keylen && memcmp(e.key.data(), key, keylen) == 0) {
-            e.last_use = gc.tick;
-            LF_CUDA(cudaGraphLaunch(e.exec, s));
-            lf::count_launch(e.kernels);
-            return LF_OK;
-        }
-    const int64_t before = lf_launch_count(0);
-    LF_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue();
-    cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(s, &graph);
-    if (rc != LF_OK || ce != cudaSuccess || !graph) {
-        if (graph) cudaGraphDestroy(graph);
-        if (rc != LF_OK) return rc;
-        lf::set_error("CUDA graph capture failed: %s", cudaGetErrorString(ce));
-        cudaGetLastError();
-        return LF_ERR_CUDA;
-    }
-    GraphCache::Entry e;
-    e.key.assign((const uint8_t *)key, (const uint8_t *)key + keylen);
-    e.kernels = lf_launch_count(0) - before;
-    e.last_use = gc.tick;
-    ce = cudaGraphInstantiate(&e.exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) {
-        lf::set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
-        return LF_ERR_CUDA;
-    }
-    if (gc.entries.size() >= 4) {   // drop the least recently used variant
-        size_t old = 0;
-        for (size_t k = 1; k < gc.entries.size(); ++k)
-            if (gc.entries[k].last_use < gc.entries[old].last_use) old = k;
-        cudaGraphExecDestroy(gc.entries[old].exec);
-        gc.entries.erase(gc.entries.begin() + old);
-    }
-    LF_CUDA(cudaGraphLaunch(e.exec, s));
-    gc.entries.push_back(e);
-    return LF_OK;
-}
-
 struct lf_model {
     lf_model_config cfg;
     int64_t n = 0;
@@ -841,7 +777,7 @@ struct lf_model {
         std::map<std::string, std::unique_ptr<lf::DevBuf<double>>> v;   // per-structure parameter / state arrays
         bool cq_dirty = true;
     } st;
-    GraphCache graphs_of, graphs_ch;
+    lf::GraphCache graphs_of, graphs_ch;
     int use_graphs = 1;                   // option "cuda_graphs"
     int accumulate_discharge = 0;         // option "accumulate_discharge" (InitLisflood / repAverageDis)
     int overlap_isolated = 1;             // option "overlap_isolated"
@@ -1388,7 +1324,7 @@ int surface_stage(lf_model *m)
         }
         return LF_OK;
     };
-    if (m->use_graphs && g->n_orders > 4) LF_CHECK(run_captured(m->graphs_of, &O, sizeof(O), st, sweep));
+    if (m->use_graphs && g->n_orders > 4) LF_CHECK(lf::run_captured(m->graphs_of, &O, sizeof(O), st, sweep));
     else LF_CHECK(sweep());
     // swap: the named maps must hold the new discharge
     for (int r = 0; r < 3; ++r) {
@@ -1661,7 +1597,7 @@ int channel_stage(lf_model *m)
         }
         return LF_OK;
     };
-    if (m->use_graphs && Lc + S > 6) LF_CHECK(run_captured(m->graphs_ch, &C, sizeof(C), sw, wavefront));
+    if (m->use_graphs && Lc + S > 6) LF_CHECK(lf::run_captured(m->graphs_ch, &C, sizeof(C), sw, wavefront));
     else LF_CHECK(wavefront());
     LF_CUDA(cudaEventRecord(m->ev_join, sw));
     LF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));

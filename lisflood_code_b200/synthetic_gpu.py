@@ -12,7 +12,7 @@ import math
 import numpy as np
 
 
-def _ldd_gpu(torch, rows, cols, seed, noise, tilt=1.0, device="cuda"):
+def _ldd_gpu(torch, rows, cols, seed, noise, tilt=1.0, device="cuda", single_outlet=False):
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     elev = torch.randn((rows, cols), generator=g, device=device, dtype=torch.float32) * noise
@@ -32,6 +32,13 @@ def _ldd_gpu(torch, rows, cols, seed, noise, tilt=1.0, device="cuda"):
         code = torch.where(better, torch.full_like(code, float(k)), code)
         del nb, drop, better
     del pad, elev, best
+    if single_outlet:
+        # one big basin (synthetic.random_ldd): the south edge becomes a collector draining to its centre cell, the only
+        # outlet of everything that reaches the edge; interior sinks remain separate small catchments
+        c0 = cols // 2
+        code[rows - 1, :c0] = 6.0
+        code[rows - 1, c0 + 1:] = 4.0
+        code[rows - 1, c0] = 5.0
     return code.reshape(-1)
 
 
@@ -44,7 +51,7 @@ def _host_accuflux_ones(ldd, rows, cols):
 
 
 def c3_generate(torch, rows, cols, seed, emit, ldd_noise=0.5, channel_threshold=60, no_rout_steps=24, dt_sec=86400.0,
-                diagnostics=False, accuflux=None, device="cuda"):
+                diagnostics=False, accuflux=None, device="cuda", single_outlet=False):
     """The C3 generator: every map of the catchment, one after the other, handed to `emit(kind, name, value)`.
 
     kind "config": value = dict of the scalars + the mask / LddToChan / LddKinematic tensors (first call);
@@ -56,7 +63,7 @@ def c3_generate(torch, rows, cols, seed, emit, ldd_noise=0.5, channel_threshold=
     g = torch.Generator(device=device)
     g.manual_seed(seed + 4242)
     U = lambda lo, hi, shape=(n,): torch.rand(shape, generator=g, device=device, dtype=torch.float64) * (hi - lo) + lo
-    ldd = _ldd_gpu(torch, rows, cols, seed, ldd_noise, device=device)
+    ldd = _ldd_gpu(torch, rows, cols, seed, ldd_noise, device=device, single_outlet=single_outlet)
     mask = torch.ones(n, dtype=torch.uint8, device=device)
     if accuflux is None:
         uparea = torch.from_numpy(_host_accuflux_ones(ldd.cpu().numpy(), rows, cols)).to(device)
@@ -235,7 +242,7 @@ class C3Device(object):
     on a crop-sized raster)."""
 
     def __init__(self, rows, cols, seed=0, ldd_noise=0.5, channel_threshold=60, no_rout_steps=24, dt_sec=86400.0,
-                 diagnostics=False, keep_host=False, distributed=False):
+                 diagnostics=False, keep_host=False, distributed=False, single_outlet=False):
         import torch
         from . import _capi
         from .hotpath import HotPathModel
@@ -295,7 +302,7 @@ class C3Device(object):
 
         self.gen = c3_generate(torch, rows, cols, seed, emit, ldd_noise=ldd_noise, channel_threshold=channel_threshold,
                                no_rout_steps=no_rout_steps, dt_sec=dt_sec, diagnostics=diagnostics or keep_host,
-                               accuflux=accuflux)
+                               accuflux=accuflux, single_outlet=single_outlet)
         self.n_local = self.model.n_local if self.distributed else n
         torch.cuda.empty_cache()
 
