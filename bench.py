@@ -740,7 +740,7 @@ def run_c5(args):
     else:
         ms_nograph, aborted = results[0][0], None
     if rank == 0:
-        cfg = {"workload": "C5 EFAS-like synthetic 1000x950 raster with 45 % sea, 6-hourly steps, feeder modules + soil + overland + "
+        cfg = {"workload": "C5 EFAS-like synthetic 1000x950 raster with 45 %% sea, 6-hourly steps, feeder modules + soil + overland + "
                            "6 routing sub-steps, split routing, 40 reservoirs + 20 lakes in the sub-step loop%s"
                            % ("; ONE raster cut over %d GPUs" % world if use_dist else ""),
                "cells": n, "cells_per_gpu": nl, "levels_overland": info["levels_overland"], "levels_channel": info["levels_channel"]}

@@ -732,6 +732,7 @@ struct lf_model {
     lf::DevBuf<int32_t> soil_to_chan;
     lf::DevBuf<int> flag;
     lf::DevBuf<int32_t> soil_list, soil_list_cnt;  // deferred soil columns (lf_soil_kernel.cuh)
+    lf::DevBuf<double> soil_side;                  // their dense side records (lean build)
     int32_t soil_list_cap = 0;
     // asynchronous input path (lf_model_set_async): H2D on a copy stream into a per-map staging buffer, layout
     // translation on the compute stream once the copy has landed
@@ -1038,15 +1039,23 @@ int soil_stage(lf_model *m)
         if (!m->soil_list.p) {
             // capacity per bucket: a quarter of the columns (typically ~6 % of all columns are deferred in total);
             // a full list degrades gracefully: the column is integrated by k_soil_pixel_flagged
-            m->soil_list_cap = (int32_t)std::max<int64_t>(1024, (3 * m->n) / 4);
+            // capacity per bucket: 3/4 of the columns with diagnostics; an eighth in the lean build, whose queued columns
+            // also get a dense side record (1-2 % of the columns are deferred after spin-up, ~6 % from a cold start)
+            const bool side = !m->cfg.diagnostics && !(getenv("LF_SOIL_SIDE") && atoi(getenv("LF_SOIL_SIDE")) == 0);
+            m->soil_list_cap = (int32_t)std::max<int64_t>(1024, side ? m->n / 8 : (3 * m->n) / 4);
             if (const char *e = getenv("LF_SOIL_LIST_CAP")) m->soil_list_cap = std::max(1, atoi(e));  // tests: force the overflow path
             LF_CHECK(m->soil_list.alloc((size_t)lfsoil::NBUCKET * m->soil_list_cap));
             LF_CHECK(m->soil_list_cnt.alloc(lfsoil::NBUCKET));
             m->bytes += (int64_t)lfsoil::NBUCKET * m->soil_list_cap * 4;
+            if (side) {
+                LF_CHECK(m->soil_side.alloc((size_t)lfsoil::NBUCKET * lfsoil::NSIDE * m->soil_list_cap));
+                m->bytes += (int64_t)lfsoil::NBUCKET * lfsoil::NSIDE * m->soil_list_cap * 8;
+            }
         }
         P.list = m->soil_list.p;
         P.list_cnt = m->soil_list_cnt.p;
         P.list_cap = m->soil_list_cap;
+        P.side = m->soil_side.p;
         LF_CUDA(cudaMemsetAsync(m->soil_list_cnt.p, 0, lfsoil::NBUCKET * sizeof(int32_t), st));
     }
     auto tick = [&](int k) {
@@ -1110,7 +1119,9 @@ int soil_stage(lf_model *m)
     do {                                                                                              \
         LF_LAUNCH_CHECK();                                                                            \
         tick(1);                                                                                      \
-        if (MBD == 8 && def_mb == 6)                                                                  \
+        if (!DG && P.side)                                                                            \
+            k_soil_veg_deferred<false, 6, true><<<grid_def6, lfsoil::SOIL_THREADS, 0, st>>>(P, D);    \
+        else if (MBD == 8 && def_mb == 6)                                                             \
             k_soil_veg_deferred<DG, 6><<<grid_def6, lfsoil::SOIL_THREADS, 0, st>>>(P, D);             \
         else                                                                                          \
             k_soil_veg_deferred<DG, MBD><<<grid_def, lfsoil::SOIL_THREADS, 0, st>>>(P, D);            \

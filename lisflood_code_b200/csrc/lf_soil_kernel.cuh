@@ -81,6 +81,11 @@ struct Ptrs {
     int32_t *list;      // [6 * list_cap]
     int32_t *list_cnt;  // [6]
     int32_t list_cap;
+    // Dense side records of the queued columns (lean build; nullptr = resume from the scattered mid-column record): the
+    // first pass has every input of the resumed half in registers / shared memory and writes it, lane-consecutive, to
+    // side[(bucket * NSIDE + field) * list_cap + slot]; k_soil_veg_deferred then reads coalesced records instead of
+    // gathering 23 values per column from 23 maps (one 32-64 byte DRAM sector each for 8 useful bytes).
+    double *side;
     // scalars
     double DtDay, InvDtDay, AvWaterThreshold, CourantCrit, DrainedFraction, LeafDrainageK, SMaxSealed, TimeSinceStart;
 };
@@ -224,6 +229,8 @@ __device__ __forceinline__ int bucket_of(int nsub)
 }
 
 enum ColumnResult { COL_DONE = 0, COL_QUEUED = 1 };
+enum SideField { SF_W1A, SF_W1B, SF_W2, SF_AVAIL, SF_INFIL, SF_PREF, SF_WRES1A, SF_WRES1B, SF_WRES2, SF_WS1A, SF_WS1B, SF_WS2,
+                 SF_KS1A, SF_KS1B, SF_KS2, SF_IM1A, SF_IM1B, SF_IM2, SF_FRAC, SF_UZ, SF_UZK, SF_GWPERC, SF_FROZEN, NSIDE };
 
 // flags of a pixel in pix_deferred: bit 0 = the per-pixel part is left to k_soil_pixel_flagged (a column of the pixel was
 // queued, or diagnostics are on); bits 1..3 = column v found its bucket list full (never seen in practice: each list holds
@@ -446,6 +453,7 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
     const bool defer = nsub > 1;
     if (__ballot_sync(act, defer)) {
         const int b = defer ? bucket_of(nsub) : -1;
+        int my_slot = -1;
 #pragma unroll
         for (int bb = 0; bb < NBUCKET; ++bb) {
             const unsigned mk = __ballot_sync(act, b == bb);
@@ -460,10 +468,39 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
                 if (slot < P.list_cap) {
                     P.list[(int64_t)bb * P.list_cap + slot] = (int32_t)k;
                     atomicOr(flags, PIX_FLAGGED);
+                    my_slot = slot;
                 } else {
                     atomicOr(flags, PIX_FLAGGED | pix_overflow_bit(v));  // list full: left to k_soil_pixel_flagged
                 }
             }
+        }
+        if (!DIAG && defer && my_slot >= 0 && P.side) {  // dense side record: everything the resumed half reads
+            double *sr = P.side + ((int64_t)b * NSIDE) * P.list_cap + my_slot;
+            const int64_t st = P.list_cap;
+            sr[SF_W1A * st] = w1a;
+            sr[SF_W1B * st] = w1b;
+            sr[SF_W2 * st] = w2;
+            sr[SF_AVAIL * st] = avail;
+            sr[SF_INFIL * st] = infil;
+            sr[SF_PREF * st] = prefflow;
+            sr[SF_WRES1A * st] = wres1a;
+            sr[SF_WRES1B * st] = wres1b;
+            sr[SF_WRES2 * st] = wres2;
+            sr[SF_WS1A * st] = ws1a;
+            sr[SF_WS1B * st] = ws1b;
+            sr[SF_WS2 * st] = ws2;
+            sr[SF_KS1A * st] = ks1a;
+            sr[SF_KS1B * st] = ks1b;
+            sr[SF_KS2 * st] = ks2;
+            sr[SF_IM1A * st] = im1a;
+            sr[SF_IM1B * st] = im1b;
+            sr[SF_IM2 * st] = im2;
+            sr[SF_FRAC * st] = frac;
+            sr[SF_UZ * st] = in.UZ();
+            sr[SF_UZK * st] = in.UZK();
+            sr[SF_GWPERC * st] = in.GwPercStep();
+            sr[SF_FROZEN * st] = frozen ? 1.0 : 0.0;
+            return COL_QUEUED;
         }
         if (defer) {  // mid-column record
             P.W1a[k] = w1a;
@@ -491,21 +528,15 @@ __device__ __forceinline__ ColumnResult soil_column(const Ptrs &P, const Diag &D
     return COL_DONE;
 }
 
-// ---- a queued column, resumed from its mid-column record: adaptive Darcy sub-steps (soilloop.py:237-312), then the
-// second half.  Writes the state and the remaining contributions (CS_UZOUT, CS_GWPERC, CS_SURF(, CS_INF)) over the record. ----
+// the Darcy sub-steps of a resumed column and its second half (shared by the two resume feeds below)
 template <bool DIAG>
-__device__ __forceinline__ void soil_column_resume(const Ptrs &P, const Diag &D, const MathTab *MT, int v, int i)
+__device__ __forceinline__ void resume_core(const Ptrs &P, const Diag &D, const MathTab *MT, int v, int i, int64_t k, bool frozen,
+                                            double w1a, double w1b, double w2, double avail, double infil, double prefflow,
+                                            double wres1a, double wres1b, double wres2, double ws1a, double ws1b, double ws2,
+                                            double ks1a, double ks1b, double ks2, double im1a, double im1b, double im2,
+                                            double frac, double uz, double uzk, double gwpercstep)
 {
-    const int64_t k = (int64_t)v * P.n + i;
-    const bool frozen = P.frozen[i] != 0;
-    const double w1a = P.W1a[k], w1b = P.W1b[k], w2 = P.W2[k];
     double *rec = crec(P, v, i);
-    const double avail = rec[CS_SURF], infil = rec[CS_UZOUT], prefflow = rec[CS_GWPERC];
-    const double wres1a = P.WRes1a[v][i], wres1b = P.WRes1b[v][i], wres2 = P.WRes2[v][i];
-    const double ws1a = P.WS1a[v][i], ws1b = P.WS1b[v][i], ws2 = P.WS2[v][i];
-    const double ks1a = P.KSat1a[v][i], ks1b = P.KSat1b[v][i], ks2 = P.KSat2[v][i];
-    const double im1a = P.InvM1a[v][i], im1b = P.InvM1b[v][i], im2 = P.InvM2[v][i];
-    const double frac = P.SoilFraction[k], uz = P.UZ[k], uzk = P.UZK[i], gwpercstep = P.GwPercStep[i];
     const bool pore1a = ws1a != 0, pore1b = ws1b != 0, pore2 = ws2 != 0;
     const double m1a = div_nr(1.0, im1a), m1b = div_nr(1.0, im1b), m2 = div_nr(1.0, im2);  // GenuM
     double k1a = unsat_k(w1a, pore1a, wres1a, ws1a, ks1a, im1a, m1a, MT);
@@ -543,6 +574,35 @@ __device__ __forceinline__ void soil_column_resume(const Ptrs &P, const Diag &D,
     rec[CS_GWPERC] = C.gwperc;
     rec[CS_SURF] = C.surf;
     if (DIAG) rec[CS_INF] = C.inf;
+}
+
+// a queued column resumed from its dense side record (bucket b, slot): coalesced reads
+template <bool DIAG>
+__device__ __forceinline__ void soil_column_resume_side(const Ptrs &P, const Diag &D, const MathTab *MT, int b, int64_t slot,
+                                                        int64_t k)
+{
+    const int v = k >= 2 * P.n ? 2 : (k >= P.n ? 1 : 0);
+    const int i = (int)(k - (int64_t)v * P.n);
+    const double *sr = P.side + ((int64_t)b * NSIDE) * P.list_cap + slot;
+    const int64_t st = P.list_cap;
+    resume_core<DIAG>(P, D, MT, v, i, k, sr[SF_FROZEN * st] != 0.0, sr[SF_W1A * st], sr[SF_W1B * st], sr[SF_W2 * st],
+                      sr[SF_AVAIL * st], sr[SF_INFIL * st], sr[SF_PREF * st], sr[SF_WRES1A * st], sr[SF_WRES1B * st],
+                      sr[SF_WRES2 * st], sr[SF_WS1A * st], sr[SF_WS1B * st], sr[SF_WS2 * st], sr[SF_KS1A * st], sr[SF_KS1B * st],
+                      sr[SF_KS2 * st], sr[SF_IM1A * st], sr[SF_IM1B * st], sr[SF_IM2 * st], sr[SF_FRAC * st], sr[SF_UZ * st],
+                      sr[SF_UZK * st], sr[SF_GWPERC * st]);
+}
+
+// ---- a queued column, resumed from its mid-column record: adaptive Darcy sub-steps (soilloop.py:237-312), then the
+// second half.  Writes the state and the remaining contributions (CS_UZOUT, CS_GWPERC, CS_SURF(, CS_INF)) over the record. ----
+template <bool DIAG>
+__device__ __forceinline__ void soil_column_resume(const Ptrs &P, const Diag &D, const MathTab *MT, int v, int i)
+{
+    const int64_t k = (int64_t)v * P.n + i;
+    const double *rec = crec(P, v, i);
+    resume_core<DIAG>(P, D, MT, v, i, k, P.frozen[i] != 0, P.W1a[k], P.W1b[k], P.W2[k], rec[CS_SURF], rec[CS_UZOUT],
+                      rec[CS_GWPERC], P.WRes1a[v][i], P.WRes1b[v][i], P.WRes2[v][i], P.WS1a[v][i], P.WS1b[v][i], P.WS2[v][i],
+                      P.KSat1a[v][i], P.KSat1b[v][i], P.KSat2[v][i], P.InvM1a[v][i], P.InvM1b[v][i], P.InvM2[v][i],
+                      P.SoilFraction[k], P.UZ[k], P.UZK[i], P.GwPercStep[i]);
 }
 
 template <bool DIAG>
@@ -710,7 +770,7 @@ constexpr int SOIL_THREADS = 128;
 // six lists, LONGEST sub-step counts first, so the few columns with 64+ sub-steps start at once and the many short ones
 // fill in behind them, and lanes of a warp stay within one bucket (trip counts within 2x).  Replaces six launches whose
 // grids had to cover the list capacity (millions of empty blocks) and whose small tails ran one after the other.
-template <bool DIAG, int MINB>
+template <bool DIAG, int MINB, bool SIDE = false>
 __global__ void __launch_bounds__(SOIL_THREADS, MINB) k_soil_veg_deferred(const __grid_constant__ Ptrs P, const __grid_constant__ Diag D)
 {
     __shared__ MathTab s_tab;
@@ -733,8 +793,12 @@ __global__ void __launch_bounds__(SOIL_THREADS, MINB) k_soil_veg_deferred(const 
                 first = end[t];
             }
         const int64_t k = P.list[(int64_t)(NBUCKET - 1 - q) * P.list_cap + (j - first)];
-        const int v = k >= 2 * P.n ? 2 : (k >= P.n ? 1 : 0);
-        soil_column_resume<DIAG>(P, D, &s_tab, v, (int)(k - (int64_t)v * P.n));
+        if (SIDE) {
+            soil_column_resume_side<DIAG>(P, D, &s_tab, NBUCKET - 1 - q, j - first, k);
+        } else {
+            const int v = k >= 2 * P.n ? 2 : (k >= P.n ? 1 : 0);
+            soil_column_resume<DIAG>(P, D, &s_tab, v, (int)(k - (int64_t)v * P.n));
+        }
     }
 }
 
