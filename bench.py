@@ -368,7 +368,7 @@ def run_c3(args):
     dominant = "soil_ms" if soil_ms >= ch_ms else "channel_ms"
     traffic = None   # measured DRAM bytes of the soil stage per step from the committed ncu capture (same raster size only)
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_soil_stage_c3_traffic.json")) as f:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_soil_stage_c3_traffic.json")) as f:
             tj = json.load(f)
         if int(tj["cells"]) == int(nl):
             traffic = int(tj["soil_stage_bytes"])
@@ -379,6 +379,20 @@ def run_c3(args):
                  "unit": "GB/s", "frac": round(soil_gbs / peak, 4), "traffic": traffic, "alg_bytes_per_cell": ALG_BYTES_SOIL,
                  "avg_launch_ms": round(soil_ms, 3)}
     fp64 = fp64_roofline(nl, info, ch_ms, clk.summary())
+    fp64_step = None      # FP64 warp instructions of the whole step (committed ncu counts, C3 size) against the pipe's peak
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_soil_stage_c3_traffic.json")) as f:
+            tj = json.load(f)
+        if int(tj["cells"]) == int(nl):
+            inst = float(tj["fp64_warp_inst_per_step"]["total"])
+            mhz = clk.summary().get("sm_mhz") or 1965.0
+            pk = 2.0 * 148 * mhz * 1e6
+            fp64_step = {"bound": "fp64", "achieved": round(inst / (ms / K * 1e-3) / 1e9, 1), "peak": round(pk / 1e9, 1),
+                         "unit": "G warp-inst/s (FP64 pipe)", "frac": round(inst / (ms / K * 1e-3) / pk, 4),
+                         "note": "whole step: the hot path is float64 Newton / van Genuchten arithmetic; at 100 % of the FP64 "
+                                 "pipe a step would take %.1f ms" % (inst / pk * 1e3)}
+    except (OSError, ValueError, KeyError):
+        pass
     roof_chan = {"bound": "hbm", "kernel": "k_chan_diagonal + k_chan_isolated_ws (24 fused channel sub-steps)",
                  "achieved": round(chan_gbs, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                  "frac": round(chan_gbs / peak, 4), "traffic": None,
@@ -424,7 +438,8 @@ def run_c3(args):
                                 "two host buffers; the timed region ends when the last map has landed); the 10-day LAI maps "
                                 "stay resident"},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
-                "roofline_stencil": roof_soil, "roofline_routing": roof_chan, "stage_ms_per_step": stage,
+                "roofline_stencil": roof_soil, "roofline_routing": roof_chan, "roofline_fp64_step": fp64_step,
+                "stage_ms_per_step": stage,
                 "soil_stats": soil_stats,
                 "cpu_baseline": cpu, "init_s": round(t_init, 2)}
     # multi-GPU default run: the same invocation also measures C4 (BASELINE.json configs[3]: 20000x20000 routing only, ONE

@@ -75,6 +75,7 @@ SIGNATURES = {
     "lf_xchg_destroy": (None, [_vp]),
     "lf_model_create_from_graphs": (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp)]),
     "lf_model_set_exchange": (C.c_int, [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32, _i64s]),
+    "lf_router_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "lf_router_destroy": (None, [_vp]),
     "lf_model_create": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "lf_model_info": (C.c_int, [_vp, C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s), C.POINTER(_i64s),

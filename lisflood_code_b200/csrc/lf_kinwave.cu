@@ -15,6 +15,8 @@
 
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "lf_common.cuh"
 #include "lf_kw_solve.cuh"
 #include "lf_xchg.cuh"
@@ -49,7 +51,10 @@ struct lf_router {
     long long imp_parity_stride = 0;
     int32_t x_cap_steps = 0, n_export = 0, n_import = 0;
     lf::GraphCache graphs;   // CUDA-graph replay of the diagonals of a run (one variant per argument set)
+    int use_graphs = 1, use_coop = 1;   // lf_router_set_option
 };
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -103,35 +108,37 @@ __global__ void k_nonfinite(const double *__restrict__ v, int64_t n, int *__rest
     if (i < n && !isfinite(v[i])) *flag = 1;
 }
 
-// One diagonal of the space-time wavefront.  Positions [lo, hi) = levels d-S+1..d.
-constexpr int KW_THREADS = 128;
+// One work item (position i, diagonal d) of the space-time wavefront.
+struct KwArgs {
+    int64_t g0;
+    const int32_t *lev, *cfirst, *cend;
+    const double *a, *dx, *q, *scale;
+    double dx_scalar;
+    double *Q0, *Q1;
+    lfkw::Params P;
+    lfx::View X;
+};
 template <bool QZ, bool HASX>
-__global__ void __launch_bounds__(KW_THREADS)
-    k_kw_diagonal(int lo, int hi, int d, int64_t g0, const int32_t *__restrict__ lev,
-                  const int32_t *__restrict__ cfirst, const int32_t *__restrict__ cend, const double *__restrict__ a,
-                  const double *__restrict__ dx, double dx_scalar, const double *__restrict__ q,
-                  const double *__restrict__ scale, double *Q0, double *Q1, lfkw::Params P, lfx::View X)
+__device__ __forceinline__ void kw_item(const KwArgs &A, int i, int d)
 {
-    int i = lo + blockIdx.x * KW_THREADS + threadIdx.x;
-    if (i >= hi) return;
-    int s = d - lev[i];
-    int64_t gs = g0 + s;  // global index of this routing step; parity selects the buffer
-    double *Qnew = (gs & 1) ? Q1 : Q0;
-    const double *Qold = (gs & 1) ? Q0 : Q1;
+    int s = d - A.lev[i];
+    int64_t gs = A.g0 + s;  // global index of this routing step; parity selects the buffer
+    double *Qnew = (gs & 1) ? A.Q1 : A.Q0;
+    const double *Qold = (gs & 1) ? A.Q0 : A.Q1;
     int xs = -1;
     if (HASX) {
-        xs = X.xslot[i];
+        xs = A.X.xslot[i];
         if (xs <= -2) {  // ghost: the owner's value of this step (router-native representation)
-            Qnew[i] = xs == lfx::INERT ? 0.0 : lfx::take(lfx::import_slot(X, -2 - xs, 0, s), X.abort_flag);
+            Qnew[i] = xs == lfx::INERT ? 0.0 : lfx::take(lfx::import_slot(A.X, -2 - xs, 0, s), A.X.abort_flag);
             return;
         }
     }
-    int c0 = cfirst[i], c1 = cend ? cend[i] : cfirst[i + 1];
+    int c0 = A.cfirst[i], c1 = A.cend ? A.cend[i] : A.cfirst[i + 1];
     double qo = Qold[i];
-    double qs = q[i];
-    if (scale) qs *= scale[s];
-    double lateral = qs * (dx ? dx[i] : dx_scalar);  // lateral_inflow = q * dx, kinematic_wave_parallel.py:163
-    double ai = a[i];
+    double qs = A.q[i];
+    if (A.scale) qs *= A.scale[s];
+    double lateral = qs * (A.dx ? A.dx[i] : A.dx_scalar);  // lateral_inflow = q * dx, kinematic_wave_parallel.py:163
+    double ai = A.a[i];
     double U = 0.0;
     double out;
     if (QZ) {
@@ -139,10 +146,39 @@ __global__ void __launch_bounds__(KW_THREADS)
         out = lfkw::solve_z(U, qo, lateral, ai);
     } else {
         for (int k = c0; k < c1; ++k) U += Qnew[k];  // upstream discharge of this step, slot order (tools:57-58)
-        out = lfkw::solve(U, qo, lateral, ai, P);
+        out = lfkw::solve(U, qo, lateral, ai, A.P);
     }
     Qnew[i] = out;
-    if (HASX && xs >= 0) lfx::push(lfx::export_slot(X, xs, 0, s), out);
+    if (HASX && xs >= 0) lfx::push(lfx::export_slot(A.X, xs, 0, s), out);
+}
+
+// One diagonal per launch.  Positions [lo, hi) = levels d-S+1..d.
+constexpr int KW_THREADS = 128;
+template <bool QZ, bool HASX>
+__global__ void __launch_bounds__(KW_THREADS) k_kw_diagonal(int lo, int hi, int d, KwArgs A)
+{
+    int i = lo + blockIdx.x * KW_THREADS + threadIdx.x;
+    if (i >= hi) return;
+    kw_item<QZ, HASX>(A, i, d);
+}
+
+// The whole run in ONE cooperative launch: a persistent grid (every block resident) walks the diagonals and meets at a
+// grid-wide barrier after each one.  On deep networks (tens of thousands of levels: C4) a diagonal is only a few
+// microseconds of work, less than the ~5 us a kernel boundary costs even inside a CUDA graph; the barrier costs ~1-2 us.
+constexpr int KW_COOP_THREADS = 256;
+template <bool QZ, bool HASX>
+__global__ void __launch_bounds__(KW_COOP_THREADS) k_kw_wavefront_coop(int nlev, int nsteps, const int32_t *__restrict__ level_start,
+                                                                        KwArgs A)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int stride = gridDim.x * KW_COOP_THREADS;
+    for (int d = 0; d < nlev + nsteps - 1; ++d) {
+        const int lo_lev = d - nsteps + 1 > 0 ? d - nsteps + 1 : 0;
+        const int hi_lev = d < nlev - 1 ? d : nlev - 1;
+        const int lo = level_start[lo_lev], hi = level_start[hi_lev + 1];
+        for (int i = lo + blockIdx.x * KW_COOP_THREADS + threadIdx.x; i < hi; i += stride) kw_item<QZ, HASX>(A, i, d);
+        grid.sync();
+    }
 }
 
 __global__ void k_i32_to_pos(const int32_t *__restrict__ src, int32_t *__restrict__ dst,
@@ -178,45 +214,74 @@ int run_steps(lf_router *r, int sec, int nsteps, const double *d_scale)
         X.parity = parity;
         LF_CHECK(lf::xchg_view_base(r->xchg, &X.abort_flag));
     }
+    KwArgs A;
+    memset(&A, 0, sizeof(A));
+    A.g0 = g0 & 1;   // only the parity matters to the kernels: equal arguments across runs keep the graph cache warm
+    A.lev = g->lev_of_pos.p;
+    A.cfirst = g->cfirst.p;
+    A.cend = g->cend.p;
+    A.a = r->a[sec].p;
+    A.dx = r->dx_is_array ? r->dx.p : nullptr;
+    A.q = r->q[sec].p;
+    A.scale = d_scale;
+    A.dx_scalar = r->dx_scalar;
+    A.Q0 = r->Q[sec][0].p;
+    A.Q1 = r->Q[sec][1].p;
+    A.P = r->P;
+    A.X = X;
+    const bool hasx = r->xslot.p != nullptr;
+    const int ndiag = L + nsteps - 1;
+    // deep network, little work per diagonal: one persistent cooperative launch with grid barriers
+    bool coop = r->use_coop && ndiag > 64 && (double)r->n * nsteps / ndiag < 4.0e6;
+    if (coop) {
+        void *fn = r->P.quintic ? (hasx ? (void *)k_kw_wavefront_coop<true, true> : (void *)k_kw_wavefront_coop<true, false>)
+                                : (hasx ? (void *)k_kw_wavefront_coop<false, true> : (void *)k_kw_wavefront_coop<false, false>);
+        int per_sm = 0;
+        LF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, KW_COOP_THREADS, 0));
+        if (per_sm < 1) {
+            coop = false;
+        } else {
+            const int64_t widest = (int64_t)r->n * nsteps / ndiag * 4 + KW_COOP_THREADS;   // blocks beyond the widest diagonals idle
+            const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)per_sm * lf::sm_count(),
+                                                                                 widest / KW_COOP_THREADS));
+            int nlev = L, ns = nsteps;
+            const int32_t *lsd = g->level_start.p;
+            void *args[] = {&nlev, &ns, &lsd, &A};
+            LF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(KW_COOP_THREADS), args, 0, st));
+            lf::count_launch();
+        }
+    }
     auto diagonals = [&]() -> int {
-        for (int d = 0; d < L + nsteps - 1; ++d) {
+        for (int d = 0; d < ndiag; ++d) {
             int lo_lev = d - nsteps + 1 > 0 ? d - nsteps + 1 : 0;
             int hi_lev = d < L - 1 ? d : L - 1;
             int lo = ls[lo_lev], hi = ls[hi_lev + 1];
             if (hi <= lo) continue;
-            const bool hasx = r->xslot.p != nullptr;
-    #define LF_KW_LAUNCH(QZ_, HX_)                                                                                        \
-        k_kw_diagonal<QZ_, HX_><<<lf::blocks_for(hi - lo, KW_THREADS), KW_THREADS, 0, st>>>(                              \
-            lo, hi, d, g0, g->lev_of_pos.p, g->cfirst.p, g->cend.p, r->a[sec].p, r->dx_is_array ? r->dx.p : nullptr,      \
-            r->dx_scalar,                                                                                                 \
-            r->q[sec].p, d_scale, r->Q[sec][0].p, r->Q[sec][1].p, r->P, X)
+            const unsigned gb = lf::blocks_for(hi - lo, KW_THREADS);
             if (r->P.quintic) {
-                if (hasx) LF_KW_LAUNCH(true, true);
-                else LF_KW_LAUNCH(true, false);
+                if (hasx) k_kw_diagonal<true, true><<<gb, KW_THREADS, 0, st>>>(lo, hi, d, A);
+                else k_kw_diagonal<true, false><<<gb, KW_THREADS, 0, st>>>(lo, hi, d, A);
             } else {
-                if (hasx) LF_KW_LAUNCH(false, true);
-                else LF_KW_LAUNCH(false, false);
+                if (hasx) k_kw_diagonal<false, true><<<gb, KW_THREADS, 0, st>>>(lo, hi, d, A);
+                else k_kw_diagonal<false, false><<<gb, KW_THREADS, 0, st>>>(lo, hi, d, A);
             }
-    #undef LF_KW_LAUNCH
             LF_LAUNCH_CHECK();
         }
         return LF_OK;
     };
-    // key of the captured graph: everything the launches depend on
-    struct Key {
-        int sec, nsteps, parity_in, x_parity;
-        const double *scale;
-        lfx::View X;
-    } key;
-    memset(&key, 0, sizeof(key));
-    key.sec = sec;
-    key.nsteps = nsteps;
-    key.parity_in = (int)(g0 & 1);
-    key.x_parity = X.parity;
-    key.scale = d_scale;
-    key.X = X;
-    if (L + nsteps > 8) LF_CHECK(lf::run_captured(r->graphs, &key, sizeof(key), st, diagonals));
-    else LF_CHECK(diagonals());
+    if (!coop) {
+        // key of the captured graph: everything the launches depend on
+        struct Key {
+            int sec, nsteps;
+            KwArgs A;
+        } key;
+        memset(&key, 0, sizeof(key));
+        key.sec = sec;
+        key.nsteps = nsteps;
+        key.A = A;
+        if (r->use_graphs && ndiag > 8) LF_CHECK(lf::run_captured(r->graphs, &key, sizeof(key), st, diagonals));
+        else LF_CHECK(diagonals());
+    }
     r->steps_done[sec] = g0 + nsteps;
     if (r->xslot.p) LF_CHECK(lf_xchg_end(r->xchg));
     return LF_OK;
@@ -469,6 +534,21 @@ int lf_router_set_exchange(lf_router *r, lf_xchg *x, const int32_t *xslot, int32
     r->x_cap_steps = cap_steps;
     r->n_export = n_export;
     r->n_import = n_import;
+    return LF_OK;
+}
+
+int lf_router_set_option(lf_router *r, const char *name, double value)
+{
+    if (!r || !name) {
+        lf::set_error("lf_router_set_option: null pointer");
+        return LF_ERR_INVALID;
+    }
+    if (strcmp(name, "cuda_graphs") == 0) r->use_graphs = value != 0;
+    else if (strcmp(name, "cooperative") == 0) r->use_coop = value != 0;
+    else {
+        lf::set_error("lf_router_set_option: unknown option '%s'", name);
+        return LF_ERR_INVALID;
+    }
     return LF_OK;
 }
 

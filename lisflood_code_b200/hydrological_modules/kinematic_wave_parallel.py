@@ -180,6 +180,10 @@ class kinematicWave:
                                               C.byref(bad)))
         self._warn(bad.value)
 
+    def set_option(self, name, value):
+        """Execution options of lf_router_set_option ("cooperative", "cuda_graphs")."""
+        _capi.check(_capi.lib().lf_router_set_option(self._router, name.encode(), float(value)))
+
     def get_discharge(self, section="main_channel", out=None):
         if out is None:
             out = np.empty(self.num_pixels, np.float64)
