@@ -119,9 +119,10 @@ int lf_router_set_inflow(lf_router *r, int section, const double *specific_later
  * host f64[nsteps]).  Same arithmetic per (pixel, step) as nsteps calls of lf_router_route. */
 int lf_router_run(lf_router *r, int section, int nsteps, const double *q_scale, int *nonfinite);
 /* LDD-cut domain decomposition: see the "Multi-GPU" block below (lf_xchg_*, lf_router_set_exchange). */
-/* Execution options of a router: "cooperative" 1 (default): a run over a deep network with little work per wavefront
- * diagonal is ONE persistent cooperative launch with a grid barrier per diagonal; "cuda_graphs" 1 (default): otherwise
- * the diagonals of a run are captured once and replayed as a CUDA graph; both 0: one plain launch per diagonal. */
+/* Execution options of a router: "cuda_graphs" 1 (default): the diagonals of a run are captured once and replayed as a
+ * CUDA graph; "cooperative" k > 0: a run over a deep network is ONE persistent cooperative launch (k resident blocks per
+ * SM) with a grid barrier per diagonal -- measured slower than graph replay on B200, off by default; both 0: one plain
+ * launch per diagonal. */
 int lf_router_set_option(lf_router *r, const char *name, double value);
 void lf_router_destroy(lf_router *r);
 

@@ -15,8 +15,6 @@
 
 #include <vector>
 
-#include <cooperative_groups.h>
-
 #include "lf_common.cuh"
 #include "lf_kw_solve.cuh"
 #include "lf_xchg.cuh"
@@ -51,10 +49,9 @@ struct lf_router {
     long long imp_parity_stride = 0;
     int32_t x_cap_steps = 0, n_export = 0, n_import = 0;
     lf::GraphCache graphs;   // CUDA-graph replay of the diagonals of a run (one variant per argument set)
-    int use_graphs = 1, use_coop = 1;   // lf_router_set_option
+    int use_graphs = 1, use_coop = 0;   // lf_router_set_option; the cooperative launch is off by default (measured slower)
+    lf::DevBuf<unsigned int> coop_counter;
 };
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -118,7 +115,9 @@ struct KwArgs {
     lfkw::Params P;
     lfx::View X;
 };
-template <bool QZ, bool HASX>
+// COOP: called from the persistent kernel, where values written by other SMs earlier in the SAME launch are read: the
+// discharge buffers are then loaded through L2 (ld.global.cg), never from a possibly stale L1 line.
+template <bool QZ, bool HASX, bool COOP = false>
 __device__ __forceinline__ void kw_item(const KwArgs &A, int i, int d)
 {
     int s = d - A.lev[i];
@@ -134,7 +133,7 @@ __device__ __forceinline__ void kw_item(const KwArgs &A, int i, int d)
         }
     }
     int c0 = A.cfirst[i], c1 = A.cend ? A.cend[i] : A.cfirst[i + 1];
-    double qo = Qold[i];
+    double qo = COOP ? __ldcg(Qold + i) : Qold[i];
     double qs = A.q[i];
     if (A.scale) qs *= A.scale[s];
     double lateral = qs * (A.dx ? A.dx[i] : A.dx_scalar);  // lateral_inflow = q * dx, kinematic_wave_parallel.py:163
@@ -142,14 +141,31 @@ __device__ __forceinline__ void kw_item(const KwArgs &A, int i, int d)
     double U = 0.0;
     double out;
     if (QZ) {
-        for (int k = c0; k < c1; ++k) U += lfkw::pow5(Qnew[k]);  // buffers hold z = Q^(1/5)
+        for (int k = c0; k < c1; ++k) U += lfkw::pow5(COOP ? __ldcg(Qnew + k) : Qnew[k]);  // buffers hold z = Q^(1/5)
         out = lfkw::solve_z(U, qo, lateral, ai);
     } else {
-        for (int k = c0; k < c1; ++k) U += Qnew[k];  // upstream discharge of this step, slot order (tools:57-58)
+        for (int k = c0; k < c1; ++k) U += COOP ? __ldcg(Qnew + k) : Qnew[k];  // upstream discharge of this step, slot order (tools:57-58)
         out = lfkw::solve(U, qo, lateral, ai, A.P);
     }
     Qnew[i] = out;
     if (HASX && xs >= 0) lfx::push(lfx::export_slot(A.X, xs, 0, s), out);
+}
+
+// Grid-wide barrier of a persistent kernel whose blocks are all resident (cooperative launch): a monotonically growing
+// arrival counter; barrier number k is passed when it reaches (k + 1) * gridDim.x.  One L2 atomic and a poll per block
+// (cooperative_groups' grid.sync() measured ~10 us per barrier here, more than a kernel boundary in a CUDA graph).
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                       // this block's stores are visible device-wide before it arrives
+        atomicAdd(counter, 1u);
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
 }
 
 // One diagonal per launch.  Positions [lo, hi) = levels d-S+1..d.
@@ -163,21 +179,25 @@ __global__ void __launch_bounds__(KW_THREADS) k_kw_diagonal(int lo, int hi, int 
 }
 
 // The whole run in ONE cooperative launch: a persistent grid (every block resident) walks the diagonals and meets at a
-// grid-wide barrier after each one.  On deep networks (tens of thousands of levels: C4) a diagonal is only a few
-// microseconds of work, less than the ~5 us a kernel boundary costs even inside a CUDA graph; the barrier costs ~1-2 us.
-constexpr int KW_COOP_THREADS = 256;
+// grid-wide barrier after each one.  Built for deep networks (tens of thousands of levels: a diagonal is only a few
+// microseconds of work) and MEASURED SLOWER than the CUDA-graph replay of one kernel per diagonal on B200 -- C2 deep
+// (2102 diagonals): graph replay 13.0 ms per 100 steps, this kernel 17.2 ms with the hand-written barrier below and
+// 23.3 ms with cooperative_groups' grid.sync() (profiles/r02_router_coop_sweep.txt) -- so it is an option
+// (lf_router_set_option("cooperative", blocks per SM)), off by default.
+constexpr int KW_COOP_THREADS = 1024;   // one fat block per SM: the grid barrier costs grow with the number of blocks
 template <bool QZ, bool HASX>
 __global__ void __launch_bounds__(KW_COOP_THREADS) k_kw_wavefront_coop(int nlev, int nsteps, const int32_t *__restrict__ level_start,
-                                                                        KwArgs A)
+                                                                        KwArgs A, unsigned int *counter)
 {
-    cg::grid_group grid = cg::this_grid();
     const int stride = gridDim.x * KW_COOP_THREADS;
+    unsigned int target = 0;
     for (int d = 0; d < nlev + nsteps - 1; ++d) {
         const int lo_lev = d - nsteps + 1 > 0 ? d - nsteps + 1 : 0;
         const int hi_lev = d < nlev - 1 ? d : nlev - 1;
         const int lo = level_start[lo_lev], hi = level_start[hi_lev + 1];
-        for (int i = lo + blockIdx.x * KW_COOP_THREADS + threadIdx.x; i < hi; i += stride) kw_item<QZ, HASX>(A, i, d);
-        grid.sync();
+        for (int i = lo + blockIdx.x * KW_COOP_THREADS + threadIdx.x; i < hi; i += stride) kw_item<QZ, HASX, true>(A, i, d);
+        target += gridDim.x;
+        grid_barrier(counter, target);
     }
 }
 
@@ -242,11 +262,14 @@ int run_steps(lf_router *r, int sec, int nsteps, const double *d_scale)
             coop = false;
         } else {
             const int64_t widest = (int64_t)r->n * nsteps / ndiag * 4 + KW_COOP_THREADS;   // blocks beyond the widest diagonals idle
-            const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)per_sm * lf::sm_count(),
+            const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)std::min(per_sm, r->use_coop) * lf::sm_count(),
                                                                                  widest / KW_COOP_THREADS));
             int nlev = L, ns = nsteps;
             const int32_t *lsd = g->level_start.p;
-            void *args[] = {&nlev, &ns, &lsd, &A};
+            if (!r->coop_counter.p) LF_CHECK(r->coop_counter.alloc(1));
+            LF_CUDA(cudaMemsetAsync(r->coop_counter.p, 0, sizeof(unsigned int), st));
+            unsigned int *ctr = r->coop_counter.p;
+            void *args[] = {&nlev, &ns, &lsd, &A, &ctr};
             LF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(KW_COOP_THREADS), args, 0, st));
             lf::count_launch();
         }
@@ -544,7 +567,7 @@ int lf_router_set_option(lf_router *r, const char *name, double value)
         return LF_ERR_INVALID;
     }
     if (strcmp(name, "cuda_graphs") == 0) r->use_graphs = value != 0;
-    else if (strcmp(name, "cooperative") == 0) r->use_coop = value != 0;
+    else if (strcmp(name, "cooperative") == 0) r->use_coop = (int)value;   // resident blocks per SM of the persistent grid, 0 = off
     else {
         lf::set_error("lf_router_set_option: unknown option '%s'", name);
         return LF_ERR_INVALID;

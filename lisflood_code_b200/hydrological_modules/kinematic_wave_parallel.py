@@ -62,6 +62,15 @@ class kinematicWave:
         _capi.check(L.lf_graph_info(g, C.byref(npix), C.byref(no), C.byref(k), C.byref(pits)))
         self.num_orders, self.max_upstream, self.num_pits = no.value, k.value, pits.value
         self._cache = {}
+        self._env_options()
+
+    def _env_options(self):
+        """Tuning runs: LF_ROUTER_COOP / LF_ROUTER_GRAPHS override the execution options of the router."""
+        import os
+        if os.environ.get("LF_ROUTER_COOP") is not None:
+            self.set_option("cooperative", float(os.environ["LF_ROUTER_COOP"]))
+        if os.environ.get("LF_ROUTER_GRAPHS") is not None:
+            self.set_option("cuda_graphs", float(os.environ["LF_ROUTER_GRAPHS"]))
 
     @classmethod
     def from_graph(cls, graph, num_pixels, alpha_channel, beta, space_delta, time_delta, alpha_floodplains=None,
@@ -92,6 +101,7 @@ class kinematicWave:
         _capi.check(L.lf_graph_info(graph, C.byref(npix), C.byref(no), C.byref(k), C.byref(pits)))
         self.num_orders, self.max_upstream, self.num_pits = no.value, k.value, pits.value
         self._cache = {}
+        self._env_options()
         return self
 
     def _as_map(self, v):

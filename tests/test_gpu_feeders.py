@@ -62,3 +62,39 @@ def test_feeders_scalar_parameters_and_lai(gpu_lib):
     M.set_lai(lai)
     assert rel_err(M.get("LAITerm", 3), lai_term(P["kgb"], lai)) < 1e-14
     assert np.array_equal(M.get("LAI", 3), lai)
+
+
+def test_dynamic_with_raw_forcing_equals_feed_and_step(gpu_lib):
+    """LisfloodModel_dyn.dynamic(raw=...) drives readmeteo / leafarea / snow / frost mirrors in the reference's order
+    (Lisflood_dynamic.py:79-105) and gives what feed() + step() give."""
+    from lisflood_code_b200 import synthetic
+    from lisflood_code_b200.hotpath import HotPathModel
+    from lisflood_code_b200.Lisflood_dynamic import LisfloodModel_dyn
+    S = synthetic.full_stack(50, 60, seed=31, mask_fraction=0.1)
+    n = S["N"]
+    rng = np.random.default_rng(8)
+    P = {"PrScaling": 1.0, "CalEvaporation": 1.0, "DeltaTSnow": rng.uniform(0, 2, n), "SnowSeason": 0.5, "TempSnow": 1.0,
+         "SnowFactor": 1.0, "SnowMeltCoef": 4.0, "TempMelt": 0.0, "lat_rad": np.full(n, 0.8), "Kfrost": 0.57, "Afrost": 0.97,
+         "FrostIndexThreshold": 56.0, "SnowWaterEquivalent": 0.45, "kgb": 0.75 * 0.72}
+    lai = {j: rng.uniform(0, 6, (3, n)) for j in range(36)}
+    A, B = HotPathModel(S), HotPathModel(S)
+    for M in (A, B):
+        M.set_feeder(P, {"SnowCoverS": np.zeros((3, n)), "FrostIndex": np.zeros(n)})
+    dyn = LisfloodModel_dyn(B)
+    from lisflood_code_b200.hydrological_modules.snow import lai_interval
+    last = None
+    for t, day in enumerate((9, 10, 11, 12)):       # day 11 starts a new LAI interval
+        raw = {"Precipitation": rng.gamma(0.8, 8.0, n).astype(np.float32), "Tavg": rng.uniform(-8, 20, n).astype(np.float32),
+               "ET0": rng.uniform(0, 6, n).astype(np.float32), "E0": rng.uniform(0, 6, n).astype(np.float32)}
+        j = lai_interval(day)
+        if j != last:
+            A.set_lai(lai[j])
+            last = j
+        A.feed(raw, day)
+        A.step()
+        dyn.dynamic(raw=raw, calendar_day=day, lai_of_interval=lambda k: lai[k])
+        for k in ("ChanQAvg", "W1a", "FrostIndex", "LAITerm"):
+            rows = 3 if k in ("W1a", "LAITerm") else 1
+            assert np.array_equal(A.get(k, rows), B.get(k, rows)), (t, k)
+    with pytest.raises(RuntimeError):
+        dyn.frost_module.dynamic()              # out of order: no snow.dynamic before it

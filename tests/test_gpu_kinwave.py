@@ -187,3 +187,26 @@ def test_nancheck_warns_once(gpu_lib):
         kw.kinematicWaveRouting(Q, np.zeros(16))
         kw.kinematicWaveRouting(Q, np.zeros(16))
     assert len(w) == 1 and kw.kinematic_wave_warning_printed
+
+
+def test_routing_accepts_any_array_like_the_reference(gpu_lib):
+    """The reference mutates whatever array it is given (float32, strided views, NumpyModified): so does the mirror."""
+    from lisflood_code_b200.global_modules.add1 import NumpyModified
+    g = load_golden("kw_40x50_masked")
+    kw = _kw(gpu_lib)(g["ldd"], g["mask"], g["alpha"], float(g["beta"]), _dx(g), float(g["dt"]))
+    want = g["q0"].copy()
+    kw.kinematicWaveRouting(want, g["q"])
+    n = want.size
+    strided = np.zeros(2 * n)
+    strided[::2] = g["q0"]
+    view = strided[::2]                                   # non-contiguous float64
+    assert kw.kinematicWaveRouting(view, g["q"]) is None
+    assert np.array_equal(strided[::2], want) and np.all(strided[1::2] == 0)
+    q32 = g["q0"].astype(np.float32)                      # float32: routed in float64, stored back as float32
+    ref32 = q32.astype(np.float64)
+    kw.kinematicWaveRouting(ref32, g["q"])
+    kw.kinematicWaveRouting(q32, g["q"])
+    assert q32.dtype == np.float32 and np.array_equal(q32, ref32.astype(np.float32))
+    wrapped = NumpyModified(g["q0"].copy(), ["pixel"])
+    kw.kinematicWaveRouting(wrapped, g["q"])
+    assert np.array_equal(np.asarray(wrapped), want)
