@@ -389,7 +389,7 @@ def run_c3(args):
             pk = 2.0 * 148 * mhz * 1e6
             fp64_step = {"bound": "fp64", "achieved": round(inst / (ms / K * 1e-3) / 1e9, 1), "peak": round(pk / 1e9, 1),
                          "unit": "G warp-inst/s (FP64 pipe)", "frac": round(inst / (ms / K * 1e-3) / pk, 4),
-                         "note": "whole step: the hot path is float64 Newton / van Genuchten arithmetic; at 100 % of the FP64 "
+                         "note": "whole step: the hot path is float64 Newton / van Genuchten arithmetic; at 100 %% of the FP64 "
                                  "pipe a step would take %.1f ms" % (inst / pk * 1e3)}
     except (OSError, ValueError, KeyError):
         pass

@@ -157,3 +157,33 @@ def test_gloo_cut_network_is_bit_identical(tmp_path, world, oracle):
     for step in range(15):
         ora.kinematicWaveRouting(Q, q * rng.uniform(0.5, 1.5))
     assert np.array_equal(got, Q)
+
+
+def test_plan_with_two_graphs_marks_inert_ghosts():
+    """The full model cuts two graphs (LddToChan, LddKinematic) with ONE pixel set per rank: a ghost that has a link only in
+    one of them is inert in the other; import blocks of the two graphs follow each other inside a rank's region."""
+    from lisflood_code_b200 import synthetic
+    from lisflood_code_b200.parallel import INERT, CutPlan, cut_edges_numpy, partition_numpy
+    S = synthetic.full_stack(80, 70, seed=3, ldd_noise=0.4, mask_fraction=0.1)
+    world = 3
+    owner = partition_numpy(S["Ldd"], S["mask"], world, subtree_fraction=0.02)
+    graphs = {}
+    for name, ldd, nsec, cap in (("overland", S["LddToChan"], 3, 1), ("channel", S["LddKinematic"], 1, 24)):
+        eu, ed = cut_edges_numpy(ldd, S["mask"], owner)
+        graphs[name] = (eu, ed, owner[eu], owner[ed], nsec, cap)
+    plan = CutPlan(graphs, world, order=("overland", "channel"))
+    assert graphs["overland"][0].size > 0 and graphs["channel"][0].size > 0
+    for r in range(world):
+        keep = owner == r
+        keep[plan.ghosts[r]] = True
+        loc = np.flatnonzero(keep)
+        xo, xc = plan.xslot("overland", r, loc), plan.xslot("channel", r, loc)
+        ghost = ~(owner[loc] == r)
+        assert np.all((xo[ghost] <= -2)) and np.all(xc[ghost] <= -2)            # ghosts are never solved, in either graph
+        assert np.all(xo[~ghost] >= -1) and np.all(xc[~ghost] >= -1)
+        live_o, live_c = (xo <= -2) & (xo != INERT), (xc <= -2) & (xc != INERT)
+        assert np.all(live_o | live_c == ghost)                                  # every ghost has a link in at least one graph
+        assert (xo == INERT).sum() == ghost.sum() - live_o.sum()
+        Po, Pc = plan.rank_plan("overland", r), plan.rank_plan("channel", r)
+        assert Po.import_offset == 0 and Pc.import_offset == 2 * Po.n_import * 3 * 1
+        assert plan.region_doubles[r] == Pc.import_offset + 2 * Pc.n_import * 1 * 24
