@@ -95,6 +95,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa(index):
+    """Pins this process to the CPU cores NVML reports as local to GPU `index`, so that page-locked host buffers are
+    allocated (first touch) on the NUMA node the GPU's PCIe root hangs off: with 8 ranks streaming forcing in and discharge
+    out, cross-socket traffic otherwise caps the aggregate host bandwidth.  Best effort; returns the core count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cores = [64 * w + b for w, bits in enumerate(words) for b in range(64) if (bits >> b) & 1]
+        if cores:
+            os.sched_setaffinity(0, cores)
+            return len(cores)
+    except Exception:
+        pass
+    return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -238,6 +256,7 @@ def run_c3(args):
     from lisflood_code_b200 import _capi
     from lisflood_code_b200.synthetic_gpu import C3Device
     L = _capi.lib()
+    numa_cores = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     _capi.check(L.lf_device_init(local))
     use_dist = world > 1
@@ -253,6 +272,8 @@ def run_c3(args):
     if os.environ.get("LF_EARLY_BPS"):      # tuning runs: resident blocks per SM of the early isolated-pixel launch
         M.set_option("early_blocks_per_sm", int(os.environ["LF_EARLY_BPS"]))
     M.set_option("overlap_isolated", 1 if args.overlap else 0)
+    if os.environ.get("LF_ISO_BPS") is not None:     # tuning runs: footprint of the isolated-pixel kernel
+        M.set_option("isolated_blocks_per_sm", int(os.environ["LF_ISO_BPS"]))
     _capi.synchronize()
     t_init = time.time() - t0
     info = M.info()
@@ -416,6 +437,7 @@ def run_c3(args):
                   "l2_policy": "every map is %.0f MB per GPU (> 126 MB L2 for more than ~1.6e7 cells per GPU); two raw forcing "
                                "sets alternate between steps, the 10-day LAI maps stay resident" % (nl * 8 / 1e6),
                   "spinup_steps": args.spinup, "co_scheduled_isolated_pixels": bool(args.overlap),
+                  "host_cores_bound_to_gpu_numa_node": numa_cores,
                   "drainage": "one basin (south-edge collector)" if args.basin == "single" else
                               "many catchments (steepest descent on tilted noise, every local sink is an outlet)"}
         if cut:
@@ -514,6 +536,10 @@ def _c3_oracle(args, rows=None):
 
 
 def cpu_baseline_c3(args):
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))     # the CPU leg may use every host core again
+    except Exception:
+        pass
     S, O, synthetic, lisf_oracle = _c3_oracle(args)
     cores = os.cpu_count() or 1
     best = None

@@ -783,6 +783,7 @@ struct lf_model {
     int accumulate_discharge = 0;         // option "accumulate_discharge" (InitLisflood / repAverageDis)
     int overlap_isolated = 1;             // option "overlap_isolated"
     int early_blocks_per_sm = 2;          // option "early_blocks_per_sm"
+    int iso_blocks_per_sm = 8;            // option "isolated_blocks_per_sm" (0: one block per chunk)
     int nancheck = 0;                     // option "flagnancheck"
     std::map<std::string, std::unique_ptr<lf::DevBuf<double>>> async_stage;
     std::map<std::string, cudaEvent_t> async_copied, async_consumed;
@@ -1506,8 +1507,14 @@ int chan_streams(lf_model *m)
     LF_CUDA(cudaMemsetAsync(m->iso_next.p, 0, 4 * sizeof(int), lf::stream()));
     // Kernels share an SM only if they agree on its L1 / shared-memory split: the soil stage asks for the maximum
     // shared-memory carve-out, so the kernels meant to run beside it ask for the same (they use no L1-resident reuse)
-    LF_CUDA(cudaFuncSetAttribute(k_chan_isolated_ws<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    LF_CUDA(cudaFuncSetAttribute(k_chan_isolated_ws<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    const void *same_split[] = {(const void *)k_chan_isolated_ws<true>, (const void *)k_chan_isolated_ws<false>,
+                                (const void *)k_chan_diagonal<true, false, false>, (const void *)k_chan_diagonal<false, false, false>,
+                                (const void *)k_chan_diagonal<true, true, false>, (const void *)k_chan_diagonal<false, true, false>,
+                                (const void *)k_chan_diagonal<true, false, true>, (const void *)k_chan_diagonal<false, false, true>,
+                                (const void *)k_chan_diagonal<true, true, true>, (const void *)k_chan_diagonal<false, true, true>,
+                                (const void *)k_chan_isolated_list<true>, (const void *)k_chan_isolated_list<false>};
+    for (const void *fn : same_split)   // the wavefront on the side stream must be able to share SMs with the isolated-pixel kernel
+        LF_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return LF_OK;
 }
 
@@ -1567,9 +1574,12 @@ int channel_stage(lf_model *m)
     LF_CUDA(cudaEventRecord(m->ev_fork, st));
     LF_CUDA(cudaStreamWaitEvent(sw, m->ev_fork, 0));
     if (iso_hi > iso_lo) {
-        // second drain of the chunk queue: fills the machine (7 resident blocks per SM at 69 registers)
+        // second drain of the chunk queue.  iso_blocks_per_sm > 0: a persistent grid of that many blocks per SM (8 fill the
+        // register file: the wavefront on the side stream then only starts once the queue is drained); 0: one block per
+        // chunk, so resident slots turn over every few microseconds and the high-priority wavefront kernels slip in.
         const unsigned nchunks = lf::blocks_for(iso_hi - iso_lo, CH_THREADS);
-        const unsigned grid = std::min<unsigned>(nchunks, (unsigned)(lf::sm_count() * 8));
+        const unsigned grid = m->iso_blocks_per_sm > 0 ? std::min<unsigned>(nchunks, (unsigned)(lf::sm_count() * m->iso_blocks_per_sm))
+                                                       : nchunks;
         if (m->quintic) k_chan_isolated_ws<true><<<grid, CH_THREADS, 0, st>>>(C, iso_lo, iso_hi, m->iso_next.p);
         else k_chan_isolated_ws<false><<<grid, CH_THREADS, 0, st>>>(C, iso_lo, iso_hi, m->iso_next.p);
         LF_LAUNCH_CHECK();
@@ -2401,6 +2411,7 @@ int lf_model_set_option(lf_model *m, const char *name, double value)
     }
     if (strcmp(name, "overlap_isolated") == 0) m->overlap_isolated = value != 0;
     else if (strcmp(name, "early_blocks_per_sm") == 0) m->early_blocks_per_sm = (int)value;
+    else if (strcmp(name, "isolated_blocks_per_sm") == 0) m->iso_blocks_per_sm = (int)value;
     else if (strcmp(name, "flagnancheck") == 0) m->nancheck = value != 0;
     else if (strcmp(name, "cuda_graphs") == 0) m->use_graphs = value != 0;
     else if (strcmp(name, "accumulate_discharge") == 0) m->accumulate_discharge = value != 0;
