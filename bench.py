@@ -324,6 +324,7 @@ def run_c3(args):
             one_step(Fdev[k % 2])
         ms = _capi.timer_stop()
         barrier()
+    host_calls = _capi.host_launch_count()
     launches = _capi.launch_count()
     st = M.stage_times(reset=True)
     M.soil_stats(enable_timing=True)      # one extra (untimed) step with per-kernel events in the soil stage
@@ -420,7 +421,12 @@ def run_c3(args):
                  "alg_bytes_per_cell_substep": ALG_BYTES_CHANNEL_SUBSTEP, "stage_ms": round(ch_ms, 3),
                  "note": "this stage is bound by the FP64 pipe, not by HBM: see roofline_fp64 (DESIGN.md section 4.5)",
                  "roofline_fp64": fp64}
-    roofline = dict(roof_soil if dominant == "soil_ms" else roof_chan)
+    # headline roofline: the per-cell stencil (the kernel BASELINE.json's HBM target is stated on), HBM-bound.  The stage
+    # that takes the most time (channel sub-steps) is bound by the FP64 pipe and reported against that pipe in
+    # roofline_routing.roofline_fp64 / roofline_fp64_step -- an HBM fraction would be fictitious for it.
+    roofline = dict(roof_soil)
+    roofline["note"] = ("the time-dominant stage is %s (%.1f ms), FP64-pipe bound: see roofline_routing.roofline_fp64 and "
+                        "roofline_fp64_step" % ("the channel sub-steps" if dominant == "channel_ms" else "this one", max(soil_ms, ch_ms)))
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_baseline_c3(args)
@@ -459,7 +465,12 @@ def run_c3(args):
                                 "discharge map ChanQAvg (float64) back to the host on the output stream (HotPathModel.get_async, "
                                 "two host buffers; the timed region ends when the last map has landed); the 10-day LAI maps "
                                 "stay resident"},
-                "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline,
+                "gpu_launches": int(launches), "host_launch_calls": int(host_calls),
+                "launch_note": "gpu_launches = kernels of this library executed in the timed region; host_launch_calls = launch "
+                               "API calls the host made for them (the level sweep of the overland routers and the wavefront "
+                               "diagonals are replayed as CUDA graphs: %.0f calls per step for %.0f kernels)"
+                               % (host_calls / max(K, 1), launches / max(K, 1)),
+                "clocks": clk.summary(), "roofline": roofline,
                 "roofline_stencil": roof_soil, "roofline_routing": roof_chan, "roofline_fp64_step": fp64_step,
                 "stage_ms_per_step": stage,
                 "soil_stats": soil_stats,

@@ -58,6 +58,9 @@ int lf_timer_start(void);
 int lf_timer_stop(double *elapsed_ms);
 /* Counts kernels launched by this library since the last reset (bench.py's gpu_launches). */
 int64_t lf_launch_count(int reset);
+/* Launch API calls the host made since that reset: a replayed CUDA graph counts once here and with all its kernels in
+ * lf_launch_count. */
+int64_t lf_host_launch_count(void);
 /* Page-locks / unlocks a host buffer the caller will pass repeatedly (faster H2D/D2H). */
 int lf_host_register(void *ptr, int64_t bytes);
 int lf_host_unregister(void *ptr);

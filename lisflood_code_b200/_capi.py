@@ -42,6 +42,7 @@ SIGNATURES = {
     "lf_timer_start": (C.c_int, []),
     "lf_timer_stop": (C.c_int, [C.POINTER(C.c_double)]),
     "lf_launch_count": (C.c_int64, [C.c_int]),
+    "lf_host_launch_count": (C.c_int64, []),
     "lf_host_register": (C.c_int, [_vp, _i64s]),
     "lf_host_unregister": (C.c_int, [_vp]),
     "lf_host_alloc": (C.c_int, [_i64s, C.POINTER(_vp)]),
@@ -239,3 +240,8 @@ def timer_stop():
 
 def launch_count(reset=False):
     return int(lib().lf_launch_count(1 if reset else 0))
+
+
+def host_launch_count():
+    """Launch API calls since the last launch_count(reset=True) (a replayed CUDA graph counts once)."""
+    return int(lib().lf_host_launch_count())

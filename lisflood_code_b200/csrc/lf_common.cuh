@@ -15,7 +15,7 @@ namespace lf {
 void set_error(const char *fmt, ...);
 cudaStream_t stream();
 int ensure_device();  // LF_OK or LF_ERR_NO_DEVICE / LF_ERR_CUDA
-void count_launch(int64_t n = 1);
+void count_launch(int64_t n = 1, int64_t api = -1);   // kernels executed, launch API calls (default: one per kernel)
 int sm_count();
 
 #define LF_CUDA(expr)                                                                              \
@@ -111,7 +111,7 @@ inline int run_captured(GraphCache &gc, const void *key, size_t keylen, cudaStre
         if (e.key.size() == keylen && memcmp(e.key.data(), key, keylen) == 0) {
             e.last_use = gc.tick;
             LF_CUDA(cudaGraphLaunch(e.exec, s));
-            lf::count_launch(e.kernels);
+            lf::count_launch(e.kernels, 1);   // the kernels of the graph run; the host made one call
             return LF_OK;
         }
     const int64_t before = lf_launch_count(0);

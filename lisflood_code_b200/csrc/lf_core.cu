@@ -12,7 +12,7 @@ cudaStream_t g_stream = nullptr;
 int g_device = -1;  // -1 = not initialised
 int g_sms = 0;
 cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
-std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_launches{0}, g_api_launches{0};
 }  // namespace
 
 namespace lf {
@@ -26,7 +26,11 @@ void set_error(const char *fmt, ...)
 }
 
 cudaStream_t stream() { return g_stream; }
-void count_launch(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void count_launch(int64_t n, int64_t api)
+{
+    g_launches.fetch_add(n, std::memory_order_relaxed);
+    g_api_launches.fetch_add(api < 0 ? n : api, std::memory_order_relaxed);
+}
 int sm_count() { return g_sms; }
 
 static int init_device(int device)
@@ -127,9 +131,14 @@ int lf_timer_stop(double *elapsed_ms)
 int64_t lf_launch_count(int reset)
 {
     int64_t v = g_launches.load();
-    if (reset) g_launches.store(0);
+    if (reset) {
+        g_launches.store(0);
+        g_api_launches.store(0);
+    }
     return v;
 }
+
+int64_t lf_host_launch_count(void) { return g_api_launches.load(); }
 
 int lf_host_register(void *ptr, int64_t bytes)
 {
