@@ -783,7 +783,7 @@ struct lf_model {
     int accumulate_discharge = 0;         // option "accumulate_discharge" (InitLisflood / repAverageDis)
     int overlap_isolated = 1;             // option "overlap_isolated"
     int early_blocks_per_sm = 2;          // option "early_blocks_per_sm"
-    int iso_blocks_per_sm = 8;            // option "isolated_blocks_per_sm" (0: one block per chunk)
+    int iso_blocks_per_sm = 6;            // option "isolated_blocks_per_sm" (0: one block per chunk)
     int nancheck = 0;                     // option "flagnancheck"
     std::map<std::string, std::unique_ptr<lf::DevBuf<double>>> async_stage;
     std::map<std::string, cudaEvent_t> async_copied, async_consumed;
@@ -1573,12 +1573,11 @@ int channel_stage(lf_model *m)
     if (!m->early_in_flight && iso_hi > iso_lo) LF_CUDA(cudaMemsetAsync(m->iso_next.p, 0, sizeof(int), st));
     LF_CUDA(cudaEventRecord(m->ev_fork, st));
     LF_CUDA(cudaStreamWaitEvent(sw, m->ev_fork, 0));
-    const int dbg = getenv("LF_CHAN_DEBUG") ? atoi(getenv("LF_CHAN_DEBUG")) : 0;   // timing experiments only (results are wrong for 1, 2)
-    auto isolated_part = [&]() -> int {
-    if (iso_hi > iso_lo && dbg != 2) {
-        // second drain of the chunk queue.  iso_blocks_per_sm > 0: a persistent grid of that many blocks per SM (8 fill the
-        // register file: the wavefront on the side stream then only starts once the queue is drained); 0: one block per
-        // chunk, so resident slots turn over every few microseconds and the high-priority wavefront kernels slip in.
+    if (iso_hi > iso_lo) {
+        // second drain of the chunk queue.  iso_blocks_per_sm > 0: a persistent grid of that many blocks per SM -- 8 fill the
+        // register file and the wavefront on the side stream then only starts once the queue is drained; 6 (default) leave
+        // room for two wavefront blocks per SM, so the two overlap (profiles/r02_channel_overlap_experiment.txt); 0: one
+        // block per chunk.
         const unsigned nchunks = lf::blocks_for(iso_hi - iso_lo, CH_THREADS);
         const unsigned grid = m->iso_blocks_per_sm > 0 ? std::min<unsigned>(nchunks, (unsigned)(lf::sm_count() * m->iso_blocks_per_sm))
                                                        : nchunks;
@@ -1592,9 +1591,6 @@ int channel_stage(lf_model *m)
             LF_LAUNCH_CHECK();
         }
     }
-    return LF_OK;
-    };
-    if (dbg != 3) LF_CHECK(isolated_part());
     // the connected network: space-time wavefront over (level, sub-step)
     auto level_end = [&](int l) { return l == Lc - 1 ? iso_lo : ls[l + 1]; };
     auto wavefront = [&]() -> int {
@@ -1623,11 +1619,8 @@ int channel_stage(lf_model *m)
         }
         return LF_OK;
     };
-    if (dbg != 1) {
-        if (m->use_graphs && Lc + S > 6) LF_CHECK(lf::run_captured(m->graphs_ch, &C, sizeof(C), sw, wavefront));
-        else LF_CHECK(wavefront());
-    }
-    if (dbg == 3) LF_CHECK(isolated_part());   // experiment: the wavefront is submitted first
+    if (m->use_graphs && Lc + S > 6) LF_CHECK(lf::run_captured(m->graphs_ch, &C, sizeof(C), sw, wavefront));
+    else LF_CHECK(wavefront());
     LF_CUDA(cudaEventRecord(m->ev_join, sw));
     LF_CUDA(cudaStreamWaitEvent(st, m->ev_join, 0));
     if (m->xchg) LF_CHECK(lf_xchg_end(m->xchg));
