@@ -1,0 +1,11 @@
+#!/bin/bash
+# the driver's multi-GPU command with the final code: N = $1
+N=${1:-8}
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node $N --master-port 29661 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r02_scale3_c3_n$N.json 2> gpurun_out/r02_scale3_n$N.err
+tail -1 gpurun_out/r02_scale3_c3_n$N.json | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); c=d['config']
+print({k:d.get(k) for k in ('value','ms_per_step','n_gpus','gpu_launches','host_launch_calls')}, 'e2e', d['e2e']['value'], d.get('stage_ms_per_step'))
+print('  c4_cut', d['c4_cut']['value'], d['c4_cut']['ms_per_step'], {k:d['c4_cut']['config'].get(k) for k in ('cut_edges','trunk_pixels')})"
+tail -3 gpurun_out/r02_scale3_n$N.err
