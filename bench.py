@@ -49,22 +49,60 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons of GPU `index` while the timed region runs: NVML in-process every 20 ms (so
+    that a timed region of a few tenths of a second still gets samples), `nvidia-smi -lms 100` when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    PERIOD_S = 0.02
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thr, self.nvml, self.h = index, [], None, None, None, None
+        self.stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical(index))
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
+
+    def _poll(self):
+        nv = self.nvml
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = int(get(self.h))
+                self.rows.append([mhz, self.mx] + ["Active" if r & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            self.stop.wait(self.PERIOD_S)
 
     def __enter__(self):
+        self.rows = []
+        self.stop.clear()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=self._read, daemon=True)
+            if self.nvml is not None:
+                self.thr = threading.Thread(target=self._poll, daemon=True)
+            else:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                              "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                             stderr=subprocess.DEVNULL, text=True)
+                self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception:
-            self.proc = None
+            self.proc = self.thr = None
         return self
 
     def _read(self):
@@ -72,6 +110,7 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -79,6 +118,8 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        elif self.thr:
+            self.thr.join(timeout=1)
 
     def summary(self):
         sm, mx, reasons = [], 0, set()
@@ -87,12 +128,12 @@ class ClockSampler:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                    if v.lower().startswith("active"):
+                    if str(v).lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def bind_to_gpu_numa(index):
@@ -356,7 +397,7 @@ def run_c3(args):
         host_sets.append(hs)
     dis_host = [torch.empty(nl, dtype=torch.float64, pin_memory=True) for _ in range(2)]
     torch.cuda.synchronize()
-    Ke = max(2, min(K, 5))
+    Ke = max(2, min(K, 10))
     Mdev = M.model if cut else M
 
     def e2e_step(i):
@@ -379,6 +420,35 @@ def run_c3(args):
     e2e_value = total_cells * Ke / e2e_s
     h2d = nl * 4 * len(names)
     d2h = nl * 8
+
+    # what the host link alone allows: the same bytes of one step copied with nothing else running, all ranks at once (GPUs
+    # of one node share PCIe switches and host memory), first each direction alone, then both together as in the e2e loop
+    scratch = {k: torch.empty(nl, dtype=torch.float32, device="cuda") for k in names}
+    dsrc = torch.zeros(nl, dtype=torch.float64, device="cuda")
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def copy_ms(do_in, do_out, reps=3):
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for r in range(reps):
+            if do_in:
+                with torch.cuda.stream(s_in):
+                    for k in names:
+                        scratch[k].copy_(host_sets[r % 2][k], non_blocking=True)
+            if do_out:
+                with torch.cuda.stream(s_out):
+                    dis_host[r % 2].copy_(dsrc, non_blocking=True)
+        torch.cuda.synchronize()
+        return reduce_ranks(time.perf_counter() - t0) * 1e3 / reps
+
+    link = {"h2d_alone_ms": round(copy_ms(True, False), 3), "d2h_alone_ms": round(copy_ms(False, True), 3),
+            "both_ms": round(copy_ms(True, True), 3)}
+    link["h2d_gbs_per_gpu"] = round(h2d / link["h2d_alone_ms"] / 1e6, 1)
+    link["d2h_gbs_per_gpu"] = round(d2h / link["d2h_alone_ms"] / 1e6, 1)
+    link["note"] = ("one step's host traffic per GPU copied with the GPU otherwise idle, all %d ranks at the same time (max over "
+                    "ranks): the floor the host link puts under an end-to-end step" % world)
+    del scratch, dsrc
 
     # ---- rooflines ---------------------------------------------------------------------------------------
     peak, peak_kind = measured_peaks()
@@ -459,7 +529,7 @@ def run_c3(args):
                 "scaling": "strong" if cut else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": "cell-updates/s", "steps": Ke, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_s * 1e3 / Ke, 3), "host_link": link,
                         "note": "per step and GPU: raw Precipitation, Tavg, ET0, E0 (float32, as the reference's NetCDF forcing) from "
                                 "pinned host memory through HotPathModel.feed (copy stream, overlapping the previous step), "
                                 "discharge map ChanQAvg (float64) back to the host on the output stream (HotPathModel.get_async, "
