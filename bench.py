@@ -342,8 +342,8 @@ def run_c3(args):
     M.set_lai(dev.lai_device(), **({"local": True} if cut else {}))
     Fdev = [dev.forcing_device() for _ in range(2)]
     torch.cuda.synchronize()
-    feed = (lambda F, day, asynchronous=False: M.feed(F, day, asynchronous=asynchronous, local=True)) if cut else \
-        (lambda F, day, asynchronous=False: M.feed(F, day, asynchronous=asynchronous))
+    feed = (lambda F, day, asynchronous=False, **kw: M.feed(F, day, asynchronous=asynchronous, local=True, **kw)) if cut else \
+        (lambda F, day, asynchronous=False, **kw: M.feed(F, day, asynchronous=asynchronous, **kw))
     day = [20]
 
     def one_step(F):
@@ -400,23 +400,52 @@ def run_c3(args):
     Ke = max(2, min(K, 10))
     Mdev = M.model if cut else M
 
-    def e2e_step(i):
-        M.step()                                  # forcing of step i was queued by the feed() of the previous call
-        day[0] = day[0] % 365 + 1
-        feed(host_sets[(i + 1) % 2], day[0], asynchronous=True)   # next step's raw maps cross PCIe while step i computes
-        Mdev.wait_outputs()                       # the discharge map of step i-1 has landed in its host buffer (the host
-        #                                           would hand it to the writer thread here: global_modules/output.py)
-        Mdev.get_async("ChanQAvg", dis_host[i % 2])   # D2H of this step's discharge map on the output stream
+    def e2e_loop(sets, outs, packings=None):
+        """Ke steps fed from the host sets `sets`, discharge into the host buffers `outs`; seconds, max over ranks."""
+        kw = (lambda i: {"packing": packings[i % 2]}) if packings else (lambda i: {})
 
-    feed(host_sets[0], day[0], asynchronous=True)
-    e2e_step(0)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(Ke):
-        e2e_step(k + 1)
-    Mdev.wait_outputs()                           # the last discharge map is on the host
-    barrier()
-    e2e_s = reduce_ranks(time.perf_counter() - t0)
+        def e2e_step(i):
+            M.step()                                  # forcing of step i was queued by the feed() of the previous call
+            day[0] = day[0] % 365 + 1
+            # next step's raw maps cross the host link while step i computes
+            feed(sets[(i + 1) % 2], day[0], asynchronous=True, **kw(i + 1))
+            Mdev.wait_outputs()                       # the discharge map of step i-1 has landed in its host buffer (the host
+            #                                           would hand it to the writer thread here: global_modules/output.py)
+            Mdev.get_async("ChanQAvg", outs[i % 2])   # D2H of this step's discharge map on the output stream
+
+        feed(sets[0], day[0], asynchronous=True, **kw(0))
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(Ke):
+            e2e_step(k + 1)
+        Mdev.wait_outputs()                           # the last discharge map is on the host
+        barrier()
+        return reduce_ranks(time.perf_counter() - t0)
+
+    e2e_s = e2e_loop(host_sets, dis_host)
+
+    # the same loop with the reference's own narrower formats on the host link: forcing still packed the CF way (int16 +
+    # scale_factor / add_offset, unpacked by the feeder kernel instead of the host reader, netcdf.py:231-232) and the
+    # discharge map written as float32 (OutputMapsDataType = float32, netcdf.py:478): half the bytes each way
+    packed_sets, packings = [], []
+    for i in range(2):
+        hs, pk = {}, {}
+        for k in names:
+            x = Fdev[i][k]
+            lo, hi = float(x.min()), float(x.max())
+            scale = (hi - lo) / 65534.0 if hi > lo else 1.0
+            offset = (hi + lo) / 2
+            h = torch.empty(nl, dtype=torch.int16, pin_memory=True)
+            h.copy_(torch.round((x.double() - offset) / scale).to(torch.int16))
+            hs[k], pk[k] = h, (scale, offset)
+        packed_sets.append(hs)
+        packings.append(pk)
+    dis_host32 = [torch.empty(nl, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    e2e_packed_s = e2e_loop(packed_sets, dis_host32, packings)
+    torch.cuda.synchronize()                          # the last queued upload still borrows the host buffers
+    del packed_sets, dis_host32
     e2e_value = total_cells * Ke / e2e_s
     h2d = nl * 4 * len(names)
     d2h = nl * 8
@@ -535,6 +564,13 @@ def run_c3(args):
                                 "discharge map ChanQAvg (float64) back to the host on the output stream (HotPathModel.get_async, "
                                 "two host buffers; the timed region ends when the last map has landed); the 10-day LAI maps "
                                 "stay resident"},
+                "e2e_packed": {"value": total_cells * Ke / e2e_packed_s, "unit": "cell-updates/s", "steps": Ke,
+                               "ms_per_step": round(e2e_packed_s * 1e3 / Ke, 3), "h2d_bytes_per_step": int(nl * 2 * len(names)),
+                               "d2h_bytes_per_step": int(nl * 4),
+                               "note": "the e2e loop with the narrower formats the reference itself reads and writes: forcing "
+                                       "as CF-packed int16 (scale_factor / add_offset applied by the feeder kernel, "
+                                       "HotPathModel.feed(packing=...)), discharge as float32 (OutputMapsDataType = float32, "
+                                       "narrowed on the device); not the headline: `e2e` keeps float32 in / float64 out"},
                 "gpu_launches": int(launches), "host_launch_calls": int(host_calls),
                 "launch_note": "gpu_launches = kernels of this library executed in the timed region; host_launch_calls = launch "
                                "API calls the host made for them (the level sweep of the overland routers and the wavefront "

@@ -177,6 +177,9 @@ int lf_model_get(lf_model *m, const char *name, double *values, int64_t count);
  * the previous step's map (writing dis.nc, time series) overlap the next step's kernels.  `values`
  * (page-locked for a real overlap) is valid after lf_model_wait_outputs. */
 int lf_model_get_async(lf_model *m, const char *name, double *values, int64_t count);
+/* The same, narrowed to float32 on the device first: OutputMapsDataType = float32 of the reference's map writer
+ * (global_modules/netcdf.py:478), half the bytes over the host link. */
+int lf_model_get_async_f32(lf_model *m, const char *name, float *values, int64_t count);
 int lf_model_wait_outputs(lf_model *m);
 /* boolean maps (u8[N]): "isFrozenSoil", "IsChannel", "IsChannelKinematic", "AtLastPointC" */
 int lf_model_set_flags(lf_model *m, const char *name, const uint8_t *values, int64_t count);
@@ -211,6 +214,15 @@ int lf_model_soil_stats(lf_model *m, int enable_timing, int64_t *deferred_column
 int lf_model_set_scalar(lf_model *m, const char *name, double value);
 int lf_model_feed(lf_model *m, const void *precipitation, const void *tavg, const void *et0, const void *e0, int32_t dtype,
                   double snowmelt_coeff, double ice_melt_coeff_north, double ice_melt_coeff_south, int32_t async);
+/* The same for forcing still packed the CF way -- int16 with the variable's scale_factor / add_offset attributes, which the
+ * reference's reader applies on the host (global_modules/netcdf.py:231-232, xarray's CF decoding): value = raw * scale_factor
+ * + add_offset, here on the device, so that half the bytes of the float32 maps cross the host link.  scale_factor /
+ * add_offset: 4 values each (Precipitation, Tavg, ET0, E0).  decode_float32 = 1 unpacks in float32 arithmetic (what a CF
+ * decoder yields for int16 data with float32 attributes), 0 in float64.  Missing-value codes are not looked at: compressed
+ * maps hold catchment pixels only. */
+int lf_model_feed_packed(lf_model *m, const int16_t *precipitation, const int16_t *tavg, const int16_t *et0, const int16_t *e0,
+                         const double *scale_factor, const double *add_offset, int32_t decode_float32, double snowmelt_coeff,
+                         double ice_melt_coeff_north, double ice_melt_coeff_south, int32_t async);
 int lf_model_set_lai(lf_model *m, const double *lai, int64_t count);
 /* Structures inside the routing sub-step loop: reservoirs (four-regime outflow rule,
  * hydrological_modules/reservoir.py:173-322) and lakes (Modified Puls, lakes.py:199-297), executed by the channel

@@ -85,6 +85,7 @@ SIGNATURES = {
     "lf_model_set_async": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
     "lf_model_get": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
     "lf_model_get_async": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
+    "lf_model_get_async_f32": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
     "lf_model_wait_outputs": (C.c_int, [_vp]),
     "lf_model_set_flags": (C.c_int, [_vp, C.c_char_p, _vp, _i64s]),
     "lf_model_soil": (C.c_int, [_vp]),
@@ -96,6 +97,8 @@ SIGNATURES = {
     "lf_model_soil_stats": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "lf_model_set_scalar": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "lf_model_feed": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32]),
+    "lf_model_feed_packed": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                       C.c_int32]),
     "lf_model_set_lai": (C.c_int, [_vp, _vp, _i64s]),
     "lf_model_set_structures": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, _vp]),
     "lf_model_structure_array": (C.c_int, [_vp, C.c_char_p, _vp, _i64s, C.c_int32]),

@@ -527,29 +527,34 @@ struct FeedPtrs {
     ScalarOrMap PrScaling, CalEvaporation, DeltaTSnow, SnowSeason, TempSnow, SnowFactor, SnowMeltCoef, TempMelt, lat_rad, Kfrost,
         Afrost, FrostIndexThreshold, SnowWaterEquivalent;
     double DtDay, snowmelt_coeff, ice_n, ice_s;
+    double scale[4], offset[4];                                  // CF packing of int16 input: value = raw * scale + offset
+    int32_t decode_f32, pad_;                                    // unpack in float32 arithmetic (as a float32 decoder does)
     double *SnowCoverS, *FrostIndex, *TotalPrecipitation;       // state
     double *Rain, *SnowMelt, *ETRef, *EWRef, *ESRef;            // forcing of the soil stage
     uint8_t *frozen;
     double *Snow, *SnowCover, *Precipitation, *Tavg;             // outputs kept for reporting (may be nullptr)
 };
-template <bool F32>
+// DT: element type of the raw maps -- 0 float64, 1 float32, 2 int16 packed by the CF convention (scale_factor / add_offset
+// attributes of the NetCDF variable, which the reference's reader applies on the host: netcdf.py:231-232)
+template <int DT>
+__device__ __forceinline__ double raw_value(const void *src, int p, double scale, double offset, int decode_f32)
+{
+    if (DT == 0) return ((const double *)src)[p];
+    if (DT == 1) return (double)((const float *)src)[p];
+    const int16_t r = ((const int16_t *)src)[p];
+    if (decode_f32) return (double)((float)r * (float)scale + (float)offset);
+    return (double)r * scale + offset;
+}
+template <int DT>
 __global__ void __launch_bounds__(256) k_feeder(FeedPtrs F)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= F.n) return;
     const int p = F.pix_of_pos[i];
-    double praw, tavg, et0, e0;
-    if (F32) {
-        praw = (double)((const float *)F.prec)[p];
-        tavg = (double)((const float *)F.tavg)[p];
-        et0 = (double)((const float *)F.et0)[p];
-        e0 = (double)((const float *)F.e0)[p];
-    } else {
-        praw = ((const double *)F.prec)[p];
-        tavg = ((const double *)F.tavg)[p];
-        et0 = ((const double *)F.et0)[p];
-        e0 = ((const double *)F.e0)[p];
-    }
+    const double praw = raw_value<DT>(F.prec, p, F.scale[0], F.offset[0], F.decode_f32);
+    const double tavg = raw_value<DT>(F.tavg, p, F.scale[1], F.offset[1], F.decode_f32);
+    const double et0 = raw_value<DT>(F.et0, p, F.scale[2], F.offset[2], F.decode_f32);
+    const double e0 = raw_value<DT>(F.e0, p, F.scale[3], F.offset[3], F.decode_f32);
     const double dt = F.DtDay;
     const double prec = praw * dt * F.PrScaling.at(i);               // readmeteo.py:66
     const double cal = F.CalEvaporation.at(i);
@@ -639,6 +644,19 @@ __global__ void k_rows_to_pix(const double *__restrict__ src, double *__restrict
     if (p >= n) return;
     int i = pos_of_pix[p];
     for (int r = 0; r < rows; ++r) dst[(int64_t)r * n + p] = src[(int64_t)r * n + i];
+}
+// position order -> reference order, narrowed to float32 (OutputMapsDataType = float32, netcdf.py:478); maps stored as
+// z = Q^(1/5) are converted on the way
+__global__ void k_rows_to_pix_f32(const double *__restrict__ src, float *__restrict__ dst, const int32_t *__restrict__ pos_of_pix,
+                                  int64_t n, int rows, int as_z)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int i = pos_of_pix[p];
+    for (int r = 0; r < rows; ++r) {
+        const double v = src[(int64_t)r * n + i];
+        dst[(int64_t)r * n + p] = (float)(as_z ? lfkw::pow5(v) : v);
+    }
 }
 __global__ void k_u8_to_pos(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const int32_t *__restrict__ pix_of_pos,
                             int64_t n)
@@ -1932,12 +1950,9 @@ int lf_model_get(lf_model *m, const char *name, double *values, int64_t count)
     return LF_OK;
 }
 
-int lf_model_get_async(lf_model *m, const char *name, double *values, int64_t count)
+// f32: narrow to float32 on the device before the copy (half the bytes over the host link)
+static int get_async_impl(lf_model *m, const char *name, void *values, int64_t count, bool f32)
 {
-    if (!m || !name || !values) {
-        lf::set_error("lf_model_get_async: null pointer");
-        return LF_ERR_INVALID;
-    }
     LF_CHECK(lf::ensure_device());
     Field *f = nullptr;
     LF_CHECK(field(m, name, &f));
@@ -1947,33 +1962,58 @@ int lf_model_get_async(lf_model *m, const char *name, double *values, int64_t co
     }
     cudaStream_t st = lf::stream();
     if (!m->out_stream) LF_CUDA(cudaStreamCreateWithFlags(&m->out_stream, cudaStreamNonBlocking));
-    auto it = m->out_stage.find(name);
+    const std::string key = f32 ? std::string(name) + "#f32" : std::string(name);
+    auto it = m->out_stage.find(key);
     if (it == m->out_stage.end()) {
         std::unique_ptr<lf::DevBuf<double>> b(new lf::DevBuf<double>());
-        LF_CHECK(b->alloc(count));
-        m->bytes += count * 8;
-        it = m->out_stage.emplace(name, std::move(b)).first;
+        const int64_t words = f32 ? (count + 1) / 2 : count;
+        LF_CHECK(b->alloc(words));
+        m->bytes += words * 8;
+        it = m->out_stage.emplace(key, std::move(b)).first;
         cudaEvent_t e1, e2;
         LF_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
         LF_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-        m->out_ready[name] = e1;
-        m->out_copied[name] = e2;
+        m->out_ready[key] = e1;
+        m->out_copied[key] = e2;
         LF_CUDA(cudaEventRecord(e2, m->out_stream));
     }
     double *stg = it->second->p;
-    LF_CUDA(cudaStreamWaitEvent(st, m->out_copied[name], 0));   // the previous copy out of this staging buffer is done
+    LF_CUDA(cudaStreamWaitEvent(st, m->out_copied[key], 0));   // the previous copy out of this staging buffer is done
     const int32_t *pos = f->order == SOIL ? m->g_of->pos_of_pix.p : m->g_ch->pos_of_pix.p;
-    k_rows_to_pix<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(f->buf.p, stg, pos, m->n, f->rows);
-    LF_LAUNCH_CHECK();
-    if (f->as_z) {
-        k_z_to_q<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(stg, m->n);
+    if (f32) {
+        k_rows_to_pix_f32<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(f->buf.p, (float *)stg, pos, m->n, f->rows, f->as_z ? 1 : 0);
         LF_LAUNCH_CHECK();
+    } else {
+        k_rows_to_pix<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(f->buf.p, stg, pos, m->n, f->rows);
+        LF_LAUNCH_CHECK();
+        if (f->as_z) {
+            k_z_to_q<<<lf::blocks_for(m->n, 256), 256, 0, st>>>(stg, m->n);
+            LF_LAUNCH_CHECK();
+        }
     }
-    LF_CUDA(cudaEventRecord(m->out_ready[name], st));
-    LF_CUDA(cudaStreamWaitEvent(m->out_stream, m->out_ready[name], 0));
-    LF_CUDA(cudaMemcpyAsync(values, stg, count * sizeof(double), cudaMemcpyDefault, m->out_stream));
-    LF_CUDA(cudaEventRecord(m->out_copied[name], m->out_stream));
+    LF_CUDA(cudaEventRecord(m->out_ready[key], st));
+    LF_CUDA(cudaStreamWaitEvent(m->out_stream, m->out_ready[key], 0));
+    LF_CUDA(cudaMemcpyAsync(values, stg, count * (f32 ? sizeof(float) : sizeof(double)), cudaMemcpyDefault, m->out_stream));
+    LF_CUDA(cudaEventRecord(m->out_copied[key], m->out_stream));
     return LF_OK;
+}
+
+int lf_model_get_async(lf_model *m, const char *name, double *values, int64_t count)
+{
+    if (!m || !name || !values) {
+        lf::set_error("lf_model_get_async: null pointer");
+        return LF_ERR_INVALID;
+    }
+    return get_async_impl(m, name, values, count, false);
+}
+
+int lf_model_get_async_f32(lf_model *m, const char *name, float *values, int64_t count)
+{
+    if (!m || !name || !values) {
+        lf::set_error("lf_model_get_async_f32: null pointer");
+        return LF_ERR_INVALID;
+    }
+    return get_async_impl(m, name, values, count, true);
 }
 
 int lf_model_wait_outputs(lf_model *m)
@@ -2183,16 +2223,14 @@ static int scalar_or_map(lf_model *m, const char *name, ScalarOrMap *out)
     return LF_OK;
 }
 
-int lf_model_feed(lf_model *m, const void *precipitation, const void *tavg, const void *et0, const void *e0, int32_t dtype,
-                  double snowmelt_coeff, double ice_melt_coeff_north, double ice_melt_coeff_south, int32_t async)
+// dtype: 0 float64, 1 float32, 2 int16 with scale / offset (one pair per map)
+static int feed_impl(lf_model *m, const void *precipitation, const void *tavg, const void *et0, const void *e0, int32_t dtype,
+                     const double *scale, const double *offset, int32_t decode_f32, double snowmelt_coeff,
+                     double ice_melt_coeff_north, double ice_melt_coeff_south, int32_t async)
 {
-    if (!m || !precipitation || !tavg || !et0 || !e0 || (dtype != 0 && dtype != 1)) {
-        lf::set_error("lf_model_feed: null pointer or bad dtype (0 = float64, 1 = float32)");
-        return LF_ERR_INVALID;
-    }
     LF_CHECK(lf::ensure_device());
     cudaStream_t st = lf::stream();
-    const size_t esz = dtype == 1 ? 4 : 8;
+    const size_t esz = dtype == 2 ? 2 : dtype == 1 ? 4 : 8;
     const size_t map_bytes = ((size_t)m->n * esz + 255) / 256 * 256;
     const void *src[4] = {precipitation, tavg, et0, e0};
     const void *dev[4];
@@ -2235,6 +2273,11 @@ int lf_model_feed(lf_model *m, const void *precipitation, const void *tavg, cons
     F.tavg = dev[1];
     F.et0 = dev[2];
     F.e0 = dev[3];
+    for (int k = 0; k < 4; ++k) {
+        F.scale[k] = scale ? scale[k] : 1.;
+        F.offset[k] = offset ? offset[k] : 0.;
+    }
+    F.decode_f32 = decode_f32 ? 1 : 0;
     LF_CHECK(scalar_or_map(m, "PrScaling", &F.PrScaling));
     LF_CHECK(scalar_or_map(m, "CalEvaporation", &F.CalEvaporation));
     LF_CHECK(scalar_or_map(m, "DeltaTSnow", &F.DeltaTSnow));
@@ -2279,14 +2322,38 @@ int lf_model_feed(lf_model *m, const void *precipitation, const void *tavg, cons
         F.Precipitation = pr;
         F.Tavg = ta;
     }
-    if (dtype == 1) k_feeder<true><<<lf::blocks_for(m->n, 256), 256, 0, st>>>(F);
-    else k_feeder<false><<<lf::blocks_for(m->n, 256), 256, 0, st>>>(F);
+    if (dtype == 2) k_feeder<2><<<lf::blocks_for(m->n, 256), 256, 0, st>>>(F);
+    else if (dtype == 1) k_feeder<1><<<lf::blocks_for(m->n, 256), 256, 0, st>>>(F);
+    else k_feeder<0><<<lf::blocks_for(m->n, 256), 256, 0, st>>>(F);
     LF_LAUNCH_CHECK();
     if (!on_device) {
         LF_CUDA(cudaEventRecord(m->raw_consumed[m->raw_turn ^ 1], st));
         if (!async) LF_CUDA(cudaStreamSynchronize(st));   // the host buffers are borrowed for the duration of the call
     }
     return LF_OK;
+}
+
+int lf_model_feed(lf_model *m, const void *precipitation, const void *tavg, const void *et0, const void *e0, int32_t dtype,
+                  double snowmelt_coeff, double ice_melt_coeff_north, double ice_melt_coeff_south, int32_t async)
+{
+    if (!m || !precipitation || !tavg || !et0 || !e0 || (dtype != 0 && dtype != 1)) {
+        lf::set_error("lf_model_feed: null pointer or bad dtype (0 = float64, 1 = float32)");
+        return LF_ERR_INVALID;
+    }
+    return feed_impl(m, precipitation, tavg, et0, e0, dtype, nullptr, nullptr, 0, snowmelt_coeff, ice_melt_coeff_north,
+                     ice_melt_coeff_south, async);
+}
+
+int lf_model_feed_packed(lf_model *m, const int16_t *precipitation, const int16_t *tavg, const int16_t *et0, const int16_t *e0,
+                         const double *scale_factor, const double *add_offset, int32_t decode_float32, double snowmelt_coeff,
+                         double ice_melt_coeff_north, double ice_melt_coeff_south, int32_t async)
+{
+    if (!m || !precipitation || !tavg || !et0 || !e0 || !scale_factor || !add_offset) {
+        lf::set_error("lf_model_feed_packed: null pointer");
+        return LF_ERR_INVALID;
+    }
+    return feed_impl(m, precipitation, tavg, et0, e0, 2, scale_factor, add_offset, decode_float32, snowmelt_coeff,
+                     ice_melt_coeff_north, ice_melt_coeff_south, async);
 }
 
 int lf_model_set_lai(lf_model *m, const double *lai, int64_t count)

@@ -10,9 +10,10 @@ global_modules/output.py:68-167, netcdf.py:170-341,432-583, zusatz.py:196-405).
   * OutputPipeline   per step: lf_model_get_async into one of two page-locked host buffers, then a writer thread
                      decompresses the map to the raster and appends it to the files while the device computes the next
                      step (the D2H copy runs on its own stream).
-  * ForcingStack     a float32 (time, y, x) NetCDF-3 forcing stack read through mmap; ForcingPrefetcher compresses the
-                     maps of the coming step into page-locked buffers on a thread and hands them to HotPathModel.feed
-                     (asynchronous H2D on the copy stream).
+  * ForcingStack     a float32 or CF-packed int16 (time, y, x) NetCDF-3 forcing stack read through mmap;
+                     ForcingPrefetcher compresses the maps of the coming step into page-locked buffers on a thread and
+                     hands them to HotPathModel.feed (asynchronous H2D on the copy stream; packed maps cross the host link
+                     as int16 and are unpacked by the feeder kernel).
 """
 import datetime
 import os
@@ -109,9 +110,11 @@ def pinned(n, dtype=np.float64):
 class OutputPipeline(object):
     """report(step) after every model step: the map leaves the device asynchronously and is written by a thread."""
 
-    def __init__(self, model, name, writers, pin=True):
+    def __init__(self, model, name, writers, pin=True, dtype=np.float64):
+        """dtype: np.float64, or np.float32 for OutputMapsDataType = float32 (netcdf.py:478) -- the map is then narrowed
+        on the device and half the bytes cross the host link."""
         self.M, self.name, self.writers = model, name, list(writers)
-        self.bufs = [pinned(model.N) if pin else np.empty(model.N) for _ in range(2)]
+        self.bufs = [pinned(model.N, dtype) if pin else np.empty(model.N, dtype) for _ in range(2)]
         self.turn, self.pending = 0, None
         self.q = queue.Queue(maxsize=2)
         self.err = None
@@ -166,21 +169,35 @@ class ForcingStack(object):
     """A (time, y, x) float32 stack in a NetCDF-3 file (what readmeteo's xarray reader delivers per step,
     readmeteo.py:61-69, netcdf.py:170-341), memory-mapped; [k] gives the compressed float32 map of step k."""
 
-    def __init__(self, path, var_name, land_mask):
+    def __init__(self, path, var_name, land_mask, packed=False):
+        """packed=True: an int16 variable with scale_factor / add_offset is handed on as stored (read_into fills an int16
+        buffer) and unpacked by the feeder kernel (HotPathModel.feed(packing=...)); otherwise it is unpacked here, on the
+        host, as the reference's reader does (netcdf.py:231-232)."""
         from scipy.io import netcdf_file
-        self.nc = netcdf_file(path, "r", mmap=True)
+        self.nc = netcdf_file(path, "r", mmap=True, maskandscale=False)
         self.var = self.nc.variables[var_name]
         self.mask = np.asarray(land_mask, bool)
         v = self.var
-        self.scale = float(getattr(v, "scale_factor", 1.0))
-        self.offset = float(getattr(v, "add_offset", 0.0))
+        self.scale = float(np.asarray(getattr(v, "scale_factor", 1.0)).reshape(-1)[0])
+        self.offset = float(np.asarray(getattr(v, "add_offset", 0.0)).reshape(-1)[0])
+        self.packed = bool(packed)
+        if self.packed and v.data.dtype.newbyteorder("=") != np.dtype(np.int16):
+            kind = str(v.data.dtype)
+            del v
+            self.close()
+            raise TypeError("ForcingStack(packed=True): variable '%s' is %s, not int16" % (var_name, kind))
 
     def __len__(self):
         return self.var.shape[0]
 
+    @property
+    def packing(self):
+        """(scale_factor, add_offset) of the variable."""
+        return self.scale, self.offset
+
     def read_into(self, k, out):
         a = self.var[k][self.mask]
-        if self.scale != 1.0 or self.offset != 0.0:
+        if not self.packed and (self.scale != 1.0 or self.offset != 0.0):
             a = a * self.scale + self.offset
         out[:] = a
         return out
@@ -190,8 +207,9 @@ class ForcingStack(object):
         self.nc.close()
 
 
-def write_forcing_stack(path, var_name, land_mask, maps, dt_sec=86400.0, start_date=None):
-    """Writes compressed float32 maps [(N,), ...] as a (time, y, x) NetCDF-3 stack (test / example data)."""
+def write_forcing_stack(path, var_name, land_mask, maps, dt_sec=86400.0, start_date=None, packing=None):
+    """Writes compressed float32 maps [(N,), ...] as a (time, y, x) NetCDF-3 stack (test / example data); with
+    packing = (scale_factor, add_offset) the maps are int16 already packed with these attributes."""
     from scipy.io import netcdf_file
     mask = np.asarray(land_mask, bool)
     rows, cols = mask.shape
@@ -202,9 +220,16 @@ def write_forcing_stack(path, var_name, land_mask, maps, dt_sec=86400.0, start_d
     nc.createDimension("x", cols)
     t = nc.createVariable("time", "f8", ("time",))
     t.units = time_units(dt_sec, start_date or datetime.datetime(2000, 1, 1))[0]
-    v = nc.createVariable(var_name, "f4", ("time", "y", "x"))
-    v._FillValue = np.float32(FILL)
-    ras = np.full((rows, cols), FILL, np.float32)
+    if packing is None:
+        v = nc.createVariable(var_name, "f4", ("time", "y", "x"))
+        v._FillValue = np.float32(FILL)
+        ras = np.full((rows, cols), FILL, np.float32)
+    else:
+        v = nc.createVariable(var_name, "i2", ("time", "y", "x"))
+        v._FillValue = np.int16(-32768)
+        v.scale_factor = np.array([packing[0]], np.float64)      # arrays: a Python float would be stored as NC_FLOAT
+        v.add_offset = np.array([packing[1]], np.float64)
+        ras = np.full((rows, cols), -32768, np.int16)
     for k, m in enumerate(maps):
         ras[mask] = m
         v[k] = ras
@@ -223,7 +248,13 @@ class ForcingPrefetcher(object):
     def __init__(self, stacks, n, first=0, last=None, pin=True):
         self.stacks = stacks
         self.last = min(len(stacks[k]) for k in self.NAMES) if last is None else last
-        self.sets = [{k: (pinned(n, np.float32) if pin else np.empty(n, np.float32)) for k in self.NAMES} for _ in range(4)]
+        packed = [bool(getattr(stacks[k], "packed", False)) for k in self.NAMES]
+        if any(packed) and not all(packed):
+            raise ValueError("ForcingPrefetcher: either all four stacks are handed on packed or none")
+        # packed stacks: int16 buffers and the attributes feed() needs -- M.feed(maps, day, packing=prefetcher.packing)
+        self.packing = {k: stacks[k].packing for k in self.NAMES} if all(packed) else None
+        dt = np.int16 if self.packing else np.float32
+        self.sets = [{k: (pinned(n, dt) if pin else np.empty(n, dt)) for k in self.NAMES} for _ in range(4)]
         self.q = queue.Queue(maxsize=1)
         self.thread = threading.Thread(target=self._run, args=(first,), daemon=True)
         self.thread.start()

@@ -178,21 +178,39 @@ class HotPathModel(object):
         for name, v in (state or {}).items():
             self.set(name, v, 3 if name == "SnowCoverS" else 1)
 
-    def feed(self, raw, calendar_day, asynchronous=False):
+    def feed(self, raw, calendar_day, asynchronous=False, packing=None, decode="float32"):
         """Raw meteo maps of the step -> forcing of the soil stage (lf_model_feed).  raw: Precipitation, Tavg, ET0, E0;
-        float32 or float64; NumPy arrays or torch tensors (host or CUDA), compressed order."""
+        float32 or float64; NumPy arrays or torch tensors (host or CUDA), compressed order.
+        packing: {name: (scale_factor, add_offset)} for int16 maps still packed the CF way (the attributes of the NetCDF
+        variable; netcdf.py:231-232): unpacked on the device (lf_model_feed_packed) in `decode` arithmetic."""
         from .hydrological_modules.snow import season_coefficients
-        maps = [raw[k] for k in ("Precipitation", "Tavg", "ET0", "E0")]
+        keys = ("Precipitation", "Tavg", "ET0", "E0")
+        maps = [raw[k] for k in keys]
         size = lambda a: a.element_size() if hasattr(a, "element_size") else a.dtype.itemsize
         count = lambda a: a.numel() if hasattr(a, "numel") else a.size
         es = size(maps[0])
-        if es not in (4, 8) or any(size(a) != es or count(a) != self.N for a in maps):
-            raise ValueError("feed: four float32 or four float64 maps of %d pixels" % self.N)
+        sizes = (2,) if packing is not None else (4, 8)
+        if es not in sizes or any(size(a) != es or count(a) != self.N for a in maps):
+            raise ValueError("feed: four %s maps of %d pixels" % ("int16" if packing is not None else "float32 or four float64",
+                                                                  self.N))
         if not hasattr(maps[0], "data_ptr"):
             maps = [np.ascontiguousarray(a) for a in maps]
             if asynchronous:
                 self.__dict__["_raw_keepalive"] = maps     # borrowed until the next synchronising call
         c, ice_n, ice_s = season_coefficients(int(calendar_day))
+        if packing is not None:
+            if decode not in ("float32", "float64"):
+                raise ValueError("feed: decode is 'float32' or 'float64'")
+            for a in maps:
+                dt = str(a.dtype)
+                if not dt.endswith("int16") or dt.endswith("uint16"):
+                    raise ValueError("feed: packed maps are int16, got %s" % dt)
+            scale = np.array([float(packing[k][0]) for k in keys])
+            offset = np.array([float(packing[k][1]) for k in keys])
+            _capi.check(_capi.lib().lf_model_feed_packed(self._h, *[_capi.ptr(a) for a in maps], _capi.ptr(scale),
+                                                         _capi.ptr(offset), 1 if decode == "float32" else 0, c, ice_n, ice_s,
+                                                         1 if asynchronous else 0))
+            return
         _capi.check(_capi.lib().lf_model_feed(self._h, *[_capi.ptr(a) for a in maps], 1 if es == 4 else 0, c, ice_n, ice_s,
                                               1 if asynchronous else 0))
 
@@ -238,9 +256,16 @@ class HotPathModel(object):
 
     def get_async(self, name, out):
         """Queues the copy of a map into `out` (page-locked NumPy array / torch tensor) without waiting; valid after
-        wait_outputs()."""
+        wait_outputs().  A float32 `out` gets the map narrowed on the device (OutputMapsDataType = float32,
+        netcdf.py:478): half the bytes over the host link."""
         size = out.numel() if hasattr(out, "numel") else out.size
-        _capi.check(_capi.lib().lf_model_get_async(self._h, name.encode(), _capi.ptr(out), size))
+        dt = str(out.dtype)
+        if dt.endswith("float64"):
+            _capi.check(_capi.lib().lf_model_get_async(self._h, name.encode(), _capi.ptr(out), size))
+        elif dt.endswith("float32"):
+            _capi.check(_capi.lib().lf_model_get_async_f32(self._h, name.encode(), _capi.ptr(out), size))
+        else:
+            raise TypeError("get_async: `out` is float64 or float32, got %s" % dt)
 
     def wait_outputs(self):
         _capi.check(_capi.lib().lf_model_wait_outputs(self._h))

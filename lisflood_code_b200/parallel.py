@@ -478,9 +478,11 @@ class DistributedHotPathModel(object):
     def set_feeder(self, P, state=None):
         self.model.set_feeder({k: self._local(v) for k, v in P.items()}, {k: self._local(v) for k, v in (state or {}).items()})
 
-    def feed(self, raw, calendar_day, asynchronous=False, local=False):
-        """Raw meteo maps of the step (global maps, or this rank's pixels with local=True)."""
-        self.model.feed(raw if local else {k: self._local(v) for k, v in raw.items()}, calendar_day, asynchronous=asynchronous)
+    def feed(self, raw, calendar_day, asynchronous=False, local=False, packing=None, decode="float32"):
+        """Raw meteo maps of the step (global maps, or this rank's pixels with local=True); packing / decode as in
+        HotPathModel.feed."""
+        self.model.feed(raw if local else {k: self._local(v) for k, v in raw.items()}, calendar_day, asynchronous=asynchronous,
+                        packing=packing, decode=decode)
 
     def set_lai(self, lai, local=False):
         self.model.set_lai(lai if local else self._local(lai))

@@ -73,3 +73,21 @@ class FeederOracle(object):
 def lai_term(kgb, lai):
     """leafarea.py:90."""
     return np.exp(-np.asarray(kgb, np.float64) * np.asarray(lai, np.float64))
+
+
+def cf_pack(values, bits=16):
+    """scale_factor / add_offset and the packed integers of a map, the CF way (NetCDF Users Guide, "Packed data values":
+    add_offset = (max + min) / 2, scale_factor = (max - min) / (2^bits - 2)); the inverse of cf_unpack up to rounding."""
+    v = np.asarray(values, np.float64)
+    lo, hi = float(v.min()), float(v.max())
+    scale = (hi - lo) / (2 ** bits - 2) if hi > lo else 1.0
+    offset = (hi + lo) / 2
+    return np.rint((v - offset) / scale).astype(np.int16), scale, offset
+
+
+def cf_unpack(raw, scale_factor, add_offset, decode="float32"):
+    """What the reference's reader hands on for a packed variable (xarray's CF decoding behind netcdf.py:231-232):
+    raw * scale_factor + add_offset in the decoder's float type -- float32 for int16 data unless the attributes are
+    float64."""
+    t = np.float32 if decode == "float32" else np.float64
+    return np.asarray(raw).astype(t) * t(scale_factor) + t(add_offset)

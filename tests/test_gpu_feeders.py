@@ -98,3 +98,72 @@ def test_dynamic_with_raw_forcing_equals_feed_and_step(gpu_lib):
             assert np.array_equal(A.get(k, rows), B.get(k, rows)), (t, k)
     with pytest.raises(RuntimeError):
         dyn.frost_module.dynamic()              # out of order: no snow.dynamic before it
+
+
+@pytest.mark.parametrize("decode", ["float32", "float64"])
+@pytest.mark.parametrize("asynchronous", [False, True])
+def test_packed_forcing_is_unpacked_on_the_device(gpu_lib, decode, asynchronous):
+    """int16 forcing with scale_factor / add_offset (CF packing, decoded on the host by the reference's reader:
+    netcdf.py:231-232) gives bit for bit what feeding the unpacked maps gives, and that agrees with the feeder oracle."""
+    from oracle.lisf_oracle_feeders import FeederOracle, cf_pack, cf_unpack
+    rng = np.random.default_rng(17)
+    n = 4099
+    P = {"PrScaling": 1.0, "CalEvaporation": 1.05, "DeltaTSnow": rng.uniform(0, 2, n), "SnowSeason": 0.5, "TempSnow": 1.0,
+         "SnowFactor": 1.0, "SnowMeltCoef": 4.0, "TempMelt": 0.0, "lat_rad": np.radians(rng.uniform(-40, 60, n)), "Kfrost": 0.57,
+         "Afrost": 0.97, "FrostIndexThreshold": 56.0, "SnowWaterEquivalent": 0.45, "kgb": 0.75 * 0.72}
+    S0 = {"SnowCoverS": rng.uniform(0, 50, (3, n)), "FrostIndex": rng.uniform(0, 60, n)}
+    A, B = _model(n, 86400.0), _model(n, 86400.0)
+    Pm = {k: (np.full(n, v) if np.ndim(v) == 0 else v) for k, v in P.items() if k != "kgb"}
+    F = FeederOracle(Pm, S0, 86400.0)
+    for M in (A, B):
+        M.set_feeder(P, S0)
+    keys = ("Rain", "SnowMelt", "ETRef", "EWRef", "ESRef", "SnowCoverS", "FrostIndex", "Snow", "SnowCover", "Precipitation", "Tavg")
+    for t, day in enumerate((15, 120, 260, 350)):
+        fields = {"Precipitation": rng.gamma(0.8, 8.0, n), "Tavg": rng.uniform(-25, 25, n), "ET0": rng.uniform(0, 6, n),
+                  "E0": rng.uniform(0, 7, n)}
+        packed, packing, unpacked = {}, {}, {}
+        for k, v in fields.items():
+            packed[k], s, o = cf_pack(v)
+            packing[k] = (s, o)
+            unpacked[k] = cf_unpack(packed[k], s, o, decode)
+            assert unpacked[k].dtype == (np.float32 if decode == "float32" else np.float64)
+            assert np.abs(unpacked[k] - v).max() <= 0.51 * s * (1 + 1e-3) + 1e-6      # it is the packing of these maps
+        A.feed(packed, day, asynchronous=asynchronous, packing=packing, decode=decode)
+        B.feed(unpacked, day)
+        gpu_lib.synchronize()
+        want = F.step({k: v.astype(np.float64) for k, v in unpacked.items()}, day)
+        for k in keys:
+            rows = 3 if k == "SnowCoverS" else 1
+            a = A.get(k, rows)
+            assert np.array_equal(a, B.get(k, rows)), (t, k)
+            if k in want:
+                assert rel_err(a, want[k]) < 1e-12, (t, k)
+    with pytest.raises(ValueError):
+        A.feed(packed, 1, packing=packing, decode="float16")
+    with pytest.raises(ValueError):
+        A.feed(unpacked, 1, packing=packing)          # not int16
+    with pytest.raises(ValueError):
+        A.feed(packed, 1)                             # int16 without its packing attributes
+
+
+def test_get_async_float32_is_the_narrowed_map(gpu_lib):
+    """OutputMapsDataType = float32 (netcdf.py:478): the map is narrowed on the device, equal to get().astype(float32)."""
+    from lisflood_code_b200 import _capi, synthetic
+    from lisflood_code_b200.hotpath import HotPathModel
+    S = synthetic.full_stack(40, 50, seed=3, mask_fraction=0.1)
+    M = HotPathModel(S)
+    out32 = _capi.pinned_empty(S["N"], np.float32)
+    kin32 = _capi.pinned_empty(S["N"], np.float32)
+    w32 = _capi.pinned_empty(3 * S["N"], np.float32)
+    for t in range(3):
+        M.set_forcing(synthetic.forcing(S, t, seed=4))
+        M.step()
+        M.get_async("ChanQAvg", out32)                # a map in the channel order
+        M.get_async("ChanQKin", kin32)                # stored as Q^(1/5) on the device (Beta = 0.6)
+        M.get_async("W1a", w32)                       # a (3, N) map in the soil order
+        M.wait_outputs()
+        assert np.array_equal(out32, M.get("ChanQAvg").astype(np.float32))
+        assert np.array_equal(kin32, M.get("ChanQKin").astype(np.float32)) and float(kin32.max()) > 0
+        assert np.array_equal(np.asarray(w32).reshape(3, -1), M.get("W1a", 3).astype(np.float32))
+    with pytest.raises(TypeError):
+        M.get_async("ChanQAvg", np.empty(S["N"], np.int32))

@@ -4,6 +4,7 @@ the maps of the stack in order.  The overlap with the device is exercised in tes
 import datetime
 
 import numpy as np
+import pytest
 
 
 def test_map_stack_and_tss(tmp_path):
@@ -60,3 +61,42 @@ def test_forcing_stack_prefetch(tmp_path):
     assert seen == [0, 1, 2, 3, 4]
     for st in stacks.values():
         st.close()
+
+
+def test_packed_forcing_stack(tmp_path):
+    """An int16 stack with scale_factor / add_offset: unpacked on the host like the reference's reader (default), or handed
+    on as stored together with its attributes (packed=True) for the feeder kernel to unpack."""
+    from lisflood_code_b200.global_modules.output import ForcingPrefetcher, ForcingStack, write_forcing_stack
+    from oracle.lisf_oracle_feeders import cf_pack, cf_unpack
+    rng = np.random.default_rng(4)
+    mask = rng.random((7, 9)) > 0.25
+    n = int(mask.sum())
+    packed, attrs, stacks, hosted = {}, {}, {}, {}
+    for name in ForcingPrefetcher.NAMES:
+        allmaps = rng.uniform(-5, 30, (4, n))
+        raw, s, o = cf_pack(allmaps)
+        packed[name], attrs[name] = list(raw), (s, o)
+        path = str(tmp_path / (name + ".nc"))
+        write_forcing_stack(path, name, mask, packed[name], packing=(s, o))
+        stacks[name] = ForcingStack(path, name, mask, packed=True)
+        hosted[name] = ForcingStack(path, name, mask)
+        assert stacks[name].packing == (s, o)
+    pf = ForcingPrefetcher(stacks, n, pin=False)
+    assert pf.packing == attrs
+    for k in range(4):
+        i, maps = pf.next()
+        assert i == k
+        for name in ForcingPrefetcher.NAMES:
+            assert maps[name].dtype == np.int16 and np.array_equal(maps[name], packed[name][k])
+            got = hosted[name].read_into(k, np.empty(n, np.float32))
+            assert np.array_equal(got, cf_unpack(packed[name][k], *attrs[name], decode="float64").astype(np.float32))
+    with pytest.raises(StopIteration):
+        pf.next()
+    with pytest.raises(ValueError):
+        ForcingPrefetcher(dict(stacks, Tavg=hosted["Tavg"]), n, pin=False)
+    for st in list(stacks.values()) + list(hosted.values()):
+        st.close()
+    data = [rng.uniform(0, 1, n).astype(np.float32)]
+    write_forcing_stack(str(tmp_path / "f.nc"), "x", mask, data)
+    with pytest.raises(TypeError):
+        ForcingStack(str(tmp_path / "f.nc"), "x", mask, packed=True)
