@@ -313,6 +313,8 @@ def run_c3(args):
     if os.environ.get("LF_EARLY_BPS"):      # tuning runs: resident blocks per SM of the early isolated-pixel launch
         M.set_option("early_blocks_per_sm", int(os.environ["LF_EARLY_BPS"]))
     M.set_option("overlap_isolated", 1 if args.overlap else 0)
+    if os.environ.get("LF_NARROW") is not None:
+        M.set_option("narrow_runs", int(os.environ["LF_NARROW"]))
     if os.environ.get("LF_ISO_BPS") is not None:     # tuning runs: footprint of the isolated-pixel kernel
         M.set_option("isolated_blocks_per_sm", int(os.environ["LF_ISO_BPS"]))
     _capi.synchronize()

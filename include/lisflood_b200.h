@@ -125,7 +125,8 @@ int lf_router_run(lf_router *r, int section, int nsteps, const double *q_scale, 
 /* Execution options of a router: "cuda_graphs" 1 (default): the diagonals of a run are captured once and replayed as a
  * CUDA graph; "cooperative" k > 0: a run over a deep network is ONE persistent cooperative launch (k resident blocks per
  * SM) with a grid barrier per diagonal -- measured slower than graph replay on B200, off by default; both 0: one plain
- * launch per diagonal. */
+ * launch per diagonal.  "narrow_runs" 1 (default): consecutive diagonals of at most 512 work items (the long tail of a deep
+ * network) run back to back in ONE single-block launch, a block barrier between two diagonals; 0: one launch each. */
 int lf_router_set_option(lf_router *r, const char *name, double value);
 void lf_router_destroy(lf_router *r);
 
@@ -243,10 +244,16 @@ int lf_model_set_structures(lf_model *m, int32_t n_reservoirs, const int64_t *re
                             const int64_t *lake_index);
 int lf_model_structure_array(lf_model *m, const char *name, double *values, int64_t count, int32_t set);
 /* Execution options of a model (name, value):
- *   "overlap_isolated"     1 (default): lf_model_step starts the sub-steps of the non-channel isolated pixels of
+ *   "overlap_isolated"     1: lf_model_step starts the sub-steps of the non-channel isolated pixels of
  *                          LddKinematic (no side flow, routing.py:512) at the top of the step, on a low-priority
- *                          stream alongside the soil stage; 0: everything of the channel stage runs inside it.
+ *                          stream alongside the soil stage; 0 (default; the step is bound by the FP64 pipe, co-running
+ *                          the two did not shorten it): everything of the channel stage runs inside it.
  *   "early_blocks_per_sm"  resident blocks per SM of that early launch (default 2).
+ *   "isolated_blocks_per_sm" resident blocks per SM of the isolated-pixel kernel inside the channel stage (default 6:
+ *                          leaves room for the wavefront's blocks, so the two overlap; 0: one block per chunk).
+ *   "narrow_runs"          1 (default): consecutive wavefront diagonals of at most 512 work items -- the long tail of a
+ *                          deep network -- run back to back in ONE single-block launch (a block barrier between two
+ *                          diagonals instead of a kernel boundary); 0: one launch per diagonal.
  *   "cuda_graphs"          1 (default): the level sweep of the overland routers and the diagonals of the channel
  *                          wavefront (hundreds of small dependent launches per step) are captured once per argument
  *                          set and replayed as CUDA graphs; 0: plain launches.

@@ -97,11 +97,13 @@ struct GraphCache {
     };
     std::vector<Entry> entries;
     uint64_t tick = 0;
-    ~GraphCache()
+    void clear()   // after a change of how the work is cut into launches (the keys do not see it)
     {
         for (Entry &e : entries)
             if (e.exec) cudaGraphExecDestroy(e.exec);
+        entries.clear();
     }
+    ~GraphCache() { clear(); }
 };
 template <class F>
 inline int run_captured(GraphCache &gc, const void *key, size_t keylen, cudaStream_t s, F &&enqueue)

@@ -50,6 +50,7 @@ struct lf_router {
     int32_t x_cap_steps = 0, n_export = 0, n_import = 0;
     lf::GraphCache graphs;   // CUDA-graph replay of the diagonals of a run (one variant per argument set)
     int use_graphs = 1, use_coop = 0;   // lf_router_set_option; the cooperative launch is off by default (measured slower)
+    int narrow_runs = 1;                // runs of narrow diagonals in one single-block launch
     lf::DevBuf<unsigned int> coop_counter;
 };
 
@@ -178,6 +179,24 @@ __global__ void __launch_bounds__(KW_THREADS) k_kw_diagonal(int lo, int hi, int 
     kw_item<QZ, HASX>(A, i, d);
 }
 
+// A run of consecutive NARROW diagonals [d0, d1) -- at most KW_RUN_THREADS items each: the long tail of a deep network,
+// where a level holds a handful of trunk pixels -- in ONE block: a __syncthreads() between two diagonals instead of a
+// kernel boundary (~1.5 us instead of the ~5 us of a graph node).  Values written by the block's other threads in earlier
+// diagonals are visible after the barrier; ghost pixels poll peer memory as in k_kw_diagonal.
+constexpr int KW_RUN_THREADS = 512;
+template <bool QZ, bool HASX>
+__global__ void __launch_bounds__(KW_RUN_THREADS) k_kw_narrow_run(int d0, int d1, int nlev, int nsteps,
+                                                                  const int32_t *__restrict__ level_start, KwArgs A)
+{
+    for (int d = d0; d < d1; ++d) {
+        const int lo_lev = d - nsteps + 1 > 0 ? d - nsteps + 1 : 0;
+        const int hi_lev = d < nlev - 1 ? d : nlev - 1;
+        const int i = level_start[lo_lev] + threadIdx.x;
+        if (i < level_start[hi_lev + 1]) kw_item<QZ, HASX>(A, i, d);
+        __syncthreads();
+    }
+}
+
 // The whole run in ONE cooperative launch: a persistent grid (every block resident) walks the diagonals and meets at a
 // grid-wide barrier after each one.  Built for deep networks (tens of thousands of levels: a diagonal is only a few
 // microseconds of work) and MEASURED SLOWER than the CUDA-graph replay of one kernel per diagonal on B200 -- C2 deep
@@ -274,8 +293,30 @@ int run_steps(lf_router *r, int sec, int nsteps, const double *d_scale)
             lf::count_launch();
         }
     }
+    auto width = [&](int d) {
+        int lo_lev = d - nsteps + 1 > 0 ? d - nsteps + 1 : 0;
+        int hi_lev = d < L - 1 ? d : L - 1;
+        return ls[hi_lev + 1] - ls[lo_lev];
+    };
+    const int32_t *lsd = g->level_start.p;
     auto diagonals = [&]() -> int {
         for (int d = 0; d < ndiag; ++d) {
+            if (r->narrow_runs && width(d) <= KW_RUN_THREADS) {   // a run of narrow diagonals: one single-block launch
+                int e = d + 1;
+                while (e < ndiag && width(e) <= KW_RUN_THREADS) ++e;
+                if (e - d >= 3) {
+                    if (r->P.quintic) {
+                        if (hasx) k_kw_narrow_run<true, true><<<1, KW_RUN_THREADS, 0, st>>>(d, e, L, nsteps, lsd, A);
+                        else k_kw_narrow_run<true, false><<<1, KW_RUN_THREADS, 0, st>>>(d, e, L, nsteps, lsd, A);
+                    } else {
+                        if (hasx) k_kw_narrow_run<false, true><<<1, KW_RUN_THREADS, 0, st>>>(d, e, L, nsteps, lsd, A);
+                        else k_kw_narrow_run<false, false><<<1, KW_RUN_THREADS, 0, st>>>(d, e, L, nsteps, lsd, A);
+                    }
+                    LF_LAUNCH_CHECK();
+                    d = e - 1;
+                    continue;
+                }
+            }
             int lo_lev = d - nsteps + 1 > 0 ? d - nsteps + 1 : 0;
             int hi_lev = d < L - 1 ? d : L - 1;
             int lo = ls[lo_lev], hi = ls[hi_lev + 1];
@@ -567,6 +608,10 @@ int lf_router_set_option(lf_router *r, const char *name, double value)
         return LF_ERR_INVALID;
     }
     if (strcmp(name, "cuda_graphs") == 0) r->use_graphs = value != 0;
+    else if (strcmp(name, "narrow_runs") == 0) {
+        r->narrow_runs = value != 0;
+        r->graphs.clear();
+    }
     else if (strcmp(name, "cooperative") == 0) r->use_coop = (int)value;   // resident blocks per SM of the persistent grid, 0 = off
     else {
         lf::set_error("lf_router_set_option: unknown option '%s'", name);

@@ -219,12 +219,10 @@ __device__ __forceinline__ void chan_substep(const ChanPtrs &C, int i, double U1
 
 constexpr int CH_THREADS = 128;
 
-// wavefront diagonal over channel-network pixels: positions [lo, hi), sub-step s = d - level
+// one work item of the channel wavefront: position i on diagonal d, sub-step s = d - level
 template <bool QZ, bool HASX, bool HASS>
-__global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo, int hi, int d)
+__device__ __forceinline__ void chan_item(const ChanPtrs &C, int i, int d)
 {
-    int i = lo + blockIdx.x * CH_THREADS + threadIdx.x;
-    if (i >= hi) return;
     int s = d - C.lev[i];
     double *Qr = (s & 1) ? C.Qr1 : C.Qr0;
     double *Q2r = (s & 1) ? C.Q2r1 : C.Q2r0;
@@ -300,6 +298,34 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo
     } else if (last) {
         C.M3[i] = X.m3;
         C.ChanQ[i] = X.chanq;
+    }
+}
+
+// wavefront diagonal over channel-network pixels: positions [lo, hi)
+template <bool QZ, bool HASX, bool HASS>
+__global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo, int hi, int d)
+{
+    int i = lo + blockIdx.x * CH_THREADS + threadIdx.x;
+    if (i >= hi) return;
+    chan_item<QZ, HASX, HASS>(C, i, d);
+}
+
+// A run of consecutive NARROW diagonals [d0, d1) -- at most CH_RUN_THREADS items each: the long tail of a deep network,
+// where a level holds a handful of trunk pixels -- in ONE block: a __syncthreads() between two diagonals instead of a
+// kernel boundary (~1.5 us instead of the ~5 us of a graph node).  n_connected: end of the last level (the isolated
+// pixels follow it in the position order).
+constexpr int CH_RUN_THREADS = 512;
+template <bool QZ, bool HASX, bool HASS>
+__global__ void __launch_bounds__(CH_RUN_THREADS) k_chan_narrow_run(ChanPtrs C, int d0, int d1, int nlev,
+                                                                    const int32_t *__restrict__ level_start, int n_connected)
+{
+    for (int d = d0; d < d1; ++d) {
+        const int lo_lev = d - C.S + 1 > 0 ? d - C.S + 1 : 0;
+        const int hi_lev = d < nlev - 1 ? d : nlev - 1;
+        const int i = level_start[lo_lev] + threadIdx.x;
+        const int hi = hi_lev == nlev - 1 ? n_connected : level_start[hi_lev + 1];
+        if (i < hi) chan_item<QZ, HASX, HASS>(C, i, d);
+        __syncthreads();
     }
 }
 
@@ -798,8 +824,9 @@ struct lf_model {
     } st;
     lf::GraphCache graphs_of, graphs_ch;
     int use_graphs = 1;                   // option "cuda_graphs"
+    int narrow_runs = 1;                  // option "narrow_runs": runs of narrow wavefront diagonals in one single-block launch
     int accumulate_discharge = 0;         // option "accumulate_discharge" (InitLisflood / repAverageDis)
-    int overlap_isolated = 1;             // option "overlap_isolated"
+    int overlap_isolated = 0;             // option "overlap_isolated" (measured: no gain)
     int early_blocks_per_sm = 2;          // option "early_blocks_per_sm"
     int iso_blocks_per_sm = 6;            // option "isolated_blocks_per_sm" (0: one block per chunk)
     int nancheck = 0;                     // option "flagnancheck"
@@ -1611,8 +1638,38 @@ int channel_stage(lf_model *m)
     }
     // the connected network: space-time wavefront over (level, sub-step)
     auto level_end = [&](int l) { return l == Lc - 1 ? iso_lo : ls[l + 1]; };
+    auto width = [&](int d) {
+        int lo_lev = d - S + 1 > 0 ? d - S + 1 : 0;
+        int hi_lev = d < Lc - 1 ? d : Lc - 1;
+        return level_end(hi_lev) - ls[lo_lev];
+    };
+    const int32_t *lsd = g->level_start.p;
     auto wavefront = [&]() -> int {
         for (int d = 0; d < Lc + S - 1; ++d) {
+            if (m->narrow_runs && width(d) <= CH_RUN_THREADS) {   // a run of narrow diagonals: one single-block launch
+                int e = d + 1;
+                while (e < Lc + S - 1 && width(e) <= CH_RUN_THREADS) ++e;
+                if (e - d >= 3) {
+#define LF_CHAN_RUN(QZ_, HX_, HS_) k_chan_narrow_run<QZ_, HX_, HS_><<<1, CH_RUN_THREADS, 0, sw>>>(C, d, e, Lc, lsd, iso_lo)
+                    if (C.sid && C.X.xslot) {
+                        if (m->quintic) LF_CHAN_RUN(true, true, true);
+                        else LF_CHAN_RUN(false, true, true);
+                    } else if (C.sid) {
+                        if (m->quintic) LF_CHAN_RUN(true, false, true);
+                        else LF_CHAN_RUN(false, false, true);
+                    } else if (C.X.xslot) {
+                        if (m->quintic) LF_CHAN_RUN(true, true, false);
+                        else LF_CHAN_RUN(false, true, false);
+                    } else {
+                        if (m->quintic) LF_CHAN_RUN(true, false, false);
+                        else LF_CHAN_RUN(false, false, false);
+                    }
+#undef LF_CHAN_RUN
+                    LF_LAUNCH_CHECK();
+                    d = e - 1;
+                    continue;
+                }
+            }
             int lo_lev = d - S + 1 > 0 ? d - S + 1 : 0;
             int hi_lev = d < Lc - 1 ? d : Lc - 1;
             int lo = ls[lo_lev], hi = level_end(hi_lev);
@@ -2482,6 +2539,10 @@ int lf_model_set_option(lf_model *m, const char *name, double value)
     else if (strcmp(name, "isolated_blocks_per_sm") == 0) m->iso_blocks_per_sm = (int)value;
     else if (strcmp(name, "flagnancheck") == 0) m->nancheck = value != 0;
     else if (strcmp(name, "cuda_graphs") == 0) m->use_graphs = value != 0;
+    else if (strcmp(name, "narrow_runs") == 0) {
+        m->narrow_runs = value != 0;
+        m->graphs_ch.clear();
+    }
     else if (strcmp(name, "accumulate_discharge") == 0) m->accumulate_discharge = value != 0;
     else {
         lf::set_error("lf_model_set_option: unknown option '%s'", name);

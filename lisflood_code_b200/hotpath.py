@@ -327,7 +327,8 @@ class HotPathModel(object):
             self.check_finite()
 
     def set_option(self, name, value):
-        """Execution options of lf_model_set_option ("overlap_isolated", "early_blocks_per_sm", "flagnancheck")."""
+        """Execution options of lf_model_set_option ("overlap_isolated", "early_blocks_per_sm", "isolated_blocks_per_sm",
+        "narrow_runs", "cuda_graphs", "accumulate_discharge", "flagnancheck")."""
         _capi.check(_capi.lib().lf_model_set_option(self._h, name.encode(), float(value)))
         if name == "flagnancheck":
             self.__dict__["_nancheck"] = bool(value)

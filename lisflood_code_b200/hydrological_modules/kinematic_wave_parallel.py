@@ -65,8 +65,10 @@ class kinematicWave:
         self._env_options()
 
     def _env_options(self):
-        """Tuning runs: LF_ROUTER_COOP / LF_ROUTER_GRAPHS override the execution options of the router."""
+        """Tuning runs: LF_ROUTER_COOP / LF_ROUTER_GRAPHS / LF_ROUTER_NARROW override the execution options of the router."""
         import os
+        if os.environ.get("LF_ROUTER_NARROW") is not None:
+            self.set_option("narrow_runs", float(os.environ["LF_ROUTER_NARROW"]))
         if os.environ.get("LF_ROUTER_COOP") is not None:
             self.set_option("cooperative", float(os.environ["LF_ROUTER_COOP"]))
         if os.environ.get("LF_ROUTER_GRAPHS") is not None:
@@ -191,7 +193,7 @@ class kinematicWave:
         self._warn(bad.value)
 
     def set_option(self, name, value):
-        """Execution options of lf_router_set_option ("cooperative", "cuda_graphs")."""
+        """Execution options of lf_router_set_option ("cooperative", "cuda_graphs", "narrow_runs")."""
         _capi.check(_capi.lib().lf_router_set_option(self._router, name.encode(), float(value)))
 
     def get_discharge(self, section="main_channel", out=None):

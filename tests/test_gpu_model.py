@@ -172,3 +172,36 @@ def test_lean_model_vs_oracle(gpu_lib, oracle, rows, cols, maskf):
             if not e < TOL:
                 bad[k] = e
         assert not bad, (t, bad)
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_narrow_runs_equal_one_launch_per_diagonal(gpu_lib, split):
+    """Channel wavefront: runs of narrow diagonals in one single-block launch (k_chan_narrow_run) against one launch per
+    diagonal, bit for bit, on a network deep enough to have both kinds."""
+    from lisflood_code_b200 import synthetic
+    S = synthetic.full_stack(420, 380, seed=12, split_routing=split, ldd_noise=0.3, mask_fraction=0.05)
+    got = {}
+    for narrow in (1, 0):
+        M = _model(gpu_lib, S)
+        M.set_option("narrow_runs", narrow)
+        for t in range(3):
+            M.step(synthetic.forcing(S, t, 12))
+        got[narrow] = {k: M.get(k) for k in ("ChanQAvg", "ChanQ", "ChanM3", "ChanQKin", "sumDis")}
+    for k in got[1]:
+        assert np.array_equal(got[1][k], got[0][k]), k
+    assert float(got[1]["ChanQAvg"].max()) > 0
+
+
+def test_early_isolated_launch_equals_serial(gpu_lib):
+    """"overlap_isolated": the non-channel isolated pixels started beside the soil stage give the same maps, bit for bit."""
+    from lisflood_code_b200 import synthetic
+    S = synthetic.full_stack(300, 260, seed=14, ldd_noise=0.5, mask_fraction=0.05)
+    got = {}
+    for overlap in (0, 1):
+        M = _model(gpu_lib, S)
+        M.set_option("overlap_isolated", overlap)
+        for t in range(3):
+            M.step(synthetic.forcing(S, t, 14))
+        got[overlap] = {k: M.get(k) for k in ("ChanQAvg", "ChanQ", "ChanM3", "ChanQKin", "sumDis", "LZ")}
+    for k in got[1]:
+        assert np.array_equal(got[1][k], got[0][k]), k
