@@ -125,8 +125,8 @@ int lf_router_run(lf_router *r, int section, int nsteps, const double *q_scale, 
 /* Execution options of a router: "cuda_graphs" 1 (default): the diagonals of a run are captured once and replayed as a
  * CUDA graph; "cooperative" k > 0: a run over a deep network is ONE persistent cooperative launch (k resident blocks per
  * SM) with a grid barrier per diagonal -- measured slower than graph replay on B200, off by default; both 0: one plain
- * launch per diagonal.  "narrow_runs" 1 (default): consecutive diagonals of at most 512 work items (the long tail of a deep
- * network) run back to back in ONE single-block launch, a block barrier between two diagonals; 0: one launch each. */
+ * launch per diagonal.  "narrow_runs" 1: consecutive diagonals of at most 512 work items run back to back in ONE
+ * single-block launch, a block barrier between two diagonals; 0 (default; measured: no gain): one launch each. */
 int lf_router_set_option(lf_router *r, const char *name, double value);
 void lf_router_destroy(lf_router *r);
 
@@ -251,9 +251,9 @@ int lf_model_structure_array(lf_model *m, const char *name, double *values, int6
  *   "early_blocks_per_sm"  resident blocks per SM of that early launch (default 2).
  *   "isolated_blocks_per_sm" resident blocks per SM of the isolated-pixel kernel inside the channel stage (default 6:
  *                          leaves room for the wavefront's blocks, so the two overlap; 0: one block per chunk).
- *   "narrow_runs"          1 (default): consecutive wavefront diagonals of at most 512 work items -- the long tail of a
- *                          deep network -- run back to back in ONE single-block launch (a block barrier between two
- *                          diagonals instead of a kernel boundary); 0: one launch per diagonal.
+ *   "narrow_runs"          1: consecutive wavefront diagonals of at most 512 work items run back to back in ONE
+ *                          single-block launch (a block barrier between two diagonals instead of a kernel boundary);
+ *                          0 (default; measured: no gain): one launch per diagonal.
  *   "cuda_graphs"          1 (default): the level sweep of the overland routers and the diagonals of the channel
  *                          wavefront (hundreds of small dependent launches per step) are captured once per argument
  *                          set and replayed as CUDA graphs; 0: plain launches.

@@ -50,7 +50,7 @@ struct lf_router {
     int32_t x_cap_steps = 0, n_export = 0, n_import = 0;
     lf::GraphCache graphs;   // CUDA-graph replay of the diagonals of a run (one variant per argument set)
     int use_graphs = 1, use_coop = 0;   // lf_router_set_option; the cooperative launch is off by default (measured slower)
-    int narrow_runs = 1;                // runs of narrow diagonals in one single-block launch
+    int narrow_runs = 0;                // runs of narrow diagonals in one single-block launch (option; measured: no gain)
     lf::DevBuf<unsigned int> coop_counter;
 };
 
@@ -179,10 +179,12 @@ __global__ void __launch_bounds__(KW_THREADS) k_kw_diagonal(int lo, int hi, int 
     kw_item<QZ, HASX>(A, i, d);
 }
 
-// A run of consecutive NARROW diagonals [d0, d1) -- at most KW_RUN_THREADS items each: the long tail of a deep network,
-// where a level holds a handful of trunk pixels -- in ONE block: a __syncthreads() between two diagonals instead of a
-// kernel boundary (~1.5 us instead of the ~5 us of a graph node).  Values written by the block's other threads in earlier
-// diagonals are visible after the barrier; ghost pixels poll peer memory as in k_kw_diagonal.
+// A run of consecutive NARROW diagonals [d0, d1) -- at most KW_RUN_THREADS items each -- in ONE block: a __syncthreads()
+// between two diagonals instead of a kernel boundary.  Values written by the block's other threads in earlier diagonals
+// are visible after the barrier; ghost pixels poll peer memory as in k_kw_diagonal.  An OPTION ("narrow_runs"), off by
+// default: the reference's ordering counts levels down from the distance to the outlet, so a deep basin is narrow only in
+// its first few hundred diagonals (the far ends of its longest paths); measured on C2 deep (13.0 ms either way) and C4
+// (38 of 28 589 diagonals merged, 809 ms either way).
 constexpr int KW_RUN_THREADS = 512;
 template <bool QZ, bool HASX>
 __global__ void __launch_bounds__(KW_RUN_THREADS) k_kw_narrow_run(int d0, int d1, int nlev, int nsteps,

@@ -310,10 +310,12 @@ __global__ void __launch_bounds__(CH_THREADS) k_chan_diagonal(ChanPtrs C, int lo
     chan_item<QZ, HASX, HASS>(C, i, d);
 }
 
-// A run of consecutive NARROW diagonals [d0, d1) -- at most CH_RUN_THREADS items each: the long tail of a deep network,
-// where a level holds a handful of trunk pixels -- in ONE block: a __syncthreads() between two diagonals instead of a
-// kernel boundary (~1.5 us instead of the ~5 us of a graph node).  n_connected: end of the last level (the isolated
-// pixels follow it in the position order).
+// A run of consecutive NARROW diagonals [d0, d1) -- at most CH_RUN_THREADS items each -- in ONE block: a __syncthreads()
+// between two diagonals instead of a kernel boundary.  An OPTION ("narrow_runs"), off by default: in the reference's
+// ordering the levels count the distance to the outlet downwards, so only the first few hundred diagonals of a deep basin
+// are narrow (the far ends of its longest paths) -- nothing to gain there --, and on C3 the fat block cannot share an SM
+// with the persistent isolated-pixel kernel, so the tail it merges runs AFTER that kernel instead of beside it (channel
+// stage 48.7 ms instead of 44.1).  n_connected: end of the last level (the isolated pixels follow it in position order).
 constexpr int CH_RUN_THREADS = 512;
 template <bool QZ, bool HASX, bool HASS>
 __global__ void __launch_bounds__(CH_RUN_THREADS) k_chan_narrow_run(ChanPtrs C, int d0, int d1, int nlev,
@@ -824,7 +826,8 @@ struct lf_model {
     } st;
     lf::GraphCache graphs_of, graphs_ch;
     int use_graphs = 1;                   // option "cuda_graphs"
-    int narrow_runs = 1;                  // option "narrow_runs": runs of narrow wavefront diagonals in one single-block launch
+    int narrow_runs = 0;                  // option "narrow_runs": runs of narrow wavefront diagonals in one single-block launch
+                                          // (off: measured slower on C3, without effect on deep basins -- DESIGN.md 4.5)
     int accumulate_discharge = 0;         // option "accumulate_discharge" (InitLisflood / repAverageDis)
     int overlap_isolated = 0;             // option "overlap_isolated" (measured: no gain)
     int early_blocks_per_sm = 2;          // option "early_blocks_per_sm"

@@ -214,8 +214,9 @@ def test_routing_accepts_any_array_like_the_reference(gpu_lib):
 
 @pytest.mark.parametrize("rows,cols,noise,steps", [(600, 500, 0.3, 30), (200, 3000, 1.0, 7)])
 def test_narrow_runs_equal_one_launch_per_diagonal(gpu_lib, rows, cols, noise, steps):
-    """One basin with a long collector: most diagonals hold a handful of pixels and run back to back in one block
-    (k_kw_narrow_run); the discharge is bit-identical to one launch per diagonal, with and without graph replay."""
+    """Option "narrow_runs": the diagonals of at most 512 work items (here the far ends of the longest paths of one basin)
+    run back to back in one block (k_kw_narrow_run); the discharge is bit-identical to one launch per diagonal, with and
+    without graph replay."""
     from lisflood_code_b200 import synthetic
     ldd, mask = synthetic.random_ldd(rows, cols, seed=41, noise=noise, single_outlet=True)
     n = int(mask.sum())
