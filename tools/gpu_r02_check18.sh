@@ -1,13 +1,10 @@
 #!/bin/bash
-# 2 GPUs: the cut router / model / structures bit-identical to one GPU with the narrow-run kernels in the wavefront
-# (plain and stress), then the driver's N = 2 command
+# 2 GPUs, final build: the cut router / model / structures bit-identical to one GPU, then the driver's N = 2 command
 mkdir -p gpurun_out
 O=gpurun_out
 T="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-timeout 300 $T --nproc-per-node 2 --master-port 29681 tools/run_dist_check.py > $O/r02_dist_check_2gpu_narrow.log 2>&1
-grep -E "PASSED|FAILED" $O/r02_dist_check_2gpu_narrow.log | tail -2
-timeout 300 $T --nproc-per-node 2 --master-port 29682 tools/run_dist_check.py --stress > $O/r02_dist_check_2gpu_narrow_stress.log 2>&1
-grep -E "PASSED|FAILED" $O/r02_dist_check_2gpu_narrow_stress.log | tail -2
+timeout 300 $T --nproc-per-node 2 --master-port 29681 tools/run_dist_check.py > $O/r02_dist_check_2gpu_final.log 2>&1
+grep -E "PASSED|FAILED" $O/r02_dist_check_2gpu_final.log | tail -2
 timeout 600 $T --nproc-per-node 2 --master-port 29683 bench.py --gpus 2 --steps 10 --warmup 3 > $O/r02_check18_c3_n2.json 2> $O/r02_check18.err
 tail -1 $O/r02_check18_c3_n2.json | python -c "
 import sys,json
