@@ -339,6 +339,21 @@ int lf_interception_water_balance(double *Interception, double *TaInterception, 
                                   const double *LAI, const double *Rain, const double *TaInterceptionMax, double drainageK,
                                   int64_t num_vegs, int64_t num_pixs);
 
+/* suctionUnsaturatedSoilPF(index_landuse_all, pF0, pF1, pF2, W1a, W1b, W2, WRes*, WS*, PoreSpaceNotZero*, GenuInvAlpha*,
+ * GenuInvM*, GenuInvN*, HeadMax), soilloop.py:402-424 (option simulatePF): pF = log10 of the capillary head [cm] of the
+ * layers 1a, 1b, 2 -- the arrays below in that order --, -1 where the head is not positive.  Writes pF. */
+typedef struct lf_soil_pf_args {
+    int64_t num_vegs, num_pixs, num_landuses;
+    const int64_t *index_landuse_all;   /* (V), host */
+    double *pF[3];                      /* (V,N) out: pF0, pF1, pF2 */
+    const double *W[3];                 /* (V,N): W1a, W1b, W2 */
+    const double *WRes[3], *WS[3];      /* (L,N) */
+    const uint8_t *PoreSpaceNotZero[3]; /* (L,N) */
+    const double *GenuInvAlpha[3], *GenuInvM[3], *GenuInvN[3]; /* (L,N) */
+    double HeadMax;
+} lf_soil_pf_args;
+int lf_suction_unsaturated_soil_pf(const lf_soil_pf_args *args);
+
 /* soilColumnsWaterBalance(index_landuse_all, is_irrigated, is_paddy_irrig, paddy_inactive, DtDay, ...), soilloop.py:78-355:
  * the 73 arguments in the reference's order (paddy rice belongs to the EPIC crop module, out of scope: is_paddy_irrig
  * must be all false, paddy_inactive is ignored).  In/out: AvailableWaterForInfiltration, DSLR, ESAct, PrefFlow,

@@ -107,6 +107,7 @@ SIGNATURES = {
     "lf_model_destroy": (None, [_vp]),
     "lf_interception_water_balance": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _i64s, _i64s]),
     "lf_soil_columns_water_balance": (C.c_int, [_vp]),
+    "lf_suction_unsaturated_soil_pf": (C.c_int, [_vp]),
 }
 
 
@@ -138,6 +139,13 @@ class SoilColumnsArgs(C.Structure):
                                      "UpperZoneK")]
                 + [("DrainedFraction", C.c_double), ("GwPercStep", _D), ("UZOutflow", _D), ("UZ", _D), ("GwPercUZLZ", _D),
                    ("NoSubS_out", _I)])
+
+
+class SoilPfArgs(C.Structure):
+    """struct lf_soil_pf_args (include/lisflood_b200.h): the arguments of suctionUnsaturatedSoilPF, layers 1a, 1b, 2."""
+    _fields_ = [("num_vegs", C.c_int64), ("num_pixs", C.c_int64), ("num_landuses", C.c_int64), ("index_landuse_all", _I),
+                ("pF", _D * 3), ("W", _D * 3), ("WRes", _D * 3), ("WS", _D * 3), ("PoreSpaceNotZero", _U * 3),
+                ("GenuInvAlpha", _D * 3), ("GenuInvM", _D * 3), ("GenuInvN", _D * 3), ("HeadMax", C.c_double)]
 
 
 _lib = None

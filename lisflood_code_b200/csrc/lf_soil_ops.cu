@@ -1,6 +1,7 @@
 // lf_soil_ops.cu -- the reference's two Numba kernels as stand-alone operators on the device:
 //   interception_water_balance   hydrological_modules/soilloop.py:27-70
 //   soilColumnsWaterBalance      hydrological_modules/soilloop.py:78-355 (helpers :360-396)
+//   suctionUnsaturatedSoilPF     hydrological_modules/soilloop.py:402-432 (option simulatePF; CUDA libm pow / log10)
 // One thread per (vegetation fraction, pixel) column, the reference's statement order, the arithmetic library of the
 // fused stage (lf_math.cuh; unsat_k / substeps_of from lf_soil_kernel.cuh).  Unlike the fused stage the operators take
 // every derived parameter (StoreMaxPervious, PowerInfPot, GenuM, PoreSpaceNotZero, W1, WRes1 ...) from the caller, as
@@ -189,6 +190,28 @@ __global__ void __launch_bounds__(OP_THREADS) k_op_soil_columns(const __grid_con
 }
 
 // host <-> device staging of one argument
+// suctionUnsaturatedSoilPF, soilloop.py:402-424: pF = log10 of the capillary head of the three soil layers, from the
+// saturation term (saturationDegree, :379-383) through the inverse Van Genuchten curve (pressureHead, :428-432).
+// An optional output computed once per reported step: the standard pow / log10 are used, not the hot path's tables.
+__global__ void __launch_bounds__(OP_THREADS) k_op_suction_pf(const __grid_constant__ lf_soil_pf_args A, const int64_t *__restrict__ landuse_of_veg)
+{
+    const int64_t k = (int64_t)blockIdx.x * OP_THREADS + threadIdx.x;
+    const int64_t V = A.num_vegs, N = A.num_pixs;
+    if (k >= V * N) return;
+    const int64_t pix = k % N, lu = landuse_of_veg[k / N] * N + pix;
+#pragma unroll
+    for (int layer = 0; layer < 3; ++layer) {
+        double sat = 0.;
+        if (A.PoreSpaceNotZero[layer][lu]) {
+            const double wres = A.WRes[layer][lu];
+            sat = dmax(dmin((A.W[layer][k] - wres) / (A.WS[layer][lu] - wres), 1.), 0.);
+        }
+        double head = A.HeadMax;
+        if (sat != 0) head = fmin(A.HeadMax, A.GenuInvAlpha[layer][lu] * pow(pow(1. / sat, A.GenuInvM[layer][lu]) - 1., A.GenuInvN[layer][lu]));
+        A.pF[layer][k] = head > 0 ? log10(head) : -1.;
+    }
+}
+
 struct Staged {
     void *dev = nullptr;
     void *host = nullptr;
@@ -380,6 +403,57 @@ extern "C" int lf_soil_columns_water_balance(const lf_soil_columns_args *args)
     if (A.NoSubS_out) OPARG(NoSubS_out, vn, int64_t, true);
 #undef OPARG
     k_op_soil_columns<<<lf::blocks_for(V * N, OP_THREADS), OP_THREADS, 0, st>>>(A);
+    LF_LAUNCH_CHECK();
+    return S.finish();
+}
+
+extern "C" int lf_suction_unsaturated_soil_pf(const lf_soil_pf_args *args)
+{
+    if (!args || args->num_vegs <= 0 || args->num_pixs <= 0 || args->num_landuses <= 0 || !args->index_landuse_all) {
+        lf::set_error("lf_suction_unsaturated_soil_pf: null argument block or empty shape");
+        return LF_ERR_INVALID;
+    }
+    LF_CHECK(lf::ensure_device());
+    lf_soil_pf_args A = *args;
+    const int64_t V = A.num_vegs, N = A.num_pixs, L = A.num_landuses;
+    if (lf::is_device_ptr(A.index_landuse_all)) {
+        lf::set_error("lf_suction_unsaturated_soil_pf: index_landuse_all is a host array");
+        return LF_ERR_INVALID;
+    }
+    for (int64_t v = 0; v < V; ++v)
+        if (A.index_landuse_all[v] < 0 || A.index_landuse_all[v] >= L) {
+            lf::set_error("lf_suction_unsaturated_soil_pf: index_landuse_all[%lld] outside 0..%lld", (long long)v, (long long)L - 1);
+            return LF_ERR_INVALID;
+        }
+    cudaStream_t st = lf::stream();
+    Stager S(st);
+    const size_t vn = (size_t)V * N, ln = (size_t)L * N;
+    void *dv = nullptr, *d_index = nullptr;
+    LF_CHECK(S.in(A.index_landuse_all, (size_t)V * sizeof(int64_t), false, &d_index));
+    for (int layer = 0; layer < 3; ++layer) {
+        if (!A.pF[layer] || !A.W[layer] || !A.WRes[layer] || !A.WS[layer] || !A.PoreSpaceNotZero[layer] || !A.GenuInvAlpha[layer] ||
+            !A.GenuInvM[layer] || !A.GenuInvN[layer]) {
+            lf::set_error("lf_suction_unsaturated_soil_pf: a map of layer %d is NULL", layer);
+            return LF_ERR_INVALID;
+        }
+        LF_CHECK(S.in(A.pF[layer], vn * sizeof(double), true, &dv));
+        A.pF[layer] = (double *)dv;
+        LF_CHECK(S.in(A.W[layer], vn * sizeof(double), false, &dv));
+        A.W[layer] = (const double *)dv;
+        LF_CHECK(S.in(A.WRes[layer], ln * sizeof(double), false, &dv));
+        A.WRes[layer] = (const double *)dv;
+        LF_CHECK(S.in(A.WS[layer], ln * sizeof(double), false, &dv));
+        A.WS[layer] = (const double *)dv;
+        LF_CHECK(S.in(A.PoreSpaceNotZero[layer], ln * sizeof(uint8_t), false, &dv));
+        A.PoreSpaceNotZero[layer] = (const uint8_t *)dv;
+        LF_CHECK(S.in(A.GenuInvAlpha[layer], ln * sizeof(double), false, &dv));
+        A.GenuInvAlpha[layer] = (const double *)dv;
+        LF_CHECK(S.in(A.GenuInvM[layer], ln * sizeof(double), false, &dv));
+        A.GenuInvM[layer] = (const double *)dv;
+        LF_CHECK(S.in(A.GenuInvN[layer], ln * sizeof(double), false, &dv));
+        A.GenuInvN[layer] = (const double *)dv;
+    }
+    k_op_suction_pf<<<lf::blocks_for(V * N, OP_THREADS), OP_THREADS, 0, st>>>(A, (const int64_t *)d_index);
     LF_LAUNCH_CHECK();
     return S.finish();
 }

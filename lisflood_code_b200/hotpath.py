@@ -84,6 +84,10 @@ class HotPathModel(object):
         self.__dict__["_h"] = C.c_void_p()
         self.__dict__["diagnostics"] = bool(diagnostics)
         self.__dict__["split"] = bool(S.get("SplitRouting"))
+        self.__dict__["DtDay"] = float(S["DtSec"]) / 86400.0
+        # option simulatePF: the parameters only the pF kernel needs (soil.py:184-190,466), kept on the host
+        self.__dict__["_pf_params"] = {k: S[k] for k in ("HeadMax",) + tuple(p + x for p in ("GenuInvAlpha", "GenuInvN")
+                                                                             for x in ("1a", "1b", "2")) if k in S}
         self.__dict__["N"] = n_active
         h = C.c_void_p()
         if graphs is not None:
@@ -244,9 +248,34 @@ class HotPathModel(object):
             return self.get("OFM3Direct") + self.get("OFM3Other") + self.get("OFM3Forest")
         elif name == "WaterDepth":                                      # surface_routing.py:203
             return self.get("M3all") * (1 / self.get("MMtoM3"))
+        elif name == "SoilMoistureStressDays":                          # option repStressDays, soilloop.py:597-598
+            return np.where(self.get("RWS", 3) < 1, self.DtDay, 0.0)    # (RWS is a map of the diagnostics build)
         if rows is None:
             rows = self._rows.get(name, 1)
         return self.get_into(name, np.empty((rows, self.N) if rows > 1 else (self.N,), np.float64))
+
+    def suction_pf(self, GenuInvAlpha=None, GenuInvN=None, HeadMax=None):
+        """Option simulatePF (soilloop.py:673-705): pF0, pF1, pF2 -- log10 of the capillary head of the layers 1a, 1b, 2 --
+        from the soil moisture of the model, by the device operator suctionUnsaturatedSoilPF.  GenuInvAlpha, GenuInvN:
+        per layer ("1a", "1b", "2") the (landuse, pixel) maps soil.initial derives (soil.py:184-190), HeadMax (:466);
+        by default the ones the model was created with.  The other parameters are the model's own."""
+        from .hydrological_modules.soilloop import suctionUnsaturatedSoilPF
+        lay = ("1a", "1b", "2")
+        try:
+            if GenuInvAlpha is None:
+                GenuInvAlpha = {x: self._pf_params["GenuInvAlpha" + x] for x in lay}
+            if GenuInvN is None:
+                GenuInvN = {x: self._pf_params["GenuInvN" + x] for x in lay}
+            if HeadMax is None:
+                HeadMax = self._pf_params["HeadMax"]
+        except KeyError as e:
+            raise KeyError("suction_pf: %s was neither passed nor part of the model's parameters" % e.args[0])
+        pf = [np.empty((3, self.N)) for _ in lay]
+        maps = lambda k: [self.get(k + x, 3) for x in lay]
+        pore = [self.get("WS" + x, 3) != 0 for x in lay]   # PoreSpaceNotZero, soil.py:226 (WS = ThetaS * depth: 0 with the depth)
+        suctionUnsaturatedSoilPF(np.arange(3), pf[0], pf[1], pf[2], *maps("W"), *maps("WRes"), *maps("WS"), *pore,
+                                 *[GenuInvAlpha[x] for x in lay], *maps("GenuInvM"), *[GenuInvN[x] for x in lay], HeadMax)
+        return pf
 
     def get_into(self, name, out):
         """Copies a map into `out` (NumPy array or torch tensor, host or CUDA, float64, contiguous)."""

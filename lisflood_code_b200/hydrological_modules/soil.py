@@ -44,7 +44,8 @@ class soil(HydroModule):
                                 'DSLRForestInitValue', 'DSLRIrrigationInitValue', 'CumIntInitValue',
                                 'CumIntForestInitValue', 'CumIntIrrigationInitValue', 'CumIntSealedInitValue',
                                 'SMaxSealed'],
-                        'drainedIrrigation': ['DrainedFraction']}
+                        'drainedIrrigation': ['DrainedFraction'],
+                        'simulatePF': ['HeadMax']}
     module_name = 'Soil'
 
     def __init__(self, soil_variable):
@@ -140,6 +141,8 @@ class soil(HydroModule):
         v.CumInterSealed = load('CumIntSealedInitValue')
         v.SMaxSealed = load('SMaxSealed')
         v.DrainedFraction = load('DrainedFraction') if v.option('drainedIrrigation') else 0.0
+        if v.option('simulatePF'):       # :464-469; pF0..2 themselves are produced on request (HotPathModel.suction_pf)
+            v.HeadMax = load('HeadMax')
 
     def dynamic_perpixel(self):
         self.var._soil_stage_call("dynamic_perpixel")

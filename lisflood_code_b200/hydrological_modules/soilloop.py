@@ -93,6 +93,38 @@ def soilColumnsWaterBalance(*args, **kwargs):
     _capi.check(_capi.lib().lf_soil_columns_water_balance(C.byref(S)))
 
 
+def suctionUnsaturatedSoilPF(index_landuse_all, pF0, pF1, pF2, W1a, W1b, W2, WRes1a, WRes1b, WRes2, WS1a, WS1b, WS2,
+                             PoreSpaceNotZero1a, PoreSpaceNotZero1b, PoreSpaceNotZero2, GenuInvAlpha1a, GenuInvAlpha1b,
+                             GenuInvAlpha2, GenuInvM1a, GenuInvM1b, GenuInvM2, GenuInvN1a, GenuInvN1b, GenuInvN2, HeadMax):
+    """The reference's Numba kernel of option simulatePF (hydrological_modules/soilloop.py:402-424) on the device: the same
+    26 arguments; pF0, pF1, pF2 -- (vegetation, pixel) float64 -- are written in place, returns None."""
+    V, N = np.shape(pF0)
+    S = _capi.SoilPfArgs()
+    idx = np.ascontiguousarray(index_landuse_all, np.int64)
+    keep = [idx]
+    S.num_vegs, S.num_pixs, S.num_landuses = V, N, int(np.shape(WRes1a)[0])
+    S.index_landuse_all = idx.ctypes.data_as(_capi._I)
+    S.HeadMax = float(HeadMax)
+    groups = {"pF": (pF0, pF1, pF2), "W": (W1a, W1b, W2), "WRes": (WRes1a, WRes1b, WRes2), "WS": (WS1a, WS1b, WS2),
+              "PoreSpaceNotZero": (PoreSpaceNotZero1a, PoreSpaceNotZero1b, PoreSpaceNotZero2),
+              "GenuInvAlpha": (GenuInvAlpha1a, GenuInvAlpha1b, GenuInvAlpha2), "GenuInvM": (GenuInvM1a, GenuInvM1b, GenuInvM2),
+              "GenuInvN": (GenuInvN1a, GenuInvN1b, GenuInvN2)}
+    for name, arrays in groups.items():
+        for layer, a in enumerate(arrays):
+            if name == "pF":
+                arr = _f64(a, "pF%d" % layer)
+            elif name == "PoreSpaceNotZero":
+                arr = np.ascontiguousarray(a).astype(np.uint8)
+            else:
+                arr = np.ascontiguousarray(a, np.float64)
+            want = (V, N) if name in ("pF", "W") else (S.num_landuses, N)
+            if arr.shape != want:
+                raise ValueError("suctionUnsaturatedSoilPF: %s of layer %d has shape %s, expected %s" % (name, layer, arr.shape, want))
+            keep.append(arr)
+            getattr(S, name)[layer] = arr.ctypes.data_as(_capi._U if name == "PoreSpaceNotZero" else _capi._D)
+    _capi.check(_capi.lib().lf_suction_unsaturated_soil_pf(C.byref(S)))
+
+
 class soilloop(HydroModule):
     input_files_keys = {'wateruse': []}
     module_name = 'SoilLoop'

@@ -70,6 +70,25 @@ def interception_water_balance(Interception, TaInterception, LeafDrainage, CumIn
                             float(drainageK), V, N)
 
 
+def suction_unsaturated_soil_pf(index_landuse_all, pF0, pF1, pF2, W1a, W1b, W2, WRes1a, WRes1b, WRes2, WS1a, WS1b, WS2,
+                                PoreSpaceNotZero1a, PoreSpaceNotZero1b, PoreSpaceNotZero2, GenuInvAlpha1a, GenuInvAlpha1b,
+                                GenuInvAlpha2, GenuInvM1a, GenuInvM1b, GenuInvM2, GenuInvN1a, GenuInvN1b, GenuInvN2, HeadMax):
+    """suctionUnsaturatedSoilPF (soilloop.py:402-424 / :673-697) with saturationDegree (:379-383) and pressureHead
+    (:428-432) restated in NumPy: same 26 arguments, pF0..2 written in place."""
+    idx = np.asarray(index_landuse_all)
+    layers = ((pF0, W1a, WRes1a, WS1a, PoreSpaceNotZero1a, GenuInvAlpha1a, GenuInvM1a, GenuInvN1a),
+              (pF1, W1b, WRes1b, WS1b, PoreSpaceNotZero1b, GenuInvAlpha1b, GenuInvM1b, GenuInvN1b),
+              (pF2, W2, WRes2, WS2, PoreSpaceNotZero2, GenuInvAlpha2, GenuInvM2, GenuInvN2))
+    with np.errstate(all="ignore"):
+        for pf, w, wres, ws, pore, inva, invm, invn in layers:
+            wres, ws, pore = np.asarray(wres)[idx], np.asarray(ws)[idx], np.asarray(pore, bool)[idx]
+            sat = np.where(pore, np.maximum(np.minimum((w - wres) / (ws - wres), 1.0), 0.0), 0.0)          # :379-383
+            safe = np.where(sat == 0, 1.0, sat)
+            head = np.minimum(HeadMax, np.asarray(inva)[idx] * ((1.0 / safe) ** np.asarray(invm)[idx] - 1.0) ** np.asarray(invn)[idx])
+            head = np.where(sat == 0, HeadMax, head)                                                       # :429-432
+            pf[...] = np.where(head > 0, np.log10(np.where(head > 0, head, 1.0)), -1.0)                    # :422-424
+
+
 def soil_columns(v, ESMax, nosubs=None):
     """soilColumnsWaterBalance on the attributes of `v` (argument list of soilloop.py:645-665)."""
     a = SoilArgs()

@@ -263,9 +263,50 @@ def feeders_case(name, n, seed, steps, dt_sec, day0):
                                                                  (out["O%d__SnowCover" % (steps - 1)] > 0).mean()))
 
 
+def soil_options_case(name, rows, cols, seed, steps=2):
+    """The option-gated extras of soilloop.dynamic_soil, executed by the reference's OWN class with the options switched on:
+    repStressDays (SoilMoistureStressDays, soilloop.py:597-598) and simulatePF (the nested Numba kernel
+    suctionUnsaturatedSoilPF, soilloop.py:673-705: pF0, pF1, pF2 from the end-of-step soil moisture)."""
+    from oracle import ref_modules
+    S = synthetic.full_stack(rows, cols, seed=seed, split_routing=False, mask_fraction=0.08, channel_threshold=12)
+    n = S["N"]
+    rng = np.random.default_rng(seed + 1000)
+    M = ref_modules.RefModel(S, options={"simulatePF": True, "repStressDays": True})
+    v = M.var
+    extra = {"HeadMax": np.float64(1.0e7)}
+    for lay in ("1a", "1b", "2"):
+        extra["GenuInvAlpha" + lay] = 1 / rng.uniform(0.004, 0.2, (3, n))
+        extra["GenuInvN" + lay] = 1 - 1 / S["GenuInvM" + lay]           # n = 1 / (1 - m), soil.py:176-186
+        for k in ("GenuInvAlpha" + lay, "GenuInvN" + lay):
+            setattr(v, k, ref_modules.numpy_modified(extra[k].copy(), v.LU_DIMS))
+    v.HeadMax = float(extra["HeadMax"])
+    for k in ("pF0", "pF1", "pF2"):
+        setattr(v, k, v.allocateVariableAllVegetation())
+    out = {"steps": np.int64(steps)}
+    out.update({"S__" + k: np.asarray(a) for k, a in S.items()})
+    out.update({"X__" + k: a for k, a in extra.items()})
+    for t in range(steps):
+        F = synthetic.forcing(S, t, seed)
+        if t == 1:
+            F = dict(F, Rain=F["Rain"] * 0.0)        # a dry step: water stress on more columns
+        for k, a in F.items():
+            out["F%d__%s" % (t, k)] = a
+        M.step(F)
+        for k in ("pF0", "pF1", "pF2", "SoilMoistureStressDays", "RWS", "W1a", "W1b", "W2"):
+            out["O%d__%s" % (t, k)] = np.asarray(getattr(v, k).values).copy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    last = steps - 1
+    print(name, "n=%d: stressed columns %.3f, pF range %.2f..%.2f, pF = -1 on %.4f" % (
+        n, (out["O%d__SoilMoistureStressDays" % last] > 0).mean(), out["O%d__pF0" % last].min(), out["O%d__pF2" % last].max(),
+        np.mean([np.mean(out["O%d__pF%d" % (last, i)] == -1) for i in range(3)])))
+
+
 def main():
     import warnings
     warnings.simplefilter("ignore")
+    if len(sys.argv) > 1 and sys.argv[1] == "soiloptions":
+        soil_options_case("soilopt_28x33", 28, 33, 91)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "feeders":
         feeders_case("feeders_daily", 900, 51, 10, 86400.0, 150)
         feeders_case("feeders_6h", 600, 52, 8, 21600.0, 340)

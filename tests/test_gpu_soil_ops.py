@@ -81,3 +81,51 @@ def test_soil_columns_operator(gpu_lib, oracle, seed, drained):
     with pytest.raises(Exception):
         a2 = dict(args, is_paddy_irrig=np.array([False, False, True]))
         soilloop.soilColumnsWaterBalance(**a2)
+
+
+def test_suction_pf_operator(gpu_lib):
+    """suctionUnsaturatedSoilPF (option simulatePF) on the device: same 26 arguments as the reference's kernel; against the
+    golden made by the reference's own soilloop class, and the edge cases of saturationDegree / pressureHead."""
+    from conftest import golden_cases, load_golden
+    from lisflood_code_b200.hydrological_modules.soilloop import suctionUnsaturatedSoilPF
+    from test_oracle_soil_options_golden import LAYERS, edge_case_arguments, pf_arguments, split_golden
+    cases = golden_cases("soilopt_")
+    assert cases
+    for case in cases:
+        g = load_golden(case)
+        S, X = split_golden(g)
+        for t in range(int(g["steps"])):
+            W = [np.ascontiguousarray(g["O%d__W%s" % (t, lay)]) for lay in LAYERS]
+            a = pf_arguments(S, X, W)
+            suctionUnsaturatedSoilPF(*a)
+            for i in range(3):
+                assert rel_err(a[1 + i], g["O%d__pF%d" % (t, i)]) < 1e-12, (case, t, i)
+    a, want = edge_case_arguments()
+    suctionUnsaturatedSoilPF(*a)
+    for i in range(3):
+        assert np.array_equal(a[1 + i], want), (i, a[1 + i])
+    with pytest.raises(ValueError):
+        a[4] = a[4][:, :1]
+        suctionUnsaturatedSoilPF(*a)
+
+
+def test_model_stress_days_and_pf(gpu_lib):
+    """The option-gated extras at model level: SoilMoistureStressDays (repStressDays) and pF0..2 (simulatePF) of a
+    diagnostics model after the steps of the golden, against the reference's own soilloop class."""
+    from conftest import golden_cases, golden_model, load_golden
+    from lisflood_code_b200.hotpath import HotPathModel
+    from test_oracle_soil_options_golden import LAYERS
+    for case in golden_cases("soilopt_"):
+        S, F, O = golden_model(case)
+        X = {k[3:]: v for k, v in load_golden(case).items() if k.startswith("X__")}
+        M = HotPathModel(S, diagnostics=True)
+        for t in range(len(F)):
+            M.step(F[t])
+            rws, want = O[t]["RWS"], O[t]["SoilMoistureStressDays"]
+            assert rel_err(M.get("RWS", 3), rws) < 1e-9
+            got = M.get("SoilMoistureStressDays")
+            clear = np.abs(rws - 1) > 1e-9           # the decision RWS < 1 is not a rounding matter there
+            assert np.array_equal(got[clear], want[clear]) and (got != want).mean() < 1e-3, t
+            pf = M.suction_pf({x: X["GenuInvAlpha" + x] for x in LAYERS}, {x: X["GenuInvN" + x] for x in LAYERS}, float(X["HeadMax"]))
+            for i in range(3):
+                assert rel_err(pf[i], O[t]["pF%d" % i]) < 1e-9, (case, t, i)
