@@ -81,3 +81,20 @@ def test_soil_columns_args_layout_matches_the_header(tmp_path):
     assert out[1:] == [getattr(_capi.SoilColumnsArgs, n).offset for n in names]
     from lisflood_code_b200.hydrological_modules import soilloop
     assert len(soilloop._SOIL_ARG_ORDER) == 73
+
+
+def test_soil_pf_args_layout_matches_the_header(tmp_path):
+    """ctypes mirror of struct lf_soil_pf_args (suctionUnsaturatedSoilPF): same size and field offsets as the C header."""
+    import subprocess
+    from lisflood_code_b200 import _capi
+    names = [n for n, _ in _capi.SoilPfArgs._fields_]
+    src = tmp_path / "layout_pf.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lisflood_b200.h"\nint main(void){\n'
+                   'printf("%zu\\n", sizeof(lf_soil_pf_args));\n'
+                   + "".join('printf("%%zu\\n", offsetof(lf_soil_pf_args, %s));\n' % n for n in names)
+                   + "return 0;}\n")
+    exe = tmp_path / "layout_pf"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == C.sizeof(_capi.SoilPfArgs)
+    assert out[1:] == [getattr(_capi.SoilPfArgs, n).offset for n in names]

@@ -25,3 +25,35 @@ def test_oracle_equals_reference(oracle, rows, cols, noise, maskf, seed):
         ref.kinematicWaveRouting(Qr, q)
         ora.kinematicWaveRouting(Qo, q)
     assert rel_err(Qo, Qr) < 1e-11
+
+
+def test_pf_restatement_equals_the_reference_helpers():
+    """saturationDegree / pressureHead of the live reference (soilloop.py:379-383, :428-432), pixel by pixel, against the
+    NumPy restatement of the pF kernel: random columns plus dry, saturated, pore-less and beyond-HeadMax ones."""
+    from oracle import lisf_oracle_model as om
+    from test_oracle_soil_options_golden import edge_case_arguments
+    kwpt, kwp, sl = ref_loader.load()
+    rng = np.random.default_rng(3)
+    V, N = 3, 400
+    idx = np.array([2, 0, 1], np.int64)          # a permuted vegetation -> land use map
+    a, _ = edge_case_arguments()
+    cases = [a]
+    wres, ws = rng.uniform(2, 30, (3, N)), rng.uniform(60, 400, (3, N))
+    pore = rng.random((3, N)) > 0.05
+    W = [np.ascontiguousarray(wres[idx] + rng.uniform(-0.05, 1.05, (V, N)) * (ws[idx] - wres[idx])) for _ in range(3)]
+    gm = rng.uniform(0.08, 0.6, (3, N))
+    cases.append([idx] + [np.empty((V, N)) for _ in range(3)] + W + [wres] * 3 + [ws] * 3 + [pore] * 3
+                 + [1 / rng.uniform(0.004, 0.2, (3, N))] * 3 + [1 / gm] * 3 + [1 - gm] * 3 + [1.0e7])
+    for a in cases:
+        om.suction_unsaturated_soil_pf(*a)
+        index, pf, W = a[0], a[1:4], a[4:7]
+        wres, ws, pore, inva, invm, invn, headmax = a[7:10], a[10:13], a[13:16], a[16:19], a[19:22], a[22:25], a[25]
+        for layer in range(3):
+            want = np.empty_like(pf[layer])
+            for v in range(want.shape[0]):
+                lu = index[v]
+                for p in range(want.shape[1]):
+                    sat = sl.saturationDegree(W[layer][v, p], pore[layer][lu, p], wres[layer][lu, p], ws[layer][lu, p])
+                    head = sl.pressureHead(sat, inva[layer][lu, p], invm[layer][lu, p], invn[layer][lu, p], headmax)
+                    want[v, p] = np.log10(head) if head > 0 else -1.0
+            assert rel_err(pf[layer], want) < 1e-13, layer
