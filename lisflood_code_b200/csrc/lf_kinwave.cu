@@ -428,9 +428,13 @@ int lf_router_create(lf_graph *g, const double *alpha, double beta, const double
         if ((rc = r->a[s].alloc(n)) || (rc = r->Q[s][0].alloc(n)) || (rc = r->Q[s][1].alloc(n)) ||
             (rc = r->q[s].alloc(n)))
             return fail(rc);
-        cudaMemsetAsync(r->Q[s][0].p, 0, n * sizeof(double), st);
-        cudaMemsetAsync(r->Q[s][1].p, 0, n * sizeof(double), st);
-        cudaMemsetAsync(r->q[s].p, 0, n * sizeof(double), st);
+        cudaError_t ez = cudaMemsetAsync(r->Q[s][0].p, 0, n * sizeof(double), st);
+        if (ez == cudaSuccess) ez = cudaMemsetAsync(r->Q[s][1].p, 0, n * sizeof(double), st);
+        if (ez == cudaSuccess) ez = cudaMemsetAsync(r->q[s].p, 0, n * sizeof(double), st);
+        if (ez != cudaSuccess) {
+            lf::set_error("lf_router_create: clearing the discharge buffers failed: %s", cudaGetErrorString(ez));
+            return fail(LF_ERR_CUDA);
+        }
     }
     if (r->dx_is_array) {
         cudaError_t e = cudaMemcpyAsync(r->stage_b.p, dx, n * sizeof(double), cudaMemcpyDefault, st);
