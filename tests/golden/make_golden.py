@@ -263,6 +263,44 @@ def feeders_case(name, n, seed, steps, dt_sec, day0):
                                                                  (out["O%d__SnowCover" % (steps - 1)] > 0).mean()))
 
 
+def real_catchment_case(kwp, name, steps=6):
+    """The reference's OWN test catchment (tests/data/LF_ETRS89_UseCase/maps: 57 x 80 cells of 5 km, 2847 in the mask, one
+    outlet), read with oracle/ref_maps.py:
+      * ldd, mask, pixarea and the PCRaster-made upstream-area map ec_upArea -- the pin of global_modules/ldd_ops.py
+        (downstream_index / lddrepair at the outlet, whose link leaves the mask; accuflux);
+      * the reference's kinematicWave on that network (codes after lddmask / lddrepair, as routing.initial hands them over,
+        routing.py:90-101), channel alpha from the catchment's own geometry maps with the formulas of routing.py:184-235,
+        space_delta = its chanlength map: graph arrays and discharge snapshots."""
+    from oracle import ref_maps
+    from lisflood_code_b200.global_modules import ldd_ops
+    M = os.path.join(ref_loader._R, "..", "..", "tests", "data", "LF_ETRS89_UseCase", "maps")
+    rd = lambda f: ref_maps.read_netcdf4_2d(os.path.join(M, f + ".nc"))
+    mask = ref_maps.read_pcraster(os.path.join(M, "mask.map")) == 1
+    ldd_raw, up_area, pixarea = rd("ec_ldd"), rd("ec_upArea"), rd("pixarea")
+    codes = ldd_ops.lddrepair_codes(ldd_raw[mask].astype(np.float64), mask)
+    C = lambda f: rd(f)[mask].astype(np.float64)
+    beta = 0.6
+    grad = np.maximum(C("changrad"), 0.0001)                                   # routing.py:184 (ChanGradMin of the use case)
+    man, bw, depth, sdxdy, length = C("ec_chanman"), C("ec_chanbw"), C("ec_chanbnkf"), C("chans"), C("chanlength")
+    wetted = bw + 2 * np.sqrt(depth ** 2 + (depth * sdxdy) ** 2)                # :229-230
+    alpha = ((man / np.sqrt(grad)) ** beta * wetted ** (2.0 / 3.0 * beta)).astype(float)   # :232-235
+    n = int(mask.sum())
+    rng = np.random.default_rng(57)
+    q0 = rng.uniform(0.05, 30.0, n)
+    q = rng.uniform(0.0, 2.0e-4, n)
+    ldd2d = np.zeros(mask.shape)
+    ldd2d[mask] = codes
+    routing_case(kwp, name, mask.shape[0], mask.shape[1], 57, 0, 0, True, steps, False, beta=beta, dt=3600.0, ldd=ldd2d, mask=mask,
+                 alpha=alpha, q0=q0, q=q, dx=length)
+    path = os.path.join(HERE, name + ".npz")
+    with np.load(path) as z:
+        out = {k: z[k] for k in z.files}
+    out.update(ldd_raw=ldd_raw[mask], pixarea=pixarea[mask], upArea=up_area[mask])
+    np.savez_compressed(path, **out)
+    print(name, "outlet links leaving the mask: %d, upstream area of the outlet %.4g m2" % (
+        int(((ldd_ops.downstream_index(ldd_raw[mask], mask) < 0) & (ldd_raw[mask] != 5)).sum()), up_area[mask].max()))
+
+
 def soil_options_case(name, rows, cols, seed, steps=2):
     """The option-gated extras of soilloop.dynamic_soil, executed by the reference's OWN class with the options switched on:
     repStressDays (SoilMoistureStressDays, soilloop.py:597-598) and simulatePF (the nested Numba kernel
@@ -304,6 +342,10 @@ def soil_options_case(name, rows, cols, seed, steps=2):
 def main():
     import warnings
     warnings.simplefilter("ignore")
+    if len(sys.argv) > 1 and sys.argv[1] == "realcatchment":
+        kwpt, kwp, sl = ref_loader.load()
+        real_catchment_case(kwp, "kwreal_etrs89_57x80")
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "soiloptions":
         soil_options_case("soilopt_28x33", 28, 33, 91)
         return

@@ -25,7 +25,10 @@ def _kw(gpu_lib):
     return kinematicWave
 
 
-@pytest.mark.parametrize("case", golden_cases("kw_"))
+KW_CASES = golden_cases("kw_") + golden_cases("kwreal_")    # kwreal_: the reference's own test catchment (57 x 80, 2847 px)
+
+
+@pytest.mark.parametrize("case", KW_CASES)
 def test_golden_graph_bit_exact(gpu_lib, case):
     g = load_golden(case)
     kw = _kw(gpu_lib)(g["ldd"], g["mask"], g["alpha"], float(g["beta"]), _dx(g), float(g["dt"]))
@@ -35,7 +38,7 @@ def test_golden_graph_bit_exact(gpu_lib, case):
         assert np.array_equal(got, g[k]), k
 
 
-@pytest.mark.parametrize("case", golden_cases("kw_"))
+@pytest.mark.parametrize("case", KW_CASES)
 def test_golden_routing(gpu_lib, case):
     g = load_golden(case)
     a2 = g.get("alpha2")

@@ -12,7 +12,10 @@ def _dx(g):
     return g["dx"] if g["dx"].ndim else float(g["dx"])
 
 
-@pytest.mark.parametrize("case", golden_cases("kw_"))
+KW_CASES = golden_cases("kw_") + golden_cases("kwreal_")    # kwreal_: the reference's own test catchment (57 x 80, 2847 px)
+
+
+@pytest.mark.parametrize("case", KW_CASES)
 def test_graph_bit_exact(oracle, case):
     g = load_golden(case)
     kw = oracle.KinematicWaveOracle(g["ldd"], g["mask"], g["alpha"], float(g["beta"]), _dx(g), float(g["dt"]))
@@ -22,7 +25,7 @@ def test_graph_bit_exact(oracle, case):
         assert np.array_equal(got, g[k]), k
 
 
-@pytest.mark.parametrize("case", golden_cases("kw_"))
+@pytest.mark.parametrize("case", KW_CASES)
 def test_routing_matches_reference(oracle, case):
     g = load_golden(case)
     a2 = g.get("alpha2")
@@ -77,3 +80,26 @@ def test_bad_section_and_bad_codes(oracle):
     cyc = np.array([[6.0, 4.0]])
     with pytest.raises(ValueError):
         oracle.KinematicWaveOracle(cyc.ravel(), np.ones((1, 2), bool), np.ones(2), 0.6, 1000.0, 3600.0)
+
+
+@pytest.mark.parametrize("case", golden_cases("kwreal_"))
+def test_ldd_operators_on_the_reference_catchment(case):
+    """global_modules/ldd_ops.py against PCRaster's own products for the reference's test catchment: the upstream-area
+    map ec_upArea = accuflux(ldd, pixarea), bit for bit; the one link that leaves the mask (the outlet) becomes a pit
+    (lddmask / lddrepair), every other code is kept."""
+    from lisflood_code_b200.global_modules import ldd_ops
+    g = load_golden(case)
+    mask, raw = g["mask"], g["ldd_raw"].astype(np.float64)
+    ds = ldd_ops.downstream_index(raw, mask)
+    leaving = (ds < 0) & (raw != 5)
+    assert leaving.sum() == 1 and g["upArea"][leaving][0] == g["upArea"].max()
+    assert np.array_equal(ldd_ops.accuflux(ds, g["pixarea"].astype(np.float64)), g["upArea"])
+    repaired = ldd_ops.lddrepair_codes(raw, mask)
+    assert np.array_equal(repaired, g["ldd"]) and np.array_equal(repaired[~leaving], raw[~leaving]) and repaired[leaving][0] == 5
+    order, hops = ldd_ops.topological_order(ds)
+    assert hops[leaving][0] == 0 and hops.max() + 1 == g["order_start_stop"].shape[0]     # as deep as the reference's ordering
+    rank = np.empty(order.size, np.int64)
+    rank[order] = np.arange(order.size)
+    assert (rank[ds >= 0] < rank[ds[ds >= 0]]).all()                    # every pixel before its downstream pixel
+    assert np.array_equal(ldd_ops.catchment_of_pits(ds), np.ones(ds.size, np.int64))    # one basin
+    assert np.array_equal(ldd_ops.upstream_sum(ds, g["upArea"]) + g["pixarea"], g["upArea"])   # upArea = own area + upstream(upArea)
