@@ -27,7 +27,7 @@ class LisSettings(object):
     def __init__(self, settings_file, sys_args=()):
         dom = xml.dom.minidom.parse(settings_file)
         self.settings_path = os.path.abspath(settings_file)
-        self.settings_dir = os.path.dirname(self.settings_path)
+        self.settings_dir = os.path.normpath(os.path.dirname(self.settings_path))
         self.flags = self._flags(sys_args)
         self.options = self._options(dom)
         self.user, self.binding = self._bindings(dom)
@@ -62,7 +62,9 @@ class LisSettings(object):
         return options
 
     def _bindings(self, dom):
-        user = {"SettingsDir": self.settings_dir, "SettingsPath": self.settings_dir}
+        project_dir = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))   # settings.py:46
+        user = {"ProjectDir": project_dir, "ProjectPath": project_dir,
+                "SettingsDir": self.settings_dir, "SettingsPath": self.settings_dir}
         for el in dom.getElementsByTagName("lfuser"):
             for t in el.getElementsByTagName("textvar"):
                 user[t.attributes["name"].value] = str(t.attributes["value"].value)
@@ -81,6 +83,8 @@ class LisSettings(object):
                 expr = expr.replace(expr[a1:a2 + 1], user[name])
                 guard += 1
             binding[k] = expr
+        if "CalendarConvention" in binding:
+            binding["calendar_type"] = binding["CalendarConvention"]      # settings.py:562
         return user, binding
 
     def check_supported(self):
