@@ -35,12 +35,18 @@ def load():
     global _mod
     if _mod is not None:
         return _mod
-    if "future" not in sys.modules:
-        fb = _stub("future.backports", OrderedDict=OrderedDict)
-        fu = _stub("future.utils", with_metaclass=lambda meta, *bases: meta("NewBase", bases or (object,), {}))
-        _stub("future", backports=fb, utils=fu)
-    if "nine" not in sys.modules:
-        _stub("nine", iteritems=lambda d: d.items(), str=str, range=range, map=map, nine=lambda c: c)
+    def ensure(name, **attrs):        # other harness modules may have installed barer stand-ins already: complete them
+        m = sys.modules.get(name)
+        if m is None:
+            return _stub(name, **attrs)
+        for k, v in attrs.items():
+            if not hasattr(m, k):
+                setattr(m, k, v)
+        return m
+    fb = ensure("future.backports", OrderedDict=OrderedDict)
+    fu = ensure("future.utils", with_metaclass=lambda meta, *bases: meta("NewBase", bases or (object,), {}))
+    ensure("future", backports=fb, utils=fu)
+    ensure("nine", iteritems=lambda d: d.items(), str=str, range=range, map=map, nine=lambda c: c)
     for n in ("pcraster", "netCDF4", "cftime"):
         if n not in sys.modules:
             sys.modules[n] = _Unavailable(n)

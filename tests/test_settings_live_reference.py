@@ -11,6 +11,15 @@ from oracle import ref_loader
 pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
 
 
+@pytest.fixture(autouse=True)
+def _keep_the_settings_singleton():
+    """LisSettings(...) registers itself as the run's settings object: put back what was there."""
+    from lisflood_code_b200.global_modules.settings import LisSettings
+    before = LisSettings._instance
+    yield
+    LisSettings._instance = before
+
+
 def _shipped_settings():
     if not ref_loader.available():
         return []
