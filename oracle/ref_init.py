@@ -289,3 +289,47 @@ def structures_initial(land_mask, raw, tables, state, options=None, DtSec=86400.
         if isinstance(v, np.ndarray) and v.dtype.kind in "fiub":
             out[k] = np.squeeze(np.asarray(v)) if v.ndim == 2 and v.shape[0] == 1 else np.asarray(v)
     return out
+
+
+def misc_and_landuse_initial(land_mask, raw, options=None, cell=None):
+    """Outputs of the reference's miscInitial.initial() (hydrological_modules/miscInitial.py:44-133) followed by
+    landusechange.initial() (landusechange.py:53-93, static maps).  options['gridSizeUserDefined'] chooses between the
+    'PixelLengthUser' / 'PixelAreaUser' inputs and the cell size of the mask map (`cell`, what MaskAttrs holds)."""
+    import types
+    M, loadmap = _install(raw, land_mask)
+    opts = dict(options or {})
+    st = sys.modules["lisflood.global_modules.settings"]
+
+    class _MaskAttrs(object):
+        @classmethod
+        def instance(cls):
+            return {"cell": cell}
+    st.MaskAttrs, st.calendar = _MaskAttrs, (lambda date, calendar_type: date)
+    if "lisflood.global_modules.netcdf" not in sys.modules:
+        sys.modules["lisflood.global_modules.netcdf"] = types.ModuleType("lisflood.global_modules.netcdf")
+        setattr(sys.modules["lisflood.global_modules"], "netcdf", sys.modules["lisflood.global_modules.netcdf"])
+    n_pix = int(np.asarray(land_mask).sum())
+    sys.modules["lisflood.global_modules.netcdf"].read_lat_from_template = lambda binding: np.asarray(
+        raw.get("lat_deg", np.zeros(n_pix)), np.float64)
+    ref_modules._FakeSettings.instance().binding.update(CalendarDayStart="01/01/1990", calendar_type="proleptic_gregorian")
+    pcr = sys.modules["pcraster"]
+    pcr.celllength, pcr.scalar = (lambda: cell), (lambda x: x)
+    add1 = sys.modules["lisflood.global_modules.add1"]
+    from lisflood_code_b200.global_modules.add1 import NumpyModified
+    # (a writable copy: with today's pandas, DataFrame.T.values is read-only and the reference assigns into it)
+    add1.loadmap, add1.compressArray, add1.NumpyModified, add1.readnetcdf = loadmap, (lambda m, *a, **k: np.asarray(m).copy()), \
+        (lambda a, dims=None: NumpyModified(np.array(a), dims)), None
+    epic = ref_modules._EPIC.instance()
+    epic.landuse_inputmap = OrderedDict(zip(epic.landuse_vegetation.keys(), ["OtherFraction", "ForestFraction",
+                                                                               "IrrigationFraction"]))   # settings.py:343-345
+    mods = {}
+    for name in ("miscInitial", "landusechange"):
+        mods[name] = ref_modules.ref_loader._load_module("lisflood.hydrological_modules." + name,
+                                                         ref_modules._R + "/hydrological_modules/%s.py" % name)
+    var = _InitVar(land_mask, raw, loadmap, opts, 0.0, 0.0)
+    del var.DtSec, var.DtSecChannel, var.DtDay           # miscInitial sets them from the bindings
+    var.coord_prescribed_vegetation = OrderedDict([("vegetation", var.prescribed_vegetation[:]), var.dim_pixel])
+    before = set(var.__dict__)
+    mods["miscInitial"].miscInitial(var).initial()
+    mods["landusechange"].landusechange(var).initial()
+    return {k: v for k, v in _collect(var).items() if k not in before}

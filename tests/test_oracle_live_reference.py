@@ -57,3 +57,35 @@ def test_pf_restatement_equals_the_reference_helpers():
                     head = sl.pressureHead(sat, inva[layer][lu, p], invm[layer][lu, p], invn[layer][lu, p], headmax)
                     want[v, p] = np.log10(head) if head > 0 else -1.0
             assert rel_err(pf[layer], want) < 1e-13, layer
+
+
+@pytest.mark.parametrize("user_grid", [True, False])
+def test_misc_and_landuse_initial_equal_the_reference(user_grid):
+    """miscInitial.initial() (grid size, unit multipliers, groundwater percolation / loss per step) and
+    landusechange.initial() (fraction maps -> SoilFraction) of the live reference against the host mirrors
+    (Lisflood_initial.InitialVariables.misc_initial / landuse_initial), attribute by attribute, bit for bit."""
+    from lisflood_code_b200.Lisflood_initial import InitialVariables
+    from oracle import ref_init
+    rng = np.random.default_rng(12)
+    mask = rng.random((9, 11)) > 0.2
+    n = int(mask.sum())
+    fr = rng.dirichlet([4, 3, 1, 0.6, 0.3, 0.2], n).T
+    raw = {"DtSec": 21600.0, "DtSecChannel": 3600.0, "GwLoss": 0.05, "GwPercValue": rng.uniform(0.0, 1.5, n),
+           "PrScaling": 1.0, "CalEvaporation": 1.0}
+    raw.update({k + "Fraction": fr[i] for i, k in enumerate(("Other", "Forest", "Irrigation", "DirectRunoff", "Water", "Rice"))})
+    if user_grid:
+        raw.update(PixelLengthUser=rng.uniform(900.0, 1100.0, n), PixelAreaUser=rng.uniform(0.9e6, 1.1e6, n))
+    else:
+        raw.update(PixelLengthUser=5000.0)       # the mirror takes the cell size from this input in both modes
+    want = ref_init.misc_and_landuse_initial(mask, raw, {"gridSizeUserDefined": user_grid}, cell=5000.0)
+    var = InitialVariables(mask, raw, {"gridSizeUserDefined": user_grid}, DtSec=raw["DtSec"], DtSecChannel=raw["DtSecChannel"])
+    var.misc_initial()
+    var.landuse_initial()
+    checked = 0
+    for k in ("PixelLength", "PixelArea", "InvPixelLength", "DtSec", "DtDay", "InvDtSec", "InvDtDay", "DtSecChannel", "MMtoM",
+              "MtoMM", "MMtoM3", "M3toMM", "GwLoss", "GwPerc", "GwPercStep", "GwLossStep", "ForestFraction",
+              "DirectRunoffFraction", "WaterFraction", "IrrigationFraction", "RiceFraction", "OtherFraction", "SoilFraction"):
+        got = np.asarray(getattr(var, k), np.float64)
+        assert np.array_equal(np.broadcast_to(got, np.shape(want[k])), want[k]), k
+        checked += 1
+    assert checked == 23
