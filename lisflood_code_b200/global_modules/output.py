@@ -80,7 +80,9 @@ class TssWriter(object):
     """zusatz.py:201-297: header (spatial datatype, settings file, date; number of columns; 'timestep'; the gauge ids),
     then one row per step: ' %8g' for the step and ' %14g' per gauge."""
 
-    def __init__(self, path, gauge_pixels, gauge_ids=None, settings_path="", datatype="scalar", header=True):
+    def __init__(self, path, gauge_pixels, gauge_ids=None, settings_path="", datatype="valuescale.scalar", header=True):
+        # datatype: str(pcraster data type).lower() of the gauge map's values; "valuescale.scalar" is what the .tss files
+        # shipped with the reference carry (tests/data/*/reference/*/dis.tss)
         self.pix = np.asarray(gauge_pixels, np.int64)
         ids = np.arange(1, self.pix.size + 1) if gauge_ids is None else np.asarray(gauge_ids)
         self.f = open(path, "w")

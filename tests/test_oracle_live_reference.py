@@ -89,3 +89,39 @@ def test_misc_and_landuse_initial_equal_the_reference(user_grid):
         assert np.array_equal(np.broadcast_to(got, np.shape(want[k])), want[k]), k
         checked += 1
     assert checked == 23
+
+
+def _shipped_tss():
+    import glob
+    import os
+    if not ref_loader.available():
+        return []
+    root = os.path.normpath(os.path.join(ref_loader._R, "..", ".."))
+    return sorted(glob.glob(os.path.join(root, "tests", "data", "*", "reference", "*", "*.tss")))
+
+
+@pytest.mark.parametrize("path", _shipped_tss(), ids=lambda p: "/".join(p.split("/")[-3:]))
+def test_tss_writer_reproduces_the_shipped_time_series(path, tmp_path):
+    """TssWriter (global_modules/output.py) fed with the numbers of a .tss file the reference ships writes that file back
+    byte for byte (header layout, column ids, ' %8g' / ' %14g' rows; zusatz.py:201-290) -- except the date stamp."""
+    from lisflood_code_b200.global_modules.output import TssWriter
+    text = open(path).read()
+    lines = text.split("\n")
+    head = lines[0]
+    assert head.startswith("timeseries ") and " settingsfile: " in head and " date: " in head
+    datatype = head.split(" ")[1]
+    settings_path = head.split(" settingsfile: ")[1].split(" date: ")[0]
+    ncols = int(lines[1])
+    assert lines[2] == "timestep"
+    ids = lines[3:3 + ncols - 1]
+    rows = [ln for ln in lines[3 + ncols - 1:] if ln]
+    out = tmp_path / "copy.tss"
+    w = TssWriter(str(out), np.arange(ncols - 1), gauge_ids=ids, settings_path=settings_path, datatype=datatype)
+    for ln in rows:
+        f = ln.split()
+        w.append(int(f[0]), np.array([float(x) for x in f[1:]]))
+    w.close()
+    mine = open(out).read().split("\n")
+    assert mine[0].split(" date: ")[0] == head.split(" date: ")[0]
+    assert mine[1:] == lines[1:]
+    assert datatype == "valuescale.scalar"          # the writer's default
