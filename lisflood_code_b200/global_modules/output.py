@@ -78,7 +78,10 @@ class MapStackWriter(object):
 
 class TssWriter(object):
     """zusatz.py:201-297: header (spatial datatype, settings file, date; number of columns; 'timestep'; the gauge ids),
-    then one row per step: ' %8g' for the step and ' %14g' per gauge."""
+    then one row per step: ' %8g' for the step and ' %14g' per gauge.  The reference samples the gauges from a PCRaster
+    scalar map (REAL4: pcraster.cellvalue, zusatz.py:340-378), so the printed numbers are the float32-rounded values --
+    all 11 190 numbers of the shipped init_daily/dis.tss equal '%g' of the float32-rounded dis.nc values, and 29 of 30
+    gauges differ in a last digit somewhere without the rounding; it is applied here too."""
 
     def __init__(self, path, gauge_pixels, gauge_ids=None, settings_path="", datatype="valuescale.scalar", header=True):
         # datatype: str(pcraster data type).lower() of the gauge map's values; "valuescale.scalar" is what the .tss files
@@ -96,7 +99,7 @@ class TssWriter(object):
     def append(self, step, values):
         row = " %8g" % step
         for v in np.asarray(values)[self.pix]:
-            row += " %14g" % v
+            row += " %14g" % np.float32(v)
         self.f.write(row + "\n")
 
     def close(self):

@@ -95,5 +95,6 @@ def prerun_products(M, steps, DtDay):
 
 
 def tss_line(values):
-    """One line of a PCRaster .tss time series as the reference writes it (6 significant digits)."""
-    return " ".join("%.6g" % v for v in values)
+    """One line of a PCRaster .tss time series as the reference writes it: 6 significant digits of the float32-rounded
+    values (the gauges are sampled from a REAL4 PCRaster map; global_modules/output.py::TssWriter)."""
+    return " ".join("%.6g" % np.float32(v) for v in values)

@@ -64,7 +64,7 @@ def test_output_pipeline_equals_synchronous_run(gpu_lib, tmp_path):
     for k in range(steps):
         assert np.array_equal(data[k][mask], want[k]), k
     rows = open(tmp_path / "dis.tss").read().splitlines()[4 + gauges.size - 1:]
-    assert rows[-1] == " %8g" % steps + "".join(" %14g" % v for v in want[-1][gauges])
+    assert rows[-1] == " %8g" % steps + "".join(" %14g" % np.float32(v) for v in want[-1][gauges])   # REAL4 sampling
 
 
 def test_packed_forcing_and_float32_output(gpu_lib, tmp_path):

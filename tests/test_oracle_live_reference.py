@@ -125,3 +125,69 @@ def test_tss_writer_reproduces_the_shipped_time_series(path, tmp_path):
     assert mine[0].split(" date: ")[0] == head.split(" date: ")[0]
     assert mine[1:] == lines[1:]
     assert datatype == "valuescale.scalar"          # the writer's default
+
+
+def _shipped_runs():
+    import glob
+    import os
+    if not ref_loader.available():
+        return []
+    root = os.path.normpath(os.path.join(ref_loader._R, "..", ".."))
+    return [d for d in sorted(glob.glob(os.path.join(root, "tests", "data", "LF_ETRS89_UseCase", "reference", "*")))
+            if os.path.exists(os.path.join(d, "dis.nc")) and os.path.exists(os.path.join(d, "dis.tss"))]
+
+
+@pytest.mark.parametrize("run", _shipped_runs(), ids=lambda p: p.split("/")[-1])
+def test_shipped_map_stack_against_time_series_and_writer(run, tmp_path):
+    """(1) The NetCDF-4 reader of the test harness (oracle/ref_maps.py) is exact: every number of the run's dis.tss is
+    '%g' of the float32-rounded value of dis.nc at the gauge pixel (the reference samples gauges from a REAL4 PCRaster map).
+    (2) MapStackWriter writes the reference's map stack: same dimensions, coordinate order, fill value, variable
+    attributes, calendar and time axis (netcdf.py:432-583); fed with the maps of the shipped dis.nc it gives them back."""
+    import datetime
+    import os
+    from scipy.io import netcdf_file
+    from lisflood_code_b200.global_modules.output import MapStackWriter
+    from oracle import ref_maps
+    f = ref_maps.H5File(os.path.join(run, "dis.nc"))
+    links = f.links()
+    dis_info, time_info = f.dataset(links["dis"]), f.dataset(links["time"])
+    dis, time = f.read(dis_info), f.read(time_info)
+    maps = os.path.normpath(os.path.join(run, "..", "..", "maps"))
+    outlets = ref_maps.read_netcdf4_2d(os.path.join(maps, "ec_outlets.nc"))
+    mask = ref_maps.read_pcraster(os.path.join(maps, "mask.map")) == 1
+    lines = open(os.path.join(run, "dis.tss")).read().split("\n")
+    ncols = int(lines[1])
+    ids = [int(x) for x in lines[3:3 + ncols - 1]]
+    rows = [ln.split() for ln in lines[3 + ncols - 1:] if ln]
+    assert len(rows) == dis.shape[0]
+    table = np.array([[float(x) for x in r[1:]] for r in rows])
+    for j, gauge in enumerate(ids):
+        (r, c), = np.argwhere(outlets == gauge)
+        assert np.array_equal(np.array([float("%g" % np.float32(v)) for v in dis[:, r, c]]), table[:, j]), gauge
+    # ---- the writer against this file
+    a = dis_info["attrs"]
+    assert float(a["_FillValue"]) == -9999.0 and (dis[:, ~mask] == -9999.0).all() and (dis[:, mask] != -9999.0).all()
+    units = time_info["attrs"]["units"]
+    kind, stamp = units.split(" since ")
+    start = datetime.datetime.strptime(stamp, "%Y-%m-%d %H:%M:%S.0")
+    dt_sec = {"days": 86400.0, "hours": 3600.0}[kind] * float(time[1] - time[0])
+    x, y = f.read(f.dataset(links["x"])), f.read(f.dataset(links["y"]))
+    assert (np.diff(y) < 0).all() and (np.diff(x) > 0).all()            # y descending, x ascending
+    path = str(tmp_path / "dis_copy.nc")
+    w = MapStackWriter(path, "dis", mask, dt_sec, start, a["standard_name"], a["long_name"], a["units"], x=x, y=y,
+                       calendar=time_info["attrs"]["calendar"])
+    nsteps = min(dis.shape[0], 12)
+    for k in range(nsteps):           # step k + 1 after the start date of the time axis carries time[k]
+        w.append(int(round(time[k] * {"days": 86400.0, "hours": 3600.0}[kind] / dt_sec)) + 1, dis[k][mask])
+    w.close()
+    nc = netcdf_file(path, "r", mmap=False)
+    v, t = nc.variables["dis"], nc.variables["time"]
+    assert t.units.decode() == units and t.calendar.decode() == time_info["attrs"]["calendar"]
+    assert t.standard_name.decode() == time_info["attrs"]["standard_name"]
+    assert np.array_equal(t[:], time[:nsteps])
+    assert v.dimensions == ("time", "y", "x") and v.shape[1:] == dis.shape[1:]
+    assert np.array_equal(v[:], dis[:nsteps]) and float(v._FillValue) == -9999.0
+    for k in ("standard_name", "long_name", "units"):
+        assert getattr(v, k).decode() == a[k], k
+    assert np.array_equal(nc.variables["x"][:], x) and np.array_equal(nc.variables["y"][:], y)
+    nc.close()
