@@ -35,14 +35,15 @@ def lddrepair_codes(ldd_codes, land_mask):
 
 def lddmask_codes(ldd_codes, keep, land_mask=None):
     """lddmask(ldd, keep): codes where `keep`, 0 (missing value -> isolated pit in kinematicWave,
-    kinematic_wave_parallel.py:68) elsewhere.  With `land_mask`, kept cells that drain into a dropped cell become
-    pits (PCRaster keeps the result a sound ldd)."""
+    kinematic_wave_parallel.py:68) elsewhere.  With `land_mask`, kept cells that drain into a dropped cell, or out of
+    the map / the mask, become pits (PCRaster keeps the result a sound ldd)."""
     codes = np.asarray(ldd_codes, np.float64)
     keep = np.asarray(keep, bool)
     out = np.where(keep, codes, 0.0)
     if land_mask is not None:
         ds = downstream_index(codes, land_mask)
         cut = keep & (ds >= 0) & ~keep[np.maximum(ds, 0)]
+        cut |= keep & (ds < 0) & (codes != 5) & (codes != 0)
         out[cut] = 5.0
     return out
 

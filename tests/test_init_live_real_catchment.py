@@ -1,0 +1,42 @@
+"""Init-time parameter derivation on the REAL inputs of the reference's own test catchment (tests/data/LF_ETRS89_UseCase:
+65 maps + 39 scalars by binding name, through the settings XML the reference ships): the reference's OWN soil.initial(),
+routing.initial() / initialSecond(), surface_routing.initial() and groundwater.initial() (oracle/ref_init.py) against the
+host mirrors, bit for bit, single and split routing.  Only where /root/reference exists (the build container)."""
+import numpy as np
+import pytest
+
+from oracle import ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_initial_on_the_reference_use_case(split):
+    from lisflood_code_b200.Lisflood_initial import InitialVariables
+    from oracle import ref_init, ref_usecase
+    from test_init_golden import _build, compare_with_reference
+    mask, raw, binding = ref_usecase.load_inputs("base.xml")
+    n = int(mask.sum())
+    assert n == 2847 and sum(np.ndim(v) > 0 for v in raw.values()) >= 60
+    dt_sec = raw["DtSec"]
+    opts = {"SplitRouting": split, "drainedIrrigation": split, "gridSizeUserDefined": True}
+    # what miscInitial / landusechange leave behind (mirrors pinned in tests/test_oracle_live_reference.py)
+    v0 = InitialVariables(mask, raw, opts, DtSec=dt_sec, DtSecChannel=raw["DtSecChannel"])
+    v0.misc_initial()
+    v0.landuse_initial()
+    state = {k: np.asarray(getattr(v0, k)) for k in ("SoilFraction", "RiceFraction", "WaterFraction", "OtherFraction",
+                                                     "IrrigationFraction", "ForestFraction", "DirectRunoffFraction", "PixelArea")}
+    g = {"mask": mask, "DtSec": np.float64(dt_sec), "SplitRouting": np.bool_(split)}
+    g.update({"raw__" + k: np.asarray(v) for k, v in raw.items()})
+    g.update({"state__" + k: v for k, v in state.items()})
+    soil_state = {k: v for k, v in state.items() if k != "PixelArea"}
+    g.update({"soil__" + k: v for k, v in ref_init.soil_initial(mask, raw, soil_state, opts, DtSec=dt_sec).items()})
+    g.update({"routing__" + k: v for k, v in ref_init.routing_initial(mask, raw, {"PixelArea": state["PixelArea"]}, opts,
+                                                                      DtSec=dt_sec, DtSecChannel=raw["DtSecChannel"]).items()})
+    gwloss = np.zeros(n) + raw["GwLoss"]
+    st2 = {"PixelLength": raw["PixelLengthUser"], "InvPixelLength": 1.0 / raw["PixelLengthUser"], "MMtoM": 0.001,
+           "NManning": g["soil__NManning"], "Beta": g["routing__Beta"], "InvBeta": g["routing__InvBeta"],
+           "AlpPow": g["routing__AlpPow"], "GwLoss": gwloss, "GwPerc": np.maximum(raw["GwPercValue"], gwloss)}
+    g.update({"surfgw__" + k: v for k, v in ref_init.surface_and_groundwater_initial(mask, raw, st2, opts, DtSec=dt_sec).items()})
+    checked = compare_with_reference(*_build(None, g))
+    assert checked >= 140

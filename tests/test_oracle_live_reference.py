@@ -191,3 +191,18 @@ def test_shipped_map_stack_against_time_series_and_writer(run, tmp_path):
         assert getattr(v, k).decode() == a[k], k
     assert np.array_equal(nc.variables["x"][:], x) and np.array_equal(nc.variables["y"][:], y)
     nc.close()
+
+
+def test_input_files_keys_equal_the_reference_classes():
+    """Every HydroModule mirror declares the inputs (binding names per option) its reference class declares; the dynamic
+    wave (out of scope) is the only option left out."""
+    from lisflood_code_b200.hydrological_modules import (groundwater, lakes, opensealed, reservoir, routing, soil, soilloop,
+                                                         surface_routing)
+    from oracle import ref_modules
+    M = ref_modules.load()
+    for name, mirror in (("soil", soil.soil), ("routing", routing.routing), ("groundwater", groundwater.groundwater),
+                         ("surface_routing", surface_routing.surface_routing), ("soilloop", soilloop.soilloop),
+                         ("opensealed", opensealed.opensealed), ("reservoir", reservoir.reservoir), ("lakes", lakes.lakes)):
+        want = {k: sorted(v) for k, v in M[name].input_files_keys.items() if k != "dynamicWave"}
+        assert {k: sorted(v) for k, v in mirror.input_files_keys.items()} == want, name
+        assert mirror.module_name == M[name].module_name, name
