@@ -206,3 +206,24 @@ def test_input_files_keys_equal_the_reference_classes():
         want = {k: sorted(v) for k, v in M[name].input_files_keys.items() if k != "dynamicWave"}
         assert {k: sorted(v) for k, v in mirror.input_files_keys.items()} == want, name
         assert mirror.module_name == M[name].module_name, name
+
+
+def test_end_maps_table_equals_the_reference_report_table():
+    """state_io.END_MAPS against the reference's own table of reported maps (global_modules/default_options.py): every end
+    map of the hot-path state is an entry reported with option repEndMaps, from the same model attribute (and row), with the
+    same option gating; and no end map of a hot-path state variable is missing."""
+    from lisflood_code_b200 import state_io
+    from oracle import ref_settings
+    ref_settings.load()
+    import sys
+    table = sys.modules["lisflood_ref_settings.global_modules.default_options"].default_options["reportedmaps"]
+    for name, (binding, attr, row) in state_io.END_MAPS.items():
+        entry = table[name]
+        assert entry.end == ["repEndMaps"], name
+        assert entry.output_var == (attr if row is None else "%s[%d]" % (attr, row)), (name, entry.output_var)
+        assert ("SplitRouting" in entry.restrictoption) == (name in state_io.SPLIT_ONLY), name
+    mine = {(attr if row is None else "%s[%d]" % (attr, row)) for _, attr, row in state_io.END_MAPS.values()}
+    hot_path_state = ("Theta", "UZ", "LZ", "DSLR", "CumInter", "OFM3", "TotalCrossSectionArea", "ChanQ", "CrossSection2Area",
+                      "Sideflow1Chan", "SnowCoverS", "FrostIndex")
+    others = {e.output_var for e in table.values() if e.end == ["repEndMaps"] and e.output_var.startswith(hot_path_state)}
+    assert others <= mine, others - mine
