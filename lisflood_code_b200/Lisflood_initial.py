@@ -58,6 +58,10 @@ class InitialVariables(object):
         self.GwPerc = np.maximum(self.loadmap('GwPercValue'), self.GwLoss)
         self.GwPercStep = self.GwPerc * self.DtDay
         self.GwLossStep = self.GwLoss * self.DtDay
+        if self._has('PrScaling'):                       # miscInitial.py:142-143 (read by the feeder kernel)
+            self.PrScaling = self.loadmap('PrScaling')
+        if self._has('CalEvaporation'):
+            self.CalEvaporation = self.loadmap('CalEvaporation')
 
     def landuse_initial(self):
         """Land-use fractions (reference: hydrological_modules/landusechange.py:53-93, static maps): SoilFraction rows =

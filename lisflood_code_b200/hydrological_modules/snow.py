@@ -64,6 +64,24 @@ class snow(HydroModule):
     def __init__(self, snow_variable):
         self.var = snow_variable
 
+    def initial(self):
+        """snow.py:53-93 on the host init object (lisflood_code_b200.Lisflood_initial.InitialVariables): parameters and the
+        snow cover of the three elevation zones (-> HotPathModel.set_feeder through feeder_arguments below)."""
+        v = self.var
+        v.DeltaTSnow = 0.9674 * v.loadmap('ElevationStD') * v.loadmap('TemperatureLapseRate')   # :57
+        v.SnowDayDegrees = SNOW_DAY_DEGREES
+        v.IceDayDegrees = ICE_DAY_DEGREES
+        v.SnowSeason = v.loadmap('SnowSeasonAdj') * 0.5                                         # :74
+        v.TempSnow = v.loadmap('TempSnow')
+        v.SnowFactor = v.loadmap('SnowFactor')
+        v.SnowMeltCoef = v.loadmap('SnowMeltCoef')
+        v.TempMelt = v.loadmap('TempMelt')
+        init = [v.loadmap('SnowCover%sInitValue' % z) for z in "ABC"]
+        v.SnowCoverS = init
+        v.SnowCoverInit = (init[0] + init[1] + init[2]) / 3                                     # :88
+        for k in ("SnowCover", "Snow", "Rain", "SnowMelt"):
+            setattr(v, k, v.maskinfo.in_zero())
+
     def dynamic(self):
         pending = self.var.__dict__.pop("_raw_meteo", None)
         if pending is None:
@@ -80,6 +98,16 @@ class frost(HydroModule):
     def __init__(self, frost_variable):
         self.var = frost_variable
 
+    def initial(self):
+        """frost.py:44-58 on the host init object."""
+        v = self.var
+        v.Kfrost = v.loadmap('Kfrost')
+        v.Afrost = v.loadmap('Afrost')
+        v.FrostIndexThreshold = v.loadmap('FrostIndexThreshold')
+        v.SnowWaterEquivalent = v.loadmap('SnowWaterEquivalent')
+        v.FrostIndex = v.loadmap('FrostIndexInitValue')
+        v.isFrozenSoil = v.FrostIndex > v.FrostIndexThreshold
+
     def dynamic(self):
         if not self.var.__dict__.pop("_frost_pending", False):
             raise RuntimeError("frost.dynamic before snow.dynamic of this step (Lisflood_dynamic.py:102-105)")
@@ -93,6 +121,14 @@ class leafarea(HydroModule):
         self.var = leafarea_variable
         self._interval = None
 
+    def initial(self):
+        """leafarea.py:44-72 on the host init object: extinction coefficient and the calendar-day -> interval lookup (the
+        36 prescribed LAI maps per fraction are handed to dynamic() by the caller: map IO is out of scope)."""
+        v = self.var
+        v.kgb = 0.75 * v.loadmap('kdf')                                                        # :48
+        v.L1 = [lai_interval(i) for i in range(367)]                                           # :63-69
+        v.LAI = v.allocateVariableAllVegetation()                                              # :71
+
     def dynamic(self, calendar_day, lai_of_interval):
         """lai_of_interval(j) -> (3, N) LAI maps (Rainfed, Forest, Irrigated prescribed fractions) of interval j; called
         only when the interval changes (the maps then stay resident on the device, with LAITerm = exp(-kgb LAI))."""
@@ -100,3 +136,15 @@ class leafarea(HydroModule):
         if j != self._interval:
             self.var.set_lai(lai_of_interval(j))
             self._interval = j
+
+
+def feeder_arguments(var, lat_rad):
+    """(parameters, initial state) for HotPathModel.set_feeder from a host init object on which miscInitial (PrScaling,
+    CalEvaporation: miscInitial.py:142-143), snow.initial, frost.initial and leafarea.initial have run; lat_rad: latitude
+    of the pixels [rad] (miscInitial.py:183-184 reads it from the NetCDF template)."""
+    n = var.num_pixel
+    full = lambda x: np.zeros(n) + x
+    P = {k: getattr(var, k) for k in FEEDER_PARAMETERS if k != "lat_rad"}
+    P["lat_rad"] = np.asarray(lat_rad, np.float64)
+    state = {"SnowCoverS": np.stack([full(x) for x in var.SnowCoverS]), "FrostIndex": full(var.FrostIndex)}
+    return P, state

@@ -333,3 +333,50 @@ def misc_and_landuse_initial(land_mask, raw, options=None, cell=None):
     mods["miscInitial"].miscInitial(var).initial()
     mods["landusechange"].landusechange(var).initial()
     return {k: v for k, v in _collect(var).items() if k not in before}
+
+
+def feeders_initial(land_mask, raw, options=None):
+    """Outputs of the reference's snow.initial() (hydrological_modules/snow.py:53-93), frost.initial() (frost.py:44-58) and
+    leafarea.initial() (leafarea.py:44-72; the 36 x 3 prescribed LAI maps are not read: loadLAI is stubbed)."""
+    import types
+    M, loadmap = _install(raw, land_mask)
+    F = ref_modules.load_feeders()
+    for name in ("snow", "frost"):
+        sys.modules["lisflood.hydrological_modules." + name].loadmap = loadmap
+    n = int(np.asarray(land_mask).sum())
+
+    class _Stack(object):                       # the surface of xarray.DataArray leafarea.initial touches
+        def __init__(self, data, coords=None, dims=None):
+            self.interval = types.SimpleNamespace(values=np.arange(data.shape[0]))
+            self.loc = self
+
+        def __setitem__(self, key, value):
+            pass
+    add1 = sys.modules["lisflood.global_modules.add1"]
+    add1.loadmap = loadmap
+    zus = sys.modules.get("lisflood.global_modules.zusatz")
+    if zus is None:
+        zus = types.ModuleType("lisflood.global_modules.zusatz")
+        sys.modules["lisflood.global_modules.zusatz"] = zus
+        setattr(sys.modules["lisflood.global_modules"], "zusatz", zus)
+    for k in ("generateName", "loadLAI"):
+        if not hasattr(zus, k):
+            setattr(zus, k, lambda *a, **kw: None)
+        if not hasattr(add1, k):
+            setattr(add1, k, lambda *a, **kw: None)
+    sys.modules["xarray"].DataArray = _Stack
+    key = "lisflood.hydrological_modules.leafarea"
+    lmod = sys.modules.get(key) or ref_modules.ref_loader._load_module(key, ref_modules._R + "/hydrological_modules/leafarea.py")
+    lmod.loadmap, lmod.loadLAI, lmod.generateName = loadmap, (lambda *a, **kw: np.zeros(n)), (lambda *a, **kw: "")
+    var = _InitVar(land_mask, raw, loadmap, dict(options or {}), 86400.0, 3600.0)
+    var.coord_prescribed_vegetation = OrderedDict([("vegetation", var.prescribed_vegetation[:]), var.dim_pixel])
+    var.PRESCRIBED_LAI = OrderedDict(zip(var.prescribed_vegetation, ["LAIOtherMaps", "LAIForestMaps", "LAIIrrigationMaps"]))
+    ref_modules._FakeSettings.instance().binding.update(LAIOtherMaps="", LAIForestMaps="", LAIIrrigationMaps="")
+    before = set(var.__dict__)
+    F["snow"](var).initial()
+    F["frost"](var).initial()
+    lmod.leafarea(var).initial()
+    out = {k: v for k, v in _collect(var).items() if k not in before}
+    out["SnowCoverS"] = np.stack([np.zeros(n) + x for x in var.SnowCoverS])
+    out["L1"] = np.asarray(var.L1)
+    return out

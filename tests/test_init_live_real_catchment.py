@@ -40,3 +40,28 @@ def test_initial_on_the_reference_use_case(split):
     g.update({"surfgw__" + k: v for k, v in ref_init.surface_and_groundwater_initial(mask, raw, st2, opts, DtSec=dt_sec).items()})
     checked = compare_with_reference(*_build(None, g))
     assert checked >= 140
+
+
+def test_feeder_initial_on_the_reference_use_case():
+    """snow.initial(), frost.initial(), leafarea.initial() of the live reference on the use case's real inputs against the
+    feeder mirrors (hydrological_modules/snow.py), bit for bit; feeder_arguments() hands them to HotPathModel.set_feeder."""
+    from lisflood_code_b200.Lisflood_initial import InitialVariables
+    from lisflood_code_b200.hydrological_modules.snow import (FEEDER_PARAMETERS, feeder_arguments, frost, leafarea, snow)
+    from oracle import ref_init, ref_usecase
+    keys = set(snow.input_files_keys["all"]) | set(frost.input_files_keys["all"]) | {"kdf", "PrScaling", "CalEvaporation"}
+    mask, raw, binding = ref_usecase.load_inputs("base.xml", keys)
+    n = int(mask.sum())
+    want = ref_init.feeders_initial(mask, raw)
+    var = InitialVariables(mask, raw, {}, DtSec=raw["DtSec"], DtSecChannel=raw["DtSecChannel"])
+    var.misc_initial()
+    snow(var).initial()
+    frost(var).initial()
+    leafarea(var).initial()
+    checked = 0
+    for k, w in want.items():
+        got = np.stack([np.zeros(n) + x for x in var.SnowCoverS]) if k == "SnowCoverS" else np.asarray(getattr(var, k))
+        assert np.array_equal(np.broadcast_to(got, np.shape(w)), w), k
+        checked += 1
+    assert checked >= 18 and np.ndim(want["DeltaTSnow"]) == 1 and np.ndim(want["SnowMeltCoef"]) == 1      # real maps
+    P, state = feeder_arguments(var, np.zeros(n))
+    assert set(P) == set(FEEDER_PARAMETERS) and state["SnowCoverS"].shape == (3, n) and state["FrostIndex"].shape == (n,)
