@@ -1,0 +1,37 @@
+"""End to end on the reference's own test catchment against the outputs the reference SHIPS
+(tests/data/LF_ETRS89_UseCase/reference/output_reference_{daily,6h}: its full model, 02/01/2016 onwards): the CPU
+restatement of the hot path -- host init mirrors on the real input maps, feeder modules on the real meteo stacks, soil,
+routing -- reproduces every soil-moisture stack of that run (three fractions, layers 1a and 2) far inside the reference's
+own comparator tolerance, and the lower zone / discharge wherever the modules outside the hot path that were switched on
+in that run (water use, rice, open-water evaporation, lakes, reservoirs) have no influence.
+Only where /root/reference exists (the build container).  The device path is checked against the same restatement."""
+import datetime
+
+import numpy as np
+import pytest
+
+from oracle import ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
+THETA = {"tha": ("Theta1a", 0), "thfa": ("Theta1a", 1), "thia": ("Theta1a", 2), "thc": ("Theta2", 0), "thfc": ("Theta2", 1),
+         "thic": ("Theta2", 2)}
+
+
+@pytest.mark.parametrize("run,dt_sec,steps", [("output_reference_daily", 86400.0, 12), ("output_reference_6h", 21600.0, 16)])
+def test_shipped_outputs_are_reproduced(run, dt_sec, steps):
+    from oracle import ref_usecase
+    R = ref_usecase.OracleRun(dt_sec=dt_sec, split=True)
+    mask, n = R.mask, int(R.mask.sum())
+    want = {k: ref_usecase.shipped_output(run, k) for k in list(THETA) + ["lz", "dis"]}
+    start = datetime.datetime(2016, 1, 2, 6, 0)
+    worst = dict.fromkeys(THETA, 0.0)
+    for k in range(steps):
+        v = R.step(start + datetime.timedelta(seconds=k * dt_sec))
+        for name, (attr, row) in THETA.items():
+            worst[name] = max(worst[name], float(np.abs(np.asarray(getattr(v, attr))[row] - want[name][k][mask]).max()))
+    assert max(worst.values()) < 1e-6, worst            # theta [-]; the reference's own comparator works at 1e-4
+    lz = np.abs(np.asarray(v.LZ) - want["lz"][steps - 1][mask])
+    assert (lz < 1e-9).sum() > 0.2 * n                  # no groundwater abstraction there
+    dis = want["dis"][steps - 1][mask]
+    rel = np.abs(np.asarray(v.ChanQAvg) - dis) / np.maximum(np.abs(dis), 1e-9)
+    assert (rel < 1e-6).sum() > 0.2 * n, int((rel < 1e-6).sum())      # headwaters no structure / abstraction reaches
