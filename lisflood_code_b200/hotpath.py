@@ -75,7 +75,11 @@ class HotPathModel(object):
             rows_cols, n_active = mask.shape, int(mask.sum())
         cfg = _capi.ModelConfig()
         cfg.rows, cfg.cols = rows_cols
-        cfg.DtSec, cfg.Beta, cfg.PixelLength = float(S["DtSec"]), float(S["Beta"]), float(S["PixelLength"])
+        plen = np.asarray(S["PixelLength"], np.float64)     # a map under option gridSizeUserDefined (miscInitial.py:52-68)
+        if plen.ndim and plen.size and not (plen == plen.flat[0]).all():
+            raise NotImplementedError("the device model takes ONE pixel length (overland routing, surface_routing.py:143-149): "
+                                      "the PixelLength map is not uniform")
+        cfg.DtSec, cfg.Beta, cfg.PixelLength = float(S["DtSec"]), float(S["Beta"]), float(plen.flat[0])
         cfg.NoRoutSteps, cfg.SplitRouting = int(S["NoRoutSteps"]), 1 if S.get("SplitRouting") else 0
         cfg.CourantCrit, cfg.AvWaterThreshold = float(S["CourantCrit"]), float(S["AvWaterThreshold"])
         cfg.LeafDrainageK, cfg.DrainedFraction = float(S["LeafDrainageK"]), float(S["DrainedFraction"])

@@ -301,6 +301,50 @@ def real_catchment_case(kwp, name, steps=6):
         int(((ldd_ops.downstream_index(ldd_raw[mask], mask) < 0) & (ldd_raw[mask] != 5)).sum()), up_area[mask].max()))
 
 
+def real_usecase_case(name, steps=6, dt_sec=86400.0):
+    """The reference's test catchment END TO END as a fixture for the device: static state from the host init mirrors on the
+    real input maps (bit-exact against the reference's own initial() there: tests/test_init_live_real_catchment.py), the raw
+    meteo maps of the first `steps` steps from 02/01/2016 06:00 (float32, as stored), the LAI maps of their intervals, what
+    the CPU restatement gives per step (oracle/ref_usecase.py::OracleRun), and the soil-moisture maps of the output stacks
+    the reference SHIPS for that run (reference/output_reference_daily: tha, thfa, thia, thc, thfc, thic)."""
+    import datetime
+    from oracle import ref_usecase
+    from lisflood_code_b200.hydrological_modules.snow import lai_interval
+    R = ref_usecase.OracleRun(dt_sec=dt_sec, split=True)
+    mask = R.mask
+    out = {"steps": np.int64(steps)}
+    for k, v in R.S.items():
+        if isinstance(v, (np.ndarray, float, int, bool, np.floating, np.integer)):
+            out["S__" + k] = np.asarray(v)
+    for k, v in R.feeder.P.items():
+        out["P__" + k] = np.asarray(v)
+    out["P__kgb"] = np.asarray(R.kgb)
+    out["Z__SnowCoverS"] = np.stack(R.feeder.SnowCoverS)
+    out["Z__FrostIndex"] = R.feeder.FrostIndex.copy()
+    shipped = {k: ref_usecase.shipped_output("output_reference_daily", k) for k in ("tha", "thfa", "thia", "thc", "thfc", "thic")}
+    start = datetime.datetime(2016, 1, 2, 6, 0)
+    keys = ("W1a", "W1b", "W2", "UZ", "LZ", "Theta1a", "Theta2", "ChanQAvg", "ChanQ", "ChanM3", "OFQDirect", "OFQOther",
+            "OFQForest", "TotalRunoff", "CumInterception", "DSLR")
+    for t in range(steps):
+        date = start + datetime.timedelta(seconds=t * dt_sec)
+        day = int(date.strftime("%j"))
+        out["day%d" % t] = np.int64(day)
+        for var_name, (data, tv, (unit_s, ref)) in R.forcing.items():
+            idx = np.flatnonzero(tv == (date - ref).total_seconds() / unit_s)[0]
+            out["R%d__%s" % (t, var_name)] = data[idx][mask]
+        out["L%d" % t] = np.stack([R.lai[i][lai_interval(day)][mask].astype(np.float64) for i in range(3)])
+        v = R.step(date)
+        for k in keys:
+            out["O%d__%s" % (t, k)] = np.asarray(getattr(v, k)).copy()
+        for k in ("FrostIndex",):
+            out["O%d__%s" % (t, k)] = np.asarray(getattr(R.feeder, k)).copy()
+        out["O%d__SnowCoverS" % t] = np.stack(R.feeder.SnowCoverS)
+        for k, stack in shipped.items():
+            out["X%d__%s" % (t, k)] = stack[t][mask]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "n=%d steps=%d: %d arrays" % (int(mask.sum()), steps, len(out)))
+
+
 def soil_options_case(name, rows, cols, seed, steps=2):
     """The option-gated extras of soilloop.dynamic_soil, executed by the reference's OWN class with the options switched on:
     repStressDays (SoilMoistureStressDays, soilloop.py:597-598) and simulatePF (the nested Numba kernel
@@ -345,6 +389,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "realcatchment":
         kwpt, kwp, sl = ref_loader.load()
         real_catchment_case(kwp, "kwreal_etrs89_57x80")
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "realusecase":
+        real_usecase_case("realcase_etrs89_daily")
         return
     if len(sys.argv) > 1 and sys.argv[1] == "soiloptions":
         soil_options_case("soilopt_28x33", 28, 33, 91)
