@@ -25,7 +25,11 @@ def _kw(gpu_lib):
     return kinematicWave
 
 
-KW_CASES = golden_cases("kw_") + golden_cases("kwreal_")    # kwreal_: the reference's own test catchment (57 x 80, 2847 px)
+# kwreal_: the reference's own test catchment (57 x 80, 2847 px).  Added after the round's GPU budget was spent and not run
+# on a GPU yet, hence a non-strict expected failure (XPASS = fine); the CPU restatement passes it (tests/test_oracle_golden.py)
+KW_CASES = golden_cases("kw_") + [
+    pytest.param(c, marks=pytest.mark.xfail(strict=False, reason="never run on a GPU yet (added after the round's GPU budget "
+                                                                  "was spent)")) for c in golden_cases("kwreal_")]
 
 
 @pytest.mark.parametrize("case", KW_CASES)
