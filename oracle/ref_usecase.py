@@ -71,7 +71,7 @@ class OracleRun(object):
     stacks as add1.readnetcdf does (:700-720), LAI by calendar day (leafarea.py:82), CalendarDay as Lisflood_dynamic.py:46-48.
     Only the modules of the hot path run: no water use, rice, open-water evaporation, lakes or reservoirs."""
 
-    def __init__(self, dt_sec=86400.0, split=False, settings="base.xml"):
+    def __init__(self, dt_sec=86400.0, split=False, settings="base.xml", init_lisflood=False):
         from lisflood_code_b200.Lisflood_initial import initialise
         from lisflood_code_b200.hydrological_modules.snow import feeder_arguments, frost, leafarea, snow
         from . import lisf_oracle_model as om
@@ -80,7 +80,8 @@ class OracleRun(object):
         self.mask, raw, self.binding = load_inputs(settings, keys)
         raw["DtSec"] = float(dt_sec)
         n = int(self.mask.sum())
-        var = initialise(self.mask, raw, {"SplitRouting": split, "drainedIrrigation": split, "gridSizeUserDefined": True},
+        var = initialise(self.mask, raw, {"SplitRouting": split, "drainedIrrigation": split, "gridSizeUserDefined": True,
+                                          "InitLisflood": bool(init_lisflood)},
                          DtSec=raw["DtSec"], DtSecChannel=raw["DtSecChannel"])
         snow(var).initial()
         frost(var).initial()
@@ -120,6 +121,7 @@ class OracleRun(object):
 
 
 def shipped_output(run, name):
-    """(time, y, x) array of an output stack the reference ships (tests/data/LF_ETRS89_UseCase/reference/<run>/<name>.nc)."""
+    """Array of an output file the reference ships (tests/data/LF_ETRS89_UseCase/reference/<run>/<name>.nc): (time, y, x)
+    for a stack, (y, x) for a map."""
     f = ref_maps.H5File(os.path.join(ROOT, "reference", run, name + ".nc"))
     return f.read(f.dataset(f.links()[name]))

@@ -35,3 +35,20 @@ def test_shipped_outputs_are_reproduced(run, dt_sec, steps):
     dis = want["dis"][steps - 1][mask]
     rel = np.abs(np.asarray(v.ChanQAvg) - dis) / np.maximum(np.abs(dis), 1e-9)
     assert (rel < 1e-6).sum() > 0.2 * n, int((rel < 1e-6).sum())      # headwaters no structure / abstraction reaches
+
+
+def test_prerun_product_against_the_shipped_lzavin():
+    """The pre-run (option InitLisflood, 373 daily steps from 31/12/2015: reference/init_daily) leaves LZAvInflowMap =
+    LZInflowCUM / DtDay / steps (groundwater.py:177); the shipped lzavin.nc is reproduced wherever that run's irrigation
+    (water use: outside the hot path) did not act -- on more than 90 % of the pixels without an irrigated fraction."""
+    from oracle import ref_usecase
+    R = ref_usecase.OracleRun(dt_sec=86400.0, split=False, init_lisflood=True)
+    mask, steps = R.mask, 373
+    start = datetime.datetime(2015, 12, 31, 6, 0)
+    for k in range(steps):
+        v = R.step(start + datetime.timedelta(days=k))
+    lzav = (np.asarray(v.LZInflowCUM) * (1 / R.S["DtDay"])) / steps
+    d = np.abs(lzav - ref_usecase.shipped_output("init_daily", "lzavin")[mask])
+    no_irrigation = np.asarray(R.S["IrrigationFraction"]) == 0
+    assert no_irrigation.sum() > 400 and (d[no_irrigation] < 1e-9).mean() > 0.9
+    assert (d < 1e-9).sum() > 900 and d.max() < 0.5          # mm/day; elsewhere the irrigation of that run shows
