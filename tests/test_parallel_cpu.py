@@ -10,7 +10,10 @@ import pytest
 from conftest import ROOT
 
 
-def _case(rows=60, cols=48, seed=5, noise=0.3, maskf=0.1):
+def _case(rows=60, cols=48, seed=5, noise=0.3, maskf=0.1, kind="synthetic"):
+    if kind == "real":      # the reference's own test catchment (tests/golden/kwreal_*.npz: 57 x 80, 2847 pixels, one outlet)
+        with np.load(os.path.join(ROOT, "tests", "golden", "kwreal_etrs89_57x80.npz")) as g:
+            return g["ldd"], g["mask"], g["alpha"], g["q0"], g["q"], g["dx"]
     from lisflood_code_b200 import synthetic
     ldd, mask = synthetic.random_ldd(rows, cols, seed=seed, noise=noise, mask_fraction=maskf, single_outlet=True)
     n = int(mask.sum())
@@ -77,7 +80,7 @@ def test_exchange_plan_is_consistent(world):
     assert len(seen) == eu.size and set(seen.values()) == {1}              # every import slot has exactly one producer
 
 
-def _worker(rank, world, port, tmp):
+def _worker(rank, world, port, tmp, kind="synthetic"):
     """Stand-in for the device path: every rank routes its sub-mask (own pixels + ghosts) with the CPU oracle, ghost
     values prescribed; the ranks exchange the discharges of their cut edges through the plan's tables and repeat the
     step until nothing changes (a value is final once its upstream path has been exchanged across all its cuts)."""
@@ -87,7 +90,7 @@ def _worker(rank, world, port, tmp):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import lisf_oracle
-    ldd, mask, alpha, q0, q, dx = _case()
+    ldd, mask, alpha, q0, q, dx = _case(kind=kind)
     owner, plan = _plan(ldd, mask, world)
     n = owner.size
     keep = owner == rank
@@ -139,18 +142,20 @@ def _worker(rank, world, port, tmp):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_gloo_cut_network_is_bit_identical(tmp_path, world, oracle):
+@pytest.mark.parametrize("world,kind", [(2, "synthetic"), (3, "synthetic"), (2, "real"), (3, "real")])
+def test_gloo_cut_network_is_bit_identical(tmp_path, world, kind, oracle):
+    """kind "real": the reference's own test catchment cut over the ranks -- its tests/test_subcatchments.py:111-112 asks
+    sub-domain results to be bit-identical to the full run."""
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), kind), nprocs=world, join=True)
     got = np.load(tmp_path / ("dist_w%d.npy" % world))
     ncut, rounds = np.load(tmp_path / ("meta_w%d.npy" % world))
     assert ncut > 0, "the test catchment must actually be cut"
-    ldd, mask, alpha, q0, q, dx = _case()
+    ldd, mask, alpha, q0, q, dx = _case(kind=kind)
     ora = oracle.KinematicWaveOracle(ldd, mask, alpha, 0.6, dx, 3600.0)
     Q = q0.copy()
     rng = np.random.default_rng(3)
