@@ -65,3 +65,42 @@ def test_feeder_initial_on_the_reference_use_case():
     assert checked >= 18 and np.ndim(want["DeltaTSnow"]) == 1 and np.ndim(want["SnowMeltCoef"]) == 1      # real maps
     P, state = feeder_arguments(var, np.zeros(n))
     assert set(P) == set(FEEDER_PARAMETERS) and state["SnowCoverS"].shape == (3, n) and state["FrostIndex"].shape == (n,)
+
+
+def test_structures_initial_on_the_reference_use_case():
+    """reservoir.initial() / lakes.initial() of the live reference on the use case's real site maps and lookup tables
+    (maps/ec_res.nc, ec_lakes.nc, tables/*.txt through the shipped settings) against the host mirrors, bit for bit."""
+    from lisflood_code_b200.Lisflood_initial import InitialVariables, initialise
+    from lisflood_code_b200.hydrological_modules.lakes import lakes
+    from lisflood_code_b200.hydrological_modules.reservoir import reservoir
+    from oracle import ref_init, ref_usecase
+    from test_structures_init_golden import SKIP
+    keys = set(reservoir.input_files_keys["simulateReservoirs"]) | set(lakes.input_files_keys["simulateLakes"])
+    tab_keys = sorted(k for k in keys if k.startswith("Tab"))
+    mask, raw, binding = ref_usecase.load_inputs("base.xml", keys - set(tab_keys))
+    tables = {k: np.loadtxt(binding[k] if binding[k].endswith(".txt") else binding[k] + ".txt", ndmin=2) for k in tab_keys}
+    assert len(tables) == 10 and all(t.shape[1] == 2 for t in tables.values())
+    opts = {"simulateLakes": True, "simulateReservoirs": True, "gridSizeUserDefined": True}
+    base = initialise(mask, raw, opts, DtSec=raw["DtSec"], DtSecChannel=raw["DtSecChannel"])
+    n = int(mask.sum())
+    state = {"IsChannel": np.asarray(base.IsChannel), "IsStructureKinematic": np.zeros(n, bool),
+             "LddKinematic": np.asarray(base.LddKinematic), "downstruct": np.asarray(base.downstruct),
+             "ChanQ": np.asarray(base.ChanQ), "DtRouting": base.DtRouting}
+    want = ref_init.structures_initial(mask, raw, tables, state, opts, DtSec=raw["DtSec"], DtSecChannel=raw["DtSecChannel"])
+    maps = dict(raw)
+    maps.update(tables)
+    var = InitialVariables(mask, maps, opts, DtSec=raw["DtSec"], DtSecChannel=raw["DtSecChannel"])
+    for k, v in state.items():
+        setattr(var, k, v.copy() if np.ndim(v) else v)
+    lakes(var).initial()
+    reservoir(var).initial()
+    checked = 0
+    for name, w in want.items():
+        if name in SKIP:
+            continue
+        assert hasattr(var, name), name
+        got = np.asarray(getattr(var, name))
+        assert got.shape == np.shape(w), (name, got.shape, np.shape(w))
+        assert np.array_equal(got.astype(np.asarray(w).dtype), w, equal_nan=True), name
+        checked += 1
+    assert checked >= 38 and var.ReservoirIndex.size > 0 and var.LakeIndex.size > 0
