@@ -52,3 +52,28 @@ def test_prerun_product_against_the_shipped_lzavin():
     no_irrigation = np.asarray(R.S["IrrigationFraction"]) == 0
     assert no_irrigation.sum() > 400 and (d[no_irrigation] < 1e-9).mean() > 0.9
     assert (d < 1e-9).sum() > 900 and d.max() < 0.5          # mm/day; elsewhere the irrigation of that run shows
+
+
+def test_whole_shipped_period_within_the_reference_comparator_tolerance():
+    """All 183 daily steps of the shipped run: the soil moisture of the rainfed and forest fractions stays inside the
+    tolerance of the reference's own comparator (1e-4; observed 2e-6) to the end; the irrigated fraction is reproduced until
+    that run's irrigation -- water use, outside the hot path -- starts in April."""
+    from oracle import ref_usecase
+    R = ref_usecase.OracleRun(dt_sec=86400.0, split=True)
+    mask = R.mask
+    want = {k: ref_usecase.shipped_output("output_reference_daily", k) for k in THETA}
+    start = datetime.datetime(2016, 1, 2, 6, 0)
+    worst, first_irrigation = dict.fromkeys(THETA, 0.0), None
+    for k in range(want["tha"].shape[0]):
+        v = R.step(start + datetime.timedelta(days=k))
+        for name, (attr, row) in THETA.items():
+            d = float(np.abs(np.asarray(getattr(v, attr))[row] - want[name][k][mask]).max())
+            if name in ("thia", "thic"):
+                if d > 1e-6 and first_irrigation is None:
+                    first_irrigation = k
+                if first_irrigation is not None:
+                    continue
+            worst[name] = max(worst[name], d)
+    assert want["tha"].shape[0] == 183 and max(worst.values()) < 1e-4, worst
+    assert max(worst[k] for k in ("tha", "thfa", "thc", "thfc")) < 1e-5, worst
+    assert first_irrigation is not None and first_irrigation > 90          # day 99 = 10 April 2016
