@@ -94,11 +94,16 @@ class InitialVariables(object):
 
     def loadtable(self, name):
         """A PCRaster lookup table (`TabTotStorage` ...) as a two-column array [site id, value]: from `maps` or, through
-        the settings binding, from a .npy file."""
+        the settings binding, from a .npy file or from the reference's own text tables ("id value" per line, .txt)."""
         if name in self.maps:
             return np.asarray(self.maps[name], np.float64).reshape(-1, 2)
+        import os
         from .global_modules.settings import LisSettings
-        return np.load(LisSettings.instance().binding[name]).astype(np.float64).reshape(-1, 2)
+        path = LisSettings.instance().binding[name]
+        for cand in (path, path + ".txt"):
+            if os.path.isfile(cand) and not cand.endswith(".npy"):
+                return np.loadtxt(cand, ndmin=2).astype(np.float64).reshape(-1, 2)
+        return np.load(path).astype(np.float64).reshape(-1, 2)
 
     def _has(self, name):
         if name is None:
@@ -169,8 +174,9 @@ class InitialVariables(object):
 
 def initialise(land_mask, maps=None, options=None, DtSec=86400.0, DtSecChannel=3600.0):
     """Runs the hot-path modules' initial() in the reference's order (Lisflood_initial.py:174-262: misc, land use,
-    soil, routing, groundwater, surface routing, routing second part) on raw inputs by binding name and returns the
-    InitialVariables object; `.state()` is what HotPathModel takes."""
+    soil, routing, groundwater, surface routing, [reservoirs, lakes, structures with options simulateReservoirs /
+    simulateLakes,] routing second part) on raw inputs by binding name and returns the InitialVariables object; `.state()`
+    is what HotPathModel takes."""
     from .hydrological_modules.groundwater import groundwater
     from .hydrological_modules.routing import routing
     from .hydrological_modules.soil import soil
@@ -183,5 +189,13 @@ def initialise(land_mask, maps=None, options=None, DtSec=86400.0, DtSecChannel=3
     r.initial()
     groundwater(var).initial()
     surface_routing(var).initial()
+    if var.option('simulateReservoirs') or var.option('simulateLakes'):
+        from .hydrological_modules.lakes import lakes
+        from .hydrological_modules.reservoir import reservoir
+        from .hydrological_modules.structures import structures
+        reservoir(var).initial()
+        lakes(var).initial()
+        structures(var).initial()
+        var.simulateReservoirs, var.simulateLakes = var.option('simulateReservoirs'), var.option('simulateLakes')
     r.initialSecond()
     return var

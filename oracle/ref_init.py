@@ -380,3 +380,37 @@ def feeders_initial(land_mask, raw, options=None):
     out["SnowCoverS"] = np.stack([np.zeros(n) + x for x in var.SnowCoverS])
     out["L1"] = np.asarray(var.L1)
     return out
+
+
+def structures_module_initial(land_mask, ldd_kinematic, is_structure, options=None):
+    """Outputs of the reference's structures.initial() (hydrological_modules/structures.py:43-61) for a channel network and
+    the structure pixels reservoir.initial() / lakes.initial() marked: LddStructuresKinematic, IsUpsOfStructureKinematicC and
+    the cut LddKinematic.  downstream / lddrepair / ifthenelse / cover / boolean are the stand-ins of _install()."""
+    from lisflood_code_b200.global_modules import ldd_ops
+    M, loadmap = _install({}, land_mask)
+    land = np.asarray(land_mask, bool)
+    key = "lisflood.hydrological_modules.structures"
+    mod = sys.modules.get(key) or ref_modules.ref_loader._load_module(key, ref_modules._R + "/hydrological_modules/structures.py")
+
+    def ds_of(ldd):
+        return ldd_ops.downstream_index(np.asarray(ldd, np.float64), land)
+
+    def downstream(ldd, x):
+        d = ds_of(ldd)
+        x = np.asarray(x)
+        return _Pcr(np.where(d >= 0, x[np.maximum(d, 0)], x))
+    mod.downstream = downstream
+    mod.boolean = lambda x: _Pcr(np.asarray(x) != 0)
+    mod.cover = lambda x, y: _Pcr(np.asarray(x))
+    mod.lddrepair = lambda ldd: _Pcr(ldd_ops.lddrepair_codes(np.asarray(ldd, np.float64), land))
+    mod.ifthenelse = lambda c, a, b: _Pcr(np.where(np.asarray(c) != 0, a, b))
+    mod.decompress = lambda a, *aa, **k: _Pcr(np.asarray(a))
+    mod.compressArray = lambda m, *a, **k: np.asarray(m).copy()
+    mod.LisSettings = ref_modules._FakeSettings
+    var = _InitVar(land_mask, {}, loadmap, dict(options or {}), 86400.0, 3600.0)
+    var.LddKinematic = _Pcr(np.array(ldd_kinematic, np.float64))
+    var.IsStructureKinematic = np.asarray(is_structure) != 0
+    mod.structures(var).initial()
+    return {"LddStructuresKinematic": np.asarray(var.LddStructuresKinematic, np.float64),
+            "IsUpsOfStructureKinematicC": np.asarray(var.IsUpsOfStructureKinematicC) != 0,
+            "LddKinematic": np.asarray(var.LddKinematic, np.float64)}

@@ -81,7 +81,7 @@ def test_structures_initial_on_the_reference_use_case():
     tables = {k: np.loadtxt(binding[k] if binding[k].endswith(".txt") else binding[k] + ".txt", ndmin=2) for k in tab_keys}
     assert len(tables) == 10 and all(t.shape[1] == 2 for t in tables.values())
     opts = {"simulateLakes": True, "simulateReservoirs": True, "gridSizeUserDefined": True}
-    base = initialise(mask, raw, opts, DtSec=raw["DtSec"], DtSecChannel=raw["DtSecChannel"])
+    base = initialise(mask, raw, {"gridSizeUserDefined": True}, DtSec=raw["DtSec"], DtSecChannel=raw["DtSecChannel"])
     n = int(mask.sum())
     state = {"IsChannel": np.asarray(base.IsChannel), "IsStructureKinematic": np.zeros(n, bool),
              "LddKinematic": np.asarray(base.LddKinematic), "downstruct": np.asarray(base.downstruct),
@@ -104,3 +104,34 @@ def test_structures_initial_on_the_reference_use_case():
         assert np.array_equal(got.astype(np.asarray(w).dtype), w, equal_nan=True), name
         checked += 1
     assert checked >= 38 and var.ReservoirIndex.size > 0 and var.LakeIndex.size > 0
+
+
+def test_init_chain_with_structures_on_the_reference_use_case():
+    """initialise() with simulateReservoirs / simulateLakes on the real inputs: the structures mirror (LDD cut just upstream
+    of every structure, structures.py:43-61) against the live reference's structures.initial(), and the resulting state is
+    what the device model and the CPU restatement take (a short run of the latter stays finite)."""
+    from lisflood_code_b200.Lisflood_initial import initialise
+    from lisflood_code_b200.hydrological_modules.lakes import lakes
+    from lisflood_code_b200.hydrological_modules.reservoir import reservoir
+    from oracle import lisf_oracle_model as om, ref_init, ref_usecase
+    keys = set(reservoir.input_files_keys["simulateReservoirs"]) | set(lakes.input_files_keys["simulateLakes"])
+    tab_keys = sorted(k for k in keys if k.startswith("Tab"))
+    mask, raw, binding = ref_usecase.load_inputs("base.xml", keys - set(tab_keys))
+    maps = dict(raw)
+    maps.update({k: np.loadtxt(binding[k] if binding[k].endswith(".txt") else binding[k] + ".txt", ndmin=2) for k in tab_keys})
+    opts = {"simulateLakes": True, "simulateReservoirs": True, "gridSizeUserDefined": True, "SplitRouting": True}
+    plain = initialise(mask, maps, dict(opts, simulateLakes=False, simulateReservoirs=False), DtSec=raw["DtSec"],
+                       DtSecChannel=raw["DtSecChannel"])
+    var = initialise(mask, maps, opts, DtSec=raw["DtSec"], DtSecChannel=raw["DtSecChannel"])
+    struct = np.asarray(var.IsStructureKinematic) != 0
+    assert struct.sum() == var.ReservoirIndex.size + var.LakeIndex.size == 36
+    want = ref_init.structures_module_initial(mask, plain.LddKinematic, struct)
+    for k, w in want.items():
+        assert np.array_equal(np.asarray(getattr(var, k)).astype(w.dtype), w), k
+    assert np.array_equal(var.LddStructuresKinematic, plain.LddKinematic)
+    cut = np.asarray(var.LddKinematic) != np.asarray(plain.LddKinematic)
+    assert cut.sum() >= 36 and (np.asarray(var.LddKinematic)[cut] == 5).all()
+    S = var.state()
+    assert S["simulateReservoirs"] is True and S["simulateLakes"] is True
+    for k in ("LddStructuresKinematic", "ReservoirIndex", "LakeIndex", "TotalReservoirStorageM3CC", "LakeAreaCC", "downstruct"):
+        assert k in S, k
