@@ -72,15 +72,20 @@ class LisSettings(object):
         for el in dom.getElementsByTagName("lfbinding"):
             for t in el.getElementsByTagName("textvar"):
                 binding[t.attributes["name"].value] = str(t.attributes["value"].value)
+        last = None          # the reference keeps the previous substitution when a variable is missing (settings.py:554-558)
         for k, expr in binding.items():
             guard = 0
             while "$(" in expr and guard < 100:
                 a1 = expr.find("$(")
-                a2 = expr.find(")", a1)
+                a2 = expr.find(")")
                 name = expr[a1 + 2:a2]
-                if name not in user:
-                    raise KeyError("no %s for %s in lfuser defined" % (name, k))
-                expr = expr.replace(expr[a1:a2 + 1], user[name])
+                if name in user:
+                    last = user[name]
+                else:
+                    print('no ', name, 'for', binding[k], ' in lfuser defined')
+                    if last is None:
+                        raise KeyError("no %s for %s in lfuser defined" % (name, k))
+                expr = expr.replace(expr[a1:a2 + 1], last)
                 guard += 1
             binding[k] = expr
         if "CalendarConvention" in binding:

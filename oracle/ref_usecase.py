@@ -17,12 +17,15 @@ def load_inputs(settings="base.xml", keys=()):
     """(land mask, {binding name: float or float64[N]}, bindings) for the init-time inputs of the hot-path modules."""
     from lisflood_code_b200.global_modules.settings import LisSettings
     from lisflood_code_b200.hydrological_modules import groundwater, routing, soil, surface_routing
+    import contextlib
+    import io
     before = LisSettings._instance
-    b = LisSettings(os.path.join(ROOT, "settings", settings)).binding
+    with contextlib.redirect_stdout(io.StringIO()):       # (the lat / lon settings name a user variable they do not define)
+        b = LisSettings(settings if os.path.isabs(settings) else os.path.join(ROOT, "settings", settings)).binding
     LisSettings._instance = before
 
-    def path_of(v):
-        for c in (v, v + ".nc", v + ".map"):
+    def path_of(v):       # loadmap: the name as given, then NetCDF / PCRaster by extension (add1.py:318-541)
+        for c in (v, v + ".nc", v + ".map", os.path.splitext(v)[0] + ".nc"):
             if os.path.isfile(c):
                 return c
         raise FileNotFoundError(v)

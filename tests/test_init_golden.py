@@ -28,7 +28,8 @@ def _build(case, g=None):
     g = load_golden(case) if g is None else g
     raw = {k[5:]: (float(v) if v.ndim == 0 else v) for k, v in g.items() if k.startswith("raw__")}
     split = bool(g["SplitRouting"])
-    var = InitialVariables(g["mask"], raw, {"SplitRouting": split, "drainedIrrigation": split}, DtSec=float(g["DtSec"]))
+    var = InitialVariables(g["mask"], raw, {"SplitRouting": split, "drainedIrrigation": split}, DtSec=float(g["DtSec"]),
+                           DtSecChannel=float(raw.get("DtSecChannel", 3600.0)))
     for k, v in g.items():
         if k.startswith("state__"):
             setattr(var, k[7:], NumpyModified(v.copy(), ["vegetation", "pixel"]) if v.ndim == 2 else v.copy())

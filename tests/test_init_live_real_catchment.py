@@ -10,14 +10,20 @@ from oracle import ref_loader
 pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
 
 
-@pytest.mark.parametrize("split", [False, True])
-def test_initial_on_the_reference_use_case(split):
+LAT_LON = "LF_lat_lon_UseCase/run_lat_lon.xml"      # the reference's second use case: a lat / lon grid, 14 x 31, PCRaster maps
+
+
+@pytest.mark.parametrize("settings,split", [("base.xml", False), ("base.xml", True), (LAT_LON, False), (LAT_LON, True)])
+def test_initial_on_the_reference_use_case(settings, split):
+    import os
     from lisflood_code_b200.Lisflood_initial import InitialVariables
     from oracle import ref_init, ref_usecase
     from test_init_golden import _build, compare_with_reference
-    mask, raw, binding = ref_usecase.load_inputs("base.xml")
+    if settings == LAT_LON:
+        settings = os.path.join(os.path.dirname(ref_usecase.ROOT), *LAT_LON.split("/"))
+    mask, raw, binding = ref_usecase.load_inputs(settings)
     n = int(mask.sum())
-    assert n == 2847 and sum(np.ndim(v) > 0 for v in raw.values()) >= 60
+    assert n in (2847, 177) and sum(np.ndim(v) > 0 for v in raw.values()) >= 55
     dt_sec = raw["DtSec"]
     opts = {"SplitRouting": split, "drainedIrrigation": split, "gridSizeUserDefined": True}
     # what miscInitial / landusechange leave behind (mirrors pinned in tests/test_oracle_live_reference.py)

@@ -25,6 +25,7 @@ def _shipped_settings():
         return []
     root = os.path.normpath(os.path.join(ref_loader._R, "..", ".."))
     files = sorted(glob.glob(os.path.join(root, "tests", "data", "*", "settings", "*.xml")))
+    files += sorted(glob.glob(os.path.join(root, "tests", "data", "*", "*.xml")))       # the lat / lon use case
     files.append(os.path.join(root, "src", "lisfloodSettings_reference.xml"))
     return [f for f in files if os.path.exists(f)]
 
